@@ -1,0 +1,187 @@
+"""Host-side mirror of the reference's solver API for the batched GPU path.
+
+Names follow the reference (file:line under /root/reference):
+  load_hsddp_setting      loadHSDDPSetting                 HSDDPSolver/common/HSDDP_CompoundTypes.h:57-82
+  HKDProblem              HKDProblem<T>                    HKDMPC/HKD-TrajOpt/HKDProblem.h:93-168
+  MHPCProblem             MHPCProblem<T>                   MHPC/MHPC-Trajopt/MHPCProblem.h:169-289
+  MultiPhaseDDP           MultiPhaseDDP<T> (batched)       HSDDPSolver/header/MultiPhaseDDP.h:25-146
+Everything numeric happens behind the C ABI (include/cafe_gpu.h); this file only marshals."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from ._ctypes_defs import (CAFE_NKERNELS, CAFE_TRACE_W, MODEL_DIMS, Deck, Info, Options)
+from .lib import check, lib
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DATA = os.path.join(REPO, "data")
+
+
+def load_hsddp_setting(fname):
+    o = Options()
+    check(lib.cafe_options_load(fname.encode(), C.byref(o)))
+    return o
+
+
+class _DeckOwner:
+    def __init__(self):
+        self._h = C.c_void_p()
+
+    @property
+    def deck(self):
+        return lib.cafe_deck_get(self._h)
+
+    def phases(self):
+        d = self.deck.contents
+        return [d.phase[i] for i in range(d.n_phases)]
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib.cafe_deck_free(self._h)
+            self._h = C.c_void_p()
+
+
+class HKDProblem(_DeckOwner):
+    """set_problem_data(config) + initialization(): HKDProblem.cpp:15-111. Hard-coded plan values of
+    HKDMPCSolver::initialize (HKDMPC.cpp:26-28) are the defaults."""
+
+    def __init__(self, reference_csv, constraint_params=None, plan_duration=0.6, time_step=0.01,
+                 nsteps_between_mpc=2, k0=0):
+        super().__init__()
+        constraint_params = constraint_params or os.path.join(DATA, "settings/hkd/constraint_params.info")
+        check(lib.cafe_deck_build_hkd(reference_csv.encode(), constraint_params.encode(), plan_duration, time_step,
+                                      nsteps_between_mpc, k0, C.byref(self._h)))
+
+    def initial_state(self, body, qJ):
+        """compute_hkd_state (HKDModel.h:66-96) with the first phase's contact."""
+        body = np.ascontiguousarray(body, dtype=np.float64)
+        qJ = np.ascontiguousarray(qJ, dtype=np.float64)
+        x0 = np.zeros(24)
+        dp = C.POINTER(C.c_double)
+        check(lib.cafe_hkd_state(body.ctypes.data_as(dp), qJ.ctypes.data_as(dp), self.phases()[0].contact,
+                                 x0.ctypes.data_as(dp)))
+        return x0
+
+
+class MHPCProblem(_DeckOwner):
+    """MHPCProblem<T>::initialization (MHPCProblem.cpp:13-250) from mhpc_config.info."""
+
+    def __init__(self, reference_csv, mhpc_config=None, settings_root=None, k0=0):
+        super().__init__()
+        mhpc_config = mhpc_config or os.path.join(DATA, "settings/mhpc/mhpc_config.info")
+        settings_root = settings_root or os.path.join(DATA, "settings")
+        check(lib.cafe_deck_build_mhpc(reference_csv.encode(), mhpc_config.encode(), settings_root.encode(), k0,
+                                       C.byref(self._h)))
+
+
+class MultiPhaseDDP:
+    """Batched MultiPhaseDDP: set_multiPhaseProblem (constructor), set_initial_condition, solve,
+    get_solver_info; results are packed host arrays instead of in-place Trajectory deques."""
+
+    def __init__(self, problem, device=0, max_batch=1):
+        self.problem = problem
+        self._h = C.c_void_p()
+        check(lib.cafe_gpu_create(problem.deck, device, max_batch, C.byref(self._h)))
+        self.B = 0
+        self.x0 = None
+
+    def close(self):
+        if self._h and self._h.value:
+            lib.cafe_gpu_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_initial_condition(self, x0):
+        x0 = np.ascontiguousarray(np.atleast_2d(x0), dtype=np.float64)
+        self.x0 = x0
+        self.B = x0.shape[0]
+
+    def set_profiling(self, on):
+        check(lib.cafe_gpu_set_profiling(self._h, 1 if on else 0))
+
+    def solve(self, option):
+        check(lib.cafe_gpu_solve_batch(self._h, self.x0.ctypes.data_as(C.c_void_p), self.B, C.byref(option)))
+
+    def solve_device(self, x0_dev_ptr, ldx, B, option):
+        self.B = B
+        check(lib.cafe_gpu_solve_batch_device(self._h, C.c_void_p(x0_dev_ptr), ldx, B, C.byref(option)))
+
+    def get_solver_info(self):
+        info = (Info * self.B)()
+        check(lib.cafe_gpu_get_info(self._h, info))
+        return [i.as_dict() for i in info]
+
+    def get_history(self, cap=64):
+        h = np.zeros((self.B, cap, 4))
+        check(lib.cafe_gpu_get_history(self._h, h.ctypes.data_as(C.c_void_p), cap))
+        return h
+
+    def get_trace(self, cap=64):
+        t = np.zeros((self.B, cap, CAFE_TRACE_W))
+        check(lib.cafe_gpu_get_trace(self._h, t.ctypes.data_as(C.c_void_p), cap))
+        return t
+
+    def solution_size(self):
+        return lib.cafe_solution_size(self.problem.deck)
+
+    def get_solution(self, b0=0, nb=None):
+        nb = self.B - b0 if nb is None else nb
+        s = np.zeros((nb, self.solution_size()))
+        check(lib.cafe_gpu_get_solution(self._h, b0, nb, s.ctypes.data_as(C.c_void_p)))
+        return s
+
+    def get_commands(self, n_gain_knots=8, out=None):
+        sz = lib.cafe_command_size(self.problem.deck, n_gain_knots)
+        if out is None:
+            out = np.zeros((self.B, sz))
+        check(lib.cafe_gpu_get_commands(self._h, n_gain_knots, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def debug_get(self, name, phase, b=0):
+        buf = np.zeros(64 * 36 * 36 + 64)
+        n = lib.cafe_gpu_debug_get(self._h, name.encode(), phase, b, buf.ctypes.data_as(C.c_void_p))
+        if n < 0:
+            check(int(n))
+        return buf[:n].copy()
+
+    def get_timing(self):
+        ms = (C.c_double * CAFE_NKERNELS)()
+        n = (C.c_long * CAFE_NKERNELS)()
+        ticks = C.c_int()
+        check(lib.cafe_gpu_get_timing(self._h, C.byref(ms), C.byref(n), C.byref(ticks)))
+        names = ["roll", "select", "accept", "lq", "bwd", "misc"]
+        return {"ms": dict(zip(names, list(ms))), "launches": dict(zip(names, list(n))), "ticks": ticks.value}
+
+
+def unpack_solution(deck, sol):
+    """Split one packed solution (cafe_solution_size doubles) into named per-phase arrays."""
+    out = []
+    off = 0
+    d = deck.contents
+    for i in range(d.n_phases):
+        ph = d.phase[i]
+        n, m, p = MODEL_DIMS[ph.model]
+        h = ph.horizon
+        r = {}
+        for name, shape in (("Xbar", (h + 1, n)), ("Ubar", (h, m)), ("Y", (h, p)), ("dU", (h, m)), ("K", (h, n, m)),
+                            ("Qu", (h, m)), ("Quu", (h, m, m)), ("Qux", (h, n, m)), ("G", (h + 1, n))):
+            cnt = int(np.prod(shape))
+            a = np.asarray(sol[off:off + cnt]).reshape(shape)
+            if len(shape) == 3:
+                a = a.transpose(0, 2, 1)  # stored column-major per knot
+            r[name] = a
+            off += cnt
+        out.append(r)
+    return out
+
+
+def measure_fp64_peak(device=0):
+    v = C.c_double()
+    check(lib.cafe_gpu_measure_fp64_peak(device, C.byref(v)))
+    return v.value

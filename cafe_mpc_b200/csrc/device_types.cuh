@@ -1,0 +1,67 @@
+// device_types.cuh — device-side view of a batch of HS-DDP problems that share one phase deck.
+//
+// HBM layout: every per-problem quantity is stored component-major with the PROBLEM index fastest
+// ("SoA over the batch"): element c of knot k of problem b lives at ((k*NC + c)*ldb + b). A warp
+// therefore always touches 32 consecutive problems of the same scalar => every global access of the
+// per-(problem,knot) kernels is a fully coalesced 256 B transaction, and the per-problem-group
+// Riccati kernel reads 8*PB-byte sector-aligned runs (PB problems per CTA).
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/cafe_deck.h"
+
+#define CAFE_MAX_ALPHAS 12
+#define CAFE_MAX_KNOTS 256
+#define CAFE_HIST_CAP 256
+
+struct PhaseDev {
+  int model, n, m, p, h, n_next, has_next;
+  int contact[4], next_contact[4], n_td, td_foot[4];
+  double dt, mu, ground_height, BG_alpha;
+  double q[CAFE_MAX_N], r[CAFE_MAX_M], qf[CAFE_MAX_N];
+  double w_footreg[3], w_swingpos[3], w_swingvel[3], w_tdvel[3];
+  CafeRebParam reb_grf, reb_torque, reb_joint, reb_minheight;
+  CafeAlParam al_td;
+  const double* ref;  // [h+1][CAFE_REF_W], shared by the batch
+  // trajectories, [(h+1) or h][dim][ldb]
+  double *X, *Xbar, *dX, *G, *Defect;
+  double *U, *Ubar, *dU, *Qu, *Y;
+  // LQ data
+  double *A, *Bm, *C, *D;                  // [h][n*n | n*m | p*n | p*m][ldb], column-major per knot
+  double *lx, *lu, *ly, *lxx, *luu, *lyy;  // [h][...][ldb]
+  double *Phix, *Phixx, *Px;               // [n | n*n | n_next*n][ldb]
+  double *lk, *dsq;                        // [h+1][ldb] per-knot cost (k=h: Phi) and |Defect[k]|^2
+  // backward-sweep outputs
+  double *K, *Quu, *Qux;                   // [h][m*n | m*m | m*n][ldb]
+  // line-search trial slots, one per step size
+  double *Xt, *Ut, *Yt, *Dt;               // [NA][(h+1)|h][dim][ldb]
+  double *cost_t, *feas_t, *ming_t;        // [NA][h+1][ldb]
+  double *maxh_t, *ht;                     // [NA][ldb], [NA][4][ldb]
+  int* fail_t;                             // [NA][ldb]
+  // augmented-Lagrangian state of the touchdown constraints
+  double *al_sigma, *al_lambda, *hval;     // [4][ldb]
+};
+
+struct CtrlDev {
+  int *active, *do_ls, *sel, *accepted;
+  int *iter_ou, *iter_in, *iter, *ls_total, *reg_total, *n_hist, *status;
+  double *reg, *cost, *merit, *feas, *merit_rho, *dV1, *dV2, *cost_prev, *merit_prev;
+  double *max_t, *max_p, *max_t_prev, *max_p_prev;
+  double *hist;   // [CAFE_HIST_CAP][4][ldb]
+  double *trace;  // [CAFE_HIST_CAP][12][ldb]
+  double *feas0_t;  // [NA][ldb] |Defect_0[0]|^2 of the first phase per trial
+  double *min_pivot;  // [ldb] smallest LDL^T pivot seen (tie monitoring)
+  int* n_active;  // single counter
+};
+
+struct SolverDev {
+  int n_phases, B, ldb, NA, n_knots;
+  double eps[CAFE_MAX_ALPHAS];
+  CafeOptions opt;
+  PhaseDev ph[CAFE_MAX_PHASES];
+  CtrlDev c;
+  const double* x0;  // [n0][ldb]
+  short knot_phase[CAFE_MAX_KNOTS], knot_k[CAFE_MAX_KNOTS];
+};
+
+// element (k, c) of problem b in an array with NC components per knot
+__device__ __forceinline__ size_t gix(int k, int NC, int c, int ldb, int b) { return ((size_t)k * NC + c) * (size_t)ldb + b; }

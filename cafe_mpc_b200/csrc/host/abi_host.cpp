@@ -1,0 +1,109 @@
+// abi_host.cpp — host-only part of the C ABI (include/cafe_gpu.h): settings, reference ingestion,
+// phase-deck building, result-layout sizes. No CUDA here.
+#include <cstring>
+#include <exception>
+#include <string>
+#include "../../../include/cafe_gpu.h"
+#include "problem_builders.h"
+
+namespace cafe {
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& s) { g_last_error = s; }
+}  // namespace cafe
+
+struct CafeDeckHandle {
+  cafe::DeckStorage st;
+  cafe::QuadReference ref;
+};
+
+extern "C" const char* cafe_last_error(void) { return cafe::g_last_error.c_str(); }
+
+#define CAFE_TRY try {
+#define CAFE_CATCH(code)                 \
+  }                                      \
+  catch (const std::exception& e) {      \
+    cafe::set_last_error(e.what());      \
+    return code;                         \
+  }                                      \
+  catch (...) {                          \
+    cafe::set_last_error("unknown error"); \
+    return code;                         \
+  }
+
+extern "C" int cafe_options_load(const char* fname, CafeOptions* out) {
+  if (!fname || !out) { cafe::set_last_error("null argument"); return CAFE_ERR_ARG; }
+  CAFE_TRY
+  cafe::load_hsddp_setting(fname, *out);
+  return 0;
+  CAFE_CATCH(CAFE_ERR_IO)
+}
+
+extern "C" int cafe_deck_build_hkd(const char* reference_csv, const char* constraint_params_info, float plan_duration,
+                                   float time_step, int nsteps_between_mpc, int k0, CafeDeckHandle** out) {
+  if (!reference_csv || !constraint_params_info || !out) { cafe::set_last_error("null argument"); return CAFE_ERR_ARG; }
+  CAFE_TRY
+  CafeDeckHandle* h = new CafeDeckHandle();
+  try {
+    h->ref.load_top_level_data(reference_csv, true, k0);
+    cafe::HKDProblem prob;
+    cafe::HKDPlanConfig cfg{plan_duration, time_step, nsteps_between_mpc};
+    prob.set_problem_data(&h->ref, cfg, constraint_params_info);
+    prob.initialization(h->st);
+  } catch (...) { delete h; throw; }
+  *out = h;
+  return 0;
+  CAFE_CATCH(CAFE_ERR_IO)
+}
+
+extern "C" int cafe_deck_build_mhpc(const char* reference_csv, const char* mhpc_config_info, const char* settings_root,
+                                    int k0, CafeDeckHandle** out) {
+  if (!reference_csv || !mhpc_config_info || !settings_root || !out) { cafe::set_last_error("null argument"); return CAFE_ERR_ARG; }
+  CAFE_TRY
+  CafeDeckHandle* h = new CafeDeckHandle();
+  try {
+    cafe::MHPCConfig cfg;
+    cafe::loadMHPCConfig(mhpc_config_info, cfg);
+    h->ref.load_top_level_data(reference_csv, false, k0);
+    cafe::MHPCProblem prob;
+    prob.set_problem_data(&h->ref, cfg, settings_root);
+    prob.initialization(h->st);
+  } catch (...) { delete h; throw; }
+  *out = h;
+  return 0;
+  CAFE_CATCH(CAFE_ERR_IO)
+}
+
+extern "C" const CafeDeck* cafe_deck_get(const CafeDeckHandle* h) { return h ? &h->st.deck : nullptr; }
+extern "C" void cafe_deck_free(CafeDeckHandle* h) { delete h; }
+
+extern "C" int cafe_hkd_state(const double body[12], const double qJ[12], const int contact[4], double x0[24]) {
+  if (!body || !qJ || !contact || !x0) { cafe::set_last_error("null argument"); return CAFE_ERR_ARG; }
+  double qdummy[12];
+  cafe::compute_hkd_state(body, body + 3, qJ, qdummy, contact);
+  for (int i = 0; i < 12; ++i) { x0[i] = body[i]; x0[12 + i] = qdummy[i]; }
+  return 0;
+}
+
+extern "C" long cafe_solution_size(const CafeDeck* deck) {
+  long s = 0;
+  for (int i = 0; i < deck->n_phases; ++i) {
+    const CafePhase& ph = deck->phase[i];
+    long n = cafe_model_n(ph.model), m = cafe_model_m(ph.model), p = cafe_model_p(ph.model), h = ph.horizon;
+    s += (h + 1) * n + h * m + h * p + h * m + h * m * n + h * m + h * m * m + h * m * n + (h + 1) * n;
+  }
+  return s;
+}
+
+extern "C" long cafe_command_size(const CafeDeck* deck, int n_gain_knots) {
+  long s = 0;
+  int left = n_gain_knots;
+  for (int i = 0; i < deck->n_phases; ++i) {
+    const CafePhase& ph = deck->phase[i];
+    long n = cafe_model_n(ph.model), m = cafe_model_m(ph.model), p = cafe_model_p(ph.model), h = ph.horizon;
+    s += (h + 1) * n + h * m + h * p;
+    long g = left < h ? left : h;
+    s += g * (m * n + m + m * m + m * n);
+    left -= (int)g;
+  }
+  return s;
+}

@@ -1,0 +1,72 @@
+// problem_builders.h — host-side mirrors of the reference's problem builders. They walk the
+// reference contact schedule with the reference's own (float) arithmetic and produce the plain-data
+// phase deck (include/cafe_deck.h) instead of a deque of SinglePhase objects wired with callbacks.
+//   HKDProblem<T>   /root/reference/HKDMPC/HKD-TrajOpt/HKDProblem.{h,cpp}
+//   MHPCProblem<T>  /root/reference/MHPC/MHPC-Trajopt/MHPCProblem.{h,cpp}
+#pragma once
+#include <string>
+#include <vector>
+#include "../../../include/cafe_deck.h"
+#include "quad_reference.h"
+
+namespace cafe {
+
+// approx_eq_scalar & friends (HSDDP_Utils.h:46-78): float tolerance 1e-6, float error
+template <typename T1, typename T2>
+inline bool approx_eq_scalar(T1 n1, T2 n2) { float tol = 1e-6; float err = std::abs(n1 - n2); return err <= tol; }
+template <typename T1, typename T2>
+inline bool approx_leq_scalar(T1 n1, T2 n2) { return n1 < n2 || approx_eq_scalar(n1, n2); }
+template <typename T1, typename T2>
+inline bool approx_geq_scalar(T1 n1, T2 n2) { return n1 > n2 || approx_eq_scalar(n1, n2); }
+
+struct DeckStorage {  // owns the memory a CafeDeck points into
+  CafeDeck deck;
+  std::vector<double> ref;
+  std::vector<float> phase_start_times, phase_end_times;
+};
+
+struct HKDPlanConfig {  // HKDProblem.h:20-25
+  float plan_duration;
+  float timeStep;
+  int nsteps_between_mpc;
+};
+
+class HKDProblem {  // HKDProblem.h:93-168
+ public:
+  void set_problem_data(QuadReference* quad_ref, const HKDPlanConfig& config, const std::string& constraint_params_fname);
+  void initialization(DeckStorage& out);  // HKDProblem.cpp:15-111
+
+ private:
+  QuadReference* quad_ref_ptr = nullptr;
+  float plan_duration = 0, dt_sim = 0, dt_mpc = 0;
+  int nsteps_between_mpc = 0;
+  CafeRebParam grf_reb_param{}, swing_reb_param{};
+  CafeAlParam td_al_param{};
+};
+
+struct MHPCConfig {  // MHPCProblem.h:43-65
+  float plan_dur_wb, plan_dur_srb, dt_mpc, dt_wb, dt_srb;
+  double BG_alpha;
+  int num_threads;
+  std::string referenceFileName, costFileName, constraintParamFileName;
+};
+void loadMHPCConfig(const std::string& fname, MHPCConfig& config);  // MHPCProblem.h:67-83
+
+class MHPCProblem {  // MHPCProblem.h:169-289
+ public:
+  void set_problem_data(QuadReference* quad_ref, const MHPCConfig& config, const std::string& settings_root);
+  void initialization(DeckStorage& out);  // MHPCProblem.cpp:13-250
+
+ private:
+  QuadReference* quad_reference = nullptr;
+  MHPCConfig pconfig{};
+  std::string root;
+  float plan_dur_all = 0;
+};
+
+// compute_hkd_state (HKDModel.h:66-96): qdummy from joint angles (swing) or foot FK (stance)
+void compute_hkd_state(const double eul[3], const double pos[3], const double qJ[12], double qdummy[12], const int contact[4]);
+
+void load_hsddp_setting(const std::string& fname, CafeOptions& o);  // loadHSDDPSetting, HSDDP_CompoundTypes.h:57-82
+
+}  // namespace cafe

@@ -1,0 +1,512 @@
+// solver.cu — GPU part of the C ABI (include/cafe_gpu.h): device arena, tick loop, result packing.
+//
+// One "tick" advances EVERY still-active problem of the batch by one DDP iteration
+// (MultiPhaseDDP::solve inner-loop body, HSDDPSolver/source/MultiPhaseDDP.cpp:277-386):
+//     k_lq -> k_bwd (sweep + linear rollout + merit parameter) -> k_roll (all step sizes at once)
+//          -> k_select (Armijo over step sizes, exits, AL update) -> k_accept
+// Per-problem control state lives on the device; the host only polls one counter per tick.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+#include "../../include/cafe_gpu.h"
+#include "kernels.cuh"
+
+namespace cafe { void set_last_error(const std::string& s); }
+
+#define CUDA_OK(call)                                                                        \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess) {                                                                 \
+      cafe::set_last_error(std::string(#call) + ": " + cudaGetErrorString(e_));              \
+      return CAFE_ERR_CUDA;                                                                  \
+    }                                                                                        \
+  } while (0)
+
+struct PackSeg { const double* src; int knots, nc; long dst; };
+
+struct CafeHandle {
+  int device = 0, max_batch = 0, ldb = 0, B = 0, NA = 0;
+  CafeDeck deck;
+  std::vector<double> ref_host;
+  SolverDev S;            // host copy (device pointers inside)
+  SolverDev* dS = nullptr;
+  char* arena = nullptr;  // everything per-problem
+  size_t arena_bytes = 0, zero_bytes = 0;  // [0, zero_bytes) is re-zeroed at every solve
+  double* d_ref = nullptr;
+  double* d_x0raw = nullptr;
+  int* d_fail = nullptr; size_t fail_bytes = 0;
+  int* h_nactive = nullptr;  // pinned
+  double* d_pack = nullptr; size_t pack_bytes = 0;
+  PackSeg* d_segs = nullptr; int max_segs = 0;
+  cudaStream_t stream = nullptr;
+  bool profiling = false;
+  double ms[CAFE_NKERNELS] = {0};
+  long launches[CAFE_NKERNELS] = {0};
+  int ticks = 0;
+  int bwd_variant = 0;  // 0: HKD deck (24,24,0)   1: MHPC deck (36,24->12,12)
+  size_t bwd_smem = 0;
+  int bwd_pb = 4;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace {
+
+using namespace cafe_dev;
+
+__global__ void k_init(const SolverDev* __restrict__ Sp, const double* __restrict__ x0raw, int n0) {
+  const SolverDev& S = *Sp;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = (int)(t % S.ldb);
+  const int gk = (int)(t / S.ldb);
+  if (gk >= S.n_knots || b >= S.B) return;
+  const int pi = S.knot_phase[gk], k = S.knot_k[gk];
+  const PhaseDev& ph = S.ph[pi];
+  const double* rec = ph.ref + (size_t)k * CAFE_REF_W;
+  for (int i = 0; i < ph.n; ++i) { const double v = rec[CAFE_REF_XR + i]; ph.Xbar[gix(k, ph.n, i, S.ldb, b)] = v; ph.X[gix(k, ph.n, i, S.ldb, b)] = v; }
+  if (k == 0) for (int i = 0; i < ph.n_td; ++i) { ph.al_sigma[(size_t)i * S.ldb + b] = ph.al_td.sigma; ph.al_lambda[(size_t)i * S.ldb + b] = ph.al_td.lambda; }
+  if (gk == 0) {
+    double* x0 = const_cast<double*>(S.x0);
+    for (int i = 0; i < n0; ++i) x0[(size_t)i * S.ldb + b] = x0raw[(size_t)b * n0 + i];
+    S.c.active[b] = 1; S.c.do_ls[b] = 1; S.c.sel[b] = -1; S.c.min_pivot[b] = 1e300;
+  }
+}
+
+__global__ void k_init_devx0(const SolverDev* __restrict__ Sp, const double* __restrict__ x0dev, int ldx, int n0) {
+  const SolverDev& S = *Sp;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= S.B) return;
+  double* x0 = const_cast<double*>(S.x0);
+  for (int i = 0; i < n0; ++i) x0[(size_t)i * S.ldb + b] = x0dev[(size_t)i * ldx + b];
+}
+
+__global__ void k_pack(const PackSeg* __restrict__ segs, int nseg, int ldb, int b0, int nb, long sol_size, double* __restrict__ out) {
+  const int s = blockIdx.y;
+  if (s >= nseg) return;
+  const PackSeg sg = segs[s];
+  const long total = (long)sg.knots * sg.nc;
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total * nb; t += (long)gridDim.x * blockDim.x) {
+    const int bb = (int)(t % nb);
+    const long e = t / nb;
+    out[(size_t)bb * sol_size + sg.dst + e] = sg.src[(size_t)e * ldb + b0 + bb];
+  }
+}
+
+__global__ void k_fp64_peak(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 0.999999, c = 1e-7;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+struct Carver {
+  size_t off = 0;
+  char* base = nullptr;
+  template <class T>
+  T* take(size_t count) {
+    off = (off + 255) & ~(size_t)255;
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += count * sizeof(T);
+    return p;
+  }
+};
+
+// lays out every per-problem array; called twice (size pass with base == nullptr, then for real)
+void carve(CafeHandle* H, Carver& cv, size_t& zero_bytes) {
+  SolverDev& S = H->S;
+  const size_t ldb = H->ldb;
+  const int NA = H->NA;
+  // ---- region re-zeroed at every solve
+  CtrlDev& c = S.c;
+  c.active = cv.take<int>(ldb); c.do_ls = cv.take<int>(ldb); c.sel = cv.take<int>(ldb); c.accepted = cv.take<int>(ldb);
+  c.iter_ou = cv.take<int>(ldb); c.iter_in = cv.take<int>(ldb); c.iter = cv.take<int>(ldb); c.ls_total = cv.take<int>(ldb);
+  c.reg_total = cv.take<int>(ldb); c.n_hist = cv.take<int>(ldb); c.status = cv.take<int>(ldb);
+  c.n_active = cv.take<int>(64);
+  c.reg = cv.take<double>(ldb); c.cost = cv.take<double>(ldb); c.merit = cv.take<double>(ldb); c.feas = cv.take<double>(ldb);
+  c.merit_rho = cv.take<double>(ldb); c.dV1 = cv.take<double>(ldb); c.dV2 = cv.take<double>(ldb);
+  c.cost_prev = cv.take<double>(ldb); c.merit_prev = cv.take<double>(ldb);
+  c.max_t = cv.take<double>(ldb); c.max_p = cv.take<double>(ldb); c.max_t_prev = cv.take<double>(ldb); c.max_p_prev = cv.take<double>(ldb);
+  c.min_pivot = cv.take<double>(ldb);
+  c.feas0_t = cv.take<double>((size_t)NA * ldb);
+  c.hist = cv.take<double>((size_t)CAFE_HIST_CAP * 4 * ldb);
+  c.trace = cv.take<double>((size_t)CAFE_HIST_CAP * 12 * ldb);
+  S.x0 = cv.take<double>((size_t)CAFE_MAX_N * ldb);
+  // fail flags of all phases, contiguous so that one memset clears them
+  {
+    int* f = cv.take<int>((size_t)S.n_phases * NA * ldb);
+    H->d_fail = f; H->fail_bytes = (size_t)S.n_phases * NA * ldb * sizeof(int);
+    for (int i = 0; i < S.n_phases; ++i) S.ph[i].fail_t = f ? f + (size_t)i * NA * ldb : nullptr;
+  }
+  for (int i = 0; i < S.n_phases; ++i) {
+    PhaseDev& ph = S.ph[i];
+    const size_t n = ph.n, m = ph.m, p = ph.p, h = ph.h;
+    ph.X = cv.take<double>((h + 1) * n * ldb); ph.Xbar = cv.take<double>((h + 1) * n * ldb); ph.dX = cv.take<double>((h + 1) * n * ldb);
+    ph.G = cv.take<double>((h + 1) * n * ldb); ph.Defect = cv.take<double>((h + 1) * n * ldb);
+    ph.U = cv.take<double>(h * m * ldb); ph.Ubar = cv.take<double>(h * m * ldb); ph.dU = cv.take<double>(h * m * ldb);
+    ph.Qu = cv.take<double>(h * m * ldb); ph.Y = cv.take<double>(h * p * ldb + 1);
+    ph.K = cv.take<double>(h * m * n * ldb);
+    ph.lk = cv.take<double>((h + 1) * ldb); ph.dsq = cv.take<double>((h + 1) * ldb);
+    ph.al_sigma = cv.take<double>(4 * ldb); ph.al_lambda = cv.take<double>(4 * ldb); ph.hval = cv.take<double>(4 * ldb);
+    ph.maxh_t = cv.take<double>((size_t)NA * ldb); ph.ht = cv.take<double>((size_t)NA * 4 * ldb);
+  }
+  zero_bytes = cv.off;
+  // ---- region whose zero pattern is static (zeroed once at create)
+  for (int i = 0; i < S.n_phases; ++i) {
+    PhaseDev& ph = S.ph[i];
+    const size_t n = ph.n, m = ph.m, p = ph.p, h = ph.h, nn = ph.n_next > 0 ? ph.n_next : 1;
+    ph.A = cv.take<double>(h * n * n * ldb); ph.Bm = cv.take<double>(h * n * m * ldb);
+    ph.C = cv.take<double>(h * p * n * ldb + 1); ph.D = cv.take<double>(h * p * m * ldb + 1);
+    ph.lx = cv.take<double>(h * n * ldb); ph.lu = cv.take<double>(h * m * ldb); ph.ly = cv.take<double>(h * p * ldb + 1);
+    ph.lxx = cv.take<double>(h * n * n * ldb); ph.luu = cv.take<double>(h * m * m * ldb); ph.lyy = cv.take<double>(h * p * p * ldb + 1);
+    ph.Phix = cv.take<double>(n * ldb); ph.Phixx = cv.take<double>(n * n * ldb); ph.Px = cv.take<double>(nn * n * ldb);
+    ph.Quu = cv.take<double>(h * m * m * ldb); ph.Qux = cv.take<double>(h * m * n * ldb);
+    ph.Xt = cv.take<double>((size_t)NA * (h + 1) * n * ldb); ph.Ut = cv.take<double>((size_t)NA * h * m * ldb);
+    ph.Yt = cv.take<double>((size_t)NA * h * p * ldb + 1); ph.Dt = cv.take<double>((size_t)NA * (h + 1) * n * ldb);
+    ph.cost_t = cv.take<double>((size_t)NA * (h + 1) * ldb); ph.feas_t = cv.take<double>((size_t)NA * (h + 1) * ldb);
+    ph.ming_t = cv.take<double>((size_t)NA * (h + 1) * ldb);
+  }
+}
+
+int compute_alphas(const CafeOptions& o, double* eps) {  // MultiPhaseDDP.cpp:109-130: eps = 1; while (eps > 1e-3) {...; eps *= alpha;}
+  int n = 0;
+  double e = 1;
+  while (e > 1e-3 && n < CAFE_MAX_ALPHAS) { eps[n++] = e; e *= o.alpha; }
+  return n;
+}
+
+template <class F>
+int timed(CafeHandle* H, int slot, F&& launch) {
+  if (H->profiling) cudaEventRecord(H->ev0, H->stream);
+  launch();
+  H->launches[slot]++;
+  if (H->profiling) {
+    cudaEventRecord(H->ev1, H->stream);
+    cudaEventSynchronize(H->ev1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, H->ev0, H->ev1);
+    H->ms[slot] += ms;
+  }
+  return 0;
+}
+
+int launch_bwd(CafeHandle* H) {
+  const int PB = H->bwd_pb;
+  const int grid = (H->B + PB - 1) / PB;
+  if (H->bwd_variant == 0) k_bwd<24, 24, 0, 4><<<grid, CAFE_NW * 4, H->bwd_smem, H->stream>>>(H->dS);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, CafeHandle** out) {
+  if (!deck || !out || max_batch <= 0 || deck->n_phases <= 0 || deck->n_phases > CAFE_MAX_PHASES) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cafe::set_last_error("no CUDA device: this library has no CPU fallback"); return CAFE_ERR_CUDA; }
+  if (device < 0 || device >= ndev) { cafe::set_last_error("bad device index"); return CAFE_ERR_ARG; }
+  CUDA_OK(cudaSetDevice(device));
+  bool all_hkd = true;
+  int n_knots = 0;
+  for (int i = 0; i < deck->n_phases; ++i) { all_hkd = all_hkd && deck->phase[i].model == CAFE_MODEL_HKD; n_knots += deck->phase[i].horizon + 1; }
+  if (!all_hkd) { cafe::set_last_error("only HKD decks are supported by this build of the GPU path"); return CAFE_ERR_UNSUPPORTED; }
+  if (n_knots > CAFE_MAX_KNOTS) { cafe::set_last_error("horizon too long"); return CAFE_ERR_UNSUPPORTED; }
+  for (int i = 0; i < deck->n_phases; ++i) {
+    const CafePhase& p = deck->phase[i];
+    if (p.reb_grf.delta < p.reb_grf.delta_min) { cafe::set_last_error("ReB delta < delta_min is not supported"); return CAFE_ERR_UNSUPPORTED; }
+  }
+  CafeHandle* H = new CafeHandle();
+  H->device = device; H->max_batch = max_batch; H->ldb = (max_batch + 31) / 32 * 32;
+  H->deck = *deck;
+  H->ref_host.assign(deck->ref, deck->ref + (size_t)deck->n_records * CAFE_REF_W);
+  H->deck.ref = H->ref_host.data();
+  H->NA = CAFE_MAX_ALPHAS;  // trial slots are sized for the longest step-size ladder
+  // the ladder depends on option.alpha; size for alpha <= 0.5 (10 trials) -- see solve
+  H->NA = 10;
+  SolverDev& S = H->S;
+  std::memset(&S, 0, sizeof(S));
+  S.n_phases = deck->n_phases; S.ldb = H->ldb; S.n_knots = n_knots;
+  int gk = 0;
+  for (int i = 0; i < deck->n_phases; ++i) {
+    const CafePhase& p = deck->phase[i];
+    PhaseDev& d = S.ph[i];
+    d.model = p.model; d.n = cafe_model_n(p.model); d.m = cafe_model_m(p.model); d.p = cafe_model_p(p.model); d.h = p.horizon;
+    d.has_next = (i < deck->n_phases - 1) ? 1 : 0;
+    d.n_next = d.has_next ? cafe_model_n(deck->phase[i + 1].model) : 0;
+    for (int l = 0; l < 4; ++l) { d.contact[l] = p.contact[l]; d.next_contact[l] = p.next_contact[l]; d.td_foot[l] = p.td_foot[l]; }
+    d.n_td = p.n_td; d.dt = p.dt; d.mu = p.mu; d.ground_height = p.ground_height; d.BG_alpha = deck->BG_alpha;
+    std::memcpy(d.q, p.q, sizeof(d.q)); std::memcpy(d.r, p.r, sizeof(d.r)); std::memcpy(d.qf, p.qf, sizeof(d.qf));
+    std::memcpy(d.w_footreg, p.w_footreg, sizeof(d.w_footreg)); std::memcpy(d.w_swingpos, p.w_swingpos, sizeof(d.w_swingpos));
+    std::memcpy(d.w_swingvel, p.w_swingvel, sizeof(d.w_swingvel)); std::memcpy(d.w_tdvel, p.w_tdvel, sizeof(d.w_tdvel));
+    d.reb_grf = p.reb_grf; d.reb_torque = p.reb_torque; d.reb_joint = p.reb_joint; d.reb_minheight = p.reb_minheight; d.al_td = p.al_td;
+    for (int k = 0; k <= p.horizon; ++k) { S.knot_phase[gk] = (short)i; S.knot_k[gk] = (short)k; ++gk; }
+  }
+  Carver sz;
+  size_t zb = 0;
+  carve(H, sz, zb);
+  H->arena_bytes = sz.off + 256;
+  cudaError_t e = cudaMalloc(&H->arena, H->arena_bytes);
+  if (e != cudaSuccess) { cafe::set_last_error(std::string("cudaMalloc arena: ") + cudaGetErrorString(e)); delete H; return CAFE_ERR_CUDA; }
+  Carver cv; cv.base = H->arena;
+  carve(H, cv, H->zero_bytes);
+  CUDA_OK(cudaMemset(H->arena, 0, H->arena_bytes));
+  CUDA_OK(cudaMalloc(&H->d_ref, H->ref_host.size() * sizeof(double)));
+  CUDA_OK(cudaMemcpy(H->d_ref, H->ref_host.data(), H->ref_host.size() * sizeof(double), cudaMemcpyHostToDevice));
+  for (int i = 0; i < deck->n_phases; ++i) S.ph[i].ref = H->d_ref + (size_t)deck->phase[i].knot_offset * CAFE_REF_W;
+  CUDA_OK(cudaMalloc(&H->d_x0raw, (size_t)H->ldb * CAFE_MAX_N * sizeof(double)));
+  CUDA_OK(cudaMalloc(&H->dS, sizeof(SolverDev)));
+  CUDA_OK(cudaMallocHost(&H->h_nactive, 64));
+  CUDA_OK(cudaStreamCreate(&H->stream));
+  CUDA_OK(cudaEventCreate(&H->ev0));
+  CUDA_OK(cudaEventCreate(&H->ev1));
+  H->max_segs = 9 * CAFE_MAX_PHASES;
+  CUDA_OK(cudaMalloc(&H->d_segs, H->max_segs * sizeof(PackSeg)));
+  H->bwd_variant = 0; H->bwd_pb = 4;
+  H->bwd_smem = (size_t)cafe_dev::BwdLayout<24, 24, 0>::total * 4 * sizeof(double);
+  CUDA_OK(cudaFuncSetAttribute(cafe_dev::k_bwd<24, 24, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H->bwd_smem));
+  *out = H;
+  return 0;
+}
+
+extern "C" int cafe_gpu_destroy(CafeHandle* H) {
+  if (!H) return 0;
+  cudaSetDevice(H->device);
+  cudaFree(H->arena); cudaFree(H->d_ref); cudaFree(H->d_x0raw); cudaFree(H->dS); cudaFree(H->d_pack); cudaFree(H->d_segs);
+  if (H->h_nactive) cudaFreeHost(H->h_nactive);
+  if (H->stream) cudaStreamDestroy(H->stream);
+  if (H->ev0) cudaEventDestroy(H->ev0);
+  if (H->ev1) cudaEventDestroy(H->ev1);
+  delete H;
+  return 0;
+}
+
+static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_dev, int ldx, int B, const CafeOptions* opt) {
+  if (!H || !opt || B <= 0 || B > H->max_batch) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
+  if (!opt->MS) { cafe::set_last_error("single shooting (MS = false) is not supported: every knot must be a shooting node"); return CAFE_ERR_UNSUPPORTED; }
+  if (opt->update_relax != 1.0 || opt->update_ReB != 1.0) { cafe::set_last_error("update_relax / update_ReB != 1 are not supported by this build"); return CAFE_ERR_UNSUPPORTED; }
+  if (opt->max_AL_iter * opt->max_DDP_iter + 1 > CAFE_HIST_CAP) { cafe::set_last_error("iteration caps exceed the history capacity"); return CAFE_ERR_UNSUPPORTED; }
+  CUDA_OK(cudaSetDevice(H->device));
+  SolverDev& S = H->S;
+  S.B = B; S.opt = *opt;
+  S.NA = compute_alphas(*opt, S.eps);
+  if (S.NA > H->NA) { cafe::set_last_error("step-size ladder longer than the allocated trial slots"); return CAFE_ERR_UNSUPPORTED; }
+  // trial-slot strides are fixed by the allocation (H->NA slots), the ladder may be shorter
+  H->B = B;
+  for (int i = 0; i < CAFE_NKERNELS; ++i) { H->ms[i] = 0; H->launches[i] = 0; }
+  H->ticks = 0;
+  cudaStream_t st = H->stream;
+  CUDA_OK(cudaMemcpyAsync(H->dS, &S, sizeof(SolverDev), cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemsetAsync(H->arena, 0, H->zero_bytes, st));
+  const int n0 = S.ph[0].n;
+  if (x0_host) CUDA_OK(cudaMemcpyAsync(H->d_x0raw, x0_host, (size_t)B * n0 * sizeof(double), cudaMemcpyHostToDevice, st));
+  const long long nthr_knots = (long long)S.ldb * S.n_knots;
+  const int tpb = 128;
+  const unsigned g_knots = (unsigned)((nthr_knots + tpb - 1) / tpb);
+  timed(H, 5, [&] { k_init<<<g_knots, tpb, 0, st>>>(H->dS, H->d_x0raw, n0); });
+  if (x0_dev) timed(H, 5, [&] { k_init_devx0<<<(B + 127) / 128, 128, 0, st>>>(H->dS, x0_dev, ldx, n0); });
+  // ---- initial rollout (eps = 0) and bookkeeping
+  {
+    SolverDev S0 = S;  // same pointers, ladder {0}
+    S0.NA = 1; S0.eps[0] = 0.0;
+    CUDA_OK(cudaMemcpyAsync(H->dS, &S0, sizeof(SolverDev), cudaMemcpyHostToDevice, st));
+    timed(H, 0, [&] { cafe_dev::k_roll<<<g_knots, tpb, 0, st>>>(H->dS, 1); });
+    timed(H, 1, [&] { cafe_dev::k_select<<<(B + 127) / 128, 128, 0, st>>>(H->dS, 0); });
+    timed(H, 2, [&] { cafe_dev::k_accept<<<g_knots, tpb, 0, st>>>(H->dS); });
+    CUDA_OK(cudaStreamSynchronize(st));  // S0 must stay alive until the copy has been consumed
+    CUDA_OK(cudaMemcpyAsync(H->dS, &S, sizeof(SolverDev), cudaMemcpyHostToDevice, st));
+  }
+  const int max_ticks = opt->max_AL_iter * opt->max_DDP_iter + 2;
+  const long long nthr_roll = nthr_knots * S.NA;
+  const unsigned g_roll = (unsigned)((nthr_roll + tpb - 1) / tpb);
+  for (int tick = 0; tick < max_ticks; ++tick) {
+    CUDA_OK(cudaMemcpyAsync(H->h_nactive, S.c.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    if (*H->h_nactive == 0) break;
+    H->ticks++;
+    timed(H, 3, [&] { cafe_dev::k_lq<<<g_knots, tpb, 0, st>>>(H->dS); });
+    timed(H, 4, [&] { launch_bwd(H); });
+    CUDA_OK(cudaMemsetAsync(H->d_fail, 0, H->fail_bytes, st));
+    timed(H, 0, [&] { cafe_dev::k_roll<<<g_roll, tpb, 0, st>>>(H->dS, S.NA); });
+    CUDA_OK(cudaMemsetAsync(S.c.n_active, 0, sizeof(int), st));
+    timed(H, 1, [&] { cafe_dev::k_select<<<(B + 127) / 128, 128, 0, st>>>(H->dS, 1); });
+    timed(H, 2, [&] { cafe_dev::k_accept<<<g_knots, tpb, 0, st>>>(H->dS); });
+  }
+  CUDA_OK(cudaStreamSynchronize(st));
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int cafe_gpu_solve_batch(CafeHandle* H, const double* x0, int B, const CafeOptions* opt) {
+  if (!x0) { cafe::set_last_error("null x0"); return CAFE_ERR_ARG; }
+  return solve_common(H, x0, nullptr, 0, B, opt);
+}
+extern "C" int cafe_gpu_solve_batch_device(CafeHandle* H, const double* x0_dev, int ldx, int B, const CafeOptions* opt) {
+  if (!x0_dev || ldx < B) { cafe::set_last_error("bad x0_dev"); return CAFE_ERR_ARG; }
+  return solve_common(H, nullptr, x0_dev, ldx, B, opt);
+}
+
+extern "C" int cafe_gpu_set_profiling(CafeHandle* H, int on) { if (!H) return CAFE_ERR_ARG; H->profiling = on != 0; return 0; }
+extern "C" int cafe_gpu_get_timing(CafeHandle* H, double ms[CAFE_NKERNELS], long launches[CAFE_NKERNELS], int* ticks) {
+  if (!H) return CAFE_ERR_ARG;
+  for (int i = 0; i < CAFE_NKERNELS; ++i) { if (ms) ms[i] = H->ms[i]; if (launches) launches[i] = H->launches[i]; }
+  if (ticks) *ticks = H->ticks;
+  return 0;
+}
+
+template <class T>
+static int fetch(CafeHandle* H, const T* dev, size_t count, std::vector<T>& host) {
+  host.resize(count);
+  CUDA_OK(cudaMemcpy(host.data(), dev, count * sizeof(T), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int cafe_gpu_get_info(CafeHandle* H, CafeInfo* info) {
+  if (!H || !info) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
+  CUDA_OK(cudaSetDevice(H->device));
+  const int B = H->B;
+  const CtrlDev& c = H->S.c;
+  std::vector<int> st, it, ls, rg, ou, nh;
+  std::vector<double> cost, feas, mt, mp;
+  int rc;
+  if ((rc = fetch(H, c.status, B, st)) || (rc = fetch(H, c.iter, B, it)) || (rc = fetch(H, c.ls_total, B, ls)) || (rc = fetch(H, c.reg_total, B, rg)) ||
+      (rc = fetch(H, c.iter_ou, B, ou)) || (rc = fetch(H, c.n_hist, B, nh)) || (rc = fetch(H, c.cost, B, cost)) || (rc = fetch(H, c.feas, B, feas)) ||
+      (rc = fetch(H, c.max_t, B, mt)) || (rc = fetch(H, c.max_p, B, mp)))
+    return rc;
+  for (int b = 0; b < B; ++b) {
+    info[b].status = st[b]; info[b].iter = it[b]; info[b].ls_iter_total = ls[b]; info[b].reg_iter_total = rg[b];
+    info[b].outer_iter = ou[b]; info[b].n_hist = nh[b]; info[b].cost = cost[b]; info[b].feas = feas[b];
+    info[b].max_tconstr = mt[b]; info[b].max_pconstr = mp[b];
+  }
+  return 0;
+}
+
+static int get_table(CafeHandle* H, const double* dev, int width, double* out, int cap) {
+  const int B = H->B, ldb = H->ldb;
+  const int rows = cap < CAFE_HIST_CAP ? cap : CAFE_HIST_CAP;
+  std::vector<double> tmp;
+  int rc = fetch(H, dev, (size_t)rows * width * ldb, tmp);
+  if (rc) return rc;
+  for (int b = 0; b < B; ++b)
+    for (int r = 0; r < rows; ++r)
+      for (int j = 0; j < width; ++j) out[((size_t)b * cap + r) * width + j] = tmp[((size_t)r * width + j) * ldb + b];
+  return 0;
+}
+extern "C" int cafe_gpu_get_history(CafeHandle* H, double* hist, int cap) {
+  if (!H || !hist || cap <= 0) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
+  CUDA_OK(cudaSetDevice(H->device));
+  return get_table(H, H->S.c.hist, 4, hist, cap);
+}
+extern "C" int cafe_gpu_get_trace(CafeHandle* H, double* trace, int cap) {
+  if (!H || !trace || cap <= 0) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
+  CUDA_OK(cudaSetDevice(H->device));
+  return get_table(H, H->S.c.trace, 12, trace, cap);
+}
+
+static int run_pack(CafeHandle* H, const std::vector<PackSeg>& segs, long rec_size, int b0, int nb, double* out) {
+  const size_t need = (size_t)nb * rec_size * sizeof(double);
+  if (need > H->pack_bytes) {
+    cudaFree(H->d_pack); H->d_pack = nullptr; H->pack_bytes = 0;
+    CUDA_OK(cudaMalloc(&H->d_pack, need));
+    H->pack_bytes = need;
+  }
+  if ((int)segs.size() > H->max_segs) { cafe::set_last_error("too many pack segments"); return CAFE_ERR_ARG; }
+  CUDA_OK(cudaMemcpyAsync(H->d_segs, segs.data(), segs.size() * sizeof(PackSeg), cudaMemcpyHostToDevice, H->stream));
+  dim3 grid(592, (unsigned)segs.size());
+  k_pack<<<grid, 256, 0, H->stream>>>(H->d_segs, (int)segs.size(), H->ldb, b0, nb, rec_size, H->d_pack);
+  CUDA_OK(cudaMemcpyAsync(out, H->d_pack, need, cudaMemcpyDeviceToHost, H->stream));
+  CUDA_OK(cudaStreamSynchronize(H->stream));
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int cafe_gpu_get_solution(CafeHandle* H, int b0, int nb, double* sol) {
+  if (!H || !sol || b0 < 0 || nb <= 0 || b0 + nb > H->B) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
+  CUDA_OK(cudaSetDevice(H->device));
+  std::vector<PackSeg> segs;
+  long off = 0;
+  for (int i = 0; i < H->S.n_phases; ++i) {
+    const PhaseDev& ph = H->S.ph[i];
+    const int n = ph.n, m = ph.m, p = ph.p, h = ph.h;
+    auto add = [&](const double* src, int knots, int nc) { if (knots * nc > 0) segs.push_back(PackSeg{src, knots, nc, off}); off += (long)knots * nc; };
+    add(ph.Xbar, h + 1, n); add(ph.Ubar, h, m); add(ph.Y, h, p); add(ph.dU, h, m); add(ph.K, h, m * n);
+    add(ph.Qu, h, m); add(ph.Quu, h, m * m); add(ph.Qux, h, m * n); add(ph.G, h + 1, n);
+  }
+  return run_pack(H, segs, off, b0, nb, sol);
+}
+
+extern "C" int cafe_gpu_get_commands(CafeHandle* H, int n_gain_knots, double* cmd) {
+  if (!H || !cmd || n_gain_knots < 0) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
+  CUDA_OK(cudaSetDevice(H->device));
+  std::vector<PackSeg> segs;
+  long off = 0;
+  int left = n_gain_knots;
+  for (int i = 0; i < H->S.n_phases; ++i) {
+    const PhaseDev& ph = H->S.ph[i];
+    const int n = ph.n, m = ph.m, p = ph.p, h = ph.h;
+    auto add = [&](const double* src, int knots, int nc) { if (knots * nc > 0) segs.push_back(PackSeg{src, knots, nc, off}); off += (long)knots * nc; };
+    add(ph.Xbar, h + 1, n); add(ph.Ubar, h, m); add(ph.Y, h, p);
+    const int g = left < h ? left : h;
+    add(ph.K, g, m * n); add(ph.Qu, g, m); add(ph.Quu, g, m * m); add(ph.Qux, g, m * n);
+    left -= g;
+  }
+  return run_pack(H, segs, off, 0, H->B, cmd);
+}
+
+extern "C" long cafe_gpu_debug_get(CafeHandle* H, const char* name, int phase, int b, double* out) {
+  if (!H || !name || !out || phase < 0 || phase >= H->S.n_phases || b < 0 || b >= H->B) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
+  if (cudaSetDevice(H->device) != cudaSuccess) return CAFE_ERR_CUDA;
+  const PhaseDev& ph = H->S.ph[phase];
+  const int n = ph.n, m = ph.m, p = ph.p, h = ph.h, nn = ph.n_next;
+  const std::string nm(name);
+  const double* src = nullptr;
+  long knots = 0, nc = 0;
+  auto set = [&](const double* s, long k, long c) { src = s; knots = k; nc = c; };
+  if (nm == "X") set(ph.X, h + 1, n); else if (nm == "Xbar") set(ph.Xbar, h + 1, n); else if (nm == "U") set(ph.U, h, m);
+  else if (nm == "Ubar") set(ph.Ubar, h, m); else if (nm == "Y") set(ph.Y, h, p); else if (nm == "Defect") set(ph.Defect, h + 1, n);
+  else if (nm == "dX") set(ph.dX, h + 1, n); else if (nm == "dU") set(ph.dU, h, m); else if (nm == "G") set(ph.G, h + 1, n);
+  else if (nm == "Qu") set(ph.Qu, h, m); else if (nm == "A") set(ph.A, h, n * n); else if (nm == "B") set(ph.Bm, h, n * m);
+  else if (nm == "C") set(ph.C, h, p * n); else if (nm == "D") set(ph.D, h, p * m); else if (nm == "K") set(ph.K, h, m * n);
+  else if (nm == "Quu") set(ph.Quu, h, m * m); else if (nm == "Qux") set(ph.Qux, h, m * n); else if (nm == "lx") set(ph.lx, h, n);
+  else if (nm == "lu") set(ph.lu, h, m); else if (nm == "ly") set(ph.ly, h, p); else if (nm == "lxx") set(ph.lxx, h, n * n);
+  else if (nm == "luu") set(ph.luu, h, m * m); else if (nm == "lyy") set(ph.lyy, h, p * p); else if (nm == "l") set(ph.lk, h + 1, 1);
+  else if (nm == "Phix") set(ph.Phix, 1, n); else if (nm == "Phixx") set(ph.Phixx, 1, n * n); else if (nm == "Px") set(ph.Px, 1, (long)nn * n);
+  else { cafe::set_last_error("unknown array name"); return CAFE_ERR_ARG; }
+  const long cnt = knots * nc;
+  if (cnt == 0) return 0;
+  if (cudaMemcpy2D(out, sizeof(double), src + b, (size_t)H->ldb * sizeof(double), sizeof(double), (size_t)cnt, cudaMemcpyDeviceToHost) != cudaSuccess) {
+    cafe::set_last_error("cudaMemcpy2D failed"); return CAFE_ERR_CUDA;
+  }
+  return cnt;
+}
+
+extern "C" int cafe_gpu_measure_fp64_peak(int device, double* tflops) {
+  if (!tflops) return CAFE_ERR_ARG;
+  CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
+  double* d = nullptr;
+  CUDA_OK(cudaMalloc(&d, (size_t)blocks * threads * sizeof(double)));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  k_fp64_peak<<<blocks, threads>>>(d, 1024);
+  double best = 0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0);
+    k_fp64_peak<<<blocks, threads>>>(d, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double fl = 2.0 * 8.0 * iters * (double)blocks * threads;
+    const double tf = fl / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d);
+  CUDA_OK(cudaGetLastError());
+  *tflops = best;
+  return 0;
+}

@@ -1,0 +1,71 @@
+"""ctypes binding of libcafe_gpu.so (the C ABI in include/cafe_gpu.h).
+
+The library must be built (cafe_mpc_b200/build.py or __graft_entry__.build()); there is no
+Python / CPU fallback: if it is missing, importing this module raises."""
+import ctypes as C
+import os
+
+from ._ctypes_defs import Deck, Info, Options, CAFE_NKERNELS
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcafe_gpu.so")
+
+
+class CafeError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("cafe error %d: %s" % (code, msg))
+        self.code = code
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "libcafe_gpu.so is not built (%s). Run `python -m cafe_mpc_b200.build`; "
+            "the product path has no fallback implementation." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, dp, ip = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)
+    lib.cafe_last_error.restype = C.c_char_p
+    lib.cafe_options_load.argtypes = [C.c_char_p, C.POINTER(Options)]
+    lib.cafe_deck_build_hkd.argtypes = [C.c_char_p, C.c_char_p, C.c_float, C.c_float, C.c_int, C.c_int, C.POINTER(vp)]
+    lib.cafe_deck_build_mhpc.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(vp)]
+    lib.cafe_deck_get.restype = C.POINTER(Deck)
+    lib.cafe_deck_get.argtypes = [vp]
+    lib.cafe_deck_free.argtypes = [vp]
+    lib.cafe_deck_free.restype = None
+    lib.cafe_hkd_state.argtypes = [dp, dp, ip, dp]
+    lib.cafe_solution_size.restype = C.c_long
+    lib.cafe_solution_size.argtypes = [C.POINTER(Deck)]
+    lib.cafe_command_size.restype = C.c_long
+    lib.cafe_command_size.argtypes = [C.POINTER(Deck), C.c_int]
+    lib.cafe_gpu_create.argtypes = [C.POINTER(Deck), C.c_int, C.c_int, C.POINTER(vp)]
+    lib.cafe_gpu_destroy.argtypes = [vp]
+    lib.cafe_gpu_solve_batch.argtypes = [vp, vp, C.c_int, C.POINTER(Options)]
+    lib.cafe_gpu_solve_batch_device.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(Options)]
+    lib.cafe_gpu_get_info.argtypes = [vp, C.POINTER(Info)]
+    lib.cafe_gpu_get_history.argtypes = [vp, vp, C.c_int]
+    lib.cafe_gpu_get_trace.argtypes = [vp, vp, C.c_int]
+    lib.cafe_gpu_get_solution.argtypes = [vp, C.c_int, C.c_int, vp]
+    lib.cafe_gpu_get_commands.argtypes = [vp, C.c_int, vp]
+    lib.cafe_gpu_get_timing.argtypes = [vp, C.POINTER(C.c_double * CAFE_NKERNELS), C.POINTER(C.c_long * CAFE_NKERNELS), ip]
+    lib.cafe_gpu_set_profiling.argtypes = [vp, C.c_int]
+    lib.cafe_gpu_debug_get.restype = C.c_long
+    lib.cafe_gpu_debug_get.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, vp]
+    lib.cafe_gpu_measure_fp64_peak.argtypes = [C.c_int, dp]
+    return lib
+
+
+lib = _load()
+
+
+def check(rc):
+    if rc != 0:
+        raise CafeError(rc, lib.cafe_last_error().decode())
+
+
+EXPORTED = [
+    "cafe_last_error", "cafe_options_load", "cafe_deck_build_hkd", "cafe_deck_build_mhpc", "cafe_deck_get",
+    "cafe_deck_free", "cafe_hkd_state", "cafe_solution_size", "cafe_command_size", "cafe_gpu_create",
+    "cafe_gpu_destroy", "cafe_gpu_solve_batch", "cafe_gpu_solve_batch_device", "cafe_gpu_get_info",
+    "cafe_gpu_get_history", "cafe_gpu_get_trace", "cafe_gpu_get_solution", "cafe_gpu_get_commands",
+    "cafe_gpu_get_timing", "cafe_gpu_set_profiling", "cafe_gpu_debug_get", "cafe_gpu_measure_fp64_peak",
+]

@@ -1,0 +1,38 @@
+"""Synthetic perturbed-initial-state batches: x0[b][j] = x0_nom[j] + s_j (2u - 1),
+u = SplitMix64(seed = 0xCAFE, counter = b*64 + j) mapped to [0,1) with 53 bits."""
+import numpy as np
+
+MASK = (1 << 64) - 1
+
+
+def splitmix64(counter, seed=0xCAFE):
+    z = (seed + (counter + 1) * 0x9E3779B97F4A7C15) & MASK
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & MASK
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & MASK
+    return z ^ (z >> 31)
+
+
+def uniform(b, j):
+    return (splitmix64(b * 64 + j) >> 11) * (1.0 / (1 << 53))
+
+
+HKD_NOMINAL_BODY = np.array([0, 0, 0, 0, 0, 0.2486, 0, 0, 0, 0, 0, 0], dtype=np.float64)  # HKDMPC.cpp:46
+HKD_NOMINAL_QJ = np.array([0, -0.8, 1.6] * 4, dtype=np.float64)                            # HKDMPC.cpp:47
+# scales: eul 0.05 rad, pos x,y 0.02 m, z 0.01 m, omega 0.1 rad/s, vel 0.1 m/s, joint angles 0.05 rad
+HKD_BODY_SCALE = np.array([0.05] * 3 + [0.02, 0.02, 0.01] + [0.1] * 3 + [0.1] * 3)
+HKD_QJ_SCALE = np.full(12, 0.05)
+
+
+def hkd_batch(problem, B, perturb=True):
+    """Perturbed HKD initial states: joint angles are perturbed BEFORE compute_hkd_state."""
+    x0 = np.zeros((B, 24))
+    for b in range(B):
+        body = HKD_NOMINAL_BODY.copy()
+        qJ = HKD_NOMINAL_QJ.copy()
+        if perturb and b > 0:  # problem 0 is the nominal problem of HKDMPCSolver::initialize
+            for j in range(12):
+                body[j] += HKD_BODY_SCALE[j] * (2 * uniform(b, j) - 1)
+            for j in range(12):
+                qJ[j] += HKD_QJ_SCALE[j] * (2 * uniform(b, 12 + j) - 1)
+        x0[b] = problem.initial_state(body, qJ)
+    return x0

@@ -1,0 +1,99 @@
+/*
+ * cafe_gpu.h — C ABI of the B200 batched HS-DDP path (libcafe_gpu.so).
+ *
+ * Drop-in boundary: these entry points are what a binding of the reference's
+ * solver API would call. Each one names the reference interface it stands behind:
+ *
+ *   cafe_options_load        loadHSDDPSetting             HSDDPSolver/common/HSDDP_CompoundTypes.h:57-82
+ *   cafe_deck_build_hkd      HKDProblem<T>::initialization HKDMPC/HKD-TrajOpt/HKDProblem.cpp:15-111
+ *                            (+ QuadReference::load_top_level_data / initialize,
+ *                               Reference/QuadReference.cpp:6-31,134-356)
+ *   cafe_deck_build_mhpc     MHPCProblem<T>::initialization MHPC/MHPC-Trajopt/MHPCProblem.cpp:13-250
+ *   cafe_hkd_state           compute_hkd_state            HKDMPC/HKD-TrajOpt/HKDModel.h:66-96
+ *   cafe_gpu_create          MultiPhaseDDP<T>::set_multiPhaseProblem  HSDDPSolver/header/MultiPhaseDDP.h:33-42
+ *   cafe_gpu_solve_batch     MultiPhaseDDP<T>::set_initial_condition + solve
+ *                                                          HSDDPSolver/header/MultiPhaseDDP.h:44-46,
+ *                                                          HSDDPSolver/source/MultiPhaseDDP.cpp:216-447
+ *   cafe_gpu_get_info        MultiPhaseDDP<T>::get_solver_info (both) HSDDPSolver/header/MultiPhaseDDP.h:84-93,
+ *                                                          MultiPhaseDDP.cpp:554-563
+ *   cafe_gpu_get_solution    reads of Trajectory::Xbar/Ubar/Y/K/dU/Qu/Quu/Qux/G after solve
+ *                                                          HSDDPSolver/header/TrajectoryManagement.h:54-85,
+ *                                                          MHPC/MHPCLocomotion.cpp:236-281
+ *
+ * Plain pointers and sizes only; every function returns 0 on success and a negative code on
+ * error (cafe_last_error() holds the text); nothing throws across the boundary. A handle is not
+ * thread-safe: one handle per host thread per GPU. There is NO CPU fallback: without a CUDA device
+ * cafe_gpu_create fails with CAFE_ERR_CUDA.
+ */
+#ifndef CAFE_GPU_H
+#define CAFE_GPU_H
+#include "cafe_deck.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CAFE_ERR_ARG -1
+#define CAFE_ERR_CUDA -2
+#define CAFE_ERR_IO -3
+#define CAFE_ERR_UNSUPPORTED -4
+
+typedef struct CafeDeckHandle CafeDeckHandle;
+typedef struct CafeHandle CafeHandle;
+
+const char* cafe_last_error(void);
+
+/* ---- host-side problem setup ---- */
+int cafe_options_load(const char* ddp_setting_info, CafeOptions* out);
+/* reorder legs = true (HKD convention), k0 = number of leading reference samples to drop */
+int cafe_deck_build_hkd(const char* reference_csv, const char* constraint_params_info, float plan_duration,
+                        float time_step, int nsteps_between_mpc, int k0, CafeDeckHandle** out);
+/* mhpc_config_info is MHPC/settings/mhpc_config.info; its costFile / constraintParamFile entries are
+ * resolved relative to settings_root (the reference resolves them relative to "../"). reference_csv
+ * overrides the file's referenceFile entry. */
+int cafe_deck_build_mhpc(const char* reference_csv, const char* mhpc_config_info, const char* settings_root,
+                         int k0, CafeDeckHandle** out);
+const CafeDeck* cafe_deck_get(const CafeDeckHandle* h);
+void cafe_deck_free(CafeDeckHandle* h);
+/* x0 = [body(12) = eul,pos,omega,vel ; qdummy(12)] from joint angles */
+int cafe_hkd_state(const double body[12], const double qJ[12], const int contact[4], double x0[24]);
+
+/* packed solution of ONE problem, in doubles; per phase, in order:
+ *   Xbar[(h+1) n]  Ubar[h m]  Y[h p]  dU[h m]  K[h m n]  Qu[h m]  Quu[h m m]  Qux[h m n]  G[(h+1) n]
+ * vectors knot-major, matrices column-major per knot (the reference's Eigen layout). */
+long cafe_solution_size(const CafeDeck* deck);
+/* compact "command" record, what the MPC loop consumes (MHPCLocomotion.cpp:236-281):
+ * per phase Xbar, Ubar, Y for all knots, then K, Qu, Quu, Qux for the first n_gain_knots knots
+ * of the whole horizon. */
+long cafe_command_size(const CafeDeck* deck, int n_gain_knots);
+
+/* ---- GPU solver ---- */
+int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, CafeHandle** out);
+int cafe_gpu_destroy(CafeHandle* h);
+/* x0: host [B][n0] row per problem. Runs every problem of the batch to its own termination. */
+int cafe_gpu_solve_batch(CafeHandle* h, const double* x0, int B, const CafeOptions* opt);
+/* same with x0 already resident on the device, layout [n0][ldb] (component-major), ldb >= B */
+int cafe_gpu_solve_batch_device(CafeHandle* h, const double* x0_dev, int ldb, int B, const CafeOptions* opt);
+int cafe_gpu_get_info(CafeHandle* h, CafeInfo* info /*[B]*/);
+/* hist: [B][hist_cap][4] = cost, feas, max_tconstr, max_pconstr per pushed entry */
+int cafe_gpu_get_history(CafeHandle* h, double* hist, int hist_cap);
+/* trace: [B][trace_cap][12], same record as the oracle's CAFE_TRACE_W */
+int cafe_gpu_get_trace(CafeHandle* h, double* trace, int trace_cap);
+int cafe_gpu_get_solution(CafeHandle* h, int b0, int nb, double* sol /*[nb][cafe_solution_size]*/);
+int cafe_gpu_get_commands(CafeHandle* h, int n_gain_knots, double* cmd /*[B][cafe_command_size]*/);
+/* device-time breakdown of the last solve, ms per kernel family, and launch counts */
+#define CAFE_NKERNELS 6 /* 0 roll 1 select 2 accept 3 lq 4 bwd 5 misc */
+int cafe_gpu_get_timing(CafeHandle* h, double ms[CAFE_NKERNELS], long launches[CAFE_NKERNELS], int* ticks);
+/* enable per-kernel CUDA-event timing (costs a few us per launch) */
+int cafe_gpu_set_profiling(CafeHandle* h, int on);
+
+/* raw read-back of an internal per-knot array of problem b (same names/layout as the oracle's cafe_oracle_get:
+ * vectors [k][i], matrices column-major per knot); for parity tests. Returns doubles written or a negative error. */
+long cafe_gpu_debug_get(CafeHandle* h, const char* name, int phase, int b, double* out);
+
+/* fp64 FMA peak microbenchmark on the current device (TFLOP/s), for the roofline denominator */
+int cafe_gpu_measure_fp64_peak(int device, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAFE_GPU_H */

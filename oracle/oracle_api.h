@@ -1,0 +1,43 @@
+/*
+ * oracle_api.h — C entry points of the CPU ORACLE.
+ *
+ * TEST INFRASTRUCTURE ONLY. The oracle is a plain-C++ restatement of the reference's
+ * HS-DDP solver and models; it exists to CHECK the CUDA path (tests/, smoke(),
+ * bench.py's cpu_baseline / --impl reference leg). Nothing in the product library
+ * links, loads or calls it.
+ */
+#ifndef CAFE_ORACLE_API_H
+#define CAFE_ORACLE_API_H
+#include "../include/cafe_deck.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* number of doubles of one packed solution (see cafe_solution_layout in cafe_gpu.h):
+ * per phase: Xbar[(h+1)n] Ubar[h m] Y[h p] dU[h m] K[h m n] Qu[h m] Quu[h m m] Qux[h m n] G[(h+1) n] */
+long cafe_oracle_solution_size(const CafeDeck* deck);
+
+/* per-iteration trace record (doubles), one per executed DDP iteration */
+#define CAFE_TRACE_W 12
+/* 0 cost_at_start 1 feas_at_start 2 dV_1 3 dV_2 4 merit_rho 5 reg_after 6 reg_iters 7 ls_iters
+ * 8 ls_success 9 eps_accepted(0 if none) 10 cost_after 11 feas_after */
+
+/* Solve one problem. hist: [hist_cap][4] = cost, feas, max_tconstr, max_pconstr.
+ * trace: [trace_cap][CAFE_TRACE_W]. sol: packed solution or NULL. Returns 0. */
+int cafe_oracle_solve(const CafeDeck* deck, const CafeOptions* opt, const double* x0,
+                      CafeInfo* info, double* hist, int hist_cap,
+                      double* trace, int trace_cap, double* sol);
+
+/* Internal per-knot array of the most recent cafe_oracle_solve (names: X Xbar U Ubar Y Defect dX dU G Qu A B C D K
+ * Quu Qux H lx lu ly lxx luu lyy l Phix Phixx Px). Returns the number of doubles written or -1. */
+long cafe_oracle_get(const char* name, int phase, double* out);
+
+/* Reference CasADi functions (from oracle/_ref) behind a flat signature, for the
+ * "re-emitted device functions == reference generated code" tests. Returns 0, or
+ * -1 if the name is unknown. in/out are dense column-major buffers. */
+int cafe_oracle_casadi_eval(const char* name, const double* const* in, double* const* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

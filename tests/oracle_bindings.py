@@ -1,0 +1,74 @@
+"""TEST INFRASTRUCTURE: ctypes access to the CPU oracle (oracle/). Only tests/, smoke() and
+bench.py's CPU-baseline legs may import this."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from cafe_mpc_b200._ctypes_defs import CAFE_TRACE_W, Deck, Info, Options
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(REPO, "oracle")
+ORACLE_LIB = os.path.join(ORACLE_DIR, "build", "libcafe_oracle.so")
+
+
+def build_oracle():
+    subprocess.run(["make", "-C", ORACLE_DIR, "-j8", "all"], check=True, capture_output=True)
+    return ORACLE_LIB
+
+
+_lib = None
+
+
+def oracle():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(ORACLE_LIB) or os.path.exists("/root/reference"):
+            build_oracle()
+        _lib = C.CDLL(ORACLE_LIB)
+        _lib.cafe_oracle_solution_size.restype = C.c_long
+        _lib.cafe_oracle_solution_size.argtypes = [C.POINTER(Deck)]
+        _lib.cafe_oracle_solve.argtypes = [C.POINTER(Deck), C.POINTER(Options), C.c_void_p, C.POINTER(Info), C.c_void_p,
+                                           C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    return _lib
+
+
+def oracle_solve(deck, opt, x0, cap=256):
+    """Returns (info dict, hist [n_hist,4], trace [iter,12], packed solution)."""
+    lib = oracle()
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    info = Info()
+    hist = np.zeros((cap, 4))
+    trace = np.zeros((cap, CAFE_TRACE_W))
+    sol = np.zeros(lib.cafe_oracle_solution_size(deck))
+    rc = lib.cafe_oracle_solve(deck, C.byref(opt), x0.ctypes.data_as(C.c_void_p), C.byref(info),
+                               hist.ctypes.data_as(C.c_void_p), cap, trace.ctypes.data_as(C.c_void_p), cap,
+                               sol.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise RuntimeError("oracle solve failed")
+    d = info.as_dict()
+    return d, hist[:d["n_hist"]], trace[:d["iter"]], sol
+
+
+def oracle_get(name, phase):
+    lib = oracle()
+    lib.cafe_oracle_get.restype = C.c_long
+    buf = np.zeros(64 * 36 * 36 + 64)
+    n = lib.cafe_oracle_get(name.encode(), phase, buf.ctypes.data_as(C.c_void_p))
+    if n < 0:
+        raise KeyError(name)
+    return buf[:n].copy()
+
+
+def casadi_eval(name, ins, out_shapes):
+    """Evaluate a reference CasADi function (oracle/_ref) on dense inputs; returns dense column-major outputs."""
+    lib = oracle()
+    ins = [np.ascontiguousarray(np.atleast_1d(np.asarray(a, dtype=np.float64))) for a in ins]
+    outs = [np.zeros(int(np.prod(s))) for s in out_shapes]
+    pin = (C.c_void_p * len(ins))(*[a.ctypes.data for a in ins])
+    pout = (C.c_void_p * len(outs))(*[a.ctypes.data for a in outs])
+    rc = lib.cafe_oracle_casadi_eval(name.encode(), pin, pout)
+    if rc != 0:
+        raise KeyError(name)
+    return [o.reshape(s, order="F") for o, s in zip(outs, out_shapes)]
