@@ -1,0 +1,166 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the same seeded
+inputs, against the committed golden fixtures, and through size-independent properties at full batch size.
+
+Tolerances (BASELINE.json north_star): contact/phase schedules and iteration counts bit-exact; per-iteration
+cost, gains and final trajectories within 1e-9 relative (relative to the largest entry of each array)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle_bindings import oracle_get, oracle_solve
+
+pytestmark = pytest.mark.gpu
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+COUNTS = ("status", "iter", "ls_iter_total", "reg_iter_total", "outer_iter", "n_hist")
+RTOL = 1e-9
+
+
+def relerr(g, o):
+    o = np.asarray(o); g = np.asarray(g)
+    if o.size == 0:
+        return 0.0
+    return float(np.max(np.abs(g - o)) / max(np.max(np.abs(o)), 1e-300))
+
+
+def solve_gpu(cm, prob, opt, x0):
+    s = cm.MultiPhaseDDP(prob, 0, len(x0))
+    s.set_initial_condition(x0)
+    s.solve(opt)
+    return s
+
+
+def test_single_hkd_solve_matches_oracle_and_golden(cm, hkd_problem, hkd_options):
+    """BASELINE config 1: the single HKD trot solve of HKDMPCSolver::initialize."""
+    from cafe_mpc_b200 import workload
+    x0 = workload.hkd_batch(hkd_problem, 1)
+    s = solve_gpu(cm, hkd_problem, hkd_options, x0)
+    gi = s.get_solver_info()[0]
+    oi, oh, ot, osol = oracle_solve(hkd_problem.deck, hkd_options, x0[0])
+    assert [gi[k] for k in COUNTS] == [oi[k] for k in COUNTS]
+    gh = s.get_history(256)[0, :gi["n_hist"]]
+    np.testing.assert_allclose(gh[:, 0], oh[:, 0], rtol=RTOL)          # per-iteration cost
+    np.testing.assert_allclose(gh[:, 1:], oh[:, 1:], rtol=1e-7, atol=1e-12)  # feasibility / violations (values ~1e-5)
+    gt = s.get_trace(256)[0, :gi["iter"]]
+    assert np.array_equal(gt[:, 6:10], ot[:, 6:10])                     # reg iters, ls iters, success, accepted eps: exact
+    np.testing.assert_allclose(gt[:, 2:4], ot[:, 2:4], rtol=1e-8)       # expected cost change
+    gsol = s.get_solution()[0]
+    gp, op = cm.unpack_solution(hkd_problem.deck, gsol), cm.unpack_solution(hkd_problem.deck, osol)
+    for pg, po in zip(gp, op):
+        for name in ("Xbar", "Ubar", "K", "dU", "Quu", "Qux", "G"):
+            assert relerr(pg[name], po[name]) < (RTOL if name in ("Xbar", "Ubar") else 1e-7), name
+    g = np.load(os.path.join(REPO, "tests/golden/hkd_trot_nominal.npz"))
+    assert [gi[k] for k in COUNTS] == list(g["counts"])
+    np.testing.assert_allclose(gh[:, 0], g["hist"][:, 0], rtol=RTOL)
+    assert abs(gi["cost"] - g["final"][0]) <= RTOL * abs(g["final"][0])
+
+
+def test_one_iteration_per_knot_parity(cm, hkd_problem, hkd_options):
+    """LQ data and every backward-sweep / linear-rollout product of the first iteration, per knot."""
+    import copy
+    from cafe_mpc_b200 import workload
+    opt = copy.copy(hkd_options)
+    opt.max_DDP_iter = 1; opt.max_AL_iter = 1; opt.cost_thresh = 1e30; opt.dynamics_feas_thresh = 1e30  # stop before the line search
+    x0 = workload.hkd_batch(hkd_problem, 4)
+    s = solve_gpu(cm, hkd_problem, opt, x0)
+    for b in (0, 3):
+        oracle_solve(hkd_problem.deck, opt, x0[b])
+        for ph in range(3):
+            for name in ("X", "U", "Defect", "l", "lx", "lu", "lxx", "luu", "A", "B", "Phix", "Phixx"):
+                assert relerr(s.debug_get(name, ph, b), oracle_get(name, ph)) < 1e-13, (name, ph)
+            for name in ("Quu", "Qux", "Qu", "K", "dU", "G", "dX"):
+                assert relerr(s.debug_get(name, ph, b), oracle_get(name, ph)) < 1e-11, (name, ph)
+        for ph in range(2):
+            assert relerr(s.debug_get("Px", ph, b), oracle_get("Px", ph)) < 1e-14
+
+
+def test_perturbed_batch_counts_bit_exact(cm, hkd_problem, hkd_options):
+    from cafe_mpc_b200 import workload
+    B = 48
+    x0 = workload.hkd_batch(hkd_problem, B)
+    s = solve_gpu(cm, hkd_problem, hkd_options, x0)
+    info = s.get_solver_info()
+    hist = s.get_history(256)
+    sol = s.get_solution()
+    for b in range(B):
+        oi, oh, ot, osol = oracle_solve(hkd_problem.deck, hkd_options, x0[b])
+        assert [info[b][k] for k in COUNTS] == [oi[k] for k in COUNTS], b
+        np.testing.assert_allclose(hist[b, :oi["n_hist"], 0], oh[:, 0], rtol=RTOL)
+        gp, op = cm.unpack_solution(hkd_problem.deck, sol[b]), cm.unpack_solution(hkd_problem.deck, osol)
+        for pg, po in zip(gp, op):
+            assert relerr(pg["Xbar"], po["Xbar"]) < RTOL and relerr(pg["Ubar"], po["Ubar"]) < RTOL
+    g = np.load(os.path.join(REPO, "tests/golden/hkd_trot_batch8.npz"))
+    for b in range(8):
+        assert [info[b][k] for k in COUNTS] == [int(v) for v in g["rows"][b, :6]]
+        assert abs(info[b]["cost"] - g["rows"][b, 6]) <= RTOL * abs(g["rows"][b, 6])
+
+
+@pytest.mark.parametrize("B", [1, 33])
+def test_ragged_batch_sizes_and_batch_position_invariance(cm, hkd_problem, hkd_options, B):
+    """A problem's result must not depend on the batch size or on its slot in the batch."""
+    from cafe_mpc_b200 import workload
+    x0 = workload.hkd_batch(hkd_problem, 40)
+    ref = solve_gpu(cm, hkd_problem, hkd_options, x0[:40])
+    rs = ref.get_solution()
+    perm = np.arange(40)[::-1][:B].copy()
+    s = solve_gpu(cm, hkd_problem, hkd_options, x0[perm])
+    ss = s.get_solution()
+    ri, si = ref.get_solver_info(), s.get_solver_info()
+    for j, b in enumerate(perm):
+        assert [si[j][k] for k in COUNTS] == [ri[b][k] for k in COUNTS]
+        assert np.array_equal(ss[j], rs[b])  # bitwise: same instruction stream per problem
+
+
+def test_outer_iteration_cap_and_history_edges(cm, hkd_problem, hkd_options):
+    import copy
+    from cafe_mpc_b200 import workload
+    x0 = workload.hkd_batch(hkd_problem, 4)
+    for al, ddp in ((1, 1), (1, 3), (2, 2)):
+        opt = copy.copy(hkd_options); opt.max_AL_iter = al; opt.max_DDP_iter = ddp
+        s = solve_gpu(cm, hkd_problem, opt, x0)
+        info = s.get_solver_info()
+        for b in range(4):
+            oi, oh, _, _ = oracle_solve(hkd_problem.deck, opt, x0[b])
+            assert [info[b][k] for k in COUNTS] == [oi[k] for k in COUNTS]
+            assert info[b]["iter"] <= al * ddp
+
+
+def test_full_size_batch_properties(cm, hkd_problem, hkd_options):
+    """BASELINE-size batch (1024): determinism, convergence flags, and the value-function identity
+    dV = -Qu^T dU >= 0 that every accepted backward sweep must satisfy."""
+    from cafe_mpc_b200 import workload
+    B = 1024
+    x0 = workload.hkd_batch(hkd_problem, B)
+    s = solve_gpu(cm, hkd_problem, hkd_options, x0)
+    i1 = s.get_solver_info()
+    c1 = s.get_commands(8)
+    s.solve(hkd_options)
+    i2 = s.get_solver_info()
+    c2 = s.get_commands(8)
+    assert np.array_equal(c1, c2) and i1 == i2  # run-to-run bitwise determinism
+    st = np.array([i["status"] for i in i1])
+    assert np.all(st == 0)
+    feas = np.array([i["feas"] for i in i1])
+    it = np.array([i["iter"] for i in i1])
+    assert np.all(feas <= hkd_options.dynamics_feas_thresh) or np.all(it == hkd_options.max_AL_iter * hkd_options.max_DDP_iter)
+    assert np.all(it >= 1) and np.all(it <= 50)
+    # spot-check 6 problems of the big batch against the oracle
+    for b in (0, 1, 511, 512, 1000, 1023):
+        oi, _, _, _ = oracle_solve(hkd_problem.deck, hkd_options, x0[b])
+        assert [i1[b][k] for k in COUNTS] == [oi[k] for k in COUNTS]
+        assert abs(i1[b]["cost"] - oi["cost"]) <= 1e-8 * abs(oi["cost"])
+
+
+def test_unsupported_options_fail_loudly(cm, hkd_problem, hkd_options):
+    import copy
+    from cafe_mpc_b200 import workload
+    from cafe_mpc_b200.lib import CafeError
+    x0 = workload.hkd_batch(hkd_problem, 2)
+    s = cm.MultiPhaseDDP(hkd_problem, 0, 2)
+    s.set_initial_condition(x0)
+    opt = copy.copy(hkd_options); opt.MS = 0
+    with pytest.raises(CafeError):
+        s.solve(opt)
+    s.set_initial_condition(workload.hkd_batch(hkd_problem, 3))
+    with pytest.raises(CafeError):  # batch larger than the handle's capacity
+        s.solve(hkd_options)

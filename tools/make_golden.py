@@ -1,0 +1,23 @@
+"""Generates tests/golden/*.npz from the CPU oracle (run in this container; commit the outputs)."""
+import os, sys
+import numpy as np
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tests"))
+import cafe_mpc_b200 as cm
+from cafe_mpc_b200 import workload
+from oracle_bindings import oracle_solve
+
+prob = cm.HKDProblem(os.path.join(cm.api.DATA, "reference/trot_heuristic/quad_reference.csv"))
+opt = cm.load_hsddp_setting(os.path.join(cm.api.DATA, "settings/hkd/ddp_setting.info"))
+x0 = workload.hkd_batch(prob, 8)
+info, hist, trace, sol = oracle_solve(prob.deck, opt, x0[0])
+counts = np.array([info[k] for k in ("status", "iter", "ls_iter_total", "reg_iter_total", "outer_iter", "n_hist")])
+np.savez_compressed(os.path.join(R, "tests/golden/hkd_trot_nominal.npz"), x0=x0[0], counts=counts, hist=hist, trace=trace, sol=sol,
+                    final=np.array([info["cost"], info["feas"], info["max_tconstr"], info["max_pconstr"]]))
+# small perturbed batch: counters and final costs only
+rows = []
+for b in range(8):
+    i, h, t, s = oracle_solve(prob.deck, opt, x0[b])
+    rows.append([i[k] for k in ("status", "iter", "ls_iter_total", "reg_iter_total", "outer_iter", "n_hist")] + [i["cost"], i["feas"]])
+np.savez_compressed(os.path.join(R, "tests/golden/hkd_trot_batch8.npz"), x0=x0, rows=np.array(rows))
+print(counts, info)
