@@ -150,6 +150,17 @@ class MultiPhaseDDP:
             check(int(n))
         return buf[:n].copy()
 
+    def command_size(self, n_gain_knots=8):
+        return lib.cafe_command_size(self.problem.deck, n_gain_knots)
+
+    def get_commands_device(self, n_gain_knots, dev_ptr):
+        check(lib.cafe_gpu_get_commands_device(self._h, n_gain_knots, C.c_void_p(dev_ptr)))
+
+    def solve_ms(self):
+        v = C.c_double()
+        check(lib.cafe_gpu_get_solve_ms(self._h, C.byref(v)))
+        return v.value
+
     def get_timing(self):
         ms = (C.c_double * CAFE_NKERNELS)()
         n = (C.c_long * CAFE_NKERNELS)()

@@ -48,7 +48,8 @@ struct CafeHandle {
   int bwd_variant = 0;  // 0: HKD deck (24,24,0)   1: MHPC deck (36,24->12,12)
   size_t bwd_smem = 0;
   int bwd_pb = 4;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evs = nullptr, eve = nullptr;
+  double total_ms = 0;
 };
 
 namespace {
@@ -261,6 +262,8 @@ extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, 
   CUDA_OK(cudaStreamCreate(&H->stream));
   CUDA_OK(cudaEventCreate(&H->ev0));
   CUDA_OK(cudaEventCreate(&H->ev1));
+  CUDA_OK(cudaEventCreate(&H->evs));
+  CUDA_OK(cudaEventCreate(&H->eve));
   H->max_segs = 9 * CAFE_MAX_PHASES;
   CUDA_OK(cudaMalloc(&H->d_segs, H->max_segs * sizeof(PackSeg)));
   H->bwd_variant = 0; H->bwd_pb = 4;
@@ -278,6 +281,8 @@ extern "C" int cafe_gpu_destroy(CafeHandle* H) {
   if (H->stream) cudaStreamDestroy(H->stream);
   if (H->ev0) cudaEventDestroy(H->ev0);
   if (H->ev1) cudaEventDestroy(H->ev1);
+  if (H->evs) cudaEventDestroy(H->evs);
+  if (H->eve) cudaEventDestroy(H->eve);
   delete H;
   return 0;
 }
@@ -297,6 +302,7 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
   for (int i = 0; i < CAFE_NKERNELS; ++i) { H->ms[i] = 0; H->launches[i] = 0; }
   H->ticks = 0;
   cudaStream_t st = H->stream;
+  CUDA_OK(cudaEventRecord(H->evs, st));
   CUDA_OK(cudaMemcpyAsync(H->dS, &S, sizeof(SolverDev), cudaMemcpyHostToDevice, st));
   CUDA_OK(cudaMemsetAsync(H->arena, 0, H->zero_bytes, st));
   const int n0 = S.ph[0].n;
@@ -333,8 +339,10 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
     timed(H, 1, [&] { cafe_dev::k_select<<<(B + 127) / 128, 128, 0, st>>>(H->dS, 1); });
     timed(H, 2, [&] { cafe_dev::k_accept<<<g_knots, tpb, 0, st>>>(H->dS); });
   }
+  CUDA_OK(cudaEventRecord(H->eve, st));
   CUDA_OK(cudaStreamSynchronize(st));
   CUDA_OK(cudaGetLastError());
+  { float ms = 0; cudaEventElapsedTime(&ms, H->evs, H->eve); H->total_ms = ms; }
   return 0;
 }
 
@@ -354,6 +362,7 @@ extern "C" int cafe_gpu_get_timing(CafeHandle* H, double ms[CAFE_NKERNELS], long
   if (ticks) *ticks = H->ticks;
   return 0;
 }
+extern "C" int cafe_gpu_get_solve_ms(CafeHandle* H, double* ms) { if (!H || !ms) return CAFE_ERR_ARG; *ms = H->total_ms; return 0; }
 
 template <class T>
 static int fetch(CafeHandle* H, const T* dev, size_t count, std::vector<T>& host) {
@@ -404,8 +413,17 @@ extern "C" int cafe_gpu_get_trace(CafeHandle* H, double* trace, int cap) {
   return get_table(H, H->S.c.trace, 12, trace, cap);
 }
 
-static int run_pack(CafeHandle* H, const std::vector<PackSeg>& segs, long rec_size, int b0, int nb, double* out) {
+static int run_pack(CafeHandle* H, const std::vector<PackSeg>& segs, long rec_size, int b0, int nb, double* out, double* dev_out = nullptr) {
   const size_t need = (size_t)nb * rec_size * sizeof(double);
+  if (dev_out) {  // pack straight into a caller-owned device buffer (e.g. the NCCL gather source)
+    if ((int)segs.size() > H->max_segs) { cafe::set_last_error("too many pack segments"); return CAFE_ERR_ARG; }
+    CUDA_OK(cudaMemcpyAsync(H->d_segs, segs.data(), segs.size() * sizeof(PackSeg), cudaMemcpyHostToDevice, H->stream));
+    dim3 grid(592, (unsigned)segs.size());
+    k_pack<<<grid, 256, 0, H->stream>>>(H->d_segs, (int)segs.size(), H->ldb, b0, nb, rec_size, dev_out);
+    CUDA_OK(cudaStreamSynchronize(H->stream));
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   if (need > H->pack_bytes) {
     cudaFree(H->d_pack); H->d_pack = nullptr; H->pack_bytes = 0;
     CUDA_OK(cudaMalloc(&H->d_pack, need));
@@ -436,8 +454,16 @@ extern "C" int cafe_gpu_get_solution(CafeHandle* H, int b0, int nb, double* sol)
   return run_pack(H, segs, off, b0, nb, sol);
 }
 
+static int commands_impl(CafeHandle* H, int n_gain_knots, double* cmd, double* dev_out);
 extern "C" int cafe_gpu_get_commands(CafeHandle* H, int n_gain_knots, double* cmd) {
   if (!H || !cmd || n_gain_knots < 0) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
+  return commands_impl(H, n_gain_knots, cmd, nullptr);
+}
+extern "C" int cafe_gpu_get_commands_device(CafeHandle* H, int n_gain_knots, double* cmd_dev) {
+  if (!H || !cmd_dev || n_gain_knots < 0) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
+  return commands_impl(H, n_gain_knots, nullptr, cmd_dev);
+}
+static int commands_impl(CafeHandle* H, int n_gain_knots, double* cmd, double* dev_out) {
   CUDA_OK(cudaSetDevice(H->device));
   std::vector<PackSeg> segs;
   long off = 0;
@@ -451,7 +477,7 @@ extern "C" int cafe_gpu_get_commands(CafeHandle* H, int n_gain_knots, double* cm
     add(ph.K, g, m * n); add(ph.Qu, g, m); add(ph.Quu, g, m * m); add(ph.Qux, g, m * n);
     left -= g;
   }
-  return run_pack(H, segs, off, 0, H->B, cmd);
+  return run_pack(H, segs, off, 0, H->B, cmd, dev_out);
 }
 
 extern "C" long cafe_gpu_debug_get(CafeHandle* H, const char* name, int phase, int b, double* out) {

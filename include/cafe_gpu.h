@@ -80,9 +80,13 @@ int cafe_gpu_get_history(CafeHandle* h, double* hist, int hist_cap);
 int cafe_gpu_get_trace(CafeHandle* h, double* trace, int trace_cap);
 int cafe_gpu_get_solution(CafeHandle* h, int b0, int nb, double* sol /*[nb][cafe_solution_size]*/);
 int cafe_gpu_get_commands(CafeHandle* h, int n_gain_knots, double* cmd /*[B][cafe_command_size]*/);
+/* same, packed into a caller-owned DEVICE buffer (source of the final NCCL gather in multi-GPU runs) */
+int cafe_gpu_get_commands_device(CafeHandle* h, int n_gain_knots, double* cmd_dev);
 /* device-time breakdown of the last solve, ms per kernel family, and launch counts */
 #define CAFE_NKERNELS 6 /* 0 roll 1 select 2 accept 3 lq 4 bwd 5 misc */
 int cafe_gpu_get_timing(CafeHandle* h, double ms[CAFE_NKERNELS], long launches[CAFE_NKERNELS], int* ticks);
+/* device time (CUDA events on the solver's stream) of the last cafe_gpu_solve_batch*, in ms */
+int cafe_gpu_get_solve_ms(CafeHandle* h, double* ms);
 /* enable per-kernel CUDA-event timing (costs a few us per launch) */
 int cafe_gpu_set_profiling(CafeHandle* h, int on);
 
