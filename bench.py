@@ -66,8 +66,8 @@ def _cpu_worker(task):
     import cafe_mpc_b200 as cm
     from oracle_bindings import oracle_solve
     x0s, = task
-    prob = cm.HKDProblem(os.path.join(REPO, "data/reference/trot_heuristic/quad_reference.csv"))
-    opt = cm.load_hsddp_setting(os.path.join(REPO, "data/settings/hkd/ddp_setting.info"))
+    prob = cm.HKDProblem(os.path.join(REPO, "data/Reference/Data/trot/heuristic/quad_reference.csv"))
+    opt = cm.load_hsddp_setting(os.path.join(REPO, "data/HKDMPC/settings/ddp_setting.info"))
     t = time.perf_counter()
     for x in x0s:
         oracle_solve(prob.deck, opt, x)
@@ -95,7 +95,7 @@ def run_reference(args):
     import cafe_mpc_b200 as cm
     from cafe_mpc_b200 import workload
     cores = len(os.sched_getaffinity(0))
-    prob = cm.HKDProblem(os.path.join(REPO, "data/reference/trot_heuristic/quad_reference.csv"))
+    prob = cm.HKDProblem(os.path.join(REPO, "data/Reference/Data/trot/heuristic/quad_reference.csv"))
     per_core = args.cpu_per_core
     x0 = workload.hkd_batch(prob, min(args.batch, cores * per_core))
     vals = []
@@ -142,8 +142,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B = args.batch
     Bg = B * world
-    prob = cm.HKDProblem(os.path.join(REPO, "data/reference/trot_heuristic/quad_reference.csv"))
-    opt = cm.load_hsddp_setting(os.path.join(REPO, "data/settings/hkd/ddp_setting.info"))
+    prob = cm.HKDProblem(os.path.join(REPO, "data/Reference/Data/trot/heuristic/quad_reference.csv"))
+    opt = cm.load_hsddp_setting(os.path.join(REPO, "data/HKDMPC/settings/ddp_setting.info"))
     x0_all = workload.hkd_batch(prob, Bg) if Bg <= 8192 else np.tile(workload.hkd_batch(prob, 8192), ((Bg + 8191) // 8192, 1))[:Bg]
     lo, hi = cdist.shard_range(Bg, world, rank)
     x0 = np.ascontiguousarray(x0_all[lo:hi])

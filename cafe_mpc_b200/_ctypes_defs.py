@@ -29,13 +29,14 @@ class Phase(C.Structure):
         ("w_tdvel", C.c_double * 3),
         ("reb_grf", RebParam), ("reb_torque", RebParam), ("reb_joint", RebParam), ("reb_minheight", RebParam),
         ("al_td", AlParam), ("mu", C.c_double), ("ground_height", C.c_double),
+        ("h_min", C.c_double), ("torque_limit", C.c_double), ("joint_lb", C.c_double * 3), ("joint_ub", C.c_double * 3),
     ]
 
 
 class Deck(C.Structure):
     _fields_ = [
         ("n_phases", C.c_int), ("n_records", C.c_int), ("phase", Phase * CAFE_MAX_PHASES),
-        ("ref", C.POINTER(C.c_double)), ("BG_alpha", C.c_double),
+        ("ref", C.POINTER(C.c_double)), ("BG_alpha", C.c_double), ("hip_yaw", C.c_double),
     ]
 
 

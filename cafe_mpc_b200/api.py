@@ -49,7 +49,7 @@ class HKDProblem(_DeckOwner):
     def __init__(self, reference_csv, constraint_params=None, plan_duration=0.6, time_step=0.01,
                  nsteps_between_mpc=2, k0=0):
         super().__init__()
-        constraint_params = constraint_params or os.path.join(DATA, "settings/hkd/constraint_params.info")
+        constraint_params = constraint_params or os.path.join(DATA, "HKDMPC/settings/constraint_params.info")
         check(lib.cafe_deck_build_hkd(reference_csv.encode(), constraint_params.encode(), plan_duration, time_step,
                                       nsteps_between_mpc, k0, C.byref(self._h)))
 
@@ -69,8 +69,8 @@ class MHPCProblem(_DeckOwner):
 
     def __init__(self, reference_csv, mhpc_config=None, settings_root=None, k0=0):
         super().__init__()
-        mhpc_config = mhpc_config or os.path.join(DATA, "settings/mhpc/mhpc_config.info")
-        settings_root = settings_root or os.path.join(DATA, "settings")
+        mhpc_config = mhpc_config or os.path.join(DATA, "MHPC/settings/mhpc_config.info")
+        settings_root = settings_root or DATA  # plays the role of the reference's "../"
         check(lib.cafe_deck_build_mhpc(reference_csv.encode(), mhpc_config.encode(), settings_root.encode(), k0,
                                        C.byref(self._h)))
 

@@ -1,19 +1,26 @@
 // mhpc_problem.cpp — phase deck for the MHPC (whole-body + single-rigid-body) problem; host-side mirror of
-// MHPCProblem<T>::initialization (/root/reference/MHPC/MHPC-Trajopt/MHPCProblem.cpp:13-250).
+//   MHPCProblem<T>::initialization / prepare_initialization / initialize_parameters / initialize_multiPhaseProblem
+//   / create_problem_one_phase / update_resetmap / add_tconstr_one_phase
+//                                   /root/reference/MHPC/MHPC-Trajopt/MHPCProblem.cpp:13-250, :403-601
+//   loadMHPCConfig                  MHPCProblem.h:67-83      loadCostWeights   MHPCCostUtil.h:10-143
+//   load_reb_params / load_al_params   HSDDPSolver/header/ConstraintsBase.h:88-111
+//   WBReference / SRBReference      MHPC/MHPC-Trajopt/MHPCReference.cpp:10-76
+#include <cmath>
+#include <cstring>
 #include <stdexcept>
 #include "info_reader.h"
 #include "problem_builders.h"
 
 namespace cafe {
 
-void loadMHPCConfig(const std::string& fname, MHPCConfig& c) {  // MHPCProblem.h:67-83
+void loadMHPCConfig(const std::string& fname, MHPCConfig& c) {
   InfoFile pt(fname);
-  c.plan_dur_wb = (float)pt.num("config.plan_dur_wb");
+  c.plan_dur_wb = (float)pt.num("config.plan_dur_wb");  // the config fields are floats (MHPCProblem.h:45-57)
   c.plan_dur_srb = (float)pt.num("config.plan_dur_srb");
   c.dt_mpc = (float)pt.num("config.dt_mpc");
   c.dt_wb = (float)pt.num("config.dt_wb");
   c.dt_srb = (float)pt.num("config.dt_srb");
-  c.BG_alpha = pt.num("config.BG_alpha");
+  c.BG_alpha = (double)(float)pt.num("config.BG_alpha");
   c.num_threads = pt.integer("config.nthreads");
   c.referenceFileName = pt.str("config.referenceFile");
   c.costFileName = pt.str("config.costFile");
@@ -24,9 +31,152 @@ void MHPCProblem::set_problem_data(QuadReference* quad_ref, const MHPCConfig& co
   quad_reference = quad_ref;
   pconfig = config;
   root = settings_root;
-  plan_dur_all = config.plan_dur_wb + config.plan_dur_srb;
+  plan_dur_all = config.plan_dur_wb + config.plan_dur_srb;  // MHPCProblem.h:209
 }
 
-void MHPCProblem::initialization(DeckStorage&) { throw std::runtime_error("MHPC deck builder not implemented yet"); }
+static CafeRebParam reb_params(const InfoFile& pt, const std::string& t) { return CafeRebParam{pt.num(t + "_ReB.delta"), pt.num(t + "_ReB.delta_min"), pt.num(t + "_ReB.eps")}; }
+
+static void fill_wb_record(double* r, const QuadAugmentedState& s) {  // WBReference::get_reference_at_t
+  for (int i = 0; i < 6; ++i) { r[CAFE_REF_XR + i] = s.body_state[i]; r[CAFE_REF_XR + 18 + i] = s.body_state[6 + i]; }
+  for (int i = 0; i < 12; ++i) {
+    r[CAFE_REF_XR + 6 + i] = s.qJ[i];
+    r[CAFE_REF_XR + 24 + i] = s.qJd[i];
+    r[CAFE_REF_UR + i] = s.torque[i];
+    r[CAFE_REF_YR + i] = s.grf[i];
+    r[CAFE_REF_PF + i] = s.foot_placements[i];
+    r[CAFE_REF_VF + i] = s.foot_velocities[i];
+    r[CAFE_REF_QJ + i] = s.qJ[i];
+  }
+  for (int i = 0; i < 3; ++i) r[CAFE_REF_PCOM + i] = s.body_state[i];
+  for (int i = 0; i < 4; ++i) r[CAFE_REF_CONTACT + i] = (double)s.contact[i];
+}
+static void fill_srb_record(double* r, const QuadAugmentedState& s) {  // SRBReference::get_reference_at_t + MHPCFootStep
+  for (int i = 0; i < 12; ++i) { r[CAFE_REF_XR + i] = s.body_state[i]; r[CAFE_REF_UR + i] = s.grf[i]; r[CAFE_REF_PF + i] = s.foot_placements[i]; r[CAFE_REF_VF + i] = s.foot_velocities[i]; r[CAFE_REF_QJ + i] = s.qJ[i]; }
+  for (int i = 0; i < 3; ++i) r[CAFE_REF_PCOM + i] = s.body_state[i];
+  for (int i = 0; i < 4; ++i) r[CAFE_REF_CONTACT + i] = (double)s.contact[i];
+}
+
+void MHPCProblem::initialization(DeckStorage& out) {
+  quad_reference->initialize(plan_dur_all);
+  CafeDeck& deck = out.deck;
+  std::memset(&deck, 0, sizeof(deck));
+  out.phase_start_times.clear();
+  out.phase_end_times.clear();
+  if (approx_leq_scalar(plan_dur_all, .0)) throw std::runtime_error("total planning horizon cannot be zero");
+
+  /* ---- prepare_initialization: cut the WB phases along the reference contact schedule (MHPCProblem.cpp:93-136) */
+  int n_wb = 0;
+  if (pconfig.plan_dur_wb > 1e-5) {
+    float start = 0.0f, end = 0.0f, t = 0.0f;
+    int contact_prev[4], contact_cur[4];
+    quad_reference->get_contact_at_t(contact_prev, t);
+    while (approx_leq_scalar(t, pconfig.plan_dur_wb)) {
+      quad_reference->get_contact_at_t(contact_cur, t);
+      bool change = false;
+      for (int l = 0; l < 4; ++l) change = change || (contact_cur[l] != contact_prev[l]);
+      if (change || approx_eq_scalar(t, pconfig.plan_dur_wb)) {
+        end = t;
+        if (n_wb >= CAFE_MAX_PHASES - 1) throw std::runtime_error("too many phases");
+        CafePhase& ph = deck.phase[n_wb];
+        ph.model = CAFE_MODEL_WB;
+        ph.horizon = (int)std::round((end - start) / pconfig.dt_wb);
+        for (int l = 0; l < 4; ++l) ph.contact[l] = contact_prev[l];
+        out.phase_start_times.push_back(start);
+        out.phase_end_times.push_back(end);
+        n_wb++;
+        for (int l = 0; l < 4; ++l) contact_prev[l] = contact_cur[l];
+        start = end;
+      }
+      t += pconfig.dt_wb;
+    }
+  }
+  int n_srb = 0, srb_h = 0;
+  float srb_start = 0;
+  if (pconfig.plan_dur_srb > 1e-5) {
+    srb_start = pconfig.plan_dur_wb;
+    srb_h = (int)std::round(pconfig.plan_dur_srb / pconfig.dt_srb);
+    n_srb = srb_h > 0 ? 1 : 0;
+  }
+  deck.n_phases = n_wb + n_srb;
+  deck.BG_alpha = pconfig.BG_alpha;
+  deck.hip_yaw = 3.1415;  // urdf/mini_cheetah_simple_correctedInertia.urdf:79 (rpy="0.0 0.0 3.1415")
+
+  /* ---- initialize_parameters (MHPCProblem.cpp:149-171) */
+  InfoFile cpt(root + "/" + pconfig.constraintParamFileName);
+  const CafeRebParam grf = reb_params(cpt, "GRF"), torque = reb_params(cpt, "Torque"), joint = reb_params(cpt, "Joint"), minh = reb_params(cpt, "MinHeight");
+  CafeAlParam td{};
+  td.sigma = cpt.num("TD_AL.sigma"); td.lambda = cpt.num("TD_AL.lambda"); td.sigma_max = cpt.num("TD_AL.sigma_max");
+  JsonWeights cw(root + "/" + pconfig.costFileName);
+
+  int rec = 0;
+  for (int i = 0; i < n_wb; ++i) { deck.phase[i].knot_offset = rec; rec += deck.phase[i].horizon + 1; }
+  if (n_srb) { CafePhase& s = deck.phase[n_wb]; s.model = CAFE_MODEL_SRB; s.horizon = srb_h; s.knot_offset = rec; rec += srb_h + 1; }
+  deck.n_records = rec;
+  out.ref.assign((size_t)rec * CAFE_REF_W, 0.0);
+
+  /* ---- WB phases (MHPCProblem.cpp:176-217, :403-601) */
+  for (int i = 0; i < n_wb; ++i) {
+    CafePhase& ph = deck.phase[i];
+    ph.dt = (double)pconfig.dt_wb;
+    ph.t_offset = out.phase_start_times[i] - out.phase_start_times[0];
+    ph.has_reset = 1;
+    if (i < n_wb - 1) for (int l = 0; l < 4; ++l) ph.next_contact[l] = deck.phase[i + 1].contact[l];
+    else quad_reference->get_contact_at_t(ph.next_contact, pconfig.plan_dur_wb + pconfig.dt_mpc);
+    ph.next_model = (i < n_wb - 1) ? CAFE_MODEL_WB : (n_srb ? CAFE_MODEL_SRB : -1);
+    ph.n_td = 0;
+    for (int l = 0; l < 4; ++l) if (ph.contact[l] == 0 && ph.next_contact[l] == 1) ph.td_foot[ph.n_td++] = l;
+    /* weights: [qw_qB, qw_qJ x4, qw_vB, qw_vJ x4 | rw x12 | qfw...] (MHPCCostUtil.h:22-80) */
+    auto fill = [&](double* dst, const char* qB, const char* qJ, const char* vB, const char* vJ) {
+      const auto &a = cw.vec(std::string("WB_Tracking_Cost.") + qB), &b = cw.vec(std::string("WB_Tracking_Cost.") + qJ),
+                 &c = cw.vec(std::string("WB_Tracking_Cost.") + vB), &d = cw.vec(std::string("WB_Tracking_Cost.") + vJ);
+      for (int j = 0; j < 6; ++j) { dst[j] = a.at(j); dst[18 + j] = c.at(j); }
+      for (int l = 0; l < 4; ++l) for (int j = 0; j < 3; ++j) { dst[6 + 3 * l + j] = b.at(j); dst[24 + 3 * l + j] = d.at(j); }
+    };
+    fill(ph.q, "qw_qB", "qw_qJ", "qw_vB", "qw_vJ");
+    fill(ph.qf, "qfw_qB", "qfw_qJ", "qfw_vB", "qfw_vJ");
+    for (int j = 0; j < 12; ++j) ph.r[j] = cw.num("WB_Tracking_Cost.rw");
+    for (int j = 0; j < 3; ++j) {
+      ph.w_footreg[j] = cw.vec("WB_FootPlace_Reg.qw_per_foot").at(j);
+      ph.w_swingpos[j] = cw.vec("Swing_Pos_Tracking.qw_per_foot").at(j);
+      ph.w_swingvel[j] = cw.vec("Swing_Vel_Tracking.qw_per_foot").at(j);
+    }
+    ph.w_tdvel[0] = 0; ph.w_tdvel[1] = 0; ph.w_tdvel[2] = 1.0;  // TDVelocityPenalty::qFoot (MHPCCost.h:196)
+    ph.reb_grf = grf; ph.reb_torque = torque; ph.reb_joint = joint; ph.reb_minheight = minh; ph.al_td = td;
+    ph.mu = 0.6;              // MHPCConstraint.cpp:11
+    ph.ground_height = 0;
+    ph.h_min = 0.20;          // MHPCConstraint.h:148
+    ph.torque_limit = 17.0;   // MHPCConstraint.cpp:77
+    const double lb[3] = {-1.3, -5.0, -M_PI}, ub[3] = {1.3, 5.0, M_PI};  // MHPCConstraint.cpp:172-173
+    for (int j = 0; j < 3; ++j) { ph.joint_lb[j] = lb[j]; ph.joint_ub[j] = ub[j]; }
+    for (int k = 0; k <= ph.horizon; ++k) {
+      float t_cost = (float)((double)ph.t_offset + (double)k * ph.dt);
+      float t_init = out.phase_start_times[i] + k * pconfig.dt_wb;
+      if (quad_reference->index_at_t(t_cost) != quad_reference->index_at_t(t_init)) throw std::runtime_error("reference index mismatch (WB)");
+      fill_wb_record(&out.ref[(size_t)(ph.knot_offset + k) * CAFE_REF_W], *quad_reference->get_a_reference_ptr_at_t(t_cost));
+    }
+  }
+  /* ---- SRB phase (MHPCProblem.cpp:219-249, :487-521) */
+  if (n_srb) {
+    CafePhase& ph = deck.phase[n_wb];
+    ph.dt = (double)pconfig.dt_srb;
+    ph.t_offset = srb_start;
+    ph.has_reset = 0;
+    ph.next_model = -1;
+    ph.n_td = 0;
+    for (int l = 0; l < 4; ++l) { ph.contact[l] = 0; ph.next_contact[l] = 0; }
+    const auto &a = cw.vec("SRB_Tracking_Cost.qw_qB"), &c = cw.vec("SRB_Tracking_Cost.qw_vB"), &af = cw.vec("SRB_Tracking_Cost.qfw_qB"), &cf = cw.vec("SRB_Tracking_Cost.qfw_vB");
+    for (int j = 0; j < 6; ++j) { ph.q[j] = a.at(j); ph.q[6 + j] = c.at(j); ph.qf[j] = af.at(j); ph.qf[6 + j] = cf.at(j); }
+    for (int j = 0; j < 12; ++j) ph.r[j] = cw.num("SRB_Tracking_Cost.rw");
+    ph.reb_minheight = minh;
+    ph.h_min = 0.18;  // MHPCConstraint.h:199
+    for (int k = 0; k <= ph.horizon; ++k) {
+      float t_cost = (float)((double)ph.t_offset + (double)k * ph.dt);
+      float t_init = srb_start + k * pconfig.dt_srb;
+      if (quad_reference->index_at_t(t_cost) != quad_reference->index_at_t(t_init)) throw std::runtime_error("reference index mismatch (SRB)");
+      fill_srb_record(&out.ref[(size_t)(ph.knot_offset + k) * CAFE_REF_W], *quad_reference->get_a_reference_ptr_at_t(t_cost));
+    }
+  }
+  deck.ref = out.ref.data();
+}
 
 }  // namespace cafe

@@ -77,6 +77,9 @@ typedef struct {
   CafeAlParam al_td;
   double mu;            /* friction coefficient (HKD 0.7, WB 0.6)                          */
   double ground_height; /* touchdown ground height (0)                                     */
+  double h_min;         /* minimum body height (WB 0.20, SRB 0.18; MHPCConstraint.h:148,199) */
+  double torque_limit;  /* WB joint torque bound (17; MHPCConstraint.cpp:77)               */
+  double joint_lb[3], joint_ub[3]; /* WB joint limits per leg (MHPCConstraint.cpp:172-175) */
 } CafePhase;
 
 typedef struct {
@@ -85,6 +88,9 @@ typedef struct {
   CafePhase phase[CAFE_MAX_PHASES];
   const double* ref; /* [n_records][CAFE_REF_W], owned by whoever built the deck           */
   double BG_alpha;   /* WB Baumgarte gain (mhpc_config.info:8)                              */
+  double hip_yaw;    /* yaw of the hip-pitch joint placement as loaded from the URDF (3.1415,
+                        urdf/mini_cheetah_simple_correctedInertia.urdf:79); the kinematic partials that
+                        replace the reference's CasADi code always use pi */
 } CafeDeck;
 
 /* Mirror of HSDDP_OPTION, field for field

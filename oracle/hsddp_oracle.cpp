@@ -328,7 +328,7 @@ void Solver::setup(const CafeDeck* deck) {
     std::unique_ptr<Phase> P;
     if (ph->model == CAFE_MODEL_HKD) P = make_hkd_phase();
     else if (ph->model == CAFE_MODEL_SRB) P = make_srb_phase();
-    else P = make_wb_phase(deck->BG_alpha);
+    else P = make_wb_phase(deck->BG_alpha, deck->hip_yaw);
     if (!P) throw std::runtime_error("oracle: model not available");
     P->allocate(ph, deck->ref + (size_t)ph->knot_offset * CAFE_REF_W);
     P->build_model();

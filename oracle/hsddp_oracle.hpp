@@ -163,7 +163,7 @@ class Phase {
 
 std::unique_ptr<Phase> make_hkd_phase();
 std::unique_ptr<Phase> make_srb_phase();
-std::unique_ptr<Phase> make_wb_phase(double BG_alpha);
+std::unique_ptr<Phase> make_wb_phase(double BG_alpha, double hip_yaw);
 
 /* MultiPhaseDDP */
 class Solver {

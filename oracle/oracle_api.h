@@ -32,6 +32,11 @@ int cafe_oracle_solve(const CafeDeck* deck, const CafeOptions* opt, const double
  * Quu Qux H lx lu ly lxx luu lyy l Phix Phixx Px). Returns the number of doubles written or -1. */
 long cafe_oracle_get(const char* name, int phase, double* out);
 
+/* Whole-body continuous-time KKT contact dynamics (WBM::dynamics_continuousTime), for the known-answer test
+ * of the reference (test/testKKTDynamics.cpp:95-121). */
+int cafe_oracle_wb_dynamics(double hip_yaw, double BG_alpha, const double* q, const double* v, const double* u,
+                            const int* contact, double* qdd, double* grf);
+
 /* Reference CasADi functions (from oracle/_ref) behind a flat signature, for the
  * "re-emitted device functions == reference generated code" tests. Returns 0, or
  * -1 if the name is unknown. in/out are dense column-major buffers. */

@@ -32,9 +32,9 @@ def data_dir():
 
 @pytest.fixture(scope="session")
 def hkd_problem(cm, data_dir):
-    return cm.HKDProblem(os.path.join(data_dir, "reference/trot_heuristic/quad_reference.csv"))
+    return cm.HKDProblem(os.path.join(data_dir, "Reference/Data/trot/heuristic/quad_reference.csv"))
 
 
 @pytest.fixture(scope="session")
 def hkd_options(cm, data_dir):
-    return cm.load_hsddp_setting(os.path.join(data_dir, "settings/hkd/ddp_setting.info"))
+    return cm.load_hsddp_setting(os.path.join(data_dir, "HKDMPC/settings/ddp_setting.info"))

@@ -104,13 +104,13 @@ def test_generated_srb_match_reference(gen_lib):
 
 # ------------------------------------------------------------------ host logic: settings, reference, deck
 def test_hsddp_settings_loader(cm, data_dir):
-    o = cm.load_hsddp_setting(os.path.join(data_dir, "settings/hkd/ddp_setting.info"))
+    o = cm.load_hsddp_setting(os.path.join(data_dir, "HKDMPC/settings/ddp_setting.info"))
     assert (o.alpha, o.gamma, o.update_penalty, o.update_relax, o.update_ReB) == (0.1, 0.01, 5, 1, 1)
     assert o.update_regularization == 2  # never read from file by the reference (file says 4)
     assert (o.max_DDP_iter, o.max_AL_iter, o.max_DDP_iter_runtime, o.max_AL_iter_runtime) == (10, 5, 1, 3)
     assert (o.cost_thresh, o.dynamics_feas_thresh, o.merit_scale, o.merit_offset) == (1e-3, 1e-3, 0.2, 1e2)
     assert (o.AL_active, o.ReB_active, o.smooth_active, o.MS) == (1, 1, 0, 1)
-    m = cm.load_hsddp_setting(os.path.join(data_dir, "settings/mhpc/ddp_setting.info"))
+    m = cm.load_hsddp_setting(os.path.join(data_dir, "MHPC/settings/ddp_setting.info"))
     assert (m.alpha, m.gamma, m.max_DDP_iter, m.max_AL_iter, m.cost_thresh, m.merit_offset) == (0.5, 0.1, 10, 20, 1e-2, 1)
 
 
@@ -144,7 +144,7 @@ def test_hkd_reference_values_are_float_rounded(hkd_problem):
 
 
 def test_hkd_start_offset_deck(cm, data_dir):
-    p = cm.HKDProblem(os.path.join(data_dir, "reference/trot_heuristic/quad_reference.csv"), k0=12)
+    p = cm.HKDProblem(os.path.join(data_dir, "Reference/Data/trot/heuristic/quad_reference.csv"), k0=12)
     ph = p.phases()
     assert sum(x.horizon for x in ph) == 60
     assert tuple(ph[0].contact) == (1, 0, 0, 1)

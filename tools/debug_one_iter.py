@@ -5,8 +5,8 @@ sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tests"))
 import cafe_mpc_b200 as cm
 from cafe_mpc_b200 import workload
 from oracle_bindings import oracle_solve, oracle_get
-prob = cm.HKDProblem(os.path.join(cm.api.DATA, "reference/trot_heuristic/quad_reference.csv"))
-opt = cm.load_hsddp_setting(os.path.join(cm.api.DATA, "settings/hkd/ddp_setting.info"))
+prob = cm.HKDProblem(os.path.join(cm.api.DATA, "Reference/Data/trot/heuristic/quad_reference.csv"))
+opt = cm.load_hsddp_setting(os.path.join(cm.api.DATA, "HKDMPC/settings/ddp_setting.info"))
 opt.max_DDP_iter = 1; opt.max_AL_iter = 1; opt.cost_thresh = 1e30; opt.dynamics_feas_thresh = 1e30
 x0 = workload.hkd_batch(prob, 4)
 s = cm.MultiPhaseDDP(prob, 0, 4); s.set_initial_condition(x0); s.solve(opt)

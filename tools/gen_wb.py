@@ -1,0 +1,93 @@
+#!/usr/bin/env python3
+"""Generates cafe_mpc_b200/csrc/gen/wb_gen.h: straight-line device functions of the whole-body model, emitted
+from the symbolic model in tools/wb_model.py (no Pinocchio, no CasADi at run time).
+
+  wb_terms        (q, v)        -> nle[18], M[18x18 lower incl. diag], J[12x18], Jdv[12], pf[12], vf[12]    hip yaw 3.1415
+                   replaces crba / nonLinearEffects / computeJointJacobians / getFrameJacobian / getFrameVelocity /
+                   getFrameAcceleration at MHPC/MHPC-Trajopt/WBM.cpp:375-411
+  wb_feet         (q, v)        -> pf[12], vf[12], J[12x18]                                                   hip yaw 3.1415
+                   replaces the kinematics getters WBM.cpp:260-364
+  wb_rnea_derivs  (q, v, a)     -> dtau_dq[18x18], dtau_dv[18x18]                                             hip yaw 3.1415
+                   replaces pinocchio::computeRNEADerivatives (WBM.cpp:474, :514)
+  wb_grav_derivs  (q)           -> dg_dq[18x18]                                                               hip yaw 3.1415
+                   replaces computeGeneralizedGravityDerivatives (WBM.cpp:520)
+  wb_kin_partials (q, v, a, F)  -> dv_dq[12x18], da_dq[12x18], da_dv[12x18], dJTF_dq[18x18]                   hip yaw pi
+                   replaces the CasADi functions footVelPartialDq / footAccPartialDq / footAccPartialDv /
+                   footForcePartialDq (MCKinematicsDerivativs.cpp), which were generated with exactly pi
+                   (SURVEY.md §9 Q16); verified against the compiled reference code to 1e-14 in tests/.
+Foot rows are stacked FL,FR,HL,HR (3 rows each)."""
+import math
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from casadi2cuda import HEADER  # noqa: E402
+from symbolic import Ctx, emit_function  # noqa: E402
+from wb_model import WBModel, hardcoded_params, make_vars, params_from_urdf  # noqa: E402
+
+URDF = "/root/reference/urdf/mini_cheetah_simple_correctedInertia.urdf"
+HIP_YAW_URDF = 3.1415
+
+
+def main():
+    out = sys.argv[1] if len(sys.argv) > 1 else "cafe_mpc_b200/csrc/gen/wb_gen.h"
+    P = params_from_urdf(URDF) if os.path.exists(URDF) else hardcoded_params()
+    pieces = []
+    # ---- Pinocchio-side quantities (hip yaw as in the URDF)
+    ctx = Ctx()
+    m = WBModel(ctx, P, HIP_YAW_URDF)
+    q, v, a = make_vars(ctx, 0, 18), make_vars(ctx, 1, 18), make_vars(ctx, 2, 18)
+    zero = [ctx.const(0.0)] * 18
+    nle = m.rnea(q, v, zero)
+    M = m.mass_matrix(q)
+    feet = m.feet(q, v, None)
+    o_nle = [(i, nle[i]) for i in range(18)]
+    o_M = [(r + 18 * c, M[r][c]) for c in range(18) for r in range(c, 18)]
+    o_J = [(3 * f + r + 12 * c, feet[f]["J"][r][c]) for f in range(4) for c in range(18) for r in range(3)]
+    o_g = [(3 * f + r, feet[f]["a"][r]) for f in range(4) for r in range(3)]
+    o_p = [(3 * f + r, feet[f]["p"][r]) for f in range(4) for r in range(3)]
+    o_v = [(3 * f + r, feet[f]["v"][r]) for f in range(4) for r in range(3)]
+    pieces.append(emit_function(ctx, "wb_terms", 2, [o_nle, o_M, o_J, o_g, o_p, o_v]))
+    pieces.append(emit_function(ctx, "wb_feet", 2, [o_p, o_v, o_J]))
+    tau = m.rnea(q, v, a)
+    o_dq = [(r + 18 * c, tau[r].d(q[c])) for c in range(18) for r in range(18)]
+    o_dv = [(r + 18 * c, tau[r].d(v[c])) for c in range(18) for r in range(18)]
+    pieces.append(emit_function(ctx, "wb_rnea_derivs", 3, [o_dq, o_dv]))
+    grav = m.rnea(q, zero, zero)
+    o_gq = [(r + 18 * c, grav[r].d(q[c])) for c in range(18) for r in range(18)]
+    pieces.append(emit_function(ctx, "wb_grav_derivs", 1, [o_gq]))
+    # ---- CasADi-side kinematic partials (hip yaw exactly pi)
+    ctx2 = Ctx()
+    m2 = WBModel(ctx2, P, math.pi)
+    q, v, a, F = make_vars(ctx2, 0, 18), make_vars(ctx2, 1, 18), make_vars(ctx2, 2, 18), make_vars(ctx2, 3, 12)
+    feet = m2.feet(q, v, a)
+    o_dv, o_daq, o_dav = [], [], []
+    jtf = [ctx2.const(0.0)] * 18
+    for f in range(4):
+        fv, fa, J = feet[f]["v"], feet[f]["a"], feet[f]["J"]
+        o_dv += [(3 * f + r + 12 * c, fv[r].d(q[c])) for c in range(18) for r in range(3)]
+        o_daq += [(3 * f + r + 12 * c, fa[r].d(q[c])) for c in range(18) for r in range(3)]
+        o_dav += [(3 * f + r + 12 * c, fa[r].d(v[c])) for c in range(18) for r in range(3)]
+        jtf = [jtf[i] + J[0][i] * F[3 * f] + J[1][i] * F[3 * f + 1] + J[2][i] * F[3 * f + 2] for i in range(18)]
+    o_jtf = [(r + 18 * c, jtf[r].d(q[c])) for c in range(18) for r in range(18)]
+    pieces.append(emit_function(ctx2, "wb_kin_partials", 4, [o_dv, o_daq, o_dav, o_jtf]))
+    # dv_dq alone (swing-foot velocity costs, touchdown velocity penalty, impact derivatives)
+    feet_v = m2.feet(q, v, None)
+    o_dv2 = []
+    for f in range(4):
+        o_dv2 += [(3 * f + r + 12 * c, feet_v[f]["v"][r].d(q[c])) for c in range(18) for r in range(3)]
+    pieces.append(emit_function(ctx2, "wb_footvel_partial", 2, [o_dv2]))
+    with open(out, "w") as fh:
+        fh.write(HEADER.replace("tools/casadi2cuda.py", "tools/gen_wb.py (symbolic whole-body model, tools/wb_model.py)"))
+        fh.write("namespace cafe_gen_wb {\n\n")
+        for code, meta in pieces:
+            fh.write("// %s: %d ops, output non-zeros %s\n" % (meta["name"], meta["ops"], meta["nnz"]))
+            fh.write(code)
+            fh.write("\n\n")
+        fh.write("}  // namespace cafe_gen_wb\n")
+    for code, meta in pieces:
+        print(meta)
+
+
+if __name__ == "__main__":
+    main()

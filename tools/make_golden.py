@@ -7,8 +7,8 @@ import cafe_mpc_b200 as cm
 from cafe_mpc_b200 import workload
 from oracle_bindings import oracle_solve
 
-prob = cm.HKDProblem(os.path.join(cm.api.DATA, "reference/trot_heuristic/quad_reference.csv"))
-opt = cm.load_hsddp_setting(os.path.join(cm.api.DATA, "settings/hkd/ddp_setting.info"))
+prob = cm.HKDProblem(os.path.join(cm.api.DATA, "Reference/Data/trot/heuristic/quad_reference.csv"))
+opt = cm.load_hsddp_setting(os.path.join(cm.api.DATA, "HKDMPC/settings/ddp_setting.info"))
 x0 = workload.hkd_batch(prob, 8)
 info, hist, trace, sol = oracle_solve(prob.deck, opt, x0[0])
 counts = np.array([info[k] for k in ("status", "iter", "ls_iter_total", "reg_iter_total", "outer_iter", "n_hist")])
