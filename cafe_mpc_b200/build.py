@@ -1,58 +1,74 @@
-"""Builds libcafe_gpu.so (CUDA kernels + C ABI + host problem builders) in-tree for sm_100a."""
+"""Builds libcafe_gpu.so (CUDA kernels + C ABI + host problem builders) in-tree for sm_100a.
+
+Every source is compiled to an object (relocatable device code) that is cached by modification time, then nvcc links
+the shared library; the generated whole-body routines live in their own translation unit because ptxas needs minutes for them."""
 import os
 import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libcafe_gpu.so")
 
-SOURCES = [
-    "solver.cu",
-    "host/abi_host.cpp",
-    "host/hkd_problem.cpp",
-    "host/mhpc_problem.cpp",
-    "host/quad_reference.cpp",
-]
+# source -> extra dependencies (besides itself and include/*.h)
+SOURCES = {
+    "solver.cu": ["kernels.cuh", "device_types.cuh", "model_hkd.cuh", "model_srb.cuh", "model_wb.cuh", "gen/hkd_gen.h", "gen/srb_gen.h"],
+    "wb_gen_wrappers.cu": ["gen/wb_gen.h"],
+    "host/abi_host.cpp": ["host/problem_builders.h", "host/quad_reference.h"],
+    "host/hkd_problem.cpp": ["host/problem_builders.h", "host/quad_reference.h", "host/info_reader.h", "gen/hkd_gen.h"],
+    "host/mhpc_problem.cpp": ["host/problem_builders.h", "host/quad_reference.h", "host/info_reader.h"],
+    "host/quad_reference.cpp": ["host/quad_reference.h"],
+}
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-lineinfo", "-std=c++17", "--shared", "-Xcompiler", "-fPIC",
+    "-O3", "-lineinfo", "-std=c++17", "-rdc=true", "-Xcompiler", "-fPIC",
     "--fmad=true", "-Xptxas", "-v", "-Xcudafe", "--diag_suppress=177",
 ]
 
 
-def needs_build():
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    for root, _, files in os.walk(CSRC):
-        for f in files:
-            if os.path.getmtime(os.path.join(root, f)) > t:
-                return True
-    inc = os.path.join(HERE, "..", "include")
-    for f in os.listdir(inc):
-        if os.path.getmtime(os.path.join(inc, f)) > t:
-            return True
-    return False
+def _mtime(p):
+    return os.path.getmtime(p) if os.path.exists(p) else 0.0
+
+
+def _stale(target, deps):
+    t = _mtime(target)
+    return t == 0.0 or any(_mtime(d) > t for d in deps)
 
 
 def build(force=False, verbose=False):
-    if not force and not needs_build():
-        return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    log = res.stdout + res.stderr
-    with open(os.path.join(HERE, "build.log"), "w") as f:
-        f.write(" ".join(cmd) + "\n" + log)
-    if res.returncode != 0:
-        sys.stderr.write(log)
-        raise RuntimeError("nvcc failed building libcafe_gpu.so")
-    if verbose:
-        print(log)
+    os.makedirs(OBJ, exist_ok=True)
+    inc = os.path.join(HERE, "..", "include")
+    incs = [os.path.join(inc, f) for f in os.listdir(inc)]
+    objs, logs, rebuilt = [], [], False
+    for src, deps in SOURCES.items():
+        obj = os.path.join(OBJ, src.replace("/", "_") + ".o")
+        objs.append(obj)
+        all_deps = [os.path.join(CSRC, src)] + [os.path.join(CSRC, d) for d in deps] + incs
+        if force or _stale(obj, all_deps):
+            cmd = [nvcc] + NVCC_FLAGS + ["-c", "-o", obj, os.path.join(CSRC, src)]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            logs.append(" ".join(cmd) + "\n" + res.stdout + res.stderr)
+            if res.returncode != 0:
+                sys.stderr.write(logs[-1])
+                raise RuntimeError("nvcc failed on " + src)
+            rebuilt = True
+    if rebuilt or not os.path.exists(LIB):
+        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-Xcompiler", "-fPIC", "-o", LIB] + objs
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        logs.append(" ".join(cmd) + "\n" + res.stdout + res.stderr)
+        if res.returncode != 0:
+            sys.stderr.write(logs[-1])
+            raise RuntimeError("nvcc link failed")
+    if logs:
+        with open(os.path.join(HERE, "build.log"), "a" if not force else "w") as f:
+            f.write("\n".join(logs))
+        if verbose:
+            print("\n".join(logs))
     return LIB
 
 
 if __name__ == "__main__":
-    build(force=True, verbose=True)
+    build(force="--force" in sys.argv, verbose=True)

@@ -16,7 +16,7 @@
 struct PhaseDev {
   int model, n, m, p, h, n_next, has_next;
   int contact[4], next_contact[4], n_td, td_foot[4];
-  double dt, mu, ground_height, BG_alpha;
+  double dt, mu, ground_height, BG_alpha, h_min, torque_limit, joint_lb[3], joint_ub[3];
   double q[CAFE_MAX_N], r[CAFE_MAX_M], qf[CAFE_MAX_N];
   double w_footreg[3], w_swingpos[3], w_swingvel[3], w_tdvel[3];
   CafeRebParam reb_grf, reb_torque, reb_joint, reb_minheight;

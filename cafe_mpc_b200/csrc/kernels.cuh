@@ -21,6 +21,8 @@
 #pragma once
 #include "device_types.cuh"
 #include "model_hkd.cuh"
+#include "model_srb.cuh"
+#include "model_wb.cuh"
 
 namespace cafe_dev {
 
@@ -64,7 +66,8 @@ __device__ void roll_knot(const SolverDev& S, int pi, int k, int a, int b) {
       ph.Ut[aU + gix(k, M, i, ldb, b)] = u[i];
     }
     double xn[N], y[PY > 0 ? PY : 1];
-    Model::dynamics(ph, rec, x, u, xn, y);
+    double l, ming;
+    Model::roll(ph, rec, x, u, xn, y, S.opt.ReB_active != 0, l, ming);
     double nrm = 0, dsq = 0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
@@ -76,8 +79,6 @@ __device__ void roll_knot(const SolverDev& S, int pi, int k, int a, int b) {
     }
 #pragma unroll
     for (int i = 0; i < PY; ++i) ph.Yt[aY + gix(k, PY, i, ldb, b)] = y[i];
-    double ming;
-    const double l = Model::running_cost(ph, rec, x, u, y, S.opt.ReB_active != 0, ming);
     ph.cost_t[aS + (size_t)k * ldb + b] = l;
     ph.feas_t[aS + (size_t)k * ldb + b] = dsq;
     ph.ming_t[aS + (size_t)k * ldb + b] = ming;
@@ -130,6 +131,8 @@ __global__ void __launch_bounds__(128) k_roll(const SolverDev* __restrict__ Sp, 
   const int pi = S.knot_phase[gk], k = S.knot_k[gk];
   switch (S.ph[pi].model) {
     case CAFE_MODEL_HKD: roll_knot<HKDModel>(S, pi, k, a, b); break;
+    case CAFE_MODEL_WB: roll_knot<WBModel>(S, pi, k, a, b); break;
+    case CAFE_MODEL_SRB: roll_knot<SRBModel>(S, pi, k, a, b); break;
     default: break;
   }
 }
@@ -152,9 +155,7 @@ __device__ void lq_knot_generic(const SolverDev& S, int pi, int k, int b) {
     for (int i = 0; i < M; ++i) u[i] = ph.U[gix(k, M, i, ldb, b)];
 #pragma unroll
     for (int i = 0; i < PY; ++i) y[i] = ph.Y[gix(k, PY, i, ldb, b)];
-    double ming;
-    ph.lk[(size_t)k * ldb + b] = Model::running_cost(ph, rec, x, u, y, S.opt.ReB_active != 0, ming);
-    Model::lq_knot(ph, k, ldb, b, rec, x, u, y, S.opt.ReB_active != 0);
+    ph.lk[(size_t)k * ldb + b] = Model::lq_knot(ph, k, ldb, b, rec, x, u, y, S.opt.ReB_active != 0);
   } else {
     double phi = Model::terminal_cost(ph, rec, x);
     if (ph.n_td > 0 && S.opt.AL_active) {
@@ -183,6 +184,8 @@ __global__ void __launch_bounds__(128) k_lq(const SolverDev* __restrict__ Sp) {
   const int pi = S.knot_phase[gk], k = S.knot_k[gk];
   switch (S.ph[pi].model) {
     case CAFE_MODEL_HKD: lq_knot_generic<HKDModel>(S, pi, k, b); break;
+    case CAFE_MODEL_WB: lq_knot_generic<WBModel>(S, pi, k, b); break;
+    case CAFE_MODEL_SRB: lq_knot_generic<SRBModel>(S, pi, k, b); break;
     default: break;
   }
 }
@@ -683,7 +686,13 @@ __global__ void __launch_bounds__(CAFE_NW* PB) k_bwd(const SolverDev* __restrict
     const double reg = s_reg[p];
     for (int pi = S.n_phases - 1; pi >= 0; --pi) {
       const int model = S.ph[pi].model, nm = S.ph[pi].has_next ? S.ph[pi + 1].model : -1;
-      if (model == CAFE_MODEL_HKD) sweep_phase<24, 24, 0, 24, PB, L>(S, pi, b, p, w, mine, ok, reg, sm, min_piv);
+      if constexpr (NX == 24) {
+        if (model == CAFE_MODEL_HKD) sweep_phase<24, 24, 0, 24, PB, L>(S, pi, b, p, w, mine, ok, reg, sm, min_piv);
+      } else {
+        if (model == CAFE_MODEL_SRB) sweep_phase<12, 12, 0, 12, PB, L>(S, pi, b, p, w, mine, ok, reg, sm, min_piv);
+        else if (model == CAFE_MODEL_WB && nm == CAFE_MODEL_SRB) sweep_phase<36, 12, 12, 12, PB, L>(S, pi, b, p, w, mine, ok, reg, sm, min_piv);
+        else if (model == CAFE_MODEL_WB) sweep_phase<36, 12, 12, 36, PB, L>(S, pi, b, p, w, mine, ok, reg, sm, min_piv);
+      }
       (void)nm;
     }
     __syncthreads();
@@ -707,7 +716,12 @@ __global__ void __launch_bounds__(CAFE_NW* PB) k_bwd(const SolverDev* __restrict
     __syncthreads();
     for (int pi = 0; pi < S.n_phases; ++pi) {
       const int model = S.ph[pi].model;
-      if (model == CAFE_MODEL_HKD) lin_phase<24, 24, PB, L>(S, pi, b, p, w, success, sm, dV1, dV2);
+      if constexpr (NX == 24) {
+        if (model == CAFE_MODEL_HKD) lin_phase<24, 24, PB, L>(S, pi, b, p, w, success, sm, dV1, dV2);
+      } else {
+        if (model == CAFE_MODEL_WB) lin_phase<36, 12, PB, L>(S, pi, b, p, w, success, sm, dV1, dV2);
+        else if (model == CAFE_MODEL_SRB) lin_phase<12, 12, PB, L>(S, pi, b, p, w, success, sm, dV1, dV2);
+      }
     }
   }
   if (w == 0 && valid) {

@@ -100,7 +100,13 @@ struct HKDModel {
     return l;
   }
 
-  // d_prel of HKDFootPlaceReg at a record
+  // dynamics + running cost of one trial knot
+  __device__ static void roll(const PhaseDev& ph, const double* rec, const double* x, const double* u, double* xn, double* y,
+                              bool reb, double& l, double& ming) {
+    dynamics(ph, rec, x, u, xn, y);
+    l = running_cost(ph, rec, x, u, y, reb, ming);
+  }
+
   __device__ static double terminal_cost(const PhaseDev& ph, const double* rec, const double* x) {
     double s = 0;
 #pragma unroll
@@ -134,9 +140,8 @@ struct HKDModel {
 
   // LQ data of one running knot, written straight into the batch-major HBM arrays.
   // A, B, lxx, luu were zeroed at allocation; only the (static) non-zero pattern is rewritten.
-  __device__ static void lq_knot(const PhaseDev& ph, int k, int ldb, int b, const double* rec, const double* x,
-                                 const double* u, const double* y, bool reb) {
-    (void)y;
+  __device__ static double lq_knot(const PhaseDev& ph, int k, int ldb, int b, const double* rec, const double* x,
+                                   const double* u, const double* y, bool reb) {
     const double dt = ph.dt;
     {
       const double c[4] = {(double)ph.contact[0], (double)ph.contact[1], (double)ph.contact[2], (double)ph.contact[3]};
@@ -213,6 +218,8 @@ struct HKDModel {
       ph.lx[gix(k, 24, i, ldb, b)] = lx[i];
       ph.lu[gix(k, 24, i, ldb, b)] = lu[i];
     }
+    double ming;
+    return running_cost(ph, rec, x, u, y, reb, ming);
   }
 
   // terminal cost partials (+ AL terms) and the reset-map Jacobian Px at X[h]

@@ -1,0 +1,518 @@
+// model_wb.cuh — device-side whole-body (WB) phase of the MHPC problem. One thread per (problem, knot); rigid-body terms
+// come from the generated straight-line functions of gen/wb_gen.h (no Pinocchio, no CasADi), the small dense KKT algebra
+// runs per thread on local arrays.
+//
+// Reference behaviour followed (file:line under /root/reference):
+//   WBM::Model::dynamics / dynamics_partial         MHPC/MHPC-Trajopt/WBM.cpp:17-139
+//   KKTContactDynamics / ...Derivatives             MHPC/MHPC-Trajopt/WBM.cpp:368-424, :459-505
+//   KKTImpact / KKTImpactDerivatives / impact       MHPC/MHPC-Trajopt/WBM.cpp:178-254, :427-456, :508-543
+//   MHPCReset::reset_map(_partial)                  MHPC/MHPC-Trajopt/MHPCReset.cpp:4-53
+//   WB costs                                        MHPC/MHPC-Trajopt/MHPCCost.cpp:4-291, MHPCCost.h:8-205
+//   WB constraints                                  MHPC/MHPC-Trajopt/MHPCConstraint.cpp:9-288
+// Pinocchio semantics restated: forwardDynamics (Cholesky(M); J Minv J^T + 1e-12 I; lambda = -(JMinvJt)^-1 (J Minv (tau-nle) + gamma);
+// qdd = Minv (tau - nle + J^T lambda)), impulseDynamics (r = 0), KKT matrix inverse (damping 0) — applied here column by column
+// instead of forming the inverse:  with R = d(M qdd + nle - J^T lambda - tau)/dz and a = d(J qdd + gamma)/dz,
+//   dlambda/dz = S^-1 (J Minv R - a),   dqdd/dz = -Minv (R - J^T dlambda/dz),   S = J Minv J^T.
+#pragma once
+#include "device_types.cuh"
+#include "model_hkd.cuh"
+
+namespace cafe_dev {
+
+// One out-of-line copy of every generated routine (defined in wb_gen_wrappers.cu, compiled separately because ptxas needs
+// minutes for these 10^4-op straight-line functions), writing into plain (local-memory) arrays; callers pre-zero the outputs.
+__device__ void wbg_terms(const double* q, const double* v, double* nle, double* Mlow, double* J, double* gam, double* pf, double* vf);
+__device__ void wbg_feet(const double* q, const double* v, double* pf, double* vf, double* J);
+__device__ void wbg_rnea_derivs(const double* q, const double* v, const double* a, double* dq, double* dv);
+__device__ void wbg_grav_derivs(const double* q, double* dq);
+__device__ void wbg_kin_partials(const double* q, const double* v, const double* a, const double* F, double* dvq, double* daq, double* dav, double* djtf);
+__device__ void wbg_footvel_partial(const double* q, const double* v, double* dvq);
+
+struct WBScratch {
+  double L[324];   // M (lower) then its Cholesky factor, column-major, ld 18
+  double J[216];   // foot Jacobians, rows 3f+r, ld 12
+  double nle[18], gam[12], pf[12], vf[12];
+  double Y[216];   // L^-1 Jc^T, 18 x nr, ld 18
+  double Ls[144];  // Cholesky of S = Y^T Y (+ damping), nr x nr, ld 12
+  double qdd[18], grf[12], lam[12];
+  int rows[12];
+  int nr;
+};
+
+// in-place Cholesky of a lower-stored n x n matrix (ld)
+__device__ __forceinline__ void chol_inplace(double* A, int n, int ld) {
+  for (int j = 0; j < n; ++j) {
+    double d = A[j + ld * j];
+    for (int k = 0; k < j; ++k) d -= A[j + ld * k] * A[j + ld * k];
+    d = sqrt(d);
+    A[j + ld * j] = d;
+    const double inv = 1.0 / d;
+    for (int i = j + 1; i < n; ++i) {
+      double s = A[i + ld * j];
+      for (int k = 0; k < j; ++k) s -= A[i + ld * k] * A[j + ld * k];
+      A[i + ld * j] = s * inv;
+    }
+  }
+}
+__device__ __forceinline__ void fwd_subst(const double* L, int n, int ld, double* x) {  // L y = x
+  for (int i = 0; i < n; ++i) { double s = x[i]; for (int k = 0; k < i; ++k) s -= L[i + ld * k] * x[k]; x[i] = s / L[i + ld * i]; }
+}
+__device__ __forceinline__ void bwd_subst(const double* L, int n, int ld, double* x) {  // L^T y = x
+  for (int i = n - 1; i >= 0; --i) { double s = x[i]; for (int k = i + 1; k < n; ++k) s -= L[k + ld * i] * x[k]; x[i] = s / L[i + ld * i]; }
+}
+
+struct WBModel {
+  static constexpr int N = 36, M = 12, PY = 12;
+
+  __device__ static void active_rows(const int* contact, WBScratch& s) {
+    s.nr = 0;
+    for (int f = 0; f < 4; ++f) if (contact[f] > 0) for (int r = 0; r < 3; ++r) s.rows[s.nr++] = 3 * f + r;
+  }
+
+  // M, nle, J, Jdot v, foot positions and velocities at (q, v); Cholesky of M; Y = L^-1 Jc^T; S = Y^T Y
+  __device__ static void kkt_setup(const double* x, WBScratch& s, double damping) {
+    for (int i = 0; i < 324; ++i) s.L[i] = 0;
+    for (int i = 0; i < 216; ++i) s.J[i] = 0;
+    wbg_terms(x, x + 18, s.nle, s.L, s.J, s.gam, s.pf, s.vf);
+    chol_inplace(s.L, 18, 18);
+    const int nr = s.nr;
+    for (int c = 0; c < nr; ++c) {
+      double* y = s.Y + 18 * c;
+      for (int i = 0; i < 18; ++i) y[i] = s.J[s.rows[c] + 12 * i];
+      fwd_subst(s.L, 18, 18, y);
+    }
+    for (int c = 0; c < nr; ++c)
+      for (int r = c; r < nr; ++r) {
+        double d = 0;
+        for (int i = 0; i < 18; ++i) d += s.Y[i + 18 * r] * s.Y[i + 18 * c];
+        s.Ls[r + 12 * c] = d + ((r == c) ? damping : 0.0);
+      }
+    if (nr > 0) chol_inplace(s.Ls, nr, 12);
+  }
+
+  // KKTContactDynamics (WBM.cpp:368-424): qdd, GRF for the phase contact set
+  __device__ static void forward(const PhaseDev& ph, const double* x, const double* u, WBScratch& s) {
+    active_rows(ph.contact, s);
+    kkt_setup(x, s, 1e-12);
+    double b[18];
+    for (int i = 0; i < 18; ++i) b[i] = ((i >= 6) ? u[i - 6] : 0.0) - s.nle[i];
+    double mb[18];
+    for (int i = 0; i < 18; ++i) mb[i] = b[i];
+    fwd_subst(s.L, 18, 18, mb);
+    const int nr = s.nr;
+    for (int i = 0; i < 12; ++i) s.grf[i] = 0;
+    if (nr > 0) {
+      // rhs = -Jc Minv b - gamma = -(Y^T L^-1 b) - gamma
+      for (int c = 0; c < nr; ++c) {
+        double d = 0;
+        for (int i = 0; i < 18; ++i) d += s.Y[i + 18 * c] * mb[i];
+        const int r = s.rows[c];
+        s.lam[c] = -d - (s.gam[r] + 2.0 * ph.BG_alpha * s.vf[r]);
+      }
+      fwd_subst(s.Ls, nr, 12, s.lam);
+      bwd_subst(s.Ls, nr, 12, s.lam);
+      for (int c = 0; c < nr; ++c) { s.grf[s.rows[c]] = s.lam[c]; for (int i = 0; i < 18; ++i) mb[i] += s.Y[i + 18 * c] * s.lam[c]; }
+    }
+    bwd_subst(s.L, 18, 18, mb);  // qdd = L^-T (L^-1 b + Y lambda)
+    for (int i = 0; i < 18; ++i) s.qdd[i] = mb[i];
+  }
+
+  // running cost from already evaluated foot kinematics (pf, vf) + ReB terms
+  __device__ static double running_cost_k(const PhaseDev& ph, const double* rec, const double* x, const double* u, const double* y,
+                                          const double* pf, const double* vf, bool reb, double& ming) {
+    double s = 0;
+    for (int i = 0; i < 36; ++i) { const double dx = x[i] - rec[CAFE_REF_XR + i]; s += dx * ph.q[i] * dx; }
+    double l = 0.5 * s;
+    s = 0;
+    for (int i = 0; i < 12; ++i) { const double du = u[i] - rec[CAFE_REF_UR + i]; s += du * ph.r[i] * du; }
+    l += 0.5 * s;
+    l *= ph.dt;
+    double lreg = 0, lpos = 0, lvel = 0;
+    for (int f = 0; f < 4; ++f) {
+      const bool c = rec[CAFE_REF_CONTACT + f] > 0;
+      const double* w = c ? ph.w_footreg : ph.w_swingpos;
+      double q2 = 0;
+      for (int a = 0; a < 3; ++a) { const double d = (pf[3 * f + a] - x[a]) - (rec[CAFE_REF_PF + 3 * f + a] - rec[CAFE_REF_PCOM + a]); q2 += d * w[a] * d; }
+      double t = .5 * q2; t *= ph.dt;
+      if (c) lreg += t; else lpos += t;
+      if (!c) {
+        double q3 = 0;
+        for (int a = 0; a < 3; ++a) { const double dv = vf[3 * f + a] - rec[CAFE_REF_VF + 3 * f + a]; q3 += dv * ph.w_swingvel[a] * dv; }
+        double t2 = .5 * q3; t2 *= ph.dt;
+        lvel += t2;
+      }
+    }
+    l += lreg; l += lpos; l += lvel;
+    ming = 0;
+    if (true) {
+      // path constraints in the reference's order: torque, joint, min height, GRF (MHPCProblem.cpp:436-481)
+      double c_t = 0, c_j = 0, c_h = 0, c_g = 0, m_t = 0, m_j = 0, m_h = 0, m_g = 0;
+      for (int i = 0; i < 12; ++i) { const double g = -u[i] - (-ph.torque_limit); m_t = fmin(m_t, g); c_t += ph.reb_torque.eps * reb_value(g, ph.reb_torque.delta); }
+      for (int i = 0; i < 12; ++i) { const double g = u[i] - (-ph.torque_limit); m_t = fmin(m_t, g); c_t += ph.reb_torque.eps * reb_value(g, ph.reb_torque.delta); }
+      for (int i = 0; i < 12; ++i) { const double g = x[6 + i] - ph.joint_lb[i % 3]; m_j = fmin(m_j, g); c_j += ph.reb_joint.eps * reb_value(g, ph.reb_joint.delta); }
+      for (int i = 0; i < 12; ++i) { const double g = -x[6 + i] - (-ph.joint_ub[i % 3]); m_j = fmin(m_j, g); c_j += ph.reb_joint.eps * reb_value(g, ph.reb_joint.delta); }
+      { const double g = x[2] - ph.h_min; m_h = fmin(m_h, g); c_h += ph.reb_minheight.eps * reb_value(g, ph.reb_minheight.delta); }
+      bool any = false;
+      for (int f = 0; f < 4; ++f)
+        if (ph.contact[f] > 0) {
+          any = true;
+          const double fx = y[3 * f], fy = y[3 * f + 1], fz = y[3 * f + 2], mu = ph.mu;
+          const double g[5] = {fz, -fx + mu * fz, fx + mu * fz, -fy + mu * fz, fy + mu * fz};
+          for (int i = 0; i < 5; ++i) { m_g = fmin(m_g, g[i]); c_g += ph.reb_grf.eps * reb_value(g[i], ph.reb_grf.delta); }
+        }
+      ming = fmin(fmin(m_t, m_j), fmin(m_h, m_g));
+      if (reb) { l += ph.dt * c_t; l += ph.dt * c_j; l += ph.dt * c_h; if (any) l += ph.dt * c_g; }
+    }
+    return l;
+  }
+
+  __device__ __noinline__ static void roll(const PhaseDev& ph, const double* rec, const double* x, const double* u, double* xn, double* y,
+                              bool reb, double& l, double& ming) {
+    WBScratch s;
+    forward(ph, x, u, s);
+    for (int i = 0; i < 18; ++i) { xn[i] = x[i] + x[18 + i] * ph.dt; xn[18 + i] = x[18 + i] + s.qdd[i] * ph.dt; }
+    for (int i = 0; i < 12; ++i) y[i] = s.grf[i];
+    l = running_cost_k(ph, rec, x, u, y, s.pf, s.vf, reb, ming);
+  }
+
+  __device__ static void feet(const double* x, double* pf, double* vf, double* J) {
+    for (int i = 0; i < 216; ++i) J[i] = 0;
+    wbg_feet(x, x + 18, pf, vf, J);
+  }
+
+  __device__ __noinline__ static double terminal_cost(const PhaseDev& ph, const double* rec, const double* x) {
+    double pf[12], vf[12], J[216];
+    feet(x, pf, vf, J);
+    double s = 0;
+    for (int i = 0; i < 36; ++i) { const double dx = x[i] - rec[CAFE_REF_XR + i]; s += dx * ph.qf[i] * dx; }
+    const double phi = s * 0.5;
+    double reg = 0;
+    for (int f = 0; f < 4; ++f) {
+      if (!(rec[CAFE_REF_CONTACT + f] > 0)) continue;
+      double q2 = 0;
+      for (int a = 0; a < 3; ++a) { const double d = (pf[3 * f + a] - x[a]) - (rec[CAFE_REF_PF + 3 * f + a] - rec[CAFE_REF_PCOM + a]); q2 += d * ph.w_footreg[a] * d; }
+      reg += .5 * q2;
+    }
+    double td = 0;
+    for (int i = 0; i < ph.n_td; ++i) { const double dv = vf[3 * ph.td_foot[i] + 2]; td += .5 * dv * ph.w_tdvel[2] * dv; }
+    return phi + reg + td;
+  }
+  __device__ __noinline__ static void terminal_constraints(const PhaseDev& ph, const double* x, double* hv) {
+    double pf[12], vf[12], J[216];
+    feet(x, pf, vf, J);
+    for (int i = 0; i < ph.n_td; ++i) hv[i] = pf[3 * ph.td_foot[i] + 2] - ph.ground_height;
+  }
+
+  // impact (KKTImpact, WBM.cpp:427-456): v+ = v + Minv Jc^T Lambda, Lambda = -(Jc Minv Jc^T)^-1 Jc v
+  __device__ static void impact(const PhaseDev& ph, const double* x, WBScratch& s, double* vpost) {
+    int st[4];
+    for (int f = 0; f < 4; ++f) st[f] = (ph.contact[f] == 0 && ph.next_contact[f] == 1) ? 1 : 0;
+    active_rows(st, s);
+    double xq[36];
+    for (int i = 0; i < 18; ++i) { xq[i] = x[i]; xq[18 + i] = 0.0; }
+    kkt_setup(xq, s, 0.0);
+    const int nr = s.nr;
+    for (int c = 0; c < nr; ++c) { double d = 0; for (int i = 0; i < 18; ++i) d += s.J[s.rows[c] + 12 * i] * x[18 + i]; s.lam[c] = -d; }
+    fwd_subst(s.Ls, nr, 12, s.lam);
+    bwd_subst(s.Ls, nr, 12, s.lam);
+    double t[18];
+    for (int i = 0; i < 18; ++i) { double d = 0; for (int c = 0; c < nr; ++c) d += s.Y[i + 18 * c] * s.lam[c]; t[i] = d; }
+    bwd_subst(s.L, 18, 18, t);
+    for (int i = 0; i < 18; ++i) vpost[i] = x[18 + i] + t[i];
+  }
+  __device__ static bool any_touchdown(const PhaseDev& ph) {
+    for (int f = 0; f < 4; ++f) if (ph.next_contact[f] - ph.contact[f] == 1) return true;
+    return false;
+  }
+  __device__ __noinline__ static void resetmap(const PhaseDev& ph, const double* x, double* xn) {
+    double full[36];
+    for (int i = 0; i < 36; ++i) full[i] = x[i];
+    if (any_touchdown(ph)) { WBScratch s; impact(ph, x, s, full + 18); }
+    if (ph.n_next == 12) { for (int i = 0; i < 6; ++i) { xn[i] = full[i]; xn[6 + i] = full[18 + i]; } }
+    else for (int i = 0; i < 36; ++i) xn[i] = full[i];
+  }
+
+  // ---- LQ data of one running knot
+  __device__ __noinline__ static double lq_knot(const PhaseDev& ph, int k, int ldb, int b, const double* rec, const double* x, const double* u,
+                                   const double* y_unused, bool reb) {
+    (void)y_unused;
+    const double dt = ph.dt;
+    WBScratch s;
+    forward(ph, x, u, s);
+    const int nr = s.nr;
+    // S without damping for the sensitivities (computeKKTContactDynamicMatrixInverse, WBM.cpp:467)
+    double Ls0[144];
+    for (int c = 0; c < nr; ++c)
+      for (int r = c; r < nr; ++r) { double d = 0; for (int i = 0; i < 18; ++i) d += s.Y[i + 18 * r] * s.Y[i + 18 * c]; Ls0[r + 12 * c] = d; }
+    if (nr > 0) chol_inplace(Ls0, nr, 12);
+    double Rq[324], Rv[324], aq[216], av[216], dvq[216];
+    for (int i = 0; i < 324; ++i) { Rq[i] = 0; Rv[i] = 0; }
+    for (int i = 0; i < 216; ++i) { aq[i] = 0; av[i] = 0; dvq[i] = 0; }
+    wbg_rnea_derivs(x, x + 18, s.qdd, Rq, Rv);
+    {
+      // dtau_dq -= d(J^T GRF)/dq ; foot acceleration / velocity partials (hip yaw = pi side)
+      double djtf[324];
+      for (int i = 0; i < 324; ++i) djtf[i] = 0;
+      wbg_kin_partials(x, x + 18, s.qdd, s.grf, dvq, aq, av, djtf);
+      for (int i = 0; i < 324; ++i) Rq[i] -= djtf[i];
+    }
+    const double bg2 = 2.0 * ph.BG_alpha;
+    for (int i = 0; i < 216; ++i) { aq[i] += bg2 * dvq[i]; av[i] += bg2 * s.J[i]; }
+    // outputs
+    double* Ag = ph.A + gix(k, 1296, 0, ldb, b);
+    double* Bg = ph.Bm + gix(k, 432, 0, ldb, b);
+    double* Cg = ph.C + gix(k, 432, 0, ldb, b);
+    double* Dg = ph.D + gix(k, 144, 0, ldb, b);
+    for (int i = 0; i < 18; ++i) { Ag[(size_t)(i + 36 * i) * ldb] = 1.0; Ag[(size_t)(i + 36 * (18 + i)) * ldb] = dt; }
+    for (int col = 0; col < 48; ++col) {
+      double r[18], w[12];
+      if (col < 18) for (int i = 0; i < 18; ++i) r[i] = Rq[i + 18 * col];
+      else if (col < 36) for (int i = 0; i < 18; ++i) r[i] = Rv[i + 18 * (col - 18)];
+      else for (int i = 0; i < 18; ++i) r[i] = (i == 6 + (col - 36)) ? -1.0 : 0.0;
+      fwd_subst(s.L, 18, 18, r);  // r <- L^-1 R
+      for (int c = 0; c < nr; ++c) {
+        double d = 0;
+        for (int i = 0; i < 18; ++i) d += s.Y[i + 18 * c] * r[i];  // (Jc Minv R)_c
+        const int row = s.rows[c];
+        const double a = (col < 18) ? aq[row + 12 * col] : (col < 36 ? av[row + 12 * (col - 18)] : 0.0);
+        w[c] = d - a;
+      }
+      if (nr > 0) { fwd_subst(Ls0, nr, 12, w); bwd_subst(Ls0, nr, 12, w); }  // dlambda/dz
+      for (int i = 0; i < 18; ++i) { double d = -r[i]; for (int c = 0; c < nr; ++c) d += s.Y[i + 18 * c] * w[c]; r[i] = d; }
+      bwd_subst(s.L, 18, 18, r);  // dqdd/dz
+      if (col < 36) {
+        for (int i = 0; i < 18; ++i) Ag[(size_t)((18 + i) + 36 * col) * ldb] = ((col == 18 + i) ? 1.0 : 0.0) + r[i] * dt;
+        for (int c = 0; c < nr; ++c) Cg[(size_t)(s.rows[c] + 12 * col) * ldb] = w[c];
+      } else {
+        for (int i = 0; i < 18; ++i) Bg[(size_t)((18 + i) + 36 * (col - 36)) * ldb] = r[i] * dt;
+        for (int c = 0; c < nr; ++c) Dg[(size_t)(s.rows[c] + 12 * (col - 36)) * ldb] = w[c];
+      }
+    }
+    // ---- cost partials
+    // lu, luu (diagonal): tracking + torque-limit barrier
+    double* luug = ph.luu + gix(k, 144, 0, ldb, b);
+    for (int i = 0; i < 12; ++i) {
+      double lu = dt * ph.r[i] * (u[i] - rec[CAFE_REF_UR + i]);
+      double luu = dt * ph.r[i];
+      if (reb) {
+        double bd1, bdd1, bd2, bdd2;
+        reb_derivs(-u[i] + ph.torque_limit, ph.reb_torque.delta, bd1, bdd1);
+        reb_derivs(u[i] + ph.torque_limit, ph.reb_torque.delta, bd2, bdd2);
+        lu += dt * (ph.reb_torque.eps * bd1 * (-1.0) + ph.reb_torque.eps * bd2);
+        luu += dt * (ph.reb_torque.eps * bdd1 + ph.reb_torque.eps * bdd2);
+      }
+      ph.lu[gix(k, 12, i, ldb, b)] = lu;
+      luug[(size_t)(13 * i) * ldb] = luu;
+    }
+    // ly, lyy: GRF barrier on the output (3x3 block per stance foot)
+    double* lyyg = ph.lyy + gix(k, 144, 0, ldb, b);
+    for (int f = 0; f < 4; ++f) {
+      double gr[3] = {0, 0, 0}, hs[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+      if (reb && ph.contact[f] > 0) {
+        const double fx = s.grf[3 * f], fy = s.grf[3 * f + 1], fz = s.grf[3 * f + 2], mu = ph.mu;
+        const double g[5] = {fz, -fx + mu * fz, fx + mu * fz, -fy + mu * fz, fy + mu * fz};
+        const double Al[5][3] = {{0, 0, 1}, {-1, 0, mu}, {1, 0, mu}, {0, -1, mu}, {0, 1, mu}};
+        for (int i = 0; i < 5; ++i) {
+          double bd, bdd;
+          reb_derivs(g[i], ph.reb_grf.delta, bd, bdd);
+          const double e1 = ph.reb_grf.eps * bd, e2 = ph.reb_grf.eps * bdd;
+          for (int r = 0; r < 3; ++r) { gr[r] += e1 * Al[i][r]; for (int c = 0; c < 3; ++c) hs[r][c] += Al[i][r] * (e2 * Al[i][c]); }
+        }
+      }
+      for (int r = 0; r < 3; ++r) {
+        ph.ly[gix(k, 12, 3 * f + r, ldb, b)] = dt * gr[r];
+        for (int c = 0; c < 3; ++c) lyyg[(size_t)((3 * f + r) + 12 * (3 * f + c)) * ldb] = dt * hs[r][c];
+      }
+    }
+    // lx, lxx
+    double lx[36];
+    for (int i = 0; i < 36; ++i) lx[i] = dt * ph.q[i] * (x[i] - rec[CAFE_REF_XR + i]);
+    double dposw[12], dvelw[12];  // weighted residuals W d per foot
+    for (int f = 0; f < 4; ++f) {
+      const bool c = rec[CAFE_REF_CONTACT + f] > 0;
+      const double* w = c ? ph.w_footreg : ph.w_swingpos;
+      for (int a = 0; a < 3; ++a) {
+        const double d = (s.pf[3 * f + a] - x[a]) - (rec[CAFE_REF_PF + 3 * f + a] - rec[CAFE_REF_PCOM + a]);
+        dposw[3 * f + a] = w[a] * d;
+        dvelw[3 * f + a] = c ? 0.0 : ph.w_swingvel[a] * (s.vf[3 * f + a] - rec[CAFE_REF_VF + 3 * f + a]);
+      }
+    }
+    for (int f = 0; f < 4; ++f) {
+      const bool c = rec[CAFE_REF_CONTACT + f] > 0;
+      for (int i = 3; i < 18; ++i) { double g = 0; for (int a = 0; a < 3; ++a) g += s.J[3 * f + a + 12 * i] * dposw[3 * f + a]; lx[i] += g * dt; }
+      if (!c)
+        for (int i = 0; i < 36; ++i) {
+          double g = 0;
+          for (int a = 0; a < 3; ++a) g += ((i < 18) ? dvq[3 * f + a + 12 * i] : s.J[3 * f + a + 12 * (i - 18)]) * dvelw[3 * f + a];
+          lx[i] += g * dt;
+        }
+    }
+    double bdj[24], bddj[24], bdh = 0, bddh = 0;
+    if (reb) {
+      for (int i = 0; i < 12; ++i) {
+        reb_derivs(x[6 + i] - ph.joint_lb[i % 3], ph.reb_joint.delta, bdj[i], bddj[i]);
+        reb_derivs(-x[6 + i] + ph.joint_ub[i % 3], ph.reb_joint.delta, bdj[12 + i], bddj[12 + i]);
+        lx[6 + i] += dt * (ph.reb_joint.eps * bdj[i] - ph.reb_joint.eps * bdj[12 + i]);
+      }
+      reb_derivs(x[2] - ph.h_min, ph.reb_minheight.delta, bdh, bddh);
+      lx[2] += dt * (ph.reb_minheight.eps * bdh);
+    }
+    for (int i = 0; i < 36; ++i) ph.lx[gix(k, 36, i, ldb, b)] = lx[i];
+    double* lxxg = ph.lxx + gix(k, 1296, 0, ldb, b);
+    for (int j = 0; j < 36; ++j)
+      for (int i = 0; i < 36; ++i) {
+        double v = (i == j) ? dt * ph.q[i] : 0.0;
+        for (int f = 0; f < 4; ++f) {
+          const bool c = rec[CAFE_REF_CONTACT + f] > 0;
+          const double* w = c ? ph.w_footreg : ph.w_swingpos;
+          if (i >= 3 && i < 18 && j >= 3 && j < 18) {
+            double hh = 0;
+            for (int a = 0; a < 3; ++a) hh += s.J[3 * f + a + 12 * i] * w[a] * s.J[3 * f + a + 12 * j];
+            v += hh * dt;
+          }
+          if (!c) {
+            double hh = 0;
+            for (int a = 0; a < 3; ++a) {
+              const double ji = (i < 18) ? dvq[3 * f + a + 12 * i] : s.J[3 * f + a + 12 * (i - 18)];
+              const double jj = (j < 18) ? dvq[3 * f + a + 12 * j] : s.J[3 * f + a + 12 * (j - 18)];
+              hh += ji * ph.w_swingvel[a] * jj;
+            }
+            v += hh * dt;
+          }
+        }
+        if (reb && i == j) {
+          if (i >= 6 && i < 18) v += dt * (ph.reb_joint.eps * bddj[i - 6] + ph.reb_joint.eps * bddj[12 + i - 6]);
+          if (i == 2) v += dt * (ph.reb_minheight.eps * bddh);
+        }
+        lxxg[(size_t)(i + 36 * j) * ldb] = v;
+      }
+    double ming;
+    return running_cost_k(ph, rec, x, u, s.grf, s.pf, s.vf, reb, ming);
+  }
+
+  // ---- terminal cost partials (+AL) and the reset-map Jacobian
+  __device__ __noinline__ static void lq_terminal(const PhaseDev& ph, int ldb, int b, const double* rec, const double* x, bool al) {
+    double pf[12], vf[12], J[216], dvq[216];
+    feet(x, pf, vf, J);
+    for (int i = 0; i < 216; ++i) dvq[i] = 0;
+    if (ph.n_td > 0) wbg_footvel_partial(x, x + 18, dvq);
+    double phix[36];
+    for (int i = 0; i < 36; ++i) phix[i] = ph.qf[i] * (x[i] - rec[CAFE_REF_XR + i]);
+    double dposw[12];
+    for (int f = 0; f < 4; ++f)
+      for (int a = 0; a < 3; ++a) dposw[3 * f + a] = ph.w_footreg[a] * ((pf[3 * f + a] - x[a]) - (rec[CAFE_REF_PF + 3 * f + a] - rec[CAFE_REF_PCOM + a]));
+    for (int f = 0; f < 4; ++f) {
+      if (!(rec[CAFE_REF_CONTACT + f] > 0)) continue;
+      for (int i = 3; i < 18; ++i) { double g = 0; for (int a = 0; a < 3; ++a) g += J[3 * f + a + 12 * i] * dposw[3 * f + a]; phix[i] += 2 * g; }
+    }
+    for (int t = 0; t < ph.n_td; ++t) {
+      const int f = ph.td_foot[t];
+      const double dv = vf[3 * f + 2];
+      for (int i = 0; i < 36; ++i) phix[i] += ((i < 18) ? dvq[3 * f + 2 + 12 * i] : J[3 * f + 2 + 12 * (i - 18)]) * ph.w_tdvel[2] * dv;
+    }
+    double cg[4] = {0, 0, 0, 0}, ch[4] = {0, 0, 0, 0};
+    const int ntd = al ? ph.n_td : 0;
+    for (int t = 0; t < ntd; ++t) {
+      const double hval = pf[3 * ph.td_foot[t] + 2] - ph.ground_height;
+      const double sigma = ph.al_sigma[(size_t)t * ldb + b], lambda = ph.al_lambda[(size_t)t * ldb + b];
+      cg[t] = sigma * hval + lambda;
+      ch[t] = sigma * (1 + hval) + lambda;
+      for (int i = 0; i < 18; ++i) phix[i] += cg[t] * J[3 * ph.td_foot[t] + 2 + 12 * i];
+    }
+    for (int i = 0; i < 36; ++i) ph.Phix[(size_t)i * ldb + b] = phix[i];
+    for (int j = 0; j < 36; ++j)
+      for (int i = 0; i < 36; ++i) {
+        double v = (i == j) ? ph.qf[i] : 0.0;
+        if (i >= 3 && i < 18 && j >= 3 && j < 18)
+          for (int f = 0; f < 4; ++f) {
+            if (!(rec[CAFE_REF_CONTACT + f] > 0)) continue;
+            double hh = 0;
+            for (int a = 0; a < 3; ++a) hh += J[3 * f + a + 12 * i] * ph.w_footreg[a] * J[3 * f + a + 12 * j];
+            v += 2 * hh;
+          }
+        for (int t = 0; t < ph.n_td; ++t) {
+          const int f = ph.td_foot[t];
+          const double ji = (i < 18) ? dvq[3 * f + 2 + 12 * i] : J[3 * f + 2 + 12 * (i - 18)];
+          const double jj = (j < 18) ? dvq[3 * f + 2 + 12 * j] : J[3 * f + 2 + 12 * (j - 18)];
+          v += ji * ph.w_tdvel[2] * jj;
+        }
+        if (i < 18 && j < 18) for (int t = 0; t < ntd; ++t) v += ch[t] * J[3 * ph.td_foot[t] + 2 + 12 * i] * J[3 * ph.td_foot[t] + 2 + 12 * j];
+        ph.Phixx[(size_t)(i + 36 * j) * ldb + b] = v;
+      }
+    if (!ph.has_next) return;
+    // ---- reset-map Jacobian: impact partial (WBM.cpp:508-543) then the WB->SRB projection (MHPCReset.cpp:31-53)
+    const int nn = ph.n_next;
+    const bool proj = (nn == 12);
+    if (!any_touchdown(ph)) {
+      for (int c = 0; c < 36; ++c)
+        for (int r = 0; r < nn; ++r) {
+          const int src = proj ? (r < 6 ? r : 12 + r) : r;
+          ph.Px[(size_t)(r + nn * c) * ldb + b] = (src == c) ? 1.0 : 0.0;
+        }
+      return;
+    }
+    WBScratch s;
+    double vpost[18];
+    impact(ph, x, s, vpost);
+    const int nr = s.nr;
+    // M itself is needed for dv+/dv = Kinv_tl M; rebuild it from its factor: M = L L^T (column by column below)
+    double Rq[324], dvq2[216], dv[18], zero18[18], imp[12];
+    for (int i = 0; i < 18; ++i) { dv[i] = vpost[i] - x[18 + i]; zero18[i] = 0; }
+    for (int i = 0; i < 324; ++i) Rq[i] = 0;
+    {
+      // d(M(q) dv + g(q))/dq - dg/dq  (computeRNEADerivatives(q, 0, v+ - v) minus computeGeneralizedGravityDerivatives)
+      double tmp[324];
+      for (int i = 0; i < 324; ++i) tmp[i] = 0;
+      wbg_rnea_derivs(x, zero18, dv, Rq, tmp);
+      for (int i = 0; i < 324; ++i) tmp[i] = 0;
+      wbg_grav_derivs(x, tmp);
+      for (int i = 0; i < 324; ++i) Rq[i] -= tmp[i];
+    }
+    // impulse scatter with the reference's segment<3>(i) indexing (WBM.cpp:454)
+    for (int i = 0; i < 12; ++i) imp[i] = 0;
+    {
+      int ci = 0;
+      for (int f = 0; f < 4; ++f) if (ph.contact[f] == 0 && ph.next_contact[f] == 1) { for (int r = 0; r < 3; ++r) imp[3 * f + r] = s.lam[ci + r]; ++ci; }
+    }
+    for (int i = 0; i < 216; ++i) dvq2[i] = 0;
+    {
+      double xv[36];
+      for (int i = 0; i < 18; ++i) { xv[i] = x[i]; xv[18 + i] = vpost[i]; }
+      double da1[216], da2[216], djtf[324];
+      for (int i = 0; i < 216; ++i) { da1[i] = 0; da2[i] = 0; }
+      for (int i = 0; i < 324; ++i) djtf[i] = 0;
+      wbg_kin_partials(xv, xv + 18, zero18, imp, dvq2, da1, da2, djtf);
+      for (int i = 0; i < 324; ++i) Rq[i] -= djtf[i];
+    }
+    for (int col = 0; col < 36; ++col) {
+      double r[18], w[12];
+      if (col < 18) for (int i = 0; i < 18; ++i) r[i] = Rq[i + 18 * col];
+      else {
+        // column of M: M e_c = L (L^T e_c)
+        const int c = col - 18;
+        double t[18];
+        for (int i = 0; i < 18; ++i) t[i] = (i <= c) ? s.L[c + 18 * i] : 0.0;  // (L^T e_c)_i = L[c][i]
+        for (int i = 0; i < 18; ++i) { double d = 0; for (int kk = 0; kk <= i; ++kk) d += s.L[i + 18 * kk] * t[kk]; r[i] = -d; }
+      }
+      fwd_subst(s.L, 18, 18, r);
+      for (int c = 0; c < nr; ++c) {
+        double d = 0;
+        for (int i = 0; i < 18; ++i) d += s.Y[i + 18 * c] * r[i];
+        w[c] = d - ((col < 18) ? dvq2[s.rows[c] + 12 * col] : 0.0);
+      }
+      if (nr > 0) { fwd_subst(s.Ls, nr, 12, w); bwd_subst(s.Ls, nr, 12, w); }
+      for (int i = 0; i < 18; ++i) { double d = -r[i]; for (int c = 0; c < nr; ++c) d += s.Y[i + 18 * c] * w[c]; r[i] = d; }
+      bwd_subst(s.L, 18, 18, r);  // column of dv+/dq (col < 18) or of Kinv_tl M (col >= 18)
+      // rows of dP_dx: [I 0; dv+/dq dv+/dv]
+      for (int rr = 0; rr < nn; ++rr) {
+        const int src = proj ? (rr < 6 ? rr : 12 + rr) : rr;
+        double v;
+        if (src < 18) v = (src == col) ? 1.0 : 0.0;
+        else v = r[src - 18];
+        ph.Px[(size_t)(rr + nn * col) * ldb + b] = v;
+      }
+    }
+  }
+};
+
+}  // namespace cafe_dev

@@ -198,6 +198,7 @@ int launch_bwd(CafeHandle* H) {
   const int PB = H->bwd_pb;
   const int grid = (H->B + PB - 1) / PB;
   if (H->bwd_variant == 0) k_bwd<24, 24, 0, 4><<<grid, CAFE_NW * 4, H->bwd_smem, H->stream>>>(H->dS);
+  else k_bwd<36, 12, 12, 3><<<grid, CAFE_NW * 3, H->bwd_smem, H->stream>>>(H->dS);
   return 0;
 }
 
@@ -212,11 +213,16 @@ extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, 
   bool all_hkd = true;
   int n_knots = 0;
   for (int i = 0; i < deck->n_phases; ++i) { all_hkd = all_hkd && deck->phase[i].model == CAFE_MODEL_HKD; n_knots += deck->phase[i].horizon + 1; }
-  if (!all_hkd) { cafe::set_last_error("only HKD decks are supported by this build of the GPU path"); return CAFE_ERR_UNSUPPORTED; }
+  bool any_hkd = false;
+  for (int i = 0; i < deck->n_phases; ++i) any_hkd = any_hkd || deck->phase[i].model == CAFE_MODEL_HKD;
+  if (!all_hkd && any_hkd) { cafe::set_last_error("a deck cannot mix HKD phases with WB/SRB phases"); return CAFE_ERR_UNSUPPORTED; }
+  for (int i = 0; i + 1 < deck->n_phases; ++i)
+    if (deck->phase[i].model == CAFE_MODEL_SRB) { cafe::set_last_error("an SRB phase must be the last phase"); return CAFE_ERR_UNSUPPORTED; }
   if (n_knots > CAFE_MAX_KNOTS) { cafe::set_last_error("horizon too long"); return CAFE_ERR_UNSUPPORTED; }
   for (int i = 0; i < deck->n_phases; ++i) {
     const CafePhase& p = deck->phase[i];
-    if (p.reb_grf.delta < p.reb_grf.delta_min) { cafe::set_last_error("ReB delta < delta_min is not supported"); return CAFE_ERR_UNSUPPORTED; }
+    if (p.reb_grf.delta < p.reb_grf.delta_min || p.reb_torque.delta < p.reb_torque.delta_min || p.reb_joint.delta < p.reb_joint.delta_min ||
+        p.reb_minheight.delta < p.reb_minheight.delta_min) { cafe::set_last_error("ReB delta < delta_min is not supported"); return CAFE_ERR_UNSUPPORTED; }
   }
   CafeHandle* H = new CafeHandle();
   H->device = device; H->max_batch = max_batch; H->ldb = (max_batch + 31) / 32 * 32;
@@ -238,6 +244,8 @@ extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, 
     d.n_next = d.has_next ? cafe_model_n(deck->phase[i + 1].model) : 0;
     for (int l = 0; l < 4; ++l) { d.contact[l] = p.contact[l]; d.next_contact[l] = p.next_contact[l]; d.td_foot[l] = p.td_foot[l]; }
     d.n_td = p.n_td; d.dt = p.dt; d.mu = p.mu; d.ground_height = p.ground_height; d.BG_alpha = deck->BG_alpha;
+    d.h_min = p.h_min; d.torque_limit = p.torque_limit;
+    for (int l = 0; l < 3; ++l) { d.joint_lb[l] = p.joint_lb[l]; d.joint_ub[l] = p.joint_ub[l]; }
     std::memcpy(d.q, p.q, sizeof(d.q)); std::memcpy(d.r, p.r, sizeof(d.r)); std::memcpy(d.qf, p.qf, sizeof(d.qf));
     std::memcpy(d.w_footreg, p.w_footreg, sizeof(d.w_footreg)); std::memcpy(d.w_swingpos, p.w_swingpos, sizeof(d.w_swingpos));
     std::memcpy(d.w_swingvel, p.w_swingvel, sizeof(d.w_swingvel)); std::memcpy(d.w_tdvel, p.w_tdvel, sizeof(d.w_tdvel));
@@ -266,9 +274,17 @@ extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, 
   CUDA_OK(cudaEventCreate(&H->eve));
   H->max_segs = 9 * CAFE_MAX_PHASES;
   CUDA_OK(cudaMalloc(&H->d_segs, H->max_segs * sizeof(PackSeg)));
-  H->bwd_variant = 0; H->bwd_pb = 4;
-  H->bwd_smem = (size_t)cafe_dev::BwdLayout<24, 24, 0>::total * 4 * sizeof(double);
-  CUDA_OK(cudaFuncSetAttribute(cafe_dev::k_bwd<24, 24, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H->bwd_smem));
+  if (all_hkd) {
+    H->bwd_variant = 0; H->bwd_pb = 4;
+    H->bwd_smem = (size_t)cafe_dev::BwdLayout<24, 24, 0>::total * 4 * sizeof(double);
+    CUDA_OK(cudaFuncSetAttribute(cafe_dev::k_bwd<24, 24, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H->bwd_smem));
+  } else {
+    H->bwd_variant = 1; H->bwd_pb = 3;
+    H->bwd_smem = (size_t)cafe_dev::BwdLayout<36, 12, 12>::total * 3 * sizeof(double);
+    CUDA_OK(cudaFuncSetAttribute(cafe_dev::k_bwd<36, 12, 12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H->bwd_smem));
+  }
+  // the per-(problem,knot) kernels of the whole-body model keep their KKT algebra in thread-local arrays
+  CUDA_OK(cudaDeviceSetLimit(cudaLimitStackSize, 64 * 1024));
   *out = H;
   return 0;
 }

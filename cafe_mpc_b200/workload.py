@@ -36,3 +36,20 @@ def hkd_batch(problem, B, perturb=True):
                 qJ[j] += HKD_QJ_SCALE[j] * (2 * uniform(b, 12 + j) - 1)
         x0[b] = problem.initial_state(body, qJ)
     return x0
+
+
+# MHPC whole-body nominal state (Loco_TO.cpp:49-55): pos (0,0,0.2183), qJ (0,-1.0,2.0) x4, rest 0
+MHPC_NOMINAL = np.zeros(36)
+MHPC_NOMINAL[2] = 0.2183
+MHPC_NOMINAL[6:18] = [0, -1.0, 2.0] * 4
+# scales: pos x,y 0.02, z 0.01; euler 0.05; joints 0.05; base lin vel 0.1; euler rate 0.1; joint vel 0.2
+MHPC_SCALE = np.array([0.02, 0.02, 0.01] + [0.05] * 3 + [0.05] * 12 + [0.1] * 3 + [0.1] * 3 + [0.2] * 12)
+
+
+def mhpc_batch(B, perturb=True):
+    x0 = np.tile(MHPC_NOMINAL, (B, 1))
+    if perturb:
+        for b in range(1, B):  # problem 0 is the nominal problem
+            for j in range(36):
+                x0[b, j] += MHPC_SCALE[j] * (2 * uniform(b, j) - 1)
+    return x0
