@@ -533,6 +533,44 @@ extern "C" long cafe_oracle_get(const char* name, int phase, double* out) {
   return (long)(w - out);
 }
 
+/* dynamics and their partials of phase `phase` at knot k for a given (x, u): xnext[n], y[p], A[n*n], B[n*m], C[p*n], D[p*m]
+ * (column-major); any output may be NULL. For the finite-difference recipe of the reference (test/testKKTDynamics.cpp:39-93). */
+extern "C" int cafe_oracle_dynamics(const CafeDeck* deck, int phase, int k, const double* x, const double* u, double* xnext, double* y,
+                                    double* A, double* B, double* C, double* D) {
+  try {
+    Solver S;
+    S.setup(deck);
+    Phase& P = *S.phases.at(phase);
+    Vec xv(x, x + P.n), uv(u, u + P.m), xn(P.n, 0.0), yv(P.p, 0.0);
+    P.dynamics(xn, yv, xv, uv, k);
+    if (xnext) std::memcpy(xnext, xn.data(), sizeof(double) * P.n);
+    if (y && P.p) std::memcpy(y, yv.data(), sizeof(double) * P.p);
+    if (A || B || C || D) {
+      Mat Am(P.n, P.n), Bm(P.n, P.m), Cm(P.p, P.n), Dm(P.p, P.m);
+      P.dynamics_partial(Am, Bm, Cm, Dm, xv, uv, k);
+      if (A) std::memcpy(A, Am.a.data(), sizeof(double) * Am.a.size());
+      if (B) std::memcpy(B, Bm.a.data(), sizeof(double) * Bm.a.size());
+      if (C && P.p) std::memcpy(C, Cm.a.data(), sizeof(double) * Cm.a.size());
+      if (D && P.p) std::memcpy(D, Dm.a.data(), sizeof(double) * Dm.a.size());
+    }
+    return 0;
+  } catch (const std::exception& e) { std::fprintf(stderr, "cafe_oracle_dynamics: %s\n", e.what()); return -1; }
+}
+
+/* reset map and its Jacobian at the end of phase `phase`: xnext[n_next], Px[n_next*n] column-major */
+extern "C" int cafe_oracle_resetmap(const CafeDeck* deck, int phase, const double* x, double* xnext, double* Px) {
+  try {
+    Solver S;
+    S.setup(deck);
+    Phase& P = *S.phases.at(phase);
+    Vec xv(x, x + P.n);
+    Vec xn = P.resetmap(xv);
+    if (xnext) std::memcpy(xnext, xn.data(), sizeof(double) * xn.size());
+    if (Px) { Mat m = P.resetmap_partial(xv); std::memcpy(Px, m.a.data(), sizeof(double) * m.a.size()); }
+    return (int)xn.size();
+  } catch (const std::exception& e) { std::fprintf(stderr, "cafe_oracle_resetmap: %s\n", e.what()); return -1; }
+}
+
 extern "C" int cafe_oracle_solve(const CafeDeck* deck, const CafeOptions* opt, const double* x0, CafeInfo* info,
                                  double* hist, int hist_cap, double* trace, int trace_cap, double* sol) {
   try {

@@ -32,6 +32,11 @@ int cafe_oracle_solve(const CafeDeck* deck, const CafeOptions* opt, const double
  * Quu Qux H lx lu ly lxx luu lyy l Phix Phixx Px). Returns the number of doubles written or -1. */
 long cafe_oracle_get(const char* name, int phase, double* out);
 
+/* Dynamics (and partials) of one phase at knot k for a given (x, u); reset map (and Jacobian) at a phase end. */
+int cafe_oracle_dynamics(const CafeDeck* deck, int phase, int k, const double* x, const double* u, double* xnext, double* y,
+                         double* A, double* B, double* C, double* D);
+int cafe_oracle_resetmap(const CafeDeck* deck, int phase, const double* x, double* xnext, double* Px);
+
 /* Whole-body continuous-time KKT contact dynamics (WBM::dynamics_continuousTime), for the known-answer test
  * of the reference (test/testKKTDynamics.cpp:95-121). */
 int cafe_oracle_wb_dynamics(double hip_yaw, double BG_alpha, const double* q, const double* v, const double* u,

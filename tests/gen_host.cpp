@@ -26,3 +26,17 @@ extern "C" int gen_eval(const char* name, const double* const* in, double* const
   else return -1;
   return 0;
 }
+
+// whole-body generated routines (only the ones instantiated here are compiled)
+#include "../cafe_mpc_b200/csrc/gen/wb_gen.h"
+extern "C" int gen_eval_wb(const char* name, const double* const* in, double* const* out) {
+  const std::string n(name);
+  auto o = [&](int k) { return [out, k](int i, double v) { out[k][i] = v; }; };
+  using namespace cafe_gen_wb;
+  if (n == "wb_terms") wb_terms(in[0], in[1], o(0), o(1), o(2), o(3), o(4), o(5));
+  else if (n == "wb_feet") wb_feet(in[0], in[1], o(0), o(1), o(2));
+  else if (n == "wb_kin_partials") wb_kin_partials(in[0], in[1], in[2], in[3], o(0), o(1), o(2), o(3));
+  else if (n == "wb_footvel_partial") wb_footvel_partial(in[0], in[1], o(0));
+  else return -1;
+  return 0;
+}

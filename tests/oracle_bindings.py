@@ -61,6 +61,44 @@ def oracle_get(name, phase):
     return buf[:n].copy()
 
 
+def oracle_dynamics(deck, phase, k, x, u, partials=False):
+    from cafe_mpc_b200._ctypes_defs import MODEL_DIMS
+    lib = oracle()
+    n, m, p = MODEL_DIMS[deck.contents.phase[phase].model]
+    x = np.ascontiguousarray(x, dtype=np.float64); u = np.ascontiguousarray(u, dtype=np.float64)
+    xn, y = np.zeros(n), np.zeros(max(p, 1))
+    A, B, Cm, D = np.zeros(n * n), np.zeros(n * m), np.zeros(max(p * n, 1)), np.zeros(max(p * m, 1))
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    null = C.c_void_p()
+    rc = lib.cafe_oracle_dynamics(deck, phase, k, vp(x), vp(u), vp(xn), vp(y), vp(A) if partials else null, vp(B) if partials else null,
+                                  vp(Cm) if partials else null, vp(D) if partials else null)
+    assert rc == 0
+    if not partials:
+        return xn, y[:p]
+    return xn, y[:p], A.reshape(n, n, order="F"), B.reshape(n, m, order="F"), Cm[:p * n].reshape(p, n, order="F"), D[:p * m].reshape(p, m, order="F")
+
+
+def oracle_resetmap(deck, phase, x, jac=False):
+    from cafe_mpc_b200._ctypes_defs import MODEL_DIMS
+    lib = oracle()
+    n = MODEL_DIMS[deck.contents.phase[phase].model][0]
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    xn = np.zeros(36); Px = np.zeros(36 * 36)
+    nn = lib.cafe_oracle_resetmap(deck, phase, x.ctypes.data_as(C.c_void_p), xn.ctypes.data_as(C.c_void_p), Px.ctypes.data_as(C.c_void_p) if jac else C.c_void_p())
+    assert nn > 0
+    return (xn[:nn], Px[:nn * n].reshape(nn, n, order="F")) if jac else xn[:nn]
+
+
+def oracle_wb_dynamics(q, v, u, contact, hip_yaw, BG_alpha=10.0):
+    lib = oracle()
+    lib.cafe_oracle_wb_dynamics.argtypes = [C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    q = np.ascontiguousarray(q, dtype=np.float64); v = np.ascontiguousarray(v, dtype=np.float64); u = np.ascontiguousarray(u, dtype=np.float64)
+    qdd, grf = np.zeros(18), np.zeros(12)
+    c = (C.c_int * 4)(*contact)
+    assert lib.cafe_oracle_wb_dynamics(hip_yaw, BG_alpha, q.ctypes.data, v.ctypes.data, u.ctypes.data, c, qdd.ctypes.data, grf.ctypes.data) == 0
+    return qdd, grf
+
+
 def casadi_eval(name, ins, out_shapes):
     """Evaluate a reference CasADi function (oracle/_ref) on dense inputs; returns dense column-major outputs."""
     lib = oracle()

@@ -1,0 +1,113 @@
+"""GPU suite for the MHPC (whole-body + single-rigid-body, cascaded fidelity) path through the C ABI:
+BASELINE configs 2 (single MHPC trot solve, GPU == CPU) and 3 (batch 1024 MHPC trot on one B200), plus the
+impact-bearing start offset that exercises the WB impact map, touchdown constraints and AL updates."""
+import copy
+import os
+
+import numpy as np
+import pytest
+
+from oracle_bindings import oracle_get, oracle_solve
+
+pytestmark = pytest.mark.gpu
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSV = os.path.join(REPO, "data/Reference/Data/trot/heuristic/quad_reference.csv")
+COUNTS = ("status", "iter", "ls_iter_total", "reg_iter_total", "outer_iter", "n_hist")
+RTOL = 1e-9
+
+
+def relerr(g, o):
+    o = np.asarray(o); g = np.asarray(g)
+    return 0.0 if o.size == 0 else float(np.max(np.abs(g - o)) / max(np.max(np.abs(o)), 1e-6))
+
+
+@pytest.fixture(scope="module")
+def opt(cm):
+    return cm.load_hsddp_setting(os.path.join(REPO, "data/MHPC/settings/ddp_setting.info"))
+
+
+def solve_gpu(cm, prob, opt, x0):
+    s = cm.MultiPhaseDDP(prob, 0, len(x0))
+    s.set_initial_condition(x0)
+    s.solve(opt)
+    return s
+
+
+def compare_with_oracle(cm, prob, opt, x0, s, which):
+    info = s.get_solver_info(); hist = s.get_history(256); sol = s.get_solution()
+    for b in which:
+        oi, oh, ot, osol = oracle_solve(prob.deck, opt, x0[b])
+        assert [info[b][k] for k in COUNTS] == [oi[k] for k in COUNTS], b          # bit-exact counters
+        np.testing.assert_allclose(hist[b, :oi["n_hist"], 0], oh[:, 0], rtol=RTOL)  # per-iteration cost
+        gp, op = cm.unpack_solution(prob.deck, sol[b]), cm.unpack_solution(prob.deck, osol)
+        for pg, po in zip(gp, op):
+            for name in ("Xbar", "Ubar", "Y", "K", "dU", "Qu", "Quu", "Qux", "G"):  # final trajectories and gains
+                assert relerr(pg[name], po[name]) < RTOL, (b, name)
+
+
+@pytest.mark.parametrize("k0", [0, 20])
+def test_single_mhpc_solve_matches_oracle_and_golden(cm, opt, k0):
+    from cafe_mpc_b200 import workload
+    prob = cm.MHPCProblem(CSV, k0=k0)
+    x0 = workload.mhpc_batch(4)
+    s = solve_gpu(cm, prob, opt, x0)
+    compare_with_oracle(cm, prob, opt, x0, s, range(4))
+    g = np.load(os.path.join(REPO, "tests/golden/mhpc_trot.npz"))
+    info = s.get_solver_info()
+    key = "k0" if k0 == 0 else "k20"
+    for b in (0, 3):
+        assert [info[b][k] for k in COUNTS] == list(g["%s_counts_%d" % (key, b)])
+        assert abs(info[b]["cost"] - g["%s_final_%d" % (key, b)][0]) <= RTOL * abs(g["%s_final_%d" % (key, b)][0])
+    if k0 == 20:
+        assert all(i["outer_iter"] > 1 for i in info)  # the AL loop really ran
+
+
+@pytest.mark.parametrize("k0", [0, 20])
+def test_mhpc_one_iteration_per_knot_parity(cm, opt, k0):
+    """Dynamics / cost / constraint partials (A, B, C, D, l**), reset-map Jacobian and every backward-sweep product per knot:
+    codegen'd analytic derivatives on the GPU vs dual-number RNEA + reference CasADi partials + explicit KKT inverse in the oracle."""
+    from cafe_mpc_b200 import workload
+    prob = cm.MHPCProblem(CSV, k0=k0)
+    o1 = copy.copy(opt)
+    o1.max_DDP_iter = 1; o1.max_AL_iter = 1; o1.cost_thresh = 1e30; o1.dynamics_feas_thresh = 1e30
+    x0 = workload.mhpc_batch(4)
+    s = solve_gpu(cm, prob, o1, x0)
+    for b in (0, 2):
+        oracle_solve(prob.deck, o1, x0[b])
+        for ph in range(3):
+            for name in ("X", "U", "Y", "Defect", "l", "lx", "lu", "ly", "lxx", "luu", "lyy", "A", "B", "C", "D", "Phix", "Phixx"):
+                assert relerr(s.debug_get(name, ph, b), oracle_get(name, ph)) < 1e-11, (name, ph)
+            for name in ("Quu", "Qux", "Qu", "K", "dU", "G", "dX"):
+                assert relerr(s.debug_get(name, ph, b), oracle_get(name, ph)) < 1e-10, (name, ph)
+        for ph in range(2):
+            assert relerr(s.debug_get("Px", ph, b), oracle_get("Px", ph)) < 1e-11, ph
+
+
+def test_mhpc_perturbed_batch_counts_bit_exact(cm, opt):
+    from cafe_mpc_b200 import workload
+    prob = cm.MHPCProblem(CSV)
+    x0 = workload.mhpc_batch(40)
+    s = solve_gpu(cm, prob, opt, x0)
+    compare_with_oracle(cm, prob, opt, x0, s, range(40))
+
+
+def test_mhpc_batch_1024_properties(cm, opt):
+    """BASELINE config 3: 1024 MHPC trot problems on one B200 — determinism, convergence flags, spot checks vs the oracle."""
+    from cafe_mpc_b200 import workload
+    prob = cm.MHPCProblem(CSV)
+    B = 1024
+    x0 = workload.mhpc_batch(B)
+    s = solve_gpu(cm, prob, opt, x0)
+    i1 = s.get_solver_info(); c1 = s.get_commands(8)
+    s.solve(opt)
+    i2 = s.get_solver_info(); c2 = s.get_commands(8)
+    assert np.array_equal(c1, c2) and i1 == i2
+    assert all(i["status"] == 0 for i in i1)
+    assert all(i["feas"] <= opt.dynamics_feas_thresh for i in i1)
+    assert all(1 <= i["iter"] <= opt.max_AL_iter * opt.max_DDP_iter for i in i1)
+    compare_with_oracle(cm, prob, opt, x0, s, (0, 1, 333, 512, 1023))
+    # value-function property: the feedback gain reduces the quadratic model, Quu of every knot is positive definite
+    sol = cm.unpack_solution(prob.deck, s.get_solution(5, 1)[0])
+    for ph in sol:
+        for Quu in ph["Quu"]:
+            assert np.all(np.linalg.eigvalsh(0.5 * (Quu + Quu.T)) > 0)

@@ -21,3 +21,19 @@ for b in range(8):
     rows.append([i[k] for k in ("status", "iter", "ls_iter_total", "reg_iter_total", "outer_iter", "n_hist")] + [i["cost"], i["feas"]])
 np.savez_compressed(os.path.join(R, "tests/golden/hkd_trot_batch8.npz"), x0=x0, rows=np.array(rows))
 print(counts, info)
+
+# ---- MHPC (whole-body + SRB) trot, t0 = 0 and the impact-bearing start offset k0 = 20
+opt2 = cm.load_hsddp_setting(os.path.join(cm.api.DATA, "MHPC/settings/ddp_setting.info"))
+csv = os.path.join(cm.api.DATA, "Reference/Data/trot/heuristic/quad_reference.csv")
+x0m = workload.mhpc_batch(4)
+out = {"x0": x0m}
+for key, k0 in (("k0", 0), ("k20", 20)):
+    pm = cm.MHPCProblem(csv, k0=k0)
+    for b in (0, 3):
+        i, h, t, s = oracle_solve(pm.deck, opt2, x0m[b])
+        out["%s_counts_%d" % (key, b)] = np.array([i[k] for k in ("status", "iter", "ls_iter_total", "reg_iter_total", "outer_iter", "n_hist")])
+        out["%s_hist_%d" % (key, b)] = h
+        out["%s_sol_%d" % (key, b)] = s
+        out["%s_final_%d" % (key, b)] = np.array([i["cost"], i["feas"], i["max_tconstr"], i["max_pconstr"]])
+        print(key, b, i)
+np.savez_compressed(os.path.join(R, "tests/golden/mhpc_trot.npz"), **out)
