@@ -27,7 +27,22 @@ F_LIN = {0: 6960.0, 1: 8200.0, 2: 1800.0}        # linear rollout per knot
 
 
 def workload_name(args):
-    return "HKD trot (3 phases h=11/25/24, n=m=24), %d perturbed problems per GPU" % args.batch
+    if args.workload == "hkd":
+        return "HKD trot (3 phases h=11/25/24, n=m=24), %d perturbed problems per GPU" % args.batch
+    return "MHPC trot (WB h=11 + WB h=14, n=36 m=12 p=12; SRB h=10, n=m=12), %d perturbed problems per GPU" % args.batch
+
+
+def make_problem(workload):
+    import cafe_mpc_b200 as cm
+    from cafe_mpc_b200 import workload as wl
+    csv = os.path.join(REPO, "data/Reference/Data/trot/heuristic/quad_reference.csv")
+    if workload == "hkd":
+        prob = cm.HKDProblem(csv)
+        opt = cm.load_hsddp_setting(os.path.join(REPO, "data/HKDMPC/settings/ddp_setting.info"))
+        return prob, opt, (lambda B: wl.hkd_batch(prob, B)), 24
+    prob = cm.MHPCProblem(csv)
+    opt = cm.load_hsddp_setting(os.path.join(REPO, "data/MHPC/settings/ddp_setting.info"))
+    return prob, opt, (lambda B: wl.mhpc_batch(B)), 36
 
 
 class ClockSampler(threading.Thread):
@@ -63,27 +78,25 @@ class ClockSampler(threading.Thread):
 
 
 def _cpu_worker(task):
-    import cafe_mpc_b200 as cm
     from oracle_bindings import oracle_solve
-    x0s, = task
-    prob = cm.HKDProblem(os.path.join(REPO, "data/Reference/Data/trot/heuristic/quad_reference.csv"))
-    opt = cm.load_hsddp_setting(os.path.join(REPO, "data/HKDMPC/settings/ddp_setting.info"))
+    x0s, workload = task
+    prob, opt, _, _ = make_problem(workload)
     t = time.perf_counter()
     for x in x0s:
         oracle_solve(prob.deck, opt, x)
     return time.perf_counter() - t
 
 
-def cpu_sample(x0, cores, per_core):
+def cpu_sample(x0, cores, per_core, workload):
     """One single-threaded oracle instance per host core over disjoint slices."""
     import multiprocessing as mp
     n = min(len(x0), cores * per_core)
     chunks = [x0[i:n:cores] for i in range(cores)]
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
-        pool.map(_cpu_worker, [(c[:1],) for c in chunks])  # warm-up: imports, page-in
+        pool.map(_cpu_worker, [(c[:1], workload) for c in chunks])  # warm-up: imports, page-in
         t = time.perf_counter()
-        pool.map(_cpu_worker, [(c,) for c in chunks])
+        pool.map(_cpu_worker, [(c, workload) for c in chunks])
         wall = time.perf_counter() - t
     return n / wall, n
 
@@ -92,15 +105,13 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import cafe_mpc_b200 as cm
-    from cafe_mpc_b200 import workload
     cores = len(os.sched_getaffinity(0))
-    prob = cm.HKDProblem(os.path.join(REPO, "data/Reference/Data/trot/heuristic/quad_reference.csv"))
+    prob, opt, gen_x0, n0 = make_problem(args.workload)
     per_core = args.cpu_per_core
-    x0 = workload.hkd_batch(prob, min(args.batch, cores * per_core))
+    x0 = gen_x0(min(args.batch, cores * per_core))
     vals = []
     for i in range(args.warmup + args.steps):
-        v, n = cpu_sample(x0, cores, per_core)
+        v, n = cpu_sample(x0, cores, per_core, args.workload)
         if i >= args.warmup:
             vals.append(v)
     v = sum(vals) / len(vals)
@@ -120,6 +131,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--batch", type=int, default=4096, help="problems per GPU")
+    ap.add_argument("--workload", default="mhpc", choices=["mhpc", "hkd"])
     ap.add_argument("--gain-knots", type=int, default=8)
     ap.add_argument("--cpu-per-core", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -142,9 +154,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B = args.batch
     Bg = B * world
-    prob = cm.HKDProblem(os.path.join(REPO, "data/Reference/Data/trot/heuristic/quad_reference.csv"))
-    opt = cm.load_hsddp_setting(os.path.join(REPO, "data/HKDMPC/settings/ddp_setting.info"))
-    x0_all = workload.hkd_batch(prob, Bg) if Bg <= 8192 else np.tile(workload.hkd_batch(prob, 8192), ((Bg + 8191) // 8192, 1))[:Bg]
+    prob, opt, gen_x0, n0 = make_problem(args.workload)
+    x0_all = gen_x0(Bg) if Bg <= 8192 else np.tile(gen_x0(8192), ((Bg + 8191) // 8192, 1))[:Bg]
     lo, hi = cdist.shard_range(Bg, world, rank)
     x0 = np.ascontiguousarray(x0_all[lo:hi])
     solver = cm.MultiPhaseDDP(prob, local, B)
@@ -227,7 +238,7 @@ def main():
                 "kernel_ms": tm["ms"], "hbm_peak_gbs": _hbm_peak()}
         if not args.no_cpu_baseline:
             cores = len(os.sched_getaffinity(0))
-            v, n = cpu_sample(x0_all[: cores * args.cpu_per_core], cores, args.cpu_per_core)
+            v, n = cpu_sample(x0_all[: cores * args.cpu_per_core], cores, args.cpu_per_core, args.workload)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": "%d problems (first of the same SplitMix64 table), one single-threaded oracle instance per core" % n}
     if rank == 0:
@@ -237,9 +248,10 @@ def main():
             "ms_per_step": 1e3 * wall / args.steps, "device_ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args), "global_batch": Bg, "per_gpu_batch": B, "parallelism": "batch sharded over %d GPU(s), no collective in the solve" % world,
-                       "settings": "HKDMPC/settings (10x5 iteration caps, alpha 0.1)", "l2": "working set per solve (>8 GB of per-problem arrays) exceeds the 126 MB L2; no flush needed",
+                       "settings": "HKDMPC/settings (10x5 iteration caps, alpha 0.1)" if args.workload == "hkd" else "MHPC/settings (10x20 iteration caps, alpha 0.5, BG_alpha 10, cost_weights_regular, constraint_params_regular)",
+                       "l2": "working set per solve (GBs of per-problem arrays) exceeds the 126 MB L2; no flush needed",
                        "mean_ddp_iterations": sum(it) / len(it), "max_ddp_iterations": max(it)},
-            "e2e": {"value": Bg * args.steps / wall_e2e, "unit": UNIT, "h2d_bytes_per_step": int(B * 24 * 8), "d2h_bytes_per_step": int(B * rec * 8),
+            "e2e": {"value": Bg * args.steps / wall_e2e, "unit": UNIT, "h2d_bytes_per_step": int(B * n0 * 8), "d2h_bytes_per_step": int(B * rec * 8),
                     "what": "cafe_gpu_solve_batch(host x0) + cafe_gpu_get_commands (Xbar,Ubar,Y all knots; K,Qu,Quu,Qux first %d knots)%s" % (args.gain_knots, " + NCCL gather to rank 0" if world > 1 else "")},
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu}))
     if world > 1:

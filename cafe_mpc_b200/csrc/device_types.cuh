@@ -43,6 +43,9 @@ struct PhaseDev {
 
 struct CtrlDev {
   int *active, *do_ls, *sel, *accepted;
+  int *ls_found, *ls_fail;            // staged line search: first successful step size found / divergence flag of the kept trial
+  double *ls_cost, *ls_feas, *ls_mt, *ls_mp, *ls_merit;  // summary of the kept (first successful, else last evaluated) trial
+  int* n_pending;                     // problems that still need more step sizes
   int *iter_ou, *iter_in, *iter, *ls_total, *reg_total, *n_hist, *status;
   double *reg, *cost, *merit, *feas, *merit_rho, *dV1, *dV2, *cost_prev, *merit_prev;
   double *max_t, *max_p, *max_t_prev, *max_p_prev;

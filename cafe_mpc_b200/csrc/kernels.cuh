@@ -120,14 +120,15 @@ __device__ void roll_knot(const SolverDev& S, int pi, int k, int a, int b) {
   }
 }
 
-__global__ void __launch_bounds__(128) k_roll(const SolverDev* __restrict__ Sp, int NA) {
+// step sizes [a0, a1) of the ladder; problems whose line search already succeeded are skipped
+__global__ void __launch_bounds__(128) k_roll(const SolverDev* __restrict__ Sp, int a0, int a1) {
   const SolverDev& S = *Sp;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int b = (int)(t % S.ldb);
   const long long r = t / S.ldb;
-  const int gk = (int)(r % S.n_knots), a = (int)(r / S.n_knots);
-  if (a >= NA || b >= S.B) return;
-  if (!S.c.active[b] || !S.c.do_ls[b]) return;
+  const int gk = (int)(r % S.n_knots), a = a0 + (int)(r / S.n_knots);
+  if (a >= a1 || b >= S.B) return;
+  if (!S.c.active[b] || !S.c.do_ls[b] || S.c.ls_found[b]) return;
   const int pi = S.knot_phase[gk], k = S.knot_k[gk];
   switch (S.ph[pi].model) {
     case CAFE_MODEL_HKD: roll_knot<HKDModel>(S, pi, k, a, b); break;
@@ -259,6 +260,29 @@ __device__ void reduce_trial(const SolverDev& S, int a, int b, double& cost, dou
   feas = sqrt(fs);
 }
 
+// Armijo test over the step sizes [a0, a1) that k_roll has just evaluated (MultiPhaseDDP::line_search, MultiPhaseDDP.cpp:95-133):
+// keeps the FIRST (largest) successful step size, else the last evaluated one; counts the problems that need more trials.
+__global__ void k_ls_scan(const SolverDev* __restrict__ Sp, int a0, int a1) {
+  const SolverDev& S = *Sp;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= S.B) return;
+  const CtrlDev& c = S.c;
+  if (!c.active[b] || !c.do_ls[b] || c.ls_found[b]) return;
+  const CafeOptions& o = S.opt;
+  const double merit_prev = c.merit_prev[b], feas_prev = c.feas[b], rho = c.merit_rho[b], dV1 = c.dV1[b], dV2 = c.dV2[b];
+  for (int a = a0; a < a1; ++a) {
+    double cost, feas, mt, mp; int fail;
+    reduce_trial(S, a, b, cost, feas, mt, mp, fail);
+    const double eps = S.eps[a];
+    const double merit = cost + rho * feas;
+    const double exp_cost_change = eps * dV1 + 0.5 * eps * eps * dV2;
+    const double exp_merit_change = exp_cost_change - eps * rho * feas_prev;
+    c.sel[b] = a; c.ls_cost[b] = cost; c.ls_feas[b] = feas; c.ls_mt[b] = mt; c.ls_mp[b] = mp; c.ls_fail[b] = fail; c.ls_merit[b] = merit;
+    if ((merit <= merit_prev + o.gamma * exp_merit_change) && !fail) { c.ls_found[b] = 1; return; }
+  }
+  if (a1 < S.NA) atomicAdd(c.n_pending, 1);
+}
+
 // mode 0: initial rollout bookkeeping (MultiPhaseDDP.cpp:238-261); mode 1: after a DDP iteration
 __global__ void k_select(const SolverDev* __restrict__ Sp, int mode) {
   const SolverDev& S = *Sp;
@@ -267,8 +291,8 @@ __global__ void k_select(const SolverDev* __restrict__ Sp, int mode) {
   const CtrlDev& c = S.c;
   const CafeOptions& o = S.opt;
   const int ldb = S.ldb;
-  c.sel[b] = -1;
-  if (!c.active[b]) return;
+  if (!c.active[b]) { c.sel[b] = -1; return; }
+  if (mode == 0 || !c.do_ls[b]) c.sel[b] = -1;
   bool inner_done = false;
   if (mode == 0) {
     double cost, feas, mt, mp; int fail;
@@ -290,22 +314,14 @@ __global__ void k_select(const SolverDev* __restrict__ Sp, int mode) {
     const int it = c.iter[b] - 1;  // trace slot of this iteration
     double* tr = (it >= 0 && it < CAFE_HIST_CAP) ? c.trace + ((size_t)it * 12) * ldb + b : nullptr;
     if (c.do_ls[b]) {
-      const double merit_prev = c.merit_prev[b], cost_prev = c.cost_prev[b], feas_prev = c.feas[b], rho = c.merit_rho[b];
-      const double dV1 = c.dV1[b], dV2 = c.dV2[b];
-      bool success = false;
-      int sel = S.NA - 1, n_ls = S.NA;
-      double cost_s = 0, feas_s = 0, mt_s = 0, mp_s = 0; int fail_s = 0;
-      for (int a = 0; a < S.NA; ++a) {
-        double cost, feas, mt, mp; int fail;
-        reduce_trial(S, a, b, cost, feas, mt, mp, fail);
-        const double eps = S.eps[a];
-        const double merit = cost + rho * feas;
-        const double exp_cost_change = eps * dV1 + 0.5 * eps * eps * dV2;
-        const double exp_merit_change = exp_cost_change - eps * rho * feas_prev;
-        cost_s = cost; feas_s = feas; mt_s = mt; mp_s = mp; fail_s = fail;
-        if ((merit <= merit_prev + o.gamma * exp_merit_change) && !fail) { success = true; sel = a; n_ls = a + 1; c.merit[b] = merit; break; }
-      }
-      c.sel[b] = sel; c.accepted[b] = success ? 1 : 0;
+      const double merit_prev = c.merit_prev[b], cost_prev = c.cost_prev[b];
+      const bool success = c.ls_found[b] != 0;
+      const int sel = c.sel[b];
+      const int n_ls = success ? sel + 1 : S.NA;
+      const double cost_s = c.ls_cost[b], feas_s = c.ls_feas[b], mt_s = c.ls_mt[b], mp_s = c.ls_mp[b];
+      const int fail_s = c.ls_fail[b];
+      if (success) c.merit[b] = c.ls_merit[b];
+      c.accepted[b] = success ? 1 : 0;
       c.ls_total[b] += n_ls;
       c.feas[b] = feas_s; c.max_t[b] = mt_s; c.max_p[b] = mp_s;
       for (int pi = 0; pi < S.n_phases; ++pi) for (int i = 0; i < S.ph[pi].n_td; ++i) S.ph[pi].hval[(size_t)i * ldb + b] = S.ph[pi].ht[((size_t)sel * 4 + i) * ldb + b];
@@ -745,6 +761,7 @@ __global__ void __launch_bounds__(CAFE_NW* PB) k_bwd(const SolverDev* __restrict
       c.merit[b] = merit; c.cost_prev[b] = cost; c.merit_prev[b] = merit;
       if (tr) { tr[(size_t)2 * ldb] = dV1; tr[(size_t)3 * ldb] = dV2; tr[(size_t)4 * ldb] = rho; }
       c.do_ls[b] = ((dV_abs < o.cost_thresh) && (feas <= o.dynamics_feas_thresh)) ? 0 : 1;
+      c.ls_found[b] = 0;
     }
   }
 }

@@ -124,6 +124,8 @@ void carve(CafeHandle* H, Carver& cv, size_t& zero_bytes) {
   // ---- region re-zeroed at every solve
   CtrlDev& c = S.c;
   c.active = cv.take<int>(ldb); c.do_ls = cv.take<int>(ldb); c.sel = cv.take<int>(ldb); c.accepted = cv.take<int>(ldb);
+  c.ls_found = cv.take<int>(ldb); c.ls_fail = cv.take<int>(ldb); c.n_pending = cv.take<int>(64);
+  c.ls_cost = cv.take<double>(ldb); c.ls_feas = cv.take<double>(ldb); c.ls_mt = cv.take<double>(ldb); c.ls_mp = cv.take<double>(ldb); c.ls_merit = cv.take<double>(ldb);
   c.iter_ou = cv.take<int>(ldb); c.iter_in = cv.take<int>(ldb); c.iter = cv.take<int>(ldb); c.ls_total = cv.take<int>(ldb);
   c.reg_total = cv.take<int>(ldb); c.n_hist = cv.take<int>(ldb); c.status = cv.take<int>(ldb);
   c.n_active = cv.take<int>(64);
@@ -333,15 +335,13 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
     SolverDev S0 = S;  // same pointers, ladder {0}
     S0.NA = 1; S0.eps[0] = 0.0;
     CUDA_OK(cudaMemcpyAsync(H->dS, &S0, sizeof(SolverDev), cudaMemcpyHostToDevice, st));
-    timed(H, 0, [&] { cafe_dev::k_roll<<<g_knots, tpb, 0, st>>>(H->dS, 1); });
+    timed(H, 0, [&] { cafe_dev::k_roll<<<g_knots, tpb, 0, st>>>(H->dS, 0, 1); });
     timed(H, 1, [&] { cafe_dev::k_select<<<(B + 127) / 128, 128, 0, st>>>(H->dS, 0); });
     timed(H, 2, [&] { cafe_dev::k_accept<<<g_knots, tpb, 0, st>>>(H->dS); });
     CUDA_OK(cudaStreamSynchronize(st));  // S0 must stay alive until the copy has been consumed
     CUDA_OK(cudaMemcpyAsync(H->dS, &S, sizeof(SolverDev), cudaMemcpyHostToDevice, st));
   }
   const int max_ticks = opt->max_AL_iter * opt->max_DDP_iter + 2;
-  const long long nthr_roll = nthr_knots * S.NA;
-  const unsigned g_roll = (unsigned)((nthr_roll + tpb - 1) / tpb);
   for (int tick = 0; tick < max_ticks; ++tick) {
     CUDA_OK(cudaMemcpyAsync(H->h_nactive, S.c.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
@@ -350,7 +350,18 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
     timed(H, 3, [&] { cafe_dev::k_lq<<<g_knots, tpb, 0, st>>>(H->dS); });
     timed(H, 4, [&] { launch_bwd(H); });
     CUDA_OK(cudaMemsetAsync(H->d_fail, 0, H->fail_bytes, st));
-    timed(H, 0, [&] { cafe_dev::k_roll<<<g_roll, tpb, 0, st>>>(H->dS, S.NA); });
+    // staged line search: step sizes are evaluated in growing groups; most problems accept one of the first
+    for (int a0 = 0, width = 1; a0 < S.NA; a0 += width, width *= 2) {
+      const int a1 = (a0 + width < S.NA) ? a0 + width : S.NA;
+      const unsigned g_stage = (unsigned)((nthr_knots * (a1 - a0) + tpb - 1) / tpb);
+      timed(H, 0, [&] { cafe_dev::k_roll<<<g_stage, tpb, 0, st>>>(H->dS, a0, a1); });
+      CUDA_OK(cudaMemsetAsync(S.c.n_pending, 0, sizeof(int), st));
+      timed(H, 1, [&] { cafe_dev::k_ls_scan<<<(B + 127) / 128, 128, 0, st>>>(H->dS, a0, a1); });
+      if (a1 >= S.NA) break;
+      CUDA_OK(cudaMemcpyAsync(H->h_nactive + 1, S.c.n_pending, sizeof(int), cudaMemcpyDeviceToHost, st));
+      CUDA_OK(cudaStreamSynchronize(st));
+      if (H->h_nactive[1] == 0) break;
+    }
     CUDA_OK(cudaMemsetAsync(S.c.n_active, 0, sizeof(int), st));
     timed(H, 1, [&] { cafe_dev::k_select<<<(B + 127) / 128, 128, 0, st>>>(H->dS, 1); });
     timed(H, 2, [&] { cafe_dev::k_accept<<<g_knots, tpb, 0, st>>>(H->dS); });
