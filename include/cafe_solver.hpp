@@ -1,0 +1,96 @@
+// cafe_solver.hpp — header-only C++ host mirror of the reference's solver-facing API on top of the C ABI
+// (include/cafe_gpu.h). Method names and call order follow the reference (file:line under /root/reference):
+//   loadHSDDPSetting(filename, option)                    HSDDPSolver/common/HSDDP_CompoundTypes.h:57-82
+//   HKDProblem / MHPCProblem ::initialization()           HKDMPC/HKD-TrajOpt/HKDProblem.cpp:15, MHPC/MHPC-Trajopt/MHPCProblem.cpp:13
+//   MultiPhaseDDP::set_multiPhaseProblem / set_initial_condition / solve / get_solver_info / get_actual_cost ...
+//                                                          HSDDPSolver/header/MultiPhaseDDP.h:33-93
+// The reference solves ONE problem per MultiPhaseDDP object; this mirror solves a batch that shares the phase deck.
+// Errors: the reference prints and returns void; here every failure throws cafe::Error (nothing crosses the C ABI as an exception).
+#pragma once
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "cafe_gpu.h"
+
+namespace cafe {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+inline void check(int rc) { if (rc != 0) throw Error(rc, cafe_last_error()); }
+
+typedef CafeOptions HSDDP_OPTION;
+inline void loadHSDDPSetting(const std::string& filename, HSDDP_OPTION& setting) { check(cafe_options_load(filename.c_str(), &setting)); }
+
+class ProblemBase {
+ public:
+  ProblemBase() {}
+  ProblemBase(const ProblemBase&) = delete;
+  ProblemBase& operator=(const ProblemBase&) = delete;
+  ~ProblemBase() { if (h_) cafe_deck_free(h_); }
+  const CafeDeck* deck() const { return cafe_deck_get(h_); }
+  int n_phases() const { return deck()->n_phases; }
+ protected:
+  CafeDeckHandle* h_ = nullptr;
+};
+
+struct HKDPlanConfig { float plan_duration = 0.6f; float timeStep = 0.01f; int nsteps_between_mpc = 2; };  // HKDMPC.cpp:26-28
+
+class HKDProblem : public ProblemBase {
+ public:
+  // reference_csv: Reference/Data/<gait>/quad_reference.csv (loaded with reorder = true); constraint file: HKDMPC/settings/constraint_params.info
+  void initialization(const std::string& reference_csv, const std::string& constraint_params_info, const HKDPlanConfig& cfg = HKDPlanConfig(), int k0 = 0) {
+    if (h_) { cafe_deck_free(h_); h_ = nullptr; }
+    check(cafe_deck_build_hkd(reference_csv.c_str(), constraint_params_info.c_str(), cfg.plan_duration, cfg.timeStep, cfg.nsteps_between_mpc, k0, &h_));
+  }
+  // compute_hkd_state (HKDModel.h:66-96) with the first phase's contact; body = [eul, pos, omega, vel]
+  std::vector<double> initial_state(const double body[12], const double qJ[12]) const {
+    std::vector<double> x0(24);
+    check(cafe_hkd_state(body, qJ, deck()->phase[0].contact, x0.data()));
+    return x0;
+  }
+};
+
+class MHPCProblem : public ProblemBase {
+ public:
+  // mhpc_config_info: MHPC/settings/mhpc_config.info; settings_root: directory that plays the reference's "../"
+  void initialization(const std::string& reference_csv, const std::string& mhpc_config_info, const std::string& settings_root, int k0 = 0) {
+    if (h_) { cafe_deck_free(h_); h_ = nullptr; }
+    check(cafe_deck_build_mhpc(reference_csv.c_str(), mhpc_config_info.c_str(), settings_root.c_str(), k0, &h_));
+  }
+};
+
+class MultiPhaseDDP {
+ public:
+  MultiPhaseDDP() {}
+  MultiPhaseDDP(const MultiPhaseDDP&) = delete;
+  MultiPhaseDDP& operator=(const MultiPhaseDDP&) = delete;
+  ~MultiPhaseDDP() { if (h_) cafe_gpu_destroy(h_); }
+
+  void set_multiPhaseProblem(const ProblemBase& problem, int max_batch, int device = 0) {
+    if (h_) { cafe_gpu_destroy(h_); h_ = nullptr; }
+    deck_ = problem.deck();
+    check(cafe_gpu_create(deck_, device, max_batch, &h_));
+  }
+  // x0: B rows of the first phase's state dimension
+  void set_initial_condition(const std::vector<double>& x0, int B) { x0_ = x0; B_ = B; }
+  void solve(HSDDP_OPTION& option) { check(cafe_gpu_solve_batch(h_, x0_.data(), B_, &option)); }
+
+  std::vector<CafeInfo> get_solver_info() const { std::vector<CafeInfo> v(B_); check(cafe_gpu_get_info(h_, v.data())); return v; }
+  // cost / dynamics feasibility / terminal / path constraint buffers (get_solver_info(cost_out, ...), MultiPhaseDDP.cpp:554-563)
+  std::vector<double> get_history(int cap) const { std::vector<double> v((size_t)B_ * cap * 4); check(cafe_gpu_get_history(h_, v.data(), cap)); return v; }
+  long solution_size() const { return cafe_solution_size(deck_); }
+  std::vector<double> get_solution(int b0, int nb) const { std::vector<double> v((size_t)nb * solution_size()); check(cafe_gpu_get_solution(h_, b0, nb, v.data())); return v; }
+  long command_size(int n_gain_knots) const { return cafe_command_size(deck_, n_gain_knots); }
+  std::vector<double> get_commands(int n_gain_knots) const { std::vector<double> v((size_t)B_ * command_size(n_gain_knots)); check(cafe_gpu_get_commands(h_, n_gain_knots, v.data())); return v; }
+  double solve_ms() const { double ms = 0; check(cafe_gpu_get_solve_ms(h_, &ms)); return ms; }
+
+ private:
+  CafeHandle* h_ = nullptr;
+  const CafeDeck* deck_ = nullptr;
+  std::vector<double> x0_;
+  int B_ = 0;
+};
+
+}  // namespace cafe

@@ -223,3 +223,17 @@ def test_gpu_create_fails_loudly_without_device(cm, hkd_problem):
     with pytest.raises(CafeError) as e:
         cm.MultiPhaseDDP(hkd_problem, 0, 4)
     assert e.value.code == -2  # CAFE_ERR_CUDA: no CPU fallback
+
+
+def test_cpp_host_mirror_compiles_and_fails_loudly_without_gpu(cm, tmp_path):
+    """include/cafe_solver.hpp + examples/mhpc_batch.cpp: the C++ mirror of the reference API links against the C ABI;
+    without a device it reports CAFE_ERR_CUDA (no CPU fallback), with a device it solves."""
+    import torch
+    exe = str(tmp_path / "mhpc_batch")
+    subprocess.run(["g++", "-std=c++17", "-I" + os.path.join(REPO, "include"), os.path.join(REPO, "examples/mhpc_batch.cpp"),
+                    "-L" + os.path.join(REPO, "cafe_mpc_b200"), "-lcafe_gpu", "-Wl,-rpath," + os.path.join(REPO, "cafe_mpc_b200"), "-o", exe], check=True)
+    r = subprocess.run([exe, os.path.join(REPO, "data"), "8"], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and "solved 8 MHPC problems" in r.stdout
+    else:
+        assert r.returncode == 1 and "no CUDA device" in r.stderr
