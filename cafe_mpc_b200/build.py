@@ -11,13 +11,14 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libcafe_gpu.so")
 
-# source -> extra dependencies (besides itself and include/*.h)
+# source -> dependencies besides itself (paths relative to csrc/)
+ABI = ["../../include/cafe_gpu.h", "../../include/cafe_deck.h"]
 SOURCES = {
-    "solver.cu": ["kernels.cuh", "device_types.cuh", "model_hkd.cuh", "model_srb.cuh", "model_wb.cuh", "gen/hkd_gen.h", "gen/srb_gen.h"],
+    "solver.cu": ["kernels.cuh", "device_types.cuh", "model_hkd.cuh", "model_srb.cuh", "model_wb.cuh", "gen/hkd_gen.h", "gen/srb_gen.h"] + ABI,
     "wb_gen_wrappers.cu": ["gen/wb_gen.h"],
-    "host/abi_host.cpp": ["host/problem_builders.h", "host/quad_reference.h"],
-    "host/hkd_problem.cpp": ["host/problem_builders.h", "host/quad_reference.h", "host/info_reader.h", "gen/hkd_gen.h"],
-    "host/mhpc_problem.cpp": ["host/problem_builders.h", "host/quad_reference.h", "host/info_reader.h"],
+    "host/abi_host.cpp": ["host/problem_builders.h", "host/quad_reference.h"] + ABI,
+    "host/hkd_problem.cpp": ["host/problem_builders.h", "host/quad_reference.h", "host/info_reader.h", "gen/hkd_gen.h"] + ABI,
+    "host/mhpc_problem.cpp": ["host/problem_builders.h", "host/quad_reference.h", "host/info_reader.h"] + ABI,
     "host/quad_reference.cpp": ["host/quad_reference.h"],
 }
 
@@ -40,13 +41,11 @@ def _stale(target, deps):
 def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(OBJ, exist_ok=True)
-    inc = os.path.join(HERE, "..", "include")
-    incs = [os.path.join(inc, f) for f in os.listdir(inc)]
     objs, logs, rebuilt = [], [], False
     for src, deps in SOURCES.items():
         obj = os.path.join(OBJ, src.replace("/", "_") + ".o")
         objs.append(obj)
-        all_deps = [os.path.join(CSRC, src)] + [os.path.join(CSRC, d) for d in deps] + incs
+        all_deps = [os.path.join(CSRC, src)] + [os.path.join(CSRC, d) for d in deps]
         if force or _stale(obj, all_deps):
             cmd = [nvcc] + NVCC_FLAGS + ["-c", "-o", obj, os.path.join(CSRC, src)]
             res = subprocess.run(cmd, capture_output=True, text=True)
