@@ -10,6 +10,13 @@
 #include "../../include/cafe_deck.h"
 
 #define CAFE_MAX_ALPHAS 12
+// per-(problem, WB knot) hand-off from k_lq to k_lq_wb_dense: chol(M) | Y = L^-1 Jc^T | chol(S) | R = [dtau_dq' dtau_dv] | a = [da_dq da_dv] (active rows)
+#define CAFE_KKT_L 0
+#define CAFE_KKT_Y 324
+#define CAFE_KKT_LS 540
+#define CAFE_KKT_R 684
+#define CAFE_KKT_A 1332
+#define CAFE_KKT_PACK 1764
 #define CAFE_MAX_KNOTS 256
 #define CAFE_HIST_CAP 256
 
@@ -29,6 +36,7 @@ struct PhaseDev {
   double *A, *Bm, *C, *D;                  // [h][n*n | n*m | p*n | p*m][ldb], column-major per knot
   double *lx, *lu, *ly, *lxx, *luu, *lyy;  // [h][...][ldb]
   double *Phix, *Phixx, *Px;               // [n | n*n | n_next*n][ldb]
+  double *kkt;                             // WB only: [h][CAFE_KKT_PACK][ldb]
   double *lk, *dsq;                        // [h+1][ldb] per-knot cost (k=h: Phi) and |Defect[k]|^2
   // backward-sweep outputs
   double *K, *Quu, *Qux;                   // [h][m*n | m*m | m*n][ldb]

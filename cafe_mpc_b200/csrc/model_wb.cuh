@@ -258,35 +258,22 @@ struct WBModel {
     }
     const double bg2 = 2.0 * ph.BG_alpha;
     for (int i = 0; i < 216; ++i) { aq[i] += bg2 * dvq[i]; av[i] += bg2 * s.J[i]; }
-    // outputs
-    double* Ag = ph.A + gix(k, 1296, 0, ldb, b);
-    double* Bg = ph.Bm + gix(k, 432, 0, ldb, b);
-    double* Cg = ph.C + gix(k, 432, 0, ldb, b);
-    double* Dg = ph.D + gix(k, 144, 0, ldb, b);
-    for (int i = 0; i < 18; ++i) { Ag[(size_t)(i + 36 * i) * ldb] = 1.0; Ag[(size_t)(i + 36 * (18 + i)) * ldb] = dt; }
-    for (int col = 0; col < 48; ++col) {
-      double r[18], w[12];
-      if (col < 18) for (int i = 0; i < 18; ++i) r[i] = Rq[i + 18 * col];
-      else if (col < 36) for (int i = 0; i < 18; ++i) r[i] = Rv[i + 18 * (col - 18)];
-      else for (int i = 0; i < 18; ++i) r[i] = (i == 6 + (col - 36)) ? -1.0 : 0.0;
-      fwd_subst(s.L, 18, 18, r);  // r <- L^-1 R
-      for (int c = 0; c < nr; ++c) {
-        double d = 0;
-        for (int i = 0; i < 18; ++i) d += s.Y[i + 18 * c] * r[i];  // (Jc Minv R)_c
-        const int row = s.rows[c];
-        const double a = (col < 18) ? aq[row + 12 * col] : (col < 36 ? av[row + 12 * (col - 18)] : 0.0);
-        w[c] = d - a;
-      }
-      if (nr > 0) { fwd_subst(Ls0, nr, 12, w); bwd_subst(Ls0, nr, 12, w); }  // dlambda/dz
-      for (int i = 0; i < 18; ++i) { double d = -r[i]; for (int c = 0; c < nr; ++c) d += s.Y[i + 18 * c] * w[c]; r[i] = d; }
-      bwd_subst(s.L, 18, 18, r);  // dqdd/dz
-      if (col < 36) {
-        for (int i = 0; i < 18; ++i) Ag[(size_t)((18 + i) + 36 * col) * ldb] = ((col == 18 + i) ? 1.0 : 0.0) + r[i] * dt;
-        for (int c = 0; c < nr; ++c) Cg[(size_t)(s.rows[c] + 12 * col) * ldb] = w[c];
-      } else {
-        for (int i = 0; i < 18; ++i) Bg[(size_t)((18 + i) + 36 * (col - 36)) * ldb] = r[i] * dt;
-        for (int c = 0; c < nr; ++c) Dg[(size_t)(s.rows[c] + 12 * (col - 36)) * ldb] = w[c];
-      }
+    // ---- hand the KKT factors and the right-hand sides to the cooperative kernel k_lq_wb_dense (kernels.cuh), which applies
+    //      dlambda/dz = S^-1 (J Minv R - a), dqdd/dz = -Minv (R - J^T dlambda/dz) column by column out of shared memory
+    {
+      double* kk = ph.kkt + gix(k, CAFE_KKT_PACK, 0, ldb, b);
+      for (int i = 0; i < 324; ++i) kk[(size_t)(CAFE_KKT_L + i) * ldb] = s.L[i];
+      for (int i = 0; i < 216; ++i) kk[(size_t)(CAFE_KKT_Y + i) * ldb] = s.Y[i];
+      for (int i = 0; i < 144; ++i) kk[(size_t)(CAFE_KKT_LS + i) * ldb] = Ls0[i];
+      for (int i = 0; i < 324; ++i) { kk[(size_t)(CAFE_KKT_R + i) * ldb] = Rq[i]; kk[(size_t)(CAFE_KKT_R + 324 + i) * ldb] = Rv[i]; }
+      for (int col = 0; col < 18; ++col)
+        for (int c = 0; c < 12; ++c) {
+          const int row = (c < nr) ? s.rows[c] : 0;
+          kk[(size_t)(CAFE_KKT_A + c + 12 * col) * ldb] = (c < nr) ? aq[row + 12 * col] : 0.0;
+          kk[(size_t)(CAFE_KKT_A + c + 12 * (18 + col)) * ldb] = (c < nr) ? av[row + 12 * col] : 0.0;
+        }
+      double* Ag = ph.A + gix(k, 1296, 0, ldb, b);
+      for (int i = 0; i < 18; ++i) { Ag[(size_t)(i + 36 * i) * ldb] = 1.0; Ag[(size_t)(i + 36 * (18 + i)) * ldb] = dt; }
     }
     // ---- cost partials
     // lu, luu (diagonal): tracking + torque-limit barrier

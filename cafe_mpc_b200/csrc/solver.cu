@@ -166,6 +166,7 @@ void carve(CafeHandle* H, Carver& cv, size_t& zero_bytes) {
     ph.lx = cv.take<double>(h * n * ldb); ph.lu = cv.take<double>(h * m * ldb); ph.ly = cv.take<double>(h * p * ldb + 1);
     ph.lxx = cv.take<double>(h * n * n * ldb); ph.luu = cv.take<double>(h * m * m * ldb); ph.lyy = cv.take<double>(h * p * p * ldb + 1);
     ph.Phix = cv.take<double>(n * ldb); ph.Phixx = cv.take<double>(n * n * ldb); ph.Px = cv.take<double>(nn * n * ldb);
+    ph.kkt = cv.take<double>(ph.model == CAFE_MODEL_WB ? h * (size_t)CAFE_KKT_PACK * ldb : 1);
     ph.Quu = cv.take<double>(h * m * m * ldb); ph.Qux = cv.take<double>(h * m * n * ldb);
     ph.Xt = cv.take<double>((size_t)NA * (h + 1) * n * ldb); ph.Ut = cv.take<double>((size_t)NA * h * m * ldb);
     ph.Yt = cv.take<double>((size_t)NA * h * p * ldb + 1); ph.Dt = cv.take<double>((size_t)NA * (h + 1) * n * ldb);
@@ -192,6 +193,27 @@ int timed(CafeHandle* H, int slot, F&& launch) {
     float ms = 0;
     cudaEventElapsedTime(&ms, H->ev0, H->ev1);
     H->ms[slot] += ms;
+  }
+  return 0;
+}
+
+// cooperative dense part of the whole-body linearisation, one launch per WB phase (template on the number of contact rows)
+int launch_lq_wb_dense(CafeHandle* H) {
+  const size_t smem = (size_t)CAFE_KKT_SM * 4 * sizeof(double);
+  for (int pi = 0; pi < H->S.n_phases; ++pi) {
+    const PhaseDev& ph = H->S.ph[pi];
+    if (ph.model != CAFE_MODEL_WB || ph.h <= 0) continue;
+    int nc = 0;
+    for (int f = 0; f < 4; ++f) nc += ph.contact[f] > 0;
+    const dim3 grid((H->B + 3) / 4, ph.h);
+    switch (nc) {
+      case 0: k_lq_wb_dense<0><<<grid, 128, smem, H->stream>>>(H->dS, pi); break;
+      case 1: k_lq_wb_dense<3><<<grid, 128, smem, H->stream>>>(H->dS, pi); break;
+      case 2: k_lq_wb_dense<6><<<grid, 128, smem, H->stream>>>(H->dS, pi); break;
+      case 3: k_lq_wb_dense<9><<<grid, 128, smem, H->stream>>>(H->dS, pi); break;
+      default: k_lq_wb_dense<12><<<grid, 128, smem, H->stream>>>(H->dS, pi); break;
+    }
+    H->launches[3]++;
   }
   return 0;
 }
@@ -285,6 +307,14 @@ extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, 
     H->bwd_smem = (size_t)cafe_dev::BwdLayout<36, 12, 12>::total * 3 * sizeof(double);
     CUDA_OK(cudaFuncSetAttribute(cafe_dev::k_bwd<36, 12, 12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H->bwd_smem));
   }
+  if (!all_hkd) {
+    const int smem = (int)(CAFE_KKT_SM * 4 * sizeof(double));
+    CUDA_OK(cudaFuncSetAttribute(cafe_dev::k_lq_wb_dense<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_OK(cudaFuncSetAttribute(cafe_dev::k_lq_wb_dense<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_OK(cudaFuncSetAttribute(cafe_dev::k_lq_wb_dense<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_OK(cudaFuncSetAttribute(cafe_dev::k_lq_wb_dense<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_OK(cudaFuncSetAttribute(cafe_dev::k_lq_wb_dense<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  }
   // the per-(problem,knot) kernels of the whole-body model keep their KKT algebra in thread-local arrays
   CUDA_OK(cudaDeviceSetLimit(cudaLimitStackSize, 64 * 1024));
   *out = H;
@@ -348,6 +378,7 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
     if (*H->h_nactive == 0) break;
     H->ticks++;
     timed(H, 3, [&] { cafe_dev::k_lq<<<g_knots, tpb, 0, st>>>(H->dS); });
+    if (H->bwd_variant == 1) timed(H, 5, [&] { launch_lq_wb_dense(H); });
     timed(H, 4, [&] { launch_bwd(H); });
     CUDA_OK(cudaMemsetAsync(H->d_fail, 0, H->fail_bytes, st));
     // staged line search: step sizes are evaluated in growing groups; most problems accept one of the first
