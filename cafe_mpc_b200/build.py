@@ -14,7 +14,7 @@ LIB = os.path.join(HERE, "libcafe_gpu.so")
 # source -> dependencies besides itself (paths relative to csrc/)
 ABI = ["../../include/cafe_gpu.h", "../../include/cafe_deck.h"]
 SOURCES = {
-    "solver.cu": ["kernels.cuh", "device_types.cuh", "model_hkd.cuh", "model_srb.cuh", "model_wb.cuh", "gen/hkd_gen.h", "gen/srb_gen.h"] + ABI,
+    "solver.cu": ["kernels.cuh", "bwd2.cuh", "device_types.cuh", "model_hkd.cuh", "model_srb.cuh", "model_wb.cuh", "gen/hkd_gen.h", "gen/srb_gen.h"] + ABI,
     "wb_gen_wrappers.cu": ["gen/wb_gen.h"],
     "host/abi_host.cpp": ["host/problem_builders.h", "host/quad_reference.h"] + ABI,
     "host/hkd_problem.cpp": ["host/problem_builders.h", "host/quad_reference.h", "host/info_reader.h", "gen/hkd_gen.h"] + ABI,

@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include "../../include/cafe_gpu.h"
 #include "kernels.cuh"
+#include "bwd2.cuh"
 
 namespace cafe { void set_last_error(const std::string& s); }
 
@@ -219,10 +220,8 @@ int launch_lq_wb_dense(CafeHandle* H) {
 }
 
 int launch_bwd(CafeHandle* H) {
-  const int PB = H->bwd_pb;
-  const int grid = (H->B + PB - 1) / PB;
-  if (H->bwd_variant == 0) k_bwd<24, 24, 0, 4><<<grid, CAFE_NW * 4, H->bwd_smem, H->stream>>>(H->dS);
-  else k_bwd<36, 12, 12, 3><<<grid, CAFE_NW * 3, H->bwd_smem, H->stream>>>(H->dS);
+  if (H->bwd_variant == 0) k_bwd2<0, 64><<<H->B, 64, H->bwd_smem, H->stream>>>(H->dS);
+  else k_bwd2<1, 64><<<H->B, 64, H->bwd_smem, H->stream>>>(H->dS);
   return 0;
 }
 
@@ -299,13 +298,13 @@ extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, 
   H->max_segs = 9 * CAFE_MAX_PHASES;
   CUDA_OK(cudaMalloc(&H->d_segs, H->max_segs * sizeof(PackSeg)));
   if (all_hkd) {
-    H->bwd_variant = 0; H->bwd_pb = 4;
-    H->bwd_smem = (size_t)cafe_dev::BwdLayout<24, 24, 0>::total * 4 * sizeof(double);
-    CUDA_OK(cudaFuncSetAttribute(cafe_dev::k_bwd<24, 24, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H->bwd_smem));
+    H->bwd_variant = 0; H->bwd_pb = 1;
+    H->bwd_smem = (size_t)cafe_dev::Bwd2Layout<24, 24, 0, false>::total * sizeof(double);
+    CUDA_OK(cudaFuncSetAttribute(cafe_dev::k_bwd2<0, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H->bwd_smem));
   } else {
-    H->bwd_variant = 1; H->bwd_pb = 3;
-    H->bwd_smem = (size_t)cafe_dev::BwdLayout<36, 12, 12>::total * 3 * sizeof(double);
-    CUDA_OK(cudaFuncSetAttribute(cafe_dev::k_bwd<36, 12, 12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H->bwd_smem));
+    H->bwd_variant = 1; H->bwd_pb = 1;
+    H->bwd_smem = (size_t)cafe_dev::Bwd2Layout<36, 12, 12, true>::total * sizeof(double);
+    CUDA_OK(cudaFuncSetAttribute(cafe_dev::k_bwd2<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H->bwd_smem));
   }
   if (!all_hkd) {
     const int smem = (int)(CAFE_KKT_SM * 4 * sizeof(double));
