@@ -355,7 +355,7 @@ __device__ void lin_phase2(const SolverDev& S, int pi, int b, int t, bool run, d
 
 // DECK: 0 = HKD phases only (24,24,0); 1 = MHPC (WB 36,12,12 + SRB 12,12,0)
 template <int DECK, int NT>
-__global__ void __launch_bounds__(NT) k_bwd2(const SolverDev* __restrict__ Sp) {
+__global__ void __launch_bounds__(NT, 4) k_bwd2(const SolverDev* __restrict__ Sp) {
   typedef Bwd2Layout<(DECK == 0 ? 24 : 36), (DECK == 0 ? 24 : 12), (DECK == 0 ? 0 : 12), (DECK == 1)> L;
   constexpr int NX = (DECK == 0 ? 24 : 36);
   const SolverDev& S = *Sp;
