@@ -10,13 +10,20 @@
 #include "../../include/cafe_deck.h"
 
 #define CAFE_MAX_ALPHAS 12
-// per-(problem, WB knot) hand-off from k_lq to k_lq_wb_dense: chol(M) | Y = L^-1 Jc^T | chol(S) | R = [dtau_dq' dtau_dv] | a = [da_dq da_dv] (active rows)
+// per-(problem, WB knot) hand-off from k_lq to k_lq_wb_dense (raw pieces; the dense kernel combines them):
+//   chol(M) | Y = L^-1 Jc^T | chol(S) | dtau_dq | dtau_dv | d(J^T F)/dq | da/dq | da/dv | dv/dq | J     (foot rows 3f+r, ld 12)
+// the generated routines write their (static) non-zero patterns straight into this array, which is zeroed once at create
 #define CAFE_KKT_L 0
 #define CAFE_KKT_Y 324
 #define CAFE_KKT_LS 540
-#define CAFE_KKT_R 684
-#define CAFE_KKT_A 1332
-#define CAFE_KKT_PACK 1764
+#define CAFE_KKT_RQ 684
+#define CAFE_KKT_RV 1008
+#define CAFE_KKT_JTF 1332
+#define CAFE_KKT_AQ 1656
+#define CAFE_KKT_AV 1872
+#define CAFE_KKT_DVQ 2088
+#define CAFE_KKT_J 2304
+#define CAFE_KKT_PACK 2520
 #define CAFE_MAX_KNOTS 256
 #define CAFE_HIST_CAP 256
 

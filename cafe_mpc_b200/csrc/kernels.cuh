@@ -209,15 +209,31 @@ __global__ void __launch_bounds__(128, 3) k_lq_wb_dense(const SolverDev* __restr
     const int p = threadIdx.x & 3, b = b0 + p;
     double* dst = sm + p * CAFE_KKT_SM;
     const double* src = ph.kkt + gix(k, CAFE_KKT_PACK, 0, ldb, b);
-    if (b < S.B && S.c.active[b])
-      for (int e = threadIdx.x >> 2; e < CAFE_KKT_PACK; e += 32) {
+    if (b < S.B && S.c.active[b]) {
+      const double bg2 = 2.0 * ph.BG_alpha;
+      int rowsA[12];
+      { int j = 0; for (int f = 0; f < 4; ++f) if (ph.contact[f] > 0) for (int r = 0; r < 3; ++r) rowsA[j++] = 3 * f + r; for (; j < 12; ++j) rowsA[j] = 0; }
+      for (int e = threadIdx.x >> 2; e < 684; e += 32) {  // factors
         const double v = src[(size_t)e * ldb];
-        if (e >= CAFE_KKT_A) { const int idx = e - CAFE_KKT_A; dst[1584 + (idx % 12) + 13 * (idx / 12)] = v; }
-        else if (e >= CAFE_KKT_R) { const int idx = e - CAFE_KKT_R; dst[900 + (idx % 18) + 19 * (idx / 18)] = v; }
-        else if (e >= CAFE_KKT_LS) { const int idx = e - CAFE_KKT_LS; const int i = idx % 12, j = idx / 12; dst[756 + j + 12 * i] = (i == j) ? 1.0 / v : v; }
+        if (e >= CAFE_KKT_LS) { const int idx = e - CAFE_KKT_LS; const int i = idx % 12, j = idx / 12; dst[756 + j + 12 * i] = (i == j) ? 1.0 / v : v; }
         else if (e >= CAFE_KKT_Y) { const int idx = e - CAFE_KKT_Y; const int i = idx % 18, c = idx / 18; dst[324 + idx] = v; dst[540 + c + 12 * i] = v; }
         else { const int i = e % 18, j = e / 18; dst[j + 18 * i] = (i == j) ? 1.0 / v : v; }
       }
+      for (int e = threadIdx.x >> 2; e < 648; e += 32) {  // R = [dtau_dq - d(J^T F)/dq | dtau_dv]
+        const int i = e % 18, col = e / 18;
+        double v = src[(size_t)(CAFE_KKT_RQ + e) * ldb];
+        if (col < 18) v -= src[(size_t)(CAFE_KKT_JTF + e) * ldb];
+        dst[900 + i + 19 * col] = v;
+      }
+      for (int e = threadIdx.x >> 2; e < NR * 36; e += 32) {  // a = [da/dq + 2 BG dv/dq | da/dv + 2 BG J] on the active rows
+        const int c = e % (NR > 0 ? NR : 1), col = e / (NR > 0 ? NR : 1);
+        const int row = rowsA[c];
+        double v;
+        if (col < 18) v = src[(size_t)(CAFE_KKT_AQ + row + 12 * col) * ldb] + bg2 * src[(size_t)(CAFE_KKT_DVQ + row + 12 * col) * ldb];
+        else v = src[(size_t)(CAFE_KKT_AV + row + 12 * (col - 18)) * ldb] + bg2 * src[(size_t)(CAFE_KKT_J + row + 12 * (col - 18)) * ldb];
+        dst[1584 + c + 13 * col] = v;
+      }
+    }
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = b0 + warp;

@@ -23,9 +23,9 @@ namespace cafe_dev {
 // minutes for these 10^4-op straight-line functions), writing into plain (local-memory) arrays; callers pre-zero the outputs.
 __device__ void wbg_terms(const double* q, const double* v, double* nle, double* Mlow, double* J, double* gam, double* pf, double* vf);
 __device__ void wbg_feet(const double* q, const double* v, double* pf, double* vf, double* J);
-__device__ void wbg_rnea_derivs(const double* q, const double* v, const double* a, double* dq, double* dv);
+__device__ void wbg_rnea_derivs(const double* q, const double* v, const double* a, double* dq, double* dv, size_t st);
 __device__ void wbg_grav_derivs(const double* q, double* dq);
-__device__ void wbg_kin_partials(const double* q, const double* v, const double* a, const double* F, double* dvq, double* daq, double* dav, double* djtf);
+__device__ void wbg_kin_partials(const double* q, const double* v, const double* a, const double* F, double* dvq, double* daq, double* dav, double* djtf, size_t st);
 __device__ void wbg_footvel_partial(const double* q, const double* v, double* dvq);
 
 struct WBScratch {
@@ -245,36 +245,22 @@ struct WBModel {
     for (int c = 0; c < nr; ++c)
       for (int r = c; r < nr; ++r) { double d = 0; for (int i = 0; i < 18; ++i) d += s.Y[i + 18 * r] * s.Y[i + 18 * c]; Ls0[r + 12 * c] = d; }
     if (nr > 0) chol_inplace(Ls0, nr, 12);
-    double Rq[324], Rv[324], aq[216], av[216], dvq[216];
-    for (int i = 0; i < 324; ++i) { Rq[i] = 0; Rv[i] = 0; }
-    for (int i = 0; i < 216; ++i) { aq[i] = 0; av[i] = 0; dvq[i] = 0; }
-    wbg_rnea_derivs(x, x + 18, s.qdd, Rq, Rv);
+    // ---- hand the KKT factors and the raw derivative pieces to the cooperative kernel k_lq_wb_dense (kernels.cuh), which forms
+    //      R = dtau_dq - d(J^T F)/dq, a = da + 2 BG (dv/dq | J) on the active rows and applies
+    //      dlambda/dz = S^-1 (J Minv R - a), dqdd/dz = -Minv (R - J^T dlambda/dz) column by column out of shared memory.
+    //      The generated routines store their static non-zero patterns directly into the batch-major array (coalesced).
+    double* kk = ph.kkt + gix(k, CAFE_KKT_PACK, 0, ldb, b);
+    const size_t st = (size_t)ldb;
+    wbg_rnea_derivs(x, x + 18, s.qdd, kk + CAFE_KKT_RQ * st, kk + CAFE_KKT_RV * st, st);
+    wbg_kin_partials(x, x + 18, s.qdd, s.grf, kk + CAFE_KKT_DVQ * st, kk + CAFE_KKT_AQ * st, kk + CAFE_KKT_AV * st, kk + CAFE_KKT_JTF * st, st);
+    for (int i = 0; i < 324; ++i) kk[(CAFE_KKT_L + i) * st] = s.L[i];
+    for (int i = 0; i < 216; ++i) { kk[(CAFE_KKT_Y + i) * st] = s.Y[i]; kk[(CAFE_KKT_J + i) * st] = s.J[i]; }
+    for (int i = 0; i < 144; ++i) kk[(CAFE_KKT_LS + i) * st] = Ls0[i];
     {
-      // dtau_dq -= d(J^T GRF)/dq ; foot acceleration / velocity partials (hip yaw = pi side)
-      double djtf[324];
-      for (int i = 0; i < 324; ++i) djtf[i] = 0;
-      wbg_kin_partials(x, x + 18, s.qdd, s.grf, dvq, aq, av, djtf);
-      for (int i = 0; i < 324; ++i) Rq[i] -= djtf[i];
-    }
-    const double bg2 = 2.0 * ph.BG_alpha;
-    for (int i = 0; i < 216; ++i) { aq[i] += bg2 * dvq[i]; av[i] += bg2 * s.J[i]; }
-    // ---- hand the KKT factors and the right-hand sides to the cooperative kernel k_lq_wb_dense (kernels.cuh), which applies
-    //      dlambda/dz = S^-1 (J Minv R - a), dqdd/dz = -Minv (R - J^T dlambda/dz) column by column out of shared memory
-    {
-      double* kk = ph.kkt + gix(k, CAFE_KKT_PACK, 0, ldb, b);
-      for (int i = 0; i < 324; ++i) kk[(size_t)(CAFE_KKT_L + i) * ldb] = s.L[i];
-      for (int i = 0; i < 216; ++i) kk[(size_t)(CAFE_KKT_Y + i) * ldb] = s.Y[i];
-      for (int i = 0; i < 144; ++i) kk[(size_t)(CAFE_KKT_LS + i) * ldb] = Ls0[i];
-      for (int i = 0; i < 324; ++i) { kk[(size_t)(CAFE_KKT_R + i) * ldb] = Rq[i]; kk[(size_t)(CAFE_KKT_R + 324 + i) * ldb] = Rv[i]; }
-      for (int col = 0; col < 18; ++col)
-        for (int c = 0; c < 12; ++c) {
-          const int row = (c < nr) ? s.rows[c] : 0;
-          kk[(size_t)(CAFE_KKT_A + c + 12 * col) * ldb] = (c < nr) ? aq[row + 12 * col] : 0.0;
-          kk[(size_t)(CAFE_KKT_A + c + 12 * (18 + col)) * ldb] = (c < nr) ? av[row + 12 * col] : 0.0;
-        }
       double* Ag = ph.A + gix(k, 1296, 0, ldb, b);
       for (int i = 0; i < 18; ++i) { Ag[(size_t)(i + 36 * i) * ldb] = 1.0; Ag[(size_t)(i + 36 * (18 + i)) * ldb] = dt; }
     }
+    const double* dvq = kk + CAFE_KKT_DVQ * st;  // read back (element i at dvq[i * st])
     // ---- cost partials
     // lu, luu (diagonal): tracking + torque-limit barrier
     double* luug = ph.luu + gix(k, 144, 0, ldb, b);
@@ -330,7 +316,7 @@ struct WBModel {
       if (!c)
         for (int i = 0; i < 36; ++i) {
           double g = 0;
-          for (int a = 0; a < 3; ++a) g += ((i < 18) ? dvq[3 * f + a + 12 * i] : s.J[3 * f + a + 12 * (i - 18)]) * dvelw[3 * f + a];
+          for (int a = 0; a < 3; ++a) g += ((i < 18) ? dvq[(3 * f + a + 12 * i) * st] : s.J[3 * f + a + 12 * (i - 18)]) * dvelw[3 * f + a];
           lx[i] += g * dt;
         }
     }
@@ -345,34 +331,50 @@ struct WBModel {
       lx[2] += dt * (ph.reb_minheight.eps * bdh);
     }
     for (int i = 0; i < 36; ++i) ph.lx[gix(k, 36, i, ldb, b)] = lx[i];
+    // lxx: diagonal (tracking + joint-limit / min-height barriers) + per-foot Gauss-Newton blocks. A foot Jacobian only has the
+    // base-rotation columns 3..5 and its own three joint columns (the first three are zeroed by the reference), the swing-foot
+    // velocity Jacobian [dv/dq | J] additionally the six base columns of the velocity half: small dense blocks per foot.
     double* lxxg = ph.lxx + gix(k, 1296, 0, ldb, b);
-    for (int j = 0; j < 36; ++j)
-      for (int i = 0; i < 36; ++i) {
-        double v = (i == j) ? dt * ph.q[i] : 0.0;
-        for (int f = 0; f < 4; ++f) {
-          const bool c = rec[CAFE_REF_CONTACT + f] > 0;
-          const double* w = c ? ph.w_footreg : ph.w_swingpos;
-          if (i >= 3 && i < 18 && j >= 3 && j < 18) {
-            double hh = 0;
-            for (int a = 0; a < 3; ++a) hh += s.J[3 * f + a + 12 * i] * w[a] * s.J[3 * f + a + 12 * j];
-            v += hh * dt;
-          }
-          if (!c) {
-            double hh = 0;
-            for (int a = 0; a < 3; ++a) {
-              const double ji = (i < 18) ? dvq[3 * f + a + 12 * i] : s.J[3 * f + a + 12 * (i - 18)];
-              const double jj = (j < 18) ? dvq[3 * f + a + 12 * j] : s.J[3 * f + a + 12 * (j - 18)];
-              hh += ji * ph.w_swingvel[a] * jj;
-            }
-            v += hh * dt;
-          }
-        }
-        if (reb && i == j) {
-          if (i >= 6 && i < 18) v += dt * (ph.reb_joint.eps * bddj[i - 6] + ph.reb_joint.eps * bddj[12 + i - 6]);
-          if (i == 2) v += dt * (ph.reb_minheight.eps * bddh);
-        }
-        lxxg[(size_t)(i + 36 * j) * ldb] = v;
+    double acc[1296];
+    for (int i = 0; i < 1296; ++i) acc[i] = 0.0;
+    for (int i = 0; i < 36; ++i) {
+      double v = dt * ph.q[i];
+      if (reb) {
+        if (i >= 6 && i < 18) v += dt * (ph.reb_joint.eps * bddj[i - 6] + ph.reb_joint.eps * bddj[12 + i - 6]);
+        if (i == 2) v += dt * (ph.reb_minheight.eps * bddh);
       }
+      acc[37 * i] = v;
+    }
+    for (int f = 0; f < 4; ++f) {
+      const bool c = rec[CAFE_REF_CONTACT + f] > 0;
+      const double* w = c ? ph.w_footreg : ph.w_swingpos;
+      int cols[15];
+      for (int a = 0; a < 3; ++a) { cols[a] = 3 + a; cols[3 + a] = 6 + 3 * f + a; }
+      for (int jj = 0; jj < 6; ++jj)
+        for (int ii = 0; ii < 6; ++ii) {
+          const int i = cols[ii], j = cols[jj];
+          double hh = 0;
+          for (int a = 0; a < 3; ++a) hh += s.J[3 * f + a + 12 * i] * w[a] * s.J[3 * f + a + 12 * j];
+          acc[i + 36 * j] += hh * dt;
+        }
+      if (!c) {
+        // columns of [dv/dq | J]: q-half 3..5 and leg; v-half 18..23 and 18 + leg
+        for (int a = 0; a < 6; ++a) cols[6 + a] = 18 + a;
+        for (int a = 0; a < 3; ++a) cols[12 + a] = 18 + 6 + 3 * f + a;
+        double jx[3][15];
+        for (int ii = 0; ii < 15; ++ii) {
+          const int i = cols[ii];
+          for (int a = 0; a < 3; ++a) jx[a][ii] = (i < 18) ? dvq[(3 * f + a + 12 * i) * st] : s.J[3 * f + a + 12 * (i - 18)];
+        }
+        for (int jj = 0; jj < 15; ++jj)
+          for (int ii = 0; ii < 15; ++ii) {
+            double hh = 0;
+            for (int a = 0; a < 3; ++a) hh += jx[a][ii] * ph.w_swingvel[a] * jx[a][jj];
+            acc[cols[ii] + 36 * cols[jj]] += hh * dt;
+          }
+      }
+    }
+    for (int i = 0; i < 1296; ++i) lxxg[(size_t)i * ldb] = acc[i];
     double ming;
     return running_cost_k(ph, rec, x, u, s.grf, s.pf, s.vf, reb, ming);
   }
@@ -450,7 +452,7 @@ struct WBModel {
       // d(M(q) dv + g(q))/dq - dg/dq  (computeRNEADerivatives(q, 0, v+ - v) minus computeGeneralizedGravityDerivatives)
       double tmp[324];
       for (int i = 0; i < 324; ++i) tmp[i] = 0;
-      wbg_rnea_derivs(x, zero18, dv, Rq, tmp);
+      wbg_rnea_derivs(x, zero18, dv, Rq, tmp, 1);
       for (int i = 0; i < 324; ++i) tmp[i] = 0;
       wbg_grav_derivs(x, tmp);
       for (int i = 0; i < 324; ++i) Rq[i] -= tmp[i];
@@ -468,7 +470,7 @@ struct WBModel {
       double da1[216], da2[216], djtf[324];
       for (int i = 0; i < 216; ++i) { da1[i] = 0; da2[i] = 0; }
       for (int i = 0; i < 324; ++i) djtf[i] = 0;
-      wbg_kin_partials(xv, xv + 18, zero18, imp, dvq2, da1, da2, djtf);
+      wbg_kin_partials(xv, xv + 18, zero18, imp, dvq2, da1, da2, djtf, 1);
       for (int i = 0; i < 324; ++i) Rq[i] -= djtf[i];
     }
     for (int col = 0; col < 36; ++col) {
