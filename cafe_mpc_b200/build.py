@@ -14,7 +14,8 @@ LIB = os.path.join(HERE, "libcafe_gpu.so")
 # source -> dependencies besides itself (paths relative to csrc/)
 ABI = ["../../include/cafe_gpu.h", "../../include/cafe_deck.h"]
 SOURCES = {
-    "solver.cu": ["kernels.cuh", "bwd2.cuh", "device_types.cuh", "model_hkd.cuh", "model_srb.cuh", "model_wb.cuh", "gen/hkd_gen.h", "gen/srb_gen.h"] + ABI,
+    "solver.cu": ["dense_kernels.cuh", "bwd2.cuh", "device_types.cuh", "launchers.h"] + ABI,
+    "knot_kernels.cu": ["knot_kernels.cuh", "launchers.h", "device_types.cuh", "model_hkd.cuh", "model_srb.cuh", "model_wb.cuh", "gen/hkd_gen.h", "gen/srb_gen.h"] + ABI,
     "wb_gen_wrappers.cu": ["gen/wb_gen.h"],
     "host/abi_host.cpp": ["host/problem_builders.h", "host/quad_reference.h"] + ABI,
     "host/hkd_problem.cpp": ["host/problem_builders.h", "host/quad_reference.h", "host/info_reader.h", "gen/hkd_gen.h"] + ABI,
@@ -27,6 +28,11 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17", "-rdc=true", "-Xcompiler", "-fPIC",
     "--fmad=true", "-Xptxas", "-v", "-Xcudafe", "--diag_suppress=177",
 ]
+
+
+# per-source extra flags: the generated whole-body routines are capped at 128 registers so that the per-(problem,knot)
+# kernels calling them reach 4 CTAs of 128 threads per SM (their local-memory traffic needs the latency hiding)
+EXTRA = {"wb_gen_wrappers.cu": ["-maxrregcount=128"], "knot_kernels.cu": ["-maxrregcount=128"]}
 
 
 def _mtime(p):
@@ -47,7 +53,7 @@ def build(force=False, verbose=False):
         objs.append(obj)
         all_deps = [os.path.join(CSRC, src)] + [os.path.join(CSRC, d) for d in deps]
         if force or _stale(obj, all_deps):
-            cmd = [nvcc] + NVCC_FLAGS + ["-c", "-o", obj, os.path.join(CSRC, src)]
+            cmd = [nvcc] + NVCC_FLAGS + EXTRA.get(src, []) + ["-c", "-o", obj, os.path.join(CSRC, src)]
             res = subprocess.run(cmd, capture_output=True, text=True)
             logs.append(" ".join(cmd) + "\n" + res.stdout + res.stderr)
             if res.returncode != 0:

@@ -1,0 +1,144 @@
+// dense_kernels.cuh — cooperative shared-memory part of the whole-body linearisation (see model_wb.cuh::lq_knot for the producer).
+#pragma once
+#include "device_types.cuh"
+
+namespace cafe_dev {
+
+// ------------------------------------------------------------------------------- K-LQ, whole-body dense part
+// KKT sensitivities of one WB phase (WBM.cpp:459-505 without forming Kinv): CTA = 4 consecutive problems at one knot, one warp
+// per problem, lane = column z of [q(18) v(18) tau(12)]; chol(M), Y = L^-1 Jc^T, chol(S) are read from shared memory at
+// warp-uniform addresses (broadcast), the column's right-hand side lives in registers.
+//   dlambda/dz = S^-1 (Jc Minv R - a),  dqdd/dz = -Minv (R - Jc^T dlambda/dz);  A = I + dt Ac, B = dt Bc, C/D = dGRF/d(x,u)
+// shared memory per problem (doubles): Lt 324 (row-major L, reciprocal diagonal) | Y 216 (18 x 12, ld 18) | Yt 216 (12 x 18, ld 12)
+//                                     | Lst 144 (row-major chol(S), reciprocal diagonal) | R 19x36 | a 13x36
+#define CAFE_KKT_SM (324 + 216 + 216 + 144 + 684 + 468)
+template <int NR>
+__global__ void __launch_bounds__(128, 3) k_lq_wb_dense(const SolverDev* __restrict__ Sp, int pi) {
+  const SolverDev& S = *Sp;
+  const PhaseDev& ph = S.ph[pi];
+  extern __shared__ double sm[];
+  const int ldb = S.ldb, k = blockIdx.y, b0 = blockIdx.x * 4;
+  {
+    const int p = threadIdx.x & 3, b = b0 + p;
+    double* dst = sm + p * CAFE_KKT_SM;
+    const double* src = ph.kkt + gix(k, CAFE_KKT_PACK, 0, ldb, b);
+    if (b < S.B && S.c.active[b]) {
+      const double bg2 = 2.0 * ph.BG_alpha;
+      int rowsA[12];
+      { int j = 0; for (int f = 0; f < 4; ++f) if (ph.contact[f] > 0) for (int r = 0; r < 3; ++r) rowsA[j++] = 3 * f + r; for (; j < 12; ++j) rowsA[j] = 0; }
+      for (int e = threadIdx.x >> 2; e < 684; e += 32) {  // factors
+        const double v = src[(size_t)e * ldb];
+        if (e >= CAFE_KKT_LS) { const int idx = e - CAFE_KKT_LS; const int i = idx % 12, j = idx / 12; dst[756 + j + 12 * i] = (i == j) ? 1.0 / v : v; }
+        else if (e >= CAFE_KKT_Y) { const int idx = e - CAFE_KKT_Y; const int i = idx % 18, c = idx / 18; dst[324 + idx] = v; dst[540 + c + 12 * i] = v; }
+        else { const int i = e % 18, j = e / 18; dst[j + 18 * i] = (i == j) ? 1.0 / v : v; }
+      }
+      for (int e = threadIdx.x >> 2; e < 648; e += 32) {  // R = [dtau_dq - d(J^T F)/dq | dtau_dv]
+        const int i = e % 18, col = e / 18;
+        double v = src[(size_t)(CAFE_KKT_RQ + e) * ldb];
+        if (col < 18) v -= src[(size_t)(CAFE_KKT_JTF + e) * ldb];
+        dst[900 + i + 19 * col] = v;
+      }
+      for (int e = threadIdx.x >> 2; e < NR * 36; e += 32) {  // a = [da/dq + 2 BG dv/dq | da/dv + 2 BG J] on the active rows
+        const int c = e % (NR > 0 ? NR : 1), col = e / (NR > 0 ? NR : 1);
+        const int row = rowsA[c];
+        double v;
+        if (col < 18) v = src[(size_t)(CAFE_KKT_AQ + row + 12 * col) * ldb] + bg2 * src[(size_t)(CAFE_KKT_DVQ + row + 12 * col) * ldb];
+        else v = src[(size_t)(CAFE_KKT_AV + row + 12 * (col - 18)) * ldb] + bg2 * src[(size_t)(CAFE_KKT_J + row + 12 * (col - 18)) * ldb];
+        dst[1584 + c + 13 * col] = v;
+      }
+    }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = b0 + warp;
+  if (b >= S.B || !S.c.active[b]) return;
+  const double* sLt = sm + warp * CAFE_KKT_SM;  // Lt[k + 18 i] = L(i,k), Lt[i + 18 i] = 1 / L(i,i)
+  const double* sY = sLt + 324;                 // Y[i + 18 c]
+  const double* sYt = sLt + 540;                // Yt[c + 12 i]
+  const double* sLst = sLt + 756;               // Lst[k + 12 i] = Ls(i,k), reciprocal diagonal
+  const double* sR = sLt + 900;
+  const double* sa = sLt + 1584;
+  const double dt = ph.dt;
+  int foot[4] = {0, 0, 0, 0};
+  { int j = 0; for (int f = 0; f < 4; ++f) if (ph.contact[f] > 0) foot[j++] = f; }
+  double* Ag = ph.A + gix(k, 1296, 0, ldb, b);
+  double* Bg = ph.Bm + gix(k, 432, 0, ldb, b);
+  double* Cg = ph.C + gix(k, 432, 0, ldb, b);
+  double* Dg = ph.D + gix(k, 144, 0, ldb, b);
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    const int col = pass * 32 + lane;
+    if (col >= 48) break;
+    double r[18], w[NR > 0 ? NR : 1];
+    if (col < 36) {
+#pragma unroll
+      for (int i = 0; i < 18; ++i) r[i] = sR[i + 19 * col];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 18; ++i) r[i] = (i == 6 + (col - 36)) ? -1.0 : 0.0;
+    }
+    // r <- L^-1 R  (row i of L is contiguous in Lt)
+#pragma unroll
+    for (int i = 0; i < 18; ++i) {
+      double s = r[i];
+#pragma unroll
+      for (int kk = 0; kk < i; ++kk) s -= sLt[kk + 18 * i] * r[kk];
+      r[i] = s * sLt[i + 18 * i];
+    }
+    if constexpr (NR > 0) {
+#pragma unroll
+      for (int c = 0; c < NR; ++c) {
+        double d = 0;
+#pragma unroll
+        for (int i = 0; i < 18; ++i) d += sY[i + 18 * c] * r[i];
+        w[c] = d - ((col < 36) ? sa[c + 13 * col] : 0.0);
+      }
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        double s = w[i];
+#pragma unroll
+        for (int kk = 0; kk < i; ++kk) s -= sLst[kk + 12 * i] * w[kk];
+        w[i] = s * sLst[i + 12 * i];
+      }
+      // back substitution with Ls^T: column i of Ls is needed; process as saxpy updates so that rows stay contiguous
+#pragma unroll
+      for (int i = NR - 1; i >= 0; --i) {
+        w[i] *= sLst[i + 12 * i];
+#pragma unroll
+        for (int kk = 0; kk < i; ++kk) w[kk] -= sLst[kk + 12 * i] * w[i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 18; ++i) {
+      double d = -r[i];
+      if constexpr (NR > 0) {
+#pragma unroll
+        for (int c = 0; c < NR; ++c) d += sYt[c + 12 * i] * w[c];
+      }
+      r[i] = d;
+    }
+    // r <- L^-T r, saxpy form (row i of L contiguous)
+#pragma unroll
+    for (int i = 17; i >= 0; --i) {
+      r[i] *= sLt[i + 18 * i];
+#pragma unroll
+      for (int kk = 0; kk < i; ++kk) r[kk] -= sLt[kk + 18 * i] * r[i];
+    }
+    if (col < 36) {
+#pragma unroll
+      for (int i = 0; i < 18; ++i) Ag[(size_t)((18 + i) + 36 * col) * ldb] = ((col == 18 + i) ? 1.0 : 0.0) + r[i] * dt;
+      if constexpr (NR > 0) {
+#pragma unroll
+        for (int c = 0; c < NR; ++c) Cg[(size_t)((3 * foot[c / 3] + c % 3) + 12 * col) * ldb] = w[c];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 18; ++i) Bg[(size_t)((18 + i) + 36 * (col - 36)) * ldb] = r[i] * dt;
+      if constexpr (NR > 0) {
+#pragma unroll
+        for (int c = 0; c < NR; ++c) Dg[(size_t)((3 * foot[c / 3] + c % 3) + 12 * (col - 36)) * ldb] = w[c];
+      }
+    }
+  }
+}
+
+}  // namespace cafe_dev

@@ -1,0 +1,17 @@
+// knot_kernels.cu — translation unit of the per-(problem, knot) kernels (k_roll, k_lq, k_accept) and the control kernels
+// (k_ls_scan, k_select). Compiled with -maxrregcount=128 (see build.py): these kernels are dominated by thread-local
+// memory traffic of the generated model routines and need 4 resident CTAs of 128 threads per SM for latency hiding.
+#include "knot_kernels.cuh"
+#include "launchers.h"
+
+namespace cafe_dev {
+
+void launch_roll(const SolverDev* dS, long long nthreads, cudaStream_t st, int a0, int a1) {
+  k_roll<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(dS, a0, a1);
+}
+void launch_lq(const SolverDev* dS, long long nthreads, cudaStream_t st) { k_lq<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(dS); }
+void launch_accept(const SolverDev* dS, long long nthreads, cudaStream_t st) { k_accept<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(dS); }
+void launch_ls_scan(const SolverDev* dS, int B, cudaStream_t st, int a0, int a1) { k_ls_scan<<<(B + 127) / 128, 128, 0, st>>>(dS, a0, a1); }
+void launch_select(const SolverDev* dS, int B, cudaStream_t st, int mode) { k_select<<<(B + 127) / 128, 128, 0, st>>>(dS, mode); }
+
+}  // namespace cafe_dev

@@ -1,0 +1,366 @@
+// knot_kernels.cuh — the per-(problem, knot) kernels and the per-problem control kernels of the batched HS-DDP path (sm_100a, fp64).
+// (The Riccati sweep lives in bwd2.cuh, the cooperative whole-body KKT sensitivities in dense_kernels.cuh.)
+//
+//   k_roll    K-ROLL : hybrid rollout of every (problem, knot, step size) + constraint values + costs
+//                      <= SinglePhase::hybrid_rollout / compute_cost      HSDDPSolver/source/SinglePhase.cpp:182-262
+//                         MultiPhaseDDP::hybrid_rollout                   HSDDPSolver/source/MultiPhaseDDP.cpp:49-92
+//   k_select  K-CTRL : merit / Armijo test over the step sizes, accept, exits, AL update, histories
+//                      <= MultiPhaseDDP::line_search / solve              MultiPhaseDDP.cpp:95-133, :216-447
+//   k_accept          : trial -> current (and -> nominal when accepted)   TrajectoryManagement.cpp:122-127
+//   k_lq      K-LQ   : dynamics / cost / constraint partials, ReB + AL folding, per-knot cost
+//                      <= SinglePhase::LQ_approximation, compute_cost     SinglePhase.cpp:236-320, :394-450
+//   k_bwd     K-BWD + K-LIN : regularised Riccati sweep across phases with impact jumps, then the
+//                      multiple-shooting linear rollout and the merit parameter
+//                      <= SinglePhase::backward_sweep / linear_rollout    SinglePhase.cpp:145-178, :323-391
+//                         MultiPhaseDDP::backward_sweep(_regularized) / linear_rollout / impact_aware_step
+//                                                                         MultiPhaseDDP.cpp:12-42, :136-213, :499-503
+//
+// Mapping: k_roll / k_lq / k_accept run one thread per (problem, knot[, step size]) with the problem
+// index fastest, so a warp is 32 problems at the same knot: identical instruction streams, coalesced
+// HBM access, no divergence except on per-problem activity flags. k_bwd runs one CTA per group of PB
+// problems, 32 workers per problem, sequential over the horizon, all matrices staged in shared memory.
+#pragma once
+#include "device_types.cuh"
+#include "model_hkd.cuh"
+#include "model_srb.cuh"
+#include "model_wb.cuh"
+
+namespace cafe_dev {
+
+// ------------------------------------------------------------------------------------------- K-ROLL
+template <class Model>
+__device__ void roll_knot(const SolverDev& S, int pi, int k, int a, int b) {
+  constexpr int N = Model::N, M = Model::M, PY = Model::PY;
+  const PhaseDev& ph = S.ph[pi];
+  const int ldb = S.ldb, h = ph.h;
+  const double eps = S.eps[a];
+  const double* rec = ph.ref + (size_t)k * CAFE_REF_W;
+  const size_t aX = (size_t)a * (h + 1) * N * ldb, aU = (size_t)a * h * M * ldb, aY = (size_t)a * h * PY * ldb;
+  const size_t aS = (size_t)a * (h + 1) * ldb;
+  double x[N], dlt[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const double xb = ph.Xbar[gix(k, N, i, ldb, b)];
+    x[i] = xb + eps * ph.dX[gix(k, N, i, ldb, b)];
+    dlt[i] = x[i] - xb;
+    ph.Xt[aX + gix(k, N, i, ldb, b)] = x[i];
+  }
+  if (pi == 0 && k == 0) {  // Defect[0] of the first phase: Xsim[0] = x0
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { const double d = S.x0[(size_t)i * ldb + b] - x[i]; ph.Dt[aX + gix(0, N, i, ldb, b)] = d; s += d * d; }
+    S.c.feas0_t[(size_t)a * ldb + b] = s;
+  }
+  if (k < h) {
+    double u[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) u[i] = 0;
+    const double* Kg = ph.K + gix(k, M * N, 0, ldb, b);
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+#pragma unroll
+      for (int i = 0; i < M; ++i) u[i] += Kg[(size_t)(i + M * j) * ldb] * dlt[j];
+    }
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      u[i] = ph.Ubar[gix(k, M, i, ldb, b)] + eps * ph.dU[gix(k, M, i, ldb, b)] + u[i];
+      ph.Ut[aU + gix(k, M, i, ldb, b)] = u[i];
+    }
+    double xn[N], y[PY > 0 ? PY : 1];
+    double l, ming;
+    Model::roll(ph, rec, x, u, xn, y, S.opt.ReB_active != 0, l, ming);
+    double nrm = 0, dsq = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      nrm += xn[i] * xn[i];
+      const double xs = ph.Xbar[gix(k + 1, N, i, ldb, b)] + eps * ph.dX[gix(k + 1, N, i, ldb, b)];
+      const double d = xn[i] - xs;
+      ph.Dt[aX + gix(k + 1, N, i, ldb, b)] = d;
+      dsq += d * d;
+    }
+#pragma unroll
+    for (int i = 0; i < PY; ++i) ph.Yt[aY + gix(k, PY, i, ldb, b)] = y[i];
+    ph.cost_t[aS + (size_t)k * ldb + b] = l;
+    ph.feas_t[aS + (size_t)k * ldb + b] = dsq;
+    ph.ming_t[aS + (size_t)k * ldb + b] = ming;
+    if (sqrt(nrm) > 1e6) atomicOr(&ph.fail_t[(size_t)a * ldb + b], 1);
+  } else {
+    double phi = Model::terminal_cost(ph, rec, x);
+    double hv[4] = {0, 0, 0, 0}, maxh = 0;
+    if (ph.n_td > 0) {
+      Model::terminal_constraints(ph, x, hv);
+      for (int i = 0; i < ph.n_td; ++i) {
+        maxh = fmax(maxh, fabs(hv[i]));
+        ph.ht[((size_t)a * 4 + i) * ldb + b] = hv[i];
+        if (S.opt.AL_active) {
+          const double sg = ph.al_sigma[(size_t)i * ldb + b], lm = ph.al_lambda[(size_t)i * ldb + b];
+          double c = 0;
+          c += 0.5 * sg * hv[i] * hv[i];
+          c += lm * hv[i];
+          phi += c;
+        }
+      }
+    }
+    ph.maxh_t[(size_t)a * ldb + b] = maxh;
+    ph.cost_t[aS + (size_t)h * ldb + b] = phi;
+    ph.ming_t[aS + (size_t)h * ldb + b] = 0;
+    double dsq = 0;
+    if (ph.has_next) {
+      const PhaseDev& nx = S.ph[pi + 1];
+      double xr[CAFE_MAX_N];
+      Model::resetmap(ph, x, xr);
+      const size_t aXn = (size_t)a * (nx.h + 1) * nx.n * ldb;
+      for (int i = 0; i < nx.n; ++i) {
+        const double xs = nx.Xbar[gix(0, nx.n, i, ldb, b)] + eps * nx.dX[gix(0, nx.n, i, ldb, b)];
+        const double d = xr[i] - xs;
+        nx.Dt[aXn + gix(0, nx.n, i, ldb, b)] = d;
+        dsq += d * d;
+      }
+    }
+    ph.feas_t[aS + (size_t)h * ldb + b] = dsq;
+  }
+}
+
+// step sizes [a0, a1) of the ladder; problems whose line search already succeeded are skipped
+__global__ void __launch_bounds__(128, 4) k_roll(const SolverDev* __restrict__ Sp, int a0, int a1) {
+  const SolverDev& S = *Sp;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = (int)(t % S.ldb);
+  const long long r = t / S.ldb;
+  const int gk = (int)(r % S.n_knots), a = a0 + (int)(r / S.n_knots);
+  if (a >= a1 || b >= S.B) return;
+  if (!S.c.active[b] || !S.c.do_ls[b] || S.c.ls_found[b]) return;
+  const int pi = S.knot_phase[gk], k = S.knot_k[gk];
+  switch (S.ph[pi].model) {
+    case CAFE_MODEL_HKD: roll_knot<HKDModel>(S, pi, k, a, b); break;
+    case CAFE_MODEL_WB: roll_knot<WBModel>(S, pi, k, a, b); break;
+    case CAFE_MODEL_SRB: roll_knot<SRBModel>(S, pi, k, a, b); break;
+    default: break;
+  }
+}
+
+// --------------------------------------------------------------------------------------------- K-LQ
+template <class Model>
+__device__ void lq_knot_generic(const SolverDev& S, int pi, int k, int b) {
+  constexpr int N = Model::N, M = Model::M, PY = Model::PY;
+  const PhaseDev& ph = S.ph[pi];
+  const int ldb = S.ldb, h = ph.h;
+  const double* rec = ph.ref + (size_t)k * CAFE_REF_W;
+  double x[N];
+  double dsq = 0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) { x[i] = ph.X[gix(k, N, i, ldb, b)]; const double d = ph.Defect[gix(k, N, i, ldb, b)]; dsq += d * d; }
+  ph.dsq[(size_t)k * ldb + b] = dsq;
+  if (k < h) {
+    double u[M], y[PY > 0 ? PY : 1];
+#pragma unroll
+    for (int i = 0; i < M; ++i) u[i] = ph.U[gix(k, M, i, ldb, b)];
+#pragma unroll
+    for (int i = 0; i < PY; ++i) y[i] = ph.Y[gix(k, PY, i, ldb, b)];
+    ph.lk[(size_t)k * ldb + b] = Model::lq_knot(ph, k, ldb, b, rec, x, u, y, S.opt.ReB_active != 0);
+  } else {
+    double phi = Model::terminal_cost(ph, rec, x);
+    if (ph.n_td > 0 && S.opt.AL_active) {
+      double hv[4];
+      Model::terminal_constraints(ph, x, hv);
+      for (int i = 0; i < ph.n_td; ++i) {
+        const double sg = ph.al_sigma[(size_t)i * ldb + b], lm = ph.al_lambda[(size_t)i * ldb + b];
+        double c = 0;
+        c += 0.5 * sg * hv[i] * hv[i];
+        c += lm * hv[i];
+        phi += c;
+      }
+    }
+    ph.lk[(size_t)h * ldb + b] = phi;
+    Model::lq_terminal(ph, ldb, b, rec, x, S.opt.AL_active != 0);
+  }
+}
+
+__global__ void __launch_bounds__(128, 4) k_lq(const SolverDev* __restrict__ Sp) {
+  const SolverDev& S = *Sp;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = (int)(t % S.ldb);
+  const int gk = (int)(t / S.ldb);
+  if (gk >= S.n_knots || b >= S.B) return;
+  if (!S.c.active[b]) return;
+  const int pi = S.knot_phase[gk], k = S.knot_k[gk];
+  switch (S.ph[pi].model) {
+    case CAFE_MODEL_HKD: lq_knot_generic<HKDModel>(S, pi, k, b); break;
+    case CAFE_MODEL_WB: lq_knot_generic<WBModel>(S, pi, k, b); break;
+    case CAFE_MODEL_SRB: lq_knot_generic<SRBModel>(S, pi, k, b); break;
+    default: break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ K-ACCEPT
+__global__ void k_accept(const SolverDev* __restrict__ Sp) {
+  const SolverDev& S = *Sp;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = (int)(t % S.ldb);
+  const int gk = (int)(t / S.ldb);
+  if (gk >= S.n_knots || b >= S.B) return;
+  const int a = S.c.sel[b];
+  if (a < 0) return;
+  const bool acc = S.c.accepted[b] != 0;
+  const int pi = S.knot_phase[gk], k = S.knot_k[gk];
+  const PhaseDev& ph = S.ph[pi];
+  const int ldb = S.ldb, h = ph.h, n = ph.n, m = ph.m, p = ph.p;
+  const size_t aX = (size_t)a * (h + 1) * n * ldb, aU = (size_t)a * h * m * ldb, aY = (size_t)a * h * p * ldb;
+  for (int i = 0; i < n; ++i) {
+    const size_t ix = gix(k, n, i, ldb, b);
+    const double v = ph.Xt[aX + ix];
+    ph.X[ix] = v;
+    ph.Defect[ix] = ph.Dt[aX + ix];
+    if (acc) ph.Xbar[ix] = v;
+  }
+  if (k < h) {
+    for (int i = 0; i < m; ++i) {
+      const size_t ix = gix(k, m, i, ldb, b);
+      const double v = ph.Ut[aU + ix];
+      ph.U[ix] = v;
+      if (acc) ph.Ubar[ix] = v;
+    }
+    for (int i = 0; i < p; ++i) { const size_t ix = gix(k, p, i, ldb, b); ph.Y[ix] = ph.Yt[aY + ix]; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ K-SELECT
+__device__ __forceinline__ void push_hist(const SolverDev& S, int b, double cost, double feas, double mt, double mp) {
+  int nh = S.c.n_hist[b];
+  if (nh < CAFE_HIST_CAP) {
+    double* hp = S.c.hist + ((size_t)nh * 4) * S.ldb + b;
+    hp[0] = cost; hp[(size_t)S.ldb] = feas; hp[(size_t)2 * S.ldb] = mt; hp[(size_t)3 * S.ldb] = mp;
+  }
+  S.c.n_hist[b] = nh + 1;
+}
+
+// sum of the per-knot partials of trial a in the reference's order: per phase (sum_k l_k) + Phi, then over phases
+__device__ void reduce_trial(const SolverDev& S, int a, int b, double& cost, double& feas, double& max_t, double& max_p, int& fail) {
+  const int ldb = S.ldb;
+  cost = 0;
+  double fs = 0;
+  max_t = 0; max_p = 0; fail = 0;
+  for (int pi = 0; pi < S.n_phases; ++pi) {
+    const PhaseDev& ph = S.ph[pi];
+    const size_t aS = (size_t)a * (ph.h + 1) * ldb;
+    double pc = 0, pf = 0, pm = 0;
+    if (pi == 0) pf += S.c.feas0_t[(size_t)a * ldb + b];
+    else pf += S.ph[pi - 1].feas_t[(size_t)a * (S.ph[pi - 1].h + 1) * ldb + (size_t)S.ph[pi - 1].h * ldb + b];
+    for (int k = 0; k < ph.h; ++k) {
+      pc += ph.cost_t[aS + (size_t)k * ldb + b];
+      pf += ph.feas_t[aS + (size_t)k * ldb + b];
+      pm = fmin(pm, ph.ming_t[aS + (size_t)k * ldb + b]);
+    }
+    pc += ph.cost_t[aS + (size_t)ph.h * ldb + b];
+    cost += pc;
+    fs += pf;
+    max_p = fmin(max_p, pm);
+    max_t = fmax(max_t, ph.maxh_t[(size_t)a * ldb + b]);
+    fail |= ph.fail_t[(size_t)a * ldb + b];
+  }
+  feas = sqrt(fs);
+}
+
+// Armijo test over the step sizes [a0, a1) that k_roll has just evaluated (MultiPhaseDDP::line_search, MultiPhaseDDP.cpp:95-133):
+// keeps the FIRST (largest) successful step size, else the last evaluated one; counts the problems that need more trials.
+__global__ void k_ls_scan(const SolverDev* __restrict__ Sp, int a0, int a1) {
+  const SolverDev& S = *Sp;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= S.B) return;
+  const CtrlDev& c = S.c;
+  if (!c.active[b] || !c.do_ls[b] || c.ls_found[b]) return;
+  const CafeOptions& o = S.opt;
+  const double merit_prev = c.merit_prev[b], feas_prev = c.feas[b], rho = c.merit_rho[b], dV1 = c.dV1[b], dV2 = c.dV2[b];
+  for (int a = a0; a < a1; ++a) {
+    double cost, feas, mt, mp; int fail;
+    reduce_trial(S, a, b, cost, feas, mt, mp, fail);
+    const double eps = S.eps[a];
+    const double merit = cost + rho * feas;
+    const double exp_cost_change = eps * dV1 + 0.5 * eps * eps * dV2;
+    const double exp_merit_change = exp_cost_change - eps * rho * feas_prev;
+    c.sel[b] = a; c.ls_cost[b] = cost; c.ls_feas[b] = feas; c.ls_mt[b] = mt; c.ls_mp[b] = mp; c.ls_fail[b] = fail; c.ls_merit[b] = merit;
+    if ((merit <= merit_prev + o.gamma * exp_merit_change) && !fail) { c.ls_found[b] = 1; return; }
+  }
+  if (a1 < S.NA) atomicAdd(c.n_pending, 1);
+}
+
+// mode 0: initial rollout bookkeeping (MultiPhaseDDP.cpp:238-261); mode 1: after a DDP iteration
+__global__ void k_select(const SolverDev* __restrict__ Sp, int mode) {
+  const SolverDev& S = *Sp;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= S.B) return;
+  const CtrlDev& c = S.c;
+  const CafeOptions& o = S.opt;
+  const int ldb = S.ldb;
+  if (!c.active[b]) { c.sel[b] = -1; return; }
+  if (mode == 0 || !c.do_ls[b]) c.sel[b] = -1;
+  bool inner_done = false;
+  if (mode == 0) {
+    double cost, feas, mt, mp; int fail;
+    reduce_trial(S, 0, b, cost, feas, mt, mp, fail);
+    c.sel[b] = 0; c.accepted[b] = 1;
+    c.cost[b] = cost; c.feas[b] = feas; c.max_t[b] = mt; c.max_p[b] = mp;
+    for (int pi = 0; pi < S.n_phases; ++pi) for (int i = 0; i < S.ph[pi].n_td; ++i) S.ph[pi].hval[(size_t)i * ldb + b] = S.ph[pi].ht[(size_t)i * ldb + b];
+    c.n_hist[b] = 0;
+    push_hist(S, b, cost, feas, mt, mp);
+    if (fail) c.status[b] = CAFE_STATUS_DIVERGED;
+    c.iter_ou[b] = 0;
+    // enter the outer loop (MultiPhaseDDP.cpp:264-276)
+    if (c.iter_ou[b] < o.max_AL_iter) {
+      c.iter_ou[b] = 1; c.max_t_prev[b] = mt; c.max_p_prev[b] = mp; c.reg[b] = 0; c.iter_in[b] = 0;
+      if (o.max_DDP_iter <= 0) inner_done = true;
+    } else { c.active[b] = 0; }
+    if (!inner_done) { if (c.active[b]) atomicAdd(c.n_active, 1); return; }
+  } else {
+    const int it = c.iter[b] - 1;  // trace slot of this iteration
+    double* tr = (it >= 0 && it < CAFE_HIST_CAP) ? c.trace + ((size_t)it * 12) * ldb + b : nullptr;
+    if (c.do_ls[b]) {
+      const double merit_prev = c.merit_prev[b], cost_prev = c.cost_prev[b];
+      const bool success = c.ls_found[b] != 0;
+      const int sel = c.sel[b];
+      const int n_ls = success ? sel + 1 : S.NA;
+      const double cost_s = c.ls_cost[b], feas_s = c.ls_feas[b], mt_s = c.ls_mt[b], mp_s = c.ls_mp[b];
+      const int fail_s = c.ls_fail[b];
+      if (success) c.merit[b] = c.ls_merit[b];
+      c.accepted[b] = success ? 1 : 0;
+      c.ls_total[b] += n_ls;
+      c.feas[b] = feas_s; c.max_t[b] = mt_s; c.max_p[b] = mp_s;
+      for (int pi = 0; pi < S.n_phases; ++pi) for (int i = 0; i < S.ph[pi].n_td; ++i) S.ph[pi].hval[(size_t)i * ldb + b] = S.ph[pi].ht[((size_t)sel * 4 + i) * ldb + b];
+      if (success) c.cost[b] = cost_s;
+      else { c.cost[b] = cost_prev; c.merit[b] = merit_prev; if (fail_s) c.status[b] = CAFE_STATUS_DIVERGED; }
+      if (tr) { tr[(size_t)7 * ldb] = n_ls; tr[(size_t)8 * ldb] = success ? 1 : 0; tr[(size_t)9 * ldb] = success ? S.eps[sel] : 0; tr[(size_t)10 * ldb] = c.cost[b]; tr[(size_t)11 * ldb] = c.feas[b]; }
+      const double cost_now = c.cost[b];
+      if ((fabs((cost_prev - cost_now) / cost_prev) < o.cost_thresh) && (c.feas[b] <= o.dynamics_feas_thresh)) inner_done = true;
+      else push_hist(S, b, cost_now, c.feas[b], c.max_t[b], c.max_p[b]);
+    } else {
+      inner_done = true;  // early exit taken in k_bwd (MultiPhaseDDP.cpp:345-349)
+      if (tr) { tr[(size_t)10 * ldb] = c.cost[b]; tr[(size_t)11 * ldb] = c.feas[b]; }
+    }
+    if (!inner_done && c.iter_in[b] >= o.max_DDP_iter) inner_done = true;
+    if (!inner_done) { atomicAdd(c.n_active, 1); return; }
+  }
+  // ---- end of an outer iteration (MultiPhaseDDP.cpp:394-425)
+  while (true) {
+    const double mt = c.max_t[b], mp = c.max_p[b], feas = c.feas[b];
+    if (mt < o.tconstr_thresh && fabs(mp) < o.pconstr_thresh && feas <= o.dynamics_feas_thresh) { c.active[b] = 0; break; }
+    if (fabs(mt - c.max_t_prev[b]) < 0.0001 && fabs(mp - c.max_p_prev[b]) < 0.0001 && feas <= o.dynamics_feas_thresh) { c.active[b] = 0; break; }
+    if (o.AL_active) {
+      for (int pi = 0; pi < S.n_phases; ++pi) {
+        const PhaseDev& ph = S.ph[pi];
+        for (int i = 0; i < ph.n_td; ++i) {  // TerminalConstraintBase::update_params (ConstraintsBase.h:375-391)
+          const double hv = ph.hval[(size_t)i * ldb + b];
+          if (fabs(hv) < o.tconstr_thresh) continue;
+          if (fabs(hv) > 0.005) { double sg = ph.al_sigma[(size_t)i * ldb + b] * o.update_penalty; ph.al_sigma[(size_t)i * ldb + b] = fmin(sg, ph.al_td.sigma_max); }
+          else ph.al_lambda[(size_t)i * ldb + b] += hv * ph.al_sigma[(size_t)i * ldb + b];
+        }
+      }
+    }
+    /* ReB update: with update_relax == update_ReB == 1 and delta >= delta_min (checked at create) it is the identity */
+    if (c.iter_ou[b] >= o.max_AL_iter) { c.active[b] = 0; break; }
+    c.iter_ou[b] += 1; c.max_t_prev[b] = mt; c.max_p_prev[b] = mp; c.reg[b] = 0; c.iter_in[b] = 0;
+    if (o.max_DDP_iter > 0) break;
+  }
+  if (c.active[b]) atomicAdd(c.n_active, 1);
+}
+
+}  // namespace cafe_dev

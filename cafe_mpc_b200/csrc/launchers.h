@@ -1,0 +1,12 @@
+// launchers.h — host-callable launch wrappers of the kernels that live in knot_kernels.cu
+#pragma once
+#include <cuda_runtime.h>
+#include "device_types.cuh"
+
+namespace cafe_dev {
+void launch_roll(const SolverDev* dS, long long nthreads, cudaStream_t st, int a0, int a1);
+void launch_lq(const SolverDev* dS, long long nthreads, cudaStream_t st);
+void launch_accept(const SolverDev* dS, long long nthreads, cudaStream_t st);
+void launch_ls_scan(const SolverDev* dS, int B, cudaStream_t st, int a0, int a1);
+void launch_select(const SolverDev* dS, int B, cudaStream_t st, int mode);
+}  // namespace cafe_dev

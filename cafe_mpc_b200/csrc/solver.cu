@@ -11,8 +11,9 @@
 #include <vector>
 #include <cuda_runtime.h>
 #include "../../include/cafe_gpu.h"
-#include "kernels.cuh"
+#include "dense_kernels.cuh"
 #include "bwd2.cuh"
+#include "launchers.h"
 
 namespace cafe { void set_last_error(const std::string& s); }
 
@@ -364,9 +365,9 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
     SolverDev S0 = S;  // same pointers, ladder {0}
     S0.NA = 1; S0.eps[0] = 0.0;
     CUDA_OK(cudaMemcpyAsync(H->dS, &S0, sizeof(SolverDev), cudaMemcpyHostToDevice, st));
-    timed(H, 0, [&] { cafe_dev::k_roll<<<g_knots, tpb, 0, st>>>(H->dS, 0, 1); });
-    timed(H, 1, [&] { cafe_dev::k_select<<<(B + 127) / 128, 128, 0, st>>>(H->dS, 0); });
-    timed(H, 2, [&] { cafe_dev::k_accept<<<g_knots, tpb, 0, st>>>(H->dS); });
+    timed(H, 0, [&] { cafe_dev::launch_roll(H->dS, nthr_knots, st, 0, 1); });
+    timed(H, 1, [&] { cafe_dev::launch_select(H->dS, B, st, 0); });
+    timed(H, 2, [&] { cafe_dev::launch_accept(H->dS, nthr_knots, st); });
     CUDA_OK(cudaStreamSynchronize(st));  // S0 must stay alive until the copy has been consumed
     CUDA_OK(cudaMemcpyAsync(H->dS, &S, sizeof(SolverDev), cudaMemcpyHostToDevice, st));
   }
@@ -376,25 +377,24 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
     CUDA_OK(cudaStreamSynchronize(st));
     if (*H->h_nactive == 0) break;
     H->ticks++;
-    timed(H, 3, [&] { cafe_dev::k_lq<<<g_knots, tpb, 0, st>>>(H->dS); });
+    timed(H, 3, [&] { cafe_dev::launch_lq(H->dS, nthr_knots, st); });
     if (H->bwd_variant == 1) timed(H, 5, [&] { launch_lq_wb_dense(H); });
     timed(H, 4, [&] { launch_bwd(H); });
     CUDA_OK(cudaMemsetAsync(H->d_fail, 0, H->fail_bytes, st));
     // staged line search: step sizes are evaluated in growing groups; most problems accept one of the first
     for (int a0 = 0, width = 1; a0 < S.NA; a0 += width, width *= 2) {
       const int a1 = (a0 + width < S.NA) ? a0 + width : S.NA;
-      const unsigned g_stage = (unsigned)((nthr_knots * (a1 - a0) + tpb - 1) / tpb);
-      timed(H, 0, [&] { cafe_dev::k_roll<<<g_stage, tpb, 0, st>>>(H->dS, a0, a1); });
+      timed(H, 0, [&] { cafe_dev::launch_roll(H->dS, nthr_knots * (a1 - a0), st, a0, a1); });
       CUDA_OK(cudaMemsetAsync(S.c.n_pending, 0, sizeof(int), st));
-      timed(H, 1, [&] { cafe_dev::k_ls_scan<<<(B + 127) / 128, 128, 0, st>>>(H->dS, a0, a1); });
+      timed(H, 1, [&] { cafe_dev::launch_ls_scan(H->dS, B, st, a0, a1); });
       if (a1 >= S.NA) break;
       CUDA_OK(cudaMemcpyAsync(H->h_nactive + 1, S.c.n_pending, sizeof(int), cudaMemcpyDeviceToHost, st));
       CUDA_OK(cudaStreamSynchronize(st));
       if (H->h_nactive[1] == 0) break;
     }
     CUDA_OK(cudaMemsetAsync(S.c.n_active, 0, sizeof(int), st));
-    timed(H, 1, [&] { cafe_dev::k_select<<<(B + 127) / 128, 128, 0, st>>>(H->dS, 1); });
-    timed(H, 2, [&] { cafe_dev::k_accept<<<g_knots, tpb, 0, st>>>(H->dS); });
+    timed(H, 1, [&] { cafe_dev::launch_select(H->dS, B, st, 1); });
+    timed(H, 2, [&] { cafe_dev::launch_accept(H->dS, nthr_knots, st); });
   }
   CUDA_OK(cudaEventRecord(H->eve, st));
   CUDA_OK(cudaStreamSynchronize(st));
