@@ -11,12 +11,30 @@
 //     an 8 x NT/8 thread grid (25-36 independent accumulators per thread),
 //   * the whole-body phases use the block structure A = [[I, dt I],[A21, A22]], B = [0; B2]: only P = H[:,18:36] enters the
 //     products (T = P [A2 B2] + epilogue, Qxx = A2^T T2 + epilogue, ...): ~40 % fewer flops, half the operand footprint,
-//   * LDL^T of (Quu - 1e-9 I) runs in one warp with warp-level barriers, the solves for [K | dU] keep each right-hand-side
-//     column in registers (thread = column) and use reciprocal pivots.
+//   * LDL^T of (Quu - 1e-9 I) and the solves for [K | dU] are one register-resident elimination (thread = column of
+//     [Quu | Qux | Qu], one 64-thread named barrier per pivot), the other warps write the outputs and prefetch meanwhile,
+//   * the solver descriptor is a __grid_constant__ kernel parameter: phase pointers and dimensions are constant-bank operands
+//     (the L1 left beside ~210 KB of shared memory is too small to keep a descriptor in global memory resident),
+//   * every per-knot operand is fetched with 8-byte cp.async (LDGSTS) straight into its shared-memory tile: the sweep issues the
+//     copies of knot k-1 as soon as the Q functions of knot k are formed (A, B, C, D tiles are dead then) and waits for them
+//     only at the top of the next iteration, the linear rollout double-buffers whole knots. No registers are spent on
+//     staging and the ~1 us global latency is hidden behind the factorisation / solves.
 #pragma once
+#include <cooperative_groups.h>
 #include "device_types.cuh"
 
 namespace cafe_dev {
+
+__device__ __forceinline__ void cp_async8(double* dst_smem, const double* src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+// pacing barrier of the CTA cluster (no memory ordering needed: it only keeps the four problems that share every 32-byte
+// sector of the problem-fastest arrays at the same knot, so that one DRAM fetch serves all four through L2)
+__device__ __forceinline__ void cluster_pace() { asm volatile("barrier.cluster.arrive.relaxed.aligned;\nbarrier.cluster.wait.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l1(const double* p) { asm volatile("prefetch.global.L1 [%0];\n" ::"l"(p)); }
 
 // C(i,j) = epi(i,j, sum_{l<KK} opA(i,l) B(l,j) + sum_{l<KK2} A2[l + lda2*i] B2[l + ldb2*j])   for i < MM, j < NN
 //   opA(i,l) = TA ? A[l + lda*i] : A[i + lda*l];  B(l,j) = B[l + ldb*j]; thread grid 8 x NT/8
@@ -75,15 +93,24 @@ struct Bwd2Layout {
   static constexpr int vG = 0, vGn = NX, vQx = 2 * NX, vD = 3 * NX, vDx = 4 * NX, vDxn = 5 * NX, vQu = 6 * NX, vDu = 6 * NX + MX,
                        vDuL = 6 * NX + 2 * MX, vLy = 6 * NX + 3 * MX, vRed = vLy + PX + 1, nVec = vRed + 2 * 128 + 1;
   static constexpr int oH = nVec;                       // H / Qxx / H_new      NX x NX (ldH)
-  static constexpr int oAB = oH + ldH * NX;             // [A B] rows KA (ldA) x (NX+MX); reused for [K | dU] (MX x (NX+1), ldM)
-  static constexpr int szAB = (ldA * (NX + MX) > ldM * (NX + 1)) ? ldA * (NX + MX) : ldM * (NX + 1);
+  static constexpr int oAB = oH + ldH * NX;             // [A B] rows KA (ldA) x (NX+MX)
+  static constexpr int szAB = ldA * (NX + MX);
   static constexpr int oT = oAB + szAB;                 // T = H [A B]  NX x (NX+MX) (ldH); reused for L (MX x MX, ldM)
   static constexpr int oQux = oT + ldH * (NX + MX);     // Qux MX x NX (ldM)
   static constexpr int oQuu = oQux + ldM * NX;          // Quu MX x MX (ldM)
   static constexpr int oCD = oQuu + ldM * MX;           // [C D]  PX x (NX+MX) (ldP)
-  static constexpr int oSCD = oCD + (PX > 0 ? ldP * (NX + MX) : 0);   // lyy [C D]
+  static constexpr int oSCD = oCD + (PX > 0 ? ldP * (NX + MX) : 0);   // lyy [C D]; reused for [K | dU] when PX > 0
   static constexpr int oLyy = oSCD + (PX > 0 ? ldP * (NX + MX) : 0);  // lyy PX x PX (ldP)
-  static constexpr int total = oLyy + (PX > 0 ? ldP * PX : 0) + 2;
+  static constexpr int szK = ldM * (NX + 1);            // [K | dU]  MX x (NX+1) (ldM): its own tile when there is no lyy [C D] tile
+  static constexpr int oK = PX > 0 ? oSCD : oLyy;
+  static constexpr int endSweep = (PX > 0 ? oLyy + ldP * PX : oK + szK) + 2;
+  static_assert(PX == 0 || szK <= ldP * (NX + MX), "[K | dU] does not fit the lyy [C D] tile");
+  // linear rollout: two stages of {K, A(stored rows), B, lxx, luu, lx, lu, d, dU}
+  static constexpr int lK = 0, lA = lK + ldM * NX, lB = lA + ldA * NX, lLxx = lB + ldA * MX, lLuu = lLxx + ldH * NX, lLx = lLuu + ldM * MX,
+                       lLu = lLx + NX, lD = lLu + MX, lDU = lD + NX, szLin = (lDU + MX + 1) | 1;
+  static constexpr int oLin = nVec;
+  static constexpr int endLin = oLin + 2 * szLin;
+  static constexpr int total = endSweep > endLin ? endSweep : endLin;
 };
 
 // One phase of the sweep. N, M, PY: phase dimensions; NNEXT: state dimension of the next phase (for the jump); WB: use the
@@ -99,7 +126,7 @@ __device__ void sweep_phase2(const SolverDev& S, int pi, int b, int t, bool run,
   double* sQu = sm + L::vQu; double* sDu = sm + L::vDu; double* sLy = sm + L::vLy;
   double* sH = sm + L::oH; double* sAB = sm + L::oAB; double* sT = sm + L::oT; double* sQux = sm + L::oQux; double* sQuu = sm + L::oQuu;
   double* sCD = sm + L::oCD; double* sSCD = sm + L::oSCD; double* sLyy = sm + L::oLyy;
-  double* sK = sAB;   // [K | dU] after A, B are dead
+  double* sK = sm + L::oK;   // [K | dU] (over lyy [C D], dead once the Q functions are formed)
   double* sL = sT;    // LDL^T factor after T is dead
   (void)sLy; (void)sCD; (void)sSCD; (void)sLyy;
   const double dt = ph.dt;
@@ -129,26 +156,30 @@ __device__ void sweep_phase2(const SolverDev& S, int pi, int b, int t, bool run,
   __syncthreads();
   if (run && ok) for (int j = t; j < N; j += NT) ph.G[gix(h, N, j, ldb, b)] = sG[j];
 
+  // asynchronous staging of [A B] (stored rows), [C D], lyy, ly, Defect[k+1] of knot k into their tiles
+  auto stage = [&](int k, int t0, int nt) {
+    const double* Ag = ph.A + gix(k, N * N, 0, ldb, b);
+    for (int e = t0; e < KA * N; e += nt) { const int i = e % KA, j = e / KA; cp_async8(sAB + i + ldA * j, Ag + (size_t)((R0 + i) + N * j) * ldb); }
+    const double* Bg = ph.Bm + gix(k, N * M, 0, ldb, b);
+    for (int e = t0; e < KA * M; e += nt) { const int i = e % KA, j = e / KA; cp_async8(sAB + i + ldA * (N + j), Bg + (size_t)((R0 + i) + N * j) * ldb); }
+    for (int j = t0; j < N; j += nt) cp_async8(sD + j, ph.Defect + gix(k + 1, N, j, ldb, b));
+    if constexpr (PY > 0) {
+      const double* Cg = ph.C + gix(k, PY * N, 0, ldb, b);
+      for (int e = t0; e < PY * N; e += nt) cp_async8(sCD + (e % PY) + ldP * (e / PY), Cg + (size_t)e * ldb);
+      const double* Dg = ph.D + gix(k, PY * M, 0, ldb, b);
+      for (int e = t0; e < PY * M; e += nt) cp_async8(sCD + (e % PY) + ldP * (N + e / PY), Dg + (size_t)e * ldb);
+      const double* Lg = ph.lyy + gix(k, PY * PY, 0, ldb, b);
+      for (int e = t0; e < PY * PY; e += nt) cp_async8(sLyy + (e % PY) + ldP * (e / PY), Lg + (size_t)e * ldb);
+      for (int j = t0; j < PY; j += nt) cp_async8(sLy + j, ph.ly + gix(k, PY, j, ldb, b));
+    }
+    cp_async_commit();
+  };
+  if (run && ok && h > 0) stage(h - 1, t, NT);
   for (int k = h - 1; k >= 0; --k) {
     const bool a2 = run && ok;
-    // ---- stage [A B] (stored rows), [C D], lyy, ly, Defect[k+1]
-    if (a2) {
-      const double* Ag = ph.A + gix(k, N * N, 0, ldb, b);
-      for (int e = t; e < KA * N; e += NT) { const int i = e % KA, j = e / KA; sAB[i + ldA * j] = Ag[(size_t)((R0 + i) + N * j) * ldb]; }
-      const double* Bg = ph.Bm + gix(k, N * M, 0, ldb, b);
-      for (int e = t; e < KA * M; e += NT) { const int i = e % KA, j = e / KA; sAB[i + ldA * (N + j)] = Bg[(size_t)((R0 + i) + N * j) * ldb]; }
-      for (int j = t; j < N; j += NT) sD[j] = ph.Defect[gix(k + 1, N, j, ldb, b)];
-      if constexpr (PY > 0) {
-        const double* Cg = ph.C + gix(k, PY * N, 0, ldb, b);
-        for (int e = t; e < PY * N; e += NT) sCD[(e % PY) + ldP * (e / PY)] = Cg[(size_t)e * ldb];
-        const double* Dg = ph.D + gix(k, PY * M, 0, ldb, b);
-        for (int e = t; e < PY * M; e += NT) sCD[(e % PY) + ldP * (N + e / PY)] = Dg[(size_t)e * ldb];
-        const double* Lg = ph.lyy + gix(k, PY * PY, 0, ldb, b);
-        for (int e = t; e < PY * PY; e += NT) sLyy[(e % PY) + ldP * (e / PY)] = Lg[(size_t)e * ldb];
-        for (int j = t; j < PY; j += NT) sLy[j] = ph.ly[gix(k, PY, j, ldb, b)];
-      }
-    }
+    cp_async_wait_all();
     __syncthreads();
+    cluster_pace();
     // ---- Gn = G + H d ; T = H [A B] ; S[C D] = lyy [C D]
     if (a2) for (int i = t; i < N; i += NT) { double s = sG[i]; for (int j = 0; j < N; ++j) s += sH[i + ldH * j] * sD[j]; sGn[i] = s; }
     if constexpr (WB) {
@@ -166,6 +197,11 @@ __device__ void sweep_phase2(const SolverDev& S, int pi, int b, int t, bool run,
     __syncthreads();
     // ---- Q functions (H is dead from here on: Qxx is written over it)
     if (a2) {
+      // the epilogues below add lxx / luu from global memory: start pulling them into L1 now
+      const double* lxxp = ph.lxx + gix(k, N * N, 0, ldb, b);
+      for (int e = t; e < N * N; e += NT) prefetch_l1(lxxp + (size_t)e * ldb);
+      const double* luup = ph.luu + gix(k, M * M, 0, ldb, b);
+      for (int e = t; e < M * M; e += NT) prefetch_l1(luup + (size_t)e * ldb);
       for (int j = t; j < N + M; j += NT) {
         double s = (j < N) ? ph.lx[gix(k, N, j, ldb, b)] : ph.lu[gix(k, M, j - N, ldb, b)];
         for (int i = 0; i < KA; ++i) s += sAB[i + ldA * j] * sGn[R0 + i];
@@ -195,61 +231,70 @@ __device__ void sweep_phase2(const SolverDev& S, int pi, int b, int t, bool run,
       });
     }
     __syncthreads();
-    // ---- outputs Quu, Qux, Qu; copies for the factorisation / solves (A, B, T are dead)
+    // ---- factorisation and solves, fused. Thread c < M+N+1 of the first NE threads keeps column c of
+    //      [Quu - 1e-9 I | Qux | Qu] in registers; at step j the owner of column j publishes the pivot and the multipliers
+    //      l_ij, every later column is updated in registers (Schur update of the matrix columns = forward substitution of the
+    //      right-hand sides). PD test (Eigen's isPositive on Quu - 1e-9 I, SinglePhase.cpp:157-165) = every pivot > 0.
+    //      The remaining warps meanwhile write Quu, Qux, Qu and start fetching knot k-1 (A, B, C, D, lyy, ly, d tiles are dead).
+    constexpr int NC = M + N + 1, NE = (NC + 31) / 32 * 32;
+    constexpr bool SPLIT = NT > NE;
     if (a2) {
-      double* Quug = ph.Quu + gix(k, M * M, 0, ldb, b);
-      for (int e = t; e < M * M; e += NT) { const int i = e % M, j = e / M; const double v = sQuu[i + ldM * j]; Quug[(size_t)e * ldb] = v; sL[i + ldM * j] = (i == j) ? v - 1e-9 : v; }
-      double* Quxg = ph.Qux + gix(k, M * N, 0, ldb, b);
-      for (int e = t; e < M * N; e += NT) { const int i = e % M, j = e / M; const double v = sQux[i + ldM * j]; Quxg[(size_t)e * ldb] = v; sK[i + ldM * j] = v; }
-      for (int j = t; j < M; j += NT) { const double v = sQu[j]; ph.Qu[gix(k, M, j, ldb, b)] = v; sK[j + ldM * N] = v; }
-    }
-    __syncthreads();
-    // ---- LDL^T of (Quu - 1e-9 I) by warp 0 (lane = row), pivots replaced by their reciprocals; PD test = every pivot > 0
-    if (t < 32 && run && ok) {
-      bool okw = true;
-      for (int j = 0; j < M; ++j) {
-        const double d = sL[j + ldM * j];
-        if (!(d > 0.0)) { okw = false; break; }
-        min_piv = fmin(min_piv, d);
-        const double inv = 1.0 / d;
-        const int i = j + 1 + t;
-        double vi = 0;
-        if (i < M) {
-          vi = sL[i + ldM * j] * inv;
-          for (int cc = j + 1; cc <= i; ++cc) sL[i + ldM * cc] -= vi * sL[cc + ldM * j];  // column j is read unscaled by every lane
-        }
-        __syncwarp();
-        if (i < M) sL[i + ldM * j] = vi;
-        if (t == 0) sL[j + ldM * j] = inv;
-        __syncwarp();
+      if (!SPLIT || t >= NE) {
+        const int t0 = SPLIT ? t - NE : t;
+        constexpr int nt = SPLIT ? NT - NE : NT;
+        if (k > 0) stage(k - 1, t0, nt);
+        double* Quug = ph.Quu + gix(k, M * M, 0, ldb, b);
+        for (int e = t0; e < M * M; e += nt) Quug[(size_t)e * ldb] = sQuu[(e % M) + ldM * (e / M)];
+        double* Quxg = ph.Qux + gix(k, M * N, 0, ldb, b);
+        for (int e = t0; e < M * N; e += nt) Quxg[(size_t)e * ldb] = sQux[(e % M) + ldM * (e / M)];
+        for (int j = t0; j < M; j += nt) ph.Qu[gix(k, M, j, ldb, b)] = sQu[j];
       }
-      if (t == 0) sm[L::vRed] = okw ? 1.0 : 0.0;
+      if (t < NE) {
+        double x[M];
+        const double* colp = (t < M) ? sQuu + ldM * t : (t < M + N) ? sQux + ldM * (t - M) : sQu;
+#pragma unroll
+        for (int i = 0; i < M; ++i) x[i] = (t < NC) ? colp[i] : 0.0;
+#pragma unroll
+        for (int i = 0; i < M; ++i) if (i == t) x[i] -= 1e-9;
+        bool pd = true;
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+          if (t == j) {
+            const double d = x[j];
+            sm[L::vRed + 1 + j] = d;
+            const double inv = 1.0 / d;
+            sL[j + ldM * j] = inv;
+#pragma unroll
+            for (int i = j + 1; i < M; ++i) sL[i + ldM * j] = x[i] * inv;
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(NE) : "memory");
+          const double d = sm[L::vRed + 1 + j];
+          if (!(d > 0.0)) { pd = false; break; }
+          min_piv = fmin(min_piv, d);
+          if (t > j) {
+#pragma unroll
+            for (int i = j + 1; i < M; ++i) x[i] -= sL[i + ldM * j] * x[j];
+          }
+        }
+        if (pd && t >= M && t < NC) {
+          // [K | dU] = -(L D L^T)^-1 [Qux | Qu]: x holds L^-1 b
+#pragma unroll
+          for (int i = 0; i < M; ++i) x[i] *= sL[i + ldM * i];
+#pragma unroll
+          for (int i = M - 1; i >= 0; --i) {
+#pragma unroll
+            for (int l = i + 1; l < M; ++l) x[i] -= sL[l + ldM * i] * x[l];
+          }
+          double* col = sK + ldM * (t - M);
+#pragma unroll
+          for (int i = 0; i < M; ++i) col[i] = -x[i];
+        }
+        if (t == 0) sm[L::vRed] = pd ? 1.0 : 0.0;
+      }
     }
     __syncthreads();
     if (run && ok && sm[L::vRed] == 0.0) ok = false;
     const bool a3 = run && ok;
-    // ---- [K | dU] = -(Quu - 1e-9 I)^-1 [Qux | Qu], thread = column
-    if (a3 && t < N + 1) {
-      double x[M];
-      double* col = sK + ldM * t;
-#pragma unroll
-      for (int i = 0; i < M; ++i) x[i] = col[i];
-#pragma unroll
-      for (int i = 0; i < M; ++i) {
-#pragma unroll
-        for (int l = 0; l < i; ++l) x[i] -= sL[i + ldM * l] * x[l];
-      }
-#pragma unroll
-      for (int i = 0; i < M; ++i) x[i] *= sL[i + ldM * i];
-#pragma unroll
-      for (int i = M - 1; i >= 0; --i) {
-#pragma unroll
-        for (int l = i + 1; l < M; ++l) x[i] -= sL[l + ldM * i] * x[l];
-      }
-#pragma unroll
-      for (int i = 0; i < M; ++i) col[i] = -x[i];
-    }
-    __syncthreads();
     // ---- value function: G = Qx + Qux^T dU ; H = sym(Qxx) + Qux^T K
     if (a3) {
       const double* dUs = sK + ldM * N;
@@ -278,87 +323,122 @@ __device__ void sweep_phase2(const SolverDev& S, int pi, int b, int t, bool run,
   __syncthreads();
 }
 
-// multiple-shooting linear rollout of one phase (SinglePhase::linear_rollout), eps = 1; NT threads split the rows
-template <int N, int M, int NT, class L>
-__device__ void lin_phase2(const SolverDev& S, int pi, int b, int t, bool run, double* sm, double& dV1, double& dV2) {
+// multiple-shooting linear rollout of one phase (SinglePhase::linear_rollout), eps = 1. Every knot's operands are staged with
+// cp.async into one of two shared-memory buffers while the previous knot is processed; dx ping-pongs between sDx and sDxn.
+// part1 / part2 accumulate this thread's share of dV_1 / dV_2 over all knots (reduced once by the caller).
+template <int N, int M, bool WB, int NT, class L>
+__device__ void lin_phase2(const SolverDev& S, int pi, int b, int t, bool run, double* sm, double& part1, double& part2) {
   const PhaseDev& ph = S.ph[pi];
   const int ldb = S.ldb, h = ph.h;
-  double* sDx = sm + L::vDx; double* sDxn = sm + L::vDxn; double* sDuL = sm + L::vDuL; double* sRed = sm + L::vRed;
-  if (run) for (int i = t; i < N; i += NT) { const double v = sDx[i] + 1.0 * ph.Defect[gix(0, N, i, ldb, b)]; sDx[i] = v; ph.dX[gix(0, N, i, ldb, b)] = v; }
-  __syncthreads();
+  constexpr int ldH = L::ldH, ldA = L::ldA, ldM = L::ldM;
+  constexpr int KA = WB ? 18 : N, R0 = WB ? 18 : 0;
+  const double dt = ph.dt;
+  double* dxb[2] = {sm + L::vDx, sm + L::vDxn};
+  double* sDuL = sm + L::vDuL;
+  auto stage = [&](int k) {
+    double* B0 = sm + L::oLin + (k & 1) * L::szLin;
+    const double* Kg = ph.K + gix(k, M * N, 0, ldb, b);
+    for (int e = t; e < M * N; e += NT) cp_async8(B0 + L::lK + (e % M) + ldM * (e / M), Kg + (size_t)e * ldb);
+    const double* Ag = ph.A + gix(k, N * N, 0, ldb, b);
+    for (int e = t; e < KA * N; e += NT) { const int i = e % KA, j = e / KA; cp_async8(B0 + L::lA + i + ldA * j, Ag + (size_t)((R0 + i) + N * j) * ldb); }
+    const double* Bg = ph.Bm + gix(k, N * M, 0, ldb, b);
+    for (int e = t; e < KA * M; e += NT) { const int i = e % KA, j = e / KA; cp_async8(B0 + L::lB + i + ldA * j, Bg + (size_t)((R0 + i) + N * j) * ldb); }
+    const double* lxxg = ph.lxx + gix(k, N * N, 0, ldb, b);
+    for (int e = t; e < N * N; e += NT) cp_async8(B0 + L::lLxx + (e % N) + ldH * (e / N), lxxg + (size_t)e * ldb);
+    const double* luug = ph.luu + gix(k, M * M, 0, ldb, b);
+    for (int e = t; e < M * M; e += NT) cp_async8(B0 + L::lLuu + (e % M) + ldM * (e / M), luug + (size_t)e * ldb);
+    for (int j = t; j < N; j += NT) {
+      cp_async8(B0 + L::lLx + j, ph.lx + gix(k, N, j, ldb, b));
+      cp_async8(B0 + L::lD + j, ph.Defect + gix(k + 1, N, j, ldb, b));
+    }
+    for (int j = t; j < M; j += NT) {
+      cp_async8(B0 + L::lLu + j, ph.lu + gix(k, M, j, ldb, b));
+      cp_async8(B0 + L::lDU + j, ph.dU + gix(k, M, j, ldb, b));
+    }
+    cp_async_commit();
+  };
+  if (run && h > 0) stage(0);
+  // on entry sDx holds the state perturbation handed over by the previous phase (or zero)
+  if (run) for (int i = t; i < N; i += NT) { const double v = dxb[0][i] + 1.0 * ph.Defect[gix(0, N, i, ldb, b)]; dxb[0][i] = v; ph.dX[gix(0, N, i, ldb, b)] = v; }
   for (int k = 0; k < h; ++k) {
-    double part1 = 0, part2 = 0;
+    const double* B0 = sm + L::oLin + (k & 1) * L::szLin;
+    const double* dx = dxb[k & 1];
+    double* dxn = dxb[(k + 1) & 1];
+    cp_async_wait_all();
+    __syncthreads();
+    cluster_pace();
     if (run) {
-      const double* Kg = ph.K + gix(k, M * N, 0, ldb, b);
-      for (int i = t; i < M; i += NT) {
+      if (k + 1 < h) stage(k + 1);
+      // du = dU + K dx (threads 0..M-1);  dV terms of the state (threads of the upper warps)
+      if (t < M) {
         double s = 0;
-        for (int j = 0; j < N; ++j) s += Kg[(size_t)(i + M * j) * ldb] * sDx[j];
-        sDuL[i] = 1.0 * ph.dU[gix(k, M, i, ldb, b)] + s;
+        for (int j = 0; j < N; ++j) s += B0[L::lK + t + ldM * j] * dx[j];
+        sDuL[t] = 1.0 * B0[L::lDU + t] + s;
+      }
+      constexpr int T1 = (NT >= 64 + N) ? 64 : (NT >= 32 + N ? 32 : 0);  // first thread of the lxx rows
+      for (int i = t - T1; i >= 0 && i < N; i += NT) {
+        double q = 0;
+        for (int j = 0; j < N; ++j) q += B0[L::lLxx + i + ldH * j] * dx[j];
+        const double dxi = dx[i];
+        part1 += B0[L::lLx + i] * dxi;
+        part2 += dxi * q;
       }
     }
     __syncthreads();
     if (run) {
-      const double* Ag = ph.A + gix(k, N * N, 0, ldb, b);
-      const double* Bg = ph.Bm + gix(k, N * M, 0, ldb, b);
-      const double* lxxg = ph.lxx + gix(k, N * N, 0, ldb, b);
-      const double* luug = ph.luu + gix(k, M * M, 0, ldb, b);
+      // dx+ = A dx + B du + d
       for (int i = t; i < N; i += NT) {
-        double s = 0, s2 = 0, q = 0;
-        for (int j = 0; j < N; ++j) { const double dxj = sDx[j]; s += Ag[(size_t)(i + N * j) * ldb] * dxj; q += lxxg[(size_t)(i + N * j) * ldb] * dxj; }
-        for (int j = 0; j < M; ++j) s2 += Bg[(size_t)(i + N * j) * ldb] * sDuL[j];
-        const double v = s + s2 + 1.0 * ph.Defect[gix(k + 1, N, i, ldb, b)];
-        sDxn[i] = v;
+        double s = 0, s2 = 0;
+        if (WB && i < 18) {
+          s = dx[i] + dt * dx[18 + i];
+        } else {
+          const int r = i - R0;
+          for (int j = 0; j < N; ++j) s += B0[L::lA + r + ldA * j] * dx[j];
+          for (int j = 0; j < M; ++j) s2 += B0[L::lB + r + ldA * j] * sDuL[j];
+        }
+        const double v = s + s2 + 1.0 * B0[L::lD + i];
+        dxn[i] = v;
         ph.dX[gix(k + 1, N, i, ldb, b)] = v;
-        const double dxi = sDx[i];
-        part1 += ph.lx[gix(k, N, i, ldb, b)] * dxi;
-        part2 += dxi * q;
       }
-      for (int i = t; i < M; i += NT) {
+      constexpr int T2 = (NT >= 64 + M) ? 64 : (NT >= 32 + M ? 32 : 0);
+      for (int i = t - T2; i >= 0 && i < M; i += NT) {
         double q = 0;
-        for (int j = 0; j < M; ++j) q += luug[(size_t)(i + M * j) * ldb] * sDuL[j];
+        for (int j = 0; j < M; ++j) q += B0[L::lLuu + i + ldM * j] * sDuL[j];
         const double dui = sDuL[i];
-        part1 += ph.lu[gix(k, M, i, ldb, b)] * dui;
+        part1 += B0[L::lLu + i] * dui;
         part2 += dui * q;
       }
     }
-    sRed[t] = part1;
-    sRed[128 + t] = part2;
-    __syncthreads();
-    if (run) {
-      if (t == 0) { double a1 = 0, a2 = 0; for (int i = 0; i < NT; ++i) { a1 += sRed[i]; a2 += sRed[128 + i]; } dV1 += a1; dV2 += a2; }
-      for (int i = t; i < N; i += NT) sDx[i] = sDxn[i];
-    }
-    __syncthreads();
+    // the next iteration's top barrier orders dxn / sDuL / buffer reuse
   }
-  double part1 = 0, part2 = 0;
+  __syncthreads();
+  const double* dx = dxb[h & 1];
   if (run) {
     for (int i = t; i < N; i += NT) {
       double q = 0;
-      for (int j = 0; j < N; ++j) q += ph.Phixx[(size_t)(i + N * j) * ldb + b] * sDx[j];
-      const double dxi = sDx[i];
+      for (int j = 0; j < N; ++j) q += ph.Phixx[(size_t)(i + N * j) * ldb + b] * dx[j];
+      const double dxi = dx[i];
       part1 += ph.Phix[(size_t)i * ldb + b] * dxi;
       part2 += dxi * q;
     }
   }
-  sRed[t] = part1;
-  sRed[128 + t] = part2;
-  __syncthreads();
-  if (run && t == 0) { double a1 = 0, a2 = 0; for (int i = 0; i < NT; ++i) { a1 += sRed[i]; a2 += sRed[128 + i]; } dV1 += a1; dV2 += a2; }
-  if (ph.has_next) {
-    const int nn = ph.n_next;
-    if (run) for (int i = t; i < nn; i += NT) { double s = 0; for (int j = 0; j < N; ++j) s += ph.Px[(size_t)(i + nn * j) * ldb + b] * sDx[j]; sDxn[i] = s; }
-    __syncthreads();
-    if (run) for (int i = t; i < nn; i += NT) sDx[i] = sDxn[i];
+  // hand the perturbation over to the next phase in sDx
+  double carry = 0;
+  const int nn = ph.has_next ? ph.n_next : N;
+  if (run && t < nn) {
+    if (ph.has_next) { double s = 0; for (int j = 0; j < N; ++j) s += ph.Px[(size_t)(t + nn * j) * ldb + b] * dx[j]; carry = s; }
+    else carry = dx[t];
   }
+  __syncthreads();
+  if (run && t < nn) dxb[0][t] = carry;
   __syncthreads();
 }
 
 // DECK: 0 = HKD phases only (24,24,0); 1 = MHPC (WB 36,12,12 + SRB 12,12,0)
 template <int DECK, int NT>
-__global__ void __launch_bounds__(NT, 4) k_bwd2(const SolverDev* __restrict__ Sp) {
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NT, 4) k_bwd2(const __grid_constant__ SolverDev S) {
   typedef Bwd2Layout<(DECK == 0 ? 24 : 36), (DECK == 0 ? 24 : 12), (DECK == 0 ? 0 : 12), (DECK == 1)> L;
   constexpr int NX = (DECK == 0 ? 24 : 36);
-  const SolverDev& S = *Sp;
   extern __shared__ double sm[];
   __shared__ double s_reg;
   __shared__ int s_state, s_regiter;  // 0 sweeping, 1 success, 2 gave up
@@ -366,43 +446,57 @@ __global__ void __launch_bounds__(NT, 4) k_bwd2(const SolverDev* __restrict__ Sp
   const CtrlDev& c = S.c;
   const CafeOptions& o = S.opt;
   const int ldb = S.ldb;
-  if (b >= S.B || !c.active[b]) return;  // whole CTA
+  // The four CTAs of a cluster own four consecutive problems and advance knot by knot together (cluster_pace); a CTA whose
+  // problem is inactive, or whose sweep is already done while a neighbour repeats it with more regularisation, keeps pace only.
+  namespace cg = cooperative_groups;
+  cg::cluster_group cl = cg::this_cluster();
+  const bool mine = b < S.B && c.active[b];
   int it = 0;
   if (t == 0) {
-    s_state = 0; s_regiter = 0; s_reg = c.reg[b];
-    // compute_cost + measure_dynamics_feasibility on the current (trial) arrays (MultiPhaseDDP.cpp:280-281)
-    double cost = 0, fs = 0;
-    for (int pi = 0; pi < S.n_phases; ++pi) {
-      const PhaseDev& ph = S.ph[pi];
-      double pc = 0, pf = 0;
-      for (int k = 0; k < ph.h; ++k) pc += ph.lk[(size_t)k * ldb + b];
-      pc += ph.lk[(size_t)ph.h * ldb + b];
-      for (int k = 0; k <= ph.h; ++k) pf += ph.dsq[(size_t)k * ldb + b];
-      cost += pc; fs += pf;
+    s_state = mine ? 0 : 3; s_regiter = 0; s_reg = mine ? c.reg[b] : 0.0;
+    if (mine) {
+      // compute_cost + measure_dynamics_feasibility on the current (trial) arrays (MultiPhaseDDP.cpp:280-281)
+      double cost = 0, fs = 0;
+      for (int pi = 0; pi < S.n_phases; ++pi) {
+        const PhaseDev& ph = S.ph[pi];
+        double pc = 0, pf = 0;
+        for (int k = 0; k < ph.h; ++k) pc += ph.lk[(size_t)k * ldb + b];
+        pc += ph.lk[(size_t)ph.h * ldb + b];
+        for (int k = 0; k <= ph.h; ++k) pf += ph.dsq[(size_t)k * ldb + b];
+        cost += pc; fs += pf;
+      }
+      c.cost[b] = cost; c.feas[b] = sqrt(fs);
+      c.iter_in[b] += 1; c.iter[b] += 1;
+      it = c.iter[b] - 1;
+      if (it < CAFE_HIST_CAP) { double* tr = c.trace + ((size_t)it * 12) * ldb + b; for (int i = 0; i < 12; ++i) tr[(size_t)i * ldb] = 0; tr[0] = cost; tr[(size_t)ldb] = sqrt(fs); }
     }
-    c.cost[b] = cost; c.feas[b] = sqrt(fs);
-    c.iter_in[b] += 1; c.iter[b] += 1;
-    it = c.iter[b] - 1;
-    if (it < CAFE_HIST_CAP) { double* tr = c.trace + ((size_t)it * 12) * ldb + b; for (int i = 0; i < 12; ++i) tr[(size_t)i * ldb] = 0; tr[0] = cost; tr[(size_t)ldb] = sqrt(fs); }
   }
-  __syncthreads();
   double min_piv = 1e300;
-  while (s_state == 0) {
+  for (int round = 0;; ++round) {
+    cl.sync();
+    bool any = false;
+    for (unsigned r = 0; r < cl.num_blocks(); ++r) any |= (*cl.map_shared_rank(&s_state, r) == 0);
+    cl.sync();
+    if (!any) {
+      if (round == 0) return;  // the whole cluster is inactive
+      break;
+    }
+    const bool sweeping = s_state == 0;
     bool ok = true;
     const double reg = s_reg;
     for (int pi = S.n_phases - 1; pi >= 0; --pi) {
       const int model = S.ph[pi].model, nm = S.ph[pi].has_next ? S.ph[pi + 1].model : -1;
       if constexpr (DECK == 0) {
-        if (model == CAFE_MODEL_HKD) sweep_phase2<24, 24, 0, 24, false, NT, L>(S, pi, b, t, true, ok, reg, sm, min_piv);
+        if (model == CAFE_MODEL_HKD) sweep_phase2<24, 24, 0, 24, false, NT, L>(S, pi, b, t, sweeping, ok, reg, sm, min_piv);
       } else {
-        if (model == CAFE_MODEL_SRB) sweep_phase2<12, 12, 0, 12, false, NT, L>(S, pi, b, t, true, ok, reg, sm, min_piv);
-        else if (model == CAFE_MODEL_WB && nm == CAFE_MODEL_SRB) sweep_phase2<36, 12, 12, 12, true, NT, L>(S, pi, b, t, true, ok, reg, sm, min_piv);
-        else if (model == CAFE_MODEL_WB) sweep_phase2<36, 12, 12, 36, true, NT, L>(S, pi, b, t, true, ok, reg, sm, min_piv);
+        if (model == CAFE_MODEL_SRB) sweep_phase2<12, 12, 0, 12, false, NT, L>(S, pi, b, t, sweeping, ok, reg, sm, min_piv);
+        else if (model == CAFE_MODEL_WB && nm == CAFE_MODEL_SRB) sweep_phase2<36, 12, 12, 12, true, NT, L>(S, pi, b, t, sweeping, ok, reg, sm, min_piv);
+        else if (model == CAFE_MODEL_WB) sweep_phase2<36, 12, 12, 36, true, NT, L>(S, pi, b, t, sweeping, ok, reg, sm, min_piv);
       }
       (void)nm;
     }
     __syncthreads();
-    if (t == 0) {
+    if (t == 0 && sweeping) {
       s_regiter += 1;
       if (ok) s_state = 1;
       else {
@@ -411,25 +505,35 @@ __global__ void __launch_bounds__(NT, 4) k_bwd2(const SolverDev* __restrict__ Sp
         if (r > 1e2) s_state = 2;
       }
     }
-    __syncthreads();
   }
   const bool success = s_state == 1;
   double dV1 = 0, dV2 = 0;
   {
     double* sDx = sm + L::vDx;
+    double* sRed = sm + L::vRed;
     for (int i = t; i < NX; i += NT) sDx[i] = 0.0;
     __syncthreads();
+    double part1 = 0, part2 = 0;
     for (int pi = 0; pi < S.n_phases; ++pi) {
       const int model = S.ph[pi].model;
       if constexpr (DECK == 0) {
-        if (model == CAFE_MODEL_HKD) lin_phase2<24, 24, NT, L>(S, pi, b, t, success, sm, dV1, dV2);
+        if (model == CAFE_MODEL_HKD) lin_phase2<24, 24, false, NT, L>(S, pi, b, t, success, sm, part1, part2);
       } else {
-        if (model == CAFE_MODEL_WB) lin_phase2<36, 12, NT, L>(S, pi, b, t, success, sm, dV1, dV2);
-        else if (model == CAFE_MODEL_SRB) lin_phase2<12, 12, NT, L>(S, pi, b, t, success, sm, dV1, dV2);
+        if (model == CAFE_MODEL_WB) lin_phase2<36, 12, true, NT, L>(S, pi, b, t, success, sm, part1, part2);
+        else if (model == CAFE_MODEL_SRB) lin_phase2<12, 12, false, NT, L>(S, pi, b, t, success, sm, part1, part2);
       }
     }
+    // dV_1, dV_2: fixed-order tree over the NT per-thread shares
+    sRed[t] = part1;
+    sRed[128 + t] = part2;
+    __syncthreads();
+    for (int w = NT / 2; w > 0; w >>= 1) {
+      if (t < w) { sRed[t] += sRed[t + w]; sRed[128 + t] += sRed[128 + t + w]; }
+      __syncthreads();
+    }
+    dV1 = sRed[0]; dV2 = sRed[128];
   }
-  if (t == 0) {
+  if (t == 0 && mine) {
     double r = s_reg / 20;
     if (r < 1e-06) r = 0;
     c.reg[b] = r;

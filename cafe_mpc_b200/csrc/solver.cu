@@ -221,8 +221,8 @@ int launch_lq_wb_dense(CafeHandle* H) {
 }
 
 int launch_bwd(CafeHandle* H) {
-  if (H->bwd_variant == 0) k_bwd2<0, 64><<<H->B, 64, H->bwd_smem, H->stream>>>(H->dS);
-  else k_bwd2<1, 128><<<H->B, 128, H->bwd_smem, H->stream>>>(H->dS);
+  if (H->bwd_variant == 0) k_bwd2<0, 128><<<(H->B + 3) / 4 * 4, 128, H->bwd_smem, H->stream>>>(H->S);
+  else k_bwd2<1, 128><<<(H->B + 3) / 4 * 4, 128, H->bwd_smem, H->stream>>>(H->S);
   return 0;
 }
 
@@ -301,7 +301,7 @@ extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, 
   if (all_hkd) {
     H->bwd_variant = 0; H->bwd_pb = 1;
     H->bwd_smem = (size_t)cafe_dev::Bwd2Layout<24, 24, 0, false>::total * sizeof(double);
-    CUDA_OK(cudaFuncSetAttribute(cafe_dev::k_bwd2<0, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H->bwd_smem));
+    CUDA_OK(cudaFuncSetAttribute(cafe_dev::k_bwd2<0, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H->bwd_smem));
   } else {
     H->bwd_variant = 1; H->bwd_pb = 1;
     H->bwd_smem = (size_t)cafe_dev::Bwd2Layout<36, 12, 12, true>::total * sizeof(double);

@@ -18,3 +18,5 @@ if len(sys.argv) > 4: opt.max_DDP_iter = int(sys.argv[4])
 x0 = np.tile(x0, ((B + len(x0) - 1) // len(x0), 1))[:B]
 s = cm.MultiPhaseDDP(prob, 0, B); s.set_initial_condition(x0); s.solve(opt)
 print("ok solve_ms", s.solve_ms(), s.get_timing()["launches"])
+info = s.get_solver_info()
+print("iters", sum(i["iter"] for i in info) / B, "sweeps(reg_iter_total)", sum(i["reg_iter_total"] for i in info) / B, "ls", sum(i["ls_iter_total"] for i in info) / B)
