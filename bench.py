@@ -232,8 +232,9 @@ def main():
         peak = cm.measure_fp64_peak(local)
         ach = flops / (tm["ms"]["bwd"] * 1e-3) / 1e12
         share = tm["ms"]["bwd"] / max(sum(tm["ms"].values()), 1e-9)
-        roof = {"bound": "fp64", "kernel": "k_bwd", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                "traffic": None, "flop_per_launch": flops / n_l, "avg_launch_ms": tm["ms"]["bwd"] / n_l, "share_of_step": share,
+        traffic, traffic_src = _ncu_traffic("k_bwd2") if (args.workload == "mhpc" and B == 4096) else (None, None)
+        roof = {"bound": "fp64", "kernel": "k_bwd2", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "traffic": traffic, "traffic_source": traffic_src, "flop_per_launch": flops / n_l, "avg_launch_ms": tm["ms"]["bwd"] / n_l, "share_of_step": share,
                 "peak_source": "measured live: cafe_gpu_measure_fp64_peak (DFMA microbenchmark, 8 independent chains/thread); MEASURED_PEAKS.json has no fp64 entry",
                 "kernel_ms": tm["ms"], "hbm_peak_gbs": _hbm_peak()}
         if not args.no_cpu_baseline:
@@ -256,6 +257,17 @@ def main():
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu}))
     if world > 1:
         dist.destroy_process_group()
+
+
+def _ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full summary of the newest round (profiles/rNN_traffic.json)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(REPO, "profiles", "r*_traffic.json")))
+    if not files:
+        return None, None
+    d = json.load(open(files[-1]))
+    k = d.get("kernels", {}).get(kernel)
+    return (k["dram_bytes_per_launch"], os.path.relpath(files[-1], REPO) + ": " + d.get("source", "")) if k else (None, None)
 
 
 def _hbm_peak():
