@@ -53,3 +53,30 @@ def mhpc_batch(B, perturb=True):
             for j in range(36):
                 x0[b, j] += MHPC_SCALE[j] * (2 * uniform(b, j) - 1)
     return x0
+
+
+# ---- MHPC running barrel roll (BASELINE config 4; Reference/Data/running_br, cost_weights_barrel.JSON,
+# constraint_params_barrel.info). Start offsets: k0 = 0 (stance -> diagonal pair -> flight) and k0 = 205 (mid-roll flight,
+# 4-foot landing impact with touchdown constraints, SURVEY.md §8 phase table).
+import os as _os
+
+_DATA = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "data")
+BARREL_CSV = _os.path.join(_DATA, "Reference/Data/running_br/quad_reference.csv")
+BARREL_CONFIG = _os.path.join(_DATA, "MHPC/settings/mhpc_config_barrel.info")
+BARREL_K0_IMPACT = 205
+
+
+def reference_state(problem):
+    """Whole-body reference state (36) at the first knot of the deck = the state the tracked motion has at the start offset."""
+    deck = problem.deck.contents
+    return np.array([deck.ref[i] for i in range(36)], dtype=np.float64)
+
+
+def barrel_batch(problem, B, perturb=True):
+    """x0 = reference state at the start offset + the same SplitMix64 perturbation table as mhpc_batch."""
+    x0 = np.tile(reference_state(problem), (B, 1))
+    if perturb:
+        for b in range(1, B):
+            for j in range(36):
+                x0[b, j] += MHPC_SCALE[j] * (2 * uniform(b, j) - 1)
+    return x0

@@ -204,3 +204,36 @@ def test_oracle_mhpc_matches_committed_golden(mhpc, mhpc_impact, mhpc_options):
             assert [info[k] for k in ("status", "iter", "ls_iter_total", "reg_iter_total", "outer_iter", "n_hist")] == list(g["%s_counts_%d" % (key, b)])
             np.testing.assert_allclose(hist[:, 0], g["%s_hist_%d" % (key, b)][:, 0], rtol=1e-9)
             np.testing.assert_allclose(sol, g["%s_sol_%d" % (key, b)], rtol=0, atol=1e-8 * np.abs(sol).max())
+
+
+# ---- BASELINE config 4: MHPC running barrel roll (Reference/Data/running_br, barrel cost weights / constraint parameters)
+def test_barrel_roll_phase_schedule_golden(cm):
+    """SURVEY.md §8 phase table: t0 = 0 -> WB0 h=6 (1,1,1,1); WB1 h=15 (0,1,0,1); WB2 h=4 flight; SRB h=10. Start offset 205 = inside
+    the roll's flight: 22 flight knots, 4-foot landing (four touchdown constraints, impact), 3 stance knots, SRB h=10."""
+    from cafe_mpc_b200 import workload
+    prob0 = cm.MHPCProblem(workload.BARREL_CSV, mhpc_config=workload.BARREL_CONFIG, k0=0)   # owns the deck the phase views point into
+    p0 = prob0.phases()
+    assert [(p.model, p.horizon, tuple(p.contact)) for p in p0] == [(1, 6, (1, 1, 1, 1)), (1, 15, (0, 1, 0, 1)), (1, 4, (0, 0, 0, 0)), (2, 10, (0, 0, 0, 0))]
+    assert [p.n_td for p in p0] == [0, 0, 0, 0]
+    prob = cm.MHPCProblem(workload.BARREL_CSV, mhpc_config=workload.BARREL_CONFIG, k0=workload.BARREL_K0_IMPACT)
+    p1 = prob.phases()
+    assert [(p.model, p.horizon, tuple(p.contact)) for p in p1] == [(1, 22, (0, 0, 0, 0)), (1, 3, (1, 1, 1, 1)), (2, 10, (0, 0, 0, 0))]
+    assert p1[0].n_td == 4 and sorted(tuple(p1[0].td_foot)) == [0, 1, 2, 3] and tuple(p1[0].next_contact) == (1, 1, 1, 1)
+    # barrel weights / parameters were picked up
+    assert list(p1[0].q)[:6] == [0.0, 0.0, 15.0, 5.0, 5.0, 5.0] and list(p1[0].w_footreg) == [0.0, 0.0, 0.0]
+    assert p1[0].reb_torque.delta == 0.1 and p1[0].reb_torque.eps == 0.1 and p1[0].reb_grf.delta == 0.1 and p1[0].al_td.sigma == 10
+    x0 = workload.reference_state(prob)
+    assert abs(x0[5]) > 3.0   # mid-roll: the roll angle of the tracked motion is beyond pi
+
+
+def test_oracle_barrel_roll_matches_committed_golden(cm, mhpc_options):
+    from cafe_mpc_b200 import workload
+    g = np.load(os.path.join(REPO, "tests/golden/mhpc_barrel.npz"))
+    for key, k0 in (("k0", 0), ("k205", workload.BARREL_K0_IMPACT)):
+        prob = cm.MHPCProblem(workload.BARREL_CSV, mhpc_config=workload.BARREL_CONFIG, k0=k0)
+        x0 = workload.barrel_batch(prob, 4)
+        assert np.array_equal(x0, g[key + "_x0"])
+        info, hist, trace, sol = oracle_solve(prob.deck, mhpc_options, x0[0])
+        assert [info[k] for k in ("status", "iter", "ls_iter_total", "reg_iter_total", "outer_iter", "n_hist")] == list(g["%s_counts_0" % key])
+        np.testing.assert_allclose(hist[:, 0], g["%s_hist_0" % key][:, 0], rtol=1e-9)
+        np.testing.assert_allclose(sol, g["%s_sol_0" % key], rtol=0, atol=1e-8 * np.abs(sol).max())

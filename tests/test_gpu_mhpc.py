@@ -16,9 +16,14 @@ COUNTS = ("status", "iter", "ls_iter_total", "reg_iter_total", "outer_iter", "n_
 RTOL = 1e-9
 
 
-def relerr(g, o):
+def relerr(g, o, floor=1e-6):
     o = np.asarray(o); g = np.asarray(g)
-    return 0.0 if o.size == 0 else float(np.max(np.abs(g - o)) / max(np.max(np.abs(o)), 1e-6))
+    return 0.0 if o.size == 0 else float(np.max(np.abs(g - o)) / max(np.max(np.abs(o)), floor))
+
+
+# Qu and dU are cancellation residuals that vanish at convergence (|Qu| ~ 1e-7 against torque-scale terms ~ 1): their error is
+# measured against max(|.|, 1e-3), everything else against its own largest entry
+FLOOR = {"Qu": 1e-3, "dU": 1e-3}
 
 
 @pytest.fixture(scope="module")
@@ -42,7 +47,7 @@ def compare_with_oracle(cm, prob, opt, x0, s, which):
         gp, op = cm.unpack_solution(prob.deck, sol[b]), cm.unpack_solution(prob.deck, osol)
         for pg, po in zip(gp, op):
             for name in ("Xbar", "Ubar", "Y", "K", "dU", "Qu", "Quu", "Qux", "G"):  # final trajectories and gains
-                assert relerr(pg[name], po[name]) < RTOL, (b, name)
+                assert relerr(pg[name], po[name], FLOOR.get(name, 1e-6)) < RTOL, (b, name)
 
 
 @pytest.mark.parametrize("k0", [0, 20])
@@ -111,3 +116,65 @@ def test_mhpc_batch_1024_properties(cm, opt):
     for ph in sol:
         for Quu in ph["Quu"]:
             assert np.all(np.linalg.eigvalsh(0.5 * (Quu + Quu.T)) > 0)
+
+
+# ---- BASELINE config 4: MHPC running barrel roll (multi-phase with impact jumps)
+@pytest.mark.parametrize("k0", [0, 205])
+def test_barrel_roll_matches_oracle_and_golden(cm, opt, k0):
+    """k0 = 0: stance -> diagonal pair -> flight -> SRB; k0 = 205: mid-roll flight (22 knots) -> 4-foot landing impact with four
+    touchdown constraints (AL loop, the reference's `segment<3>(i)` impulse scatter with several landing feet) -> stance -> SRB."""
+    from cafe_mpc_b200 import workload
+    prob = cm.MHPCProblem(workload.BARREL_CSV, mhpc_config=workload.BARREL_CONFIG, k0=k0)
+    g = np.load(os.path.join(REPO, "tests/golden/mhpc_barrel.npz"))
+    key = "k0" if k0 == 0 else "k205"
+    assert np.array_equal(np.array([[p.model, p.horizon] + list(p.contact) + [p.n_td] for p in prob.phases()]), g[key + "_phases"])
+    x0 = workload.barrel_batch(prob, 4)
+    assert np.array_equal(x0, g[key + "_x0"])
+    s = solve_gpu(cm, prob, opt, x0)
+    compare_with_oracle(cm, prob, opt, x0, s, range(3))
+    info = s.get_solver_info(); hist = s.get_history(256); sol = s.get_solution()
+    for b in (0,):
+        assert [info[b][k] for k in COUNTS] == list(g["%s_counts_%d" % (key, b)])
+        np.testing.assert_allclose(hist[b, :info[b]["n_hist"], 0], g["%s_hist_%d" % (key, b)][:, 0], rtol=RTOL)
+        assert relerr(sol[b], g["%s_sol_%d" % (key, b)]) < RTOL
+    if k0 == 205:
+        assert info[0]["outer_iter"] > 1 and info[0]["max_tconstr"] < 0.005   # the landing constraints were enforced by the AL loop
+
+
+def test_barrel_roll_impact_knot_parity(cm, opt):
+    """One iteration at the impact-bearing offset: flight-phase (no contact) dynamics partials, the 4-foot impact map and its
+    Jacobian Px (36x36), touchdown-constraint terms and the value jump Px^T H Px, per knot against the oracle."""
+    from cafe_mpc_b200 import workload
+    prob = cm.MHPCProblem(workload.BARREL_CSV, mhpc_config=workload.BARREL_CONFIG, k0=workload.BARREL_K0_IMPACT)
+    o1 = copy.copy(opt)
+    o1.max_DDP_iter = 1; o1.max_AL_iter = 1; o1.cost_thresh = 1e30; o1.dynamics_feas_thresh = 1e30
+    x0 = workload.barrel_batch(prob, 4)
+    s = solve_gpu(cm, prob, o1, x0)
+    for b in (0, 2):
+        oracle_solve(prob.deck, o1, x0[b])
+        for ph in range(3):
+            for name in ("X", "U", "Y", "Defect", "l", "lx", "lu", "ly", "lxx", "luu", "lyy", "A", "B", "C", "D", "Phix", "Phixx"):
+                assert relerr(s.debug_get(name, ph, b), oracle_get(name, ph)) < 1e-11, (name, ph)
+            for name in ("Quu", "Qux", "Qu", "K", "dU", "G", "dX"):
+                assert relerr(s.debug_get(name, ph, b), oracle_get(name, ph)) < 1e-10, (name, ph)
+        for ph in range(2):
+            assert relerr(s.debug_get("Px", ph, b), oracle_get("Px", ph)) < 1e-11, ph
+
+
+def test_barrel_roll_batch_256_properties(cm, opt):
+    """256 perturbed mid-roll problems: deterministic, every problem ends with a legal status and iteration count, problems that
+    converge satisfy the landing constraints; spot checks against the oracle."""
+    from cafe_mpc_b200 import workload
+    prob = cm.MHPCProblem(workload.BARREL_CSV, mhpc_config=workload.BARREL_CONFIG, k0=workload.BARREL_K0_IMPACT)
+    B = 256
+    x0 = workload.barrel_batch(prob, B)
+    s = solve_gpu(cm, prob, opt, x0)
+    i1 = s.get_solver_info(); c1 = s.get_commands(8)
+    s.solve(opt)
+    assert np.array_equal(c1, s.get_commands(8)) and i1 == s.get_solver_info()
+    cap = opt.max_AL_iter * opt.max_DDP_iter
+    assert all(1 <= i["iter"] <= cap for i in i1)
+    done = [i for i in i1 if i["iter"] < cap and i["status"] == 0]
+    assert len(done) > B // 2
+    assert all(np.isfinite([i["cost"], i["feas"], i["max_tconstr"], i["max_pconstr"]]).all() for i in i1)
+    compare_with_oracle(cm, prob, opt, x0, s, (0, 2, 3, 4))   # problem 3 runs into the 10 x 20 iteration cap (1863 line-search trials)

@@ -37,3 +37,19 @@ for key, k0 in (("k0", 0), ("k20", 20)):
         out["%s_final_%d" % (key, b)] = np.array([i["cost"], i["feas"], i["max_tconstr"], i["max_pconstr"]])
         print(key, b, i)
 np.savez_compressed(os.path.join(R, "tests/golden/mhpc_trot.npz"), **out)
+
+# ---- MHPC running barrel roll (BASELINE config 4): k0 = 0 and the mid-roll offset with the 4-foot landing impact
+out = {}
+for key, k0 in (("k0", 0), ("k205", workload.BARREL_K0_IMPACT)):
+    pm = cm.MHPCProblem(workload.BARREL_CSV, mhpc_config=workload.BARREL_CONFIG, k0=k0)
+    x0b = workload.barrel_batch(pm, 4)
+    out[key + "_x0"] = x0b
+    out[key + "_phases"] = np.array([[p.model, p.horizon] + list(p.contact) + [p.n_td] for p in pm.phases()])
+    for b in (0, 3):
+        i, h, t, s = oracle_solve(pm.deck, opt2, x0b[b])
+        out["%s_counts_%d" % (key, b)] = np.array([i[k] for k in ("status", "iter", "ls_iter_total", "reg_iter_total", "outer_iter", "n_hist")])
+        out["%s_hist_%d" % (key, b)] = h
+        out["%s_sol_%d" % (key, b)] = s
+        out["%s_final_%d" % (key, b)] = np.array([i["cost"], i["feas"], i["max_tconstr"], i["max_pconstr"]])
+        print("barrel", key, b, i)
+np.savez_compressed(os.path.join(R, "tests/golden/mhpc_barrel.npz"), **out)
