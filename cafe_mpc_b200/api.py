@@ -75,6 +75,19 @@ class MHPCProblem(_DeckOwner):
                                        C.byref(self._h)))
 
 
+LCM_FIELDS = (("torque", 12), ("eul", 3), ("pos", 3), ("qJ", 12), ("vWorld", 3), ("eulrate", 3), ("qJd", 12), ("GRF", 12), ("feedback", 432),
+              ("Qu", 12), ("Quu", 144), ("Qux", 432))   # lcmtypes/MHPC_Command_lcmt.lcm, per-problem fields in struct order
+
+
+def unpack_lcm_command(rec, n_steps):
+    """Splits one float32 record of get_lcm_commands into {field: [n_steps, width]} (matrices stay column-major flat, as on the wire)."""
+    out, off = {}, 0
+    for name, w in LCM_FIELDS:
+        out[name] = rec[off:off + n_steps * w].reshape(n_steps, w)
+        off += n_steps * w
+    return out
+
+
 class MultiPhaseDDP:
     """Batched MultiPhaseDDP: set_multiPhaseProblem (constructor), set_initial_condition, solve,
     get_solver_info; results are packed host arrays instead of in-place Trajectory deques."""
@@ -142,6 +155,15 @@ class MultiPhaseDDP:
             out = np.zeros((self.B, sz))
         check(lib.cafe_gpu_get_commands(self._h, n_gain_knots, out.ctypes.data_as(C.c_void_p)))
         return out
+
+    def get_lcm_commands(self, n_steps=8):
+        """float32 MHPC_Command_lcmt record per problem (see include/cafe_gpu.h); use unpack_lcm_command to name the fields."""
+        out = np.zeros((self.B, lib.cafe_lcm_command_size(n_steps)), dtype=np.float32)
+        check(lib.cafe_gpu_get_lcm_commands(self._h, n_steps, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def get_lcm_commands_device(self, n_steps, dev_ptr):
+        check(lib.cafe_gpu_get_lcm_commands_device(self._h, n_steps, C.c_void_p(dev_ptr)))
 
     def debug_get(self, name, phase, b=0):
         buf = np.zeros(64 * 36 * 36 + 64)

@@ -96,6 +96,22 @@ __global__ void k_pack(const PackSeg* __restrict__ segs, int nseg, int ldb, int 
   }
 }
 
+// float32 wire record (MHPC_Command_lcmt field order): one segment = nk knots x w components taken from components
+// [c0, c0+w) of an array with nc_src components per knot, starting at knot k0 of its phase
+struct PackSegF { const double* src; int nc_src, c0, w, k0, nk; long dst; };
+__global__ void k_pack_lcm(const PackSegF* __restrict__ segs, int nseg, int ldb, int nb, long rec_size, float* __restrict__ out) {
+  const int s = blockIdx.y;
+  if (s >= nseg) return;
+  const PackSegF sg = segs[s];
+  const long total = (long)sg.nk * sg.w;
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total * nb; t += (long)gridDim.x * blockDim.x) {
+    const int bb = (int)(t % nb);
+    const long e = t / nb;
+    const int kk = (int)(e / sg.w), c = (int)(e % sg.w);
+    out[(size_t)bb * rec_size + sg.dst + e] = (float)sg.src[((size_t)(sg.k0 + kk) * sg.nc_src + sg.c0 + c) * ldb + bb];
+  }
+}
+
 __global__ void k_fp64_peak(double* out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
   const double m = 0.999999, c = 1e-7;
@@ -536,6 +552,56 @@ static int commands_impl(CafeHandle* H, int n_gain_knots, double* cmd, double* d
   }
   return run_pack(H, segs, off, 0, H->B, cmd, dev_out);
 }
+
+// ---- MHPC_Command_lcmt record (lcmtypes/MHPC_Command_lcmt.lcm, filled on the host by MHPCLocomotion.cpp:236-281): emitted
+//      as float32 straight from the device arrays for the first n_steps whole-body knots of the horizon
+extern "C" long cafe_lcm_command_size(int n_steps) { return n_steps > 0 ? 1080L * n_steps : 0; }
+
+static int lcm_impl(CafeHandle* H, int n_steps, float* out, float* dev_out) {
+  if (!H || n_steps <= 0 || (!out && !dev_out)) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
+  CUDA_OK(cudaSetDevice(H->device));
+  int wb_knots = 0;
+  for (int i = 0; i < H->S.n_phases && H->S.ph[i].model == CAFE_MODEL_WB; ++i) wb_knots += H->S.ph[i].h;
+  if (wb_knots < n_steps) { cafe::set_last_error("the deck has fewer leading whole-body knots than the requested command steps"); return CAFE_ERR_UNSUPPORTED; }
+  const long N = n_steps, rec = 1080L * N;
+  // field bases, in the order of the LCM struct: torque eul pos qJ vWorld eulrate qJd GRF feedback Qu Quu Qux
+  const long oTorque = 0, oEul = 12 * N, oPos = 15 * N, oQj = 18 * N, oVw = 30 * N, oEr = 33 * N, oQjd = 36 * N, oGrf = 48 * N, oFb = 60 * N, oQu = 492 * N,
+             oQuu = 504 * N, oQux = 648 * N;
+  std::vector<PackSegF> segs;
+  int s0 = 0;
+  for (int i = 0; i < H->S.n_phases && s0 < n_steps; ++i) {
+    const PhaseDev& ph = H->S.ph[i];
+    const int g = std::min(ph.h, n_steps - s0);
+    auto add = [&](const double* src, int nc_src, int c0, int w, long base) { segs.push_back(PackSegF{src, nc_src, c0, w, 0, g, base + (long)s0 * w}); };
+    add(ph.Ubar, 12, 0, 12, oTorque);
+    add(ph.Xbar, 36, 3, 3, oEul); add(ph.Xbar, 36, 0, 3, oPos); add(ph.Xbar, 36, 6, 12, oQj);
+    add(ph.Xbar, 36, 18, 3, oVw); add(ph.Xbar, 36, 21, 3, oEr); add(ph.Xbar, 36, 24, 12, oQjd);
+    add(ph.Y, 12, 0, 12, oGrf); add(ph.K, 432, 0, 432, oFb); add(ph.Qu, 12, 0, 12, oQu); add(ph.Quu, 144, 0, 144, oQuu); add(ph.Qux, 432, 0, 432, oQux);
+    s0 += g;
+  }
+  const size_t need = (size_t)H->B * rec * sizeof(float);
+  float* dst = dev_out;
+  if (!dst) {
+    if (need > H->pack_bytes) {
+      cudaFree(H->d_pack); H->d_pack = nullptr; H->pack_bytes = 0;
+      CUDA_OK(cudaMalloc(&H->d_pack, need));
+      H->pack_bytes = need;
+    }
+    dst = reinterpret_cast<float*>(H->d_pack);
+  }
+  PackSegF* d_segs = nullptr;
+  CUDA_OK(cudaMalloc(&d_segs, segs.size() * sizeof(PackSegF)));
+  CUDA_OK(cudaMemcpyAsync(d_segs, segs.data(), segs.size() * sizeof(PackSegF), cudaMemcpyHostToDevice, H->stream));
+  dim3 grid(592, (unsigned)segs.size());
+  k_pack_lcm<<<grid, 256, 0, H->stream>>>(d_segs, (int)segs.size(), H->ldb, H->B, rec, dst);
+  if (out) CUDA_OK(cudaMemcpyAsync(out, dst, need, cudaMemcpyDeviceToHost, H->stream));
+  CUDA_OK(cudaStreamSynchronize(H->stream));
+  CUDA_OK(cudaGetLastError());
+  cudaFree(d_segs);
+  return 0;
+}
+extern "C" int cafe_gpu_get_lcm_commands(CafeHandle* H, int n_steps, float* out) { return lcm_impl(H, n_steps, out, nullptr); }
+extern "C" int cafe_gpu_get_lcm_commands_device(CafeHandle* H, int n_steps, float* out_dev) { return lcm_impl(H, n_steps, nullptr, out_dev); }
 
 extern "C" long cafe_gpu_debug_get(CafeHandle* H, const char* name, int phase, int b, double* out) {
   if (!H || !name || !out || phase < 0 || phase >= H->S.n_phases || b < 0 || b >= H->B) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }

@@ -82,6 +82,15 @@ int cafe_gpu_get_solution(CafeHandle* h, int b0, int nb, double* sol /*[nb][cafe
 int cafe_gpu_get_commands(CafeHandle* h, int n_gain_knots, double* cmd /*[B][cafe_command_size]*/);
 /* same, packed into a caller-owned DEVICE buffer (source of the final NCCL gather in multi-GPU runs) */
 int cafe_gpu_get_commands_device(CafeHandle* h, int n_gain_knots, double* cmd_dev);
+/* Wire-format step after the path: the per-problem part of MHPC_Command_lcmt (lcmtypes/MHPC_Command_lcmt.lcm), which
+ * MHPCLocomotion::publish_mpc_cmd fills on the host from Xbar/Ubar/Y/K/Qu/Quu/Qux with cast<float>() (MHPCLocomotion.cpp:236-281).
+ * Emitted as float32 directly from the device arrays for the first n_steps whole-body knots; per problem, in the struct's order:
+ *   torque[N][12] eul[N][3] pos[N][3] qJ[N][12] vWorld[N][3] eulrate[N][3] qJd[N][12] GRF[N][12] feedback[N][432] Qu[N][12]
+ *   Quu[N][144] Qux[N][432]          (matrices column-major = Eigen .data() order; N = n_steps; 1080 N floats)
+ * The deck-level fields (mpc_times, contacts, statusTimes) are the same for every problem and stay with the caller. */
+long cafe_lcm_command_size(int n_steps);
+int cafe_gpu_get_lcm_commands(CafeHandle* h, int n_steps, float* out /*[B][cafe_lcm_command_size]*/);
+int cafe_gpu_get_lcm_commands_device(CafeHandle* h, int n_steps, float* out_dev);
 /* device-time breakdown of the last solve, ms per kernel family, and launch counts */
 #define CAFE_NKERNELS 6 /* 0 roll 1 select 2 accept 3 lq 4 bwd 5 misc */
 int cafe_gpu_get_timing(CafeHandle* h, double ms[CAFE_NKERNELS], long launches[CAFE_NKERNELS], int* ticks);

@@ -178,3 +178,28 @@ def test_barrel_roll_batch_256_properties(cm, opt):
     assert len(done) > B // 2
     assert all(np.isfinite([i["cost"], i["feas"], i["max_tconstr"], i["max_pconstr"]]).all() for i in i1)
     compare_with_oracle(cm, prob, opt, x0, s, (0, 2, 3, 4))   # problem 3 runs into the 10 x 20 iteration cap (1863 line-search trials)
+
+
+def test_lcm_command_record_is_the_float_cast_of_the_solution(cm, opt):
+    """the per-problem MHPC_Command_lcmt fields packed on the device == cast<float>() of the double solution
+    (MHPCLocomotion.cpp:236-281), for steps that cross the WB0 -> WB1 phase boundary."""
+    from cafe_mpc_b200 import workload
+    prob = cm.MHPCProblem(CSV, k0=20)   # WB0 h=16, WB1 h=9
+    x0 = workload.mhpc_batch(6)
+    s = solve_gpu(cm, prob, opt, x0)
+    N = 20
+    rec = s.get_lcm_commands(N)
+    assert rec.dtype == np.float32 and rec.shape == (6, 1080 * N)
+    sol = s.get_solution()
+    for b in (0, 5):
+        ph = cm.unpack_solution(prob.deck, sol[b])
+        cat = lambda name: np.concatenate([np.asarray(ph[0][name])[:16], np.asarray(ph[1][name])[:N - 16]])
+        X, U, Y = cat("Xbar"), cat("Ubar"), cat("Y")
+        f = cm.unpack_lcm_command(rec[b], N)
+        exp = {"torque": U, "pos": X[:, 0:3], "eul": X[:, 3:6], "qJ": X[:, 6:18], "vWorld": X[:, 18:21], "eulrate": X[:, 21:24], "qJd": X[:, 24:36], "GRF": Y,
+               "Qu": cat("Qu"), "feedback": np.stack([k.flatten(order="F") for k in cat("K")]), "Quu": np.stack([k.flatten(order="F") for k in cat("Quu")]),
+               "Qux": np.stack([k.flatten(order="F") for k in cat("Qux")])}
+        for name, v in exp.items():
+            assert np.array_equal(f[name], v.astype(np.float32)), name
+    with pytest.raises(Exception):
+        s.get_lcm_commands(26)   # more steps than whole-body knots
