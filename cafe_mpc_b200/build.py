@@ -16,7 +16,7 @@ ABI = ["../../include/cafe_gpu.h", "../../include/cafe_deck.h"]
 SOURCES = {
     "solver.cu": ["dense_kernels.cuh", "bwd2.cuh", "device_types.cuh", "launchers.h"] + ABI,
     "knot_kernels.cu": ["knot_kernels.cuh", "launchers.h", "device_types.cuh", "model_hkd.cuh", "model_srb.cuh", "model_wb.cuh", "gen/hkd_gen.h", "gen/srb_gen.h"] + ABI,
-    "wb_gen_wrappers.cu": ["gen/wb_gen.h"],
+    "wb_gen_wrappers.cu": ["gen/wb_gen.h", "wb_pieces.h"],
     "host/abi_host.cpp": ["host/problem_builders.h", "host/quad_reference.h"] + ABI,
     "host/hkd_problem.cpp": ["host/problem_builders.h", "host/quad_reference.h", "host/info_reader.h", "gen/hkd_gen.h"] + ABI,
     "host/mhpc_problem.cpp": ["host/problem_builders.h", "host/quad_reference.h", "host/info_reader.h"] + ABI,

@@ -7,11 +7,12 @@ from the symbolic model in tools/wb_model.py (no Pinocchio, no CasADi at run tim
                    getFrameAcceleration at MHPC/MHPC-Trajopt/WBM.cpp:375-411
   wb_feet         (q, v)        -> pf[12], vf[12], J[12x18]                                                   hip yaw 3.1415
                    replaces the kinematics getters WBM.cpp:260-364
-  wb_rnea_derivs  (q, v, a)     -> dtau_dq[18x18], dtau_dv[18x18]                                             hip yaw 3.1415
-                   replaces pinocchio::computeRNEADerivatives (WBM.cpp:474, :514)
+  wb_rnea_derivs_{trunk,leg0..3} (q, v, a) -> that inertia group's share of dtau_dq[18x18], dtau_dv[18x18]   hip yaw 3.1415
+                   together they replace pinocchio::computeRNEADerivatives (WBM.cpp:474, :514)
   wb_grav_derivs  (q)           -> dg_dq[18x18]                                                               hip yaw 3.1415
                    replaces computeGeneralizedGravityDerivatives (WBM.cpp:520)
-  wb_kin_partials (q, v, a, F)  -> dv_dq[12x18], da_dq[12x18], da_dv[12x18], dJTF_dq[18x18]                   hip yaw pi
+  wb_kin_partials_foot{0..3} (q, v, a, F) -> that foot's rows of dv_dq[12x18], da_dq[12x18], da_dv[12x18] and its share of
+                   dJTF_dq[18x18]                                                                              hip yaw pi
                    replaces the CasADi functions footVelPartialDq / footAccPartialDq / footAccPartialDv /
                    footForcePartialDq (MCKinematicsDerivativs.cpp), which were generated with exactly pi
                    (SURVEY.md §9 Q16); verified against the compiled reference code to 1e-14 in tests/.
@@ -49,10 +50,14 @@ def main():
     o_v = [(3 * f + r, feet[f]["v"][r]) for f in range(4) for r in range(3)]
     pieces.append(emit_function(ctx, "wb_terms", 2, [o_nle, o_M, o_J, o_g, o_p, o_v]))
     pieces.append(emit_function(ctx, "wb_feet", 2, [o_p, o_v, o_J]))
-    tau = m.rnea(q, v, a)
-    o_dq = [(r + 18 * c, tau[r].d(q[c])) for c in range(18) for r in range(18)]
-    o_dv = [(r + 18 * c, tau[r].d(v[c])) for c in range(18) for r in range(18)]
-    pieces.append(emit_function(ctx, "wb_rnea_derivs", 3, [o_dq, o_dv]))
+    # RNEA derivatives, split by inertia: tau = tau[trunk] + sum_f tau[leg f] (RNEA is linear in the inertias); tau[leg f] depends
+    # on the base and on leg f only, so every piece is a short function with a small live set (the monolithic 34.6 k-op version
+    # spilled ~260 KB per call). The pieces overlap only in rows 0..5 x columns 3..5 (summed by the caller, wb_pieces.h).
+    for name, only in [("trunk", {5})] + [("leg%d" % f, {6 + 3 * f, 7 + 3 * f, 8 + 3 * f}) for f in range(4)]:
+        tau = m.rnea(q, v, a, only=only)
+        o_dq = [(r + 18 * c, tau[r].d(q[c])) for c in range(18) for r in range(18)]
+        o_dv = [(r + 18 * c, tau[r].d(v[c])) for c in range(18) for r in range(18)]
+        pieces.append(emit_function(ctx, "wb_rnea_derivs_" + name, 3, [o_dq, o_dv]))
     grav = m.rnea(q, zero, zero)
     o_gq = [(r + 18 * c, grav[r].d(q[c])) for c in range(18) for r in range(18)]
     pieces.append(emit_function(ctx, "wb_grav_derivs", 1, [o_gq]))
@@ -61,16 +66,18 @@ def main():
     m2 = WBModel(ctx2, P, math.pi)
     q, v, a, F = make_vars(ctx2, 0, 18), make_vars(ctx2, 1, 18), make_vars(ctx2, 2, 18), make_vars(ctx2, 3, 12)
     feet = m2.feet(q, v, a)
-    o_dv, o_daq, o_dav = [], [], []
-    jtf = [ctx2.const(0.0)] * 18
+    # one function per foot: its rows of dv/dq, da/dq, da/dv and its share d(J_f^T F_f)/dq of the contact-force term; the shares
+    # overlap only in rows 3..5 x columns 3..5 (summed by the caller, wb_pieces.h)
     for f in range(4):
         fv, fa, J = feet[f]["v"], feet[f]["a"], feet[f]["J"]
-        o_dv += [(3 * f + r + 12 * c, fv[r].d(q[c])) for c in range(18) for r in range(3)]
-        o_daq += [(3 * f + r + 12 * c, fa[r].d(q[c])) for c in range(18) for r in range(3)]
-        o_dav += [(3 * f + r + 12 * c, fa[r].d(v[c])) for c in range(18) for r in range(3)]
-        jtf = [jtf[i] + J[0][i] * F[3 * f] + J[1][i] * F[3 * f + 1] + J[2][i] * F[3 * f + 2] for i in range(18)]
-    o_jtf = [(r + 18 * c, jtf[r].d(q[c])) for c in range(18) for r in range(18)]
-    pieces.append(emit_function(ctx2, "wb_kin_partials", 4, [o_dv, o_daq, o_dav, o_jtf]))
+        o_dv = [(3 * f + r + 12 * c, fv[r].d(q[c])) for c in range(18) for r in range(3)]
+        o_daq = [(3 * f + r + 12 * c, fa[r].d(q[c])) for c in range(18) for r in range(3)]
+        o_dav = [(3 * f + r + 12 * c, fa[r].d(v[c])) for c in range(18) for r in range(3)]
+        jtf = [J[0][i] * F[3 * f] + J[1][i] * F[3 * f + 1] + J[2][i] * F[3 * f + 2] for i in range(18)]
+        o_jtf = [(r + 18 * c, jtf[r].d(q[c])) for c in range(18) for r in range(18)]
+        pieces.append(emit_function(ctx2, "wb_kin_partials_foot%d" % f, 4, [o_dv, o_daq, o_dav, o_jtf]))
+        nz = [(i % 18, i // 18) for i, s_ in o_jtf if not s_.is_zero()]
+        print("jtf foot", f, "rows", sorted(set(r for r, c in nz)), "cols", sorted(set(c for r, c in nz)))
     # dv_dq alone (swing-foot velocity costs, touchdown velocity penalty, impact derivatives)
     feet_v = m2.feet(q, v, None)
     o_dv2 = []

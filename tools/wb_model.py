@@ -148,8 +148,10 @@ class WBModel:
             out.append({"R": R, "p": p, "axw": axw, "w": w, "v": vl, "al": al, "a": ac})
         return out
 
-    def rnea(self, q, v, a, gravity=True):
-        """tau = M(q) a + nle(q, v)  (gravity (0,0,-9.81)); world-frame Newton-Euler."""
+    def rnea(self, q, v, a, gravity=True, only=None):
+        """tau = M(q) a + nle(q, v)  (gravity (0,0,-9.81)); world-frame Newton-Euler. `only`: set of joint indices whose bodies
+        are kept (RNEA is linear in the inertias: tau = tau[trunk] + sum over legs tau[leg f], and tau[leg f] depends on the base
+        and on leg f only)."""
         K = self.K
         kin = self.kinematics(q, v, a)
         n = len(self.joints)
@@ -157,7 +159,7 @@ class WBModel:
         N = [[K(0.0)] * 3 for _ in range(n)]
         for i, j in enumerate(self.joints):
             b = j["body"]
-            if b is None:
+            if b is None or (only is not None and i not in only):
                 continue
             k = kin[i]
             cw = matvec(k["R"], [K(x) for x in b["com"]])
