@@ -333,48 +333,57 @@ struct WBModel {
     for (int i = 0; i < 36; ++i) ph.lx[gix(k, 36, i, ldb, b)] = lx[i];
     // lxx: diagonal (tracking + joint-limit / min-height barriers) + per-foot Gauss-Newton blocks. A foot Jacobian only has the
     // base-rotation columns 3..5 and its own three joint columns (the first three are zeroed by the reference), the swing-foot
-    // velocity Jacobian [dv/dq | J] additionally the six base columns of the velocity half: small dense blocks per foot.
+    // velocity Jacobian [dv/dq | J] additionally the six base columns of the velocity half. Only this static pattern is written
+    // (the array is zeroed once at create, the contact flags of a knot never change): entries private to a foot go straight to HBM,
+    // the 9 x 9 base block {3,4,5,18..23} shared by the feet is accumulated in bb first. Same summation order per entry as a dense
+    // accumulation (diagonal, then per foot position term, velocity term).
     double* lxxg = ph.lxx + gix(k, 1296, 0, ldb, b);
-    double acc[1296];
-    for (int i = 0; i < 1296; ++i) acc[i] = 0.0;
+    double dg[36], bb[81];
     for (int i = 0; i < 36; ++i) {
       double v = dt * ph.q[i];
       if (reb) {
         if (i >= 6 && i < 18) v += dt * (ph.reb_joint.eps * bddj[i - 6] + ph.reb_joint.eps * bddj[12 + i - 6]);
         if (i == 2) v += dt * (ph.reb_minheight.eps * bddh);
       }
-      acc[37 * i] = v;
+      dg[i] = v;
     }
+    for (int i = 0; i < 81; ++i) bb[i] = 0.0;
+    for (int p = 0; p < 9; ++p) bb[10 * p] = dg[p < 3 ? 3 + p : 15 + p];
+    for (int i = 0; i < 3; ++i) lxxg[(size_t)(37 * i) * ldb] = dg[i];
     for (int f = 0; f < 4; ++f) {
       const bool c = rec[CAFE_REF_CONTACT + f] > 0;
       const double* w = c ? ph.w_footreg : ph.w_swingpos;
-      int cols[15];
-      for (int a = 0; a < 3; ++a) { cols[a] = 3 + a; cols[3 + a] = 6 + 3 * f + a; }
-      for (int jj = 0; jj < 6; ++jj)
-        for (int ii = 0; ii < 6; ++ii) {
+      // local column list: 0..2 base rotation, 3..5 leg q, 6..11 base velocity, 12..14 leg v; bpos = slot in the base block or -1
+      int cols[15], bpos[15];
+      for (int a = 0; a < 3; ++a) { cols[a] = 3 + a; bpos[a] = a; cols[3 + a] = 6 + 3 * f + a; bpos[3 + a] = -1; cols[12 + a] = 24 + 3 * f + a; bpos[12 + a] = -1; }
+      for (int a = 0; a < 6; ++a) { cols[6 + a] = 18 + a; bpos[6 + a] = 3 + a; }
+      const int nc = c ? 6 : 15;
+      double jx[3][15];
+      for (int ii = 0; ii < 15; ++ii) {
+        const int i = cols[ii];
+        for (int a = 0; a < 3; ++a) jx[a][ii] = c ? 0.0 : ((i < 18) ? dvq[(3 * f + a + 12 * i) * st] : s.J[3 * f + a + 12 * (i - 18)]);
+      }
+      for (int jj = 0; jj < nc; ++jj)
+        for (int ii = 0; ii < nc; ++ii) {
           const int i = cols[ii], j = cols[jj];
-          double hh = 0;
-          for (int a = 0; a < 3; ++a) hh += s.J[3 * f + a + 12 * i] * w[a] * s.J[3 * f + a + 12 * j];
-          acc[i + 36 * j] += hh * dt;
-        }
-      if (!c) {
-        // columns of [dv/dq | J]: q-half 3..5 and leg; v-half 18..23 and 18 + leg
-        for (int a = 0; a < 6; ++a) cols[6 + a] = 18 + a;
-        for (int a = 0; a < 3; ++a) cols[12 + a] = 18 + 6 + 3 * f + a;
-        double jx[3][15];
-        for (int ii = 0; ii < 15; ++ii) {
-          const int i = cols[ii];
-          for (int a = 0; a < 3; ++a) jx[a][ii] = (i < 18) ? dvq[(3 * f + a + 12 * i) * st] : s.J[3 * f + a + 12 * (i - 18)];
-        }
-        for (int jj = 0; jj < 15; ++jj)
-          for (int ii = 0; ii < 15; ++ii) {
+          const bool shared = bpos[ii] >= 0 && bpos[jj] >= 0;
+          double val = shared ? bb[bpos[ii] + 9 * bpos[jj]] : ((i == j) ? dg[i] : 0.0);
+          if (ii < 6 && jj < 6) {
+            double hh = 0;
+            for (int a = 0; a < 3; ++a) hh += s.J[3 * f + a + 12 * i] * w[a] * s.J[3 * f + a + 12 * j];
+            val += hh * dt;
+          }
+          if (!c) {
             double hh = 0;
             for (int a = 0; a < 3; ++a) hh += jx[a][ii] * ph.w_swingvel[a] * jx[a][jj];
-            acc[cols[ii] + 36 * cols[jj]] += hh * dt;
+            val += hh * dt;
           }
-      }
+          if (shared) bb[bpos[ii] + 9 * bpos[jj]] = val; else lxxg[(size_t)(i + 36 * j) * ldb] = val;
+        }
+      if (c) for (int a = 0; a < 3; ++a) { const int i = 24 + 3 * f + a; lxxg[(size_t)(37 * i) * ldb] = dg[i]; }  // leg-velocity diagonal of a stance foot
     }
-    for (int i = 0; i < 1296; ++i) lxxg[(size_t)i * ldb] = acc[i];
+    for (int q = 0; q < 9; ++q)
+      for (int p = 0; p < 9; ++p) lxxg[(size_t)((p < 3 ? 3 + p : 15 + p) + 36 * (q < 3 ? 3 + q : 15 + q)) * ldb] = bb[p + 9 * q];
     double ming;
     return running_cost_k(ph, rec, x, u, s.grf, s.pf, s.vf, reb, ming);
   }
