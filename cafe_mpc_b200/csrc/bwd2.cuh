@@ -50,7 +50,7 @@ __device__ __forceinline__ void gemm_nt(const double* __restrict__ A, int lda, c
   for (int r = 0; r < TR; ++r)
 #pragma unroll
     for (int q = 0; q < TC; ++q) acc[r][q] = 0;
-#pragma unroll 2
+#pragma unroll 6
   for (int l = 0; l < KK; ++l) {
     double av[TR], bv[TC];
 #pragma unroll
@@ -63,7 +63,7 @@ __device__ __forceinline__ void gemm_nt(const double* __restrict__ A, int lda, c
       for (int q = 0; q < TC; ++q) acc[r][q] += av[r] * bv[q];
   }
   if constexpr (KK2 > 0) {
-#pragma unroll 2
+#pragma unroll 6
     for (int l = 0; l < KK2; ++l) {
       double av[TR], bv[TC];
 #pragma unroll
