@@ -6,9 +6,22 @@
 
 namespace cafe_dev {
 
-__device__ __noinline__ void wbg_terms(const double* q, const double* v, double* nle, double* Mlow, double* J, double* gam, double* pf, double* vf) {
-  cafe_gen_wb::wb_terms(q, v, [&](int i, double x) { nle[i] = x; }, [&](int i, double x) { Mlow[i] = x; }, [&](int i, double x) { J[i] = x; },
-                        [&](int i, double x) { gam[i] = x; }, [&](int i, double x) { pf[i] = x; }, [&](int i, double x) { vf[i] = x; });
+// M (lower, ld 18; the caller zero-initialises it), nle, foot Jacobians, Jdot v, foot positions / velocities: trunk + one piece per leg
+__device__ __noinline__ void wbg_terms_trunk(const double* q, const double* v, double* nle, double* Mlow) {
+  cafe_gen_wb::wb_terms_trunk(q, v, cafe_gen_wb::BiasDst{nle}, cafe_gen_wb::MassDst{Mlow});
+}
+#define CAFE_TERMS_LEG(F)                                                                                                                        \
+  __device__ __noinline__ void wbg_terms_leg##F(const double* q, const double* v, double* nle, double* Mlow, double* J, double* gam, double* pf, \
+                                                double* vf) {                                                                                    \
+    cafe_gen_wb::wb_terms_leg##F(q, v, cafe_gen_wb::BiasDst{nle}, cafe_gen_wb::MassDst{Mlow}, cafe_gen_wb::PlainDst{J, 1},                       \
+                                 cafe_gen_wb::PlainDst{gam, 1}, cafe_gen_wb::PlainDst{pf, 1}, cafe_gen_wb::PlainDst{vf, 1});                     \
+  }
+CAFE_TERMS_LEG(0) CAFE_TERMS_LEG(1) CAFE_TERMS_LEG(2) CAFE_TERMS_LEG(3)
+__device__ void wbg_terms(const double* q, const double* v, double* nle, double* Mlow, double* J, double* gam, double* pf, double* vf) {
+  for (int i = 0; i < 6; ++i) nle[i] = 0.0;
+  wbg_terms_trunk(q, v, nle, Mlow);
+  wbg_terms_leg0(q, v, nle, Mlow, J, gam, pf, vf); wbg_terms_leg1(q, v, nle, Mlow, J, gam, pf, vf);
+  wbg_terms_leg2(q, v, nle, Mlow, J, gam, pf, vf); wbg_terms_leg3(q, v, nle, Mlow, J, gam, pf, vf);
 }
 __device__ __noinline__ void wbg_feet(const double* q, const double* v, double* pf, double* vf, double* J) {
   cafe_gen_wb::wb_feet(q, v, [&](int i, double x) { pf[i] = x; }, [&](int i, double x) { vf[i] = x; }, [&](int i, double x) { J[i] = x; });

@@ -41,6 +41,17 @@ struct JtfDst {
   }
 };
 
+// shares of the mass matrix (lower triangle, ld 18) and of the bias vector: rows/columns 0..5 are common to all pieces and are
+// accumulated onto a zero-initialised destination, the rest is private to one leg
+struct MassDst {
+  double* p;
+  CAFE_HD void operator()(int idx, double x) const { if (idx % 18 < 6 && idx / 18 < 6) p[idx] += x; else p[idx] = x; }
+};
+struct BiasDst {
+  double* p;
+  CAFE_HD void operator()(int idx, double x) const { if (idx < 6) p[idx] += x; else p[idx] = x; }
+};
+
 struct PlainDst {
   double* p; size_t st;
   CAFE_HD void operator()(int idx, double x) const { p[idx * st] = x; }

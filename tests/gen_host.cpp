@@ -35,6 +35,13 @@ extern "C" int gen_eval_wb(const char* name, const double* const* in, double* co
   auto o = [&](int k) { return [out, k](int i, double v) { out[k][i] = v; }; };
   using namespace cafe_gen_wb;
   if (n == "wb_terms") wb_terms(in[0], in[1], o(0), o(1), o(2), o(3), o(4), o(5));
+  else if (n == "wb_terms_pieces") {  // trunk + four legs onto zero-initialised outputs, composed like the device wrapper does
+    wb_terms_trunk(in[0], in[1], BiasDst{out[0]}, MassDst{out[1]});
+    wb_terms_leg0(in[0], in[1], BiasDst{out[0]}, MassDst{out[1]}, PlainDst{out[2], 1}, PlainDst{out[3], 1}, PlainDst{out[4], 1}, PlainDst{out[5], 1});
+    wb_terms_leg1(in[0], in[1], BiasDst{out[0]}, MassDst{out[1]}, PlainDst{out[2], 1}, PlainDst{out[3], 1}, PlainDst{out[4], 1}, PlainDst{out[5], 1});
+    wb_terms_leg2(in[0], in[1], BiasDst{out[0]}, MassDst{out[1]}, PlainDst{out[2], 1}, PlainDst{out[3], 1}, PlainDst{out[4], 1}, PlainDst{out[5], 1});
+    wb_terms_leg3(in[0], in[1], BiasDst{out[0]}, MassDst{out[1]}, PlainDst{out[2], 1}, PlainDst{out[3], 1}, PlainDst{out[4], 1}, PlainDst{out[5], 1});
+  }
   else if (n == "wb_feet") wb_feet(in[0], in[1], o(0), o(1), o(2));
   else if (n == "wb_kin_partials") {  // the four per-foot pieces, composed like the device wrapper does
     wb_kin_partials_foot0(in[0], in[1], in[2], in[3], PlainDst{out[0], 1}, PlainDst{out[1], 1}, PlainDst{out[2], 1}, JtfDst<0>{out[3], 1});

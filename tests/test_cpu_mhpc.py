@@ -140,6 +140,30 @@ def test_generated_dynamics_terms_match_oracle_model(gen_lib):
         np.testing.assert_allclose(J @ v, vf, atol=1e-13)  # v_foot = J v
 
 
+def test_generated_pieces_sum_to_the_whole(gen_lib):
+    """The device path evaluates M, nle, the foot kinematics and the RNEA derivatives as trunk + one piece per leg (smaller live
+    sets): the composed pieces equal the monolithic generated routine, and the RNEA-derivative pieces equal central differences of
+    tau = M qdd + nle built from it."""
+    rng = np.random.default_rng(23)
+    shapes = [(18,), (18, 18), (12, 18), (12,), (12,), (12,)]
+    for _ in range(3):
+        q, v, a = rng.normal(size=18) * .5, rng.normal(size=18), rng.normal(size=18) * 3
+        whole = gen_wb(gen_lib, "wb_terms", [q, v], shapes)
+        parts = gen_wb(gen_lib, "wb_terms_pieces", [q, v], shapes)
+        for w, p_ in zip(whole, parts):
+            np.testing.assert_allclose(p_, w, rtol=0, atol=1e-13 * max(1.0, np.abs(w).max()))
+
+        def tau(q_, v_):
+            nle, Ml = gen_wb(gen_lib, "wb_terms", [q_, v_], shapes)[:2]
+            return (np.tril(Ml) + np.tril(Ml, -1).T) @ a + nle
+        dq, dv = gen_wb(gen_lib, "wb_rnea_derivs", [q, v, a], [(18, 18), (18, 18)])
+        e = 1e-6
+        for i in range(18):
+            d = np.zeros(18); d[i] = e
+            np.testing.assert_allclose(dq[:, i], (tau(q + d, v) - tau(q - d, v)) / (2 * e), atol=2e-6 * max(1.0, np.abs(dq).max()))
+            np.testing.assert_allclose(dv[:, i], (tau(q, v + d) - tau(q, v - d)) / (2 * e), atol=2e-6 * max(1.0, np.abs(dv).max()))
+
+
 def _fd_check(prob, phase, x, u, n, tol):
     xn, y, A, B, Cm, D = oracle_dynamics(prob.deck, phase, 3, x, u, partials=True)
     e = 1e-6

@@ -48,7 +48,23 @@ def main():
     o_g = [(3 * f + r, feet[f]["a"][r]) for f in range(4) for r in range(3)]
     o_p = [(3 * f + r, feet[f]["p"][r]) for f in range(4) for r in range(3)]
     o_v = [(3 * f + r, feet[f]["v"][r]) for f in range(4) for r in range(3)]
-    pieces.append(emit_function(ctx, "wb_terms", 2, [o_nle, o_M, o_J, o_g, o_p, o_v]))
+    pieces.append(emit_function(ctx, "wb_terms", 2, [o_nle, o_M, o_J, o_g, o_p, o_v]))   # monolithic version: host tests only
+    # the same quantities split by inertia group (M and nle are linear in the inertias; foot f's kinematics involve the base and
+    # leg f only): trunk -> its share of nle, M; leg f -> its share of nle, M and foot f's J, Jdot v, position, velocity. The
+    # shares overlap in rows/columns 0..5 only (accumulated by the caller, wb_pieces.h).
+    for name, only, f in [("trunk", {5}, None)] + [("leg%d" % f, {6 + 3 * f, 7 + 3 * f, 8 + 3 * f}, f) for f in range(4)]:
+        nle_p = m.rnea(q, v, zero, only=only)
+        cols = {}
+        def mcol(c):
+            if c not in cols:
+                e = [ctx.const(1.0 if i == c else 0.0) for i in range(18)]
+                cols[c] = m.rnea(q, zero, e, gravity=False, only=only)
+            return cols[c]
+        outs = [[(i, nle_p[i]) for i in range(18)], [(r + 18 * c, mcol(c)[r]) for c in range(18) for r in range(c, 18)]]
+        if f is not None:
+            outs += [[(3 * f + r + 12 * c, feet[f]["J"][r][c]) for c in range(18) for r in range(3)], [(3 * f + r, feet[f]["a"][r]) for r in range(3)],
+                     [(3 * f + r, feet[f]["p"][r]) for r in range(3)], [(3 * f + r, feet[f]["v"][r]) for r in range(3)]]
+        pieces.append(emit_function(ctx, "wb_terms_" + name, 2, outs))
     pieces.append(emit_function(ctx, "wb_feet", 2, [o_p, o_v, o_J]))
     # RNEA derivatives, split by inertia: tau = tau[trunk] + sum_f tau[leg f] (RNEA is linear in the inertias); tau[leg f] depends
     # on the base and on leg f only, so every piece is a short function with a small live set (the monolithic 34.6 k-op version
