@@ -494,6 +494,19 @@ void Solver::solve(const CafeOptions& o) {
 /* ---------------- C API */
 using namespace oracle;
 
+/* TEST HOOK: the Eigen-3.3 LDLT restatement on its own. A: n x n column-major (lower part used). Returns isPositive();
+ * inv receives solve(Identity) (what SinglePhase::backward_sweep uses as Quu_inv), pivot the smallest |D| entry. */
+extern "C" int cafe_oracle_ldlt(const double* A, int n, double* inv, double* min_pivot) {
+  oracle::Mat M(n, n);
+  for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) M(i, j) = A[i + n * j];
+  oracle::PivLDLT f;
+  f.compute(M);
+  if (inv) { oracle::Mat X = f.solveIdentity(); for (int j = 0; j < n; ++j) for (int i = 0; i < n; ++i) inv[i + n * j] = X(i, j); }
+  if (min_pivot) *min_pivot = f.min_pivot;
+  return f.isPositive() ? 1 : 0;
+}
+
+
 extern "C" long cafe_oracle_solution_size(const CafeDeck* deck) {
   long s = 0;
   for (int i = 0; i < deck->n_phases; ++i) {

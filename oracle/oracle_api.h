@@ -16,6 +16,8 @@ extern "C" {
 /* number of doubles of one packed solution (see cafe_solution_layout in cafe_gpu.h):
  * per phase: Xbar[(h+1)n] Ubar[h m] Y[h p] dU[h m] K[h m n] Qu[h m] Quu[h m m] Qux[h m n] G[(h+1) n] */
 long cafe_oracle_solution_size(const CafeDeck* deck);
+/* test hook: the Eigen-3.3 pivoted LDLT restatement alone (isPositive, solve(Identity), smallest pivot) */
+int cafe_oracle_ldlt(const double* A, int n, double* inv, double* min_pivot);
 
 /* per-iteration trace record (doubles), one per executed DDP iteration */
 #define CAFE_TRACE_W 12

@@ -188,10 +188,34 @@ def test_oracle_iterations_decrease_merit(hkd_problem, hkd_options):
 
 
 def test_oracle_ldlt_matches_numpy():
+    """The restatement of Eigen 3.3's pivoted LDLT behind the oracle's PD test and Quu^-1 (SinglePhase.cpp:366-375): inverse against
+    numpy, sign decision on definite / indefinite / semidefinite matrices, and permutation invariance of the decision."""
     from oracle_bindings import oracle
-    lib = oracle()  # noqa: F841  (exercised through the solver; here check PD decision on the golden run)
-    A = np.array([[4., 1, 0], [1, 3, 1], [0, 1, 2]])
-    assert np.all(np.linalg.eigvalsh(A) > 0)
+    lib = oracle()
+    lib.cafe_oracle_ldlt.restype = C.c_int
+    rng = np.random.default_rng(3)
+
+    def ldlt(A):
+        A = np.asfortranarray(A, dtype=np.float64)
+        n = A.shape[0]
+        inv = np.zeros((n, n), order="F")
+        piv = C.c_double()
+        pos = lib.cafe_oracle_ldlt(A.ctypes.data_as(C.c_void_p), n, inv.ctypes.data_as(C.c_void_p), C.byref(piv))
+        return bool(pos), inv, piv.value
+
+    for n in (1, 3, 12, 24):
+        B = rng.normal(size=(n, n + 2))
+        A = B @ B.T + 1e-3 * np.eye(n)                      # SPD, like Quu + reg I
+        pos, inv, piv = ldlt(A)
+        assert pos and piv > 0
+        np.testing.assert_allclose(inv, np.linalg.inv(A), rtol=1e-9, atol=1e-9 * np.abs(np.linalg.inv(A)).max())
+        perm = rng.permutation(n)
+        assert ldlt(A[np.ix_(perm, perm)])[0]
+        w, V = np.linalg.eigh(A)
+        w[0] = -abs(w[0]) - 0.1                               # one negative eigenvalue: the sweep must be rejected
+        assert not ldlt((V * w) @ V.T)[0]
+    assert ldlt(np.zeros((4, 4)))[0]                          # Eigen: ZeroSign counts as positive (isPositive())
+    assert not ldlt(-np.eye(3))[0]
 
 
 # ------------------------------------------------------------------ C ABI: loads and exports every declared symbol
