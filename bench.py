@@ -243,6 +243,18 @@ def main():
                 "traffic": traffic, "traffic_source": traffic_src, "flop_per_launch": flops / n_l, "avg_launch_ms": tm["ms"]["bwd"] / n_l, "share_of_step": share,
                 "peak_source": "measured live: cafe_gpu_measure_fp64_peak (DFMA microbenchmark, 8 independent chains/thread); MEASURED_PEAKS.json has no fp64 entry",
                 "kernel_ms": tm["ms"], "hbm_peak_gbs": _hbm_peak()}
+        # secondary figures per kernel family: share of the step and, where a committed ncu capture exists, the HBM fraction
+        # (DRAM bytes of one full-batch launch x launches / live kernel time; later ticks run fewer active problems, so this is an upper bound)
+        per = {}
+        tot_ms = max(sum(tm["ms"].values()), 1e-9)
+        for fam, kname in (("roll", "k_roll"), ("lq", "k_lq"), ("bwd", "k_bwd2"), ("misc", None), ("select", None), ("accept", None)):
+            e = {"ms": tm["ms"][fam], "launches": tm["launches"][fam], "share_of_step": tm["ms"][fam] / tot_ms}
+            tb, _ = _ncu_traffic(kname) if (kname and args.workload == "mhpc" and B == 4096) else (None, None)
+            if tb and tm["ms"][fam] > 0:
+                gbs = tb * tm["launches"][fam] / (tm["ms"][fam] * 1e-3) / 1e9
+                e["hbm_gbs_upper_bound"] = gbs; e["hbm_frac_upper_bound"] = gbs / _hbm_peak()
+            per[fam] = e
+        roof["per_kernel"] = per
         if not args.no_cpu_baseline:
             cores = len(os.sched_getaffinity(0))
             v, n = cpu_sample(x0_all[: cores * args.cpu_per_core], cores, args.cpu_per_core, args.workload)

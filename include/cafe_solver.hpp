@@ -78,6 +78,28 @@ class MultiPhaseDDP {
   void solve(HSDDP_OPTION& option) { check(cafe_gpu_solve_batch(h_, x0_.data(), B_, &option)); }
 
   std::vector<CafeInfo> get_solver_info() const { std::vector<CafeInfo> v(B_); check(cafe_gpu_get_info(h_, v.data())); return v; }
+  // the reference's scalar getters (header/MultiPhaseDDP.h:77-93), for problem b of the batch
+  void get_solver_info(int b, int& n_iters, int& n_ls_iters, int& n_reg_iters, float& solve_time) const {
+    const CafeInfo i = get_solver_info().at(b);
+    n_iters = i.iter; n_ls_iters = i.ls_iter_total; n_reg_iters = i.reg_iter_total; solve_time = (float)solve_ms();  // batch time: the problems run together
+  }
+  double get_actual_cost(int b) const { return get_solver_info().at(b).cost; }
+  double get_dyn_infeasibility(int b) const { return get_solver_info().at(b).feas; }
+  double get_terminal_constraint_violation(int b) const { return get_solver_info().at(b).max_tconstr; }
+  double get_path_constraint_violation(int b) const { return get_solver_info().at(b).max_pconstr; }
+  // the four per-iteration buffers of get_solver_info(cost, dyn_feas, eqn_feas, ineq_feas) (float like the reference), problem b
+  void get_solver_info(int b, std::vector<float>& cost, std::vector<float>& dyn_feas, std::vector<float>& eqn_feas, std::vector<float>& ineq_feas) const {
+    const int cap = 256;
+    const std::vector<double> h = get_history(cap);
+    const int n = get_solver_info().at(b).n_hist;
+    cost.clear(); dyn_feas.clear(); eqn_feas.clear(); ineq_feas.clear();
+    for (int i = 0; i < n && i < cap; ++i) {
+      const double* r = &h[((size_t)b * cap + i) * 4];
+      cost.push_back((float)r[0]); dyn_feas.push_back((float)r[1]); eqn_feas.push_back((float)r[2]); ineq_feas.push_back((float)r[3]);
+    }
+  }
+  // float32 MHPC_Command_lcmt fields for the first n_steps whole-body knots (what publish_mpc_cmd sends, MHPCLocomotion.cpp:236-281)
+  std::vector<float> get_lcm_commands(int n_steps) const { std::vector<float> v((size_t)B_ * cafe_lcm_command_size(n_steps)); check(cafe_gpu_get_lcm_commands(h_, n_steps, v.data())); return v; }
   // cost / dynamics feasibility / terminal / path constraint buffers (get_solver_info(cost_out, ...), MultiPhaseDDP.cpp:554-563)
   std::vector<double> get_history(int cap) const { std::vector<double> v((size_t)B_ * cap * 4); check(cafe_gpu_get_history(h_, v.data(), cap)); return v; }
   long solution_size() const { return cafe_solution_size(deck_); }
