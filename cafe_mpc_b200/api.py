@@ -11,7 +11,7 @@ import os
 
 import numpy as np
 
-from ._ctypes_defs import (CAFE_NKERNELS, CAFE_TRACE_W, MODEL_DIMS, Deck, Info, Options)
+from ._ctypes_defs import (CAFE_NKERNELS, CAFE_REF_W, CAFE_TRACE_W, MODEL_DIMS, Deck, Info, Options)
 from .lib import check, lib
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -35,6 +35,11 @@ class _DeckOwner:
     def phases(self):
         d = self.deck.contents
         return [d.phase[i] for i in range(d.n_phases)]
+
+    def reference_records(self):
+        """Copy of the deck's per-knot reference records, [n_records, CAFE_REF_W] (layout: include/cafe_deck.h CAFE_REF_*)."""
+        d = self.deck.contents
+        return np.ctypeslib.as_array(d.ref, shape=(d.n_records, CAFE_REF_W)).copy()
 
     def __del__(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -155,6 +160,14 @@ class MultiPhaseDDP:
             out = np.zeros((self.B, sz))
         check(lib.cafe_gpu_get_commands(self._h, n_gain_knots, out.ctypes.data_as(C.c_void_p)))
         return out
+
+    def set_references(self, refs):
+        """Per-problem reference records [B, n_records, CAFE_REF_W] on the shared phase schedule (None: back to the deck's)."""
+        if refs is None:
+            check(lib.cafe_gpu_set_references(self._h, None, 0))
+            return
+        refs = np.ascontiguousarray(refs, dtype=np.float64)
+        check(lib.cafe_gpu_set_references(self._h, refs.ctypes.data_as(C.c_void_p), refs.shape[0]))
 
     def get_lcm_commands(self, n_steps=8):
         """float32 MHPC_Command_lcmt record per problem (see include/cafe_gpu.h); use unpack_lcm_command to name the fields."""

@@ -35,7 +35,8 @@ struct PhaseDev {
   double w_footreg[3], w_swingpos[3], w_swingvel[3], w_tdvel[3];
   CafeRebParam reb_grf, reb_torque, reb_joint, reb_minheight;
   CafeAlParam al_td;
-  const double* ref;  // [h+1][CAFE_REF_W], shared by the batch
+  const double* ref;     // [h+1][CAFE_REF_W], shared by the batch
+  const double* ref_pp;  // optional per-problem records [h+1][CAFE_REF_W][ldb] (same contact schedule), else nullptr
   // trajectories, [(h+1) or h][dim][ldb]
   double *X, *Xbar, *dX, *G, *Defect;
   double *U, *Ubar, *dU, *Qu, *Y;
@@ -80,6 +81,13 @@ struct SolverDev {
   const double* x0;  // [n0][ldb]
   short knot_phase[CAFE_MAX_KNOTS], knot_k[CAFE_MAX_KNOTS];
 };
+
+// reference record of knot k as problem b sees it: the deck's shared record, or the problem's own (copied to thread-local storage)
+__device__ __forceinline__ const double* knot_record(const PhaseDev& ph, int k, int ldb, int b, double* local) {
+  if (!ph.ref_pp) return ph.ref + (size_t)k * CAFE_REF_W;
+  for (int c = 0; c < CAFE_REF_W; ++c) local[c] = ph.ref_pp[((size_t)k * CAFE_REF_W + c) * (size_t)ldb + b];
+  return local;
+}
 
 // element (k, c) of problem b in an array with NC components per knot
 __device__ __forceinline__ size_t gix(int k, int NC, int c, int ldb, int b) { return ((size_t)k * NC + c) * (size_t)ldb + b; }

@@ -34,7 +34,8 @@ __device__ void roll_knot(const SolverDev& S, int pi, int k, int a, int b) {
   const PhaseDev& ph = S.ph[pi];
   const int ldb = S.ldb, h = ph.h;
   const double eps = S.eps[a];
-  const double* rec = ph.ref + (size_t)k * CAFE_REF_W;
+  double rec_local[CAFE_REF_W];
+  const double* rec = knot_record(ph, k, ldb, b, rec_local);
   const size_t aX = (size_t)a * (h + 1) * N * ldb, aU = (size_t)a * h * M * ldb, aY = (size_t)a * h * PY * ldb;
   const size_t aS = (size_t)a * (h + 1) * ldb;
   double x[N], dlt[N];
@@ -145,7 +146,8 @@ __device__ void lq_knot_generic(const SolverDev& S, int pi, int k, int b) {
   constexpr int N = Model::N, M = Model::M, PY = Model::PY;
   const PhaseDev& ph = S.ph[pi];
   const int ldb = S.ldb, h = ph.h;
-  const double* rec = ph.ref + (size_t)k * CAFE_REF_W;
+  double rec_local[CAFE_REF_W];
+  const double* rec = knot_record(ph, k, ldb, b, rec_local);
   double x[N];
   double dsq = 0;
 #pragma unroll

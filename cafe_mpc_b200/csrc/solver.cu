@@ -37,6 +37,7 @@ struct CafeHandle {
   char* arena = nullptr;  // everything per-problem
   size_t arena_bytes = 0, zero_bytes = 0;  // [0, zero_bytes) is re-zeroed at every solve
   double* d_ref = nullptr;
+  double* d_ref_pp = nullptr; int ref_pp_B = 0;  // per-problem reference records [n_records][CAFE_REF_W][ldb]
   double* d_x0raw = nullptr;
   int* d_fail = nullptr; size_t fail_bytes = 0;
   int* h_nactive = nullptr;  // pinned
@@ -66,7 +67,8 @@ __global__ void k_init(const SolverDev* __restrict__ Sp, const double* __restric
   if (gk >= S.n_knots || b >= S.B) return;
   const int pi = S.knot_phase[gk], k = S.knot_k[gk];
   const PhaseDev& ph = S.ph[pi];
-  const double* rec = ph.ref + (size_t)k * CAFE_REF_W;
+  double rec_local[CAFE_REF_W];
+  const double* rec = knot_record(ph, k, S.ldb, b, rec_local);
   for (int i = 0; i < ph.n; ++i) { const double v = rec[CAFE_REF_XR + i]; ph.Xbar[gix(k, ph.n, i, S.ldb, b)] = v; ph.X[gix(k, ph.n, i, S.ldb, b)] = v; }
   if (k == 0) for (int i = 0; i < ph.n_td; ++i) { ph.al_sigma[(size_t)i * S.ldb + b] = ph.al_td.sigma; ph.al_lambda[(size_t)i * S.ldb + b] = ph.al_td.lambda; }
   if (gk == 0) {
@@ -303,7 +305,7 @@ extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, 
   CUDA_OK(cudaMemset(H->arena, 0, H->arena_bytes));
   CUDA_OK(cudaMalloc(&H->d_ref, H->ref_host.size() * sizeof(double)));
   CUDA_OK(cudaMemcpy(H->d_ref, H->ref_host.data(), H->ref_host.size() * sizeof(double), cudaMemcpyHostToDevice));
-  for (int i = 0; i < deck->n_phases; ++i) S.ph[i].ref = H->d_ref + (size_t)deck->phase[i].knot_offset * CAFE_REF_W;
+  for (int i = 0; i < deck->n_phases; ++i) { S.ph[i].ref = H->d_ref + (size_t)deck->phase[i].knot_offset * CAFE_REF_W; S.ph[i].ref_pp = nullptr; }
   CUDA_OK(cudaMalloc(&H->d_x0raw, (size_t)H->ldb * CAFE_MAX_N * sizeof(double)));
   CUDA_OK(cudaMalloc(&H->dS, sizeof(SolverDev)));
   CUDA_OK(cudaMallocHost(&H->h_nactive, 64));
@@ -340,7 +342,7 @@ extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, 
 extern "C" int cafe_gpu_destroy(CafeHandle* H) {
   if (!H) return 0;
   cudaSetDevice(H->device);
-  cudaFree(H->arena); cudaFree(H->d_ref); cudaFree(H->d_x0raw); cudaFree(H->dS); cudaFree(H->d_pack); cudaFree(H->d_segs);
+  cudaFree(H->arena); cudaFree(H->d_ref); cudaFree(H->d_ref_pp); cudaFree(H->d_x0raw); cudaFree(H->dS); cudaFree(H->d_pack); cudaFree(H->d_segs);
   if (H->h_nactive) cudaFreeHost(H->h_nactive);
   if (H->stream) cudaStreamDestroy(H->stream);
   if (H->ev0) cudaEventDestroy(H->ev0);
@@ -356,6 +358,7 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
   if (!opt->MS) { cafe::set_last_error("single shooting (MS = false) is not supported: every knot must be a shooting node"); return CAFE_ERR_UNSUPPORTED; }
   if (opt->update_relax != 1.0 || opt->update_ReB != 1.0) { cafe::set_last_error("update_relax / update_ReB != 1 are not supported by this build"); return CAFE_ERR_UNSUPPORTED; }
   if (opt->max_AL_iter * opt->max_DDP_iter + 1 > CAFE_HIST_CAP) { cafe::set_last_error("iteration caps exceed the history capacity"); return CAFE_ERR_UNSUPPORTED; }
+  if (H->S.ph[0].ref_pp && B > H->ref_pp_B) { cafe::set_last_error("batch larger than the per-problem reference set"); return CAFE_ERR_ARG; }
   CUDA_OK(cudaSetDevice(H->device));
   SolverDev& S = H->S;
   S.B = B; S.opt = *opt;
@@ -551,6 +554,36 @@ static int commands_impl(CafeHandle* H, int n_gain_knots, double* cmd, double* d
     left -= g;
   }
   return run_pack(H, segs, off, 0, H->B, cmd, dev_out);
+}
+
+// ---- per-problem references with a shared contact schedule: every problem tracks its own records
+extern "C" int cafe_gpu_set_references(CafeHandle* H, const double* refs, int B) {
+  if (!H) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
+  CUDA_OK(cudaSetDevice(H->device));
+  SolverDev& S = H->S;
+  if (!refs) {  // back to the deck's shared records
+    for (int i = 0; i < S.n_phases; ++i) S.ph[i].ref_pp = nullptr;
+    H->ref_pp_B = 0;
+    return 0;
+  }
+  if (B <= 0 || B > H->max_batch) { cafe::set_last_error("bad batch size for the reference set"); return CAFE_ERR_ARG; }
+  const size_t nrec = (size_t)H->deck.n_records, W = CAFE_REF_W, ldb = (size_t)H->ldb;
+  // the phase deck (horizons, contacts, touchdown feet) is shared: the contact flags of every record must be the deck's
+  for (int b = 0; b < B; ++b)
+    for (size_t r = 0; r < nrec; ++r)
+      for (int f = 0; f < 4; ++f)
+        if (refs[((size_t)b * nrec + r) * W + CAFE_REF_CONTACT + f] != H->ref_host[r * W + CAFE_REF_CONTACT + f]) {
+          cafe::set_last_error("per-problem references must keep the deck's contact schedule");
+          return CAFE_ERR_UNSUPPORTED;
+        }
+  std::vector<double> t(nrec * W * ldb, 0.0);  // batch-major transpose
+  for (int b = 0; b < B; ++b)
+    for (size_t e = 0; e < nrec * W; ++e) t[e * ldb + b] = refs[(size_t)b * nrec * W + e];
+  if (!H->d_ref_pp) CUDA_OK(cudaMalloc(&H->d_ref_pp, t.size() * sizeof(double)));
+  CUDA_OK(cudaMemcpy(H->d_ref_pp, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
+  for (int i = 0; i < S.n_phases; ++i) S.ph[i].ref_pp = H->d_ref_pp + (size_t)H->deck.phase[i].knot_offset * W * ldb;
+  H->ref_pp_B = B;
+  return 0;
 }
 
 // ---- MHPC_Command_lcmt record (lcmtypes/MHPC_Command_lcmt.lcm, filled on the host by MHPCLocomotion.cpp:236-281): emitted

@@ -80,3 +80,29 @@ def barrel_batch(problem, B, perturb=True):
             for j in range(36):
                 x0[b, j] += MHPC_SCALE[j] * (2 * uniform(b, j) - 1)
     return x0
+
+
+# ---- per-problem references on a shared phase schedule: every problem is commanded a different forward
+# speed. Record layout: include/cafe_deck.h (CAFE_REF_XR 0, PF 72, PCOM 84, W 120).
+def speed_command_references(problem, B, max_dv=0.2):
+    """Returns [B, n_records, 120]: problem b tracks the deck's reference shifted by a constant extra forward speed
+    dv_b = max_dv (2u - 1), u = SplitMix64 counter b*64 + 40 (problem 0 keeps the deck's reference): x position += dv t,
+    forward velocity += dv, reference foot placements and CoM x += dv t. Contact flags (the phase schedule) are untouched."""
+    base = problem.reference_records()
+    d = problem.deck.contents
+    refs = np.tile(base, (B, 1, 1))
+    t_of, vx_of = np.zeros(d.n_records), np.zeros(d.n_records, dtype=int)
+    for i in range(d.n_phases):
+        ph = d.phase[i]
+        for k in range(ph.horizon + 1):
+            t_of[ph.knot_offset + k] = ph.t_offset + k * ph.dt
+            vx_of[ph.knot_offset + k] = {0: 9, 1: 18, 2: 6}[ph.model]   # index of the forward velocity in the state: HKD, WB, SRB
+    px_of = np.array([{0: 3, 1: 0, 2: 0}[d.phase[i].model] for i in range(d.n_phases) for _ in range(d.phase[i].horizon + 1)])
+    for b in range(1, B):
+        dv = max_dv * (2 * uniform(b, 40) - 1)
+        for r in range(d.n_records):
+            refs[b, r, px_of[r]] += dv * t_of[r]
+            refs[b, r, vx_of[r]] += dv
+            refs[b, r, 72:84:3] += dv * t_of[r]
+            refs[b, r, 84] += dv * t_of[r]
+    return refs

@@ -69,6 +69,11 @@ long cafe_command_size(const CafeDeck* deck, int n_gain_knots);
 /* ---- GPU solver ---- */
 int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, CafeHandle** out);
 int cafe_gpu_destroy(CafeHandle* h);
+/* Optional per-problem references (different velocity commands / targets per problem) on the deck's shared phase schedule:
+ * refs = host [B][deck->n_records][CAFE_REF_W], same record layout as CafeDeck.ref (what WBReference / SRBReference /
+ * HKDSinglePhaseReference hand to the costs, MHPCReference.cpp:10-76, HKDReference.cpp:8-62); contact flags must equal the deck's.
+ * Also replaces the cold-start guess Xbar = reference. refs = NULL returns to the shared records. */
+int cafe_gpu_set_references(CafeHandle* h, const double* refs, int B);
 /* x0: host [B][n0] row per problem. Runs every problem of the batch to its own termination. */
 int cafe_gpu_solve_batch(CafeHandle* h, const double* x0, int B, const CafeOptions* opt);
 /* same with x0 already resident on the device, layout [n0][ldb] (component-major), ldb >= B */

@@ -51,6 +51,15 @@ def oracle_solve(deck, opt, x0, cap=256):
     return d, hist[:d["n_hist"]], trace[:d["iter"]], sol
 
 
+def deck_with_references(deck, records):
+    """A copy of the deck whose reference records are `records` ([n_records, 120]); keep the returned tuple alive while in use."""
+    from cafe_mpc_b200._ctypes_defs import Deck
+    d2 = Deck.from_buffer_copy(deck.contents)
+    rec = np.ascontiguousarray(records, dtype=np.float64)
+    d2.ref = rec.ctypes.data_as(C.POINTER(C.c_double))
+    return C.pointer(d2), (d2, rec)
+
+
 def oracle_get(name, phase):
     lib = oracle()
     lib.cafe_oracle_get.restype = C.c_long

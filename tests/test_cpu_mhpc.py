@@ -261,3 +261,20 @@ def test_oracle_barrel_roll_matches_committed_golden(cm, mhpc_options):
         assert [info[k] for k in ("status", "iter", "ls_iter_total", "reg_iter_total", "outer_iter", "n_hist")] == list(g["%s_counts_0" % key])
         np.testing.assert_allclose(hist[:, 0], g["%s_hist_0" % key][:, 0], rtol=1e-9)
         np.testing.assert_allclose(sol, g["%s_sol_0" % key], rtol=0, atol=1e-8 * np.abs(sol).max())
+
+
+def test_per_problem_reference_set_keeps_the_schedule(cm, mhpc_impact, mhpc_options):
+    """workload.speed_command_references: same contact flags in every record, shifted targets; the oracle run on a deck that
+    carries another problem's records gives another solution (what the GPU per-problem path is checked against)."""
+    from cafe_mpc_b200 import workload
+    from oracle_bindings import deck_with_references
+    refs = workload.speed_command_references(mhpc_impact, 4)
+    base = mhpc_impact.reference_records()
+    assert refs.shape == (4,) + base.shape and np.array_equal(refs[0], base)
+    assert np.array_equal(refs[:, :, 99:103], np.tile(base[:, 99:103], (4, 1, 1)))       # CAFE_REF_CONTACT
+    assert np.abs(refs[2, :, 18] - base[:, 18])[:26].min() > 0                            # WB forward-velocity target moved
+    x0 = workload.mhpc_batch(1)[0]
+    i0, _, _, s0 = oracle_solve(mhpc_impact.deck, mhpc_options, x0)
+    dk, keep = deck_with_references(mhpc_impact.deck, refs[2])
+    i2, _, _, s2 = oracle_solve(dk, mhpc_options, x0)
+    assert i0["status"] == 0 and i2["status"] == 0 and abs(i0["cost"] - i2["cost"]) > 1e-6 and not np.allclose(s0, s2)

@@ -203,3 +203,40 @@ def test_lcm_command_record_is_the_float_cast_of_the_solution(cm, opt):
             assert np.array_equal(f[name], v.astype(np.float32)), name
     with pytest.raises(Exception):
         s.get_lcm_commands(26)   # more steps than whole-body knots
+
+
+def test_per_problem_references_match_oracle(cm, opt):
+    """SURVEY §8(f)4: every problem tracks its own reference (different commanded forward speed) on the shared phase schedule;
+    GPU == oracle run problem by problem on a deck carrying that problem's records. Impact-bearing offset so that the AL loop runs."""
+    from cafe_mpc_b200 import workload
+    from oracle_bindings import deck_with_references
+    prob = cm.MHPCProblem(CSV, k0=20)
+    B = 6
+    x0 = workload.mhpc_batch(B)
+    refs = workload.speed_command_references(prob, B)
+    assert np.array_equal(refs[0], prob.reference_records()) and not np.array_equal(refs[3], refs[0])
+    s = cm.MultiPhaseDDP(prob, 0, B)
+    s.set_initial_condition(x0)
+    s.solve(opt)
+    shared_info = s.get_solver_info()
+    s.set_references(refs)
+    s.solve(opt)
+    info = s.get_solver_info(); hist = s.get_history(256); sol = s.get_solution()
+    assert info[0] == shared_info[0]                 # problem 0 kept the deck's reference
+    assert any(info[b]["cost"] != shared_info[b]["cost"] for b in range(1, B))
+    for b in range(B):
+        dk, keep = deck_with_references(prob.deck, refs[b])
+        oi, oh, ot, osol = oracle_solve(dk, opt, x0[b])
+        assert [info[b][k] for k in COUNTS] == [oi[k] for k in COUNTS], b
+        np.testing.assert_allclose(hist[b, :oi["n_hist"], 0], oh[:, 0], rtol=RTOL)
+        gp, op = cm.unpack_solution(prob.deck, sol[b]), cm.unpack_solution(prob.deck, osol)
+        for pg, po in zip(gp, op):
+            for name in ("Xbar", "Ubar", "Y", "K", "dU", "Qu", "Quu", "Qux", "G"):
+                assert relerr(pg[name], po[name], FLOOR.get(name, 1e-6)) < RTOL, (b, name)
+    # a reference set that changes the contact schedule is refused, and NULL restores the shared records
+    bad = refs.copy(); bad[2, 5, 99] = 1.0 - bad[2, 5, 99]
+    with pytest.raises(Exception):
+        s.set_references(bad)
+    s.set_references(None)
+    s.solve(opt)
+    assert s.get_solver_info() == shared_info
