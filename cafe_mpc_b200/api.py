@@ -169,6 +169,15 @@ class MultiPhaseDDP:
         refs = np.ascontiguousarray(refs, dtype=np.float64)
         check(lib.cafe_gpu_set_references(self._h, refs.ctypes.data_as(C.c_void_p), refs.shape[0]))
 
+    def set_initial_guess(self, guess):
+        """Warm start: packed solutions [B, solution_size] whose Xbar / Ubar / K start the next solves (None: cold start)."""
+        if guess is None:
+            check(lib.cafe_gpu_set_initial_guess(self._h, None, 0))
+            return
+        guess = np.ascontiguousarray(guess, dtype=np.float64)
+        assert guess.shape[1] == lib.cafe_solution_size(self.problem.deck)
+        check(lib.cafe_gpu_set_initial_guess(self._h, guess.ctypes.data_as(C.c_void_p), guess.shape[0]))
+
     def get_lcm_commands(self, n_steps=8):
         """float32 MHPC_Command_lcmt record per problem (see include/cafe_gpu.h); use unpack_lcm_command to name the fields."""
         out = np.zeros((self.B, lib.cafe_lcm_command_size(n_steps)), dtype=np.float32)

@@ -37,7 +37,8 @@ struct CafeHandle {
   char* arena = nullptr;  // everything per-problem
   size_t arena_bytes = 0, zero_bytes = 0;  // [0, zero_bytes) is re-zeroed at every solve
   double* d_ref = nullptr;
-  double* d_ref_pp = nullptr; int ref_pp_B = 0;  // per-problem reference records [n_records][CAFE_REF_W][ldb]
+  double* d_ref_pp = nullptr; int ref_pp_B = 0;
+  double* d_guess = nullptr; size_t guess_bytes = 0; int guess_B = 0;  // packed initial guesses [B][solution_size] (warm start)  // per-problem reference records [n_records][CAFE_REF_W][ldb]
   double* d_x0raw = nullptr;
   int* d_fail = nullptr; size_t fail_bytes = 0;
   int* h_nactive = nullptr;  // pinned
@@ -95,6 +96,22 @@ __global__ void k_pack(const PackSeg* __restrict__ segs, int nseg, int ldb, int 
     const int bb = (int)(t % nb);
     const long e = t / nb;
     out[(size_t)bb * sol_size + sg.dst + e] = sg.src[(size_t)e * ldb + b0 + bb];
+  }
+}
+
+// inverse of k_pack for the warm start: packed records -> batch-major arrays (optionally two destinations: Xbar and X, Ubar and U)
+struct UnpackSeg { double* dst; double* dst2; int knots, nc; long src; };
+__global__ void k_unpack(const UnpackSeg* __restrict__ segs, int nseg, int ldb, int nb, long sol_size, const double* __restrict__ in) {
+  const int s = blockIdx.y;
+  if (s >= nseg) return;
+  const UnpackSeg sg = segs[s];
+  const long total = (long)sg.knots * sg.nc;
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total * nb; t += (long)gridDim.x * blockDim.x) {
+    const int bb = (int)(t % nb);
+    const long e = t / nb;
+    const double v = in[(size_t)bb * sol_size + sg.src + e];
+    sg.dst[(size_t)e * ldb + bb] = v;
+    if (sg.dst2) sg.dst2[(size_t)e * ldb + bb] = v;
   }
 }
 
@@ -342,7 +359,7 @@ extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, 
 extern "C" int cafe_gpu_destroy(CafeHandle* H) {
   if (!H) return 0;
   cudaSetDevice(H->device);
-  cudaFree(H->arena); cudaFree(H->d_ref); cudaFree(H->d_ref_pp); cudaFree(H->d_x0raw); cudaFree(H->dS); cudaFree(H->d_pack); cudaFree(H->d_segs);
+  cudaFree(H->arena); cudaFree(H->d_ref); cudaFree(H->d_ref_pp); cudaFree(H->d_guess); cudaFree(H->d_x0raw); cudaFree(H->dS); cudaFree(H->d_pack); cudaFree(H->d_segs);
   if (H->h_nactive) cudaFreeHost(H->h_nactive);
   if (H->stream) cudaStreamDestroy(H->stream);
   if (H->ev0) cudaEventDestroy(H->ev0);
@@ -358,6 +375,7 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
   if (!opt->MS) { cafe::set_last_error("single shooting (MS = false) is not supported: every knot must be a shooting node"); return CAFE_ERR_UNSUPPORTED; }
   if (opt->update_relax != 1.0 || opt->update_ReB != 1.0) { cafe::set_last_error("update_relax / update_ReB != 1 are not supported by this build"); return CAFE_ERR_UNSUPPORTED; }
   if (opt->max_AL_iter * opt->max_DDP_iter + 1 > CAFE_HIST_CAP) { cafe::set_last_error("iteration caps exceed the history capacity"); return CAFE_ERR_UNSUPPORTED; }
+  if (H->guess_B > 0 && B > H->guess_B) { cafe::set_last_error("batch larger than the initial-guess set"); return CAFE_ERR_ARG; }
   if (H->S.ph[0].ref_pp && B > H->ref_pp_B) { cafe::set_last_error("batch larger than the per-problem reference set"); return CAFE_ERR_ARG; }
   CUDA_OK(cudaSetDevice(H->device));
   SolverDev& S = H->S;
@@ -379,6 +397,28 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
   const unsigned g_knots = (unsigned)((nthr_knots + tpb - 1) / tpb);
   timed(H, 5, [&] { k_init<<<g_knots, tpb, 0, st>>>(H->dS, H->d_x0raw, n0); });
   if (x0_dev) timed(H, 5, [&] { k_init_devx0<<<(B + 127) / 128, 128, 0, st>>>(H->dS, x0_dev, ldx, n0); });
+  if (H->guess_B > 0) {
+    // warm start: Xbar (= X), Ubar (= U) and K of the caller's guess replace the cold-start values; the first rollout (eps = 0)
+    // then applies U = Ubar + K (X - Xbar) around it, which is how the reference re-solves after MHPCProblem::update
+    std::vector<UnpackSeg> segs;
+    long off = 0;
+    for (int i = 0; i < S.n_phases; ++i) {
+      PhaseDev& ph = S.ph[i];
+      const int n = ph.n, m = ph.m, p = ph.p, h = ph.h;
+      segs.push_back(UnpackSeg{ph.Xbar, ph.X, h + 1, n, off}); off += (long)(h + 1) * n;
+      segs.push_back(UnpackSeg{ph.Ubar, ph.U, h, m, off}); off += (long)h * m;
+      off += (long)h * p + (long)h * m;  // Y, dU
+      segs.push_back(UnpackSeg{ph.K, nullptr, h, m * n, off}); off += (long)h * m * n;
+      off += (long)h * m + (long)h * m * m + (long)h * m * n + (long)(h + 1) * n;  // Qu, Quu, Qux, G
+    }
+    UnpackSeg* d_us = nullptr;
+    CUDA_OK(cudaMalloc(&d_us, segs.size() * sizeof(UnpackSeg)));
+    CUDA_OK(cudaMemcpyAsync(d_us, segs.data(), segs.size() * sizeof(UnpackSeg), cudaMemcpyHostToDevice, st));
+    dim3 grid(592, (unsigned)segs.size());
+    timed(H, 5, [&] { k_unpack<<<grid, 256, 0, st>>>(d_us, (int)segs.size(), H->ldb, B, off, H->d_guess); });
+    CUDA_OK(cudaStreamSynchronize(st));
+    cudaFree(d_us);
+  }
   // ---- initial rollout (eps = 0) and bookkeeping
   {
     SolverDev S0 = S;  // same pointers, ladder {0}
@@ -554,6 +594,23 @@ static int commands_impl(CafeHandle* H, int n_gain_knots, double* cmd, double* d
     left -= g;
   }
   return run_pack(H, segs, off, 0, H->B, cmd, dev_out);
+}
+
+// ---- warm start: initial Xbar / Ubar / K per problem, in the packed solution layout (the other arrays of the record are ignored)
+extern "C" int cafe_gpu_set_initial_guess(CafeHandle* H, const double* guess, int B) {
+  if (!H) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
+  CUDA_OK(cudaSetDevice(H->device));
+  if (!guess) { H->guess_B = 0; return 0; }  // back to the cold start (Xbar = reference, zero controls and gains)
+  if (B <= 0 || B > H->max_batch) { cafe::set_last_error("bad batch size for the initial-guess set"); return CAFE_ERR_ARG; }
+  const size_t need = (size_t)B * (size_t)cafe_solution_size(&H->deck) * sizeof(double);
+  if (need > H->guess_bytes) {
+    cudaFree(H->d_guess); H->d_guess = nullptr; H->guess_bytes = 0;
+    CUDA_OK(cudaMalloc(&H->d_guess, need));
+    H->guess_bytes = need;
+  }
+  CUDA_OK(cudaMemcpy(H->d_guess, guess, need, cudaMemcpyHostToDevice));
+  H->guess_B = B;
+  return 0;
 }
 
 // ---- per-problem references with a shared contact schedule: every problem tracks its own records

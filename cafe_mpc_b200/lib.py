@@ -71,6 +71,6 @@ EXPORTED = [
     "cafe_deck_free", "cafe_hkd_state", "cafe_solution_size", "cafe_command_size", "cafe_gpu_create",
     "cafe_gpu_destroy", "cafe_gpu_solve_batch", "cafe_gpu_solve_batch_device", "cafe_gpu_get_info",
     "cafe_gpu_get_history", "cafe_gpu_get_trace", "cafe_gpu_get_solution", "cafe_gpu_get_commands", "cafe_gpu_get_commands_device", "cafe_gpu_get_solve_ms",
-    "cafe_gpu_set_references", "cafe_lcm_command_size", "cafe_gpu_get_lcm_commands", "cafe_gpu_get_lcm_commands_device",
+    "cafe_gpu_set_references", "cafe_gpu_set_initial_guess", "cafe_lcm_command_size", "cafe_gpu_get_lcm_commands", "cafe_gpu_get_lcm_commands_device",
     "cafe_gpu_get_timing", "cafe_gpu_set_profiling", "cafe_gpu_debug_get", "cafe_gpu_measure_fp64_peak",
 ]

@@ -74,6 +74,11 @@ int cafe_gpu_destroy(CafeHandle* h);
  * HKDSinglePhaseReference hand to the costs, MHPCReference.cpp:10-76, HKDReference.cpp:8-62); contact flags must equal the deck's.
  * Also replaces the cold-start guess Xbar = reference. refs = NULL returns to the shared records. */
 int cafe_gpu_set_references(CafeHandle* h, const double* refs, int B);
+/* Warm start (receding-horizon re-solves): initial Xbar / Ubar / K per problem in the packed solution layout, host
+ * [B][cafe_solution_size] (the other arrays of the record are ignored). It stands for the trajectories MHPCProblem::update leaves
+ * behind (MHPCProblem.cpp:252-397): MultiPhaseDDP::solve begins with hybrid_rollout(eps = 0), U = Ubar + K (X - Xbar), around
+ * them (MultiPhaseDDP.cpp:238). Stays in force for the following solves; guess = NULL returns to the cold start. */
+int cafe_gpu_set_initial_guess(CafeHandle* h, const double* guess, int B);
 /* x0: host [B][n0] row per problem. Runs every problem of the batch to its own termination. */
 int cafe_gpu_solve_batch(CafeHandle* h, const double* x0, int B, const CafeOptions* opt);
 /* same with x0 already resident on the device, layout [n0][ldb] (component-major), ldb >= B */

@@ -584,12 +584,27 @@ extern "C" int cafe_oracle_resetmap(const CafeDeck* deck, int phase, const doubl
   } catch (const std::exception& e) { std::fprintf(stderr, "cafe_oracle_resetmap: %s\n", e.what()); return -1; }
 }
 
-extern "C" int cafe_oracle_solve(const CafeDeck* deck, const CafeOptions* opt, const double* x0, CafeInfo* info,
-                                 double* hist, int hist_cap, double* trace, int trace_cap, double* sol) {
+/* guess (optional): initial Xbar / Ubar / K in the packed solution layout (cafe_solution_size doubles; the other arrays of the record
+ * are ignored). This is the state MHPCProblem::update leaves behind for the re-solve: MultiPhaseDDP::solve starts with
+ * hybrid_rollout(eps = 0), i.e. U = Ubar + K (X - Xbar) around whatever the trajectories hold (MultiPhaseDDP.cpp:238). */
+static void apply_guess(Solver& S, const double* guess) {
+  const double* r = guess;
+  auto getv = [&](std::vector<Vec>& V, int cnt, bool use) { for (int k = 0; k < cnt; ++k) for (double& v : V[k]) { if (use) v = *r; ++r; } };
+  auto getm = [&](std::vector<Mat>& M, int cnt, bool use) { for (int k = 0; k < cnt; ++k) for (double& v : M[k].a) { if (use) v = *r; ++r; } };
+  for (auto& P : S.phases) {
+    getv(P->Xbar, P->h + 1, true); getv(P->Ubar, P->h, true); getv(P->Y, P->h, false); getv(P->dU, P->h, false); getm(P->K, P->h, true);
+    getv(P->Qu, P->h, false); getm(P->Quu, P->h, false); getm(P->Qux, P->h, false); getv(P->G, P->h + 1, false);
+    P->X = P->Xbar; P->U = P->Ubar;
+  }
+}
+
+extern "C" int cafe_oracle_solve_warm(const CafeDeck* deck, const CafeOptions* opt, const double* x0, const double* guess, CafeInfo* info,
+                                      double* hist, int hist_cap, double* trace, int trace_cap, double* sol) {
   try {
     g_last.reset(new Solver());
     Solver& S = *g_last;
     S.setup(deck);
+    if (guess) apply_guess(S, guess);
     S.x0.assign(x0, x0 + S.phases[0]->n);
     S.solve(*opt);
     if (info) {
@@ -614,4 +629,9 @@ extern "C" int cafe_oracle_solve(const CafeDeck* deck, const CafeOptions* opt, c
     std::fprintf(stderr, "cafe_oracle_solve: %s\n", e.what());
     return -1;
   }
+}
+
+extern "C" int cafe_oracle_solve(const CafeDeck* deck, const CafeOptions* opt, const double* x0, CafeInfo* info,
+                                 double* hist, int hist_cap, double* trace, int trace_cap, double* sol) {
+  return cafe_oracle_solve_warm(deck, opt, x0, nullptr, info, hist, hist_cap, trace, trace_cap, sol);
 }

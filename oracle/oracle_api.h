@@ -29,6 +29,11 @@ int cafe_oracle_ldlt(const double* A, int n, double* inv, double* min_pivot);
 int cafe_oracle_solve(const CafeDeck* deck, const CafeOptions* opt, const double* x0,
                       CafeInfo* info, double* hist, int hist_cap,
                       double* trace, int trace_cap, double* sol);
+/* Same, started from an initial guess: Xbar / Ubar / K taken from `guess` (packed solution layout, other arrays ignored; NULL =
+ * the cold start above). Restates the re-solve after MHPCProblem::update: the solver begins with hybrid_rollout(eps = 0) around
+ * whatever the trajectories hold (MultiPhaseDDP.cpp:238). */
+int cafe_oracle_solve_warm(const CafeDeck* deck, const CafeOptions* opt, const double* x0, const double* guess,
+                           CafeInfo* info, double* hist, int hist_cap, double* trace, int trace_cap, double* sol);
 
 /* Internal per-knot array of the most recent cafe_oracle_solve (names: X Xbar U Ubar Y Defect dX dU G Qu A B C D K
  * Quu Qux H lx lu ly lxx luu lyy l Phix Phixx Px). Returns the number of doubles written or -1. */

@@ -34,17 +34,21 @@ def oracle():
     return _lib
 
 
-def oracle_solve(deck, opt, x0, cap=256):
-    """Returns (info dict, hist [n_hist,4], trace [iter,12], packed solution)."""
+def oracle_solve(deck, opt, x0, cap=256, guess=None):
+    """Returns (info dict, hist [n_hist,4], trace [iter,12], packed solution). guess: packed solution whose Xbar/Ubar/K start the solve."""
     lib = oracle()
     x0 = np.ascontiguousarray(x0, dtype=np.float64)
     info = Info()
     hist = np.zeros((cap, 4))
     trace = np.zeros((cap, CAFE_TRACE_W))
     sol = np.zeros(lib.cafe_oracle_solution_size(deck))
-    rc = lib.cafe_oracle_solve(deck, C.byref(opt), x0.ctypes.data_as(C.c_void_p), C.byref(info),
-                               hist.ctypes.data_as(C.c_void_p), cap, trace.ctypes.data_as(C.c_void_p), cap,
-                               sol.ctypes.data_as(C.c_void_p))
+    g = None
+    if guess is not None:
+        g = np.ascontiguousarray(guess, dtype=np.float64)
+        assert g.size == sol.size
+    rc = lib.cafe_oracle_solve_warm(deck, C.byref(opt), x0.ctypes.data_as(C.c_void_p), g.ctypes.data_as(C.c_void_p) if g is not None else None,
+                                    C.byref(info), hist.ctypes.data_as(C.c_void_p), cap, trace.ctypes.data_as(C.c_void_p), cap,
+                                    sol.ctypes.data_as(C.c_void_p))
     if rc != 0:
         raise RuntimeError("oracle solve failed")
     d = info.as_dict()

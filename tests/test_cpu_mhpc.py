@@ -278,3 +278,35 @@ def test_per_problem_reference_set_keeps_the_schedule(cm, mhpc_impact, mhpc_opti
     dk, keep = deck_with_references(mhpc_impact.deck, refs[2])
     i2, _, _, s2 = oracle_solve(dk, mhpc_options, x0)
     assert i0["status"] == 0 and i2["status"] == 0 and abs(i0["cost"] - i2["cost"]) > 1e-6 and not np.allclose(s0, s2)
+
+
+def test_receding_horizon_shift_and_oracle_warm_start(cm, mhpc_options):
+    """cafe_mpc_b200/mpc.py: shifting a solution by two knots keeps the overlapping knots, pads the tail like push_back_state, drops an
+    exhausted first phase, and the oracle started from that guess under the run-time caps ends far closer to feasible than a cold start."""
+    import copy
+    from cafe_mpc_b200 import mpc, workload
+    ort = copy.copy(mhpc_options)
+    ort.max_AL_iter = mhpc_options.max_AL_iter_runtime; ort.max_DDP_iter = mhpc_options.max_DDP_iter_runtime
+    x0 = workload.mhpc_batch(2)[1]
+    p0 = cm.MHPCProblem(CSV, k0=10)      # WB0 h=1: the next shift removes it, and a new phase opens at the tail
+    p1 = cm.MHPCProblem(CSV, k0=12)
+    assert [p.horizon for p in p0.phases()] == [1, 24, 10] and [p.horizon for p in p1.phases()] == [24, 1, 10]
+    i0, _, _, sol = oracle_solve(p0.deck, mhpc_options, x0)
+    old = cm.unpack_solution(p0.deck, sol)
+    g = mpc.shift_guess(p0, 10, p1, 12, old)
+    np.testing.assert_array_equal(g[0]["Xbar"][:24], old[1]["Xbar"][1:25])         # absolute knots 12..35 of the old second phase
+    np.testing.assert_array_equal(g[0]["Ubar"][:23], old[1]["Ubar"][1:24])
+    np.testing.assert_array_equal(g[0]["K"][:23], old[1]["K"][1:24])
+    np.testing.assert_array_equal(g[0]["Xbar"][24], old[1]["Xbar"][24])            # push_back_state(X.back())
+    assert not g[0]["Ubar"][23].any() and not g[0]["K"][23].any()
+    np.testing.assert_array_equal(g[1]["Xbar"], p1.reference_records()[25:27, :36])  # the phase the old plan did not have
+    np.testing.assert_array_equal(g[2]["Xbar"], old[2]["Xbar"])                    # SRB phase is not shifted (dt_mpc < dt_srb)
+    packed = mpc.pack_solution(p1, g)
+    back = cm.unpack_solution(p1.deck, packed)
+    for a, b_ in zip(g, back):
+        for k in ("Xbar", "Ubar", "K"):
+            np.testing.assert_array_equal(a[k], b_[k])
+    x1 = mpc.state_at(p0, old, 2)
+    iw, _, _, _ = oracle_solve(p1.deck, ort, x1, guess=packed)
+    ic, _, _, _ = oracle_solve(p1.deck, ort, x1)
+    assert iw["iter"] <= 4 and ic["iter"] <= 4 and iw["feas"] < 0.2 * ic["feas"]

@@ -240,3 +240,42 @@ def test_per_problem_references_match_oracle(cm, opt):
     s.set_references(None)
     s.solve(opt)
     assert s.get_solver_info() == shared_info
+
+
+def test_receding_horizon_warm_start_matches_oracle(cm, opt):
+    """SURVEY §8(f)1 (first slice): receding-horizon re-solves. The plan is shifted by dt_mpc / dt_wb = 2 knots per step (phase removal
+    at k0 = 12, a new one-knot phase opened at the tail), the previous solution becomes the warm-start guess (cafe_mpc_b200/mpc.py),
+    and the re-solve runs under the run-time iteration caps (max_AL_iter_runtime x max_DDP_iter_runtime). GPU == oracle at every step."""
+    from cafe_mpc_b200 import mpc, workload
+    ort = copy.copy(opt)
+    ort.max_AL_iter = opt.max_AL_iter_runtime; ort.max_DDP_iter = opt.max_DDP_iter_runtime
+    B, k0 = 4, 8
+    prob = cm.MHPCProblem(CSV, k0=k0)
+    x0 = workload.mhpc_batch(B)
+    s = solve_gpu(cm, prob, opt, x0)
+    sol = s.get_solution()
+    for step in range(3):
+        k1 = k0 + 2
+        p1 = cm.MHPCProblem(CSV, k0=k1)
+        guess = mpc.shifted_guess_batch(prob, k0, p1, k1, sol)
+        # the "measured" state of the next step: the plan's own prediction two knots ahead, nudged
+        x1 = np.stack([mpc.state_at(prob, cm.unpack_solution(prob.deck, sol[b]), 2) for b in range(B)]) + 1e-3 * (x0 - x0[0])
+        s1 = cm.MultiPhaseDDP(p1, 0, B)
+        s1.set_initial_condition(x1)
+        s1.set_initial_guess(guess)
+        s1.solve(ort)
+        info = s1.get_solver_info(); hist = s1.get_history(256); sol1 = s1.get_solution()
+        for b in range(B):
+            oi, oh, ot, osol = oracle_solve(p1.deck, ort, x1[b], guess=guess[b])
+            assert [info[b][k] for k in COUNTS] == [oi[k] for k in COUNTS], (step, b)
+            np.testing.assert_allclose(hist[b, :oi["n_hist"], 0], oh[:, 0], rtol=RTOL)
+            gp, op = cm.unpack_solution(p1.deck, sol1[b]), cm.unpack_solution(p1.deck, osol)
+            for pg, po in zip(gp, op):
+                for name in ("Xbar", "Ubar", "Y", "K", "dU", "Qu", "Quu", "Qux", "G"):
+                    assert relerr(pg[name], po[name], FLOOR.get(name, 1e-6)) < RTOL, (step, b, name)
+        # the warm start pays: same caps from the cold start end far from feasible
+        s1.set_initial_guess(None)
+        s1.solve(ort)
+        cold = s1.get_solver_info()
+        assert all(info[b]["feas"] < 0.2 * cold[b]["feas"] for b in range(B))
+        prob, k0, sol = p1, k1, sol1
