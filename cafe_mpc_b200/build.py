@@ -48,18 +48,25 @@ def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(OBJ, exist_ok=True)
     objs, logs, rebuilt = [], [], False
+    jobs = []
     for src, deps in SOURCES.items():
         obj = os.path.join(OBJ, src.replace("/", "_") + ".o")
         objs.append(obj)
         all_deps = [os.path.join(CSRC, src)] + [os.path.join(CSRC, d) for d in deps]
         if force or _stale(obj, all_deps):
-            cmd = [nvcc] + NVCC_FLAGS + EXTRA.get(src, []) + ["-c", "-o", obj, os.path.join(CSRC, src)]
-            res = subprocess.run(cmd, capture_output=True, text=True)
-            logs.append(" ".join(cmd) + "\n" + res.stdout + res.stderr)
-            if res.returncode != 0:
-                sys.stderr.write(logs[-1])
-                raise RuntimeError("nvcc failed on " + src)
-            rebuilt = True
+            jobs.append((src, [nvcc] + NVCC_FLAGS + EXTRA.get(src, []) + ["-c", "-o", obj, os.path.join(CSRC, src)]))
+    # the translation units are independent: compile them side by side (ptxas needs minutes for the generated routines)
+    procs = [(src, cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)) for src, cmd in jobs]
+    failed = None
+    for src, cmd, pr in procs:
+        out, _ = pr.communicate()
+        logs.append(" ".join(cmd) + "\n" + out)
+        if pr.returncode != 0 and failed is None:
+            failed = src
+            sys.stderr.write(logs[-1])
+        rebuilt = True
+    if failed is not None:
+        raise RuntimeError("nvcc failed on " + failed)
     if rebuilt or not os.path.exists(LIB):
         cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-Xcompiler", "-fPIC", "-o", LIB] + objs
         res = subprocess.run(cmd, capture_output=True, text=True)

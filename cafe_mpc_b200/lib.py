@@ -20,7 +20,7 @@ class CafeError(RuntimeError):
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
-            "libcafe_gpu.so is not built (%s). Run `python -m cafe_mpc_b200.build`; "
+            "libcafe_gpu.so is not built (%s). Run `python cafe_mpc_b200/build.py`; "
             "the product path has no fallback implementation." % LIB_PATH)
     lib = C.CDLL(LIB_PATH)
     vp, dp, ip = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)
