@@ -33,6 +33,11 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 // pacing barrier of the CTA cluster (no memory ordering needed: it only keeps the four problems that share every 32-byte
 // sector of the problem-fastest arrays at the same knot, so that one DRAM fetch serves all four through L2)
+// the CTAs of a cluster meet every CAFE_PACE-th knot (power of two): the L2 keeps a few knots of four problems resident, so
+// a drift of a few knots still lets one DRAM fetch serve all four, and the barrier cost drops by that factor
+#ifndef CAFE_PACE
+#define CAFE_PACE 4
+#endif
 __device__ __forceinline__ void cluster_pace() { asm volatile("barrier.cluster.arrive.relaxed.aligned;\nbarrier.cluster.wait.aligned;\n" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l1(const double* p) { asm volatile("prefetch.global.L1 [%0];\n" ::"l"(p)); }
 
@@ -85,15 +90,109 @@ __device__ __forceinline__ void gemm_nt(const double* __restrict__ A, int lda, c
     }
 }
 
+// ---- fp64 tensor-core path (DMMA, mma.sync.m8n8k4.f64) -----------------------------------------------------------------
+// The register-tiled gemm_nt above is bound by shared-memory operand traffic: every k step issues 8 LDS.64 (two wavefronts
+// each, mostly broadcast) for 15 DFMAs, ncu shows the LSU data pipe at 45 % and the fp64 pipe at 10 %. One DMMA multiplies an
+// 8x4 by a 4x8 fragment (256 FMAs) from ONE operand double per lane and matrix: 4 wavefronts per 256 FMAs instead of 16 per
+// 480, an eighth of the issue slots, and every lane fetches a distinct element (no bandwidth lost to broadcasts).
+// Fragment layout (PTX ISA, m8n8k4 .f64): g = lane/4, tg = lane%4:  a = A(g, tg),  b = B(tg, g),  c0,c1 = C(g, 2 tg + {0,1}).
+// With every leading dimension = 4 (mod 8) doubles the 16 lanes of a half warp (4 values of g x 4 of tg) hit 32 distinct
+// banks for both operand orientations (element + ld * k and k + ld * element).
+#ifndef CAFE_BWD_MMA
+#define CAFE_BWD_MMA 1
+#endif
+__host__ __device__ constexpr int ld_mma(int n) { return CAFE_BWD_MMA ? ((n % 8) <= 4 ? n - n % 8 + 4 : n - n % 8 + 12) : (n | 1); }
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  // volatile: the instruction is warp-collective; it must never be duplicated into lane-predicated copies
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// tile lists: which 8x8 output tiles a product needs, in column-major order
+struct NoPre { __device__ __forceinline__ double operator()(int, int) const { return 0.0; } };
+template <int MM, int NN>
+struct TilesFull {
+  static constexpr int MT = (MM + 7) / 8, COUNT = MT * ((NN + 7) / 8);
+  static __device__ __forceinline__ void map(int q, int& m0, int& n0) { m0 = (q % MT) * 8; n0 = (q / MT) * 8; }
+};
+// the (N+M) x (N+M) product [A B]^T T without its upper right block (rows < N, columns >= N): Qxx, Qux, Quu but not Qxu
+template <int N, int M>
+struct TilesQ {
+  static constexpr int MT = (N + M + 7) / 8, NFULL = (N + 7) / 8, MS = N / 8, NREST = (N + M + 7) / 8 - NFULL;
+  static constexpr int COUNT = NFULL * MT + NREST * (MT - MS);
+  static __device__ __forceinline__ void map(int q, int& m0, int& n0) {
+    if (q < NFULL * MT) { m0 = (q % MT) * 8; n0 = (q / MT) * 8; }
+    else { const int r = q - NFULL * MT; m0 = (MS + r % (MT - MS)) * 8; n0 = (NFULL + r / (MT - MS)) * 8; }
+  }
+};
+
+// C(i,j) = epi(i,j, sum_{l<KK} opA(i,l) B(l,j) + sum_{l<KK2} A2[l + lda2*i] B2[l + ldb2*j])   for i < MM, j < NN, tiles of TL
+//   opA(i,l) = TA ? A[l + lda*i] : A[i + lda*l];  B(l,j) = B[l + ldb*j].  The NT/32 warps take the tiles round robin, four at a
+//   time (independent accumulators). Rows / columns past MM / NN are read from whatever follows in shared memory and only
+//   reach outputs that are dropped. pre(i,j) is added to the product (a global-memory addend, fetched before the k loop so that
+//   its latency hides behind the DMMAs). k runs to the next multiple of 4 WITHOUT a mask (a per-lane select around a collective
+//   instruction invites lane-predicated code): the caller guarantees that the k padding of one operand is zero and that of the
+//   other finite (Bwd2Layout: zero pad rows of [A B], zero pad columns behind H; shared memory is cleared at kernel start).
+template <int MM, int NN, int KK, bool TA, int KK2, int NT, class TL, class Pre, class Epi>
+__device__ __forceinline__ void gemm_mma(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
+                                         const double* __restrict__ A2, int lda2, const double* __restrict__ B2, int ldb2, int t, bool run, Pre pre, Epi epi) {
+  constexpr int NW = NT / 32, G = (NT > 128) ? 2 : 4, KS = (KK + 3) / 4, KS2 = (KK2 + 3) / 4;
+  if (!run) return;
+  __syncwarp();
+  const int w = t >> 5, lane = t & 31, g = lane >> 2, tg = lane & 3;
+  for (int q0 = w; q0 < TL::COUNT; q0 += NW * G) {
+    double c[G][2];
+    int m0[G], n0[G];
+    const double* ap[G]; const double* bp[G]; const double* ap2[G]; const double* bp2[G];
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+      const int q = q0 + u * NW;
+      TL::map(q < TL::COUNT ? q : q0, m0[u], n0[u]);   // a pass that runs out of tiles repeats its first one (result dropped)
+      ap[u] = TA ? A + tg + lda * (m0[u] + g) : A + (m0[u] + g) + lda * tg;
+      bp[u] = B + tg + ldb * (n0[u] + g);
+      if constexpr (KK2 > 0) { ap2[u] = A2 + tg + lda2 * (m0[u] + g); bp2[u] = B2 + tg + ldb2 * (n0[u] + g); }
+      c[u][0] = 0; c[u][1] = 0;
+    }
+    // addends of the epilogue that come from global memory: requested now, consumed after the k loop
+    double pv[G][2];
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+      const int i = m0[u] + g, j = n0[u] + 2 * tg;
+      pv[u][0] = (i < MM && j < NN) ? pre(i, j) : 0.0;
+      pv[u][1] = (i < MM && j + 1 < NN) ? pre(i, j + 1) : 0.0;
+    }
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+      for (int u = 0; u < G; ++u) dmma884(c[u][0], c[u][1], TA ? ap[u][ks * 4] : ap[u][ks * 4 * lda], bp[u][ks * 4]);
+    }
+    if constexpr (KK2 > 0) {
+#pragma unroll
+      for (int ks = 0; ks < KS2; ++ks) {
+#pragma unroll
+        for (int u = 0; u < G; ++u) dmma884(c[u][0], c[u][1], ap2[u][ks * 4], bp2[u][ks * 4]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+      if (q0 + u * NW < TL::COUNT) {
+        const int i = m0[u] + g, j = n0[u] + 2 * tg;
+        if (i < MM && j < NN) epi(i, j, c[u][0] + pv[u][0]);
+        if (i < MM && j + 1 < NN) epi(i, j + 1, c[u][1] + pv[u][1]);
+      }
+    }
+  }
+}
+
 // shared-memory plan (doubles) of one problem whose largest phase is (NX, MX, PX); WBS: structured whole-body storage
 template <int NX, int MX, int PX, bool WBS>
 struct Bwd2Layout {
-  static constexpr int ldH = NX | 1, KA = WBS ? 18 : NX, ldA = KA | 1, ldM = MX | 1, ldP = (PX > 0 ? PX : 1) | 1;
+  static constexpr int ldH = ld_mma(NX), KA = WBS ? 18 : NX, ldA = ld_mma(KA), ldM = ld_mma(MX), ldP = ld_mma(PX > 0 ? PX : 1);
   // vectors
   static constexpr int vG = 0, vGn = NX, vQx = 2 * NX, vD = 3 * NX, vDx = 4 * NX, vDxn = 5 * NX, vQu = 6 * NX, vDu = 6 * NX + MX,
-                       vDuL = 6 * NX + 2 * MX, vLy = 6 * NX + 3 * MX, vRed = vLy + PX + 1, nVec = vRed + 2 * 128 + 1;
+                       vDuL = 6 * NX + 2 * MX, vLy = 6 * NX + 3 * MX, vRed = vLy + PX + 1, nVec = vRed + 2 * 256 + 1;   // vRed: pivots / flags, then two NT-wide reduction rows (NT <= 256)
   static constexpr int oH = nVec;                       // H / Qxx / H_new      NX x NX (ldH)
-  static constexpr int oAB = oH + ldH * NX;             // [A B] rows KA (ldA) x (NX+MX)
+  static constexpr int oAB = oH + ldH * (NX + 2);       // [A B] rows KA (ldA) x (NX+MX); two zero pad columns behind H (k padding of P = H(:,18:36))
   static constexpr int szAB = ldA * (NX + MX);
   static constexpr int oT = oAB + szAB;                 // T = H [A B]  NX x (NX+MX) (ldH); reused for L (MX x MX, ldM)
   static constexpr int oQux = oT + ldH * (NX + MX);     // Qux MX x NX (ldM)
@@ -110,7 +209,7 @@ struct Bwd2Layout {
                        lLu = lLx + NX, lD = lLu + MX, lDU = lD + NX, szLin = (lDU + MX + 1) | 1;
   static constexpr int oLin = nVec;
   static constexpr int endLin = oLin + 2 * szLin;
-  static constexpr int total = endSweep > endLin ? endSweep : endLin;
+  static constexpr int total = (endSweep > endLin ? endSweep : endLin) + 64;   // slack: fragment loads of partial edge tiles run past the last tile
 };
 
 // One phase of the sweep. N, M, PY: phase dimensions; NNEXT: state dimension of the next phase (for the jump); WB: use the
@@ -174,14 +273,33 @@ __device__ void sweep_phase2(const SolverDev& S, int pi, int b, int t, bool run,
     }
     cp_async_commit();
   };
+  if constexpr (CAFE_BWD_MMA && ldA > KA) {
+    // k padding of [A B] (rows KA..ldA-1, never staged): zero again, the jump above used the area for Px
+    constexpr int PAD = ldA - KA;
+    if (run && ok) for (int e = t; e < PAD * (N + M); e += NT) sAB[KA + (e % PAD) + ldA * (e / PAD)] = 0.0;
+  }
   if (run && ok && h > 0) stage(h - 1, t, NT);
   for (int k = h - 1; k >= 0; --k) {
     const bool a2 = run && ok;
     cp_async_wait_all();
     __syncthreads();
-    cluster_pace();
+    if ((k & (CAFE_PACE - 1)) == 0) cluster_pace();
     // ---- Gn = G + H d ; T = H [A B] ; S[C D] = lyy [C D]
-    if (a2) for (int i = t; i < N; i += NT) { double s = sG[i]; for (int j = 0; j < N; ++j) s += sH[i + ldH * j] * sD[j]; sGn[i] = s; }
+    if (a2) for (int i = NT - 1 - t; i < N; i += NT) { double s = sG[i]; for (int j = 0; j < N; ++j) s += sH[i + ldH * j] * sD[j]; sGn[i] = s; }   // last warps: fewest tiles
+#if CAFE_BWD_MMA
+    if constexpr (WB) {
+      // T = P [A2 B2] + [H(:,0:18), dt H(:,0:18), 0],  P = H(:,18:36)
+      gemm_mma<N, N + M, 18, false, 0, NT, TilesFull<N, N + M>>(sH + ldH * 18, ldH, sAB, ldA, nullptr, 0, nullptr, 0, t, a2, NoPre(), [&](int i, int j, double v) {
+        if (j < 18) v += sH[i + ldH * j];
+        else if (j < 36) v += dt * sH[i + ldH * (j - 18)];
+        sT[i + ldH * j] = v;
+      });
+    } else {
+      gemm_mma<N, N + M, N, false, 0, NT, TilesFull<N, N + M>>(sH, ldH, sAB, ldA, nullptr, 0, nullptr, 0, t, a2, NoPre(), [&](int i, int j, double v) { sT[i + ldH * j] = v; });
+    }
+    if constexpr (PY > 0)
+      gemm_mma<PY, N + M, PY, false, 0, NT, TilesFull<PY, N + M>>(sLyy, ldP, sCD, ldP, nullptr, 0, nullptr, 0, t, a2, NoPre(), [&](int i, int j, double v) { sSCD[i + ldP * j] = v; });
+#else
     if constexpr (WB) {
       // T = P [A2 B2] + [H(:,0:18), dt H(:,0:18), 0],  P = H(:,18:36)
       gemm_nt<N, N + M, 18, false, 0, NT>(sH + ldH * 18, ldH, sAB, ldA, nullptr, 0, nullptr, 0, t, a2, [&](int i, int j, double v) {
@@ -194,14 +312,17 @@ __device__ void sweep_phase2(const SolverDev& S, int pi, int b, int t, bool run,
     }
     if constexpr (PY > 0)
       gemm_nt<PY, N + M, PY, false, 0, NT>(sLyy, ldP, sCD, ldP, nullptr, 0, nullptr, 0, t, a2, [&](int i, int j, double v) { sSCD[i + ldP * j] = v; });
+#endif
     __syncthreads();
     // ---- Q functions (H is dead from here on: Qxx is written over it)
     if (a2) {
+#if !CAFE_BWD_MMA
       // the epilogues below add lxx / luu from global memory: start pulling them into L1 now
       const double* lxxp = ph.lxx + gix(k, N * N, 0, ldb, b);
       for (int e = t; e < N * N; e += NT) prefetch_l1(lxxp + (size_t)e * ldb);
       const double* luup = ph.luu + gix(k, M * M, 0, ldb, b);
       for (int e = t; e < M * M; e += NT) prefetch_l1(luup + (size_t)e * ldb);
+#endif
       for (int j = t; j < N + M; j += NT) {
         double s = (j < N) ? ph.lx[gix(k, N, j, ldb, b)] : ph.lu[gix(k, M, j - N, ldb, b)];
         for (int i = 0; i < KA; ++i) s += sAB[i + ldA * j] * sGn[R0 + i];
@@ -210,6 +331,33 @@ __device__ void sweep_phase2(const SolverDev& S, int pi, int b, int t, bool run,
         if (j < N) sQx[j] = s; else sQu[j - N] = s;
       }
     }
+#if CAFE_BWD_MMA
+    {
+      // [Qxx Qxu; Qux Quu] = [A B]^T T_rows (+ [C D]^T lyy [C D]) is ONE (N+M)^2 product; its upper right block is not needed
+      const double* lxxg = ph.lxx + gix(k, N * N, 0, ldb, b);
+      const double* luug = ph.luu + gix(k, M * M, 0, ldb, b);
+      gemm_mma<N + M, N + M, KA, true, PY, NT, TilesQ<N, M>>(sAB, ldA, sT + R0, ldH, sCD, ldP, sSCD, ldP, t, a2,
+        [&](int i, int j) -> double {   // lxx / luu: 8-byte loads of a problem-fastest array, issued before the k loop
+          if (j < N) return (i < N) ? lxxg[(size_t)(i + N * j) * ldb] : 0.0;
+          return (i >= N) ? luug[(size_t)((i - N) + M * (j - N)) * ldb] : 0.0;
+        },
+        [&](int i, int j, double v) {
+        if (j < N) {
+          if (i < N) {   // Qxx = lxx + A^T T_A (+ C^T S_C) + reg I   (H is dead: written over it)
+            if constexpr (WB) { if (i < 18) v += sT[i + ldH * j]; else v += dt * sT[(i - 18) + ldH * j]; }
+            if (i == j) v += reg;
+            sH[i + ldH * j] = v;
+          } else {       // Qux = B^T T_A (+ D^T S_C)
+            sQux[(i - N) + ldM * j] = v;
+          }
+        } else if (i >= N) {   // Quu = luu + B^T T_B (+ D^T S_D) + reg I
+          const int iu = i - N, ju = j - N;
+          if (iu == ju) v += reg;
+          sQuu[iu + ldM * ju] = v;
+        }
+      });
+    }
+#else
     {
       const double* lxxg = ph.lxx + gix(k, N * N, 0, ldb, b);
       const double* luug = ph.luu + gix(k, M * M, 0, ldb, b);
@@ -230,6 +378,7 @@ __device__ void sweep_phase2(const SolverDev& S, int pi, int b, int t, bool run,
         sQuu[i + ldM * j] = v;
       });
     }
+#endif
     __syncthreads();
     // ---- factorisation and solves, fused. Thread c < M+N+1 of the first NE threads keeps column c of
     //      [Quu - 1e-9 I | Qux | Qu] in registers; at step j the owner of column j publishes the pivot and the multipliers
@@ -308,10 +457,21 @@ __device__ void sweep_phase2(const SolverDev& S, int pi, int b, int t, bool run,
       double* Kg = ph.K + gix(k, M * N, 0, ldb, b);
       for (int e = t; e < M * N; e += NT) Kg[(size_t)e * ldb] = sK[(e % M) + ldM * (e / M)];
       // symmetrise Qxx in place: disjoint (i<j) pairs
-      for (int e = t; e < N * N; e += NT) { const int i = e % N, j = e / N; if (i < j) { const double s = (sH[i + ldH * j] + sH[j + ldH * i]) / 2; sH[i + ldH * j] = s; sH[j + ldH * i] = s; } }
+      {
+        int i = t % N, j = t / N;   // element (i, j), advanced by NT per step without divisions
+        for (int e = t; e < N * N; e += NT) {
+          if (i < j) { const double s = (sH[i + ldH * j] + sH[j + ldH * i]) / 2; sH[i + ldH * j] = s; sH[j + ldH * i] = s; }
+          i += NT % N; j += NT / N;
+          if (i >= N) { i -= N; ++j; }
+        }
+      }
     }
     __syncthreads();
+#if CAFE_BWD_MMA
+    gemm_mma<N, N, M, true, 0, NT, TilesFull<N, N>>(sQux, ldM, sK, ldM, nullptr, 0, nullptr, 0, t, a3, NoPre(), [&](int i, int j, double v) { sH[i + ldH * j] += v; });
+#else
     gemm_nt<N, N, M, true, 0, NT>(sQux, ldM, sK, ldM, nullptr, 0, nullptr, 0, t, a3, [&](int i, int j, double v) { sH[i + ldH * j] += v; });
+#endif
     __syncthreads();
   }
   // ---- G[0] += H[0] Defect[0]
@@ -366,7 +526,7 @@ __device__ void lin_phase2(const SolverDev& S, int pi, int b, int t, bool run, d
     double* dxn = dxb[(k + 1) & 1];
     cp_async_wait_all();
     __syncthreads();
-    cluster_pace();
+    if ((k & (CAFE_PACE - 1)) == 0) cluster_pace();
     if (run) {
       if (k + 1 < h) stage(k + 1);
       // du = dU + K dx (threads 0..M-1);  dV terms of the state (threads of the upper warps)
@@ -471,6 +631,8 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NT, 4) k_bwd2(const 
       if (it < CAFE_HIST_CAP) { double* tr = c.trace + ((size_t)it * 12) * ldb + b; for (int i = 0; i < 12; ++i) tr[(size_t)i * ldb] = 0; tr[0] = cost; tr[(size_t)ldb] = sqrt(fs); }
     }
   }
+  // every word of the tiles is finite from here on (the fragment loads of partial edge tiles read neighbouring tiles)
+  for (int e = t; e < L::total; e += NT) sm[e] = 0.0;
   double min_piv = 1e300;
   for (int round = 0;; ++round) {
     cl.sync();
@@ -525,13 +687,13 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NT, 4) k_bwd2(const 
     }
     // dV_1, dV_2: fixed-order tree over the NT per-thread shares
     sRed[t] = part1;
-    sRed[128 + t] = part2;
+    sRed[NT + t] = part2;
     __syncthreads();
     for (int w = NT / 2; w > 0; w >>= 1) {
-      if (t < w) { sRed[t] += sRed[t + w]; sRed[128 + t] += sRed[128 + t + w]; }
+      if (t < w) { sRed[t] += sRed[t + w]; sRed[NT + t] += sRed[NT + t + w]; }
       __syncthreads();
     }
-    dV1 = sRed[0]; dV2 = sRed[128];
+    dV1 = sRed[0]; dV2 = sRed[NT];
   }
   if (t == 0 && mine) {
     double r = s_reg / 20;

@@ -6,6 +6,7 @@
 //          -> k_select (Armijo over step sizes, exits, AL update) -> k_accept
 // Per-problem control state lives on the device; the host only polls one counter per tick.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -51,6 +52,7 @@ struct CafeHandle {
   int ticks = 0;
   int bwd_variant = 0;  // 0: HKD deck (24,24,0)   1: MHPC deck (36,24->12,12)
   size_t bwd_smem = 0;
+  int bwd_nt = 128;     // threads per problem of the MHPC sweep (dev switch CAFE_BWD_NT)
   int bwd_pb = 4;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evs = nullptr, eve = nullptr;
   double total_ms = 0;
@@ -256,8 +258,10 @@ int launch_lq_wb_dense(CafeHandle* H) {
 }
 
 int launch_bwd(CafeHandle* H) {
-  if (H->bwd_variant == 0) k_bwd2<0, 128><<<(H->B + 3) / 4 * 4, 128, H->bwd_smem, H->stream>>>(H->S);
-  else k_bwd2<1, 128><<<(H->B + 3) / 4 * 4, 128, H->bwd_smem, H->stream>>>(H->S);
+  const unsigned grid = (H->B + 3) / 4 * 4;
+  if (H->bwd_variant == 0) k_bwd2<0, 128><<<grid, 128, H->bwd_smem, H->stream>>>(H->S);
+  else if (H->bwd_nt == 256) k_bwd2<1, 256><<<grid, 256, H->bwd_smem, H->stream>>>(H->S);
+  else k_bwd2<1, 128><<<grid, 128, H->bwd_smem, H->stream>>>(H->S);
   return 0;
 }
 
@@ -341,6 +345,8 @@ extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, 
     H->bwd_variant = 1; H->bwd_pb = 1;
     H->bwd_smem = (size_t)cafe_dev::Bwd2Layout<36, 12, 12, true>::total * sizeof(double);
     CUDA_OK(cudaFuncSetAttribute(cafe_dev::k_bwd2<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H->bwd_smem));
+    CUDA_OK(cudaFuncSetAttribute(cafe_dev::k_bwd2<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H->bwd_smem));
+    if (const char* e = std::getenv("CAFE_BWD_NT")) H->bwd_nt = std::atoi(e) == 256 ? 256 : 128;
   }
   if (!all_hkd) {
     const int smem = (int)(CAFE_KKT_SM * 4 * sizeof(double));
