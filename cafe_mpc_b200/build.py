@@ -32,7 +32,9 @@ NVCC_FLAGS = [
 
 # per-source extra flags: the generated whole-body routines are capped at 128 registers so that the per-(problem,knot)
 # kernels calling them reach 4 CTAs of 128 threads per SM (their local-memory traffic needs the latency hiding)
-EXTRA = {"wb_gen_wrappers.cu": ["-maxrregcount=128"], "knot_kernels.cu": ["-maxrregcount=128"]}
+_RC = os.environ.get("CAFE_KNOT_MAXRREG", "128")   # dev switch for occupancy experiments
+_MINB = str(max(1, 65536 // (128 * int(_RC))))
+EXTRA = {"wb_gen_wrappers.cu": ["-maxrregcount=" + _RC], "knot_kernels.cu": ["-maxrregcount=" + _RC, "-DCAFE_KNOT_MINB=" + _MINB]}
 
 
 def _mtime(p):

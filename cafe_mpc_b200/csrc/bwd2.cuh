@@ -602,15 +602,17 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NT, 4) k_bwd2(const 
   extern __shared__ double sm[];
   __shared__ double s_reg;
   __shared__ int s_state, s_regiter;  // 0 sweeping, 1 success, 2 gave up
-  const int t = threadIdx.x, b = blockIdx.x;
+  // CTA i sweeps the i-th problem that is still iterating (c.act_list, ascending); the tail CTAs of the last cluster idle
   const CtrlDev& c = S.c;
+  const bool listed = (int)blockIdx.x < S.n_act;
+  const int t = threadIdx.x, b = listed ? c.act_list[blockIdx.x] : 0;
   const CafeOptions& o = S.opt;
   const int ldb = S.ldb;
   // The four CTAs of a cluster own four consecutive problems and advance knot by knot together (cluster_pace); a CTA whose
   // problem is inactive, or whose sweep is already done while a neighbour repeats it with more regularisation, keeps pace only.
   namespace cg = cooperative_groups;
   cg::cluster_group cl = cg::this_cluster();
-  const bool mine = b < S.B && c.active[b];
+  const bool mine = listed && c.active[b];
   int it = 0;
   if (t == 0) {
     s_state = mine ? 0 : 3; s_regiter = 0; s_reg = mine ? c.reg[b] : 0.0;

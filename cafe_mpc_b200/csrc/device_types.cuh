@@ -70,10 +70,15 @@ struct CtrlDev {
   double *feas0_t;  // [NA][ldb] |Defect_0[0]|^2 of the first phase per trial
   double *min_pivot;  // [ldb] smallest LDL^T pivot seen (tie monitoring)
   int* n_active;  // single counter
+  // index lists (ascending problem index), rebuilt by k_compact: problems still iterating / problems whose line search needs
+  // more step sizes. The per-(problem, knot) kernels and the sweep run over these lists, so that warps and CTAs stay full when
+  // most of the batch has already converged.
+  int *act_list, *pend_list;
 };
 
 struct SolverDev {
   int n_phases, B, ldb, NA, n_knots;
+  int n_act;  // length of c.act_list (host copy only: set before k_bwd2 is launched with the descriptor by value)
   double eps[CAFE_MAX_ALPHAS];
   CafeOptions opt;
   PhaseDev ph[CAFE_MAX_PHASES];

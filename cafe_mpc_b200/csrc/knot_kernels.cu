@@ -6,10 +6,17 @@
 
 namespace cafe_dev {
 
-void launch_roll(const SolverDev* dS, long long nthreads, cudaStream_t st, int a0, int a1) {
-  k_roll<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(dS, a0, a1);
+void launch_roll(const SolverDev* dS, int n_knots, cudaStream_t st, int a0, int a1, const int* list, int n_list) {
+  if (n_list <= 0) return;
+  const long long nthreads = (long long)((n_list + 31) & ~31) * n_knots * (a1 - a0);
+  k_roll<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(dS, a0, a1, list, n_list);
 }
-void launch_lq(const SolverDev* dS, long long nthreads, cudaStream_t st) { k_lq<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(dS); }
+void launch_lq(const SolverDev* dS, int n_knots, cudaStream_t st, const int* list, int n_list) {
+  if (n_list <= 0) return;
+  const long long nthreads = (long long)((n_list + 31) & ~31) * n_knots;
+  k_lq<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(dS, list, n_list);
+}
+void launch_compact(const SolverDev* dS, cudaStream_t st, int mode) { k_compact<<<1, 1024, 0, st>>>(dS, mode); }
 void launch_accept(const SolverDev* dS, long long nthreads, cudaStream_t st) { k_accept<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(dS); }
 void launch_ls_scan(const SolverDev* dS, int B, cudaStream_t st, int a0, int a1) { k_ls_scan<<<(B + 127) / 128, 128, 0, st>>>(dS, a0, a1); }
 void launch_select(const SolverDev* dS, int B, cudaStream_t st, int mode) { k_select<<<(B + 127) / 128, 128, 0, st>>>(dS, mode); }

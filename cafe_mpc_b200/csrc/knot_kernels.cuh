@@ -25,6 +25,10 @@
 #include "model_srb.cuh"
 #include "model_wb.cuh"
 
+// resident CTAs per SM the per-(problem,knot) kernels are compiled for (register cap = 65536 / (128 * CAFE_KNOT_MINB))
+#ifndef CAFE_KNOT_MINB
+#define CAFE_KNOT_MINB 4
+#endif
 namespace cafe_dev {
 
 // ------------------------------------------------------------------------------------------- K-ROLL
@@ -123,13 +127,16 @@ __device__ void roll_knot(const SolverDev& S, int pi, int k, int a, int b) {
 }
 
 // step sizes [a0, a1) of the ladder; problems whose line search already succeeded are skipped
-__global__ void __launch_bounds__(128, 4) k_roll(const SolverDev* __restrict__ Sp, int a0, int a1) {
+// thread = (entry j of the index list, knot, step size), j fastest: a warp is 32 listed problems of one knot
+__global__ void __launch_bounds__(128, CAFE_KNOT_MINB) k_roll(const SolverDev* __restrict__ Sp, int a0, int a1, const int* __restrict__ list, int n_list) {
   const SolverDev& S = *Sp;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = (int)(t % S.ldb);
-  const long long r = t / S.ldb;
+  const int ldj = (n_list + 31) & ~31;
+  const int j = (int)(t % ldj);
+  const long long r = t / ldj;
   const int gk = (int)(r % S.n_knots), a = a0 + (int)(r / S.n_knots);
-  if (a >= a1 || b >= S.B) return;
+  if (a >= a1 || j >= n_list) return;
+  const int b = list[j];
   if (!S.c.active[b] || !S.c.do_ls[b] || S.c.ls_found[b]) return;
   const int pi = S.knot_phase[gk], k = S.knot_k[gk];
   switch (S.ph[pi].model) {
@@ -178,12 +185,14 @@ __device__ void lq_knot_generic(const SolverDev& S, int pi, int k, int b) {
   }
 }
 
-__global__ void __launch_bounds__(128, 4) k_lq(const SolverDev* __restrict__ Sp) {
+__global__ void __launch_bounds__(128, CAFE_KNOT_MINB) k_lq(const SolverDev* __restrict__ Sp, const int* __restrict__ list, int n_list) {
   const SolverDev& S = *Sp;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = (int)(t % S.ldb);
-  const int gk = (int)(t / S.ldb);
-  if (gk >= S.n_knots || b >= S.B) return;
+  const int ldj = (n_list + 31) & ~31;
+  const int j = (int)(t % ldj);
+  const int gk = (int)(t / ldj);
+  if (gk >= S.n_knots || j >= n_list) return;
+  const int b = list[j];
   if (!S.c.active[b]) return;
   const int pi = S.knot_phase[gk], k = S.knot_k[gk];
   switch (S.ph[pi].model) {
@@ -284,6 +293,34 @@ __global__ void k_ls_scan(const SolverDev* __restrict__ Sp, int a0, int a1) {
     if ((merit <= merit_prev + o.gamma * exp_merit_change) && !fail) { c.ls_found[b] = 1; return; }
   }
   if (a1 < S.NA) atomicAdd(c.n_pending, 1);
+}
+
+// Ordered compaction of a per-problem predicate into an index list (one CTA of 1024 threads; B <= a few 10^4).
+// mode 0: problems still iterating -> c.act_list, c.n_active;  mode 1: line searches that need more step sizes -> c.pend_list, c.n_pending
+__global__ void __launch_bounds__(1024) k_compact(const SolverDev* __restrict__ Sp, int mode) {
+  const SolverDev& S = *Sp;
+  const CtrlDev& c = S.c;
+  __shared__ int warp_tot[32];
+  __shared__ int base;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  int* list = mode == 0 ? c.act_list : c.pend_list;
+  if (t == 0) base = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < S.B; b0 += 1024) {
+    const int b = b0 + t;
+    bool p = false;
+    if (b < S.B) p = (mode == 0) ? (c.active[b] != 0) : (c.active[b] && c.do_ls[b] && !c.ls_found[b]);
+    const unsigned m = __ballot_sync(0xffffffffu, p);
+    if (lane == 0) warp_tot[w] = __popc(m);
+    __syncthreads();
+    int off = base;
+    for (int i = 0; i < w; ++i) off += warp_tot[i];
+    if (p) list[off + __popc(m & ((1u << lane) - 1u))] = b;
+    __syncthreads();
+    if (t == 0) { int sum = 0; for (int i = 0; i < 32; ++i) sum += warp_tot[i]; base += sum; }
+    __syncthreads();
+  }
+  if (t == 0) *(mode == 0 ? c.n_active : c.n_pending) = base;
 }
 
 // mode 0: initial rollout bookkeeping (MultiPhaseDDP.cpp:238-261); mode 1: after a DDP iteration

@@ -168,6 +168,7 @@ void carve(CafeHandle* H, Carver& cv, size_t& zero_bytes) {
   c.iter_ou = cv.take<int>(ldb); c.iter_in = cv.take<int>(ldb); c.iter = cv.take<int>(ldb); c.ls_total = cv.take<int>(ldb);
   c.reg_total = cv.take<int>(ldb); c.n_hist = cv.take<int>(ldb); c.status = cv.take<int>(ldb);
   c.n_active = cv.take<int>(64);
+  c.act_list = cv.take<int>(ldb); c.pend_list = cv.take<int>(ldb);
   c.reg = cv.take<double>(ldb); c.cost = cv.take<double>(ldb); c.merit = cv.take<double>(ldb); c.feas = cv.take<double>(ldb);
   c.merit_rho = cv.take<double>(ldb); c.dV1 = cv.take<double>(ldb); c.dV2 = cv.take<double>(ldb);
   c.cost_prev = cv.take<double>(ldb); c.merit_prev = cv.take<double>(ldb);
@@ -258,7 +259,8 @@ int launch_lq_wb_dense(CafeHandle* H) {
 }
 
 int launch_bwd(CafeHandle* H) {
-  const unsigned grid = (H->B + 3) / 4 * 4;
+  const unsigned grid = (H->S.n_act + 3) / 4 * 4;   // clusters of four listed problems
+  if (grid == 0) return 0;
   if (H->bwd_variant == 0) k_bwd2<0, 128><<<grid, 128, H->bwd_smem, H->stream>>>(H->S);
   else if (H->bwd_nt == 256) k_bwd2<1, 256><<<grid, 256, H->bwd_smem, H->stream>>>(H->S);
   else k_bwd2<1, 128><<<grid, 128, H->bwd_smem, H->stream>>>(H->S);
@@ -430,8 +432,11 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
     SolverDev S0 = S;  // same pointers, ladder {0}
     S0.NA = 1; S0.eps[0] = 0.0;
     CUDA_OK(cudaMemcpyAsync(H->dS, &S0, sizeof(SolverDev), cudaMemcpyHostToDevice, st));
-    timed(H, 0, [&] { cafe_dev::launch_roll(H->dS, nthr_knots, st, 0, 1); });
+    timed(H, 1, [&] { cafe_dev::launch_compact(H->dS, st, 0); });   // every problem is active: the identity list
+    timed(H, 0, [&] { cafe_dev::launch_roll(H->dS, S.n_knots, st, 0, 1, S.c.act_list, B); });
+    CUDA_OK(cudaMemsetAsync(S.c.n_active, 0, sizeof(int), st));
     timed(H, 1, [&] { cafe_dev::launch_select(H->dS, B, st, 0); });
+    timed(H, 1, [&] { cafe_dev::launch_compact(H->dS, st, 0); });
     timed(H, 2, [&] { cafe_dev::launch_accept(H->dS, nthr_knots, st); });
     CUDA_OK(cudaStreamSynchronize(st));  // S0 must stay alive until the copy has been consumed
     CUDA_OK(cudaMemcpyAsync(H->dS, &S, sizeof(SolverDev), cudaMemcpyHostToDevice, st));
@@ -442,23 +447,30 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
     CUDA_OK(cudaStreamSynchronize(st));
     if (*H->h_nactive == 0) break;
     H->ticks++;
-    timed(H, 3, [&] { cafe_dev::launch_lq(H->dS, nthr_knots, st); });
+    const int n_act = *H->h_nactive;   // = length of c.act_list (k_compact)
+    H->S.n_act = n_act;
+    timed(H, 3, [&] { cafe_dev::launch_lq(H->dS, S.n_knots, st, S.c.act_list, n_act); });
     if (H->bwd_variant == 1) timed(H, 5, [&] { launch_lq_wb_dense(H); });
     timed(H, 4, [&] { launch_bwd(H); });
     CUDA_OK(cudaMemsetAsync(H->d_fail, 0, H->fail_bytes, st));
     // staged line search: step sizes are evaluated in growing groups; most problems accept one of the first
     for (int a0 = 0, width = 1; a0 < S.NA; a0 += width, width *= 2) {
       const int a1 = (a0 + width < S.NA) ? a0 + width : S.NA;
-      timed(H, 0, [&] { cafe_dev::launch_roll(H->dS, nthr_knots * (a1 - a0), st, a0, a1); });
+      // the first group runs over the active list (problems that skip the line search return at once), later groups over
+      // the list of line searches that still need step sizes
+      if (a0 == 0) timed(H, 0, [&] { cafe_dev::launch_roll(H->dS, S.n_knots, st, a0, a1, S.c.act_list, n_act); });
+      else timed(H, 0, [&] { cafe_dev::launch_roll(H->dS, S.n_knots, st, a0, a1, S.c.pend_list, H->h_nactive[1]); });
       CUDA_OK(cudaMemsetAsync(S.c.n_pending, 0, sizeof(int), st));
       timed(H, 1, [&] { cafe_dev::launch_ls_scan(H->dS, B, st, a0, a1); });
       if (a1 >= S.NA) break;
+      timed(H, 1, [&] { cafe_dev::launch_compact(H->dS, st, 1); });
       CUDA_OK(cudaMemcpyAsync(H->h_nactive + 1, S.c.n_pending, sizeof(int), cudaMemcpyDeviceToHost, st));
       CUDA_OK(cudaStreamSynchronize(st));
       if (H->h_nactive[1] == 0) break;
     }
     CUDA_OK(cudaMemsetAsync(S.c.n_active, 0, sizeof(int), st));
     timed(H, 1, [&] { cafe_dev::launch_select(H->dS, B, st, 1); });
+    timed(H, 1, [&] { cafe_dev::launch_compact(H->dS, st, 0); });
     timed(H, 2, [&] { cafe_dev::launch_accept(H->dS, nthr_knots, st); });
   }
   CUDA_OK(cudaEventRecord(H->eve, st));
