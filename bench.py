@@ -241,7 +241,7 @@ def main():
         traffic, traffic_src = _ncu_traffic("k_bwd2") if (args.workload == "mhpc" and B == 4096) else (None, None)
         roof = {"bound": "fp64", "kernel": "k_bwd2", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "flop_per_launch": flops / n_l, "avg_launch_ms": tm["ms"]["bwd"] / n_l, "share_of_step": share,
-                "peak_source": "measured live: cafe_gpu_measure_fp64_peak (DFMA microbenchmark, 8 independent chains/thread); MEASURED_PEAKS.json has no fp64 entry",
+                "peak_source": "measured live: cafe_gpu_measure_fp64_peak = max(DFMA chains, DMMA m8n8k4 chains) microbenchmark; MEASURED_PEAKS.json has no fp64 entry",
                 "kernel_ms": tm["ms"], "hbm_peak_gbs": _hbm_peak()}
         # secondary figures per kernel family: share of the step and, where a committed ncu capture exists, the HBM fraction
         # (DRAM bytes of one full-batch launch x launches / live kernel time; later ticks run fewer active problems, so this is an upper bound)

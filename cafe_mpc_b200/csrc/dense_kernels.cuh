@@ -5,40 +5,42 @@
 namespace cafe_dev {
 
 // ------------------------------------------------------------------------------- K-LQ, whole-body dense part
-// KKT sensitivities of one WB phase (WBM.cpp:459-505 without forming Kinv): CTA = 4 consecutive problems at one knot, one warp
-// per problem, lane = column z of [q(18) v(18) tau(12)]; chol(M), Y = L^-1 Jc^T, chol(S) are read from shared memory at
+// KKT sensitivities of one WB phase (WBM.cpp:459-505 without forming Kinv): CTA = 4 consecutive entries of the active list at one knot,
+// one warp per problem, lane = column z of [q(18) v(18) tau(12)]; chol(M), Y = L^-1 Jc^T, chol(S) are read from shared memory at
 // warp-uniform addresses (broadcast), the column's right-hand side lives in registers.
 //   dlambda/dz = S^-1 (Jc Minv R - a),  dqdd/dz = -Minv (R - Jc^T dlambda/dz);  A = I + dt Ac, B = dt Bc, C/D = dGRF/d(x,u)
 // shared memory per problem (doubles): Lt 324 (row-major L, reciprocal diagonal) | Y 216 (18 x 12, ld 18) | Yt 216 (12 x 18, ld 12)
 //                                     | Lst 144 (row-major chol(S), reciprocal diagonal) | R 19x36 | a 13x36
 #define CAFE_KKT_SM (324 + 216 + 216 + 144 + 684 + 468)
+// one warp per problem, two passes over the 48 columns (one thread per column, 192 threads, measured slower: 30.9 vs 27.7 ms per batch)
+#define CAFE_DENSE_NT 128
 template <int NR>
-__global__ void __launch_bounds__(128, 3) k_lq_wb_dense(const SolverDev* __restrict__ Sp, int pi) {
+__global__ void __launch_bounds__(CAFE_DENSE_NT, 3) k_lq_wb_dense(const SolverDev* __restrict__ Sp, int pi, const int* __restrict__ list, int n_list) {
   const SolverDev& S = *Sp;
   const PhaseDev& ph = S.ph[pi];
   extern __shared__ double sm[];
   const int ldb = S.ldb, k = blockIdx.y, b0 = blockIdx.x * 4;
   {
-    const int p = threadIdx.x & 3, b = b0 + p;
+    const int p = threadIdx.x & 3, jl = b0 + p, b = jl < n_list ? list[jl] : 0;   // entries b0..b0+3 of the active list
     double* dst = sm + p * CAFE_KKT_SM;
     const double* src = ph.kkt + gix(k, CAFE_KKT_PACK, 0, ldb, b);
-    if (b < S.B && S.c.active[b]) {
+    if (jl < n_list && S.c.active[b]) {
       const double bg2 = 2.0 * ph.BG_alpha;
       int rowsA[12];
       { int j = 0; for (int f = 0; f < 4; ++f) if (ph.contact[f] > 0) for (int r = 0; r < 3; ++r) rowsA[j++] = 3 * f + r; for (; j < 12; ++j) rowsA[j] = 0; }
-      for (int e = threadIdx.x >> 2; e < 684; e += 32) {  // factors
+      for (int e = threadIdx.x >> 2; e < 684; e += CAFE_DENSE_NT / 4) {  // factors
         const double v = src[(size_t)e * ldb];
         if (e >= CAFE_KKT_LS) { const int idx = e - CAFE_KKT_LS; const int i = idx % 12, j = idx / 12; dst[756 + j + 12 * i] = (i == j) ? 1.0 / v : v; }
         else if (e >= CAFE_KKT_Y) { const int idx = e - CAFE_KKT_Y; const int i = idx % 18, c = idx / 18; dst[324 + idx] = v; dst[540 + c + 12 * i] = v; }
         else { const int i = e % 18, j = e / 18; dst[j + 18 * i] = (i == j) ? 1.0 / v : v; }
       }
-      for (int e = threadIdx.x >> 2; e < 648; e += 32) {  // R = [dtau_dq - d(J^T F)/dq | dtau_dv]
+      for (int e = threadIdx.x >> 2; e < 648; e += CAFE_DENSE_NT / 4) {  // R = [dtau_dq - d(J^T F)/dq | dtau_dv]
         const int i = e % 18, col = e / 18;
         double v = src[(size_t)(CAFE_KKT_RQ + e) * ldb];
         if (col < 18) v -= src[(size_t)(CAFE_KKT_JTF + e) * ldb];
         dst[900 + i + 19 * col] = v;
       }
-      for (int e = threadIdx.x >> 2; e < NR * 36; e += 32) {  // a = [da/dq + 2 BG dv/dq | da/dv + 2 BG J] on the active rows
+      for (int e = threadIdx.x >> 2; e < NR * 36; e += CAFE_DENSE_NT / 4) {  // a = [da/dq + 2 BG dv/dq | da/dv + 2 BG J] on the active rows
         const int c = e % (NR > 0 ? NR : 1), col = e / (NR > 0 ? NR : 1);
         const int row = rowsA[c];
         double v;
@@ -49,9 +51,11 @@ __global__ void __launch_bounds__(128, 3) k_lq_wb_dense(const SolverDev* __restr
     }
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = b0 + warp;
-  if (b >= S.B || !S.c.active[b]) return;
-  const double* sLt = sm + warp * CAFE_KKT_SM;  // Lt[k + 18 i] = L(i,k), Lt[i + 18 i] = 1 / L(i,i)
+  const int prob = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (b0 + prob >= n_list) return;
+  const int b = list[b0 + prob];
+  if (!S.c.active[b]) return;
+  const double* sLt = sm + prob * CAFE_KKT_SM;  // Lt[k + 18 i] = L(i,k), Lt[i + 18 i] = 1 / L(i,i)
   const double* sY = sLt + 324;                 // Y[i + 18 c]
   const double* sYt = sLt + 540;                // Yt[c + 12 i]
   const double* sLst = sLt + 756;               // Lst[k + 12 i] = Ls(i,k), reciprocal diagonal

@@ -143,6 +143,19 @@ __global__ void k_fp64_peak(double* out, int iters) {
   out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
+// the same measurement on the fp64 tensor pipe: 8 independent m8n8k4 accumulator pairs per warp (256 FMAs per instruction)
+__global__ void k_fp64_mma_peak(double* out, int iters) {
+  double c[8][2];
+  const double a = 1e-3 * (threadIdx.x & 31), b = 1e-3;
+  for (int i = 0; i < 8; ++i) { c[i][0] = i; c[i][1] = -i; }
+  for (int it = 0; it < iters; ++it)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cafe_dev::dmma884(c[i][0], c[i][1], a, b);
+  double s = 0;
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 struct Carver {
   size_t off = 0;
   char* base = nullptr;
@@ -245,13 +258,14 @@ int launch_lq_wb_dense(CafeHandle* H) {
     if (ph.model != CAFE_MODEL_WB || ph.h <= 0) continue;
     int nc = 0;
     for (int f = 0; f < 4; ++f) nc += ph.contact[f] > 0;
-    const dim3 grid((H->B + 3) / 4, ph.h);
+    if (H->S.n_act <= 0) continue;
+    const dim3 grid((H->S.n_act + 3) / 4, ph.h);
     switch (nc) {
-      case 0: k_lq_wb_dense<0><<<grid, 128, smem, H->stream>>>(H->dS, pi); break;
-      case 1: k_lq_wb_dense<3><<<grid, 128, smem, H->stream>>>(H->dS, pi); break;
-      case 2: k_lq_wb_dense<6><<<grid, 128, smem, H->stream>>>(H->dS, pi); break;
-      case 3: k_lq_wb_dense<9><<<grid, 128, smem, H->stream>>>(H->dS, pi); break;
-      default: k_lq_wb_dense<12><<<grid, 128, smem, H->stream>>>(H->dS, pi); break;
+      case 0: k_lq_wb_dense<0><<<grid, CAFE_DENSE_NT, smem, H->stream>>>(H->dS, pi, H->S.c.act_list, H->S.n_act); break;
+      case 1: k_lq_wb_dense<3><<<grid, CAFE_DENSE_NT, smem, H->stream>>>(H->dS, pi, H->S.c.act_list, H->S.n_act); break;
+      case 2: k_lq_wb_dense<6><<<grid, CAFE_DENSE_NT, smem, H->stream>>>(H->dS, pi, H->S.c.act_list, H->S.n_act); break;
+      case 3: k_lq_wb_dense<9><<<grid, CAFE_DENSE_NT, smem, H->stream>>>(H->dS, pi, H->S.c.act_list, H->S.n_act); break;
+      default: k_lq_wb_dense<12><<<grid, CAFE_DENSE_NT, smem, H->stream>>>(H->dS, pi, H->S.c.act_list, H->S.n_act); break;
     }
     H->launches[3]++;
   }
@@ -758,6 +772,20 @@ extern "C" int cafe_gpu_measure_fp64_peak(int device, double* tflops) {
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     const double fl = 2.0 * 8.0 * iters * (double)blocks * threads;
+    const double tf = fl / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  // DMMA: the pipe the sweep GEMMs run on; the roofline denominator is the larger of the two
+  k_fp64_mma_peak<<<blocks, threads>>>(d, 256);
+  for (int rep = 0; rep < 5; ++rep) {
+    const int it2 = 1 << 13;
+    cudaEventRecord(e0);
+    k_fp64_mma_peak<<<blocks, threads>>>(d, it2);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double fl = 2.0 * 256.0 * 8.0 * it2 * (double)blocks * (threads / 32);
     const double tf = fl / (ms * 1e-3) / 1e12;
     if (tf > best) best = tf;
   }
