@@ -29,6 +29,10 @@ __device__ __forceinline__ void cp_async8(double* dst_smem, const double* src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async16(double* dst_smem, const double* src) {   // both 16-byte aligned; .cg: straight from L2
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 // pacing barrier of the CTA cluster (no memory ordering needed: it only keeps the four problems that share every 32-byte
@@ -206,7 +210,7 @@ struct Bwd2Layout {
   static_assert(PX == 0 || szK <= ldP * (NX + MX), "[K | dU] does not fit the lyy [C D] tile");
   // linear rollout: two stages of {K, A(stored rows), B, lxx, luu, lx, lu, d, dU}
   static constexpr int lK = 0, lA = lK + ldM * NX, lB = lA + ldA * NX, lLxx = lB + ldA * MX, lLuu = lLxx + ldH * NX, lLx = lLuu + ldM * MX,
-                       lLu = lLx + NX, lD = lLu + MX, lDU = lD + NX, szLin = (lDU + MX + 1) | 1;
+                       lLu = lLx + NX, lD = lLu + MX, lDU = lD + NX, szLin = (lDU + MX + 2) & ~1;   // even: the second stage stays 16-byte aligned
   static constexpr int oLin = nVec;
   static constexpr int endLin = oLin + 2 * szLin;
   static constexpr int total = (endSweep > endLin ? endSweep : endLin) + 64;   // slack: fragment loads of partial edge tiles run past the last tile
@@ -257,16 +261,21 @@ __device__ void sweep_phase2(const SolverDev& S, int pi, int b, int t, bool run,
 
   // asynchronous staging of [A B] (stored rows), [C D], lyy, ly, Defect[k+1] of knot k into their tiles
   auto stage = [&](int k, int t0, int nt) {
-    const double* Ag = ph.A + gix(k, N * N, 0, ldb, b);
-    for (int e = t0; e < KA * N; e += nt) { const int i = e % KA, j = e / KA; cp_async8(sAB + i + ldA * j, Ag + (size_t)((R0 + i) + N * j) * ldb); }
-    const double* Bg = ph.Bm + gix(k, N * M, 0, ldb, b);
-    for (int e = t0; e < KA * M; e += nt) { const int i = e % KA, j = e / KA; cp_async8(sAB + i + ldA * (N + j), Bg + (size_t)((R0 + i) + N * j) * ldb); }
+    if constexpr (WB) {
+      // the producer (k_lq_wb_dense) wrote these two tiles problem-major in exactly this layout: contiguous 16-byte copies
+      static_assert(ldA * (N + M) == CAFE_WB_AB_TILE && ldP * (N + M) == CAFE_WB_CD_TILE && L::oAB % 2 == 0 && L::oCD % 2 == 0, "tile layout");
+      const double* ABt = ph.ABpm + ((size_t)b * h + k) * CAFE_WB_AB_TILE;
+      for (int e = t0; e < CAFE_WB_AB_TILE / 2; e += nt) cp_async16(sAB + 2 * e, ABt + 2 * e);
+      const double* CDt = ph.CDpm + ((size_t)b * h + k) * CAFE_WB_CD_TILE;
+      for (int e = t0; e < CAFE_WB_CD_TILE / 2; e += nt) cp_async16(sCD + 2 * e, CDt + 2 * e);
+    } else {
+      const double* Ag = ph.A + gix(k, N * N, 0, ldb, b);
+      for (int e = t0; e < KA * N; e += nt) { const int i = e % KA, j = e / KA; cp_async8(sAB + i + ldA * j, Ag + (size_t)((R0 + i) + N * j) * ldb); }
+      const double* Bg = ph.Bm + gix(k, N * M, 0, ldb, b);
+      for (int e = t0; e < KA * M; e += nt) { const int i = e % KA, j = e / KA; cp_async8(sAB + i + ldA * (N + j), Bg + (size_t)((R0 + i) + N * j) * ldb); }
+    }
     for (int j = t0; j < N; j += nt) cp_async8(sD + j, ph.Defect + gix(k + 1, N, j, ldb, b));
     if constexpr (PY > 0) {
-      const double* Cg = ph.C + gix(k, PY * N, 0, ldb, b);
-      for (int e = t0; e < PY * N; e += nt) cp_async8(sCD + (e % PY) + ldP * (e / PY), Cg + (size_t)e * ldb);
-      const double* Dg = ph.D + gix(k, PY * M, 0, ldb, b);
-      for (int e = t0; e < PY * M; e += nt) cp_async8(sCD + (e % PY) + ldP * (N + e / PY), Dg + (size_t)e * ldb);
       const double* Lg = ph.lyy + gix(k, PY * PY, 0, ldb, b);
       for (int e = t0; e < PY * PY; e += nt) cp_async8(sLyy + (e % PY) + ldP * (e / PY), Lg + (size_t)e * ldb);
       for (int j = t0; j < PY; j += nt) cp_async8(sLy + j, ph.ly + gix(k, PY, j, ldb, b));
@@ -456,6 +465,11 @@ __device__ void sweep_phase2(const SolverDev& S, int pi, int b, int t, bool run,
       for (int j = t; j < M; j += NT) ph.dU[gix(k, M, j, ldb, b)] = dUs[j];
       double* Kg = ph.K + gix(k, M * N, 0, ldb, b);
       for (int e = t; e < M * N; e += NT) Kg[(size_t)e * ldb] = sK[(e % M) + ldM * (e / M)];
+      if constexpr (WB) {   // second, problem-major copy for the linear rollout of this kernel (16-byte stores / copies)
+        static_assert(ldM * N == CAFE_WB_K_TILE && L::oK % 2 == 0, "K tile layout");
+        double2* Kt = reinterpret_cast<double2*>(ph.Kpm + ((size_t)b * h + k) * CAFE_WB_K_TILE);
+        for (int e = t; e < CAFE_WB_K_TILE / 2; e += NT) Kt[e] = reinterpret_cast<const double2*>(sK)[e];
+      }
       // symmetrise Qxx in place: disjoint (i<j) pairs
       {
         int i = t % N, j = t / N;   // element (i, j), advanced by NT per step without divisions
@@ -497,12 +511,20 @@ __device__ void lin_phase2(const SolverDev& S, int pi, int b, int t, bool run, d
   double* sDuL = sm + L::vDuL;
   auto stage = [&](int k) {
     double* B0 = sm + L::oLin + (k & 1) * L::szLin;
-    const double* Kg = ph.K + gix(k, M * N, 0, ldb, b);
-    for (int e = t; e < M * N; e += NT) cp_async8(B0 + L::lK + (e % M) + ldM * (e / M), Kg + (size_t)e * ldb);
-    const double* Ag = ph.A + gix(k, N * N, 0, ldb, b);
-    for (int e = t; e < KA * N; e += NT) { const int i = e % KA, j = e / KA; cp_async8(B0 + L::lA + i + ldA * j, Ag + (size_t)((R0 + i) + N * j) * ldb); }
-    const double* Bg = ph.Bm + gix(k, N * M, 0, ldb, b);
-    for (int e = t; e < KA * M; e += NT) { const int i = e % KA, j = e / KA; cp_async8(B0 + L::lB + i + ldA * j, Bg + (size_t)((R0 + i) + N * j) * ldb); }
+    if constexpr (WB) {
+      static_assert(L::oLin % 2 == 0 && L::szLin % 2 == 0 && L::lK % 2 == 0 && L::lA % 2 == 0 && L::lB == L::lA + ldA * N, "linear-rollout tile layout");
+      const double* Kt = ph.Kpm + ((size_t)b * h + k) * CAFE_WB_K_TILE;
+      for (int e = t; e < CAFE_WB_K_TILE / 2; e += NT) cp_async16(B0 + L::lK + 2 * e, Kt + 2 * e);
+      const double* ABt = ph.ABpm + ((size_t)b * h + k) * CAFE_WB_AB_TILE;   // [A2 | B2] are adjacent in the stage buffer as well
+      for (int e = t; e < CAFE_WB_AB_TILE / 2; e += NT) cp_async16(B0 + L::lA + 2 * e, ABt + 2 * e);
+    } else {
+      const double* Kg = ph.K + gix(k, M * N, 0, ldb, b);
+      for (int e = t; e < M * N; e += NT) cp_async8(B0 + L::lK + (e % M) + ldM * (e / M), Kg + (size_t)e * ldb);
+      const double* Ag = ph.A + gix(k, N * N, 0, ldb, b);
+      for (int e = t; e < KA * N; e += NT) { const int i = e % KA, j = e / KA; cp_async8(B0 + L::lA + i + ldA * j, Ag + (size_t)((R0 + i) + N * j) * ldb); }
+      const double* Bg = ph.Bm + gix(k, N * M, 0, ldb, b);
+      for (int e = t; e < KA * M; e += NT) { const int i = e % KA, j = e / KA; cp_async8(B0 + L::lB + i + ldA * j, Bg + (size_t)((R0 + i) + N * j) * ldb); }
+    }
     const double* lxxg = ph.lxx + gix(k, N * N, 0, ldb, b);
     for (int e = t; e < N * N; e += NT) cp_async8(B0 + L::lLxx + (e % N) + ldH * (e / N), lxxg + (size_t)e * ldb);
     const double* luug = ph.luu + gix(k, M * M, 0, ldb, b);
@@ -599,7 +621,7 @@ template <int DECK, int NT>
 __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NT, 4) k_bwd2(const __grid_constant__ SolverDev S) {
   typedef Bwd2Layout<(DECK == 0 ? 24 : 36), (DECK == 0 ? 24 : 12), (DECK == 0 ? 0 : 12), (DECK == 1)> L;
   constexpr int NX = (DECK == 0 ? 24 : 36);
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   __shared__ double s_reg;
   __shared__ int s_state, s_regiter;  // 0 sweeping, 1 success, 2 gave up
   // CTA i sweeps the i-th problem that is still iterating (c.act_list, ascending); the tail CTAs of the last cluster idle

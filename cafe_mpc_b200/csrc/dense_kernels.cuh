@@ -64,10 +64,9 @@ __global__ void __launch_bounds__(CAFE_DENSE_NT, 3) k_lq_wb_dense(const SolverDe
   const double dt = ph.dt;
   int foot[4] = {0, 0, 0, 0};
   { int j = 0; for (int f = 0; f < 4; ++f) if (ph.contact[f] > 0) foot[j++] = f; }
-  double* Ag = ph.A + gix(k, 1296, 0, ldb, b);
-  double* Bg = ph.Bm + gix(k, 432, 0, ldb, b);
-  double* Cg = ph.C + gix(k, 432, 0, ldb, b);
-  double* Dg = ph.D + gix(k, 144, 0, ldb, b);
+  // outputs go to the problem-major tiles the backward sweep stages with 16-byte copies: column `col` of [A B] rows 18..35 / [C D]
+  double* ABt = ph.ABpm + ((size_t)b * ph.h + k) * CAFE_WB_AB_TILE;
+  double* CDt = ph.CDpm + ((size_t)b * ph.h + k) * CAFE_WB_CD_TILE;
 #pragma unroll 1
   for (int pass = 0; pass < 2; ++pass) {
     const int col = pass * 32 + lane;
@@ -127,20 +126,11 @@ __global__ void __launch_bounds__(CAFE_DENSE_NT, 3) k_lq_wb_dense(const SolverDe
 #pragma unroll
       for (int kk = 0; kk < i; ++kk) r[kk] -= sLt[kk + 18 * i] * r[i];
     }
-    if (col < 36) {
 #pragma unroll
-      for (int i = 0; i < 18; ++i) Ag[(size_t)((18 + i) + 36 * col) * ldb] = ((col == 18 + i) ? 1.0 : 0.0) + r[i] * dt;
-      if constexpr (NR > 0) {
+    for (int i = 0; i < 18; ++i) ABt[i + 20 * col] = ((col == 18 + i) ? 1.0 : 0.0) + r[i] * dt;   // col >= 36: the B columns (never on the diagonal)
+    if constexpr (NR > 0) {
 #pragma unroll
-        for (int c = 0; c < NR; ++c) Cg[(size_t)((3 * foot[c / 3] + c % 3) + 12 * col) * ldb] = w[c];
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 18; ++i) Bg[(size_t)((18 + i) + 36 * (col - 36)) * ldb] = r[i] * dt;
-      if constexpr (NR > 0) {
-#pragma unroll
-        for (int c = 0; c < NR; ++c) Dg[(size_t)((3 * foot[c / 3] + c % 3) + 12 * (col - 36)) * ldb] = w[c];
-      }
+      for (int c = 0; c < NR; ++c) CDt[(3 * foot[c / 3] + c % 3) + 12 * col] = w[c];
     }
   }
 }

@@ -24,6 +24,10 @@
 #define CAFE_KKT_DVQ 2088
 #define CAFE_KKT_J 2304
 #define CAFE_KKT_PACK 2520
+// problem-major tiles of the whole-body sweep (doubles): [A B] rows 18..35 as 20 x 48 (ld 20), [C D] 12 x 48, K 12 x 36
+#define CAFE_WB_AB_TILE 960
+#define CAFE_WB_CD_TILE 576
+#define CAFE_WB_K_TILE 432
 #define CAFE_MAX_KNOTS 256
 #define CAFE_HIST_CAP 256
 
@@ -45,6 +49,10 @@ struct PhaseDev {
   double *lx, *lu, *ly, *lxx, *luu, *lyy;  // [h][...][ldb]
   double *Phix, *Phixx, *Px;               // [n | n*n | n_next*n][ldb]
   double *kkt;                             // WB only: [h][CAFE_KKT_PACK][ldb]
+  // WB only, PROBLEM-major copies laid out exactly like the shared-memory tiles of the backward sweep (bwd2.cuh), so that a CTA
+  // fetches them with 16-byte cp.async from contiguous memory (an 8-byte element of a problem-fastest array costs one L1 wavefront
+  // each): [b][h][20 x 48] rows 18..35 of [A B] (rows 18, 19 of the tile: zero padding), [b][h][12 x 48] [C D], [b][h][12 x 36] K
+  double *ABpm, *CDpm, *Kpm;
   double *lk, *dsq;                        // [h+1][ldb] per-knot cost (k=h: Phi) and |Defect[k]|^2
   // backward-sweep outputs
   double *K, *Quu, *Qux;                   // [h][m*n | m*m | m*n][ldb]

@@ -220,6 +220,9 @@ void carve(CafeHandle* H, Carver& cv, size_t& zero_bytes) {
     ph.lxx = cv.take<double>(h * n * n * ldb); ph.luu = cv.take<double>(h * m * m * ldb); ph.lyy = cv.take<double>(h * p * p * ldb + 1);
     ph.Phix = cv.take<double>(n * ldb); ph.Phixx = cv.take<double>(n * n * ldb); ph.Px = cv.take<double>(nn * n * ldb);
     ph.kkt = cv.take<double>(ph.model == CAFE_MODEL_WB ? h * (size_t)CAFE_KKT_PACK * ldb : 1);
+    const bool wb = ph.model == CAFE_MODEL_WB;
+    ph.ABpm = cv.take<double>(wb ? h * (size_t)CAFE_WB_AB_TILE * ldb : 2); ph.CDpm = cv.take<double>(wb ? h * (size_t)CAFE_WB_CD_TILE * ldb : 2);
+    ph.Kpm = cv.take<double>(wb ? h * (size_t)CAFE_WB_K_TILE * ldb : 2);
     ph.Quu = cv.take<double>(h * m * m * ldb); ph.Qux = cv.take<double>(h * m * n * ldb);
     ph.Xt = cv.take<double>((size_t)NA * (h + 1) * n * ldb); ph.Ut = cv.take<double>((size_t)NA * h * m * ldb);
     ph.Yt = cv.take<double>((size_t)NA * h * p * ldb + 1); ph.Dt = cv.take<double>((size_t)NA * (h + 1) * n * ldb);
@@ -744,6 +747,30 @@ extern "C" long cafe_gpu_debug_get(CafeHandle* H, const char* name, int phase, i
   else if (nm == "luu") set(ph.luu, h, m * m); else if (nm == "lyy") set(ph.lyy, h, p * p); else if (nm == "l") set(ph.lk, h + 1, 1);
   else if (nm == "Phix") set(ph.Phix, 1, n); else if (nm == "Phixx") set(ph.Phixx, 1, n * n); else if (nm == "Px") set(ph.Px, 1, (long)nn * n);
   else { cafe::set_last_error("unknown array name"); return CAFE_ERR_ARG; }
+  if (ph.model == CAFE_MODEL_WB && (nm == "A" || nm == "B" || nm == "C" || nm == "D")) {
+    // the whole-body linearisation is stored problem-major in the sweep's tile layout (ABpm, CDpm); rows 0..17 of A are the
+    // static [I, dt I] pattern kept in the batch-major array
+    std::vector<double> ab((size_t)h * CAFE_WB_AB_TILE), cd((size_t)h * CAFE_WB_CD_TILE), a0;
+    if (cudaMemcpy(ab.data(), ph.ABpm + (size_t)b * h * CAFE_WB_AB_TILE, ab.size() * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(cd.data(), ph.CDpm + (size_t)b * h * CAFE_WB_CD_TILE, cd.size() * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) {
+      cafe::set_last_error("cudaMemcpy failed"); return CAFE_ERR_CUDA;
+    }
+    if (nm == "A") {
+      a0.resize((size_t)h * 1296);
+      if (cudaMemcpy2D(a0.data(), sizeof(double), ph.A + b, (size_t)H->ldb * sizeof(double), sizeof(double), (size_t)h * 1296, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        cafe::set_last_error("cudaMemcpy2D failed"); return CAFE_ERR_CUDA;
+      }
+    }
+    for (int k = 0; k < h; ++k) {
+      if (nm == "A") for (int j = 0; j < 36; ++j) for (int i = 0; i < 36; ++i)
+        out[(size_t)k * 1296 + i + 36 * j] = i < 18 ? a0[(size_t)k * 1296 + i + 36 * j] : ab[(size_t)k * CAFE_WB_AB_TILE + (i - 18) + 20 * j];
+      else if (nm == "B") for (int j = 0; j < 12; ++j) for (int i = 0; i < 36; ++i)
+        out[(size_t)k * 432 + i + 36 * j] = i < 18 ? 0.0 : ab[(size_t)k * CAFE_WB_AB_TILE + (i - 18) + 20 * (36 + j)];
+      else if (nm == "C") for (int j = 0; j < 36; ++j) for (int i = 0; i < 12; ++i) out[(size_t)k * 432 + i + 12 * j] = cd[(size_t)k * CAFE_WB_CD_TILE + i + 12 * j];
+      else for (int j = 0; j < 12; ++j) for (int i = 0; i < 12; ++i) out[(size_t)k * 144 + i + 12 * j] = cd[(size_t)k * CAFE_WB_CD_TILE + i + 12 * (36 + j)];
+    }
+    return (long)knots * nc;
+  }
   const long cnt = knots * nc;
   if (cnt == 0) return 0;
   if (cudaMemcpy2D(out, sizeof(double), src + b, (size_t)H->ldb * sizeof(double), sizeof(double), (size_t)cnt, cudaMemcpyDeviceToHost) != cudaSuccess) {
