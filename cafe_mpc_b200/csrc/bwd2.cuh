@@ -43,6 +43,8 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 #define CAFE_PACE 4
 #endif
 __device__ __forceinline__ void cluster_pace() { asm volatile("barrier.cluster.arrive.relaxed.aligned;\nbarrier.cluster.wait.aligned;\n" ::: "memory"); }
+// bit e of a structural-pattern mask (read-only, the same for every problem: served by L1)
+__device__ __forceinline__ bool mask_bit(const unsigned long long* __restrict__ m, int e) { return (__ldg(m + (e >> 6)) >> (e & 63)) & 1ULL; }
 __device__ __forceinline__ void prefetch_l1(const double* p) { asm volatile("prefetch.global.L1 [%0];\n" ::"l"(p)); }
 
 // C(i,j) = epi(i,j, sum_{l<KK} opA(i,l) B(l,j) + sum_{l<KK2} A2[l + lda2*i] B2[l + ldb2*j])   for i < MM, j < NN
@@ -277,7 +279,8 @@ __device__ void sweep_phase2(const SolverDev& S, int pi, int b, int t, bool run,
     for (int j = t0; j < N; j += nt) cp_async8(sD + j, ph.Defect + gix(k + 1, N, j, ldb, b));
     if constexpr (PY > 0) {
       const double* Lg = ph.lyy + gix(k, PY * PY, 0, ldb, b);
-      for (int e = t0; e < PY * PY; e += nt) cp_async8(sLyy + (e % PY) + ldP * (e / PY), Lg + (size_t)e * ldb);
+      // lyy: one 3 x 3 block per foot (GRF barrier on the output); the rest of the tile stays zero (cleared at kernel start)
+      for (int e = t0; e < PY * 3; e += nt) { const int j = e / 3, i = 3 * (j / 3) + e % 3; cp_async8(sLyy + i + ldP * j, Lg + (size_t)(i + PY * j) * ldb); }
       for (int j = t0; j < PY; j += nt) cp_async8(sLy + j, ph.ly + gix(k, PY, j, ldb, b));
     }
     cp_async_commit();
@@ -345,10 +348,17 @@ __device__ void sweep_phase2(const SolverDev& S, int pi, int b, int t, bool run,
       // [Qxx Qxu; Qux Quu] = [A B]^T T_rows (+ [C D]^T lyy [C D]) is ONE (N+M)^2 product; its upper right block is not needed
       const double* lxxg = ph.lxx + gix(k, N * N, 0, ldb, b);
       const double* luug = ph.luu + gix(k, M * M, 0, ldb, b);
+      const unsigned long long* lmask = WB ? ph.lxx_mask + (size_t)k * CAFE_LXX_MASK_WORDS : nullptr;
+      (void)lmask;
       gemm_mma<N + M, N + M, KA, true, PY, NT, TilesQ<N, M>>(sAB, ldA, sT + R0, ldH, sCD, ldP, sSCD, ldP, t, a2,
         [&](int i, int j) -> double {   // lxx / luu: 8-byte loads of a problem-fastest array, issued before the k loop
-          if (j < N) return (i < N) ? lxxg[(size_t)(i + N * j) * ldb] : 0.0;
-          return (i >= N) ? luug[(size_t)((i - N) + M * (j - N)) * ldb] : 0.0;
+          if constexpr (WB) {           // only the structural non-zeros: lxx by its per-knot pattern, luu is diagonal
+            if (j < N) return (i < N && mask_bit(lmask, i + N * j)) ? lxxg[(size_t)(i + N * j) * ldb] : 0.0;
+            return (i >= N && i == j) ? luug[(size_t)((i - N) + M * (j - N)) * ldb] : 0.0;
+          } else {
+            if (j < N) return (i < N) ? lxxg[(size_t)(i + N * j) * ldb] : 0.0;
+            return (i >= N) ? luug[(size_t)((i - N) + M * (j - N)) * ldb] : 0.0;
+          }
         },
         [&](int i, int j, double v) {
         if (j < N) {
@@ -526,9 +536,21 @@ __device__ void lin_phase2(const SolverDev& S, int pi, int b, int t, bool run, d
       for (int e = t; e < KA * M; e += NT) { const int i = e % KA, j = e / KA; cp_async8(B0 + L::lB + i + ldA * j, Bg + (size_t)((R0 + i) + N * j) * ldb); }
     }
     const double* lxxg = ph.lxx + gix(k, N * N, 0, ldb, b);
-    for (int e = t; e < N * N; e += NT) cp_async8(B0 + L::lLxx + (e % N) + ldH * (e / N), lxxg + (size_t)e * ldb);
     const double* luug = ph.luu + gix(k, M * M, 0, ldb, b);
-    for (int e = t; e < M * M; e += NT) cp_async8(B0 + L::lLuu + (e % M) + ldM * (e / M), luug + (size_t)e * ldb);
+    if constexpr (WB) {
+      // structural non-zeros only (the consumers below skip the other tile entries, which may hold another knot's values)
+      const unsigned long long* lmask = ph.lxx_mask + (size_t)k * CAFE_LXX_MASK_WORDS;
+      int i = t % N, j = t / N;
+      for (int e = t; e < N * N; e += NT) {
+        if (mask_bit(lmask, e)) cp_async8(B0 + L::lLxx + i + ldH * j, lxxg + (size_t)e * ldb);
+        i += NT % N; j += NT / N;
+        if (i >= N) { i -= N; ++j; }
+      }
+      for (int e = t; e < M; e += NT) cp_async8(B0 + L::lLuu + e + ldM * e, luug + (size_t)(e + M * e) * ldb);
+    } else {
+      for (int e = t; e < N * N; e += NT) cp_async8(B0 + L::lLxx + (e % N) + ldH * (e / N), lxxg + (size_t)e * ldb);
+      for (int e = t; e < M * M; e += NT) cp_async8(B0 + L::lLuu + (e % M) + ldM * (e / M), luug + (size_t)e * ldb);
+    }
     for (int j = t; j < N; j += NT) {
       cp_async8(B0 + L::lLx + j, ph.lx + gix(k, N, j, ldb, b));
       cp_async8(B0 + L::lD + j, ph.Defect + gix(k + 1, N, j, ldb, b));
@@ -560,7 +582,12 @@ __device__ void lin_phase2(const SolverDev& S, int pi, int b, int t, bool run, d
       constexpr int T1 = (NT >= 64 + N) ? 64 : (NT >= 32 + N ? 32 : 0);  // first thread of the lxx rows
       for (int i = t - T1; i >= 0 && i < N; i += NT) {
         double q = 0;
-        for (int j = 0; j < N; ++j) q += B0[L::lLxx + i + ldH * j] * dx[j];
+        if constexpr (WB) {
+          const unsigned long long* lmask = ph.lxx_mask + (size_t)k * CAFE_LXX_MASK_WORDS;
+          for (int j = 0; j < N; ++j) if (mask_bit(lmask, i + N * j)) q += B0[L::lLxx + i + ldH * j] * dx[j];
+        } else {
+          for (int j = 0; j < N; ++j) q += B0[L::lLxx + i + ldH * j] * dx[j];
+        }
         const double dxi = dx[i];
         part1 += B0[L::lLx + i] * dxi;
         part2 += dxi * q;
@@ -585,7 +612,8 @@ __device__ void lin_phase2(const SolverDev& S, int pi, int b, int t, bool run, d
       constexpr int T2 = (NT >= 64 + M) ? 64 : (NT >= 32 + M ? 32 : 0);
       for (int i = t - T2; i >= 0 && i < M; i += NT) {
         double q = 0;
-        for (int j = 0; j < M; ++j) q += B0[L::lLuu + i + ldM * j] * sDuL[j];
+        if constexpr (WB) q = B0[L::lLuu + i + ldM * i] * sDuL[i];   // luu is diagonal
+        else for (int j = 0; j < M; ++j) q += B0[L::lLuu + i + ldM * j] * sDuL[j];
         const double dui = sDuL[i];
         part1 += B0[L::lLu + i] * dui;
         part2 += dui * q;

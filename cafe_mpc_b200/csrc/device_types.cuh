@@ -28,6 +28,7 @@
 #define CAFE_WB_AB_TILE 960
 #define CAFE_WB_CD_TILE 576
 #define CAFE_WB_K_TILE 432
+#define CAFE_LXX_MASK_WORDS 21
 #define CAFE_MAX_KNOTS 256
 #define CAFE_HIST_CAP 256
 
@@ -53,6 +54,10 @@ struct PhaseDev {
   // fetches them with 16-byte cp.async from contiguous memory (an 8-byte element of a problem-fastest array costs one L1 wavefront
   // each): [b][h][20 x 48] rows 18..35 of [A B] (rows 18, 19 of the tile: zero padding), [b][h][12 x 48] [C D], [b][h][12 x 36] K
   double *ABpm, *CDpm, *Kpm;
+  // WB only: structural non-zero pattern of lxx per knot (bit i + 36 j of 21 64-bit words), built on the host from the contact
+  // flags of the knot's reference record (the rule of WBModel::lq_knot). The sweep fetches only these entries of lxx; luu is
+  // diagonal and lyy has one 3 x 3 block per foot for this model.
+  const unsigned long long* lxx_mask;
   double *lk, *dsq;                        // [h+1][ldb] per-knot cost (k=h: Phi) and |Defect[k]|^2
   // backward-sweep outputs
   double *K, *Quu, *Qux;                   // [h][m*n | m*m | m*n][ldb]

@@ -39,6 +39,7 @@ struct CafeHandle {
   size_t arena_bytes = 0, zero_bytes = 0;  // [0, zero_bytes) is re-zeroed at every solve
   double* d_ref = nullptr;
   double* d_ref_pp = nullptr; int ref_pp_B = 0;
+  unsigned long long* d_lxx_mask = nullptr;   // structural lxx patterns of the whole-body knots
   double* d_guess = nullptr; size_t guess_bytes = 0; int guess_B = 0;  // packed initial guesses [B][solution_size] (warm start)  // per-problem reference records [n_records][CAFE_REF_W][ldb]
   double* d_x0raw = nullptr;
   int* d_fail = nullptr; size_t fail_bytes = 0;
@@ -346,6 +347,38 @@ extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, 
   CUDA_OK(cudaMalloc(&H->d_ref, H->ref_host.size() * sizeof(double)));
   CUDA_OK(cudaMemcpy(H->d_ref, H->ref_host.data(), H->ref_host.size() * sizeof(double), cudaMemcpyHostToDevice));
   for (int i = 0; i < deck->n_phases; ++i) { S.ph[i].ref = H->d_ref + (size_t)deck->phase[i].knot_offset * CAFE_REF_W; S.ph[i].ref_pp = nullptr; }
+  {
+    // structural pattern of the whole-body lxx per knot (WBModel::lq_knot): the diagonal, the base block {3,4,5,18..23}^2 shared by
+    // the feet, and per foot {3,4,5, own leg q}^2 in stance or {3,4,5, own leg q, 18..23, own leg v}^2 in swing, the stance flag
+    // being the contact flag of the knot's reference record
+    std::vector<unsigned long long> masks;
+    std::vector<size_t> first(deck->n_phases, 0);
+    for (int i = 0; i < deck->n_phases; ++i) {
+      first[i] = masks.size();
+      if (deck->phase[i].model != CAFE_MODEL_WB) continue;
+      for (int k = 0; k < deck->phase[i].horizon; ++k) {
+        unsigned long long w[CAFE_LXX_MASK_WORDS] = {0};
+        auto setbit = [&](int r, int c) { const int e = r + 36 * c; w[e >> 6] |= 1ULL << (e & 63); };
+        for (int d = 0; d < 36; ++d) setbit(d, d);
+        const int base[9] = {3, 4, 5, 18, 19, 20, 21, 22, 23};
+        for (int a = 0; a < 9; ++a) for (int c = 0; c < 9; ++c) setbit(base[a], base[c]);
+        const double* rec = H->ref_host.data() + ((size_t)deck->phase[i].knot_offset + k) * CAFE_REF_W;
+        for (int f = 0; f < 4; ++f) {
+          int cols[15];
+          for (int a = 0; a < 3; ++a) { cols[a] = 3 + a; cols[3 + a] = 6 + 3 * f + a; cols[12 + a] = 24 + 3 * f + a; }
+          for (int a = 0; a < 6; ++a) cols[6 + a] = 18 + a;
+          const int nc = rec[CAFE_REF_CONTACT + f] > 0 ? 6 : 15;
+          for (int a = 0; a < nc; ++a) for (int c = 0; c < nc; ++c) setbit(cols[a], cols[c]);
+        }
+        masks.insert(masks.end(), w, w + CAFE_LXX_MASK_WORDS);
+      }
+    }
+    if (!masks.empty()) {
+      CUDA_OK(cudaMalloc(&H->d_lxx_mask, masks.size() * sizeof(unsigned long long)));
+      CUDA_OK(cudaMemcpy(H->d_lxx_mask, masks.data(), masks.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    }
+    for (int i = 0; i < deck->n_phases; ++i) S.ph[i].lxx_mask = (deck->phase[i].model == CAFE_MODEL_WB && H->d_lxx_mask) ? H->d_lxx_mask + first[i] : nullptr;
+  }
   CUDA_OK(cudaMalloc(&H->d_x0raw, (size_t)H->ldb * CAFE_MAX_N * sizeof(double)));
   CUDA_OK(cudaMalloc(&H->dS, sizeof(SolverDev)));
   CUDA_OK(cudaMallocHost(&H->h_nactive, 64));
@@ -384,7 +417,7 @@ extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, 
 extern "C" int cafe_gpu_destroy(CafeHandle* H) {
   if (!H) return 0;
   cudaSetDevice(H->device);
-  cudaFree(H->arena); cudaFree(H->d_ref); cudaFree(H->d_ref_pp); cudaFree(H->d_guess); cudaFree(H->d_x0raw); cudaFree(H->dS); cudaFree(H->d_pack); cudaFree(H->d_segs);
+  cudaFree(H->arena); cudaFree(H->d_ref); cudaFree(H->d_ref_pp); cudaFree(H->d_lxx_mask); cudaFree(H->d_guess); cudaFree(H->d_x0raw); cudaFree(H->dS); cudaFree(H->d_pack); cudaFree(H->d_segs);
   if (H->h_nactive) cudaFreeHost(H->h_nactive);
   if (H->stream) cudaStreamDestroy(H->stream);
   if (H->ev0) cudaEventDestroy(H->ev0);
