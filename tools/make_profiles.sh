@@ -8,7 +8,7 @@ $CMD > gpurun_out/${R}_plain.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${R}_launches_mhpc.csv $CMD > gpurun_out/${R}_ncu_launch.log 2>&1
 CMD2="python tools/profile_cmd.py mhpc 4096 1 3"
 $CMD2 > gpurun_out/${R}_plain2.log 2>&1
-ncu --set full --clock-control none -k regex:'k_bwd2|k_lq|k_roll' -s 4 -c 4 -o /tmp/${R}_full_mhpc -f $CMD2 > gpurun_out/${R}_ncu_full.log 2>&1
+ncu --set full --clock-control none -k regex:'k_bwd2|k_lq|k_roll' -s 4 -c 5 -o /tmp/${R}_full_mhpc -f $CMD2 > gpurun_out/${R}_ncu_full.log 2>&1
 # the report itself is ~100 MB (SASS of the generated whole-body code): only its raw metric page travels back
 ncu -i /tmp/${R}_full_mhpc.ncu-rep --page raw --csv > gpurun_out/${R}_full_mhpc_raw.csv
 tail -n 3 gpurun_out/${R}_plain.log
