@@ -262,6 +262,7 @@ __device__ void sweep_phase2(const SolverDev& S, int pi, int b, int t, bool run,
   if (run && ok) for (int j = t; j < N; j += NT) ph.G[gix(h, N, j, ldb, b)] = sG[j];
 
   // asynchronous staging of [A B] (stored rows), [C D], lyy, ly, Defect[k+1] of knot k into their tiles
+  const unsigned long long* hm = WB ? nullptr : ph.hkd_mask;   // HKD: structural patterns of A, B, lxx, luu (else nullptr)
   auto stage = [&](int k, int t0, int nt) {
     if constexpr (WB) {
       // the producer (k_lq_wb_dense) wrote these two tiles problem-major in exactly this layout: contiguous 16-byte copies
@@ -272,9 +273,14 @@ __device__ void sweep_phase2(const SolverDev& S, int pi, int b, int t, bool run,
       for (int e = t0; e < CAFE_WB_CD_TILE / 2; e += nt) cp_async16(sCD + 2 * e, CDt + 2 * e);
     } else {
       const double* Ag = ph.A + gix(k, N * N, 0, ldb, b);
-      for (int e = t0; e < KA * N; e += nt) { const int i = e % KA, j = e / KA; cp_async8(sAB + i + ldA * j, Ag + (size_t)((R0 + i) + N * j) * ldb); }
       const double* Bg = ph.Bm + gix(k, N * M, 0, ldb, b);
-      for (int e = t0; e < KA * M; e += nt) { const int i = e % KA, j = e / KA; cp_async8(sAB + i + ldA * (N + j), Bg + (size_t)((R0 + i) + N * j) * ldb); }
+      if (hm != nullptr) {   // structural non-zeros only (86 + 60 of 1152 for the HKD model)
+        for (int e = t0; e < N * N; e += nt) if (mask_bit(hm, e)) cp_async8(sAB + (e % N) + ldA * (e / N), Ag + (size_t)e * ldb);
+        for (int e = t0; e < N * M; e += nt) if (mask_bit(hm + 9, e)) cp_async8(sAB + (e % N) + ldA * (N + e / N), Bg + (size_t)e * ldb);
+      } else {
+        for (int e = t0; e < KA * N; e += nt) { const int i = e % KA, j = e / KA; cp_async8(sAB + i + ldA * j, Ag + (size_t)((R0 + i) + N * j) * ldb); }
+        for (int e = t0; e < KA * M; e += nt) { const int i = e % KA, j = e / KA; cp_async8(sAB + i + ldA * (N + j), Bg + (size_t)((R0 + i) + N * j) * ldb); }
+      }
     }
     for (int j = t0; j < N; j += nt) cp_async8(sD + j, ph.Defect + gix(k + 1, N, j, ldb, b));
     if constexpr (PY > 0) {
@@ -289,6 +295,12 @@ __device__ void sweep_phase2(const SolverDev& S, int pi, int b, int t, bool run,
     // k padding of [A B] (rows KA..ldA-1, never staged): zero again, the jump above used the area for Px
     constexpr int PAD = ldA - KA;
     if (run && ok) for (int e = t; e < PAD * (N + M); e += NT) sAB[KA + (e % PAD) + ldA * (e / PAD)] = 0.0;
+  }
+  if (hm != nullptr) {
+    // only the structural non-zeros of [A B] are staged: the rest of the tile (used for Px above) must be zero
+    __syncthreads();
+    if (run && ok) for (int e = t; e < ldA * (N + M); e += NT) sAB[e] = 0.0;
+    __syncthreads();
   }
   if (run && ok && h > 0) stage(h - 1, t, NT);
   for (int k = h - 1; k >= 0; --k) {
@@ -356,8 +368,8 @@ __device__ void sweep_phase2(const SolverDev& S, int pi, int b, int t, bool run,
             if (j < N) return (i < N && mask_bit(lmask, i + N * j)) ? lxxg[(size_t)(i + N * j) * ldb] : 0.0;
             return (i >= N && i == j) ? luug[(size_t)((i - N) + M * (j - N)) * ldb] : 0.0;
           } else {
-            if (j < N) return (i < N) ? lxxg[(size_t)(i + N * j) * ldb] : 0.0;
-            return (i >= N) ? luug[(size_t)((i - N) + M * (j - N)) * ldb] : 0.0;
+            if (j < N) return (i < N && (hm == nullptr || mask_bit(hm + 18, i + N * j))) ? lxxg[(size_t)(i + N * j) * ldb] : 0.0;
+            return (i >= N && (hm == nullptr || mask_bit(hm + 27, (i - N) + M * (j - N)))) ? luug[(size_t)((i - N) + M * (j - N)) * ldb] : 0.0;
           }
         },
         [&](int i, int j, double v) {
@@ -475,10 +487,10 @@ __device__ void sweep_phase2(const SolverDev& S, int pi, int b, int t, bool run,
       for (int j = t; j < M; j += NT) ph.dU[gix(k, M, j, ldb, b)] = dUs[j];
       double* Kg = ph.K + gix(k, M * N, 0, ldb, b);
       for (int e = t; e < M * N; e += NT) Kg[(size_t)e * ldb] = sK[(e % M) + ldM * (e / M)];
-      if constexpr (WB) {   // second, problem-major copy for the linear rollout of this kernel (16-byte stores / copies)
-        static_assert(ldM * N == CAFE_WB_K_TILE && L::oK % 2 == 0, "K tile layout");
-        double2* Kt = reinterpret_cast<double2*>(ph.Kpm + ((size_t)b * h + k) * CAFE_WB_K_TILE);
-        for (int e = t; e < CAFE_WB_K_TILE / 2; e += NT) Kt[e] = reinterpret_cast<const double2*>(sK)[e];
+      {   // second, problem-major copy (the ld x N tile as it is) for the linear rollout of this kernel: 16-byte stores / copies
+        static_assert(L::oK % 2 == 0 && (ldM * N) % 2 == 0, "K tile layout");
+        double2* Kt = reinterpret_cast<double2*>(ph.Kpm + ((size_t)b * h + k) * (ldM * N));
+        for (int e = t; e < ldM * N / 2; e += NT) Kt[e] = reinterpret_cast<const double2*>(sK)[e];
       }
       // symmetrise Qxx in place: disjoint (i<j) pairs
       {
@@ -519,21 +531,34 @@ __device__ void lin_phase2(const SolverDev& S, int pi, int b, int t, bool run, d
   const double dt = ph.dt;
   double* dxb[2] = {sm + L::vDx, sm + L::vDxn};
   double* sDuL = sm + L::vDuL;
+  const unsigned long long* hm = WB ? nullptr : ph.hkd_mask;
+  if (hm != nullptr) {
+    // the HKD tiles are staged at their structural non-zeros only and consumed densely: everything else must be zero
+    __syncthreads();
+    if (run) for (int e = t; e < 2 * L::szLin; e += NT) sm[L::oLin + e] = 0.0;
+    __syncthreads();
+  }
   auto stage = [&](int k) {
     double* B0 = sm + L::oLin + (k & 1) * L::szLin;
+    static_assert(L::oLin % 2 == 0 && L::szLin % 2 == 0 && L::lK % 2 == 0 && L::lA % 2 == 0, "linear-rollout tile layout");
+    {
+      const double* Kt = ph.Kpm + ((size_t)b * h + k) * (ldM * N);   // the sweep's problem-major copy of the ld x N tile
+      for (int e = t; e < ldM * N / 2; e += NT) cp_async16(B0 + L::lK + 2 * e, Kt + 2 * e);
+    }
     if constexpr (WB) {
-      static_assert(L::oLin % 2 == 0 && L::szLin % 2 == 0 && L::lK % 2 == 0 && L::lA % 2 == 0 && L::lB == L::lA + ldA * N, "linear-rollout tile layout");
-      const double* Kt = ph.Kpm + ((size_t)b * h + k) * CAFE_WB_K_TILE;
-      for (int e = t; e < CAFE_WB_K_TILE / 2; e += NT) cp_async16(B0 + L::lK + 2 * e, Kt + 2 * e);
+      static_assert(L::lB == L::lA + ldA * N, "[A2 | B2] adjacent");
       const double* ABt = ph.ABpm + ((size_t)b * h + k) * CAFE_WB_AB_TILE;   // [A2 | B2] are adjacent in the stage buffer as well
       for (int e = t; e < CAFE_WB_AB_TILE / 2; e += NT) cp_async16(B0 + L::lA + 2 * e, ABt + 2 * e);
     } else {
-      const double* Kg = ph.K + gix(k, M * N, 0, ldb, b);
-      for (int e = t; e < M * N; e += NT) cp_async8(B0 + L::lK + (e % M) + ldM * (e / M), Kg + (size_t)e * ldb);
       const double* Ag = ph.A + gix(k, N * N, 0, ldb, b);
-      for (int e = t; e < KA * N; e += NT) { const int i = e % KA, j = e / KA; cp_async8(B0 + L::lA + i + ldA * j, Ag + (size_t)((R0 + i) + N * j) * ldb); }
       const double* Bg = ph.Bm + gix(k, N * M, 0, ldb, b);
-      for (int e = t; e < KA * M; e += NT) { const int i = e % KA, j = e / KA; cp_async8(B0 + L::lB + i + ldA * j, Bg + (size_t)((R0 + i) + N * j) * ldb); }
+      if (hm != nullptr) {
+        for (int e = t; e < N * N; e += NT) if (mask_bit(hm, e)) cp_async8(B0 + L::lA + (e % N) + ldA * (e / N), Ag + (size_t)e * ldb);
+        for (int e = t; e < N * M; e += NT) if (mask_bit(hm + 9, e)) cp_async8(B0 + L::lB + (e % N) + ldA * (e / N), Bg + (size_t)e * ldb);
+      } else {
+        for (int e = t; e < KA * N; e += NT) { const int i = e % KA, j = e / KA; cp_async8(B0 + L::lA + i + ldA * j, Ag + (size_t)((R0 + i) + N * j) * ldb); }
+        for (int e = t; e < KA * M; e += NT) { const int i = e % KA, j = e / KA; cp_async8(B0 + L::lB + i + ldA * j, Bg + (size_t)((R0 + i) + N * j) * ldb); }
+      }
     }
     const double* lxxg = ph.lxx + gix(k, N * N, 0, ldb, b);
     const double* luug = ph.luu + gix(k, M * M, 0, ldb, b);
@@ -547,6 +572,9 @@ __device__ void lin_phase2(const SolverDev& S, int pi, int b, int t, bool run, d
         if (i >= N) { i -= N; ++j; }
       }
       for (int e = t; e < M; e += NT) cp_async8(B0 + L::lLuu + e + ldM * e, luug + (size_t)(e + M * e) * ldb);
+    } else if (hm != nullptr) {
+      for (int e = t; e < N * N; e += NT) if (mask_bit(hm + 18, e)) cp_async8(B0 + L::lLxx + (e % N) + ldH * (e / N), lxxg + (size_t)e * ldb);
+      for (int e = t; e < M * M; e += NT) if (mask_bit(hm + 27, e)) cp_async8(B0 + L::lLuu + (e % M) + ldM * (e / M), luug + (size_t)e * ldb);
     } else {
       for (int e = t; e < N * N; e += NT) cp_async8(B0 + L::lLxx + (e % N) + ldH * (e / N), lxxg + (size_t)e * ldb);
       for (int e = t; e < M * M; e += NT) cp_async8(B0 + L::lLuu + (e % M) + ldM * (e / M), luug + (size_t)e * ldb);

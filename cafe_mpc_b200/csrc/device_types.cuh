@@ -58,6 +58,8 @@ struct PhaseDev {
   // flags of the knot's reference record (the rule of WBModel::lq_knot). The sweep fetches only these entries of lxx; luu is
   // diagonal and lyy has one 3 x 3 block per foot for this model.
   const unsigned long long* lxx_mask;
+  // HKD only: structural patterns of A, B, lxx, luu (576-bit masks, 9 words each, the same for every knot and phase)
+  const unsigned long long* hkd_mask;
   double *lk, *dsq;                        // [h+1][ldb] per-knot cost (k=h: Phi) and |Defect[k]|^2
   // backward-sweep outputs
   double *K, *Quu, *Qux;                   // [h][m*n | m*m | m*n][ldb]

@@ -12,6 +12,22 @@
 
 namespace cafe {
 
+void hkd_lq_patterns(unsigned long long out[36]) {
+  for (int i = 0; i < 36; ++i) out[i] = 0;
+  auto setbit = [&](int which, int e) { out[9 * which + (e >> 6)] |= 1ULL << (e & 63); };
+  double x[24], u[24], c[4] = {1, 0, 1, 0};
+  const double dt = 0.01;
+  for (int i = 0; i < 24; ++i) { x[i] = 0.1 + 0.01 * i; u[i] = 0.2 - 0.01 * i; }
+  cafe_gen_hkd::hkinodyn_par(x, u, &dt, c, [&](int i, double) { setbit(0, i); }, [&](int i, double) { setbit(1, i); });
+  for (int d = 0; d < 24; ++d) setbit(2, d + 24 * d);
+  for (int leg = 0; leg < 4; ++leg)
+    for (int a = 0; a < 2; ++a) { setbit(2, (3 + a) + 24 * (12 + 3 * leg + a)); setbit(2, (12 + 3 * leg + a) + 24 * (3 + a)); }
+  for (int leg = 0; leg < 4; ++leg)
+    for (int r = 0; r < 3; ++r) for (int cc = 0; cc < 3; ++cc) setbit(3, (3 * leg + r) + 24 * (3 * leg + cc));
+  for (int d = 12; d < 24; ++d) setbit(3, d + 24 * d);
+}
+
+
 void load_hsddp_setting(const std::string& fname, CafeOptions& o) {
   InfoFile pt(fname);
   std::memset(&o, 0, sizeof(o));

@@ -64,6 +64,10 @@ class MHPCProblem {  // MHPCProblem.h:169-289
   float plan_dur_all = 0;
 };
 
+// Structural non-zero patterns of the HKD linearisation as 576-bit masks (bit i + 24 j; 9 words each, in the order A, B, lxx, luu):
+// A and B are the CCS patterns of the generated hkinodyn_par (recorded by running it with index-collecting store functors), lxx and
+// luu follow HKDModel::lq_knot (model_hkd.cuh). The backward sweep fetches only these entries.
+void hkd_lq_patterns(unsigned long long out[36]);
 // compute_hkd_state (HKDModel.h:66-96): qdummy from joint angles (swing) or foot FK (stance)
 void compute_hkd_state(const double eul[3], const double pos[3], const double qJ[12], double qdummy[12], const int contact[4]);
 

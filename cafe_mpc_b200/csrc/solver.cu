@@ -15,6 +15,7 @@
 #include "dense_kernels.cuh"
 #include "bwd2.cuh"
 #include "launchers.h"
+#include "host/problem_builders.h"
 
 namespace cafe { void set_last_error(const std::string& s); }
 
@@ -39,7 +40,8 @@ struct CafeHandle {
   size_t arena_bytes = 0, zero_bytes = 0;  // [0, zero_bytes) is re-zeroed at every solve
   double* d_ref = nullptr;
   double* d_ref_pp = nullptr; int ref_pp_B = 0;
-  unsigned long long* d_lxx_mask = nullptr;   // structural lxx patterns of the whole-body knots
+  unsigned long long* d_lxx_mask = nullptr;
+  unsigned long long* d_hkd_mask = nullptr;   // structural A / B / lxx / luu patterns of the HKD model   // structural lxx patterns of the whole-body knots
   double* d_guess = nullptr; size_t guess_bytes = 0; int guess_B = 0;  // packed initial guesses [B][solution_size] (warm start)  // per-problem reference records [n_records][CAFE_REF_W][ldb]
   double* d_x0raw = nullptr;
   int* d_fail = nullptr; size_t fail_bytes = 0;
@@ -223,7 +225,7 @@ void carve(CafeHandle* H, Carver& cv, size_t& zero_bytes) {
     ph.kkt = cv.take<double>(ph.model == CAFE_MODEL_WB ? h * (size_t)CAFE_KKT_PACK * ldb : 1);
     const bool wb = ph.model == CAFE_MODEL_WB;
     ph.ABpm = cv.take<double>(wb ? h * (size_t)CAFE_WB_AB_TILE * ldb : 2); ph.CDpm = cv.take<double>(wb ? h * (size_t)CAFE_WB_CD_TILE * ldb : 2);
-    ph.Kpm = cv.take<double>(wb ? h * (size_t)CAFE_WB_K_TILE * ldb : 2);
+    ph.Kpm = cv.take<double>(h * (size_t)cafe_dev::ld_mma((int)m) * n * ldb + 2);
     ph.Quu = cv.take<double>(h * m * m * ldb); ph.Qux = cv.take<double>(h * m * n * ldb);
     ph.Xt = cv.take<double>((size_t)NA * (h + 1) * n * ldb); ph.Ut = cv.take<double>((size_t)NA * h * m * ldb);
     ph.Yt = cv.take<double>((size_t)NA * h * p * ldb + 1); ph.Dt = cv.take<double>((size_t)NA * (h + 1) * n * ldb);
@@ -379,6 +381,13 @@ extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, 
     }
     for (int i = 0; i < deck->n_phases; ++i) S.ph[i].lxx_mask = (deck->phase[i].model == CAFE_MODEL_WB && H->d_lxx_mask) ? H->d_lxx_mask + first[i] : nullptr;
   }
+  if (all_hkd) {
+    unsigned long long hm[36];
+    cafe::hkd_lq_patterns(hm);
+    CUDA_OK(cudaMalloc(&H->d_hkd_mask, sizeof(hm)));
+    CUDA_OK(cudaMemcpy(H->d_hkd_mask, hm, sizeof(hm), cudaMemcpyHostToDevice));
+  }
+  for (int i = 0; i < deck->n_phases; ++i) S.ph[i].hkd_mask = (deck->phase[i].model == CAFE_MODEL_HKD) ? H->d_hkd_mask : nullptr;
   CUDA_OK(cudaMalloc(&H->d_x0raw, (size_t)H->ldb * CAFE_MAX_N * sizeof(double)));
   CUDA_OK(cudaMalloc(&H->dS, sizeof(SolverDev)));
   CUDA_OK(cudaMallocHost(&H->h_nactive, 64));
@@ -417,7 +426,7 @@ extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, 
 extern "C" int cafe_gpu_destroy(CafeHandle* H) {
   if (!H) return 0;
   cudaSetDevice(H->device);
-  cudaFree(H->arena); cudaFree(H->d_ref); cudaFree(H->d_ref_pp); cudaFree(H->d_lxx_mask); cudaFree(H->d_guess); cudaFree(H->d_x0raw); cudaFree(H->dS); cudaFree(H->d_pack); cudaFree(H->d_segs);
+  cudaFree(H->arena); cudaFree(H->d_ref); cudaFree(H->d_ref_pp); cudaFree(H->d_lxx_mask); cudaFree(H->d_hkd_mask); cudaFree(H->d_guess); cudaFree(H->d_x0raw); cudaFree(H->dS); cudaFree(H->d_pack); cudaFree(H->d_segs);
   if (H->h_nactive) cudaFreeHost(H->h_nactive);
   if (H->stream) cudaStreamDestroy(H->stream);
   if (H->ev0) cudaEventDestroy(H->ev0);
