@@ -423,10 +423,12 @@ __device__ void sweep_phase2(const SolverDev& S, int pi, int b, int t, bool run,
         const int t0 = SPLIT ? t - NE : t;
         constexpr int nt = SPLIT ? NT - NE : NT;
         if (k > 0) stage(k - 1, t0, nt);
-        double* Quug = ph.Quu + gix(k, M * M, 0, ldb, b);
-        for (int e = t0; e < M * M; e += nt) Quug[(size_t)e * ldb] = sQuu[(e % M) + ldM * (e / M)];
-        double* Quxg = ph.Qux + gix(k, M * N, 0, ldb, b);
-        for (int e = t0; e < M * N; e += nt) Quxg[(size_t)e * ldb] = sQux[(e % M) + ldM * (e / M)];
+        // Quu, Qux leave as whole tiles (problem-major, 16-byte stores): only the result packers read them
+        static_assert(L::oQuu % 2 == 0 && L::oQux % 2 == 0 && (ldM * M) % 2 == 0 && (ldM * N) % 2 == 0, "Quu / Qux tile layout");
+        double2* Quut = reinterpret_cast<double2*>(ph.Quu + ((size_t)b * h + k) * (ldM * M));
+        for (int e = t0; e < ldM * M / 2; e += nt) Quut[e] = reinterpret_cast<const double2*>(sQuu)[e];
+        double2* Quxt = reinterpret_cast<double2*>(ph.Qux + ((size_t)b * h + k) * (ldM * N));
+        for (int e = t0; e < ldM * N / 2; e += nt) Quxt[e] = reinterpret_cast<const double2*>(sQux)[e];
         for (int j = t0; j < M; j += nt) ph.Qu[gix(k, M, j, ldb, b)] = sQu[j];
       }
       if (t < NE) {

@@ -62,7 +62,8 @@ struct PhaseDev {
   const unsigned long long* hkd_mask;
   double *lk, *dsq;                        // [h+1][ldb] per-knot cost (k=h: Phi) and |Defect[k]|^2
   // backward-sweep outputs
-  double *K, *Quu, *Qux;                   // [h][m*n | m*m | m*n][ldb]
+  double *K;                               // [h][m*n][ldb]
+  double *Quu, *Qux;                       // PROBLEM-major tiles [b][h][ld(m) x m | ld(m) x n] (read by the result packers only)
   // line-search trial slots, one per step size
   double *Xt, *Ut, *Yt, *Dt;               // [NA][(h+1)|h][dim][ldb]
   double *cost_t, *feas_t, *ming_t;        // [NA][h+1][ldb]

@@ -28,7 +28,9 @@ namespace cafe { void set_last_error(const std::string& s); }
     }                                                                                        \
   } while (0)
 
-struct PackSeg { const double* src; int knots, nc; long dst; };
+// one array of the packed records. pm_ld > 0: the source is a problem-major tile array [b][pm_h][pm_ld x (nc / pm_rows)] (the sweep's
+// Quu / Qux outputs), element e of a knot = row e % pm_rows, column e / pm_rows; else batch-major [knot][nc][ldb]
+struct PackSeg { const double* src; int knots, nc; long dst; int pm_ld, pm_rows, pm_h; };
 
 struct CafeHandle {
   int device = 0, max_batch = 0, ldb = 0, B = 0, NA = 0;
@@ -100,7 +102,14 @@ __global__ void k_pack(const PackSeg* __restrict__ segs, int nseg, int ldb, int 
   for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total * nb; t += (long)gridDim.x * blockDim.x) {
     const int bb = (int)(t % nb);
     const long e = t / nb;
-    out[(size_t)bb * sol_size + sg.dst + e] = sg.src[(size_t)e * ldb + b0 + bb];
+    double v;
+    if (sg.pm_ld > 0) {
+      const int kk = (int)(e / sg.nc), c = (int)(e % sg.nc);
+      v = sg.src[((size_t)(b0 + bb) * sg.pm_h + kk) * ((size_t)sg.pm_ld * (sg.nc / sg.pm_rows)) + (c % sg.pm_rows) + sg.pm_ld * (c / sg.pm_rows)];
+    } else {
+      v = sg.src[(size_t)e * ldb + b0 + bb];
+    }
+    out[(size_t)bb * sol_size + sg.dst + e] = v;
   }
 }
 
@@ -122,7 +131,7 @@ __global__ void k_unpack(const UnpackSeg* __restrict__ segs, int nseg, int ldb, 
 
 // float32 wire record (MHPC_Command_lcmt field order): one segment = nk knots x w components taken from components
 // [c0, c0+w) of an array with nc_src components per knot, starting at knot k0 of its phase
-struct PackSegF { const double* src; int nc_src, c0, w, k0, nk; long dst; };
+struct PackSegF { const double* src; int nc_src, c0, w, k0, nk; long dst; int pm_ld, pm_rows, pm_h; };   // pm_*: as in PackSeg
 __global__ void k_pack_lcm(const PackSegF* __restrict__ segs, int nseg, int ldb, int nb, long rec_size, float* __restrict__ out) {
   const int s = blockIdx.y;
   if (s >= nseg) return;
@@ -132,7 +141,14 @@ __global__ void k_pack_lcm(const PackSegF* __restrict__ segs, int nseg, int ldb,
     const int bb = (int)(t % nb);
     const long e = t / nb;
     const int kk = (int)(e / sg.w), c = (int)(e % sg.w);
-    out[(size_t)bb * rec_size + sg.dst + e] = (float)sg.src[((size_t)(sg.k0 + kk) * sg.nc_src + sg.c0 + c) * ldb + bb];
+    double v;
+    if (sg.pm_ld > 0) {
+      const int cc = sg.c0 + c;
+      v = sg.src[((size_t)bb * sg.pm_h + sg.k0 + kk) * ((size_t)sg.pm_ld * (sg.nc_src / sg.pm_rows)) + (cc % sg.pm_rows) + sg.pm_ld * (cc / sg.pm_rows)];
+    } else {
+      v = sg.src[((size_t)(sg.k0 + kk) * sg.nc_src + sg.c0 + c) * ldb + bb];
+    }
+    out[(size_t)bb * rec_size + sg.dst + e] = (float)v;
   }
 }
 
@@ -226,7 +242,7 @@ void carve(CafeHandle* H, Carver& cv, size_t& zero_bytes) {
     const bool wb = ph.model == CAFE_MODEL_WB;
     ph.ABpm = cv.take<double>(wb ? h * (size_t)CAFE_WB_AB_TILE * ldb : 2); ph.CDpm = cv.take<double>(wb ? h * (size_t)CAFE_WB_CD_TILE * ldb : 2);
     ph.Kpm = cv.take<double>(h * (size_t)cafe_dev::ld_mma((int)m) * n * ldb + 2);
-    ph.Quu = cv.take<double>(h * m * m * ldb); ph.Qux = cv.take<double>(h * m * n * ldb);
+    ph.Quu = cv.take<double>(h * (size_t)cafe_dev::ld_mma((int)m) * m * ldb + 2); ph.Qux = cv.take<double>(h * (size_t)cafe_dev::ld_mma((int)m) * n * ldb + 2);   // problem-major tiles [b][h][ld(m) x m | n]
     ph.Xt = cv.take<double>((size_t)NA * (h + 1) * n * ldb); ph.Ut = cv.take<double>((size_t)NA * h * m * ldb);
     ph.Yt = cv.take<double>((size_t)NA * h * p * ldb + 1); ph.Dt = cv.take<double>((size_t)NA * (h + 1) * n * ldb);
     ph.cost_t = cv.take<double>((size_t)NA * (h + 1) * ldb); ph.feas_t = cv.take<double>((size_t)NA * (h + 1) * ldb);
@@ -640,9 +656,10 @@ extern "C" int cafe_gpu_get_solution(CafeHandle* H, int b0, int nb, double* sol)
   for (int i = 0; i < H->S.n_phases; ++i) {
     const PhaseDev& ph = H->S.ph[i];
     const int n = ph.n, m = ph.m, p = ph.p, h = ph.h;
-    auto add = [&](const double* src, int knots, int nc) { if (knots * nc > 0) segs.push_back(PackSeg{src, knots, nc, off}); off += (long)knots * nc; };
+    auto add = [&](const double* src, int knots, int nc) { if (knots * nc > 0) segs.push_back(PackSeg{src, knots, nc, off, 0, 0, 0}); off += (long)knots * nc; };
+    auto add_pm = [&](const double* src, int knots, int nc) { if (knots * nc > 0) segs.push_back(PackSeg{src, knots, nc, off, cafe_dev::ld_mma(m), m, h}); off += (long)knots * nc; };
     add(ph.Xbar, h + 1, n); add(ph.Ubar, h, m); add(ph.Y, h, p); add(ph.dU, h, m); add(ph.K, h, m * n);
-    add(ph.Qu, h, m); add(ph.Quu, h, m * m); add(ph.Qux, h, m * n); add(ph.G, h + 1, n);
+    add(ph.Qu, h, m); add_pm(ph.Quu, h, m * m); add_pm(ph.Qux, h, m * n); add(ph.G, h + 1, n);
   }
   return run_pack(H, segs, off, b0, nb, sol);
 }
@@ -664,10 +681,11 @@ static int commands_impl(CafeHandle* H, int n_gain_knots, double* cmd, double* d
   for (int i = 0; i < H->S.n_phases; ++i) {
     const PhaseDev& ph = H->S.ph[i];
     const int n = ph.n, m = ph.m, p = ph.p, h = ph.h;
-    auto add = [&](const double* src, int knots, int nc) { if (knots * nc > 0) segs.push_back(PackSeg{src, knots, nc, off}); off += (long)knots * nc; };
+    auto add = [&](const double* src, int knots, int nc) { if (knots * nc > 0) segs.push_back(PackSeg{src, knots, nc, off, 0, 0, 0}); off += (long)knots * nc; };
+    auto add_pm = [&](const double* src, int knots, int nc) { if (knots * nc > 0) segs.push_back(PackSeg{src, knots, nc, off, cafe_dev::ld_mma(m), m, h}); off += (long)knots * nc; };
     add(ph.Xbar, h + 1, n); add(ph.Ubar, h, m); add(ph.Y, h, p);
     const int g = left < h ? left : h;
-    add(ph.K, g, m * n); add(ph.Qu, g, m); add(ph.Quu, g, m * m); add(ph.Qux, g, m * n);
+    add(ph.K, g, m * n); add(ph.Qu, g, m); add_pm(ph.Quu, g, m * m); add_pm(ph.Qux, g, m * n);
     left -= g;
   }
   return run_pack(H, segs, off, 0, H->B, cmd, dev_out);
@@ -739,11 +757,12 @@ static int lcm_impl(CafeHandle* H, int n_steps, float* out, float* dev_out) {
   for (int i = 0; i < H->S.n_phases && s0 < n_steps; ++i) {
     const PhaseDev& ph = H->S.ph[i];
     const int g = std::min(ph.h, n_steps - s0);
-    auto add = [&](const double* src, int nc_src, int c0, int w, long base) { segs.push_back(PackSegF{src, nc_src, c0, w, 0, g, base + (long)s0 * w}); };
+    auto add = [&](const double* src, int nc_src, int c0, int w, long base) { segs.push_back(PackSegF{src, nc_src, c0, w, 0, g, base + (long)s0 * w, 0, 0, 0}); };
+    auto add_pm = [&](const double* src, int nc_src, int c0, int w, long base) { segs.push_back(PackSegF{src, nc_src, c0, w, 0, g, base + (long)s0 * w, cafe_dev::ld_mma(12), 12, ph.h}); };
     add(ph.Ubar, 12, 0, 12, oTorque);
     add(ph.Xbar, 36, 3, 3, oEul); add(ph.Xbar, 36, 0, 3, oPos); add(ph.Xbar, 36, 6, 12, oQj);
     add(ph.Xbar, 36, 18, 3, oVw); add(ph.Xbar, 36, 21, 3, oEr); add(ph.Xbar, 36, 24, 12, oQjd);
-    add(ph.Y, 12, 0, 12, oGrf); add(ph.K, 432, 0, 432, oFb); add(ph.Qu, 12, 0, 12, oQu); add(ph.Quu, 144, 0, 144, oQuu); add(ph.Qux, 432, 0, 432, oQux);
+    add(ph.Y, 12, 0, 12, oGrf); add(ph.K, 432, 0, 432, oFb); add(ph.Qu, 12, 0, 12, oQu); add_pm(ph.Quu, 144, 0, 144, oQuu); add_pm(ph.Qux, 432, 0, 432, oQux);
     s0 += g;
   }
   const size_t need = (size_t)H->B * rec * sizeof(float);
@@ -789,6 +808,17 @@ extern "C" long cafe_gpu_debug_get(CafeHandle* H, const char* name, int phase, i
   else if (nm == "luu") set(ph.luu, h, m * m); else if (nm == "lyy") set(ph.lyy, h, p * p); else if (nm == "l") set(ph.lk, h + 1, 1);
   else if (nm == "Phix") set(ph.Phix, 1, n); else if (nm == "Phixx") set(ph.Phixx, 1, n * n); else if (nm == "Px") set(ph.Px, 1, (long)nn * n);
   else { cafe::set_last_error("unknown array name"); return CAFE_ERR_ARG; }
+  if (nm == "Quu" || nm == "Qux") {
+    // problem-major tiles [b][h][ld(m) x cols] written by the sweep
+    const int ldm = cafe_dev::ld_mma(m), cols = nm == "Quu" ? m : n;
+    std::vector<double> tl((size_t)h * ldm * cols);
+    if (tl.empty()) return 0;
+    if (cudaMemcpy(tl.data(), src + (size_t)b * h * ldm * cols, tl.size() * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) {
+      cafe::set_last_error("cudaMemcpy failed"); return CAFE_ERR_CUDA;
+    }
+    for (int k = 0; k < h; ++k) for (int j = 0; j < cols; ++j) for (int i = 0; i < m; ++i) out[(size_t)k * m * cols + i + m * j] = tl[((size_t)k * cols + j) * ldm + i];
+    return (long)knots * nc;
+  }
   if (ph.model == CAFE_MODEL_WB && (nm == "A" || nm == "B" || nm == "C" || nm == "D")) {
     // the whole-body linearisation is stored problem-major in the sweep's tile layout (ABpm, CDpm); rows 0..17 of A are the
     // static [I, dt I] pattern kept in the batch-major array
