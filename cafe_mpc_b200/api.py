@@ -178,6 +178,18 @@ class MultiPhaseDDP:
         assert guess.shape[1] == lib.cafe_solution_size(self.problem.deck)
         check(lib.cafe_gpu_set_initial_guess(self._h, guess.ctypes.data_as(C.c_void_p), guess.shape[0]))
 
+    def shift_guess_from(self, prev, prev_k0, k0, B=None):
+        """Warm start from the solution held by the solver `prev` (deck at start offset prev_k0), shifted to this solver's deck (start
+        offset k0) on the device - the receding-horizon update of MHPCProblem::update without a host round trip."""
+        check(lib.cafe_gpu_shift_guess(self._h, prev._h, prev_k0, k0, self.B if B is None else B))
+
+    def planned_state(self, knots_ahead):
+        """[B, n] planned state `knots_ahead` knots after the start of the plan."""
+        n = MODEL_DIMS[self.problem.phases()[0].model][0]
+        out = np.zeros((self.B, n))
+        check(lib.cafe_gpu_get_planned_state(self._h, knots_ahead, out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def get_lcm_commands(self, n_steps=8):
         """float32 MHPC_Command_lcmt record per problem (see include/cafe_gpu.h); use unpack_lcm_command to name the fields."""
         out = np.zeros((self.B, lib.cafe_lcm_command_size(n_steps)), dtype=np.float32)

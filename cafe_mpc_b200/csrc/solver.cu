@@ -129,6 +129,24 @@ __global__ void k_unpack(const UnpackSeg* __restrict__ segs, int nseg, int ldb, 
   }
 }
 
+// Receding-horizon shift on the device: one entry = one knot of one array (Xbar, Ubar or K) of the NEW deck's packed guess record,
+// filled from a knot of the previous solver's arrays (src, batch-major with its own ldb) or, for states of a phase the old plan did
+// not have yet, from the new deck's reference record (ref, optionally per problem). Entries without a source stay zero.
+struct ShiftEntry { const double* src; const double* ref; const double* ref_pp; int src_knot, nc, ref_knot; long dst; };
+__global__ void k_shift_guess(const ShiftEntry* __restrict__ ent, int n_ent, int ldb_src, int ldb_dst, int nb, long sol_size, double* __restrict__ out) {
+  const int s = blockIdx.y;
+  if (s >= n_ent) return;
+  const ShiftEntry e = ent[s];
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < (long)e.nc * nb; t += (long)gridDim.x * blockDim.x) {
+    const int bb = (int)(t % nb), c = (int)(t / nb);
+    double v;
+    if (e.src) v = e.src[((size_t)e.src_knot * e.nc + c) * ldb_src + bb];
+    else if (e.ref_pp) v = e.ref_pp[((size_t)e.ref_knot * CAFE_REF_W + CAFE_REF_XR + c) * ldb_dst + bb];
+    else v = e.ref[(size_t)e.ref_knot * CAFE_REF_W + CAFE_REF_XR + c];
+    out[(size_t)bb * sol_size + e.dst + c] = v;
+  }
+}
+
 // float32 wire record (MHPC_Command_lcmt field order): one segment = nk knots x w components taken from components
 // [c0, c0+w) of an array with nc_src components per knot, starting at knot k0 of its phase
 struct PackSegF { const double* src; int nc_src, c0, w, k0, nk; long dst; int pm_ld, pm_rows, pm_h; };   // pm_*: as in PackSeg
@@ -706,6 +724,110 @@ extern "C" int cafe_gpu_set_initial_guess(CafeHandle* H, const double* guess, in
   CUDA_OK(cudaMemcpy(H->d_guess, guess, need, cudaMemcpyHostToDevice));
   H->guess_B = B;
   return 0;
+}
+
+// ---- receding-horizon warm start without leaving the device: what MHPCProblem::update / update_WB_plan /
+//      update_SRB_plan do to the trajectories (MHPCProblem.cpp:252-397, TrajectoryManagement.cpp:130-228), as a map from the knots of
+//      the new deck (start offset dst_k0) to the knots of the previous plan (start offset src_k0) held by `src`:
+//        * a whole-body phase continues the old phase with the same stance that overlaps it in absolute time (popped knots vanish),
+//        * knots past the old plan's end repeat its last state (push_back_state(X.back())), zero control and gain,
+//        * a phase the old plan did not have starts from the new deck's reference states (zero control and gain),
+//        * the trailing reduced-order phase is kept as it is while its horizon is unchanged (update_SRB_plan: nsteps = 0).
+extern "C" int cafe_gpu_shift_guess(CafeHandle* dst, CafeHandle* src, int src_k0, int dst_k0, int B) {
+  if (!dst || !src || dst == src || B <= 0 || B > dst->max_batch || B > src->B || dst_k0 < src_k0) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
+  if (dst->device != src->device) { cafe::set_last_error("both solvers must live on the same device"); return CAFE_ERR_ARG; }
+  CUDA_OK(cudaSetDevice(dst->device));
+  struct Range { int idx, s, e; int contact[4]; };
+  auto wb_ranges = [](const CafeHandle* H, int k0) {
+    std::vector<Range> out;
+    int s = k0;
+    for (int i = 0; i < H->S.n_phases && H->S.ph[i].model == CAFE_MODEL_WB; ++i) {
+      Range r{i, s, s + H->S.ph[i].h, {0, 0, 0, 0}};
+      for (int f = 0; f < 4; ++f) r.contact[f] = H->S.ph[i].contact[f];
+      out.push_back(r);
+      s += H->S.ph[i].h;
+    }
+    return out;
+  };
+  const std::vector<Range> old_r = wb_ranges(src, src_k0), new_r = wb_ranges(dst, dst_k0);
+  if (old_r.empty()) { cafe::set_last_error("the previous deck has no leading whole-body phase"); return CAFE_ERR_UNSUPPORTED; }
+  const PhaseDev& last = src->S.ph[old_r.back().idx];
+  const int old_end = old_r.back().e;
+  std::vector<ShiftEntry> ent;
+  long off = 0;
+  for (int i = 0; i < dst->S.n_phases; ++i) {
+    const PhaseDev& ph = dst->S.ph[i];
+    const int n = ph.n, m = ph.m, p = ph.p, h = ph.h;
+    const long oX = off, oU = oX + (long)(h + 1) * n, oK = oU + (long)h * m + (long)h * p + (long)h * m;
+    off = oK + (long)h * m * n + (long)h * m + (long)h * m * m + (long)h * m * n + (long)(h + 1) * n;
+    const double* ref = ph.ref; const double* ref_pp = ph.ref_pp;
+    auto x_from = [&](const PhaseDev* sp, int sk, int k) { ent.push_back(ShiftEntry{sp ? sp->Xbar : nullptr, ref, ref_pp, sk, n, k, oX + (long)k * n}); };
+    auto uk_from = [&](const PhaseDev& sp, int sk, int k) {
+      ent.push_back(ShiftEntry{sp.Ubar, nullptr, nullptr, sk, m, 0, oU + (long)k * m});
+      ent.push_back(ShiftEntry{sp.K, nullptr, nullptr, sk, m * n, 0, oK + (long)k * m * n});
+    };
+    if (ph.model != CAFE_MODEL_WB) {
+      const int j = (int)old_r.size() + (i - (int)new_r.size());
+      const bool keep = j >= 0 && j < src->S.n_phases && src->S.ph[j].model == ph.model && src->S.ph[j].h == h;
+      for (int k = 0; k <= h; ++k) { x_from(keep ? &src->S.ph[j] : nullptr, k, k); if (keep && k < h) uk_from(src->S.ph[j], k, k); }
+      continue;
+    }
+    const Range& nr = new_r[i];
+    const Range* sr = nullptr;
+    for (const Range& r : old_r) {
+      bool same = true;
+      for (int f = 0; f < 4; ++f) same = same && r.contact[f] == nr.contact[f];
+      if (same && r.s <= nr.e && r.e >= nr.s) { sr = &r; break; }
+    }
+    const bool continues_last = sr && sr->idx == old_r.back().idx;
+    for (int k = 0; k <= h; ++k) {
+      const int a = nr.s + k;
+      if (sr && sr->s <= a && a <= sr->e) x_from(&src->S.ph[sr->idx], a - sr->s, k);
+      else if (continues_last && a > old_end) x_from(&last, last.h, k);
+      else x_from(nullptr, 0, k);
+      if (k < h && sr && sr->s <= a && a < sr->e) uk_from(src->S.ph[sr->idx], a - sr->s, k);
+    }
+  }
+  const long sol_size = cafe_solution_size(&dst->deck);
+  if (off != sol_size) { cafe::set_last_error("internal: packed record size mismatch"); return CAFE_ERR_ARG; }
+  const size_t need = (size_t)B * (size_t)sol_size * sizeof(double);
+  if (need > dst->guess_bytes) {
+    cudaFree(dst->d_guess); dst->d_guess = nullptr; dst->guess_bytes = 0;
+    CUDA_OK(cudaMalloc(&dst->d_guess, need));
+    dst->guess_bytes = need;
+  }
+  // the previous solve ran on src's stream: order this after it, and later solves of dst after this
+  CUDA_OK(cudaStreamSynchronize(src->stream));
+  cudaStream_t st = dst->stream;
+  CUDA_OK(cudaMemsetAsync(dst->d_guess, 0, need, st));
+  ShiftEntry* d_ent = nullptr;
+  CUDA_OK(cudaMalloc(&d_ent, ent.size() * sizeof(ShiftEntry)));
+  CUDA_OK(cudaMemcpyAsync(d_ent, ent.data(), ent.size() * sizeof(ShiftEntry), cudaMemcpyHostToDevice, st));
+  dim3 grid(64, (unsigned)ent.size());
+  k_shift_guess<<<grid, 256, 0, st>>>(d_ent, (int)ent.size(), src->ldb, dst->ldb, B, sol_size, dst->d_guess);
+  CUDA_OK(cudaStreamSynchronize(st));
+  CUDA_OK(cudaGetLastError());
+  cudaFree(d_ent);
+  dst->guess_B = B;
+  return 0;
+}
+
+// planned state `knots_ahead` knots after the start of the plan (post-reset state at a phase boundary): out [B][n] on the host
+extern "C" int cafe_gpu_get_planned_state(CafeHandle* H, int knots_ahead, double* out) {
+  if (!H || !out || knots_ahead < 0) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
+  CUDA_OK(cudaSetDevice(H->device));
+  int k = knots_ahead;
+  for (int i = 0; i < H->S.n_phases; ++i) {
+    const PhaseDev& ph = H->S.ph[i];
+    if (k < ph.h || ph.model != CAFE_MODEL_WB || i == H->S.n_phases - 1) {
+      if (k > ph.h || ph.n != H->S.ph[0].n) break;
+      std::vector<PackSeg> segs{PackSeg{ph.Xbar + (size_t)k * ph.n * H->ldb, 1, ph.n, 0, 0, 0, 0}};
+      return run_pack(H, segs, ph.n, 0, H->B, out);
+    }
+    k -= ph.h;
+  }
+  cafe::set_last_error("beyond the plan");
+  return CAFE_ERR_ARG;
 }
 
 // ---- per-problem references with a shared contact schedule: every problem tracks its own records

@@ -49,6 +49,8 @@ def _load():
     lib.cafe_gpu_get_solution.argtypes = [vp, C.c_int, C.c_int, vp]
     lib.cafe_gpu_get_commands.argtypes = [vp, C.c_int, vp]
     lib.cafe_gpu_get_commands_device.argtypes = [vp, C.c_int, vp]
+    lib.cafe_gpu_shift_guess.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
+    lib.cafe_gpu_get_planned_state.argtypes = [vp, C.c_int, vp]
     lib.cafe_gpu_get_solve_ms.argtypes = [vp, dp]
     lib.cafe_gpu_get_timing.argtypes = [vp, C.POINTER(C.c_double * CAFE_NKERNELS), C.POINTER(C.c_long * CAFE_NKERNELS), ip]
     lib.cafe_gpu_set_profiling.argtypes = [vp, C.c_int]
@@ -71,6 +73,6 @@ EXPORTED = [
     "cafe_deck_free", "cafe_hkd_state", "cafe_solution_size", "cafe_command_size", "cafe_gpu_create",
     "cafe_gpu_destroy", "cafe_gpu_solve_batch", "cafe_gpu_solve_batch_device", "cafe_gpu_get_info",
     "cafe_gpu_get_history", "cafe_gpu_get_trace", "cafe_gpu_get_solution", "cafe_gpu_get_commands", "cafe_gpu_get_commands_device", "cafe_gpu_get_solve_ms",
-    "cafe_gpu_set_references", "cafe_gpu_set_initial_guess", "cafe_lcm_command_size", "cafe_gpu_get_lcm_commands", "cafe_gpu_get_lcm_commands_device",
+    "cafe_gpu_set_references", "cafe_gpu_set_initial_guess", "cafe_gpu_shift_guess", "cafe_gpu_get_planned_state", "cafe_lcm_command_size", "cafe_gpu_get_lcm_commands", "cafe_gpu_get_lcm_commands_device",
     "cafe_gpu_get_timing", "cafe_gpu_set_profiling", "cafe_gpu_debug_get", "cafe_gpu_measure_fp64_peak",
 ]

@@ -79,6 +79,15 @@ int cafe_gpu_set_references(CafeHandle* h, const double* refs, int B);
  * behind (MHPCProblem.cpp:252-397): MultiPhaseDDP::solve begins with hybrid_rollout(eps = 0), U = Ubar + K (X - Xbar), around
  * them (MultiPhaseDDP.cpp:238). Stays in force for the following solves; guess = NULL returns to the cold start. */
 int cafe_gpu_set_initial_guess(CafeHandle* h, const double* guess, int B);
+/* The same warm start without leaving the device: the guess of `dst` (deck at start offset dst_k0 of the reference file) is built from
+ * the solution held by `src` (deck at start offset src_k0 <= dst_k0, same device, solved with at least B problems) by the shift
+ * MHPCProblem::update applies to the trajectories (MHPCProblem.cpp:252-397; Trajectory::pop_front / push_back_state,
+ * TrajectoryManagement.cpp:130-228): popped knots vanish, a phase continues the old phase with the same stance, knots past the old
+ * plan repeat its last state with zero control and gain, a new phase starts from the reference, the reduced-order tail is kept. */
+int cafe_gpu_shift_guess(CafeHandle* dst, CafeHandle* src, int src_k0, int dst_k0, int B);
+/* Planned state `knots_ahead` knots after the start of the plan, out [B][n] (host): the state an MPC loop hands to the next solve
+ * (MHPCLocomotion::update takes it from the simulator; a closed-loop Monte-Carlo without one uses the plan's own prediction). */
+int cafe_gpu_get_planned_state(CafeHandle* h, int knots_ahead, double* out);
 /* x0: host [B][n0] row per problem. Runs every problem of the batch to its own termination. */
 int cafe_gpu_solve_batch(CafeHandle* h, const double* x0, int B, const CafeOptions* opt);
 /* same with x0 already resident on the device, layout [n0][ldb] (component-major), ldb >= B */

@@ -279,3 +279,40 @@ def test_receding_horizon_warm_start_matches_oracle(cm, opt):
         cold = s1.get_solver_info()
         assert all(info[b]["feas"] < 0.2 * cold[b]["feas"] for b in range(B))
         prob, k0, sol = p1, k1, sol1
+
+
+@pytest.mark.gpu
+def test_device_shift_equals_host_shift(cm, opt):
+    """the receding-horizon shift done on the device (cafe_gpu_shift_guess: previous solver's arrays -> packed guess of the
+    next deck) is the same data movement as cafe_mpc_b200/mpc.py on the host: identical warm-started solves, bit for bit, over a chain
+    that removes a phase at the front and opens one at the tail; cafe_gpu_get_planned_state == mpc.state_at."""
+    from cafe_mpc_b200 import mpc, workload
+    ort = copy.copy(opt)
+    ort.max_AL_iter = opt.max_AL_iter_runtime; ort.max_DDP_iter = opt.max_DDP_iter_runtime
+    B, k0 = 6, 8
+    prob = cm.MHPCProblem(CSV, k0=k0)
+    x0 = workload.mhpc_batch(B)
+    s = solve_gpu(cm, prob, opt, x0)
+    for step in range(3):
+        k1 = k0 + 2
+        p1 = cm.MHPCProblem(CSV, k0=k1)
+        sol = s.get_solution()
+        x1_host = mpc.state_at(prob, mpc.unpack_batch(prob, sol), 2)
+        x1 = s.planned_state(2)
+        assert np.array_equal(x1, x1_host), step
+        x1 = x1 + 1e-3 * (x0 - x0[0])
+        # host path
+        sh = cm.MultiPhaseDDP(p1, 0, B)
+        sh.set_initial_condition(x1)
+        sh.set_initial_guess(mpc.shifted_guess_batch(prob, k0, p1, k1, sol))
+        sh.solve(ort)
+        # device path
+        sd = cm.MultiPhaseDDP(p1, 0, B)
+        sd.set_initial_condition(x1)
+        sd.shift_guess_from(s, k0, k1)
+        sd.solve(ort)
+        ih, idv = sh.get_solver_info(), sd.get_solver_info()
+        assert [[i[k] for k in COUNTS] for i in ih] == [[i[k] for k in COUNTS] for i in idv], step
+        assert np.array_equal(sh.get_solution(), sd.get_solution()), step
+        sh.close(); s.close()
+        s, prob, k0 = sd, p1, k1

@@ -2,7 +2,9 @@
 initialisation caps, then `steps` MPC updates: shift the plan by dt_mpc / dt_wb = 2 knots, warm start from the previous solution
 (cafe_mpc_b200/mpc.py), re-solve under the run-time caps (max_AL_iter_runtime x max_DDP_iter_runtime, MHPCLocomotion.cpp:86-87).
 The "measured" state of the next step is the plan's own prediction two knots ahead plus a small disturbance (no simulator here).
-Prints one JSON line per step. usage: mpc_loop.py [B] [steps] [k0]"""
+Prints one JSON line per step. usage: mpc_loop.py [B] [steps] [k0] [host|device]
+"device": the shift runs on the GPU (cafe_gpu_shift_guess from the previous solver's arrays, cafe_gpu_get_planned_state for the next
+initial state); "host": D2H of the packed solutions, numpy shift (cafe_mpc_b200/mpc.py), H2D of the guess."""
 import copy, json, os, sys, time
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, R)
@@ -13,6 +15,7 @@ from cafe_mpc_b200 import mpc, workload
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 k0 = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+mode = sys.argv[4] if len(sys.argv) > 4 else "device"
 csv = os.path.join(R, "data/Reference/Data/trot/heuristic/quad_reference.csv")
 opt = cm.load_hsddp_setting(os.path.join(R, "data/MHPC/settings/ddp_setting.info"))
 ort = copy.copy(opt)
@@ -28,26 +31,38 @@ s.solve(opt)
 info = s.get_solver_info()
 print(json.dumps({"step": 0, "k0": k0, "phases": [p.horizon for p in prob.phases()], "solve_ms": round(s.solve_ms(), 2), "solves_per_s": round(B / s.solve_ms() * 1e3, 1),
                   "mean_iter": sum(i["iter"] for i in info) / B, "mean_cost": float(np.mean([i["cost"] for i in info])), "max_feas": max(i["feas"] for i in info)}), flush=True)
-sol = s.get_solution()
+sol = s.get_solution() if mode == "host" else None
 for step in range(1, steps + 1):
     t0 = time.perf_counter()
     k1 = k0 + 2
     p1 = cm.MHPCProblem(csv, k0=k1)
-    guess = mpc.shifted_guess_batch(prob, k0, p1, k1, sol)
-    x1 = mpc.state_at(prob, mpc.unpack_batch(prob, sol), 2) + noise
-    t1 = time.perf_counter()
-    s.close()
-    s = cm.MultiPhaseDDP(p1, 0, B)
-    s.set_initial_condition(x1)
-    s.set_initial_guess(guess)
+    if mode == "host":
+        guess = mpc.shifted_guess_batch(prob, k0, p1, k1, sol)
+        x1 = mpc.state_at(prob, mpc.unpack_batch(prob, sol), 2) + noise
+        t1 = time.perf_counter()
+        s.close()
+        s = cm.MultiPhaseDDP(p1, 0, B)
+        s.set_initial_condition(x1)
+        s.set_initial_guess(guess)
+    else:
+        x1 = s.planned_state(2) + noise
+        s1 = cm.MultiPhaseDDP(p1, 0, B)
+        s1.set_initial_condition(x1)
+        s1.shift_guess_from(s, k0, k1)
+        t1 = time.perf_counter()
+        s.close()
+        s = s1
     t2 = time.perf_counter()
     s.solve(ort)
     ms = s.solve_ms()
     info = s.get_solver_info()
-    sol = s.get_solution()
+    if mode == "host":
+        sol = s.get_solution()
+    else:
+        cmd = s.get_lcm_commands(8)   # what the controller consumes (float32 MHPC_Command_lcmt fields)
     t3 = time.perf_counter()
-    print(json.dumps({"step": step, "k0": k1, "phases": [p.horizon for p in p1.phases()], "solve_ms": round(ms, 2), "solves_per_s": round(B / ms * 1e3, 1),
+    print(json.dumps({"step": step, "mode": mode, "k0": k1, "phases": [p.horizon for p in p1.phases()], "solve_ms": round(ms, 2), "solves_per_s": round(B / ms * 1e3, 1),
                       "mean_iter": sum(i["iter"] for i in info) / B, "mean_cost": float(np.mean([i["cost"] for i in info])),
-                      "max_feas": max(i["feas"] for i in info), "host_shift_ms": round(1e3 * (t1 - t0), 1), "handle_and_upload_ms": round(1e3 * (t2 - t1), 1),
-                      "solve_and_readback_ms": round(1e3 * (t3 - t2), 1)}), flush=True)
+                      "max_feas": max(i["feas"] for i in info), "shift_ms": round(1e3 * (t1 - t0), 1), "handle_and_upload_ms": round(1e3 * (t2 - t1), 1),
+                      "solve_and_readback_ms": round(1e3 * (t3 - t2), 1), "step_wall_ms": round(1e3 * (t3 - t0), 1)}), flush=True)
     prob, k0 = p1, k1
