@@ -84,6 +84,25 @@ extern "C" int cafe_hkd_state(const double body[12], const double qJ[12], const 
   return 0;
 }
 
+extern "C" int cafe_deck_lq_pattern(const CafeDeck* deck, int phase, int knot, int which, unsigned long long* out) {
+  if (!deck || !out || phase < 0 || phase >= deck->n_phases || knot < 0 || knot >= deck->phase[phase].horizon || which < 0 || which > 3) {
+    cafe::set_last_error("bad argument"); return CAFE_ERR_ARG;
+  }
+  const int model = deck->phase[phase].model;
+  if (model == CAFE_MODEL_HKD) {
+    unsigned long long hm[36];
+    cafe::hkd_lq_patterns(hm);
+    for (int i = 0; i < 9; ++i) out[i] = hm[9 * which + i];
+    return 9;
+  }
+  if (model == CAFE_MODEL_WB && which == 2) {
+    cafe::wb_lxx_pattern(deck->ref + ((size_t)deck->phase[phase].knot_offset + knot) * CAFE_REF_W, out);
+    return 21;
+  }
+  cafe::set_last_error("no structural pattern is kept for this array of this model");
+  return CAFE_ERR_UNSUPPORTED;
+}
+
 extern "C" long cafe_solution_size(const CafeDeck* deck) {
   long s = 0;
   for (int i = 0; i < deck->n_phases; ++i) {

@@ -13,6 +13,22 @@
 
 namespace cafe {
 
+void wb_lxx_pattern(const double* rec, unsigned long long out[21]) {
+  for (int i = 0; i < 21; ++i) out[i] = 0;
+  auto setbit = [&](int r, int c) { const int e = r + 36 * c; out[e >> 6] |= 1ULL << (e & 63); };
+  for (int d = 0; d < 36; ++d) setbit(d, d);
+  const int base[9] = {3, 4, 5, 18, 19, 20, 21, 22, 23};
+  for (int a = 0; a < 9; ++a) for (int c = 0; c < 9; ++c) setbit(base[a], base[c]);
+  for (int f = 0; f < 4; ++f) {
+    int cols[15];
+    for (int a = 0; a < 3; ++a) { cols[a] = 3 + a; cols[3 + a] = 6 + 3 * f + a; cols[12 + a] = 24 + 3 * f + a; }
+    for (int a = 0; a < 6; ++a) cols[6 + a] = 18 + a;
+    const int nc = rec[CAFE_REF_CONTACT + f] > 0 ? 6 : 15;
+    for (int a = 0; a < nc; ++a) for (int c = 0; c < nc; ++c) setbit(cols[a], cols[c]);
+  }
+}
+
+
 void loadMHPCConfig(const std::string& fname, MHPCConfig& c) {
   InfoFile pt(fname);
   c.plan_dur_wb = (float)pt.num("config.plan_dur_wb");  // the config fields are floats (MHPCProblem.h:45-57)

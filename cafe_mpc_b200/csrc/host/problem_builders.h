@@ -68,6 +68,11 @@ class MHPCProblem {  // MHPCProblem.h:169-289
 // A and B are the CCS patterns of the generated hkinodyn_par (recorded by running it with index-collecting store functors), lxx and
 // luu follow HKDModel::lq_knot (model_hkd.cuh). The backward sweep fetches only these entries.
 void hkd_lq_patterns(unsigned long long out[36]);
+// Structural non-zero pattern of the whole-body lxx of one running knot as a 1296-bit mask (bit i + 36 j, 21 words), from the contact
+// flags of the knot's reference record `rec` (CAFE_REF_W doubles): the rule of WBModel::lq_knot (model_wb.cuh) = MHPCCost.cpp's cost
+// objects: the diagonal, the base block {3,4,5,18..23}^2 shared by the feet, and per foot {3,4,5, own leg q}^2 in stance or
+// {3,4,5, own leg q, 18..23, own leg v}^2 in swing.
+void wb_lxx_pattern(const double* rec, unsigned long long out[21]);
 // compute_hkd_state (HKDModel.h:66-96): qdummy from joint angles (swing) or foot FK (stance)
 void compute_hkd_state(const double eul[3], const double pos[3], const double qJ[12], double qdummy[12], const int contact[4]);
 

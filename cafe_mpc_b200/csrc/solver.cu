@@ -384,28 +384,15 @@ extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, 
   CUDA_OK(cudaMemcpy(H->d_ref, H->ref_host.data(), H->ref_host.size() * sizeof(double), cudaMemcpyHostToDevice));
   for (int i = 0; i < deck->n_phases; ++i) { S.ph[i].ref = H->d_ref + (size_t)deck->phase[i].knot_offset * CAFE_REF_W; S.ph[i].ref_pp = nullptr; }
   {
-    // structural pattern of the whole-body lxx per knot (WBModel::lq_knot): the diagonal, the base block {3,4,5,18..23}^2 shared by
-    // the feet, and per foot {3,4,5, own leg q}^2 in stance or {3,4,5, own leg q, 18..23, own leg v}^2 in swing, the stance flag
-    // being the contact flag of the knot's reference record
+    // structural pattern of the whole-body lxx per knot (cafe::wb_lxx_pattern, host/mhpc_problem.cpp)
     std::vector<unsigned long long> masks;
     std::vector<size_t> first(deck->n_phases, 0);
     for (int i = 0; i < deck->n_phases; ++i) {
       first[i] = masks.size();
       if (deck->phase[i].model != CAFE_MODEL_WB) continue;
       for (int k = 0; k < deck->phase[i].horizon; ++k) {
-        unsigned long long w[CAFE_LXX_MASK_WORDS] = {0};
-        auto setbit = [&](int r, int c) { const int e = r + 36 * c; w[e >> 6] |= 1ULL << (e & 63); };
-        for (int d = 0; d < 36; ++d) setbit(d, d);
-        const int base[9] = {3, 4, 5, 18, 19, 20, 21, 22, 23};
-        for (int a = 0; a < 9; ++a) for (int c = 0; c < 9; ++c) setbit(base[a], base[c]);
-        const double* rec = H->ref_host.data() + ((size_t)deck->phase[i].knot_offset + k) * CAFE_REF_W;
-        for (int f = 0; f < 4; ++f) {
-          int cols[15];
-          for (int a = 0; a < 3; ++a) { cols[a] = 3 + a; cols[3 + a] = 6 + 3 * f + a; cols[12 + a] = 24 + 3 * f + a; }
-          for (int a = 0; a < 6; ++a) cols[6 + a] = 18 + a;
-          const int nc = rec[CAFE_REF_CONTACT + f] > 0 ? 6 : 15;
-          for (int a = 0; a < nc; ++a) for (int c = 0; c < nc; ++c) setbit(cols[a], cols[c]);
-        }
+        unsigned long long w[CAFE_LXX_MASK_WORDS];
+        cafe::wb_lxx_pattern(H->ref_host.data() + ((size_t)deck->phase[i].knot_offset + k) * CAFE_REF_W, w);
         masks.insert(masks.end(), w, w + CAFE_LXX_MASK_WORDS);
       }
     }

@@ -33,6 +33,7 @@ def _load():
     lib.cafe_deck_free.argtypes = [vp]
     lib.cafe_deck_free.restype = None
     lib.cafe_hkd_state.argtypes = [dp, dp, ip, dp]
+    lib.cafe_deck_lq_pattern.argtypes = [C.POINTER(Deck), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_ulonglong)]
     lib.cafe_solution_size.restype = C.c_long
     lib.cafe_solution_size.argtypes = [C.POINTER(Deck)]
     lib.cafe_command_size.restype = C.c_long
@@ -70,7 +71,7 @@ def check(rc):
 
 EXPORTED = [
     "cafe_last_error", "cafe_options_load", "cafe_deck_build_hkd", "cafe_deck_build_mhpc", "cafe_deck_get",
-    "cafe_deck_free", "cafe_hkd_state", "cafe_solution_size", "cafe_command_size", "cafe_gpu_create",
+    "cafe_deck_free", "cafe_hkd_state", "cafe_deck_lq_pattern", "cafe_solution_size", "cafe_command_size", "cafe_gpu_create",
     "cafe_gpu_destroy", "cafe_gpu_solve_batch", "cafe_gpu_solve_batch_device", "cafe_gpu_get_info",
     "cafe_gpu_get_history", "cafe_gpu_get_trace", "cafe_gpu_get_solution", "cafe_gpu_get_commands", "cafe_gpu_get_commands_device", "cafe_gpu_get_solve_ms",
     "cafe_gpu_set_references", "cafe_gpu_set_initial_guess", "cafe_gpu_shift_guess", "cafe_gpu_get_planned_state", "cafe_lcm_command_size", "cafe_gpu_get_lcm_commands", "cafe_gpu_get_lcm_commands_device",

@@ -54,6 +54,12 @@ int cafe_deck_build_mhpc(const char* reference_csv, const char* mhpc_config_info
                          int k0, CafeDeckHandle** out);
 const CafeDeck* cafe_deck_get(const CafeDeckHandle* h);
 void cafe_deck_free(CafeDeckHandle* h);
+/* Structural non-zero pattern the backward sweep assumes for one LQ array of a running knot, as a bit mask (bit i + rows * j):
+ * which = 0 A, 1 B, 2 lxx, 3 luu. HKD phases: all four (576 bits, 9 words; A / B are the CCS patterns of the generated
+ * hkinodyn_par, HKDModel.h:33-61); whole-body phases: lxx only (1296 bits, 21 words; MHPCCost.cpp's cost objects + the ReB terms).
+ * Returns the number of 64-bit words written (out holds at least 21), < 0 on error. Entries outside the pattern are never read
+ * by the sweep: tests check the oracle's arrays against these masks. */
+int cafe_deck_lq_pattern(const CafeDeck* deck, int phase, int knot, int which, unsigned long long* out);
 /* x0 = [body(12) = eul,pos,omega,vel ; qdummy(12)] from joint angles */
 int cafe_hkd_state(const double body[12], const double qJ[12], const int contact[4], double x0[24]);
 

@@ -310,3 +310,52 @@ def test_receding_horizon_shift_and_oracle_warm_start(cm, mhpc_options):
     iw, _, _, _ = oracle_solve(p1.deck, ort, x1, guess=packed)
     ic, _, _, _ = oracle_solve(p1.deck, ort, x1)
     assert iw["iter"] <= 4 and ic["iter"] <= 4 and iw["feas"] < 0.2 * ic["feas"]
+
+
+def _mask_bits(words, rows, cols):
+    """[rows, cols] boolean matrix from a column-major bit mask (bit i + rows * j)."""
+    m = np.zeros((rows, cols), dtype=bool)
+    for e in range(rows * cols):
+        if (int(words[e >> 6]) >> (e & 63)) & 1:
+            m[e % rows, e // rows] = True
+    return m
+
+
+def _pattern(cm, prob, phase, knot, which, rows, cols):
+    from cafe_mpc_b200.lib import lib
+    out = (C.c_ulonglong * 21)()
+    n = lib.cafe_deck_lq_pattern(prob.deck, phase, knot, which, out)
+    assert n > 0
+    return _mask_bits(list(out), rows, cols)
+
+
+@pytest.mark.parametrize("k0", [0, 20])
+def test_structural_lxx_patterns_cover_the_oracle(cm, mhpc_options, k0):
+    """The backward sweep fetches the whole-body lxx only at the structural non-zeros of cafe_deck_lq_pattern (diagonal, base block,
+    per-foot blocks from the knot's contact flags). Safety net: every non-zero the oracle produces (tracking, foot placement, swing-foot
+    position / velocity costs, ReB joint-limit and height terms) lies inside the mask of its knot - in the stance / swing mixes of both
+    whole-body phases and after an impact - and luu is diagonal, lyy block diagonal per foot, as the sweep assumes."""
+    import copy
+    from cafe_mpc_b200 import workload
+    prob = cm.MHPCProblem(CSV, k0=k0)
+    o1 = copy.copy(mhpc_options)
+    o1.max_DDP_iter = 2; o1.max_AL_iter = 1; o1.cost_thresh = 1e30; o1.dynamics_feas_thresh = 1e30
+    x0 = workload.mhpc_batch(3)[2]
+    oracle_solve(prob.deck, o1, x0)
+    from oracle_bindings import oracle_get
+    for ph, p in enumerate(prob.phases()):
+        if p.model != 1:
+            continue
+        lxx = oracle_get("lxx", ph).reshape(p.horizon, 36, 36).transpose(0, 2, 1)   # column-major per knot -> [k][i][j]
+        luu = oracle_get("luu", ph).reshape(p.horizon, 12, 12)
+        lyy = oracle_get("lyy", ph).reshape(p.horizon, 12, 12)
+        nnz = []
+        for k in range(p.horizon):
+            mask = _pattern(cm, prob, ph, k, 2, 36, 36)
+            assert np.array_equal(mask, mask.T)
+            assert not np.any((lxx[k] != 0) & ~mask), (ph, k, np.argwhere((lxx[k] != 0) & ~mask)[:4])
+            nnz.append(int(mask.sum()))
+            assert np.count_nonzero(luu[k] - np.diag(np.diag(luu[k]))) == 0
+            blk = np.kron(np.eye(4), np.ones((3, 3))) > 0
+            assert not np.any((lyy[k] != 0) & ~blk)
+        assert 100 < min(nnz) and max(nnz) < 750   # a third to a half of the 1296 entries

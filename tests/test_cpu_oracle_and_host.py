@@ -261,3 +261,33 @@ def test_cpp_host_mirror_compiles_and_fails_loudly_without_gpu(cm, tmp_path):
         assert r.returncode == 0 and "solved 8 MHPC problems" in r.stdout
     else:
         assert r.returncode == 1 and "no CUDA device" in r.stderr
+
+
+def test_structural_hkd_patterns_cover_the_oracle(cm):
+    """HKD: the sweep stages A, B, lxx, luu only at the structural non-zeros of cafe_deck_lq_pattern. A / B are the CCS patterns of the
+    reference's generated hkinodyn_par (86 and 60 entries, HKDModel.h:33-61), lxx the diagonal + foot-placement couplings, luu one 3x3
+    GRF block per leg + the joint-velocity diagonal. Every non-zero of the oracle's arrays (reference CasADi code) lies inside them."""
+    import copy
+    from cafe_mpc_b200 import workload
+    from cafe_mpc_b200.lib import lib
+    from oracle_bindings import oracle_get, oracle_solve
+    prob = cm.HKDProblem(os.path.join(REPO, "data/Reference/Data/trot/heuristic/quad_reference.csv"))
+    opt = cm.load_hsddp_setting(os.path.join(REPO, "data/HKDMPC/settings/ddp_setting.info"))
+    o1 = copy.copy(opt)
+    o1.max_DDP_iter = 2; o1.max_AL_iter = 1; o1.cost_thresh = 1e30; o1.dynamics_feas_thresh = 1e30
+    oracle_solve(prob.deck, o1, workload.hkd_batch(prob, 3)[2])
+    masks = []
+    for which in range(4):
+        out = (C.c_ulonglong * 21)()
+        assert lib.cafe_deck_lq_pattern(prob.deck, 0, 0, which, out) == 9
+        m = np.zeros((24, 24), dtype=bool)
+        for e in range(576):
+            if (int(out[e >> 6]) >> (e & 63)) & 1:
+                m[e % 24, e // 24] = True
+        masks.append(m)
+    assert [int(m.sum()) for m in masks] == [86, 60, 40, 48]
+    for ph, p in enumerate(prob.phases()):
+        for which, name in enumerate(("A", "B", "lxx", "luu")):
+            arr = oracle_get(name, ph).reshape(p.horizon, 24, 24).transpose(0, 2, 1)
+            bad = (arr != 0) & ~masks[which][None]
+            assert not bad.any(), (name, ph, np.argwhere(bad)[:4])
