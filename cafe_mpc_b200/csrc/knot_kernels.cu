@@ -13,7 +13,7 @@ void launch_roll(const SolverDev* dS, int n_knots, cudaStream_t st, int a0, int 
 }
 void launch_lq(const SolverDev* dS, int n_knots, cudaStream_t st, const int* list, int n_list) {
   if (n_list <= 0) return;
-  const long long nthreads = (long long)((n_list + 31) & ~31) * n_knots;
+  const long long nthreads = (long long)((n_list + 127) & ~127) * n_knots;
   k_lq<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(dS, list, n_list);
 }
 void launch_compact(const SolverDev* dS, cudaStream_t st, int mode) { k_compact<<<1, 1024, 0, st>>>(dS, mode); }

@@ -185,10 +185,11 @@ __device__ void lq_knot_generic(const SolverDev& S, int pi, int k, int b) {
   }
 }
 
+// the list is padded to a multiple of the CTA size: one knot per CTA (the whole-body pieces run in lock step, model_wb.cuh)
 __global__ void __launch_bounds__(128, CAFE_KNOT_MINB) k_lq(const SolverDev* __restrict__ Sp, const int* __restrict__ list, int n_list) {
   const SolverDev& S = *Sp;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int ldj = (n_list + 31) & ~31;
+  const int ldj = (n_list + 127) & ~127;
   const int j = (int)(t % ldj);
   const int gk = (int)(t / ldj);
   if (gk >= S.n_knots || j >= n_list) return;

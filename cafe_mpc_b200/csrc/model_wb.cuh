@@ -27,6 +27,12 @@ __device__ void wbg_rnea_derivs(const double* q, const double* v, const double* 
 __device__ void wbg_grav_derivs(const double* q, double* dq);
 __device__ void wbg_kin_partials(const double* q, const double* v, const double* a, const double* F, double* dvq, double* daq, double* dav, double* djtf, size_t st);
 __device__ void wbg_footvel_partial(const double* q, const double* v, double* dvq);
+#ifndef CAFE_LQ_LOCKSTEP
+#define CAFE_LQ_LOCKSTEP 1
+#endif
+__device__ void wbg_terms_lockstep(const double* q, const double* v, double* nle, double* Mlow, double* J, double* gam, double* pf, double* vf);
+__device__ void wbg_rnea_derivs_lockstep(const double* q, const double* v, const double* a, double* dq, double* dv, size_t st);
+__device__ void wbg_kin_partials_lockstep(const double* q, const double* v, const double* a, const double* F, double* dvq, double* daq, double* dav, double* djtf, size_t st);
 
 struct WBScratch {
   double L[324];   // M (lower) then its Cholesky factor, column-major, ld 18
@@ -70,10 +76,13 @@ struct WBModel {
   }
 
   // M, nle, J, Jdot v, foot positions and velocities at (q, v); Cholesky of M; Y = L^-1 Jc^T; S = Y^T Y
+  // LOCK: the caller guarantees that every live thread of the CTA is here (running knots in k_roll / k_lq): lock-step pieces
+  template <bool LOCK = false>
   __device__ static void kkt_setup(const double* x, WBScratch& s, double damping) {
     for (int i = 0; i < 324; ++i) s.L[i] = 0;
     for (int i = 0; i < 216; ++i) s.J[i] = 0;
-    wbg_terms(x, x + 18, s.nle, s.L, s.J, s.gam, s.pf, s.vf);
+    if (LOCK && CAFE_LQ_LOCKSTEP) wbg_terms_lockstep(x, x + 18, s.nle, s.L, s.J, s.gam, s.pf, s.vf);
+    else wbg_terms(x, x + 18, s.nle, s.L, s.J, s.gam, s.pf, s.vf);
     chol_inplace(s.L, 18, 18);
     const int nr = s.nr;
     for (int c = 0; c < nr; ++c) {
@@ -91,9 +100,10 @@ struct WBModel {
   }
 
   // KKTContactDynamics (WBM.cpp:368-424): qdd, GRF for the phase contact set
+  template <bool LOCK = false>
   __device__ static void forward(const PhaseDev& ph, const double* x, const double* u, WBScratch& s) {
     active_rows(ph.contact, s);
-    kkt_setup(x, s, 1e-12);
+    kkt_setup<LOCK>(x, s, 1e-12);
     double b[18];
     for (int i = 0; i < 18; ++i) b[i] = ((i >= 6) ? u[i - 6] : 0.0) - s.nle[i];
     double mb[18];
@@ -238,7 +248,7 @@ struct WBModel {
     (void)y_unused;
     const double dt = ph.dt;
     WBScratch s;
-    forward(ph, x, u, s);
+    forward(ph, x, u, s);   // (lock-step wbg_terms measured no gain: the 7.4 k-op pieces fit the instruction cache)
     const int nr = s.nr;
     // S without damping for the sensitivities (computeKKTContactDynamicMatrixInverse, WBM.cpp:467)
     double Ls0[144];
@@ -251,8 +261,14 @@ struct WBModel {
     //      The generated routines store their static non-zero patterns directly into the batch-major array (coalesced).
     double* kk = ph.kkt + gix(k, CAFE_KKT_PACK, 0, ldb, b);
     const size_t st = (size_t)ldb;
+#if CAFE_LQ_LOCKSTEP
+    // k_lq guarantees that every live thread of the CTA is here (one running whole-body knot per CTA): lock-step pieces
+    wbg_rnea_derivs_lockstep(x, x + 18, s.qdd, kk + CAFE_KKT_RQ * st, kk + CAFE_KKT_RV * st, st);
+    wbg_kin_partials_lockstep(x, x + 18, s.qdd, s.grf, kk + CAFE_KKT_DVQ * st, kk + CAFE_KKT_AQ * st, kk + CAFE_KKT_AV * st, kk + CAFE_KKT_JTF * st, st);
+#else
     wbg_rnea_derivs(x, x + 18, s.qdd, kk + CAFE_KKT_RQ * st, kk + CAFE_KKT_RV * st, st);
     wbg_kin_partials(x, x + 18, s.qdd, s.grf, kk + CAFE_KKT_DVQ * st, kk + CAFE_KKT_AQ * st, kk + CAFE_KKT_AV * st, kk + CAFE_KKT_JTF * st, st);
+#endif
     for (int i = 0; i < 324; ++i) kk[(CAFE_KKT_L + i) * st] = s.L[i];
     for (int i = 0; i < 216; ++i) { kk[(CAFE_KKT_Y + i) * st] = s.Y[i]; kk[(CAFE_KKT_J + i) * st] = s.J[i]; }
     for (int i = 0; i < 144; ++i) kk[(CAFE_KKT_LS + i) * st] = Ls0[i];

@@ -23,6 +23,15 @@ __device__ void wbg_terms(const double* q, const double* v, double* nle, double*
   wbg_terms_leg0(q, v, nle, Mlow, J, gam, pf, vf); wbg_terms_leg1(q, v, nle, Mlow, J, gam, pf, vf);
   wbg_terms_leg2(q, v, nle, Mlow, J, gam, pf, vf); wbg_terms_leg3(q, v, nle, Mlow, J, gam, pf, vf);
 }
+// lock-step variant (see wbg_rnea_derivs_lockstep): every live thread of the CTA evaluates a running knot of the same phase
+__device__ void wbg_terms_lockstep(const double* q, const double* v, double* nle, double* Mlow, double* J, double* gam, double* pf, double* vf) {
+  for (int i = 0; i < 6; ++i) nle[i] = 0.0;
+  __syncthreads(); wbg_terms_trunk(q, v, nle, Mlow);
+  __syncthreads(); wbg_terms_leg0(q, v, nle, Mlow, J, gam, pf, vf);
+  __syncthreads(); wbg_terms_leg1(q, v, nle, Mlow, J, gam, pf, vf);
+  __syncthreads(); wbg_terms_leg2(q, v, nle, Mlow, J, gam, pf, vf);
+  __syncthreads(); wbg_terms_leg3(q, v, nle, Mlow, J, gam, pf, vf);
+}
 __device__ __noinline__ void wbg_feet(const double* q, const double* v, double* pf, double* vf, double* J) {
   cafe_gen_wb::wb_feet(q, v, [&](int i, double x) { pf[i] = x; }, [&](int i, double x) { vf[i] = x; }, [&](int i, double x) { J[i] = x; });
 }
@@ -40,6 +49,16 @@ __device__ void wbg_rnea_derivs(const double* q, const double* v, const double* 
   wbg_rnea_trunk(q, v, a, dq, dv, st);
   wbg_rnea_leg0(q, v, a, dq, dv, st); wbg_rnea_leg1(q, v, a, dq, dv, st); wbg_rnea_leg2(q, v, a, dq, dv, st); wbg_rnea_leg3(q, v, a, dq, dv, st);
 }
+// Lock-step variants for k_lq (every live thread of the CTA evaluates the same running knot): a CTA barrier between the pieces keeps
+// the four warps inside the same stretch of straight-line code, so that they share instruction-cache lines (ncu: stall_no_instruction
+// 8.5 cycles per issue without it; each leg piece is tens of KB of SASS).
+__device__ void wbg_rnea_derivs_lockstep(const double* q, const double* v, const double* a, double* dq, double* dv, size_t st) {
+  __syncthreads(); wbg_rnea_trunk(q, v, a, dq, dv, st);
+  __syncthreads(); wbg_rnea_leg0(q, v, a, dq, dv, st);
+  __syncthreads(); wbg_rnea_leg1(q, v, a, dq, dv, st);
+  __syncthreads(); wbg_rnea_leg2(q, v, a, dq, dv, st);
+  __syncthreads(); wbg_rnea_leg3(q, v, a, dq, dv, st);
+}
 __device__ __noinline__ void wbg_grav_derivs(const double* q, double* dq) {
   cafe_gen_wb::wb_grav_derivs(q, [&](int i, double x) { dq[i] = x; });
 }
@@ -53,6 +72,12 @@ CAFE_KIN_FOOT(0) CAFE_KIN_FOOT(1) CAFE_KIN_FOOT(2) CAFE_KIN_FOOT(3)
 __device__ void wbg_kin_partials(const double* q, const double* v, const double* a, const double* F, double* dvq, double* daq, double* dav, double* djtf, size_t st) {
   wbg_kin_foot0(q, v, a, F, dvq, daq, dav, djtf, st); wbg_kin_foot1(q, v, a, F, dvq, daq, dav, djtf, st);
   wbg_kin_foot2(q, v, a, F, dvq, daq, dav, djtf, st); wbg_kin_foot3(q, v, a, F, dvq, daq, dav, djtf, st);
+}
+__device__ void wbg_kin_partials_lockstep(const double* q, const double* v, const double* a, const double* F, double* dvq, double* daq, double* dav, double* djtf, size_t st) {
+  __syncthreads(); wbg_kin_foot0(q, v, a, F, dvq, daq, dav, djtf, st);
+  __syncthreads(); wbg_kin_foot1(q, v, a, F, dvq, daq, dav, djtf, st);
+  __syncthreads(); wbg_kin_foot2(q, v, a, F, dvq, daq, dav, djtf, st);
+  __syncthreads(); wbg_kin_foot3(q, v, a, F, dvq, daq, dav, djtf, st);
 }
 __device__ __noinline__ void wbg_footvel_partial(const double* q, const double* v, double* dvq) {
   cafe_gen_wb::wb_footvel_partial(q, v, [&](int i, double x) { dvq[i] = x; });
