@@ -261,8 +261,9 @@ def main():
                    "traffic_source": traffic_src, "bytes_per_launch": lq_bytes / n_lq, "avg_launch_ms": lq_ms / n_lq,
                    "share_of_step": lq_ms / max(sum(tm["ms"].values()), 1e-9),
                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy bandwidth)",
-                   "note": "algorithmic bytes = the reference's LQ inputs and outputs per knot (A,B,C,D, cost partials); DRAM traffic far above it = register "
-                           "spills and thread-local arrays of the generated whole-body routines"}
+                   "note": "algorithmic bytes = the reference's dense LQ inputs and outputs per knot (A,B,C,D, cost partials); whole-body decks: DRAM traffic "
+                           "far above it = register spills and thread-local arrays of the generated routines; HKD decks: structural zeros of A, B, lxx, "
+                           "luu are never rewritten, so fewer bytes move than this count"}
         # `roofline` is the stage with the larger share of the step; the other one rides along
         roof = dict(roof_lq if lq_ms > tm["ms"]["bwd"] else roof_bwd)
         roof["other"] = roof_bwd if lq_ms > tm["ms"]["bwd"] else roof_lq
