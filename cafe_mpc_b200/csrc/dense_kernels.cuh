@@ -28,25 +28,58 @@ __global__ void __launch_bounds__(CAFE_DENSE_NT, 3) k_lq_wb_dense(const SolverDe
       const double bg2 = 2.0 * ph.BG_alpha;
       int rowsA[12];
       { int j = 0; for (int f = 0; f < 4; ++f) if (ph.contact[f] > 0) for (int r = 0; r < 3; ++r) rowsA[j++] = 3 * f + r; for (; j < 12; ++j) rowsA[j] = 0; }
-      for (int e = threadIdx.x >> 2; e < 684; e += CAFE_DENSE_NT / 4) {  // factors
-        const double v = src[(size_t)e * ldb];
-        if (e >= CAFE_KKT_LS) { const int idx = e - CAFE_KKT_LS; const int i = idx % 12, j = idx / 12; dst[756 + j + 12 * i] = (i == j) ? 1.0 / v : v; }
-        else if (e >= CAFE_KKT_Y) { const int idx = e - CAFE_KKT_Y; const int i = idx % 18, c = idx / 18; dst[324 + idx] = v; dst[540 + c + 12 * i] = v; }
-        else { const int i = e % 18, j = e / 18; dst[j + 18 * i] = (i == j) ? 1.0 / v : v; }
+      // every loop below first issues a batch of independent global loads and only then consumes them: one element per iteration
+      // made the CTA wait a full memory latency ~60 times in a row (ncu: long-scoreboard 13.6 cycles per issue)
+      constexpr int ST = CAFE_DENSE_NT / 4, UB = 8;
+      for (int e0 = threadIdx.x >> 2; e0 < 684; e0 += ST * UB) {  // factors
+        double v[UB];
+#pragma unroll
+        for (int u = 0; u < UB; ++u) { const int e = e0 + ST * u; v[u] = e < 684 ? src[(size_t)e * ldb] : 0.0; }
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+          const int e = e0 + ST * u;
+          if (e >= 684) break;
+          if (e >= CAFE_KKT_LS) { const int idx = e - CAFE_KKT_LS; const int i = idx % 12, j = idx / 12; dst[756 + j + 12 * i] = (i == j) ? 1.0 / v[u] : v[u]; }
+          else if (e >= CAFE_KKT_Y) { const int idx = e - CAFE_KKT_Y; const int i = idx % 18, c = idx / 18; dst[324 + idx] = v[u]; dst[540 + c + 12 * i] = v[u]; }
+          else { const int i = e % 18, j = e / 18; dst[j + 18 * i] = (i == j) ? 1.0 / v[u] : v[u]; }
+        }
       }
-      for (int e = threadIdx.x >> 2; e < 648; e += CAFE_DENSE_NT / 4) {  // R = [dtau_dq - d(J^T F)/dq | dtau_dv]
-        const int i = e % 18, col = e / 18;
-        double v = src[(size_t)(CAFE_KKT_RQ + e) * ldb];
-        if (col < 18) v -= src[(size_t)(CAFE_KKT_JTF + e) * ldb];
-        dst[900 + i + 19 * col] = v;
+      for (int e0 = threadIdx.x >> 2; e0 < 648; e0 += ST * UB) {  // R = [dtau_dq - d(J^T F)/dq | dtau_dv]
+        double v[UB], w[UB];
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+          const int e = e0 + ST * u;
+          v[u] = e < 648 ? src[(size_t)(CAFE_KKT_RQ + e) * ldb] : 0.0;
+          w[u] = e < 324 ? src[(size_t)(CAFE_KKT_JTF + e) * ldb] : 0.0;   // columns 0..17 only
+        }
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+          const int e = e0 + ST * u;
+          if (e >= 648) break;
+          const int i = e % 18, col = e / 18;
+          dst[900 + i + 19 * col] = (col < 18) ? v[u] - w[u] : v[u];
+        }
       }
-      for (int e = threadIdx.x >> 2; e < NR * 36; e += CAFE_DENSE_NT / 4) {  // a = [da/dq + 2 BG dv/dq | da/dv + 2 BG J] on the active rows
-        const int c = e % (NR > 0 ? NR : 1), col = e / (NR > 0 ? NR : 1);
-        const int row = rowsA[c];
-        double v;
-        if (col < 18) v = src[(size_t)(CAFE_KKT_AQ + row + 12 * col) * ldb] + bg2 * src[(size_t)(CAFE_KKT_DVQ + row + 12 * col) * ldb];
-        else v = src[(size_t)(CAFE_KKT_AV + row + 12 * (col - 18)) * ldb] + bg2 * src[(size_t)(CAFE_KKT_J + row + 12 * (col - 18)) * ldb];
-        dst[1584 + c + 13 * col] = v;
+      for (int e0 = threadIdx.x >> 2; e0 < NR * 36; e0 += ST * UB) {  // a = [da/dq + 2 BG dv/dq | da/dv + 2 BG J] on the active rows
+        double v[UB], w[UB];
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+          const int e = e0 + ST * u;
+          const int c = e % (NR > 0 ? NR : 1), col = e / (NR > 0 ? NR : 1);
+          const int row = rowsA[c];
+          const bool in = e < NR * 36;
+          const int o1 = (col < 18) ? CAFE_KKT_AQ + row + 12 * col : CAFE_KKT_AV + row + 12 * (col - 18);
+          const int o2 = (col < 18) ? CAFE_KKT_DVQ + row + 12 * col : CAFE_KKT_J + row + 12 * (col - 18);
+          v[u] = in ? src[(size_t)o1 * ldb] : 0.0;
+          w[u] = in ? src[(size_t)o2 * ldb] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+          const int e = e0 + ST * u;
+          if (e >= NR * 36) break;
+          const int c = e % (NR > 0 ? NR : 1), col = e / (NR > 0 ? NR : 1);
+          dst[1584 + c + 13 * col] = v[u] + bg2 * w[u];
+        }
       }
     }
   }
