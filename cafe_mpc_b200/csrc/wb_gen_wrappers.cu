@@ -1,6 +1,11 @@
 // wb_gen_wrappers.cu — out-of-line instantiations of the generated whole-body routines (gen/wb_gen.h), one copy each,
 // with plain array outputs. Separate translation unit (relocatable device code) so that the slow ptxas pass over these
 // straight-line functions only re-runs when the generated header changes.
+// The routines that only k_lq calls (RNEA derivatives, kinematic partials) carry a CAFE_GEN_SYNC marker every 1024 operations: a CTA
+// barrier here. k_lq gives every CTA one knot (knot_kernels.cuh), so all live threads of a CTA run the same routine and meet at the same
+// markers; the four warps then stay within ~10 KB of the straight-line code and share instruction-cache lines.
+#define CAFE_GEN_SYNC __syncthreads();
+#define CAFE_HD __device__ __forceinline__   // device-only instantiations here (the host tests include the header on their own)
 #include "gen/wb_gen.h"
 #include "wb_pieces.h"
 

@@ -28,6 +28,7 @@ from wb_model import WBModel, hardcoded_params, make_vars, params_from_urdf  # n
 
 URDF = "/root/reference/urdf/mini_cheetah_simple_correctedInertia.urdf"
 HIP_YAW_URDF = 3.1415
+SYNC_EVERY = 1024   # operations between two CAFE_GEN_SYNC markers in the routines that only k_lq calls
 
 
 def main():
@@ -73,7 +74,7 @@ def main():
         tau = m.rnea(q, v, a, only=only)
         o_dq = [(r + 18 * c, tau[r].d(q[c])) for c in range(18) for r in range(18)]
         o_dv = [(r + 18 * c, tau[r].d(v[c])) for c in range(18) for r in range(18)]
-        pieces.append(emit_function(ctx, "wb_rnea_derivs_" + name, 3, [o_dq, o_dv]))
+        pieces.append(emit_function(ctx, "wb_rnea_derivs_" + name, 3, [o_dq, o_dv], sync_every=SYNC_EVERY))   # k_lq only: lock-step markers
     grav = m.rnea(q, zero, zero)
     o_gq = [(r + 18 * c, grav[r].d(q[c])) for c in range(18) for r in range(18)]
     pieces.append(emit_function(ctx, "wb_grav_derivs", 1, [o_gq]))
@@ -91,7 +92,7 @@ def main():
         o_dav = [(3 * f + r + 12 * c, fa[r].d(v[c])) for c in range(18) for r in range(3)]
         jtf = [J[0][i] * F[3 * f] + J[1][i] * F[3 * f + 1] + J[2][i] * F[3 * f + 2] for i in range(18)]
         o_jtf = [(r + 18 * c, jtf[r].d(q[c])) for c in range(18) for r in range(18)]
-        pieces.append(emit_function(ctx2, "wb_kin_partials_foot%d" % f, 4, [o_dv, o_daq, o_dav, o_jtf]))
+        pieces.append(emit_function(ctx2, "wb_kin_partials_foot%d" % f, 4, [o_dv, o_daq, o_dav, o_jtf], sync_every=SYNC_EVERY))
         nz = [(i % 18, i // 18) for i, s_ in o_jtf if not s_.is_zero()]
         print("jtf foot", f, "rows", sorted(set(r for r, c in nz)), "cols", sorted(set(c for r, c in nz)))
     # dv_dq alone (swing-foot velocity costs, touchdown velocity penalty, impact derivatives)
@@ -102,6 +103,7 @@ def main():
     pieces.append(emit_function(ctx2, "wb_footvel_partial", 2, [o_dv2]))
     with open(out, "w") as fh:
         fh.write(HEADER.replace("tools/casadi2cuda.py", "tools/gen_wb.py (symbolic whole-body model, tools/wb_model.py)"))
+        fh.write("#ifndef CAFE_GEN_SYNC\n#define CAFE_GEN_SYNC\n#endif\n")
         fh.write("namespace cafe_gen_wb {\n\n")
         for code, meta in pieces:
             fh.write("// %s: %d ops, output non-zeros %s\n" % (meta["name"], meta["ops"], meta["nnz"]))

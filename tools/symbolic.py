@@ -125,8 +125,10 @@ class Sym:
     def d(self, var): return Sym(self.c, self.c.diff(self.i, var.i))
 
 
-def emit_function(ctx, name, n_in, outputs, out_names=None, decl="CAFE_HD"):
+def emit_function(ctx, name, n_in, outputs, out_names=None, decl="CAFE_HD", sync_every=0):
     """outputs: list (one per output array) of lists of (dense_index, Sym). Zero entries are skipped.
+    sync_every > 0: a CAFE_GEN_SYNC marker after every sync_every operations (a CTA barrier where the includer defines it so: the
+    warps of a CTA then stay inside the same stretch of straight-line code and share instruction-cache lines; empty by default).
     Emits `template<class O0,...> CAFE_HD void name(const double* i0, ..., O0 o0, ...)`."""
     d = ctx.d
     live = set()
@@ -177,6 +179,8 @@ def emit_function(ctx, name, n_in, outputs, out_names=None, decl="CAFE_HD"):
         else:
             lines.append("  const double t%d = %s(%s);" % (i, op, ref(nd[1]))); n_ops += 1
         store(i)
+        if sync_every > 0 and op != "arg" and n_ops % sync_every == 0 and lines[-1] != "  CAFE_GEN_SYNC":
+            lines.append("  CAFE_GEN_SYNC")
     lines.append("}")
     nnz = [sum(1 for _, s in lst if not s.is_zero()) for lst in outputs]
     return "\n".join(lines), {"name": name, "ops": n_ops, "nnz": nnz}
