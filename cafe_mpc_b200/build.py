@@ -34,7 +34,7 @@ NVCC_FLAGS = [
 # kernels calling them reach 4 CTAs of 128 threads per SM (their local-memory traffic needs the latency hiding)
 _RC = os.environ.get("CAFE_KNOT_MAXRREG", "128")   # dev switch for occupancy experiments
 _MINB = str(max(1, 65536 // (128 * int(_RC))))
-EXTRA = {"wb_gen_wrappers.cu": ["-maxrregcount=" + _RC], "knot_kernels.cu": ["-maxrregcount=" + _RC, "-DCAFE_KNOT_MINB=" + _MINB]}
+EXTRA = {"wb_gen_wrappers.cu": ["-maxrregcount=" + _RC], "knot_kernels.cu": ["-maxrregcount=" + _RC, "-DCAFE_KNOT_MINB=" + _MINB] + os.environ.get("CAFE_KNOT_DEFS", "").split()}
 
 
 def _mtime(p):
