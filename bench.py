@@ -37,6 +37,9 @@ def workload_name(args):
     if args.workload == "barrel":
         return ("MHPC running barrel roll at the impact-bearing start offset k0=205 (WB flight h=22 -> 4-foot landing impact -> WB h=3; SRB h=10), "
                 "%d perturbed problems per GPU" % args.batch)
+    if args.workload == "loco":
+        return ("LocoProblem (Locomotion/Loco_TO.cpp): whole-body-only 1.0 s flypace plan, 9 WB phases / 100 knots, three flight -> stance "
+                "touchdowns, torque + GRF barriers, %d perturbed problems per GPU" % args.batch)
     return "MHPC trot (WB h=11 + WB h=14, n=36 m=12 p=12; SRB h=10, n=m=12), %d perturbed problems per GPU" % args.batch
 
 
@@ -52,6 +55,9 @@ def make_problem(workload):
     if workload == "barrel":
         prob = cm.MHPCProblem(wl.BARREL_CSV, mhpc_config=wl.BARREL_CONFIG, k0=wl.BARREL_K0_IMPACT)
         return prob, opt, (lambda B: wl.barrel_batch(prob, B)), 36
+    if workload == "loco":
+        prob = cm.LocoProblem()
+        return prob, cm.load_hsddp_setting(wl.LOCO_DDP_SETTING), (lambda B: wl.mhpc_batch(B)), 36
     prob = cm.MHPCProblem(csv)
     return prob, opt, (lambda B: wl.mhpc_batch(B)), 36
 
@@ -142,7 +148,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--batch", type=int, default=4096, help="problems per GPU")
-    ap.add_argument("--workload", default="mhpc", choices=["mhpc", "hkd", "barrel"])
+    ap.add_argument("--workload", default="mhpc", choices=["mhpc", "hkd", "barrel", "loco"])
     ap.add_argument("--gain-knots", type=int, default=8)
     ap.add_argument("--cpu-per-core", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -294,7 +300,8 @@ def main():
             "config": {"workload": workload_name(args), "global_batch": Bg, "per_gpu_batch": B, "parallelism": "batch sharded over %d GPU(s), no collective in the solve" % world,
                        "settings": {"hkd": "HKDMPC/settings (10x5 iteration caps, alpha 0.1)",
                                     "mhpc": "MHPC/settings (10x20 iteration caps, alpha 0.5, BG_alpha 10, cost_weights_regular, constraint_params_regular)",
-                                    "barrel": "MHPC/settings (10x20 iteration caps, alpha 0.5, BG_alpha 10, cost_weights_barrel, constraint_params_barrel)"}[args.workload],
+                                    "barrel": "MHPC/settings (10x20 iteration caps, alpha 0.5, BG_alpha 10, cost_weights_barrel, constraint_params_barrel)",
+                                    "loco": "Locomotion/settings (30x10 iteration caps, alpha 0.5, BG_alpha 10, loco_cost_weights, loco_constraint_params)"}[args.workload],
                        "l2": "working set per solve (GBs of per-problem arrays) exceeds the 126 MB L2; no flush needed",
                        "mean_ddp_iterations": sum(it) / len(it), "max_ddp_iterations": max(it)},
             "e2e": {"value": Bg * args.steps / wall_e2e, "unit": UNIT, "h2d_bytes_per_step": int(B * n0 * 8), "d2h_bytes_per_step": int(B * rec * 8),

@@ -30,6 +30,7 @@ class Phase(C.Structure):
         ("reb_grf", RebParam), ("reb_torque", RebParam), ("reb_joint", RebParam), ("reb_minheight", RebParam),
         ("al_td", AlParam), ("mu", C.c_double), ("ground_height", C.c_double),
         ("h_min", C.c_double), ("torque_limit", C.c_double), ("joint_lb", C.c_double * 3), ("joint_ub", C.c_double * 3),
+        ("no_joint_limit", C.c_int), ("no_min_height", C.c_int),
     ]
 
 

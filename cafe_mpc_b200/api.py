@@ -80,6 +80,19 @@ class MHPCProblem(_DeckOwner):
                                        C.byref(self._h)))
 
 
+class LocoProblem(_DeckOwner):
+    """LocoProblem<T> (Locomotion/LocoProblem.cpp:7-84; driver Loco_TO.cpp:16-82): whole-body-only locomotion trajectory
+    optimisation from Locomotion/settings/loco_config.info — torque-limit and GRF barriers only, touchdown constraints as in MHPC."""
+
+    def __init__(self, reference_csv=None, loco_config=None, settings_root=None, k0=0):
+        super().__init__()
+        reference_csv = reference_csv or os.path.join(DATA, "Reference/Data/flypace/quad_reference.csv")  # loco_config.info: referenceFile flypace
+        loco_config = loco_config or os.path.join(DATA, "MHPC/MHPC-Trajopt/Locomotion/settings/loco_config.info")
+        settings_root = settings_root or DATA
+        check(lib.cafe_deck_build_loco(reference_csv.encode(), loco_config.encode(), settings_root.encode(), k0,
+                                       C.byref(self._h)))
+
+
 LCM_FIELDS = (("torque", 12), ("eul", 3), ("pos", 3), ("qJ", 12), ("vWorld", 3), ("eulrate", 3), ("qJd", 12), ("GRF", 12), ("feedback", 432),
               ("Qu", 12), ("Quu", 144), ("Qux", 432))   # lcmtypes/MHPC_Command_lcmt.lcm, per-problem fields in struct order
 

@@ -30,11 +30,12 @@
 #define CAFE_WB_K_TILE 432
 #define CAFE_LXX_MASK_WORDS 21
 #define CAFE_MAX_KNOTS 256
-#define CAFE_HIST_CAP 256
+#define CAFE_HIST_CAP 320  // LocoProblem settings: 30 x 10 iterations + the initial entry
 
 struct PhaseDev {
   int model, n, m, p, h, n_next, has_next;
   int contact[4], next_contact[4], n_td, td_foot[4];
+  int no_joint_limit, no_min_height;  // WB path-constraint set (CafePhase: LocoProblem drops the joint-limit and min-height barriers)
   double dt, mu, ground_height, BG_alpha, h_min, torque_limit, joint_lb[3], joint_ub[3];
   double q[CAFE_MAX_N], r[CAFE_MAX_M], qf[CAFE_MAX_N];
   double w_footreg[3], w_swingpos[3], w_swingvel[3], w_tdvel[3];

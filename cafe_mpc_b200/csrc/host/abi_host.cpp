@@ -73,6 +73,25 @@ extern "C" int cafe_deck_build_mhpc(const char* reference_csv, const char* mhpc_
   CAFE_CATCH(CAFE_ERR_IO)
 }
 
+extern "C" int cafe_deck_build_loco(const char* reference_csv, const char* loco_config_info, const char* settings_root,
+                                    int k0, CafeDeckHandle** out) {
+  if (!reference_csv || !loco_config_info || !settings_root || !out) { cafe::set_last_error("null argument"); return CAFE_ERR_ARG; }
+  CAFE_TRY
+  CafeDeckHandle* h = new CafeDeckHandle();
+  try {
+    cafe::MHPCConfig cfg;
+    cafe::loadMHPCConfig(loco_config_info, cfg);
+    h->ref.load_top_level_data(reference_csv, false, k0);
+    cafe::MHPCProblem prob;
+    prob.loco = true;
+    prob.set_problem_data(&h->ref, cfg, settings_root);
+    prob.initialization(h->st);
+  } catch (...) { delete h; throw; }
+  *out = h;
+  return 0;
+  CAFE_CATCH(CAFE_ERR_IO)
+}
+
 extern "C" const CafeDeck* cafe_deck_get(const CafeDeckHandle* h) { return h ? &h->st.deck : nullptr; }
 extern "C" void cafe_deck_free(CafeDeckHandle* h) { delete h; }
 

@@ -119,7 +119,9 @@ void MHPCProblem::initialization(DeckStorage& out) {
 
   /* ---- initialize_parameters (MHPCProblem.cpp:149-171) */
   InfoFile cpt(root + "/" + pconfig.constraintParamFileName);
-  const CafeRebParam grf = reb_params(cpt, "GRF"), torque = reb_params(cpt, "Torque"), joint = reb_params(cpt, "Joint"), minh = reb_params(cpt, "MinHeight");
+  /* LocoProblem::initialize_parameters (LocoProblem.cpp:7-26) loads GRF, Torque and TD only; its settings file has no other block */
+  const CafeRebParam grf = reb_params(cpt, "GRF"), torque = reb_params(cpt, "Torque");
+  const CafeRebParam joint = loco ? CafeRebParam{1, 1, 0} : reb_params(cpt, "Joint"), minh = loco ? CafeRebParam{1, 1, 0} : reb_params(cpt, "MinHeight");
   CafeAlParam td{};
   td.sigma = cpt.num("TD_AL.sigma"); td.lambda = cpt.num("TD_AL.lambda"); td.sigma_max = cpt.num("TD_AL.sigma_max");
   JsonWeights cw(root + "/" + pconfig.costFileName);
@@ -162,6 +164,7 @@ void MHPCProblem::initialization(DeckStorage& out) {
     ph.ground_height = 0;
     ph.h_min = 0.20;          // MHPCConstraint.h:148
     ph.torque_limit = 17.0;   // MHPCConstraint.cpp:77
+    ph.no_joint_limit = ph.no_min_height = loco ? 1 : 0;  // LocoProblem.cpp:64-82: TorqueLimit + WBGRF only
     const double lb[3] = {-1.3, -5.0, -M_PI}, ub[3] = {1.3, 5.0, M_PI};  // MHPCConstraint.cpp:172-173
     for (int j = 0; j < 3; ++j) { ph.joint_lb[j] = lb[j]; ph.joint_ub[j] = ub[j]; }
     for (int k = 0; k <= ph.horizon; ++k) {

@@ -56,6 +56,9 @@ class MHPCProblem {  // MHPCProblem.h:169-289
  public:
   void set_problem_data(QuadReference* quad_ref, const MHPCConfig& config, const std::string& settings_root);
   void initialization(DeckStorage& out);  // MHPCProblem.cpp:13-250
+  // LocoProblem (MHPC/MHPC-Trajopt/Locomotion/LocoProblem.cpp:7-84): the same builder with initialize_parameters reading only the
+  // GRF / Torque / TD blocks and create_problem_one_phase attaching only the torque and GRF barriers to a whole-body phase
+  bool loco = false;
 
  private:
   QuadReference* quad_reference = nullptr;

@@ -159,9 +159,12 @@ struct WBModel {
       double c_t = 0, c_j = 0, c_h = 0, c_g = 0, m_t = 0, m_j = 0, m_h = 0, m_g = 0;
       for (int i = 0; i < 12; ++i) { const double g = -u[i] - (-ph.torque_limit); m_t = fmin(m_t, g); c_t += ph.reb_torque.eps * reb_value(g, ph.reb_torque.delta); }
       for (int i = 0; i < 12; ++i) { const double g = u[i] - (-ph.torque_limit); m_t = fmin(m_t, g); c_t += ph.reb_torque.eps * reb_value(g, ph.reb_torque.delta); }
-      for (int i = 0; i < 12; ++i) { const double g = x[6 + i] - ph.joint_lb[i % 3]; m_j = fmin(m_j, g); c_j += ph.reb_joint.eps * reb_value(g, ph.reb_joint.delta); }
-      for (int i = 0; i < 12; ++i) { const double g = -x[6 + i] - (-ph.joint_ub[i % 3]); m_j = fmin(m_j, g); c_j += ph.reb_joint.eps * reb_value(g, ph.reb_joint.delta); }
-      { const double g = x[2] - ph.h_min; m_h = fmin(m_h, g); c_h += ph.reb_minheight.eps * reb_value(g, ph.reb_minheight.delta); }
+      const bool jl = !ph.no_joint_limit, mh = !ph.no_min_height;  // LocoProblem keeps torque + GRF only (LocoProblem.cpp:64-82)
+      if (jl) {
+        for (int i = 0; i < 12; ++i) { const double g = x[6 + i] - ph.joint_lb[i % 3]; m_j = fmin(m_j, g); c_j += ph.reb_joint.eps * reb_value(g, ph.reb_joint.delta); }
+        for (int i = 0; i < 12; ++i) { const double g = -x[6 + i] - (-ph.joint_ub[i % 3]); m_j = fmin(m_j, g); c_j += ph.reb_joint.eps * reb_value(g, ph.reb_joint.delta); }
+      }
+      if (mh) { const double g = x[2] - ph.h_min; m_h = fmin(m_h, g); c_h += ph.reb_minheight.eps * reb_value(g, ph.reb_minheight.delta); }
       bool any = false;
       for (int f = 0; f < 4; ++f)
         if (ph.contact[f] > 0) {
@@ -171,7 +174,7 @@ struct WBModel {
           for (int i = 0; i < 5; ++i) { m_g = fmin(m_g, g[i]); c_g += ph.reb_grf.eps * reb_value(g[i], ph.reb_grf.delta); }
         }
       ming = fmin(fmin(m_t, m_j), fmin(m_h, m_g));
-      if (reb) { l += ph.dt * c_t; l += ph.dt * c_j; l += ph.dt * c_h; if (any) l += ph.dt * c_g; }
+      if (reb) { l += ph.dt * c_t; if (jl) l += ph.dt * c_j; if (mh) l += ph.dt * c_h; if (any) l += ph.dt * c_g; }
     }
     return l;
   }
@@ -337,12 +340,15 @@ struct WBModel {
         }
     }
     double bdj[24], bddj[24], bdh = 0, bddh = 0;
-    if (reb) {
+    const bool jl = reb && !ph.no_joint_limit, mh = reb && !ph.no_min_height;
+    if (jl) {
       for (int i = 0; i < 12; ++i) {
         reb_derivs(x[6 + i] - ph.joint_lb[i % 3], ph.reb_joint.delta, bdj[i], bddj[i]);
         reb_derivs(-x[6 + i] + ph.joint_ub[i % 3], ph.reb_joint.delta, bdj[12 + i], bddj[12 + i]);
         lx[6 + i] += dt * (ph.reb_joint.eps * bdj[i] - ph.reb_joint.eps * bdj[12 + i]);
       }
+    }
+    if (mh) {
       reb_derivs(x[2] - ph.h_min, ph.reb_minheight.delta, bdh, bddh);
       lx[2] += dt * (ph.reb_minheight.eps * bdh);
     }
@@ -357,10 +363,8 @@ struct WBModel {
     double dg[36], bb[81];
     for (int i = 0; i < 36; ++i) {
       double v = dt * ph.q[i];
-      if (reb) {
-        if (i >= 6 && i < 18) v += dt * (ph.reb_joint.eps * bddj[i - 6] + ph.reb_joint.eps * bddj[12 + i - 6]);
-        if (i == 2) v += dt * (ph.reb_minheight.eps * bddh);
-      }
+      if (jl && i >= 6 && i < 18) v += dt * (ph.reb_joint.eps * bddj[i - 6] + ph.reb_joint.eps * bddj[12 + i - 6]);
+      if (mh && i == 2) v += dt * (ph.reb_minheight.eps * bddh);
       dg[i] = v;
     }
     for (int i = 0; i < 81; ++i) bb[i] = 0.0;

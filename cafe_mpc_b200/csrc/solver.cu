@@ -363,7 +363,7 @@ extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, 
     d.n_next = d.has_next ? cafe_model_n(deck->phase[i + 1].model) : 0;
     for (int l = 0; l < 4; ++l) { d.contact[l] = p.contact[l]; d.next_contact[l] = p.next_contact[l]; d.td_foot[l] = p.td_foot[l]; }
     d.n_td = p.n_td; d.dt = p.dt; d.mu = p.mu; d.ground_height = p.ground_height; d.BG_alpha = deck->BG_alpha;
-    d.h_min = p.h_min; d.torque_limit = p.torque_limit;
+    d.h_min = p.h_min; d.torque_limit = p.torque_limit; d.no_joint_limit = p.no_joint_limit; d.no_min_height = p.no_min_height;
     for (int l = 0; l < 3; ++l) { d.joint_lb[l] = p.joint_lb[l]; d.joint_ub[l] = p.joint_ub[l]; }
     std::memcpy(d.q, p.q, sizeof(d.q)); std::memcpy(d.r, p.r, sizeof(d.r)); std::memcpy(d.qf, p.qf, sizeof(d.qf));
     std::memcpy(d.w_footreg, p.w_footreg, sizeof(d.w_footreg)); std::memcpy(d.w_swingpos, p.w_swingpos, sizeof(d.w_swingpos));

@@ -106,3 +106,8 @@ def speed_command_references(problem, B, max_dv=0.2):
             refs[b, r, 72:84:3] += dv * t_of[r]
             refs[b, r, 84] += dv * t_of[r]
     return refs
+
+
+# ---- LocoProblem (MHPC/MHPC-Trajopt/Locomotion): whole-body-only locomotion trajectory optimisation, 1 s flypace plan.
+# Loco_TO.cpp:49-55 starts it from MHPC_NOMINAL; mhpc_batch is its perturbed batch.
+LOCO_DDP_SETTING = _os.path.join(_DATA, "MHPC/MHPC-Trajopt/Locomotion/settings/loco_ddp_setting.info")

@@ -80,6 +80,9 @@ typedef struct {
   double h_min;         /* minimum body height (WB 0.20, SRB 0.18; MHPCConstraint.h:148,199) */
   double torque_limit;  /* WB joint torque bound (17; MHPCConstraint.cpp:77)               */
   double joint_lb[3], joint_ub[3]; /* WB joint limits per leg (MHPCConstraint.cpp:172-175) */
+  /* WB path-constraint set. 0/0 = MHPCProblem (torque, joint, min height, GRF; MHPCProblem.cpp:436-481);
+   * 1/1 = LocoProblem (torque and GRF only; Locomotion/LocoProblem.cpp:64-82) */
+  int no_joint_limit, no_min_height;
 } CafePhase;
 
 typedef struct {

@@ -9,6 +9,8 @@
  *                            (+ QuadReference::load_top_level_data / initialize,
  *                               Reference/QuadReference.cpp:6-31,134-356)
  *   cafe_deck_build_mhpc     MHPCProblem<T>::initialization MHPC/MHPC-Trajopt/MHPCProblem.cpp:13-250
+ *   cafe_deck_build_loco     LocoProblem<T> (initialize_parameters, create_problem_one_phase)
+ *                                                         MHPC/MHPC-Trajopt/Locomotion/LocoProblem.cpp:7-84
  *   cafe_hkd_state           compute_hkd_state            HKDMPC/HKD-TrajOpt/HKDModel.h:66-96
  *   cafe_gpu_create          MultiPhaseDDP<T>::set_multiPhaseProblem  HSDDPSolver/header/MultiPhaseDDP.h:33-42
  *   cafe_gpu_solve_batch     MultiPhaseDDP<T>::set_initial_condition + solve
@@ -51,6 +53,11 @@ int cafe_deck_build_hkd(const char* reference_csv, const char* constraint_params
  * resolved relative to settings_root (the reference resolves them relative to "../"). reference_csv
  * overrides the file's referenceFile entry. */
 int cafe_deck_build_mhpc(const char* reference_csv, const char* mhpc_config_info, const char* settings_root,
+                         int k0, CafeDeckHandle** out);
+/* LocoProblem<T> (MHPC/MHPC-Trajopt/Locomotion/LocoProblem.cpp:7-84, driver Loco_TO.cpp:16-82): whole-body-only locomotion
+ * trajectory optimisation. Same arguments as cafe_deck_build_mhpc with Locomotion/settings/loco_config.info; the whole-body
+ * phases carry the torque-limit and GRF barriers only (no joint-limit / min-height barrier), touchdown constraints as in MHPC. */
+int cafe_deck_build_loco(const char* reference_csv, const char* loco_config_info, const char* settings_root,
                          int k0, CafeDeckHandle** out);
 const CafeDeck* cafe_deck_get(const CafeDeckHandle* h);
 void cafe_deck_free(CafeDeckHandle* h);

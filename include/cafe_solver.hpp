@@ -61,6 +61,16 @@ class MHPCProblem : public ProblemBase {
   }
 };
 
+// LocoProblem<T> : MHPCProblem<T> (MHPC/MHPC-Trajopt/Locomotion/LocoProblem.h:8-25): whole-body-only locomotion trajectory optimisation,
+// torque-limit and GRF barriers only. loco_config_info: Locomotion/settings/loco_config.info
+class LocoProblem : public MHPCProblem {
+ public:
+  void initialization(const std::string& reference_csv, const std::string& loco_config_info, const std::string& settings_root, int k0 = 0) {
+    if (h_) { cafe_deck_free(h_); h_ = nullptr; }
+    check(cafe_deck_build_loco(reference_csv.c_str(), loco_config_info.c_str(), settings_root.c_str(), k0, &h_));
+  }
+};
+
 class MultiPhaseDDP {
  public:
   MultiPhaseDDP() {}

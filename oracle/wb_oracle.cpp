@@ -69,8 +69,9 @@ class WBPhase : public Phase {
   void build_model() override {
     /* MHPCProblem.cpp:436-481: Torque, Joint, MinHeight, then GRF when any foot is in contact */
     PathConstraint tq; tq.kind = 0; tq.create(24, h, n, m, p, ph->reb_torque); pcon.push_back(tq);
-    PathConstraint jl; jl.kind = 1; jl.create(24, h, n, m, p, ph->reb_joint); pcon.push_back(jl);
-    PathConstraint mh; mh.kind = 2; mh.create(1, h, n, m, p, ph->reb_minheight); pcon.push_back(mh);
+    /* LocoProblem.cpp:64-82 keeps Torque and GRF only */
+    if (!ph->no_joint_limit) { PathConstraint jl; jl.kind = 1; jl.create(24, h, n, m, p, ph->reb_joint); pcon.push_back(jl); }
+    if (!ph->no_min_height) { PathConstraint mh; mh.kind = 2; mh.create(1, h, n, m, p, ph->reb_minheight); pcon.push_back(mh); }
     int nc = 0;
     for (int l = 0; l < 4; ++l) nc += ph->contact[l] > 0;
     if (nc > 0) { PathConstraint g; g.kind = 3; g.create(5 * nc, h, n, m, p, ph->reb_grf); pcon.push_back(g); }

@@ -359,3 +359,51 @@ def test_structural_lxx_patterns_cover_the_oracle(cm, mhpc_options, k0):
             blk = np.kron(np.eye(4), np.ones((3, 3))) > 0
             assert not np.any((lyy[k] != 0) & ~blk)
         assert 100 < min(nnz) and max(nnz) < 750   # a third to a half of the 1296 entries
+
+
+# ---- next tier: LocoProblem, the whole-body-only locomotion trajectory optimisation (Locomotion/Loco_TO.cpp)
+def test_loco_problem_deck_golden(cm):
+    """loco_config.info: 1.0 s whole-body plan on the flypace reference, no SRB tail. LocoProblem::create_problem_one_phase
+    (LocoProblem.cpp:29-84) attaches the torque and GRF barriers only; add_tconstr_one_phase still adds the touchdown constraints."""
+    from cafe_mpc_b200 import workload
+    prob = cm.LocoProblem()
+    ph = prob.phases()
+    g = np.load(os.path.join(REPO, "tests/golden/loco_flypace.npz"))
+    assert np.array_equal(np.array([[p.model, p.horizon] + list(p.contact) + [p.n_td, p.no_joint_limit, p.no_min_height] for p in ph]), g["phases"])
+    assert all(p.model == 1 and p.no_joint_limit == 1 and p.no_min_height == 1 for p in ph) and sum(p.horizon for p in ph) == 100
+    assert [p.next_model for p in ph] == [1] * (len(ph) - 1) + [-1]
+    assert [(p.horizon, tuple(p.contact)) for p in ph[:3]] == [(6, (1, 1, 1, 1)), (15, (0, 1, 0, 1)), (10, (0, 0, 0, 0))]
+    assert ph[2].n_td == 2 and tuple(ph[2].next_contact) == (1, 0, 1, 0)
+    # loco_constraint_params.info / loco_cost_weights.JSON were picked up
+    assert ph[0].reb_grf.delta == 0.2 and ph[0].reb_torque.delta == 0.1 and ph[0].reb_torque.eps == 0.01 and ph[0].al_td.sigma == 20
+    opt = cm.load_hsddp_setting(workload.LOCO_DDP_SETTING)
+    assert (opt.max_AL_iter, opt.max_DDP_iter) == (30, 10)
+    # an MHPC deck keeps all four barriers
+    assert all(p.no_joint_limit == 0 and p.no_min_height == 0 for p in cm.MHPCProblem(CSV).phases())
+
+
+def test_oracle_loco_matches_committed_golden(cm):
+    from cafe_mpc_b200 import workload
+    g = np.load(os.path.join(REPO, "tests/golden/loco_flypace.npz"))
+    prob = cm.LocoProblem()
+    opt = cm.load_hsddp_setting(workload.LOCO_DDP_SETTING)
+    x0 = workload.mhpc_batch(4)
+    assert np.array_equal(x0, g["x0"])
+    info, hist, trace, sol = oracle_solve(prob.deck, opt, x0[0], cap=320)
+    assert [info[k] for k in ("status", "iter", "ls_iter_total", "reg_iter_total", "outer_iter", "n_hist")] == list(g["counts_0"])
+    np.testing.assert_allclose(hist[:, 0], g["hist_0"][:, 0], rtol=1e-9)
+    np.testing.assert_allclose(sol, g["sol_0"], rtol=0, atol=1e-8 * np.abs(sol).max())
+    assert info["outer_iter"] > 1   # the touchdown constraints of the flight phases drove the AL loop
+
+
+def test_oracle_joint_and_height_barriers_matter(cm, mhpc, mhpc_options):
+    """Dropping the joint-limit / min-height barriers from an MHPC deck changes the cost the oracle reports (the flags are live)."""
+    from cafe_mpc_b200 import workload
+    from cafe_mpc_b200._ctypes_defs import Deck
+    x0 = workload.mhpc_batch(2)[1]
+    i0, _, _, _ = oracle_solve(mhpc.deck, mhpc_options, x0)
+    d2 = Deck.from_buffer_copy(mhpc.deck.contents)
+    for i in range(d2.n_phases):
+        d2.phase[i].no_joint_limit = 1; d2.phase[i].no_min_height = 1
+    i1, _, _, _ = oracle_solve(C.pointer(d2), mhpc_options, x0)
+    assert i0["cost"] != i1["cost"] and i0["status"] == i1["status"] == 0   # (-log barriers of well-satisfied constraints are negative: the cost goes up)

@@ -316,3 +316,41 @@ def test_device_shift_equals_host_shift(cm, opt):
         assert np.array_equal(sh.get_solution(), sd.get_solution()), step
         sh.close(); s.close()
         s, prob, k0 = sd, p1, k1
+
+
+# ---- next tier: LocoProblem, whole-body-only locomotion TO (9 WB phases, 100 knots, three flight -> stance impacts)
+def test_loco_problem_matches_oracle_and_golden(cm):
+    from cafe_mpc_b200 import workload
+    prob = cm.LocoProblem()
+    lopt = cm.load_hsddp_setting(workload.LOCO_DDP_SETTING)
+    g = np.load(os.path.join(REPO, "tests/golden/loco_flypace.npz"))
+    x0 = workload.mhpc_batch(4)
+    assert np.array_equal(x0, g["x0"])
+    s = solve_gpu(cm, prob, lopt, x0)
+    compare_with_oracle(cm, prob, lopt, x0, s, (0, 1))
+    info = s.get_solver_info(); hist = s.get_history(256); sol = s.get_solution()
+    for b in (0, 3):
+        assert [info[b][k] for k in COUNTS] == list(g["counts_%d" % b])
+        np.testing.assert_allclose(hist[b, :info[b]["n_hist"], 0], g["hist_%d" % b][:, 0], rtol=RTOL)
+        assert relerr(sol[b], g["sol_%d" % b]) < RTOL
+    assert all(i["outer_iter"] > 1 for i in info)
+
+
+def test_mhpc_deck_without_joint_and_height_barriers_matches_oracle(cm, opt):
+    """The constraint-set flags on an MHPC deck (WB + SRB): GPU == oracle with the two barriers dropped, and != the full deck."""
+    import ctypes as C
+    from cafe_mpc_b200 import workload
+    from cafe_mpc_b200._ctypes_defs import Deck
+
+    class _P:
+        pass
+    base = cm.MHPCProblem(CSV, k0=20)
+    d2 = Deck.from_buffer_copy(base.deck.contents)
+    for i in range(d2.n_phases):
+        d2.phase[i].no_joint_limit = 1; d2.phase[i].no_min_height = 1
+    p2 = _P(); p2.deck = C.pointer(d2); p2._keep = base
+    x0 = workload.mhpc_batch(4)
+    s = solve_gpu(cm, p2, opt, x0)
+    compare_with_oracle(cm, p2, opt, x0, s, (0, 2))
+    s0 = solve_gpu(cm, base, opt, x0)
+    assert s0.get_solver_info()[2]["cost"] != s.get_solver_info()[2]["cost"]

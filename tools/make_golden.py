@@ -53,3 +53,17 @@ for key, k0 in (("k0", 0), ("k205", workload.BARREL_K0_IMPACT)):
         out["%s_final_%d" % (key, b)] = np.array([i["cost"], i["feas"], i["max_tconstr"], i["max_pconstr"]])
         print("barrel", key, b, i)
 np.savez_compressed(os.path.join(R, "tests/golden/mhpc_barrel.npz"), **out)
+
+# ---- LocoProblem (Locomotion/LocoProblem.cpp, Loco_TO.cpp): whole-body-only 1 s flypace plan, torque + GRF barriers only
+pl = cm.LocoProblem()
+optl = cm.load_hsddp_setting(workload.LOCO_DDP_SETTING)
+x0l = workload.mhpc_batch(4)   # Loco_TO.cpp:49-55 is the nominal state of this table
+out = {"x0": x0l, "phases": np.array([[p.model, p.horizon] + list(p.contact) + [p.n_td, p.no_joint_limit, p.no_min_height] for p in pl.phases()])}
+for b in (0, 3):
+    i, h, t, s = oracle_solve(pl.deck, optl, x0l[b], cap=320)
+    out["counts_%d" % b] = np.array([i[k] for k in ("status", "iter", "ls_iter_total", "reg_iter_total", "outer_iter", "n_hist")])
+    out["hist_%d" % b] = h
+    out["sol_%d" % b] = s
+    out["final_%d" % b] = np.array([i["cost"], i["feas"], i["max_tconstr"], i["max_pconstr"]])
+    print("loco", b, i)
+np.savez_compressed(os.path.join(R, "tests/golden/loco_flypace.npz"), **out)
