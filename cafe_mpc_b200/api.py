@@ -93,6 +93,25 @@ class LocoProblem(_DeckOwner):
                                        C.byref(self._h)))
 
 
+class BarrelRollProblem(_DeckOwner):
+    """The in-place barrel roll of BarrelRollTO.cpp:65-275: six hand-scheduled whole-body phases, per-phase weights, fixed desired
+    states, BarrelRoll:: barriers (incl. the joint-speed limit), four-foot touchdown constraints after both flight phases."""
+
+    def __init__(self, cost_weights=None, constraint_params=None):
+        super().__init__()
+        d = os.path.join(DATA, "MHPC/MHPC-Trajopt/BarrelRoll/setting")
+        cost_weights = cost_weights or os.path.join(d, "br_cost_weights.JSON")
+        constraint_params = constraint_params or os.path.join(d, "br_constraint_params.info")
+        check(lib.cafe_deck_build_barrel_to(cost_weights.encode(), constraint_params.encode(), C.byref(self._h)))
+
+    def initial_guess(self, x0):
+        """Packed guesses [B, solution_size] holding the interpolated state trajectory of BarrelRollTO.cpp:131-147 (for set_initial_guess)."""
+        x0 = np.ascontiguousarray(np.atleast_2d(x0), dtype=np.float64)
+        g = np.zeros((x0.shape[0], lib.cafe_solution_size(self.deck)))
+        check(lib.cafe_barrel_to_initial_guess(self.deck, x0.ctypes.data_as(C.c_void_p), x0.shape[0], g.ctypes.data_as(C.c_void_p)))
+        return g
+
+
 LCM_FIELDS = (("torque", 12), ("eul", 3), ("pos", 3), ("qJ", 12), ("vWorld", 3), ("eulrate", 3), ("qJd", 12), ("GRF", 12), ("feedback", 432),
               ("Qu", 12), ("Quu", 144), ("Qux", 432))   # lcmtypes/MHPC_Command_lcmt.lcm, per-problem fields in struct order
 

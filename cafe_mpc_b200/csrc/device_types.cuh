@@ -35,7 +35,10 @@
 struct PhaseDev {
   int model, n, m, p, h, n_next, has_next;
   int contact[4], next_contact[4], n_td, td_foot[4];
-  int no_joint_limit, no_min_height;  // WB path-constraint set (CafePhase: LocoProblem drops the joint-limit and min-height barriers)
+  int no_joint_limit, no_min_height, joint_speed_limit;
+  CafeRebParam reb_jointvel;  // BarrelRoll::JointSpeedLimit
+  double jointvel_lb, jointvel_ub;
+   // WB path-constraint set (CafePhase: LocoProblem drops the joint-limit and min-height barriers)
   double dt, mu, ground_height, BG_alpha, h_min, torque_limit, joint_lb[3], joint_ub[3];
   double q[CAFE_MAX_N], r[CAFE_MAX_M], qf[CAFE_MAX_N];
   double w_footreg[3], w_swingpos[3], w_swingvel[3], w_tdvel[3];

@@ -92,6 +92,25 @@ extern "C" int cafe_deck_build_loco(const char* reference_csv, const char* loco_
   CAFE_CATCH(CAFE_ERR_IO)
 }
 
+extern "C" int cafe_deck_build_barrel_to(const char* cost_weights_json, const char* constraint_params_info, CafeDeckHandle** out) {
+  if (!cost_weights_json || !constraint_params_info || !out) { cafe::set_last_error("null argument"); return CAFE_ERR_ARG; }
+  CAFE_TRY
+  CafeDeckHandle* h = new CafeDeckHandle();
+  try { cafe::build_barrel_to_deck(cost_weights_json, constraint_params_info, h->st); } catch (...) { delete h; throw; }
+  *out = h;
+  return 0;
+  CAFE_CATCH(CAFE_ERR_IO)
+}
+
+extern "C" int cafe_barrel_to_initial_guess(const CafeDeck* deck, const double* x0, int B, double* guess) {
+  if (!deck || !x0 || !guess || B <= 0 || deck->n_phases != 6) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
+  for (int i = 0; i < 6; ++i) if (deck->phase[i].model != CAFE_MODEL_WB) { cafe::set_last_error("not a barrel-roll deck"); return CAFE_ERR_ARG; }
+  const long sz = cafe_solution_size(deck);
+  std::memset(guess, 0, (size_t)B * sz * sizeof(double));
+  for (int b = 0; b < B; ++b) cafe::barrel_to_guess(*deck, x0 + (size_t)b * 36, guess + (size_t)b * sz);
+  return 0;
+}
+
 extern "C" const CafeDeck* cafe_deck_get(const CafeDeckHandle* h) { return h ? &h->st.deck : nullptr; }
 extern "C" void cafe_deck_free(CafeDeckHandle* h) { delete h; }
 

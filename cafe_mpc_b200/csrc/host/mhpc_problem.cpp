@@ -199,3 +199,119 @@ void MHPCProblem::initialization(DeckStorage& out) {
 }
 
 }  // namespace cafe
+
+/* ================= in-place barrel roll (MHPC/MHPC-Trajopt/BarrelRoll/BarrelRollTO.cpp:65-275) =================
+ * Six hand-scheduled whole-body phases, no reference file: the tracking cost of phase i pulls towards a fixed desired state
+ * xf_des[i] (set_reference_state, :171-174) with its own weight set (cost_phase_{i+1}), the barriers are the BarrelRoll:: copies
+ * (torque, joint speed, joint, min height 0.13, GRF), the two flight phases end with a four-foot touchdown constraint (:232-241).
+ * No foot regularisation / swing tracking / touchdown-velocity cost: those weights are zero in the deck (they add exact zeros). */
+namespace cafe {
+
+static const double kBarrelSwitch[7] = {0.0, 0.12, 0.33, 0.75, 0.90, 1.10, 1.25};  // BarrelRollTO.cpp:70
+static const int kBarrelContact[6][4] = {{1, 1, 1, 1}, {0, 1, 0, 1}, {0, 0, 0, 0}, {1, 1, 1, 1}, {0, 0, 0, 0}, {1, 1, 1, 1}};  // :76-81
+
+static void barrel_desired_states(double xd[6][36]) {  // load_desired_final_states, BarrelRollTO.cpp:277-339 (x = pos, eul, qJ, vWorld, euld, qJd)
+  double pos[3] = {0, 0, 0}, eul[3] = {0, 0, 0}, vW[3] = {0, 0, 0}, euld[3] = {0, 0, 0}, qJ[12], qJd[12];
+  for (int l = 0; l < 4; ++l) { qJ[3 * l] = 0; qJ[3 * l + 1] = -1.2; qJ[3 * l + 2] = 2.4; }
+  for (int i = 0; i < 12; ++i) qJd[i] = 0;
+  auto put = [&](int i) {
+    for (int j = 0; j < 3; ++j) { xd[i][j] = pos[j]; xd[i][3 + j] = eul[j]; xd[i][18 + j] = vW[j]; xd[i][21 + j] = euld[j]; }
+    for (int j = 0; j < 12; ++j) { xd[i][6 + j] = qJ[j]; xd[i][24 + j] = qJd[j]; }
+  };
+  pos[0] = 0; pos[1] = -0.15; pos[2] = 0.26; eul[0] = 0; eul[1] = 0; eul[2] = M_PI / 6; euld[2] = 3.0 * M_PI; vW[0] = 0; vW[1] = -1.0; vW[2] = 2.0;
+  put(0);
+  pos[0] = 0; pos[1] = -0.25; pos[2] = 0.33; eul[0] = 0; eul[1] = 0; eul[2] = 0.5 * M_PI; euld[0] = 0; euld[1] = 0; euld[2] = 3.0 * M_PI; vW[0] = 0; vW[1] = -1.2; vW[2] = 2.0;
+  { const double q[12] = {M_PI / 6, -1.0, 2.0, -M_PI / 5, -0.5, 1.0, M_PI / 6, -1.0, 2.0, -M_PI / 5, -0.5, 1.0}; for (int j = 0; j < 12; ++j) qJ[j] = q[j]; }
+  put(1);
+  pos[0] = 0.0; pos[1] = -0.55; pos[2] = 0.22; eul[0] = 0; eul[1] = 0; eul[2] = 2.0 * M_PI; euld[0] = 0; euld[1] = 0; euld[2] = 3.0 * M_PI; vW[0] = 0.0; vW[1] = -1.5; vW[2] = -2.5;
+  { const double q[12] = {0.3, -1.1, 2.2, -0.3, -1.1, 2.2, 0.3, -1.1, 2.2, -0.3, -1.1, 2.2}; for (int j = 0; j < 12; ++j) qJ[j] = q[j]; }
+  put(2);
+  pos[2] = 0.25; eul[2] = 2 * M_PI; euld[2] = 0; vW[0] = 0; vW[1] = 0; vW[2] = 0;
+  put(3);
+  for (int l = 0; l < 4; ++l) { qJ[3 * l] = 0; qJ[3 * l + 1] = -1.0; qJ[3 * l + 2] = 2.0; }
+  put(4);
+  put(5);
+}
+
+void build_barrel_to_deck(const std::string& cost_json, const std::string& constraint_info, DeckStorage& out) {
+  CafeDeck& deck = out.deck;
+  std::memset(&deck, 0, sizeof(deck));
+  out.phase_start_times.clear(); out.phase_end_times.clear();
+  const double dt = 0.01;  // BarrelRollTO.cpp:68 (a double here, not the float of mhpc_config.info)
+  deck.n_phases = 6;
+  deck.BG_alpha = 10.0;    // :89
+  deck.hip_yaw = 3.1415;
+  InfoFile cpt(constraint_info);
+  JsonWeights cw(cost_json);
+  const CafeRebParam grf = reb_params(cpt, "GRF"), torque = reb_params(cpt, "Torque"), jv = reb_params(cpt, "JointVel"), joint = reb_params(cpt, "Joint"), minh = reb_params(cpt, "MinHeight");
+  CafeAlParam td{};
+  td.sigma = cpt.num("TD_AL.sigma"); td.lambda = cpt.num("TD_AL.lambda"); td.sigma_max = cpt.num("TD_AL.sigma_max");
+  double xd[6][36];
+  barrel_desired_states(xd);
+  int rec = 0;
+  for (int i = 0; i < 6; ++i) {
+    CafePhase& ph = deck.phase[i];
+    ph.model = CAFE_MODEL_WB;
+    ph.horizon = (int)std::round((kBarrelSwitch[i + 1] - kBarrelSwitch[i]) / dt);  // :125
+    ph.knot_offset = rec; rec += ph.horizon + 1;
+    out.phase_start_times.push_back((float)kBarrelSwitch[i]); out.phase_end_times.push_back((float)kBarrelSwitch[i + 1]);
+  }
+  deck.n_records = rec;
+  out.ref.assign((size_t)rec * CAFE_REF_W, 0.0);
+  for (int i = 0; i < 6; ++i) {
+    CafePhase& ph = deck.phase[i];
+    ph.dt = dt;
+    ph.t_offset = (float)kBarrelSwitch[i];  // set_time_offset(switching_times[i]), :129
+    ph.has_reset = i < 5 ? 1 : 0;            // :157-169
+    ph.next_model = i < 5 ? CAFE_MODEL_WB : -1;
+    for (int l = 0; l < 4; ++l) { ph.contact[l] = kBarrelContact[i][l]; ph.next_contact[l] = kBarrelContact[i < 5 ? i + 1 : i][l]; }
+    ph.n_td = 0;
+    if (i == 2 || i == 4) for (int l = 0; l < 4; ++l) ph.td_foot[ph.n_td++] = l;  // TouchDown(Vec4<int>::Ones()), :232-241
+    const std::string sec = "cost_phase_" + std::to_string(i + 1) + ".";  // load_cost_weights, :341-412
+    auto fill = [&](double* dst, const char* qB, const char* qJ, const char* vB, const char* vJ) {
+      const auto &a = cw.vec(sec + qB), &b = cw.vec(sec + qJ), &c = cw.vec(sec + vB), &d = cw.vec(sec + vJ);
+      for (int j = 0; j < 6; ++j) { dst[j] = a.at(j); dst[18 + j] = c.at(j); }
+      for (int l = 0; l < 4; ++l) for (int j = 0; j < 3; ++j) { dst[6 + 3 * l + j] = b.at(j); dst[24 + 3 * l + j] = d.at(j); }
+    };
+    fill(ph.q, "qw_qB", "qw_qJ", "qw_vB", "qw_vJ");
+    fill(ph.qf, "qfw_qB", "qfw_qJ", "qfw_vB", "qfw_vJ");
+    for (int j = 0; j < 12; ++j) ph.r[j] = cw.num(sec + "rw");
+    ph.reb_grf = grf; ph.reb_torque = torque; ph.reb_joint = joint; ph.reb_minheight = minh; ph.al_td = td;
+    ph.joint_speed_limit = 1; ph.reb_jointvel = jv; ph.jointvel_lb = -20.0; ph.jointvel_ub = 20.0;  // BarrelRollConstraints.h:71-72
+    ph.mu = 0.6;             // BarrelRollConstraints.cpp:11
+    ph.ground_height = 0;    // :236
+    ph.h_min = 0.13;         // BarrelRollConstraints.h:147
+    ph.torque_limit = 17.0;  // BarrelRollConstraints.cpp:77
+    const double lb[3] = {-1.3, -5.0, -M_PI}, ub[3] = {1.3, 5.0, M_PI};  // :124-125
+    for (int j = 0; j < 3; ++j) { ph.joint_lb[j] = lb[j]; ph.joint_ub[j] = ub[j]; }
+    for (int k = 0; k <= ph.horizon; ++k) {
+      double* r = &out.ref[(size_t)(ph.knot_offset + k) * CAFE_REF_W];
+      for (int j = 0; j < 36; ++j) r[CAFE_REF_XR + j] = xd[i][j];  // set_reference_state(xf_des[i], 0), :173
+      for (int l = 0; l < 4; ++l) r[CAFE_REF_CONTACT + l] = (double)ph.contact[l];
+    }
+  }
+  deck.ref = out.ref.data();
+}
+
+// Initial state trajectory of BarrelRollTO.cpp:131-147: phase i interpolates linearly from the previous phase's desired state (phase 0:
+// from the initial state) to its own over the phase duration, with the reference's float time arithmetic. Writes Xbar into packed
+// solution records (cafe_solution_size doubles each; controls and gains stay zero).
+void barrel_to_guess(const CafeDeck& deck, const double* x0, double* guess) {
+  size_t off = 0;
+  for (int i = 0; i < deck.n_phases; ++i) {
+    const CafePhase& ph = deck.phase[i];
+    const long n = 36, m = 12, p = 12, h = ph.horizon;
+    const double* x1 = deck.ref + (size_t)ph.knot_offset * CAFE_REF_W + CAFE_REF_XR;
+    const double* xa = i == 0 ? x0 : deck.ref + (size_t)deck.phase[i - 1].knot_offset * CAFE_REF_W + CAFE_REF_XR;
+    float t = 0.0;
+    const float t_dur = kBarrelSwitch[i + 1] - kBarrelSwitch[i];
+    for (int k = 0; k <= h; ++k) {
+      const float s = t / t_dur;
+      for (int j = 0; j < 36; ++j) guess[off + (size_t)k * n + j] = xa[j] + (x1[j] - xa[j]) * s;  // lerp_eigen_vectors, :43-53
+      t += 0.01;
+    }
+    off += (h + 1) * n + h * m + h * p + h * m + h * m * n + h * m + h * m * m + h * m * n + (h + 1) * n;
+  }
+}
+
+}  // namespace cafe

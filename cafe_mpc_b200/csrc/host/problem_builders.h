@@ -67,6 +67,10 @@ class MHPCProblem {  // MHPCProblem.h:169-289
   float plan_dur_all = 0;
 };
 
+// In-place barrel roll, BarrelRollTO.cpp:65-275 (six hand-scheduled whole-body phases, fixed desired states, per-phase weights)
+void build_barrel_to_deck(const std::string& cost_json, const std::string& constraint_info, DeckStorage& out);
+void barrel_to_guess(const CafeDeck& deck, const double* x0, double* guess);
+
 // Structural non-zero patterns of the HKD linearisation as 576-bit masks (bit i + 24 j; 9 words each, in the order A, B, lxx, luu):
 // A and B are the CCS patterns of the generated hkinodyn_par (recorded by running it with index-collecting store functors), lxx and
 // luu follow HKDModel::lq_knot (model_hkd.cuh). The backward sweep fetches only these entries.

@@ -155,11 +155,15 @@ struct WBModel {
     l += lreg; l += lpos; l += lvel;
     ming = 0;
     if (true) {
-      // path constraints in the reference's order: torque, joint, min height, GRF (MHPCProblem.cpp:436-481)
-      double c_t = 0, c_j = 0, c_h = 0, c_g = 0, m_t = 0, m_j = 0, m_h = 0, m_g = 0;
+      // path constraints in the reference's order: torque, [joint speed: BarrelRollTO.cpp:190-198], joint, min height, GRF (MHPCProblem.cpp:436-481)
+      double c_t = 0, c_j = 0, c_h = 0, c_g = 0, c_v = 0, m_t = 0, m_j = 0, m_h = 0, m_g = 0, m_v = 0;
       for (int i = 0; i < 12; ++i) { const double g = -u[i] - (-ph.torque_limit); m_t = fmin(m_t, g); c_t += ph.reb_torque.eps * reb_value(g, ph.reb_torque.delta); }
       for (int i = 0; i < 12; ++i) { const double g = u[i] - (-ph.torque_limit); m_t = fmin(m_t, g); c_t += ph.reb_torque.eps * reb_value(g, ph.reb_torque.delta); }
       const bool jl = !ph.no_joint_limit, mh = !ph.no_min_height;  // LocoProblem keeps torque + GRF only (LocoProblem.cpp:64-82)
+      if (ph.joint_speed_limit) {
+        for (int i = 0; i < 12; ++i) { const double g = x[24 + i] - ph.jointvel_lb; m_v = fmin(m_v, g); c_v += ph.reb_jointvel.eps * reb_value(g, ph.reb_jointvel.delta); }
+        for (int i = 0; i < 12; ++i) { const double g = -x[24 + i] - (-ph.jointvel_ub); m_v = fmin(m_v, g); c_v += ph.reb_jointvel.eps * reb_value(g, ph.reb_jointvel.delta); }
+      }
       if (jl) {
         for (int i = 0; i < 12; ++i) { const double g = x[6 + i] - ph.joint_lb[i % 3]; m_j = fmin(m_j, g); c_j += ph.reb_joint.eps * reb_value(g, ph.reb_joint.delta); }
         for (int i = 0; i < 12; ++i) { const double g = -x[6 + i] - (-ph.joint_ub[i % 3]); m_j = fmin(m_j, g); c_j += ph.reb_joint.eps * reb_value(g, ph.reb_joint.delta); }
@@ -173,8 +177,8 @@ struct WBModel {
           const double g[5] = {fz, -fx + mu * fz, fx + mu * fz, -fy + mu * fz, fy + mu * fz};
           for (int i = 0; i < 5; ++i) { m_g = fmin(m_g, g[i]); c_g += ph.reb_grf.eps * reb_value(g[i], ph.reb_grf.delta); }
         }
-      ming = fmin(fmin(m_t, m_j), fmin(m_h, m_g));
-      if (reb) { l += ph.dt * c_t; if (jl) l += ph.dt * c_j; if (mh) l += ph.dt * c_h; if (any) l += ph.dt * c_g; }
+      ming = fmin(fmin(fmin(m_t, m_j), fmin(m_h, m_g)), m_v);
+      if (reb) { l += ph.dt * c_t; if (ph.joint_speed_limit) l += ph.dt * c_v; if (jl) l += ph.dt * c_j; if (mh) l += ph.dt * c_h; if (any) l += ph.dt * c_g; }
     }
     return l;
   }
@@ -352,6 +356,17 @@ struct WBModel {
       reb_derivs(x[2] - ph.h_min, ph.reb_minheight.delta, bdh, bddh);
       lx[2] += dt * (ph.reb_minheight.eps * bdh);
     }
+    const bool jv = reb && ph.joint_speed_limit;
+    double bddv[12];
+    if (jv) {
+      for (int i = 0; i < 12; ++i) {
+        double b1, b2, d1, d2;
+        reb_derivs(x[24 + i] - ph.jointvel_lb, ph.reb_jointvel.delta, b1, d1);
+        reb_derivs(-x[24 + i] + ph.jointvel_ub, ph.reb_jointvel.delta, b2, d2);
+        lx[24 + i] += dt * (ph.reb_jointvel.eps * b1 - ph.reb_jointvel.eps * b2);
+        bddv[i] = ph.reb_jointvel.eps * d1 + ph.reb_jointvel.eps * d2;
+      }
+    }
     for (int i = 0; i < 36; ++i) ph.lx[gix(k, 36, i, ldb, b)] = lx[i];
     // lxx: diagonal (tracking + joint-limit / min-height barriers) + per-foot Gauss-Newton blocks. A foot Jacobian only has the
     // base-rotation columns 3..5 and its own three joint columns (the first three are zeroed by the reference), the swing-foot
@@ -365,6 +380,7 @@ struct WBModel {
       double v = dt * ph.q[i];
       if (jl && i >= 6 && i < 18) v += dt * (ph.reb_joint.eps * bddj[i - 6] + ph.reb_joint.eps * bddj[12 + i - 6]);
       if (mh && i == 2) v += dt * (ph.reb_minheight.eps * bddh);
+      if (jv && i >= 24) v += dt * bddv[i - 24];
       dg[i] = v;
     }
     for (int i = 0; i < 81; ++i) bb[i] = 0.0;

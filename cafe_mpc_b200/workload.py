@@ -111,3 +111,4 @@ def speed_command_references(problem, B, max_dv=0.2):
 # ---- LocoProblem (MHPC/MHPC-Trajopt/Locomotion): whole-body-only locomotion trajectory optimisation, 1 s flypace plan.
 # Loco_TO.cpp:49-55 starts it from MHPC_NOMINAL; mhpc_batch is its perturbed batch.
 LOCO_DDP_SETTING = _os.path.join(_DATA, "MHPC/MHPC-Trajopt/Locomotion/settings/loco_ddp_setting.info")
+BARREL_TO_DDP_SETTING = _os.path.join(_DATA, "MHPC/MHPC-Trajopt/BarrelRoll/setting/br_ddp_setting.info")   # in-place barrel roll (BarrelRollTO.cpp)

@@ -83,6 +83,11 @@ typedef struct {
   /* WB path-constraint set. 0/0 = MHPCProblem (torque, joint, min height, GRF; MHPCProblem.cpp:436-481);
    * 1/1 = LocoProblem (torque and GRF only; Locomotion/LocoProblem.cpp:64-82) */
   int no_joint_limit, no_min_height;
+  /* BarrelRoll::JointSpeedLimit (BarrelRoll/BarrelRollConstraints.cpp:151-193, .h:71-72): qJd - lb >= 0, -qJd + ub >= 0 on the twelve
+   * joint rates, attached between the torque and the joint-limit barrier (BarrelRollTO.cpp:190-198). 0 = absent (MHPC, Loco). */
+  int joint_speed_limit;
+  CafeRebParam reb_jointvel;
+  double jointvel_lb, jointvel_ub;
 } CafePhase;
 
 typedef struct {

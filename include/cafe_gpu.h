@@ -11,6 +11,7 @@
  *   cafe_deck_build_mhpc     MHPCProblem<T>::initialization MHPC/MHPC-Trajopt/MHPCProblem.cpp:13-250
  *   cafe_deck_build_loco     LocoProblem<T> (initialize_parameters, create_problem_one_phase)
  *                                                         MHPC/MHPC-Trajopt/Locomotion/LocoProblem.cpp:7-84
+ *   cafe_deck_build_barrel_to / cafe_barrel_to_initial_guess   main() of MHPC/MHPC-Trajopt/BarrelRoll/BarrelRollTO.cpp:65-275
  *   cafe_hkd_state           compute_hkd_state            HKDMPC/HKD-TrajOpt/HKDModel.h:66-96
  *   cafe_gpu_create          MultiPhaseDDP<T>::set_multiPhaseProblem  HSDDPSolver/header/MultiPhaseDDP.h:33-42
  *   cafe_gpu_solve_batch     MultiPhaseDDP<T>::set_initial_condition + solve
@@ -59,6 +60,14 @@ int cafe_deck_build_mhpc(const char* reference_csv, const char* mhpc_config_info
  * phases carry the torque-limit and GRF barriers only (no joint-limit / min-height barrier), touchdown constraints as in MHPC. */
 int cafe_deck_build_loco(const char* reference_csv, const char* loco_config_info, const char* settings_root,
                          int k0, CafeDeckHandle** out);
+/* In-place barrel roll (MHPC/MHPC-Trajopt/BarrelRoll/BarrelRollTO.cpp:65-275): six hand-scheduled whole-body phases
+ * (stance, right pair, flight, stance, flight, stance; switching times :70), per-phase weight sets from br_cost_weights.JSON, fixed
+ * desired states (:277-339), the BarrelRoll:: barriers incl. the joint-speed limit (br_constraint_params.info), four-foot touchdown
+ * constraints at the end of both flight phases. No reference file. */
+int cafe_deck_build_barrel_to(const char* cost_weights_json, const char* constraint_params_info, CafeDeckHandle** out);
+/* The state trajectory BarrelRollTO.cpp:131-147 starts from (linear interpolation between the desired states; phase 0 from x0) as
+ * packed guesses for cafe_gpu_set_initial_guess: x0 = host [B][36], guess = host [B][cafe_solution_size(deck)] (controls, gains zero). */
+int cafe_barrel_to_initial_guess(const CafeDeck* deck, const double* x0, int B, double* guess);
 const CafeDeck* cafe_deck_get(const CafeDeckHandle* h);
 void cafe_deck_free(CafeDeckHandle* h);
 /* Structural non-zero pattern the backward sweep assumes for one LQ array of a running knot, as a bit mask (bit i + rows * j):

@@ -71,6 +71,21 @@ class LocoProblem : public MHPCProblem {
   }
 };
 
+// The in-place barrel roll built by main() of MHPC/MHPC-Trajopt/BarrelRoll/BarrelRollTO.cpp:65-275 (no problem class in the reference)
+class BarrelRollProblem : public ProblemBase {
+ public:
+  void initialization(const std::string& br_cost_weights_json, const std::string& br_constraint_params_info) {
+    if (h_) { cafe_deck_free(h_); h_ = nullptr; }
+    check(cafe_deck_build_barrel_to(br_cost_weights_json.c_str(), br_constraint_params_info.c_str(), &h_));
+  }
+  // interpolated initial state trajectories (BarrelRollTO.cpp:131-147) as packed guesses for MultiPhaseDDP::set_initial_guess
+  std::vector<double> initial_guess(const double* x0, int B) const {
+    std::vector<double> g((size_t)B * (size_t)cafe_solution_size(deck()));
+    check(cafe_barrel_to_initial_guess(deck(), x0, B, g.data()));
+    return g;
+  }
+};
+
 class MultiPhaseDDP {
  public:
   MultiPhaseDDP() {}

@@ -69,6 +69,8 @@ class WBPhase : public Phase {
   void build_model() override {
     /* MHPCProblem.cpp:436-481: Torque, Joint, MinHeight, then GRF when any foot is in contact */
     PathConstraint tq; tq.kind = 0; tq.create(24, h, n, m, p, ph->reb_torque); pcon.push_back(tq);
+    /* BarrelRollTO.cpp:190-198: the joint-speed barrier sits between the torque and the joint-limit barrier */
+    if (ph->joint_speed_limit) { PathConstraint jv; jv.kind = 4; jv.create(24, h, n, m, p, ph->reb_jointvel); pcon.push_back(jv); }
     /* LocoProblem.cpp:64-82 keeps Torque and GRF only */
     if (!ph->no_joint_limit) { PathConstraint jl; jl.kind = 1; jl.create(24, h, n, m, p, ph->reb_joint); pcon.push_back(jl); }
     if (!ph->no_min_height) { PathConstraint mh; mh.kind = 2; mh.create(1, h, n, m, p, ph->reb_minheight); pcon.push_back(mh); }
@@ -439,6 +441,7 @@ class WBPhase : public Phase {
       if (pc.kind == 0) for (int i = 0; i < 12; ++i) { pc.data[k][i].g = -u[i] - (-ph->torque_limit); pc.data[k][12 + i].g = u[i] - (-ph->torque_limit); }
       else if (pc.kind == 1) for (int i = 0; i < 12; ++i) { pc.data[k][i].g = x[6 + i] - ph->joint_lb[i % 3]; pc.data[k][12 + i].g = -x[6 + i] - (-ph->joint_ub[i % 3]); }
       else if (pc.kind == 2) pc.data[k][0].g = x[2] - ph->h_min;
+      else if (pc.kind == 4) for (int i = 0; i < 12; ++i) { pc.data[k][i].g = x[24 + i] - ph->jointvel_lb; pc.data[k][12 + i].g = -x[24 + i] - (-ph->jointvel_ub); }
       else {
         int i = 0;
         const double mu = ph->mu;
@@ -457,6 +460,7 @@ class WBPhase : public Phase {
       if (pc.kind == 0) for (int i = 0; i < 12; ++i) { pc.data[k][i].gu.assign(12, 0.0); pc.data[k][i].gu[i] = -1; pc.data[k][12 + i].gu.assign(12, 0.0); pc.data[k][12 + i].gu[i] = 1; }
       else if (pc.kind == 1) for (int i = 0; i < 12; ++i) { pc.data[k][i].gx.assign(36, 0.0); pc.data[k][i].gx[6 + i] = 1; pc.data[k][12 + i].gx.assign(36, 0.0); pc.data[k][12 + i].gx[6 + i] = -1; }
       else if (pc.kind == 2) { pc.data[k][0].gx.assign(36, 0.0); pc.data[k][0].gx[2] = 1; }
+      else if (pc.kind == 4) for (int i = 0; i < 12; ++i) { pc.data[k][i].gx.assign(36, 0.0); pc.data[k][i].gx[24 + i] = 1; pc.data[k][12 + i].gx.assign(36, 0.0); pc.data[k][12 + i].gx[24 + i] = -1; }
       else {
         int i = 0;
         const double mu = ph->mu;

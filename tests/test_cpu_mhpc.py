@@ -407,3 +407,55 @@ def test_oracle_joint_and_height_barriers_matter(cm, mhpc, mhpc_options):
         d2.phase[i].no_joint_limit = 1; d2.phase[i].no_min_height = 1
     i1, _, _, _ = oracle_solve(C.pointer(d2), mhpc_options, x0)
     assert i0["cost"] != i1["cost"] and i0["status"] == i1["status"] == 0   # (-log barriers of well-satisfied constraints are negative: the cost goes up)
+
+
+# ---- next tier: the in-place barrel roll of BarrelRoll/BarrelRollTO.cpp
+def test_barrel_to_deck_and_guess(cm):
+    """Six hand-scheduled whole-body phases (switching times 0, .12, .33, .75, .90, 1.10, 1.25 s), fixed desired states, per-phase
+    weights, joint-speed barrier on every phase, four-foot touchdown constraints after both flight phases, interpolated initial states."""
+    from cafe_mpc_b200 import mpc, workload
+    prob = cm.BarrelRollProblem()
+    ph = prob.phases()
+    g = np.load(os.path.join(REPO, "tests/golden/barrel_to.npz"))
+    assert np.array_equal(np.array([[p.model, p.horizon] + list(p.contact) + [p.n_td, p.joint_speed_limit] for p in ph]), g["phases"])
+    assert [p.horizon for p in ph] == [12, 21, 42, 15, 20, 15]
+    assert [tuple(p.contact) for p in ph] == [(1, 1, 1, 1), (0, 1, 0, 1), (0, 0, 0, 0), (1, 1, 1, 1), (0, 0, 0, 0), (1, 1, 1, 1)]
+    assert [p.n_td for p in ph] == [0, 0, 4, 0, 4, 0] and all(p.joint_speed_limit == 1 and p.no_joint_limit == 0 and p.h_min == 0.13 for p in ph)
+    assert ph[0].dt == 0.01 and (ph[0].jointvel_lb, ph[0].jointvel_ub) == (-20.0, 20.0) and ph[0].reb_jointvel.delta == 0.1
+    assert list(ph[0].w_footreg) == [0, 0, 0] and list(ph[0].w_swingpos) == [0, 0, 0] and list(ph[0].w_tdvel) == [0, 0, 0]
+    # weights of cost_phase_1 / cost_phase_2 (br_cost_weights.JSON), desired states (BarrelRollTO.cpp:277-339)
+    assert list(ph[0].q)[:6] == [0.0, 5.0, 10.0, 2.0, 2.0, 2.0] and ph[0].r[0] == 0.2 and ph[1].r[0] == 0.05 and list(ph[1].qf)[18:24] == [1.0, 1.0, 5.0, 1.0, 1.0, 5.0]
+    rec = prob.reference_records()
+    x1 = rec[ph[1].knot_offset, :36]
+    assert np.allclose(x1[:6], [0, -0.25, 0.33, 0, 0, 0.5 * math.pi]) and np.allclose(x1[6:12], [math.pi / 6, -1.0, 2.0, -math.pi / 5, -0.5, 1.0]) and x1[23] == 3.0 * math.pi
+    assert np.array_equal(rec[ph[5].knot_offset, :36], rec[ph[4].knot_offset, :36]) and rec[ph[3].knot_offset, 5] == 2 * math.pi and rec[ph[3].knot_offset, 23] == 0
+    # interpolated initial states: phase 0 starts at x0 and ends (float time arithmetic) next to xf_des[0]; controls and gains are zero
+    x0 = workload.mhpc_batch(4)
+    gs = prob.initial_guess(x0)
+    parts = mpc.unpack_batch(prob, gs)
+    assert np.array_equal(parts[0]["Xbar"][:, 0], x0)
+    assert np.allclose(parts[0]["Xbar"][2, -1], rec[0, :36], atol=1e-6) and np.allclose(parts[3]["Xbar"][1, 0], rec[ph[2].knot_offset, :36], atol=1e-12)
+    assert all(not r["Ubar"].any() and not r["K"].any() for r in parts)
+    assert np.array_equal(np.concatenate([r["Xbar"][0] for r in parts]), g["guess_xbar_0"])
+    # hand check of one interpolated knot with the reference's float arithmetic: s = float(t) / float(dur), t accumulated in float
+    t = np.float32(0.0)
+    for _ in range(5):
+        t = np.float32(np.float64(t) + 0.01)
+    s = float(t / np.float32(0.33 - 0.12))
+    xa, xb = rec[0, :36], rec[ph[1].knot_offset, :36]
+    assert np.array_equal(parts[1]["Xbar"][0, 5], xa + (xb - xa) * s)
+
+
+def test_oracle_barrel_to_matches_committed_golden(cm):
+    from cafe_mpc_b200 import workload
+    g = np.load(os.path.join(REPO, "tests/golden/barrel_to.npz"))
+    prob = cm.BarrelRollProblem()
+    opt = cm.load_hsddp_setting(workload.BARREL_TO_DDP_SETTING)
+    assert (opt.max_AL_iter, opt.max_DDP_iter) == (30, 10)
+    opt.max_AL_iter = 5   # the golden's caps (the full caps take ~30 s per problem on the CPU)
+    x0 = workload.mhpc_batch(4)
+    info, hist, trace, sol = oracle_solve(prob.deck, opt, x0[0], cap=320, guess=prob.initial_guess(x0)[0])
+    assert [info[k] for k in ("status", "iter", "ls_iter_total", "reg_iter_total", "outer_iter", "n_hist")] == list(g["counts_0"])
+    np.testing.assert_allclose(hist[:, 0], g["hist_0"][:, 0], rtol=1e-9)
+    np.testing.assert_allclose(sol, g["sol_0"], rtol=0, atol=1e-8 * np.abs(sol).max())
+    assert hist[-1, 0] < 0.05 * hist[0, 0]   # 3 635 -> 125: the roll is being found

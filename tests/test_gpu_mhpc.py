@@ -354,3 +354,56 @@ def test_mhpc_deck_without_joint_and_height_barriers_matches_oracle(cm, opt):
     compare_with_oracle(cm, p2, opt, x0, s, (0, 2))
     s0 = solve_gpu(cm, base, opt, x0)
     assert s0.get_solver_info()[2]["cost"] != s.get_solver_info()[2]["cost"]
+
+
+# ---- next tier: in-place barrel roll (BarrelRollTO.cpp): joint-speed barrier, per-phase weights, fixed desired
+#      states, two four-foot landings, solve started from the interpolated state trajectory
+def test_barrel_to_matches_oracle_and_golden(cm):
+    """The solve starts from a wildly infeasible interpolated trajectory (defect norm 57, cost 3 635) and differences of 1e-11 in the
+    first sweep grow by a factor 3-5 per iteration while the roll is being found (1e-6 at worst around iteration 30) before they
+    collapse again at convergence: every DECISION (iteration, line-search, regularisation and AL counters) still matches the oracle bit
+    for bit, the first iteration matches per knot at 1e-11, the final cost at the full 30 x 10 caps at 1e-8."""
+    from cafe_mpc_b200 import workload
+    prob = cm.BarrelRollProblem()
+    fopt = cm.load_hsddp_setting(workload.BARREL_TO_DDP_SETTING)
+    g = np.load(os.path.join(REPO, "tests/golden/barrel_to.npz"))
+    x0 = workload.mhpc_batch(4)
+    guess = prob.initial_guess(x0)
+    s = cm.MultiPhaseDDP(prob, 0, 4)
+    s.set_initial_condition(x0)
+    s.set_initial_guess(guess)
+    # (1) first iteration, per knot: LQ data incl. the joint-speed barrier terms, the two four-foot impact maps, every sweep product
+    o1 = copy.copy(fopt)
+    o1.max_DDP_iter = 1; o1.max_AL_iter = 1; o1.cost_thresh = 1e30; o1.dynamics_feas_thresh = 1e30
+    s.solve(o1)
+    for b in (0, 2):
+        oracle_solve(prob.deck, o1, x0[b], guess=guess[b])
+        for ph in range(6):
+            for name in ("X", "U", "Y", "Defect", "l", "lx", "lu", "ly", "lxx", "luu", "lyy", "A", "B", "C", "D", "Phix", "Phixx"):
+                assert relerr(s.debug_get(name, ph, b), oracle_get(name, ph)) < 1e-11, (name, ph)
+            for name in ("Quu", "Qux", "Qu", "K", "dU", "G", "dX"):
+                assert relerr(s.debug_get(name, ph, b), oracle_get(name, ph)) < 1e-10, (name, ph)
+        for ph in range(5):
+            assert relerr(s.debug_get("Px", ph, b), oracle_get("Px", ph)) < 1e-11, ph
+    # (2) 5 x 10 caps against the committed golden and the oracle: counters bit-exact, costs within the amplification described above
+    bopt = copy.copy(fopt)
+    bopt.max_AL_iter = 5
+    s.solve(bopt)
+    info = s.get_solver_info(); hist = s.get_history(320); sol = s.get_solution()
+    for b in (0, 3):
+        assert [info[b][k] for k in COUNTS] == list(g["counts_%d" % b]), (b, info[b])
+        np.testing.assert_allclose(hist[b, :3, 0], g["hist_%d" % b][:3, 0], rtol=2e-9)
+        np.testing.assert_allclose(hist[b, :info[b]["n_hist"], 0], g["hist_%d" % b][:, 0], rtol=1e-5)
+        gp, op = cm.unpack_solution(prob.deck, sol[b]), cm.unpack_solution(prob.deck, g["sol_%d" % b])
+        for pg, po in zip(gp, op):
+            for name in ("Xbar", "Ubar", "Y"):
+                assert relerr(pg[name], po[name]) < 1e-4, (b, name)
+    oi, oh, ot, osol = oracle_solve(prob.deck, bopt, x0[1], cap=320, guess=guess[1])
+    assert [info[1][k] for k in COUNTS] == [oi[k] for k in COUNTS]
+    # (3) full caps, problem 0: 300 iterations / ~2 100 line-search trials decided identically, same final cost
+    s.solve(fopt)
+    i0 = s.get_solver_info()[0]
+    oi, oh, ot, osol = oracle_solve(prob.deck, fopt, x0[0], cap=320, guess=guess[0])
+    assert [i0[k] for k in COUNTS] == [oi[k] for k in COUNTS]
+    assert abs(i0["cost"] - oi["cost"]) < 1e-8 * abs(oi["cost"]) and abs(i0["max_tconstr"] - oi["max_tconstr"]) < 1e-6 * abs(oi["max_tconstr"])
+    assert oi["cost"] < 0.01 * oh[0, 0] and oi["max_tconstr"] < fopt.tconstr_thresh   # the roll was found, both landings enforced

@@ -67,3 +67,21 @@ for b in (0, 3):
     out["final_%d" % b] = np.array([i["cost"], i["feas"], i["max_tconstr"], i["max_pconstr"]])
     print("loco", b, i)
 np.savez_compressed(os.path.join(R, "tests/golden/loco_flypace.npz"), **out)
+
+# ---- in-place barrel roll (BarrelRoll/BarrelRollTO.cpp): six hand-scheduled WB phases, joint-speed barrier, interpolated initial states.
+# The full 30 x 10 caps take ~30 s per problem on the CPU (the solve runs into them); the golden uses 5 x 10.
+pb = cm.BarrelRollProblem()
+optb = cm.load_hsddp_setting(workload.BARREL_TO_DDP_SETTING)
+optb.max_AL_iter = 5
+x0b = workload.mhpc_batch(4)
+gb = pb.initial_guess(x0b)
+out = {"x0": x0b, "guess_xbar_0": np.concatenate([r["Xbar"][0] for r in __import__("cafe_mpc_b200.mpc", fromlist=["x"]).unpack_batch(pb, gb)]),
+       "phases": np.array([[p.model, p.horizon] + list(p.contact) + [p.n_td, p.joint_speed_limit] for p in pb.phases()])}
+for b in (0, 3):
+    i, h, t, s = oracle_solve(pb.deck, optb, x0b[b], cap=320, guess=gb[b])
+    out["counts_%d" % b] = np.array([i[k] for k in ("status", "iter", "ls_iter_total", "reg_iter_total", "outer_iter", "n_hist")])
+    out["hist_%d" % b] = h
+    out["sol_%d" % b] = s
+    out["final_%d" % b] = np.array([i["cost"], i["feas"], i["max_tconstr"], i["max_pconstr"]])
+    print("barrel_to", b, i)
+np.savez_compressed(os.path.join(R, "tests/golden/barrel_to.npz"), **out)
