@@ -31,7 +31,7 @@ class Phase(C.Structure):
         ("al_td", AlParam), ("mu", C.c_double), ("ground_height", C.c_double),
         ("h_min", C.c_double), ("torque_limit", C.c_double), ("joint_lb", C.c_double * 3), ("joint_ub", C.c_double * 3),
         ("no_joint_limit", C.c_int), ("no_min_height", C.c_int),
-        ("joint_speed_limit", C.c_int), ("reb_jointvel", RebParam), ("jointvel_lb", C.c_double), ("jointvel_ub", C.c_double),
+        ("joint_speed_limit", C.c_int), ("reb_jointvel", RebParam), ("jointvel_lb", C.c_double), ("jointvel_ub", C.c_double), ("single_shooting", C.c_int),
     ]
 
 

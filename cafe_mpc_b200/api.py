@@ -72,12 +72,19 @@ class HKDProblem(_DeckOwner):
 class MHPCProblem(_DeckOwner):
     """MHPCProblem<T>::initialization (MHPCProblem.cpp:13-250) from mhpc_config.info."""
 
-    def __init__(self, reference_csv, mhpc_config=None, settings_root=None, k0=0):
+    def __init__(self, reference_csv, mhpc_config=None, settings_root=None, k0=0, mpc_update_nsteps=0):
+        """mpc_update_nsteps > 0: the deck stands for the problem after MHPCProblem::update (shift of nsteps = dt_mpc / dt_wb knots)
+        rather than after initialization(): a freshly opened tail phase (horizon <= nsteps) has no shooting states (MHPCProblem.cpp:366-369)."""
         super().__init__()
         mhpc_config = mhpc_config or os.path.join(DATA, "MHPC/settings/mhpc_config.info")
         settings_root = settings_root or DATA  # plays the role of the reference's "../"
         check(lib.cafe_deck_build_mhpc(reference_csv.encode(), mhpc_config.encode(), settings_root.encode(), k0,
                                        C.byref(self._h)))
+        self.single_shooting_phase = -1
+        if mpc_update_nsteps > 0:
+            r = C.c_int(-1)
+            check(lib.cafe_deck_mark_mpc_update(self._h, mpc_update_nsteps, C.byref(r)))
+            self.single_shooting_phase = r.value
 
 
 class LocoProblem(_DeckOwner):

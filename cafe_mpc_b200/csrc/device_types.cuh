@@ -35,7 +35,7 @@
 struct PhaseDev {
   int model, n, m, p, h, n_next, has_next;
   int contact[4], next_contact[4], n_td, td_foot[4];
-  int no_joint_limit, no_min_height, joint_speed_limit;
+  int no_joint_limit, no_min_height, joint_speed_limit, single_shooting;
   CafeRebParam reb_jointvel;  // BarrelRoll::JointSpeedLimit
   double jointvel_lb, jointvel_ub;
    // WB path-constraint set (CafePhase: LocoProblem drops the joint-limit and min-height barriers)

@@ -111,6 +111,19 @@ extern "C" int cafe_barrel_to_initial_guess(const CafeDeck* deck, const double* 
   return 0;
 }
 
+extern "C" int cafe_deck_mark_mpc_update(CafeDeckHandle* h, int nsteps, int* marked_phase) {
+  if (!h || nsteps < 1 || !marked_phase) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
+  *marked_phase = -1;
+  CafeDeck& d = h->st.deck;
+  int last = -1;
+  for (int i = 0; i < d.n_phases; ++i) if (d.phase[i].model != CAFE_MODEL_SRB) last = i;
+  if (last < 0) return 0;
+  // MHPCProblem.cpp:366-369: every phase but a tail phase not longer than the shift gets update_SS_config(h + 1); a tail phase that
+  // short was opened by this very update (an older one has grown past nsteps), its SS_set is still empty (SinglePhase.cpp:34)
+  if (d.phase[last].horizon <= nsteps) { d.phase[last].single_shooting = 1; *marked_phase = last; }
+  return 0;
+}
+
 extern "C" const CafeDeck* cafe_deck_get(const CafeDeckHandle* h) { return h ? &h->st.deck : nullptr; }
 extern "C" void cafe_deck_free(CafeDeckHandle* h) { delete h; }
 

@@ -32,6 +32,40 @@
 namespace cafe_dev {
 
 // ------------------------------------------------------------------------------------------- K-ROLL
+// State of knot k of a phase WITHOUT shooting states (PhaseDev::single_shooting; SinglePhase.cpp:187-221 with an empty SS_set): the
+// phase is integrated from the state the previous phase hands over (its trial end state through the reset map; the solver's x0 for
+// the first phase), U = Ubar + eps dU + K (X - Xbar). Such a phase is the freshly opened tail of an MPC update, at most dt_mpc / dt
+// knots long, so every knot's thread simply repeats the short chain (same routine, same inputs: bit-identical across threads).
+template <class Model>
+__device__ __noinline__ void single_shooting_state(const SolverDev& S, int pi, int k, int a, int b, double* x) {
+  constexpr int N = Model::N, M = Model::M, PY = Model::PY;
+  const PhaseDev& ph = S.ph[pi];
+  const int ldb = S.ldb;
+  const double eps = S.eps[a];
+  if (pi == 0) {
+    for (int i = 0; i < N; ++i) x[i] = S.x0[(size_t)i * ldb + b];
+  } else {
+    const PhaseDev& pv = S.ph[pi - 1];
+    double xe[N];
+    for (int i = 0; i < N; ++i) xe[i] = pv.Xbar[gix(pv.h, N, i, ldb, b)] + eps * pv.dX[gix(pv.h, N, i, ldb, b)];
+    Model::resetmap(pv, xe, x);
+  }
+  double rec_local[CAFE_REF_W];
+  for (int kk = 0; kk < k; ++kk) {
+    const double* rec = knot_record(ph, kk, ldb, b, rec_local);
+    double u[M], xn[N], y[PY > 0 ? PY : 1], l, ming;
+    for (int i = 0; i < M; ++i) u[i] = 0;
+    const double* Kg = ph.K + gix(kk, M * N, 0, ldb, b);
+    for (int j = 0; j < N; ++j) {
+      const double dj = x[j] - ph.Xbar[gix(kk, N, j, ldb, b)];
+      for (int i = 0; i < M; ++i) u[i] += Kg[(size_t)(i + M * j) * ldb] * dj;
+    }
+    for (int i = 0; i < M; ++i) u[i] = ph.Ubar[gix(kk, M, i, ldb, b)] + eps * ph.dU[gix(kk, M, i, ldb, b)] + u[i];
+    Model::roll(ph, rec, x, u, xn, y, S.opt.ReB_active != 0, l, ming);
+    for (int i = 0; i < N; ++i) x[i] = xn[i];
+  }
+}
+
 template <class Model>
 __device__ void roll_knot(const SolverDev& S, int pi, int k, int a, int b) {
   constexpr int N = Model::N, M = Model::M, PY = Model::PY;
@@ -43,10 +77,12 @@ __device__ void roll_knot(const SolverDev& S, int pi, int k, int a, int b) {
   const size_t aX = (size_t)a * (h + 1) * N * ldb, aU = (size_t)a * h * M * ldb, aY = (size_t)a * h * PY * ldb;
   const size_t aS = (size_t)a * (h + 1) * ldb;
   double x[N], dlt[N];
+  const bool ss = ph.single_shooting != 0;
+  if (ss) single_shooting_state<Model>(S, pi, k, a, b, x);
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     const double xb = ph.Xbar[gix(k, N, i, ldb, b)];
-    x[i] = xb + eps * ph.dX[gix(k, N, i, ldb, b)];
+    if (!ss) x[i] = xb + eps * ph.dX[gix(k, N, i, ldb, b)];
     dlt[i] = x[i] - xb;
     ph.Xt[aX + gix(k, N, i, ldb, b)] = x[i];
   }
@@ -78,7 +114,7 @@ __device__ void roll_knot(const SolverDev& S, int pi, int k, int a, int b) {
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       nrm += xn[i] * xn[i];
-      const double xs = ph.Xbar[gix(k + 1, N, i, ldb, b)] + eps * ph.dX[gix(k + 1, N, i, ldb, b)];
+      const double xs = ss ? xn[i] : ph.Xbar[gix(k + 1, N, i, ldb, b)] + eps * ph.dX[gix(k + 1, N, i, ldb, b)];  // X[k+1] = Xsim[k+1] without shooting states
       const double d = xn[i] - xs;
       ph.Dt[aX + gix(k + 1, N, i, ldb, b)] = d;
       dsq += d * d;
@@ -116,7 +152,7 @@ __device__ void roll_knot(const SolverDev& S, int pi, int k, int a, int b) {
       Model::resetmap(ph, x, xr);
       const size_t aXn = (size_t)a * (nx.h + 1) * nx.n * ldb;
       for (int i = 0; i < nx.n; ++i) {
-        const double xs = nx.Xbar[gix(0, nx.n, i, ldb, b)] + eps * nx.dX[gix(0, nx.n, i, ldb, b)];
+        const double xs = nx.single_shooting ? xr[i] : nx.Xbar[gix(0, nx.n, i, ldb, b)] + eps * nx.dX[gix(0, nx.n, i, ldb, b)];
         const double d = xr[i] - xs;
         nx.Dt[aXn + gix(0, nx.n, i, ldb, b)] = d;
         dsq += d * d;

@@ -340,6 +340,7 @@ extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, 
   if (n_knots > CAFE_MAX_KNOTS) { cafe::set_last_error("horizon too long"); return CAFE_ERR_UNSUPPORTED; }
   for (int i = 0; i < deck->n_phases; ++i) {
     const CafePhase& p = deck->phase[i];
+    if (p.single_shooting && i > 0 && deck->phase[i - 1].model != p.model) { cafe::set_last_error("a single-shooting phase must follow a phase of the same model"); return CAFE_ERR_UNSUPPORTED; }
     if (p.reb_grf.delta < p.reb_grf.delta_min || p.reb_torque.delta < p.reb_torque.delta_min || p.reb_joint.delta < p.reb_joint.delta_min ||
         p.reb_minheight.delta < p.reb_minheight.delta_min || (p.joint_speed_limit && p.reb_jointvel.delta < p.reb_jointvel.delta_min)) { cafe::set_last_error("ReB delta < delta_min is not supported"); return CAFE_ERR_UNSUPPORTED; }
   }
@@ -364,6 +365,7 @@ extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, 
     for (int l = 0; l < 4; ++l) { d.contact[l] = p.contact[l]; d.next_contact[l] = p.next_contact[l]; d.td_foot[l] = p.td_foot[l]; }
     d.n_td = p.n_td; d.dt = p.dt; d.mu = p.mu; d.ground_height = p.ground_height; d.BG_alpha = deck->BG_alpha;
     d.h_min = p.h_min; d.torque_limit = p.torque_limit; d.no_joint_limit = p.no_joint_limit; d.no_min_height = p.no_min_height;
+    d.single_shooting = p.single_shooting;
     d.joint_speed_limit = p.joint_speed_limit; d.reb_jointvel = p.reb_jointvel; d.jointvel_lb = p.jointvel_lb; d.jointvel_ub = p.jointvel_ub;
     for (int l = 0; l < 3; ++l) { d.joint_lb[l] = p.joint_lb[l]; d.joint_ub[l] = p.joint_ub[l]; }
     std::memcpy(d.q, p.q, sizeof(d.q)); std::memcpy(d.r, p.r, sizeof(d.r)); std::memcpy(d.qf, p.qf, sizeof(d.qf));

@@ -88,6 +88,11 @@ typedef struct {
   int joint_speed_limit;
   CafeRebParam reb_jointvel;
   double jointvel_lb, jointvel_ub;
+  /* 1 = the phase has no shooting states (SS_set empty): hybrid_rollout integrates it sequentially from the state the previous phase
+   * hands over, X[k+1] = Xsim[k+1], zero defects (SinglePhase.cpp:187-221). The reference leaves the tail whole-body phase like that
+   * in the MPC update that opens it, until it is longer than the shift (MHPCProblem.cpp:366-369); 0 = every knot is a shooting
+   * state (update_SS_config(h + 1)). Supported when the previous phase (if any) has the same model. */
+  int single_shooting;
 } CafePhase;
 
 typedef struct {

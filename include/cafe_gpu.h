@@ -68,6 +68,10 @@ int cafe_deck_build_barrel_to(const char* cost_weights_json, const char* constra
 /* The state trajectory BarrelRollTO.cpp:131-147 starts from (linear interpolation between the desired states; phase 0 from x0) as
  * packed guesses for cafe_gpu_set_initial_guess: x0 = host [B][36], guess = host [B][cafe_solution_size(deck)] (controls, gains zero). */
 int cafe_barrel_to_initial_guess(const CafeDeck* deck, const double* x0, int B, double* guess);
+/* Marks a deck built at a later start offset as the product of MHPCProblem::update (MHPCProblem.cpp:252-372) rather than of
+ * initialization(): a tail whole-body phase not longer than the shift (nsteps = round(dt_mpc / dt_wb)) was opened by that update and has
+ * no shooting states yet (:366-369) -> CafePhase::single_shooting. *marked_phase = index of that phase, -1 if there is none. */
+int cafe_deck_mark_mpc_update(CafeDeckHandle* h, int nsteps, int* marked_phase);
 const CafeDeck* cafe_deck_get(const CafeDeckHandle* h);
 void cafe_deck_free(CafeDeckHandle* h);
 /* Structural non-zero pattern the backward sweep assumes for one LQ array of a running knot, as a bit mask (bit i + rows * j):

@@ -196,8 +196,10 @@ void Phase::linear_rollout(double eps) {
  * (update_SS_config(h+1): HKDProblem.cpp:105, MHPCProblem.cpp:209,243). */
 bool Phase::hybrid_rollout(double eps, bool MS) {
   Xsim[0] = x_init;
+  const bool ss = ph->single_shooting != 0;  /* empty SS_set: the freshly opened tail phase of an MPC update (MHPCProblem.cpp:366-369) */
   /* SS_set.front()==0 */
-  for (int i = 0; i < n; ++i) X[0][i] = Xbar[0][i] + eps * dX[0][i];
+  if (!ss) for (int i = 0; i < n; ++i) X[0][i] = Xbar[0][i] + eps * dX[0][i];
+  else X[0] = x_init;
   for (int k = 0; k < h; ++k) {
     Vec dx(n);
     for (int i = 0; i < n; ++i) dx[i] = X[k][i] - Xbar[k][i];
@@ -207,7 +209,7 @@ bool Phase::hybrid_rollout(double eps, bool MS) {
     double nrm = 0;
     for (int i = 0; i < n; ++i) nrm += Xsim[k + 1][i] * Xsim[k + 1][i];
     if (std::sqrt(nrm) > 1e6) return false;
-    if (MS) { for (int i = 0; i < n; ++i) X[k + 1][i] = Xbar[k + 1][i] + eps * dX[k + 1][i]; }
+    if (MS && !ss) { for (int i = 0; i < n; ++i) X[k + 1][i] = Xbar[k + 1][i] + eps * dX[k + 1][i]; }
     else X[k + 1] = Xsim[k + 1];
     path_constraints(X[k], U[k], Y[k], k);
   }

@@ -245,7 +245,9 @@ def test_per_problem_references_match_oracle(cm, opt):
 def test_receding_horizon_warm_start_matches_oracle(cm, opt):
     """SURVEY §8(f)1 (first slice): receding-horizon re-solves. The plan is shifted by dt_mpc / dt_wb = 2 knots per step (phase removal
     at k0 = 12, a new one-knot phase opened at the tail), the previous solution becomes the warm-start guess (cafe_mpc_b200/mpc.py),
-    and the re-solve runs under the run-time iteration caps (max_AL_iter_runtime x max_DDP_iter_runtime). GPU == oracle at every step."""
+    and the re-solve runs under the run-time iteration caps (max_AL_iter_runtime x max_DDP_iter_runtime). GPU == oracle at every step.
+    The decks are marked as products of MHPCProblem::update: the one-knot tail phase opened at k0 = 12 has no shooting states in that
+    step (MHPCProblem.cpp:366-369) and is integrated sequentially from the state the previous phase hands over."""
     from cafe_mpc_b200 import mpc, workload
     ort = copy.copy(opt)
     ort.max_AL_iter = opt.max_AL_iter_runtime; ort.max_DDP_iter = opt.max_DDP_iter_runtime
@@ -256,7 +258,8 @@ def test_receding_horizon_warm_start_matches_oracle(cm, opt):
     sol = s.get_solution()
     for step in range(3):
         k1 = k0 + 2
-        p1 = cm.MHPCProblem(CSV, k0=k1)
+        p1 = cm.MHPCProblem(CSV, k0=k1, mpc_update_nsteps=2)
+        assert p1.single_shooting_phase == (1 if k1 == 12 else -1)
         guess = mpc.shifted_guess_batch(prob, k0, p1, k1, sol)
         # the "measured" state of the next step: the plan's own prediction two knots ahead, nudged
         x1 = np.stack([mpc.state_at(prob, cm.unpack_solution(prob.deck, sol[b]), 2) for b in range(B)]) + 1e-3 * (x0 - x0[0])
@@ -273,6 +276,16 @@ def test_receding_horizon_warm_start_matches_oracle(cm, opt):
             for pg, po in zip(gp, op):
                 for name in ("Xbar", "Ubar", "Y", "K", "dU", "Qu", "Quu", "Qux", "G"):
                     assert relerr(pg[name], po[name], FLOOR.get(name, 1e-6)) < RTOL, (step, b, name)
+        if k1 == 12:
+            # no shooting states in the tail phase: its defects vanish identically, and the flag is live (an all-shooting deck at the
+            # same offset ends elsewhere)
+            for b in range(B):
+                assert not np.any(s1.debug_get("Defect", 1, b))
+            p1ms = cm.MHPCProblem(CSV, k0=k1)
+            s2 = cm.MultiPhaseDDP(p1ms, 0, B)
+            s2.set_initial_condition(x1); s2.set_initial_guess(guess); s2.solve(ort)
+            assert all(a["cost"] != c["cost"] for a, c in zip(info, s2.get_solver_info()))
+            s2.close()
         # the warm start pays: same caps from the cold start end far from feasible
         s1.set_initial_guess(None)
         s1.solve(ort)

@@ -35,7 +35,7 @@ sol = s.get_solution() if mode == "host" else None
 for step in range(1, steps + 1):
     t0 = time.perf_counter()
     k1 = k0 + 2
-    p1 = cm.MHPCProblem(csv, k0=k1)
+    p1 = cm.MHPCProblem(csv, k0=k1, mpc_update_nsteps=2)   # deck after MHPCProblem::update: a freshly opened tail phase has no shooting states
     if mode == "host":
         guess = mpc.shifted_guess_batch(prob, k0, p1, k1, sol)
         x1 = mpc.state_at(prob, mpc.unpack_batch(prob, sol), 2) + noise
