@@ -52,11 +52,18 @@ class HKDProblem(_DeckOwner):
     HKDMPCSolver::initialize (HKDMPC.cpp:26-28) are the defaults."""
 
     def __init__(self, reference_csv, constraint_params=None, plan_duration=0.6, time_step=0.01,
-                 nsteps_between_mpc=2, k0=0):
+                 nsteps_between_mpc=2, k0=0, mpc_update=False):
+        """mpc_update: the deck stands for the problem after HKDProblem::update (HKDProblem.cpp:117-222) rather than after initialization():
+        a tail phase of at most 2 knots was opened by that update and has no shooting states yet (:213-217)."""
         super().__init__()
         constraint_params = constraint_params or os.path.join(DATA, "HKDMPC/settings/constraint_params.info")
         check(lib.cafe_deck_build_hkd(reference_csv.encode(), constraint_params.encode(), plan_duration, time_step,
                                       nsteps_between_mpc, k0, C.byref(self._h)))
+        self.single_shooting_phase = -1
+        if mpc_update:
+            r = C.c_int(-1)
+            check(lib.cafe_deck_mark_mpc_update(self._h, 2, C.byref(r)))   # the literal 2 of HKDProblem.cpp:213
+            self.single_shooting_phase = r.value
 
     def initial_state(self, body, qJ):
         """compute_hkd_state (HKDModel.h:66-96) with the first phase's contact."""

@@ -8,22 +8,28 @@ HSDDPSolver/source/TrajectoryManagement.cpp:130-228, SinglePhase.cpp:513-528) as
   * the SRB phase is NOT shifted while dt_mpc < dt_srb (update_SRB_plan: nsteps = floor(dt_mpc / dt_srb) = 0) - its arrays are kept,
   * everything else (dU, value function, Q terms) does not matter for the re-solve: MultiPhaseDDP::solve starts with
     hybrid_rollout(eps = 0), U = Ubar + K (X - Xbar).
+The same function serves the HKD application (HKDProblem::update, HKDMPC/HKD-TrajOpt/HKDProblem.cpp:117-222: identical front / back
+bookkeeping on its 24-state phases, no reduced-order tail, plus the quirk Ubar[0] = 0 of the front trajectory, :220).
 Differences to the reference, by construction: the last state copied is Xbar (the reference copies X, equal unless the final line search
-ended on a rejected trial); a phase opened at the tail by a contact change starts from the new deck's reference states (the reference
-constructs a fresh phase object there) and is a shooting phase from the start (MHPCProblem.cpp:366-369 keeps it single shooting until it
-is longer than the shift)."""
+ended on a rejected trial); a phase opened at the tail by a contact change is given the new deck's reference states where the reference
+constructs a fresh zero trajectory - immaterial once the deck is marked as an MPC update (MHPCProblem(..., mpc_update_nsteps=2),
+HKDProblem(..., mpc_update=True)): that phase then has no shooting states (MHPCProblem.cpp:366-369, HKDProblem.cpp:213-217), is integrated
+from the previous phase's hand-over state with zero gains, and its Xbar is never read."""
 import numpy as np
 
 from ._ctypes_defs import MODEL_DIMS
 
 WB = 1
+HKD = 0
 
 
 def _wb_ranges(problem, k0):
-    """[(phase index, absolute first knot, absolute last state index)] of the leading whole-body phases."""
+    """[(phase index, absolute first knot, absolute last state index)] of the leading full-order phases (whole-body for MHPC decks,
+    hybrid kinodynamic for HKD decks)."""
     out, s = [], k0
+    lead = problem.phases()[0].model
     for i, ph in enumerate(problem.phases()):
-        if ph.model != WB:
+        if ph.model != lead:
             break
         out.append((i, s, s + ph.horizon, tuple(ph.contact)))
         s += ph.horizon
@@ -75,10 +81,11 @@ def shift_guess(old_problem, old_k0, new_problem, new_k0, old_phases):
     last_state = np.asarray(old_phases[old_r[-1][0]]["Xbar"])[..., -1, :]
     old_end = old_r[-1][2]
     out = []
+    lead_model = new_problem.phases()[0].model
     for i, ph in enumerate(new_problem.phases()):
         n, m, p = MODEL_DIMS[ph.model]
         h = ph.horizon
-        if ph.model != WB:
+        if ph.model != lead_model:
             # trailing reduced-order phase: kept as it is when the horizons agree, else cold start from the reference
             j = len(old_r) + (i - len(new_r))
             if j < len(old_phases) and np.asarray(old_phases[j]["Ubar"]).shape[-2] == h:
@@ -103,6 +110,8 @@ def shift_guess(old_problem, old_k0, new_problem, new_k0, old_phases):
                 U[..., k, :] = np.asarray(old_phases[src[0][0]]["Ubar"])[..., a - src[0][1], :]
                 K[..., k, :, :] = np.asarray(old_phases[src[0][0]]["K"])[..., a - src[0][1], :, :]
         out.append({"Xbar": X, "Ubar": U, "K": K})
+    if lead_model == HKD and out[0]["Ubar"].shape[-2] > 0:
+        out[0]["Ubar"][..., 0, :] = 0.0                                 # HKDProblem.cpp:220
     assert d.n_phases == len(out)
     return out
 
@@ -111,7 +120,7 @@ def state_at(problem, phases, knots_ahead):
     """Planned whole-body state `knots_ahead` knots after the start of the plan (crossing phase boundaries: the post-reset state)."""
     k = knots_ahead
     for ph, r in zip(problem.phases(), phases):
-        if k < ph.horizon or ph.model != WB:
+        if k < ph.horizon or ph.model not in (WB, HKD):
             return np.array(np.asarray(r["Xbar"])[..., k, :])
         k -= ph.horizon
     raise ValueError("beyond the plan")

@@ -291,3 +291,39 @@ def test_structural_hkd_patterns_cover_the_oracle(cm):
             arr = oracle_get(name, ph).reshape(p.horizon, 24, 24).transpose(0, 2, 1)
             bad = (arr != 0) & ~masks[which][None]
             assert not bad.any(), (name, ph, np.argwhere(bad)[:4])
+
+
+def test_hkd_receding_horizon_shift_and_single_shooting_tail(cm, hkd_options):
+    """HKDProblem::update as a function of the previous solution (cafe_mpc_b200/mpc.py): two knots popped at the front, the last phase
+    padded with copies of its last state, a one-knot tail phase opened at offset 2, Ubar[0] of the front phase zeroed (HKDProblem.cpp:220).
+    The marked deck's tail phase has no shooting states: the oracle leaves zero defects there and ends elsewhere than on an unmarked deck."""
+    import copy
+    from cafe_mpc_b200 import mpc, workload
+    from oracle_bindings import oracle_get, oracle_solve
+    csv = os.path.join(REPO, "data/Reference/Data/trot/heuristic/quad_reference.csv")
+    ort = copy.copy(hkd_options)
+    ort.max_AL_iter = 2; ort.max_DDP_iter = 1   # HKDMPC.cpp:102-103
+    p0 = cm.HKDProblem(csv, k0=0)
+    p1 = cm.HKDProblem(csv, k0=2, mpc_update=True)
+    p1ms = cm.HKDProblem(csv, k0=2)
+    assert [p.horizon for p in p0.phases()] == [11, 25, 24] and [p.horizon for p in p1.phases()] == [9, 25, 25, 1]
+    assert p1.single_shooting_phase == 3 and [p.single_shooting for p in p1.phases()] == [0, 0, 0, 1] and p1ms.single_shooting_phase == -1
+    assert cm.HKDProblem(csv, k0=4, mpc_update=True).single_shooting_phase == -1      # h = 3 > 2: a shooting phase again
+    x0 = workload.hkd_batch(p0, 2)[1]
+    _, _, _, sol = oracle_solve(p0.deck, hkd_options, x0)
+    old = cm.unpack_solution(p0.deck, sol)
+    g = mpc.shift_guess(p0, 0, p1, 2, old)
+    np.testing.assert_array_equal(g[0]["Xbar"], old[0]["Xbar"][2:])
+    np.testing.assert_array_equal(g[0]["Ubar"][1:], old[0]["Ubar"][3:])
+    assert not g[0]["Ubar"][0].any() and old[0]["Ubar"][2].any()                       # the quirk of :220
+    np.testing.assert_array_equal(g[0]["K"], old[0]["K"][2:])
+    np.testing.assert_array_equal(g[2]["Xbar"][:25], old[2]["Xbar"]); np.testing.assert_array_equal(g[2]["Xbar"][25], old[2]["Xbar"][24])
+    assert not g[2]["Ubar"][24].any() and not g[2]["K"][24].any()
+    packed = mpc.pack_solution(p1, g)
+    x1 = mpc.state_at(p0, old, 2)
+    iw, _, _, _ = oracle_solve(p1.deck, ort, x1, guess=packed)
+    assert not oracle_get("Defect", 3).any()
+    im, _, _, _ = oracle_solve(p1ms.deck, ort, x1, guess=packed)
+    assert oracle_get("Defect", 3).any() and iw["cost"] != im["cost"]
+    ic, _, _, _ = oracle_solve(p1.deck, ort, x1)
+    assert iw["iter"] <= 2 and iw["feas"] < 0.05 * ic["feas"]

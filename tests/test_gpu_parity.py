@@ -164,3 +164,54 @@ def test_unsupported_options_fail_loudly(cm, hkd_problem, hkd_options):
     s.set_initial_condition(workload.hkd_batch(hkd_problem, 3))
     with pytest.raises(CafeError):  # batch larger than the handle's capacity
         s.solve(hkd_options)
+
+
+def test_hkd_receding_horizon_chain_matches_oracle(cm, hkd_options):
+    """SURVEY §8(f)1 for the HKD application: HKDProblem::update (HKDProblem.cpp:117-222) shifts the plan by nsteps_between_mpc = 2 knots,
+    HKDMPCSolver::update re-solves it under the caps 2 x 1 (HKDMPC.cpp:102-103) from the shifted previous solution. Six steps from the
+    start of the trot reference: a one-knot tail phase opens at offset 2 (no shooting states in that step, HKDProblem.cpp:213-217), the
+    front phase disappears at offset 12; Ubar[0] of the front phase is zeroed every step (:220). GPU == oracle at every step."""
+    import copy
+    from cafe_mpc_b200 import mpc, workload
+    csv = os.path.join(REPO, "data/Reference/Data/trot/heuristic/quad_reference.csv")
+    ort = copy.copy(hkd_options)
+    ort.max_AL_iter = 2; ort.max_DDP_iter = 1
+    B, k0 = 3, 0
+    prob = cm.HKDProblem(csv, k0=k0)
+    x0 = workload.hkd_batch(prob, B)
+    s = solve_gpu(cm, prob, hkd_options, x0)
+    sol = s.get_solution()
+    seen_ss = seen_removal = False
+    for step in range(6):
+        k1 = k0 + 2
+        p1 = cm.HKDProblem(csv, k0=k1, mpc_update=True)
+        seen_ss = seen_ss or p1.single_shooting_phase >= 0
+        seen_removal = seen_removal or len(p1.phases()) < len(prob.phases())
+        guess = mpc.shifted_guess_batch(prob, k0, p1, k1, sol)
+        assert not mpc.unpack_batch(p1, guess)[0]["Ubar"][:, 0].any()
+        x1 = np.stack([mpc.state_at(prob, cm.unpack_solution(prob.deck, sol[b]), 2) for b in range(B)])
+        x1[:, 3:6] += 1e-3 * (x0[:, 3:6] - x0[0, 3:6])   # the "measured" state: the plan's own prediction, position nudged
+        s1 = cm.MultiPhaseDDP(p1, 0, B)
+        s1.set_initial_condition(x1)
+        s1.set_initial_guess(guess)
+        s1.solve(ort)
+        info = s1.get_solver_info(); hist = s1.get_history(64); sol1 = s1.get_solution()
+        for b in range(B):
+            oi, oh, ot, osol = oracle_solve(p1.deck, ort, x1[b], guess=guess[b])
+            assert [info[b][k] for k in COUNTS] == [oi[k] for k in COUNTS], (step, b)
+            np.testing.assert_allclose(hist[b, :oi["n_hist"], 0], oh[:, 0], rtol=RTOL, atol=1e-9)
+            gp, op = cm.unpack_solution(p1.deck, sol1[b]), cm.unpack_solution(p1.deck, osol)
+            for pg, po in zip(gp, op):
+                for name in ("Xbar", "Ubar", "K", "Quu", "Qux"):
+                    assert relerr(pg[name], po[name]) < (RTOL if name in ("Xbar", "Ubar") else 1e-7), (step, b, name)
+        if p1.single_shooting_phase >= 0:
+            for b in range(B):
+                assert not np.any(s1.debug_get("Defect", p1.single_shooting_phase, b))
+        # the warm start pays: the same caps from the cold start end far from feasible
+        s1.set_initial_guess(None)
+        s1.solve(ort)
+        cold = s1.get_solver_info()
+        assert all(info[b]["feas"] < 0.05 * cold[b]["feas"] for b in range(B))
+        s1.close()
+        prob, k0, sol = p1, k1, sol1
+    assert seen_ss and seen_removal
