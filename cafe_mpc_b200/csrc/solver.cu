@@ -731,7 +731,9 @@ extern "C" int cafe_gpu_shift_guess(CafeHandle* dst, CafeHandle* src, int src_k0
   auto wb_ranges = [](const CafeHandle* H, int k0) {
     std::vector<Range> out;
     int s = k0;
-    for (int i = 0; i < H->S.n_phases && H->S.ph[i].model == CAFE_MODEL_WB; ++i) {
+    const int lead = H->S.ph[0].model;  // whole-body for MHPC decks, hybrid kinodynamic for HKD decks (HKDProblem::update, HKDProblem.cpp:117-222)
+    if (lead == CAFE_MODEL_SRB) return out;
+    for (int i = 0; i < H->S.n_phases && H->S.ph[i].model == lead; ++i) {
       Range r{i, s, s + H->S.ph[i].h, {0, 0, 0, 0}};
       for (int f = 0; f < 4; ++f) r.contact[f] = H->S.ph[i].contact[f];
       out.push_back(r);
@@ -740,7 +742,8 @@ extern "C" int cafe_gpu_shift_guess(CafeHandle* dst, CafeHandle* src, int src_k0
     return out;
   };
   const std::vector<Range> old_r = wb_ranges(src, src_k0), new_r = wb_ranges(dst, dst_k0);
-  if (old_r.empty()) { cafe::set_last_error("the previous deck has no leading whole-body phase"); return CAFE_ERR_UNSUPPORTED; }
+  if (old_r.empty() || new_r.empty() || src->S.ph[0].model != dst->S.ph[0].model) { cafe::set_last_error("both decks must start with full-order phases of the same model"); return CAFE_ERR_UNSUPPORTED; }
+  const int lead_model = dst->S.ph[0].model;
   const PhaseDev& last = src->S.ph[old_r.back().idx];
   const int old_end = old_r.back().e;
   std::vector<ShiftEntry> ent;
@@ -753,10 +756,11 @@ extern "C" int cafe_gpu_shift_guess(CafeHandle* dst, CafeHandle* src, int src_k0
     const double* ref = ph.ref; const double* ref_pp = ph.ref_pp;
     auto x_from = [&](const PhaseDev* sp, int sk, int k) { ent.push_back(ShiftEntry{sp ? sp->Xbar : nullptr, ref, ref_pp, sk, n, k, oX + (long)k * n}); };
     auto uk_from = [&](const PhaseDev& sp, int sk, int k) {
-      ent.push_back(ShiftEntry{sp.Ubar, nullptr, nullptr, sk, m, 0, oU + (long)k * m});
+      // HKDProblem.cpp:220: the first control of the front trajectory is zeroed by every HKD update (the record is pre-zeroed)
+      if (!(lead_model == CAFE_MODEL_HKD && i == 0 && k == 0)) ent.push_back(ShiftEntry{sp.Ubar, nullptr, nullptr, sk, m, 0, oU + (long)k * m});
       ent.push_back(ShiftEntry{sp.K, nullptr, nullptr, sk, m * n, 0, oK + (long)k * m * n});
     };
-    if (ph.model != CAFE_MODEL_WB) {
+    if (ph.model != lead_model) {
       const int j = (int)old_r.size() + (i - (int)new_r.size());
       const bool keep = j >= 0 && j < src->S.n_phases && src->S.ph[j].model == ph.model && src->S.ph[j].h == h;
       for (int k = 0; k <= h; ++k) { x_from(keep ? &src->S.ph[j] : nullptr, k, k); if (keep && k < h) uk_from(src->S.ph[j], k, k); }
@@ -809,7 +813,7 @@ extern "C" int cafe_gpu_get_planned_state(CafeHandle* H, int knots_ahead, double
   int k = knots_ahead;
   for (int i = 0; i < H->S.n_phases; ++i) {
     const PhaseDev& ph = H->S.ph[i];
-    if (k < ph.h || ph.model != CAFE_MODEL_WB || i == H->S.n_phases - 1) {
+    if (k < ph.h || ph.model != H->S.ph[0].model || i == H->S.n_phases - 1) {
       if (k > ph.h || ph.n != H->S.ph[0].n) break;
       std::vector<PackSeg> segs{PackSeg{ph.Xbar + (size_t)k * ph.n * H->ldb, 1, ph.n, 0, 0, 0, 0}};
       return run_pack(H, segs, ph.n, 0, H->B, out);

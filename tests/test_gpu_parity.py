@@ -215,3 +215,36 @@ def test_hkd_receding_horizon_chain_matches_oracle(cm, hkd_options):
         s1.close()
         prob, k0, sol = p1, k1, sol1
     assert seen_ss and seen_removal
+
+
+def test_hkd_device_shift_equals_host_shift(cm, hkd_options):
+    """cafe_gpu_shift_guess on HKD decks (HKDProblem::update incl. the Ubar[0] = 0 quirk) == cafe_mpc_b200/mpc.py on the host, bit for
+    bit, over a chain that opens a tail phase (offset 2) — and cafe_gpu_get_planned_state == mpc.state_at."""
+    import copy
+    from cafe_mpc_b200 import mpc, workload
+    csv = os.path.join(REPO, "data/Reference/Data/trot/heuristic/quad_reference.csv")
+    ort = copy.copy(hkd_options)
+    ort.max_AL_iter = 2; ort.max_DDP_iter = 1
+    B, k0 = 5, 0
+    prob = cm.HKDProblem(csv, k0=k0)
+    x0 = workload.hkd_batch(prob, B)
+    s = solve_gpu(cm, prob, hkd_options, x0)
+    for step in range(3):
+        k1 = k0 + 2
+        p1 = cm.HKDProblem(csv, k0=k1, mpc_update=True)
+        sol = s.get_solution()
+        x1 = s.planned_state(2)
+        assert np.array_equal(x1, mpc.state_at(prob, mpc.unpack_batch(prob, sol), 2)), step
+        sh = cm.MultiPhaseDDP(p1, 0, B)
+        sh.set_initial_condition(x1)
+        sh.set_initial_guess(mpc.shifted_guess_batch(prob, k0, p1, k1, sol))
+        sh.solve(ort)
+        sd = cm.MultiPhaseDDP(p1, 0, B)
+        sd.set_initial_condition(x1)
+        sd.shift_guess_from(s, k0, k1)
+        sd.solve(ort)
+        ih, idv = sh.get_solver_info(), sd.get_solver_info()
+        assert [[i[k] for k in COUNTS] for i in ih] == [[i[k] for k in COUNTS] for i in idv], step
+        assert np.array_equal(sh.get_solution(), sd.get_solution()), step
+        sh.close(); s.close()
+        s, prob, k0 = sd, p1, k1
