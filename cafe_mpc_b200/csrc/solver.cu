@@ -51,6 +51,11 @@ struct CafeHandle {
   double* d_pack = nullptr; size_t pack_bytes = 0;
   PackSeg* d_segs = nullptr; int max_segs = 0;
   cudaStream_t stream = nullptr;
+  // second stream of a tick: the active list is cut in two and the LQ -> dense -> sweep -> first rollout chains of the halves run
+  // on two streams, so that one half's kernels fill the wave tails of the other's (per-problem results do not depend on it)
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int split_min = 1024;  // smallest active list that is cut (CAFE_SPLIT_MIN; 0 = never)
   bool profiling = false;
   double ms[CAFE_NKERNELS] = {0};
   long launches[CAFE_NKERNELS] = {0};
@@ -291,33 +296,37 @@ int timed(CafeHandle* H, int slot, F&& launch) {
 }
 
 // cooperative dense part of the whole-body linearisation, one launch per WB phase (template on the number of contact rows)
-int launch_lq_wb_dense(CafeHandle* H) {
+int launch_lq_wb_dense(CafeHandle* H, const int* list = nullptr, int n_list = -1, cudaStream_t st = nullptr) {
+  if (!list) { list = H->S.c.act_list; n_list = H->S.n_act; st = H->stream; }
   const size_t smem = (size_t)CAFE_KKT_SM * 4 * sizeof(double);
   for (int pi = 0; pi < H->S.n_phases; ++pi) {
     const PhaseDev& ph = H->S.ph[pi];
     if (ph.model != CAFE_MODEL_WB || ph.h <= 0) continue;
     int nc = 0;
     for (int f = 0; f < 4; ++f) nc += ph.contact[f] > 0;
-    if (H->S.n_act <= 0) continue;
-    const dim3 grid((H->S.n_act + 3) / 4, ph.h);
+    if (n_list <= 0) continue;
+    const dim3 grid((n_list + 3) / 4, ph.h);
     switch (nc) {
-      case 0: k_lq_wb_dense<0><<<grid, CAFE_DENSE_NT, smem, H->stream>>>(H->dS, pi, H->S.c.act_list, H->S.n_act); break;
-      case 1: k_lq_wb_dense<3><<<grid, CAFE_DENSE_NT, smem, H->stream>>>(H->dS, pi, H->S.c.act_list, H->S.n_act); break;
-      case 2: k_lq_wb_dense<6><<<grid, CAFE_DENSE_NT, smem, H->stream>>>(H->dS, pi, H->S.c.act_list, H->S.n_act); break;
-      case 3: k_lq_wb_dense<9><<<grid, CAFE_DENSE_NT, smem, H->stream>>>(H->dS, pi, H->S.c.act_list, H->S.n_act); break;
-      default: k_lq_wb_dense<12><<<grid, CAFE_DENSE_NT, smem, H->stream>>>(H->dS, pi, H->S.c.act_list, H->S.n_act); break;
+      case 0: k_lq_wb_dense<0><<<grid, CAFE_DENSE_NT, smem, st>>>(H->dS, pi, list, n_list); break;
+      case 1: k_lq_wb_dense<3><<<grid, CAFE_DENSE_NT, smem, st>>>(H->dS, pi, list, n_list); break;
+      case 2: k_lq_wb_dense<6><<<grid, CAFE_DENSE_NT, smem, st>>>(H->dS, pi, list, n_list); break;
+      case 3: k_lq_wb_dense<9><<<grid, CAFE_DENSE_NT, smem, st>>>(H->dS, pi, list, n_list); break;
+      default: k_lq_wb_dense<12><<<grid, CAFE_DENSE_NT, smem, st>>>(H->dS, pi, list, n_list); break;
     }
     H->launches[3]++;
   }
   return 0;
 }
 
-int launch_bwd(CafeHandle* H) {
-  const unsigned grid = (H->S.n_act + 3) / 4 * 4;   // clusters of four listed problems
+int launch_bwd(CafeHandle* H, int first = 0, int n_list = -1, cudaStream_t st = nullptr) {
+  if (n_list < 0) { n_list = H->S.n_act; st = H->stream; }
+  const unsigned grid = (n_list + 3) / 4 * 4;   // clusters of four listed problems
   if (grid == 0) return 0;
-  if (H->bwd_variant == 0) k_bwd2<0, 128><<<grid, 128, H->bwd_smem, H->stream>>>(H->S);
-  else if (H->bwd_nt == 256) k_bwd2<1, 256><<<grid, 256, H->bwd_smem, H->stream>>>(H->S);
-  else k_bwd2<1, 128><<<grid, 128, H->bwd_smem, H->stream>>>(H->S);
+  SolverDev S = H->S;   // the kernel's descriptor: entries [first, first + n_list) of the active list
+  S.c.act_list += first; S.n_act = n_list;
+  if (H->bwd_variant == 0) k_bwd2<0, 128><<<grid, 128, H->bwd_smem, st>>>(S);
+  else if (H->bwd_nt == 256) k_bwd2<1, 256><<<grid, 256, H->bwd_smem, st>>>(S);
+  else k_bwd2<1, 128><<<grid, 128, H->bwd_smem, st>>>(S);
   return 0;
 }
 
@@ -416,6 +425,10 @@ extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, 
   CUDA_OK(cudaMalloc(&H->dS, sizeof(SolverDev)));
   CUDA_OK(cudaMallocHost(&H->h_nactive, 64));
   CUDA_OK(cudaStreamCreate(&H->stream));
+  CUDA_OK(cudaStreamCreate(&H->stream2));
+  CUDA_OK(cudaEventCreateWithFlags(&H->ev_fork, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&H->ev_join, cudaEventDisableTiming));
+  if (const char* e = getenv("CAFE_SPLIT_MIN")) H->split_min = atoi(e);
   CUDA_OK(cudaEventCreate(&H->ev0));
   CUDA_OK(cudaEventCreate(&H->ev1));
   CUDA_OK(cudaEventCreate(&H->evs));
@@ -453,6 +466,9 @@ extern "C" int cafe_gpu_destroy(CafeHandle* H) {
   cudaFree(H->arena); cudaFree(H->d_ref); cudaFree(H->d_ref_pp); cudaFree(H->d_lxx_mask); cudaFree(H->d_hkd_mask); cudaFree(H->d_guess); cudaFree(H->d_x0raw); cudaFree(H->dS); cudaFree(H->d_pack); cudaFree(H->d_segs);
   if (H->h_nactive) cudaFreeHost(H->h_nactive);
   if (H->stream) cudaStreamDestroy(H->stream);
+  if (H->stream2) cudaStreamDestroy(H->stream2);
+  if (H->ev_fork) cudaEventDestroy(H->ev_fork);
+  if (H->ev_join) cudaEventDestroy(H->ev_join);
   if (H->ev0) cudaEventDestroy(H->ev0);
   if (H->ev1) cudaEventDestroy(H->ev1);
   if (H->evs) cudaEventDestroy(H->evs);
@@ -532,16 +548,37 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
     H->ticks++;
     const int n_act = *H->h_nactive;   // = length of c.act_list (k_compact)
     H->S.n_act = n_act;
-    timed(H, 3, [&] { cafe_dev::launch_lq(H->dS, S.n_knots, st, S.c.act_list, n_act); });
-    if (H->bwd_variant == 1) timed(H, 5, [&] { launch_lq_wb_dense(H); });
-    timed(H, 4, [&] { launch_bwd(H); });
     CUDA_OK(cudaMemsetAsync(H->d_fail, 0, H->fail_bytes, st));
+    const bool split = !H->profiling && H->split_min > 0 && n_act >= H->split_min;
+    const int a1_first = 1 < S.NA ? 1 : S.NA;
+    if (split) {
+      // two halves of the active list on two streams: LQ -> dense -> sweep -> first line-search group per half
+      const int half = (n_act / 2) & ~127;
+      cudaStream_t s2 = H->stream2;
+      CUDA_OK(cudaEventRecord(H->ev_fork, st));
+      CUDA_OK(cudaStreamWaitEvent(s2, H->ev_fork, 0));
+      const int* lst = S.c.act_list;
+      cafe_dev::launch_lq(H->dS, S.n_knots, st, lst, half);
+      cafe_dev::launch_lq(H->dS, S.n_knots, s2, lst + half, n_act - half);
+      if (H->bwd_variant == 1) { launch_lq_wb_dense(H, lst, half, st); launch_lq_wb_dense(H, lst + half, n_act - half, s2); }
+      launch_bwd(H, 0, half, st);
+      launch_bwd(H, half, n_act - half, s2);
+      cafe_dev::launch_roll(H->dS, S.n_knots, st, 0, a1_first, lst, half);
+      cafe_dev::launch_roll(H->dS, S.n_knots, s2, 0, a1_first, lst + half, n_act - half);
+      H->launches[3] += 2; H->launches[4] += 2; H->launches[0] += 2;
+      CUDA_OK(cudaEventRecord(H->ev_join, s2));
+      CUDA_OK(cudaStreamWaitEvent(st, H->ev_join, 0));
+    } else {
+      timed(H, 3, [&] { cafe_dev::launch_lq(H->dS, S.n_knots, st, S.c.act_list, n_act); });
+      if (H->bwd_variant == 1) timed(H, 5, [&] { launch_lq_wb_dense(H); });
+      timed(H, 4, [&] { launch_bwd(H); });
+    }
     // staged line search: step sizes are evaluated in growing groups; most problems accept one of the first
     for (int a0 = 0, width = 1; a0 < S.NA; a0 += width, width *= 2) {
       const int a1 = (a0 + width < S.NA) ? a0 + width : S.NA;
       // the first group runs over the active list (problems that skip the line search return at once), later groups over
       // the list of line searches that still need step sizes
-      if (a0 == 0) timed(H, 0, [&] { cafe_dev::launch_roll(H->dS, S.n_knots, st, a0, a1, S.c.act_list, n_act); });
+      if (a0 == 0) { if (!split) timed(H, 0, [&] { cafe_dev::launch_roll(H->dS, S.n_knots, st, a0, a1, S.c.act_list, n_act); }); }
       else timed(H, 0, [&] { cafe_dev::launch_roll(H->dS, S.n_knots, st, a0, a1, S.c.pend_list, H->h_nactive[1]); });
       CUDA_OK(cudaMemsetAsync(S.c.n_pending, 0, sizeof(int), st));
       timed(H, 1, [&] { cafe_dev::launch_ls_scan(H->dS, B, st, a0, a1); });
