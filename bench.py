@@ -37,6 +37,9 @@ def workload_name(args):
     if args.workload == "barrel":
         return ("MHPC running barrel roll at the impact-bearing start offset k0=205 (WB flight h=22 -> 4-foot landing impact -> WB h=3; SRB h=10), "
                 "%d perturbed problems per GPU" % args.batch)
+    if args.workload == "barrel_to":
+        return ("in-place barrel roll (BarrelRoll/BarrelRollTO.cpp): 6 WB phases / 125 knots, joint-speed barrier, two 4-foot landings, solve started from "
+                "the interpolated state trajectory, %d perturbed problems per GPU" % args.batch)
     if args.workload == "loco":
         return ("LocoProblem (Locomotion/Loco_TO.cpp): whole-body-only 1.0 s flypace plan, 9 WB phases / 100 knots, three flight -> stance "
                 "touchdowns, torque + GRF barriers, %d perturbed problems per GPU" % args.batch)
@@ -55,6 +58,9 @@ def make_problem(workload):
     if workload == "barrel":
         prob = cm.MHPCProblem(wl.BARREL_CSV, mhpc_config=wl.BARREL_CONFIG, k0=wl.BARREL_K0_IMPACT)
         return prob, opt, (lambda B: wl.barrel_batch(prob, B)), 36
+    if workload == "barrel_to":
+        prob = cm.BarrelRollProblem()
+        return prob, cm.load_hsddp_setting(wl.BARREL_TO_DDP_SETTING), (lambda B: wl.mhpc_batch(B)), 36
     if workload == "loco":
         prob = cm.LocoProblem()
         return prob, cm.load_hsddp_setting(wl.LOCO_DDP_SETTING), (lambda B: wl.mhpc_batch(B)), 36
@@ -100,7 +106,7 @@ def _cpu_worker(task):
     prob, opt, _, _ = make_problem(workload)
     t = time.perf_counter()
     for x in x0s:
-        oracle_solve(prob.deck, opt, x)
+        oracle_solve(prob.deck, opt, x, cap=320, guess=prob.initial_guess(x)[0] if workload == "barrel_to" else None)
     return time.perf_counter() - t
 
 
@@ -148,7 +154,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--batch", type=int, default=4096, help="problems per GPU")
-    ap.add_argument("--workload", default="mhpc", choices=["mhpc", "hkd", "barrel", "loco"])
+    ap.add_argument("--workload", default="mhpc", choices=["mhpc", "hkd", "barrel", "loco", "barrel_to"])
     ap.add_argument("--gain-knots", type=int, default=8)
     ap.add_argument("--cpu-per-core", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -176,6 +182,8 @@ def main():
     lo, hi = cdist.shard_range(Bg, world, rank)
     x0 = np.ascontiguousarray(x0_all[lo:hi])
     solver = cm.MultiPhaseDDP(prob, local, B)
+    if args.workload == "barrel_to":
+        solver.set_initial_guess(prob.initial_guess(x0))   # BarrelRollTO.cpp:131-147: part of the problem set-up, stays in force
     # device-resident inputs: x0 as [n0][ldb]
     x0_dev = torch.from_numpy(np.ascontiguousarray(x0.T)).cuda()
     x0_pin = torch.from_numpy(x0).pin_memory()
@@ -301,6 +309,7 @@ def main():
                        "settings": {"hkd": "HKDMPC/settings (10x5 iteration caps, alpha 0.1)",
                                     "mhpc": "MHPC/settings (10x20 iteration caps, alpha 0.5, BG_alpha 10, cost_weights_regular, constraint_params_regular)",
                                     "barrel": "MHPC/settings (10x20 iteration caps, alpha 0.5, BG_alpha 10, cost_weights_barrel, constraint_params_barrel)",
+                                    "barrel_to": "BarrelRoll/setting (30x10 iteration caps, alpha 0.5, BG_alpha 10, br_cost_weights, br_constraint_params)",
                                     "loco": "Locomotion/settings (30x10 iteration caps, alpha 0.5, BG_alpha 10, loco_cost_weights, loco_constraint_params)"}[args.workload],
                        "l2": "working set per solve (GBs of per-problem arrays) exceeds the 126 MB L2; no flush needed",
                        "mean_ddp_iterations": sum(it) / len(it), "max_ddp_iterations": max(it)},
