@@ -242,6 +242,13 @@ class MultiPhaseDDP:
         check(lib.cafe_gpu_get_lcm_commands(self._h, n_steps, out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def get_hkd_lcm_commands(self, n_steps=9):
+        """Per-problem float32 fields of hkd_command_lcmt (HKDMPC.cpp:243-290): [B, 180 n_steps] = hkd_controls[N][24], des_body_state[N][12],
+        feedback[N][12][12]; n_steps = nsteps_between_mpc + 7 in the reference."""
+        out = np.zeros((self.B, lib.cafe_hkd_lcm_command_size(n_steps)), dtype=np.float32)
+        check(lib.cafe_gpu_get_hkd_lcm_commands(self._h, n_steps, out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def get_lcm_commands_device(self, n_steps, dev_ptr):
         check(lib.cafe_gpu_get_lcm_commands_device(self._h, n_steps, C.c_void_p(dev_ptr)))
 

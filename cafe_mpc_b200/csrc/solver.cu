@@ -154,7 +154,8 @@ __global__ void k_shift_guess(const ShiftEntry* __restrict__ ent, int n_ent, int
 
 // float32 wire record (MHPC_Command_lcmt field order): one segment = nk knots x w components taken from components
 // [c0, c0+w) of an array with nc_src components per knot, starting at knot k0 of its phase
-struct PackSegF { const double* src; int nc_src, c0, w, k0, nk; long dst; int pm_ld, pm_rows, pm_h; };   // pm_*: as in PackSeg
+struct PackSegF { const double* src; int nc_src, c0, w, k0, nk; long dst; int pm_ld, pm_rows, pm_h; int tr_cols, tr_ld; };   // pm_*: as in PackSeg
+// tr_cols > 0: the w components are a row-major (w / tr_cols) x tr_cols block read from a column-major matrix with tr_ld rows (wire [m][n] = K(m, n))
 __global__ void k_pack_lcm(const PackSegF* __restrict__ segs, int nseg, int ldb, int nb, long rec_size, float* __restrict__ out) {
   const int s = blockIdx.y;
   if (s >= nseg) return;
@@ -169,7 +170,8 @@ __global__ void k_pack_lcm(const PackSegF* __restrict__ segs, int nseg, int ldb,
       const int cc = sg.c0 + c;
       v = sg.src[((size_t)bb * sg.pm_h + sg.k0 + kk) * ((size_t)sg.pm_ld * (sg.nc_src / sg.pm_rows)) + (cc % sg.pm_rows) + sg.pm_ld * (cc / sg.pm_rows)];
     } else {
-      v = sg.src[((size_t)(sg.k0 + kk) * sg.nc_src + sg.c0 + c) * ldb + bb];
+      const int cc = sg.tr_cols > 0 ? sg.c0 + (c / sg.tr_cols) + sg.tr_ld * (c % sg.tr_cols) : sg.c0 + c;
+      v = sg.src[((size_t)(sg.k0 + kk) * sg.nc_src + cc) * ldb + bb];
     }
     out[(size_t)bb * rec_size + sg.dst + e] = (float)v;
   }
@@ -895,9 +897,49 @@ extern "C" int cafe_gpu_set_references(CafeHandle* H, const double* refs, int B)
 //      as float32 straight from the device arrays for the first n_steps whole-body knots of the horizon
 extern "C" long cafe_lcm_command_size(int n_steps) { return n_steps > 0 ? 1080L * n_steps : 0; }
 
-static int lcm_impl(CafeHandle* H, int n_steps, float* out, float* dev_out) {
+extern "C" long cafe_hkd_lcm_command_size(int n_steps) { return n_steps > 0 ? 180L * n_steps : 0; }
+
+static int lcm_impl(CafeHandle* H, int n_steps, float* out, float* dev_out, bool hkd = false) {
   if (!H || n_steps <= 0 || (!out && !dev_out)) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
   CUDA_OK(cudaSetDevice(H->device));
+  if (hkd) {
+    // hkd_command_lcmt (lcmtypes/hkd_command_lcmt.lcm) as HKDMPCSolver::publish_mpc_cmd fills it (HKDMPC.cpp:243-290): per step the 24
+    // controls, the first 12 states and the upper-left 12 x 12 block of K as [m][n]; steps run on across phase boundaries
+    int knots = 0;
+    for (int i = 0; i < H->S.n_phases && H->S.ph[i].model == CAFE_MODEL_HKD; ++i) knots += H->S.ph[i].h;
+    if (H->S.ph[0].model != CAFE_MODEL_HKD || knots < n_steps) { cafe::set_last_error("not an HKD deck, or fewer knots than the requested command steps"); return CAFE_ERR_UNSUPPORTED; }
+    const long N = n_steps, rec = 180L * N, oU = 0, oX = 24 * N, oFb = 36 * N;
+    std::vector<PackSegF> segs;
+    int s0 = 0;
+    for (int i = 0; i < H->S.n_phases && s0 < n_steps; ++i) {
+      const PhaseDev& ph = H->S.ph[i];
+      const int g = std::min(ph.h, n_steps - s0);
+      segs.push_back(PackSegF{ph.Ubar, 24, 0, 24, 0, g, oU + (long)s0 * 24, 0, 0, 0, 0, 0});
+      segs.push_back(PackSegF{ph.Xbar, 24, 0, 12, 0, g, oX + (long)s0 * 12, 0, 0, 0, 0, 0});
+      segs.push_back(PackSegF{ph.K, 576, 0, 144, 0, g, oFb + (long)s0 * 144, 0, 0, 0, 12, 24});
+      s0 += g;
+    }
+    const size_t need = (size_t)H->B * rec * sizeof(float);
+    float* dst = dev_out;
+    if (!dst) {
+      if (need > H->pack_bytes) {
+        cudaFree(H->d_pack); H->d_pack = nullptr; H->pack_bytes = 0;
+        CUDA_OK(cudaMalloc(&H->d_pack, need));
+        H->pack_bytes = need;
+      }
+      dst = reinterpret_cast<float*>(H->d_pack);
+    }
+    PackSegF* d_segs = nullptr;
+    CUDA_OK(cudaMalloc(&d_segs, segs.size() * sizeof(PackSegF)));
+    CUDA_OK(cudaMemcpyAsync(d_segs, segs.data(), segs.size() * sizeof(PackSegF), cudaMemcpyHostToDevice, H->stream));
+    dim3 grid(592, (unsigned)segs.size());
+    k_pack_lcm<<<grid, 256, 0, H->stream>>>(d_segs, (int)segs.size(), H->ldb, H->B, rec, dst);
+    if (out) CUDA_OK(cudaMemcpyAsync(out, dst, need, cudaMemcpyDeviceToHost, H->stream));
+    CUDA_OK(cudaStreamSynchronize(H->stream));
+    CUDA_OK(cudaGetLastError());
+    cudaFree(d_segs);
+    return 0;
+  }
   int wb_knots = 0;
   for (int i = 0; i < H->S.n_phases && H->S.ph[i].model == CAFE_MODEL_WB; ++i) wb_knots += H->S.ph[i].h;
   if (wb_knots < n_steps) { cafe::set_last_error("the deck has fewer leading whole-body knots than the requested command steps"); return CAFE_ERR_UNSUPPORTED; }
@@ -910,8 +952,8 @@ static int lcm_impl(CafeHandle* H, int n_steps, float* out, float* dev_out) {
   for (int i = 0; i < H->S.n_phases && s0 < n_steps; ++i) {
     const PhaseDev& ph = H->S.ph[i];
     const int g = std::min(ph.h, n_steps - s0);
-    auto add = [&](const double* src, int nc_src, int c0, int w, long base) { segs.push_back(PackSegF{src, nc_src, c0, w, 0, g, base + (long)s0 * w, 0, 0, 0}); };
-    auto add_pm = [&](const double* src, int nc_src, int c0, int w, long base) { segs.push_back(PackSegF{src, nc_src, c0, w, 0, g, base + (long)s0 * w, cafe_dev::ld_mma(12), 12, ph.h}); };
+    auto add = [&](const double* src, int nc_src, int c0, int w, long base) { segs.push_back(PackSegF{src, nc_src, c0, w, 0, g, base + (long)s0 * w, 0, 0, 0, 0, 0}); };
+    auto add_pm = [&](const double* src, int nc_src, int c0, int w, long base) { segs.push_back(PackSegF{src, nc_src, c0, w, 0, g, base + (long)s0 * w, cafe_dev::ld_mma(12), 12, ph.h, 0, 0}); };
     add(ph.Ubar, 12, 0, 12, oTorque);
     add(ph.Xbar, 36, 3, 3, oEul); add(ph.Xbar, 36, 0, 3, oPos); add(ph.Xbar, 36, 6, 12, oQj);
     add(ph.Xbar, 36, 18, 3, oVw); add(ph.Xbar, 36, 21, 3, oEr); add(ph.Xbar, 36, 24, 12, oQjd);
@@ -941,6 +983,8 @@ static int lcm_impl(CafeHandle* H, int n_steps, float* out, float* dev_out) {
 }
 extern "C" int cafe_gpu_get_lcm_commands(CafeHandle* H, int n_steps, float* out) { return lcm_impl(H, n_steps, out, nullptr); }
 extern "C" int cafe_gpu_get_lcm_commands_device(CafeHandle* H, int n_steps, float* out_dev) { return lcm_impl(H, n_steps, nullptr, out_dev); }
+extern "C" int cafe_gpu_get_hkd_lcm_commands(CafeHandle* H, int n_steps, float* out) { return lcm_impl(H, n_steps, out, nullptr, true); }
+extern "C" int cafe_gpu_get_hkd_lcm_commands_device(CafeHandle* H, int n_steps, float* out_dev) { return lcm_impl(H, n_steps, nullptr, out_dev, true); }
 
 extern "C" long cafe_gpu_debug_get(CafeHandle* H, const char* name, int phase, int b, double* out) {
   if (!H || !name || !out || phase < 0 || phase >= H->S.n_phases || b < 0 || b >= H->B) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }

@@ -44,6 +44,10 @@ def _load():
     lib.cafe_command_size.argtypes = [C.POINTER(Deck), C.c_int]
     lib.cafe_lcm_command_size.restype = C.c_long
     lib.cafe_lcm_command_size.argtypes = [C.c_int]
+    lib.cafe_hkd_lcm_command_size.restype = C.c_long
+    lib.cafe_hkd_lcm_command_size.argtypes = [C.c_int]
+    lib.cafe_gpu_get_hkd_lcm_commands.argtypes = [vp, C.c_int, vp]
+    lib.cafe_gpu_get_hkd_lcm_commands_device.argtypes = [vp, C.c_int, vp]
     lib.cafe_gpu_create.argtypes = [C.POINTER(Deck), C.c_int, C.c_int, C.POINTER(vp)]
     lib.cafe_gpu_destroy.argtypes = [vp]
     lib.cafe_gpu_solve_batch.argtypes = [vp, vp, C.c_int, C.POINTER(Options)]
@@ -78,6 +82,6 @@ EXPORTED = [
     "cafe_deck_free", "cafe_hkd_state", "cafe_deck_lq_pattern", "cafe_solution_size", "cafe_command_size", "cafe_gpu_create",
     "cafe_gpu_destroy", "cafe_gpu_solve_batch", "cafe_gpu_solve_batch_device", "cafe_gpu_get_info",
     "cafe_gpu_get_history", "cafe_gpu_get_trace", "cafe_gpu_get_solution", "cafe_gpu_get_commands", "cafe_gpu_get_commands_device", "cafe_gpu_get_solve_ms",
-    "cafe_gpu_set_references", "cafe_gpu_set_initial_guess", "cafe_gpu_shift_guess", "cafe_gpu_get_planned_state", "cafe_lcm_command_size", "cafe_gpu_get_lcm_commands", "cafe_gpu_get_lcm_commands_device",
+    "cafe_gpu_set_references", "cafe_gpu_set_initial_guess", "cafe_gpu_shift_guess", "cafe_gpu_get_planned_state", "cafe_lcm_command_size", "cafe_gpu_get_lcm_commands", "cafe_gpu_get_lcm_commands_device", "cafe_hkd_lcm_command_size", "cafe_gpu_get_hkd_lcm_commands", "cafe_gpu_get_hkd_lcm_commands_device",
     "cafe_gpu_get_timing", "cafe_gpu_set_profiling", "cafe_gpu_debug_get", "cafe_gpu_measure_fp64_peak",
 ]

@@ -136,6 +136,13 @@ int cafe_gpu_get_commands_device(CafeHandle* h, int n_gain_knots, double* cmd_de
 long cafe_lcm_command_size(int n_steps);
 int cafe_gpu_get_lcm_commands(CafeHandle* h, int n_steps, float* out /*[B][cafe_lcm_command_size]*/);
 int cafe_gpu_get_lcm_commands_device(CafeHandle* h, int n_steps, float* out_dev);
+/* The same for the HKD application: the per-problem part of hkd_command_lcmt (lcmtypes/hkd_command_lcmt.lcm) as
+ * HKDMPCSolver::publish_mpc_cmd fills it (HKDMPC/HKDMPC.cpp:243-290; N = nsteps_between_mpc + 7 there), float32, per problem:
+ *   hkd_controls[N][24] (Ubar)  des_body_state[N][12] (first 12 states of Xbar)  feedback[N][12][12] (K(m, n), m major)   = 180 N floats
+ * Steps run on across phase boundaries (s >= horizon -> next phase). mpc_times, contacts, statusTimes, foot_placement stay with the caller. */
+long cafe_hkd_lcm_command_size(int n_steps);
+int cafe_gpu_get_hkd_lcm_commands(CafeHandle* h, int n_steps, float* out /*[B][cafe_hkd_lcm_command_size]*/);
+int cafe_gpu_get_hkd_lcm_commands_device(CafeHandle* h, int n_steps, float* out_dev);
 /* device-time breakdown of the last solve, ms per kernel family, and launch counts */
 #define CAFE_NKERNELS 6 /* 0 roll 1 select 2 accept 3 lq 4 bwd 5 misc */
 int cafe_gpu_get_timing(CafeHandle* h, double ms[CAFE_NKERNELS], long launches[CAFE_NKERNELS], int* ticks);

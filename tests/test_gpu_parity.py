@@ -248,3 +248,30 @@ def test_hkd_device_shift_equals_host_shift(cm, hkd_options):
         assert np.array_equal(sh.get_solution(), sd.get_solution()), step
         sh.close(); s.close()
         s, prob, k0 = sd, p1, k1
+
+
+def test_hkd_lcm_command_packing(cm, hkd_options):
+    """cafe_gpu_get_hkd_lcm_commands == the loops of HKDMPCSolver::publish_mpc_cmd (HKDMPC.cpp:243-290) applied to the packed solution:
+    float32 casts of Ubar, Xbar[:12] and K(m, n) for m, n < 12, nine steps that cross the first phase boundary (start offset 8: h = 3)."""
+    from cafe_mpc_b200 import workload
+    csv = os.path.join(REPO, "data/Reference/Data/trot/heuristic/quad_reference.csv")
+    prob = cm.HKDProblem(csv, k0=8)
+    assert prob.phases()[0].horizon == 3
+    B, N = 5, 9
+    x0 = workload.hkd_batch(prob, B)
+    s = solve_gpu(cm, prob, hkd_options, x0)
+    wire = s.get_hkd_lcm_commands(N)
+    assert wire.dtype == np.float32 and wire.shape == (B, 180 * N)
+    sol = s.get_solution()
+    for b in range(B):
+        phases = cm.unpack_solution(prob.deck, sol[b])
+        U = np.concatenate([p["Ubar"] for p in phases])[:N]
+        X = np.concatenate([p["Xbar"][:-1] for p in phases])[:N]
+        K = np.concatenate([p["K"] for p in phases])[:N]            # [k, m, n]
+        assert np.array_equal(wire[b, :24 * N].reshape(N, 24), U.astype(np.float32))
+        assert np.array_equal(wire[b, 24 * N:36 * N].reshape(N, 12), X[:, :12].astype(np.float32))
+        assert np.array_equal(wire[b, 36 * N:].reshape(N, 12, 12), K[:, :12, :12].astype(np.float32))
+        assert np.abs(K[:, :12, :12]).max() > 0
+    from cafe_mpc_b200.lib import CafeError
+    with pytest.raises(CafeError):
+        s.get_hkd_lcm_commands(1000)
