@@ -53,8 +53,9 @@ struct CafeHandle {
   cudaStream_t stream = nullptr;
   // second stream of a tick: the active list is cut in two and the LQ -> dense -> sweep -> first rollout chains of the halves run
   // on two streams, so that one half's kernels fill the wave tails of the other's (per-problem results do not depend on it)
-  cudaStream_t stream2 = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t stream2[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+  int split_n = 2;       // number of parts (CAFE_SPLIT_N, 2..4)
   int split_min = 1024;  // smallest active list that is cut (CAFE_SPLIT_MIN; 0 = never)
   bool profiling = false;
   double ms[CAFE_NKERNELS] = {0};
@@ -427,10 +428,10 @@ extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, 
   CUDA_OK(cudaMalloc(&H->dS, sizeof(SolverDev)));
   CUDA_OK(cudaMallocHost(&H->h_nactive, 64));
   CUDA_OK(cudaStreamCreate(&H->stream));
-  CUDA_OK(cudaStreamCreate(&H->stream2));
+  for (int i = 0; i < 3; ++i) { CUDA_OK(cudaStreamCreate(&H->stream2[i])); CUDA_OK(cudaEventCreateWithFlags(&H->ev_join[i], cudaEventDisableTiming)); }
   CUDA_OK(cudaEventCreateWithFlags(&H->ev_fork, cudaEventDisableTiming));
-  CUDA_OK(cudaEventCreateWithFlags(&H->ev_join, cudaEventDisableTiming));
   if (const char* e = getenv("CAFE_SPLIT_MIN")) H->split_min = atoi(e);
+  if (const char* e = getenv("CAFE_SPLIT_N")) { H->split_n = atoi(e); if (H->split_n < 2) H->split_n = 2; if (H->split_n > 4) H->split_n = 4; }
   CUDA_OK(cudaEventCreate(&H->ev0));
   CUDA_OK(cudaEventCreate(&H->ev1));
   CUDA_OK(cudaEventCreate(&H->evs));
@@ -468,9 +469,8 @@ extern "C" int cafe_gpu_destroy(CafeHandle* H) {
   cudaFree(H->arena); cudaFree(H->d_ref); cudaFree(H->d_ref_pp); cudaFree(H->d_lxx_mask); cudaFree(H->d_hkd_mask); cudaFree(H->d_guess); cudaFree(H->d_x0raw); cudaFree(H->dS); cudaFree(H->d_pack); cudaFree(H->d_segs);
   if (H->h_nactive) cudaFreeHost(H->h_nactive);
   if (H->stream) cudaStreamDestroy(H->stream);
-  if (H->stream2) cudaStreamDestroy(H->stream2);
+  for (int i = 0; i < 3; ++i) { if (H->stream2[i]) cudaStreamDestroy(H->stream2[i]); if (H->ev_join[i]) cudaEventDestroy(H->ev_join[i]); }
   if (H->ev_fork) cudaEventDestroy(H->ev_fork);
-  if (H->ev_join) cudaEventDestroy(H->ev_join);
   if (H->ev0) cudaEventDestroy(H->ev0);
   if (H->ev1) cudaEventDestroy(H->ev1);
   if (H->evs) cudaEventDestroy(H->evs);
@@ -554,22 +554,23 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
     const bool split = !H->profiling && H->split_min > 0 && n_act >= H->split_min;
     const int a1_first = 1 < S.NA ? 1 : S.NA;
     if (split) {
-      // two halves of the active list on two streams: LQ -> dense -> sweep -> first line-search group per half
-      const int half = (n_act / 2) & ~127;
-      cudaStream_t s2 = H->stream2;
-      CUDA_OK(cudaEventRecord(H->ev_fork, st));
-      CUDA_OK(cudaStreamWaitEvent(s2, H->ev_fork, 0));
+      // the active list in split_n parts on as many streams: LQ -> dense -> sweep -> first line-search group per part
+      const int np = H->split_n;
+      const int part = ((n_act + np - 1) / np + 127) & ~127;
       const int* lst = S.c.act_list;
-      cafe_dev::launch_lq(H->dS, S.n_knots, st, lst, half);
-      cafe_dev::launch_lq(H->dS, S.n_knots, s2, lst + half, n_act - half);
-      if (H->bwd_variant == 1) { launch_lq_wb_dense(H, lst, half, st); launch_lq_wb_dense(H, lst + half, n_act - half, s2); }
-      launch_bwd(H, 0, half, st);
-      launch_bwd(H, half, n_act - half, s2);
-      cafe_dev::launch_roll(H->dS, S.n_knots, st, 0, a1_first, lst, half);
-      cafe_dev::launch_roll(H->dS, S.n_knots, s2, 0, a1_first, lst + half, n_act - half);
-      H->launches[3] += 2; H->launches[4] += 2; H->launches[0] += 2;
-      CUDA_OK(cudaEventRecord(H->ev_join, s2));
-      CUDA_OK(cudaStreamWaitEvent(st, H->ev_join, 0));
+      CUDA_OK(cudaEventRecord(H->ev_fork, st));
+      for (int q = 0; q < np; ++q) {
+        const int first = q * part, cnt = std::min(part, n_act - first);
+        if (cnt <= 0) break;
+        cudaStream_t sq = q == 0 ? st : H->stream2[q - 1];
+        if (q > 0) CUDA_OK(cudaStreamWaitEvent(sq, H->ev_fork, 0));
+        cafe_dev::launch_lq(H->dS, S.n_knots, sq, lst + first, cnt);
+        if (H->bwd_variant == 1) launch_lq_wb_dense(H, lst + first, cnt, sq);
+        launch_bwd(H, first, cnt, sq);
+        cafe_dev::launch_roll(H->dS, S.n_knots, sq, 0, a1_first, lst + first, cnt);
+        H->launches[3]++; H->launches[4]++; H->launches[0]++;
+        if (q > 0) { CUDA_OK(cudaEventRecord(H->ev_join[q - 1], sq)); CUDA_OK(cudaStreamWaitEvent(st, H->ev_join[q - 1], 0)); }
+      }
     } else {
       timed(H, 3, [&] { cafe_dev::launch_lq(H->dS, S.n_knots, st, S.c.act_list, n_act); });
       if (H->bwd_variant == 1) timed(H, 5, [&] { launch_lq_wb_dense(H); });
