@@ -352,7 +352,9 @@ extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, 
   if (n_knots > CAFE_MAX_KNOTS) { cafe::set_last_error("horizon too long"); return CAFE_ERR_UNSUPPORTED; }
   for (int i = 0; i < deck->n_phases; ++i) {
     const CafePhase& p = deck->phase[i];
-    if (p.single_shooting && i > 0 && deck->phase[i - 1].model != p.model) { cafe::set_last_error("a single-shooting phase must follow a phase of the same model"); return CAFE_ERR_UNSUPPORTED; }
+    if (p.single_shooting && i > 0 && (deck->phase[i - 1].model != p.model || deck->phase[i - 1].single_shooting)) {
+      cafe::set_last_error("a single-shooting phase must follow a shooting phase of the same model"); return CAFE_ERR_UNSUPPORTED;
+    }
     if (p.reb_grf.delta < p.reb_grf.delta_min || p.reb_torque.delta < p.reb_torque.delta_min || p.reb_joint.delta < p.reb_joint.delta_min ||
         p.reb_minheight.delta < p.reb_minheight.delta_min || (p.joint_speed_limit && p.reb_jointvel.delta < p.reb_jointvel.delta_min)) { cafe::set_last_error("ReB delta < delta_min is not supported"); return CAFE_ERR_UNSUPPORTED; }
   }

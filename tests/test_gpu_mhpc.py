@@ -420,3 +420,35 @@ def test_barrel_to_matches_oracle_and_golden(cm):
     assert [i0[k] for k in COUNTS] == [oi[k] for k in COUNTS]
     assert abs(i0["cost"] - oi["cost"]) < 1e-8 * abs(oi["cost"]) and abs(i0["max_tconstr"] - oi["max_tconstr"]) < 1e-6 * abs(oi["max_tconstr"])
     assert oi["cost"] < 0.01 * oh[0, 0] and oi["max_tconstr"] < fopt.tconstr_thresh   # the roll was found, both landings enforced
+
+
+def test_single_shooting_first_phase_matches_oracle(cm, opt):
+    """CafePhase::single_shooting on the FIRST phase (integrated from the solver's x0; every knot thread repeats the chain of up to 11
+    whole-body steps) and the create-time checks on the flag."""
+    import ctypes as C
+    from cafe_mpc_b200 import workload
+    from cafe_mpc_b200._ctypes_defs import Deck
+    from cafe_mpc_b200.lib import CafeError
+
+    class _P:
+        pass
+    base = cm.MHPCProblem(CSV)
+    d2 = Deck.from_buffer_copy(base.deck.contents)
+    d2.phase[0].single_shooting = 1
+    p2 = _P(); p2.deck = C.pointer(d2); p2._keep = base
+    x0 = workload.mhpc_batch(3)
+    s = solve_gpu(cm, p2, opt, x0)
+    compare_with_oracle(cm, p2, opt, x0, s, (0, 2))
+    for b in range(3):
+        assert not np.any(s.debug_get("Defect", 0, b))   # no shooting states: the defects of that phase vanish identically
+    assert s.get_solver_info()[1]["cost"] != solve_gpu(cm, base, opt, x0).get_solver_info()[1]["cost"]
+    d3 = Deck.from_buffer_copy(d2)
+    d3.phase[1].single_shooting = 1          # two phases in a row without shooting states: not supported
+    p3 = _P(); p3.deck = C.pointer(d3)
+    with pytest.raises(CafeError):
+        cm.MultiPhaseDDP(p3, 0, 1)
+    d4 = Deck.from_buffer_copy(base.deck.contents)
+    d4.phase[2].single_shooting = 1          # SRB after WB: the hand-over needs the same model on both sides
+    p4 = _P(); p4.deck = C.pointer(d4)
+    with pytest.raises(CafeError):
+        cm.MultiPhaseDDP(p4, 0, 1)
