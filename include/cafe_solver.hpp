@@ -30,6 +30,9 @@ class ProblemBase {
   ProblemBase& operator=(const ProblemBase&) = delete;
   ~ProblemBase() { if (h_) cafe_deck_free(h_); }
   const CafeDeck* deck() const { return cafe_deck_get(h_); }
+  // the deck stands for the problem after update() (MHPCProblem.cpp:252-372, HKDProblem.cpp:117-222; nsteps = shift in knots, 2 for HKD): a tail
+  // phase that update has just opened has no shooting states yet. Returns the index of that phase, -1 if there is none.
+  int mark_mpc_update(int nsteps) { int which = -1; check(cafe_deck_mark_mpc_update(h_, nsteps, &which)); return which; }
   int n_phases() const { return deck()->n_phases; }
  protected:
   CafeDeckHandle* h_ = nullptr;
@@ -101,6 +104,8 @@ class MultiPhaseDDP {
   // x0: B rows of the first phase's state dimension
   void set_initial_condition(const std::vector<double>& x0, int B) { x0_ = x0; B_ = B; }
   void solve(HSDDP_OPTION& option) { check(cafe_gpu_solve_batch(h_, x0_.data(), B_, &option)); }
+  // initial Xbar / Ubar / K per problem in the packed solution layout ([B][solution_size()]); an empty vector returns to the cold start
+  void set_initial_guess(const std::vector<double>& guess) { check(cafe_gpu_set_initial_guess(h_, guess.empty() ? nullptr : guess.data(), B_)); }
 
   std::vector<CafeInfo> get_solver_info() const { std::vector<CafeInfo> v(B_); check(cafe_gpu_get_info(h_, v.data())); return v; }
   // the reference's scalar getters (header/MultiPhaseDDP.h:77-93), for problem b of the batch
@@ -125,6 +130,8 @@ class MultiPhaseDDP {
   }
   // float32 MHPC_Command_lcmt fields for the first n_steps whole-body knots (what publish_mpc_cmd sends, MHPCLocomotion.cpp:236-281)
   std::vector<float> get_lcm_commands(int n_steps) const { std::vector<float> v((size_t)B_ * cafe_lcm_command_size(n_steps)); check(cafe_gpu_get_lcm_commands(h_, n_steps, v.data())); return v; }
+  // float32 hkd_command_lcmt fields (hkd_controls, des_body_state, feedback) for n_steps knots (HKDMPCSolver::publish_mpc_cmd, HKDMPC.cpp:243-290)
+  std::vector<float> get_hkd_lcm_commands(int n_steps) const { std::vector<float> v((size_t)B_ * cafe_hkd_lcm_command_size(n_steps)); check(cafe_gpu_get_hkd_lcm_commands(h_, n_steps, v.data())); return v; }
   // receding horizon (MHPCProblem::update, MHPCProblem.cpp:252-397): warm start of this solver (deck at start offset k0) from the plan held
   // by `prev` (deck at start offset prev_k0), shifted on the device; and the planned state `knots_ahead` knots into the plan, [B][n]
   void shift_guess_from(const MultiPhaseDDP& prev, int prev_k0, int k0) { check(cafe_gpu_shift_guess(h_, prev.h_, prev_k0, k0, B_)); }

@@ -261,6 +261,15 @@ def test_cpp_host_mirror_compiles_and_fails_loudly_without_gpu(cm, tmp_path):
         assert r.returncode == 0 and "solved 8 MHPC problems" in r.stdout
     else:
         assert r.returncode == 1 and "no CUDA device" in r.stderr
+    # BarrelRollTO.cpp's main() on a batch: deck builder + interpolated initial guess + solve through the mirror
+    exe2 = str(tmp_path / "barrel_roll_to")
+    subprocess.run(["g++", "-std=c++17", "-I" + os.path.join(REPO, "include"), os.path.join(REPO, "examples/barrel_roll_to.cpp"),
+                    "-L" + os.path.join(REPO, "cafe_mpc_b200"), "-lcafe_gpu", "-Wl,-rpath," + os.path.join(REPO, "cafe_mpc_b200"), "-o", exe2], check=True)
+    r = subprocess.run([exe2, os.path.join(REPO, "data"), "4"], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and "solved 4 barrel-roll problems" in r.stdout
+    else:
+        assert r.returncode == 1 and "no CUDA device" in r.stderr
 
 
 def test_structural_hkd_patterns_cover_the_oracle(cm):
