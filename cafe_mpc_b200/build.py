@@ -14,9 +14,11 @@ LIB = os.path.join(HERE, "libcafe_gpu.so")
 # source -> dependencies besides itself (paths relative to csrc/)
 ABI = ["../../include/cafe_gpu.h", "../../include/cafe_deck.h"]
 SOURCES = {
-    "solver.cu": ["dense_kernels.cuh", "bwd2.cuh", "device_types.cuh", "launchers.h"] + ABI,
+    "solver.cu": ["bwd2.cuh", "device_types.cuh", "launchers.h"] + ABI,
     "knot_kernels.cu": ["knot_kernels.cuh", "launchers.h", "device_types.cuh", "model_hkd.cuh", "model_srb.cuh", "model_wb.cuh", "gen/hkd_gen.h", "gen/srb_gen.h"] + ABI,
     "wb_gen_wrappers.cu": ["gen/wb_gen.h", "wb_pieces.h"],
+    "wb_leg_kernels.cu": ["gen/wb_leg_gen.h", "gen/wb_gen.h", "wb_leg_tables.h", "device_types.cuh", "launchers.h"] + ABI,
+    "wb_coop.cu": ["wb_coop.cuh", "wb_leg_tables.h", "device_types.cuh", "model_hkd.cuh", "gen/hkd_gen.h", "launchers.h"] + ABI,
     "host/abi_host.cpp": ["host/problem_builders.h", "host/quad_reference.h"] + ABI,
     "host/hkd_problem.cpp": ["host/problem_builders.h", "host/quad_reference.h", "host/info_reader.h", "gen/hkd_gen.h"] + ABI,
     "host/mhpc_problem.cpp": ["host/problem_builders.h", "host/quad_reference.h", "host/info_reader.h"] + ABI,
@@ -34,7 +36,8 @@ NVCC_FLAGS = [
 # kernels calling them reach 4 CTAs of 128 threads per SM (their local-memory traffic needs the latency hiding)
 _RC = os.environ.get("CAFE_KNOT_MAXRREG", "128")   # dev switch for occupancy experiments
 _MINB = str(max(1, 65536 // (128 * int(_RC))))
-EXTRA = {"wb_gen_wrappers.cu": ["-maxrregcount=" + _RC], "knot_kernels.cu": ["-maxrregcount=" + _RC, "-DCAFE_KNOT_MINB=" + _MINB] + os.environ.get("CAFE_KNOT_DEFS", "").split()}
+_LRC = os.environ.get("CAFE_LEG_MAXRREG", "255")    # register cap of the leg-parallel straight-line kernels
+EXTRA = {"wb_gen_wrappers.cu": ["-maxrregcount=" + _RC], "wb_leg_kernels.cu": ["-maxrregcount=" + _LRC, "-DCAFE_LEG_MINB=" + str(max(1, 65536 // (128 * int(_LRC))))], "knot_kernels.cu": ["-maxrregcount=" + _RC, "-DCAFE_KNOT_MINB=" + _MINB] + os.environ.get("CAFE_KNOT_DEFS", "").split()}
 
 
 def _mtime(p):

@@ -29,6 +29,16 @@
 #define CAFE_WB_CD_TILE 576
 #define CAFE_WB_K_TILE 432
 #define CAFE_LXX_MASK_WORDS 21
+// whole-body hand-off arrays of the leg-parallel kernels (wb_leg_kernels.cu -> wb_coop.cuh), batch-major [slot][ldb]:
+//   terms pack  TM = [trunk: nle 6 | M 6x6 (r + 6c)] [leg f: CAFE_WBL_TM_W compact slots] x 4      (gen/wb_leg_gen.h)
+//   deriv pack  DP = [trunk: dtau/dq 3x3 | dtau/dv 3x3 (rows, columns 3..5)] [leg f: CAFE_WBL_DP_W compact slots] x 4
+#define CAFE_TM_LEG_W 79
+#define CAFE_DP_LEG_W 198
+#define CAFE_TM_TRUNK_W 42
+#define CAFE_DP_TRUNK_W 18
+#define CAFE_TM_W (CAFE_TM_TRUNK_W + 4 * CAFE_TM_LEG_W)
+#define CAFE_DP_W (CAFE_DP_TRUNK_W + 4 * CAFE_DP_LEG_W)
+#define CAFE_LXX_LIST_CAP 704
 #define CAFE_MAX_KNOTS 256
 #define CAFE_HIST_CAP 320  // LocoProblem settings: 30 x 10 iterations + the initial entry
 
@@ -53,7 +63,12 @@ struct PhaseDev {
   double *A, *Bm, *C, *D;                  // [h][n*n | n*m | p*n | p*m][ldb], column-major per knot
   double *lx, *lu, *ly, *lxx, *luu, *lyy;  // [h][...][ldb]
   double *Phix, *Phixx, *Px;               // [n | n*n | n_next*n][ldb]
-  double *kkt;                             // WB only: [h][CAFE_KKT_PACK][ldb]
+  double *kkt;                             // WB only: [h][CAFE_KKT_PACK][ldb]  (legacy hand-off, unused by the leg-parallel path)
+  // WB only: rigid-body terms of every line-search trial (k_wb_terms -> k_wb_fwd; the accepted trial's are reused by the next
+  // linearisation), joint accelerations of every trial, derivative pieces of the current iterate (k_wb_derivs -> k_wb_lq)
+  double *tm;                              // [NA][h][CAFE_TM_W][ldb]
+  double *qdd_t;                           // [NA][h][18][ldb]
+  double *dp;                              // [h][CAFE_DP_W][ldb]
   // WB only, PROBLEM-major copies laid out exactly like the shared-memory tiles of the backward sweep (bwd2.cuh), so that a CTA
   // fetches them with 16-byte cp.async from contiguous memory (an 8-byte element of a problem-fastest array costs one L1 wavefront
   // each): [b][h][20 x 48] rows 18..35 of [A B] (rows 18, 19 of the tile: zero padding), [b][h][12 x 48] [C D], [b][h][12 x 36] K
@@ -94,6 +109,7 @@ struct CtrlDev {
   // more step sizes. The per-(problem, knot) kernels and the sweep run over these lists, so that warps and CTAs stay full when
   // most of the batch has already converged.
   int *act_list, *pend_list;
+  int *cur_slot;  // trial slot whose rollout produced the current iterate X, U (its rigid-body terms are reused by the linearisation)
 };
 
 struct SolverDev {
@@ -105,6 +121,8 @@ struct SolverDev {
   CtrlDev c;
   const double* x0;  // [n0][ldb]
   short knot_phase[CAFE_MAX_KNOTS], knot_k[CAFE_MAX_KNOTS];
+  short wbk_gk[CAFE_MAX_KNOTS];  // global knot indices of the running whole-body knots (k < h of WB phases)
+  int n_wbk;
 };
 
 // reference record of knot k as problem b sees it: the deck's shared record, or the problem's own (copied to thread-local storage)

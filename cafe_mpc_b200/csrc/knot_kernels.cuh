@@ -107,6 +107,9 @@ __device__ void roll_knot(const SolverDev& S, int pi, int k, int a, int b) {
       u[i] = ph.Ubar[gix(k, M, i, ldb, b)] + eps * ph.dU[gix(k, M, i, ldb, b)] + u[i];
       ph.Ut[aU + gix(k, M, i, ldb, b)] = u[i];
     }
+    // whole-body running knots continue in k_wb_terms (leg-parallel rigid-body terms) and k_wb_fwd (cooperative KKT solve, x+,
+    // GRF, cost, defects) from the trial state and control stored above
+    if constexpr (Model::COOP) return;
     double xn[N], y[PY > 0 ? PY : 1];
     double l, ming;
     Model::roll(ph, rec, x, u, xn, y, S.opt.ReB_active != 0, l, ming);
@@ -197,6 +200,7 @@ __device__ void lq_knot_generic(const SolverDev& S, int pi, int k, int b) {
   for (int i = 0; i < N; ++i) { x[i] = ph.X[gix(k, N, i, ldb, b)]; const double d = ph.Defect[gix(k, N, i, ldb, b)]; dsq += d * d; }
   ph.dsq[(size_t)k * ldb + b] = dsq;
   if (k < h) {
+    if constexpr (Model::COOP) return;   // whole-body running knots: k_wb_derivs + k_wb_lq
     double u[M], y[PY > 0 ? PY : 1];
 #pragma unroll
     for (int i = 0; i < M; ++i) u[i] = ph.U[gix(k, M, i, ldb, b)];
@@ -221,7 +225,7 @@ __device__ void lq_knot_generic(const SolverDev& S, int pi, int k, int b) {
   }
 }
 
-// the list is padded to a multiple of the CTA size: one knot per CTA (the whole-body pieces run in lock step, model_wb.cuh)
+// the list is padded to a multiple of the CTA size: one knot per CTA (uniform control flow inside a CTA)
 __global__ void __launch_bounds__(128, CAFE_KNOT_MINB) k_lq(const SolverDev* __restrict__ Sp, const int* __restrict__ list, int n_list) {
   const SolverDev& S = *Sp;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -250,6 +254,7 @@ __global__ void k_accept(const SolverDev* __restrict__ Sp) {
   const int a = S.c.sel[b];
   if (a < 0) return;
   const bool acc = S.c.accepted[b] != 0;
+  if (gk == 0) S.c.cur_slot[b] = a;   // the rigid-body terms of this trial are the linearisation's (k_wb_lq)
   const int pi = S.knot_phase[gk], k = S.knot_k[gk];
   const PhaseDev& ph = S.ph[pi];
   const int ldb = S.ldb, h = ph.h, n = ph.n, m = ph.m, p = ph.p;

@@ -29,6 +29,7 @@ __device__ __forceinline__ void reb_derivs(double g, double delta, double& bd, d
 
 struct HKDModel {
   static constexpr int N = 24, M = 24, PY = 0;
+  static constexpr bool COOP = false;
 
   __device__ static void foot_position(int leg, const double* x, double* pf) {
     const double pos[3] = {x[3], x[4], x[5]}, eul[3] = {x[0], x[1], x[2]};

@@ -13,6 +13,7 @@ namespace cafe_dev {
 
 struct SRBModel {
   static constexpr int N = 12, M = 12, PY = 0;
+  static constexpr bool COOP = false;
 
   __device__ static double running_cost(const PhaseDev& ph, const double* rec, const double* x, const double* u, bool reb, double& ming) {
     double s = 0;

@@ -1,6 +1,7 @@
-// model_wb.cuh — device-side whole-body (WB) phase of the MHPC problem. One thread per (problem, knot); rigid-body terms
-// come from the generated straight-line functions of gen/wb_gen.h (no Pinocchio, no CasADi), the small dense KKT algebra
-// runs per thread on local arrays.
+// model_wb.cuh — device-side whole-body (WB) phase of the MHPC problem, thread-per-knot parts: the TERMINAL knot of a phase (terminal
+// cost, touchdown constraints, impact map and its Jacobian) and the short single-shooting chains of an MPC tail phase. Rigid-body
+// terms come from the generated straight-line functions of gen/wb_gen.h (no Pinocchio, no CasADi), the small dense KKT algebra
+// runs per thread on local arrays. The RUNNING knots (the hot path) live in wb_leg_kernels.cu + wb_coop.cuh.
 //
 // Reference behaviour followed (file:line under /root/reference):
 //   WBM::Model::dynamics / dynamics_partial         MHPC/MHPC-Trajopt/WBM.cpp:17-139
@@ -27,12 +28,6 @@ __device__ void wbg_rnea_derivs(const double* q, const double* v, const double* 
 __device__ void wbg_grav_derivs(const double* q, double* dq);
 __device__ void wbg_kin_partials(const double* q, const double* v, const double* a, const double* F, double* dvq, double* daq, double* dav, double* djtf, size_t st);
 __device__ void wbg_footvel_partial(const double* q, const double* v, double* dvq);
-#ifndef CAFE_LQ_LOCKSTEP
-#define CAFE_LQ_LOCKSTEP 1
-#endif
-__device__ void wbg_terms_lockstep(const double* q, const double* v, double* nle, double* Mlow, double* J, double* gam, double* pf, double* vf);
-__device__ void wbg_rnea_derivs_lockstep(const double* q, const double* v, const double* a, double* dq, double* dv, size_t st);
-__device__ void wbg_kin_partials_lockstep(const double* q, const double* v, const double* a, const double* F, double* dvq, double* daq, double* dav, double* djtf, size_t st);
 
 struct WBScratch {
   double L[324];   // M (lower) then its Cholesky factor, column-major, ld 18
@@ -69,6 +64,9 @@ __device__ __forceinline__ void bwd_subst(const double* L, int n, int ld, double
 
 struct WBModel {
   static constexpr int N = 36, M = 12, PY = 12;
+  // running knots are evaluated by the leg-parallel / cooperative kernels (wb_leg_kernels.cu, wb_coop.cuh); what stays here is the
+  // terminal knot (cost, touchdown constraints, impact map and its Jacobian) and the short single-shooting chains of an MPC tail phase
+  static constexpr bool COOP = true;
 
   __device__ static void active_rows(const int* contact, WBScratch& s) {
     s.nr = 0;
@@ -76,13 +74,10 @@ struct WBModel {
   }
 
   // M, nle, J, Jdot v, foot positions and velocities at (q, v); Cholesky of M; Y = L^-1 Jc^T; S = Y^T Y
-  // LOCK: the caller guarantees that every live thread of the CTA is here (running knots in k_roll / k_lq): lock-step pieces
-  template <bool LOCK = false>
   __device__ static void kkt_setup(const double* x, WBScratch& s, double damping) {
     for (int i = 0; i < 324; ++i) s.L[i] = 0;
     for (int i = 0; i < 216; ++i) s.J[i] = 0;
-    if (LOCK && CAFE_LQ_LOCKSTEP) wbg_terms_lockstep(x, x + 18, s.nle, s.L, s.J, s.gam, s.pf, s.vf);
-    else wbg_terms(x, x + 18, s.nle, s.L, s.J, s.gam, s.pf, s.vf);
+    wbg_terms(x, x + 18, s.nle, s.L, s.J, s.gam, s.pf, s.vf);
     chol_inplace(s.L, 18, 18);
     const int nr = s.nr;
     for (int c = 0; c < nr; ++c) {
@@ -100,10 +95,9 @@ struct WBModel {
   }
 
   // KKTContactDynamics (WBM.cpp:368-424): qdd, GRF for the phase contact set
-  template <bool LOCK = false>
   __device__ static void forward(const PhaseDev& ph, const double* x, const double* u, WBScratch& s) {
     active_rows(ph.contact, s);
-    kkt_setup<LOCK>(x, s, 1e-12);
+    kkt_setup(x, s, 1e-12);
     double b[18];
     for (int i = 0; i < 18; ++i) b[i] = ((i >= 6) ? u[i - 6] : 0.0) - s.nle[i];
     double mb[18];
@@ -249,180 +243,8 @@ struct WBModel {
     else for (int i = 0; i < 36; ++i) xn[i] = full[i];
   }
 
-  // ---- LQ data of one running knot
-  __device__ __noinline__ static double lq_knot(const PhaseDev& ph, int k, int ldb, int b, const double* rec, const double* x, const double* u,
-                                   const double* y_unused, bool reb) {
-    (void)y_unused;
-    const double dt = ph.dt;
-    WBScratch s;
-    forward(ph, x, u, s);   // (lock-step wbg_terms measured no gain: the 7.4 k-op pieces fit the instruction cache)
-    const int nr = s.nr;
-    // S without damping for the sensitivities (computeKKTContactDynamicMatrixInverse, WBM.cpp:467)
-    double Ls0[144];
-    for (int c = 0; c < nr; ++c)
-      for (int r = c; r < nr; ++r) { double d = 0; for (int i = 0; i < 18; ++i) d += s.Y[i + 18 * r] * s.Y[i + 18 * c]; Ls0[r + 12 * c] = d; }
-    if (nr > 0) chol_inplace(Ls0, nr, 12);
-    // ---- hand the KKT factors and the raw derivative pieces to the cooperative kernel k_lq_wb_dense (kernels.cuh), which forms
-    //      R = dtau_dq - d(J^T F)/dq, a = da + 2 BG (dv/dq | J) on the active rows and applies
-    //      dlambda/dz = S^-1 (J Minv R - a), dqdd/dz = -Minv (R - J^T dlambda/dz) column by column out of shared memory.
-    //      The generated routines store their static non-zero patterns directly into the batch-major array (coalesced).
-    double* kk = ph.kkt + gix(k, CAFE_KKT_PACK, 0, ldb, b);
-    const size_t st = (size_t)ldb;
-#if CAFE_LQ_LOCKSTEP
-    // k_lq guarantees that every live thread of the CTA is here (one running whole-body knot per CTA): lock-step pieces
-    wbg_rnea_derivs_lockstep(x, x + 18, s.qdd, kk + CAFE_KKT_RQ * st, kk + CAFE_KKT_RV * st, st);
-    wbg_kin_partials_lockstep(x, x + 18, s.qdd, s.grf, kk + CAFE_KKT_DVQ * st, kk + CAFE_KKT_AQ * st, kk + CAFE_KKT_AV * st, kk + CAFE_KKT_JTF * st, st);
-#else
-    wbg_rnea_derivs(x, x + 18, s.qdd, kk + CAFE_KKT_RQ * st, kk + CAFE_KKT_RV * st, st);
-    wbg_kin_partials(x, x + 18, s.qdd, s.grf, kk + CAFE_KKT_DVQ * st, kk + CAFE_KKT_AQ * st, kk + CAFE_KKT_AV * st, kk + CAFE_KKT_JTF * st, st);
-#endif
-    for (int i = 0; i < 324; ++i) kk[(CAFE_KKT_L + i) * st] = s.L[i];
-    for (int i = 0; i < 216; ++i) { kk[(CAFE_KKT_Y + i) * st] = s.Y[i]; kk[(CAFE_KKT_J + i) * st] = s.J[i]; }
-    for (int i = 0; i < 144; ++i) kk[(CAFE_KKT_LS + i) * st] = Ls0[i];
-    {
-      double* Ag = ph.A + gix(k, 1296, 0, ldb, b);
-      for (int i = 0; i < 18; ++i) { Ag[(size_t)(i + 36 * i) * ldb] = 1.0; Ag[(size_t)(i + 36 * (18 + i)) * ldb] = dt; }
-    }
-    const double* dvq = kk + CAFE_KKT_DVQ * st;  // read back (element i at dvq[i * st])
-    // ---- cost partials
-    // lu, luu (diagonal): tracking + torque-limit barrier
-    double* luug = ph.luu + gix(k, 144, 0, ldb, b);
-    for (int i = 0; i < 12; ++i) {
-      double lu = dt * ph.r[i] * (u[i] - rec[CAFE_REF_UR + i]);
-      double luu = dt * ph.r[i];
-      if (reb) {
-        double bd1, bdd1, bd2, bdd2;
-        reb_derivs(-u[i] + ph.torque_limit, ph.reb_torque.delta, bd1, bdd1);
-        reb_derivs(u[i] + ph.torque_limit, ph.reb_torque.delta, bd2, bdd2);
-        lu += dt * (ph.reb_torque.eps * bd1 * (-1.0) + ph.reb_torque.eps * bd2);
-        luu += dt * (ph.reb_torque.eps * bdd1 + ph.reb_torque.eps * bdd2);
-      }
-      ph.lu[gix(k, 12, i, ldb, b)] = lu;
-      luug[(size_t)(13 * i) * ldb] = luu;
-    }
-    // ly, lyy: GRF barrier on the output (3x3 block per stance foot)
-    double* lyyg = ph.lyy + gix(k, 144, 0, ldb, b);
-    for (int f = 0; f < 4; ++f) {
-      double gr[3] = {0, 0, 0}, hs[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-      if (reb && ph.contact[f] > 0) {
-        const double fx = s.grf[3 * f], fy = s.grf[3 * f + 1], fz = s.grf[3 * f + 2], mu = ph.mu;
-        const double g[5] = {fz, -fx + mu * fz, fx + mu * fz, -fy + mu * fz, fy + mu * fz};
-        const double Al[5][3] = {{0, 0, 1}, {-1, 0, mu}, {1, 0, mu}, {0, -1, mu}, {0, 1, mu}};
-        for (int i = 0; i < 5; ++i) {
-          double bd, bdd;
-          reb_derivs(g[i], ph.reb_grf.delta, bd, bdd);
-          const double e1 = ph.reb_grf.eps * bd, e2 = ph.reb_grf.eps * bdd;
-          for (int r = 0; r < 3; ++r) { gr[r] += e1 * Al[i][r]; for (int c = 0; c < 3; ++c) hs[r][c] += Al[i][r] * (e2 * Al[i][c]); }
-        }
-      }
-      for (int r = 0; r < 3; ++r) {
-        ph.ly[gix(k, 12, 3 * f + r, ldb, b)] = dt * gr[r];
-        for (int c = 0; c < 3; ++c) lyyg[(size_t)((3 * f + r) + 12 * (3 * f + c)) * ldb] = dt * hs[r][c];
-      }
-    }
-    // lx, lxx
-    double lx[36];
-    for (int i = 0; i < 36; ++i) lx[i] = dt * ph.q[i] * (x[i] - rec[CAFE_REF_XR + i]);
-    double dposw[12], dvelw[12];  // weighted residuals W d per foot
-    for (int f = 0; f < 4; ++f) {
-      const bool c = rec[CAFE_REF_CONTACT + f] > 0;
-      const double* w = c ? ph.w_footreg : ph.w_swingpos;
-      for (int a = 0; a < 3; ++a) {
-        const double d = (s.pf[3 * f + a] - x[a]) - (rec[CAFE_REF_PF + 3 * f + a] - rec[CAFE_REF_PCOM + a]);
-        dposw[3 * f + a] = w[a] * d;
-        dvelw[3 * f + a] = c ? 0.0 : ph.w_swingvel[a] * (s.vf[3 * f + a] - rec[CAFE_REF_VF + 3 * f + a]);
-      }
-    }
-    for (int f = 0; f < 4; ++f) {
-      const bool c = rec[CAFE_REF_CONTACT + f] > 0;
-      for (int i = 3; i < 18; ++i) { double g = 0; for (int a = 0; a < 3; ++a) g += s.J[3 * f + a + 12 * i] * dposw[3 * f + a]; lx[i] += g * dt; }
-      if (!c)
-        for (int i = 0; i < 36; ++i) {
-          double g = 0;
-          for (int a = 0; a < 3; ++a) g += ((i < 18) ? dvq[(3 * f + a + 12 * i) * st] : s.J[3 * f + a + 12 * (i - 18)]) * dvelw[3 * f + a];
-          lx[i] += g * dt;
-        }
-    }
-    double bdj[24], bddj[24], bdh = 0, bddh = 0;
-    const bool jl = reb && !ph.no_joint_limit, mh = reb && !ph.no_min_height;
-    if (jl) {
-      for (int i = 0; i < 12; ++i) {
-        reb_derivs(x[6 + i] - ph.joint_lb[i % 3], ph.reb_joint.delta, bdj[i], bddj[i]);
-        reb_derivs(-x[6 + i] + ph.joint_ub[i % 3], ph.reb_joint.delta, bdj[12 + i], bddj[12 + i]);
-        lx[6 + i] += dt * (ph.reb_joint.eps * bdj[i] - ph.reb_joint.eps * bdj[12 + i]);
-      }
-    }
-    if (mh) {
-      reb_derivs(x[2] - ph.h_min, ph.reb_minheight.delta, bdh, bddh);
-      lx[2] += dt * (ph.reb_minheight.eps * bdh);
-    }
-    const bool jv = reb && ph.joint_speed_limit;
-    double bddv[12];
-    if (jv) {
-      for (int i = 0; i < 12; ++i) {
-        double b1, b2, d1, d2;
-        reb_derivs(x[24 + i] - ph.jointvel_lb, ph.reb_jointvel.delta, b1, d1);
-        reb_derivs(-x[24 + i] + ph.jointvel_ub, ph.reb_jointvel.delta, b2, d2);
-        lx[24 + i] += dt * (ph.reb_jointvel.eps * b1 - ph.reb_jointvel.eps * b2);
-        bddv[i] = ph.reb_jointvel.eps * d1 + ph.reb_jointvel.eps * d2;
-      }
-    }
-    for (int i = 0; i < 36; ++i) ph.lx[gix(k, 36, i, ldb, b)] = lx[i];
-    // lxx: diagonal (tracking + joint-limit / min-height barriers) + per-foot Gauss-Newton blocks. A foot Jacobian only has the
-    // base-rotation columns 3..5 and its own three joint columns (the first three are zeroed by the reference), the swing-foot
-    // velocity Jacobian [dv/dq | J] additionally the six base columns of the velocity half. Only this static pattern is written
-    // (the array is zeroed once at create, the contact flags of a knot never change): entries private to a foot go straight to HBM,
-    // the 9 x 9 base block {3,4,5,18..23} shared by the feet is accumulated in bb first. Same summation order per entry as a dense
-    // accumulation (diagonal, then per foot position term, velocity term).
-    double* lxxg = ph.lxx + gix(k, 1296, 0, ldb, b);
-    double dg[36], bb[81];
-    for (int i = 0; i < 36; ++i) {
-      double v = dt * ph.q[i];
-      if (jl && i >= 6 && i < 18) v += dt * (ph.reb_joint.eps * bddj[i - 6] + ph.reb_joint.eps * bddj[12 + i - 6]);
-      if (mh && i == 2) v += dt * (ph.reb_minheight.eps * bddh);
-      if (jv && i >= 24) v += dt * bddv[i - 24];
-      dg[i] = v;
-    }
-    for (int i = 0; i < 81; ++i) bb[i] = 0.0;
-    for (int p = 0; p < 9; ++p) bb[10 * p] = dg[p < 3 ? 3 + p : 15 + p];
-    for (int i = 0; i < 3; ++i) lxxg[(size_t)(37 * i) * ldb] = dg[i];
-    for (int f = 0; f < 4; ++f) {
-      const bool c = rec[CAFE_REF_CONTACT + f] > 0;
-      const double* w = c ? ph.w_footreg : ph.w_swingpos;
-      // local column list: 0..2 base rotation, 3..5 leg q, 6..11 base velocity, 12..14 leg v; bpos = slot in the base block or -1
-      int cols[15], bpos[15];
-      for (int a = 0; a < 3; ++a) { cols[a] = 3 + a; bpos[a] = a; cols[3 + a] = 6 + 3 * f + a; bpos[3 + a] = -1; cols[12 + a] = 24 + 3 * f + a; bpos[12 + a] = -1; }
-      for (int a = 0; a < 6; ++a) { cols[6 + a] = 18 + a; bpos[6 + a] = 3 + a; }
-      const int nc = c ? 6 : 15;
-      double jx[3][15];
-      for (int ii = 0; ii < 15; ++ii) {
-        const int i = cols[ii];
-        for (int a = 0; a < 3; ++a) jx[a][ii] = c ? 0.0 : ((i < 18) ? dvq[(3 * f + a + 12 * i) * st] : s.J[3 * f + a + 12 * (i - 18)]);
-      }
-      for (int jj = 0; jj < nc; ++jj)
-        for (int ii = 0; ii < nc; ++ii) {
-          const int i = cols[ii], j = cols[jj];
-          const bool shared = bpos[ii] >= 0 && bpos[jj] >= 0;
-          double val = shared ? bb[bpos[ii] + 9 * bpos[jj]] : ((i == j) ? dg[i] : 0.0);
-          if (ii < 6 && jj < 6) {
-            double hh = 0;
-            for (int a = 0; a < 3; ++a) hh += s.J[3 * f + a + 12 * i] * w[a] * s.J[3 * f + a + 12 * j];
-            val += hh * dt;
-          }
-          if (!c) {
-            double hh = 0;
-            for (int a = 0; a < 3; ++a) hh += jx[a][ii] * ph.w_swingvel[a] * jx[a][jj];
-            val += hh * dt;
-          }
-          if (shared) bb[bpos[ii] + 9 * bpos[jj]] = val; else lxxg[(size_t)(i + 36 * j) * ldb] = val;
-        }
-      if (c) for (int a = 0; a < 3; ++a) { const int i = 24 + 3 * f + a; lxxg[(size_t)(37 * i) * ldb] = dg[i]; }  // leg-velocity diagonal of a stance foot
-    }
-    for (int q = 0; q < 9; ++q)
-      for (int p = 0; p < 9; ++p) lxxg[(size_t)((p < 3 ? 3 + p : 15 + p) + 36 * (q < 3 ? 3 + q : 15 + q)) * ldb] = bb[p + 9 * q];
-    double ming;
-    return running_cost_k(ph, rec, x, u, s.grf, s.pf, s.vf, reb, ming);
-  }
+  // (LQ data of a running knot: k_wb_derivs + k_wb_lq)
+  __device__ static double lq_knot(const PhaseDev&, int, int, int, const double*, const double*, const double*, const double*, bool) { return 0.0; }
 
   // ---- terminal cost partials (+AL) and the reset-map Jacobian
   __device__ __noinline__ static void lq_terminal(const PhaseDev& ph, int ldb, int b, const double* rec, const double* x, bool al) {

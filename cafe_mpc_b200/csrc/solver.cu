@@ -12,7 +12,6 @@
 #include <vector>
 #include <cuda_runtime.h>
 #include "../../include/cafe_gpu.h"
-#include "dense_kernels.cuh"
 #include "bwd2.cuh"
 #include "launchers.h"
 #include "host/problem_builders.h"
@@ -85,6 +84,10 @@ __global__ void k_init(const SolverDev* __restrict__ Sp, const double* __restric
   const double* rec = knot_record(ph, k, S.ldb, b, rec_local);
   for (int i = 0; i < ph.n; ++i) { const double v = rec[CAFE_REF_XR + i]; ph.Xbar[gix(k, ph.n, i, S.ldb, b)] = v; ph.X[gix(k, ph.n, i, S.ldb, b)] = v; }
   if (k == 0) for (int i = 0; i < ph.n_td; ++i) { ph.al_sigma[(size_t)i * S.ldb + b] = ph.al_td.sigma; ph.al_lambda[(size_t)i * S.ldb + b] = ph.al_td.lambda; }
+  if (ph.model == CAFE_MODEL_WB && k < ph.h) {   // rows 0..17 of A = [I, dt I] never change (rows 18..35 live in the problem-major tiles)
+    double* Ag = ph.A + gix(k, 1296, 0, S.ldb, b);
+    for (int i = 0; i < 18; ++i) { Ag[(size_t)(i + 36 * i) * S.ldb] = 1.0; Ag[(size_t)(i + 36 * (18 + i)) * S.ldb] = ph.dt; }
+  }
   if (gk == 0) {
     double* x0 = const_cast<double*>(S.x0);
     for (int i = 0; i < n0; ++i) x0[(size_t)i * S.ldb + b] = x0raw[(size_t)b * n0 + i];
@@ -226,7 +229,7 @@ void carve(CafeHandle* H, Carver& cv, size_t& zero_bytes) {
   c.iter_ou = cv.take<int>(ldb); c.iter_in = cv.take<int>(ldb); c.iter = cv.take<int>(ldb); c.ls_total = cv.take<int>(ldb);
   c.reg_total = cv.take<int>(ldb); c.n_hist = cv.take<int>(ldb); c.status = cv.take<int>(ldb);
   c.n_active = cv.take<int>(64);
-  c.act_list = cv.take<int>(ldb); c.pend_list = cv.take<int>(ldb);
+  c.act_list = cv.take<int>(ldb); c.pend_list = cv.take<int>(ldb); c.cur_slot = cv.take<int>(ldb);
   c.reg = cv.take<double>(ldb); c.cost = cv.take<double>(ldb); c.merit = cv.take<double>(ldb); c.feas = cv.take<double>(ldb);
   c.merit_rho = cv.take<double>(ldb); c.dV1 = cv.take<double>(ldb); c.dV2 = cv.take<double>(ldb);
   c.cost_prev = cv.take<double>(ldb); c.merit_prev = cv.take<double>(ldb);
@@ -264,8 +267,10 @@ void carve(CafeHandle* H, Carver& cv, size_t& zero_bytes) {
     ph.lx = cv.take<double>(h * n * ldb); ph.lu = cv.take<double>(h * m * ldb); ph.ly = cv.take<double>(h * p * ldb + 1);
     ph.lxx = cv.take<double>(h * n * n * ldb); ph.luu = cv.take<double>(h * m * m * ldb); ph.lyy = cv.take<double>(h * p * p * ldb + 1);
     ph.Phix = cv.take<double>(n * ldb); ph.Phixx = cv.take<double>(n * n * ldb); ph.Px = cv.take<double>(nn * n * ldb);
-    ph.kkt = cv.take<double>(ph.model == CAFE_MODEL_WB ? h * (size_t)CAFE_KKT_PACK * ldb : 1);
+    ph.kkt = nullptr;
     const bool wb = ph.model == CAFE_MODEL_WB;
+    ph.tm = cv.take<double>(wb ? (size_t)NA * h * CAFE_TM_W * ldb : 1); ph.qdd_t = cv.take<double>(wb ? (size_t)NA * h * 18 * ldb : 1);
+    ph.dp = cv.take<double>(wb ? h * (size_t)CAFE_DP_W * ldb : 1);
     ph.ABpm = cv.take<double>(wb ? h * (size_t)CAFE_WB_AB_TILE * ldb : 2); ph.CDpm = cv.take<double>(wb ? h * (size_t)CAFE_WB_CD_TILE * ldb : 2);
     ph.Kpm = cv.take<double>(h * (size_t)cafe_dev::ld_mma((int)m) * n * ldb + 2);
     ph.Quu = cv.take<double>(h * (size_t)cafe_dev::ld_mma((int)m) * m * ldb + 2); ph.Qux = cv.take<double>(h * (size_t)cafe_dev::ld_mma((int)m) * n * ldb + 2);   // problem-major tiles [b][h][ld(m) x m | n]
@@ -298,29 +303,6 @@ int timed(CafeHandle* H, int slot, F&& launch) {
   return 0;
 }
 
-// cooperative dense part of the whole-body linearisation, one launch per WB phase (template on the number of contact rows)
-int launch_lq_wb_dense(CafeHandle* H, const int* list = nullptr, int n_list = -1, cudaStream_t st = nullptr) {
-  if (!list) { list = H->S.c.act_list; n_list = H->S.n_act; st = H->stream; }
-  const size_t smem = (size_t)CAFE_KKT_SM * 4 * sizeof(double);
-  for (int pi = 0; pi < H->S.n_phases; ++pi) {
-    const PhaseDev& ph = H->S.ph[pi];
-    if (ph.model != CAFE_MODEL_WB || ph.h <= 0) continue;
-    int nc = 0;
-    for (int f = 0; f < 4; ++f) nc += ph.contact[f] > 0;
-    if (n_list <= 0) continue;
-    const dim3 grid((n_list + 3) / 4, ph.h);
-    switch (nc) {
-      case 0: k_lq_wb_dense<0><<<grid, CAFE_DENSE_NT, smem, st>>>(H->dS, pi, list, n_list); break;
-      case 1: k_lq_wb_dense<3><<<grid, CAFE_DENSE_NT, smem, st>>>(H->dS, pi, list, n_list); break;
-      case 2: k_lq_wb_dense<6><<<grid, CAFE_DENSE_NT, smem, st>>>(H->dS, pi, list, n_list); break;
-      case 3: k_lq_wb_dense<9><<<grid, CAFE_DENSE_NT, smem, st>>>(H->dS, pi, list, n_list); break;
-      default: k_lq_wb_dense<12><<<grid, CAFE_DENSE_NT, smem, st>>>(H->dS, pi, list, n_list); break;
-    }
-    H->launches[3]++;
-  }
-  return 0;
-}
-
 int launch_bwd(CafeHandle* H, int first = 0, int n_list = -1, cudaStream_t st = nullptr) {
   if (n_list < 0) { n_list = H->S.n_act; st = H->stream; }
   const unsigned grid = (n_list + 3) / 4 * 4;   // clusters of four listed problems
@@ -334,6 +316,17 @@ int launch_bwd(CafeHandle* H, int first = 0, int n_list = -1, cudaStream_t st = 
 }
 
 }  // namespace
+
+// inside cafe_gpu_create after the handle exists: a failure releases everything created so far
+#define CUDA_OK_H(call)                                                                      \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess) {                                                                 \
+      cafe::set_last_error(std::string(#call) + ": " + cudaGetErrorString(e_));              \
+      cafe_gpu_destroy(H);                                                                   \
+      return CAFE_ERR_CUDA;                                                                  \
+    }                                                                                        \
+  } while (0)
 
 extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, CafeHandle** out) {
   if (!deck || !out || max_batch <= 0 || deck->n_phases <= 0 || deck->n_phases > CAFE_MAX_PHASES) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
@@ -386,19 +379,22 @@ extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, 
     std::memcpy(d.w_footreg, p.w_footreg, sizeof(d.w_footreg)); std::memcpy(d.w_swingpos, p.w_swingpos, sizeof(d.w_swingpos));
     std::memcpy(d.w_swingvel, p.w_swingvel, sizeof(d.w_swingvel)); std::memcpy(d.w_tdvel, p.w_tdvel, sizeof(d.w_tdvel));
     d.reb_grf = p.reb_grf; d.reb_torque = p.reb_torque; d.reb_joint = p.reb_joint; d.reb_minheight = p.reb_minheight; d.al_td = p.al_td;
-    for (int k = 0; k <= p.horizon; ++k) { S.knot_phase[gk] = (short)i; S.knot_k[gk] = (short)k; ++gk; }
+    for (int k = 0; k <= p.horizon; ++k) {
+      if (p.model == CAFE_MODEL_WB && k < p.horizon) S.wbk_gk[S.n_wbk++] = (short)gk;
+      S.knot_phase[gk] = (short)i; S.knot_k[gk] = (short)k; ++gk;
+    }
   }
   Carver sz;
   size_t zb = 0;
   carve(H, sz, zb);
   H->arena_bytes = sz.off + 256;
   cudaError_t e = cudaMalloc(&H->arena, H->arena_bytes);
-  if (e != cudaSuccess) { cafe::set_last_error(std::string("cudaMalloc arena: ") + cudaGetErrorString(e)); delete H; return CAFE_ERR_CUDA; }
+  if (e != cudaSuccess) { cafe::set_last_error(std::string("cudaMalloc arena: ") + cudaGetErrorString(e)); H->arena = nullptr; cafe_gpu_destroy(H); return CAFE_ERR_CUDA; }
   Carver cv; cv.base = H->arena;
   carve(H, cv, H->zero_bytes);
-  CUDA_OK(cudaMemset(H->arena, 0, H->arena_bytes));
-  CUDA_OK(cudaMalloc(&H->d_ref, H->ref_host.size() * sizeof(double)));
-  CUDA_OK(cudaMemcpy(H->d_ref, H->ref_host.data(), H->ref_host.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_OK_H(cudaMemset(H->arena, 0, H->arena_bytes));
+  CUDA_OK_H(cudaMalloc(&H->d_ref, H->ref_host.size() * sizeof(double)));
+  CUDA_OK_H(cudaMemcpy(H->d_ref, H->ref_host.data(), H->ref_host.size() * sizeof(double), cudaMemcpyHostToDevice));
   for (int i = 0; i < deck->n_phases; ++i) { S.ph[i].ref = H->d_ref + (size_t)deck->phase[i].knot_offset * CAFE_REF_W; S.ph[i].ref_pp = nullptr; }
   {
     // structural pattern of the whole-body lxx per knot (cafe::wb_lxx_pattern, host/mhpc_problem.cpp)
@@ -414,53 +410,56 @@ extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, 
       }
     }
     if (!masks.empty()) {
-      CUDA_OK(cudaMalloc(&H->d_lxx_mask, masks.size() * sizeof(unsigned long long)));
-      CUDA_OK(cudaMemcpy(H->d_lxx_mask, masks.data(), masks.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+      CUDA_OK_H(cudaMalloc(&H->d_lxx_mask, masks.size() * sizeof(unsigned long long)));
+      CUDA_OK_H(cudaMemcpy(H->d_lxx_mask, masks.data(), masks.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
     }
     for (int i = 0; i < deck->n_phases; ++i) S.ph[i].lxx_mask = (deck->phase[i].model == CAFE_MODEL_WB && H->d_lxx_mask) ? H->d_lxx_mask + first[i] : nullptr;
   }
   if (all_hkd) {
     unsigned long long hm[36];
     cafe::hkd_lq_patterns(hm);
-    CUDA_OK(cudaMalloc(&H->d_hkd_mask, sizeof(hm)));
-    CUDA_OK(cudaMemcpy(H->d_hkd_mask, hm, sizeof(hm), cudaMemcpyHostToDevice));
+    CUDA_OK_H(cudaMalloc(&H->d_hkd_mask, sizeof(hm)));
+    CUDA_OK_H(cudaMemcpy(H->d_hkd_mask, hm, sizeof(hm), cudaMemcpyHostToDevice));
   }
   for (int i = 0; i < deck->n_phases; ++i) S.ph[i].hkd_mask = (deck->phase[i].model == CAFE_MODEL_HKD) ? H->d_hkd_mask : nullptr;
-  CUDA_OK(cudaMalloc(&H->d_x0raw, (size_t)H->ldb * CAFE_MAX_N * sizeof(double)));
-  CUDA_OK(cudaMalloc(&H->dS, sizeof(SolverDev)));
-  CUDA_OK(cudaMallocHost(&H->h_nactive, 64));
-  CUDA_OK(cudaStreamCreate(&H->stream));
-  for (int i = 0; i < 3; ++i) { CUDA_OK(cudaStreamCreate(&H->stream2[i])); CUDA_OK(cudaEventCreateWithFlags(&H->ev_join[i], cudaEventDisableTiming)); }
-  CUDA_OK(cudaEventCreateWithFlags(&H->ev_fork, cudaEventDisableTiming));
+  CUDA_OK_H(cudaMalloc(&H->d_x0raw, (size_t)H->ldb * CAFE_MAX_N * sizeof(double)));
+  CUDA_OK_H(cudaMalloc(&H->dS, sizeof(SolverDev)));
+  CUDA_OK_H(cudaMallocHost(&H->h_nactive, 64));
+  CUDA_OK_H(cudaStreamCreate(&H->stream));
+  for (int i = 0; i < 3; ++i) { CUDA_OK_H(cudaStreamCreate(&H->stream2[i])); CUDA_OK_H(cudaEventCreateWithFlags(&H->ev_join[i], cudaEventDisableTiming)); }
+  CUDA_OK_H(cudaEventCreateWithFlags(&H->ev_fork, cudaEventDisableTiming));
   if (const char* e = getenv("CAFE_SPLIT_MIN")) H->split_min = atoi(e);
   if (const char* e = getenv("CAFE_SPLIT_N")) { H->split_n = atoi(e); if (H->split_n < 2) H->split_n = 2; if (H->split_n > 4) H->split_n = 4; }
-  CUDA_OK(cudaEventCreate(&H->ev0));
-  CUDA_OK(cudaEventCreate(&H->ev1));
-  CUDA_OK(cudaEventCreate(&H->evs));
-  CUDA_OK(cudaEventCreate(&H->eve));
+  CUDA_OK_H(cudaEventCreate(&H->ev0));
+  CUDA_OK_H(cudaEventCreate(&H->ev1));
+  CUDA_OK_H(cudaEventCreate(&H->evs));
+  CUDA_OK_H(cudaEventCreate(&H->eve));
   H->max_segs = 9 * CAFE_MAX_PHASES;
-  CUDA_OK(cudaMalloc(&H->d_segs, H->max_segs * sizeof(PackSeg)));
+  CUDA_OK_H(cudaMalloc(&H->d_segs, H->max_segs * sizeof(PackSeg)));
   if (all_hkd) {
     H->bwd_variant = 0; H->bwd_pb = 1;
     H->bwd_smem = (size_t)cafe_dev::Bwd2Layout<24, 24, 0, false>::total * sizeof(double);
-    CUDA_OK(cudaFuncSetAttribute(cafe_dev::k_bwd2<0, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H->bwd_smem));
+    CUDA_OK_H(cudaFuncSetAttribute(cafe_dev::k_bwd2<0, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H->bwd_smem));
   } else {
     H->bwd_variant = 1; H->bwd_pb = 1;
     H->bwd_smem = (size_t)cafe_dev::Bwd2Layout<36, 12, 12, true>::total * sizeof(double);
-    CUDA_OK(cudaFuncSetAttribute(cafe_dev::k_bwd2<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H->bwd_smem));
-    CUDA_OK(cudaFuncSetAttribute(cafe_dev::k_bwd2<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H->bwd_smem));
+    CUDA_OK_H(cudaFuncSetAttribute(cafe_dev::k_bwd2<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H->bwd_smem));
+    CUDA_OK_H(cudaFuncSetAttribute(cafe_dev::k_bwd2<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H->bwd_smem));
     if (const char* e = std::getenv("CAFE_BWD_NT")) H->bwd_nt = std::atoi(e) == 256 ? 256 : 128;
   }
+  if (!all_hkd && cafe_dev::wb_coop_configure() != 0) { cafe::set_last_error("cudaFuncSetAttribute (cooperative whole-body kernels) failed"); cafe_gpu_destroy(H); return CAFE_ERR_CUDA; }
+  // Thread-local arrays survive only in the terminal-knot code of the whole-body model (impact map and its Jacobian) and in the
+  // single-shooting chains; their out-of-line callees need call-stack room. The limit is a per-context setting shared with every
+  // other CUDA user of the process, so it is only ever RAISED, and only to what these kernels need (their own frame as reported by
+  // cudaFuncGetAttributes plus the deepest callee chain, bounded by CAFE_STACK_BYTES, default 24 KiB).
   if (!all_hkd) {
-    const int smem = (int)(CAFE_KKT_SM * 4 * sizeof(double));
-    CUDA_OK(cudaFuncSetAttribute(cafe_dev::k_lq_wb_dense<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CUDA_OK(cudaFuncSetAttribute(cafe_dev::k_lq_wb_dense<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CUDA_OK(cudaFuncSetAttribute(cafe_dev::k_lq_wb_dense<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CUDA_OK(cudaFuncSetAttribute(cafe_dev::k_lq_wb_dense<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CUDA_OK(cudaFuncSetAttribute(cafe_dev::k_lq_wb_dense<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    size_t need = cafe_dev::knot_kernels_local_bytes() + 8192, cur = 0;
+    size_t cap = 24 * 1024;
+    if (const char* e = getenv("CAFE_STACK_BYTES")) cap = (size_t)atol(e);
+    if (need < cap) need = cap;
+    CUDA_OK_H(cudaDeviceGetLimit(&cur, cudaLimitStackSize));
+    if (cur < need) CUDA_OK_H(cudaDeviceSetLimit(cudaLimitStackSize, need));
   }
-  // the per-(problem,knot) kernels of the whole-body model keep their KKT algebra in thread-local arrays
-  CUDA_OK(cudaDeviceSetLimit(cudaLimitStackSize, 64 * 1024));
   *out = H;
   return 0;
 }
@@ -506,8 +505,8 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
   const long long nthr_knots = (long long)S.ldb * S.n_knots;
   const int tpb = 128;
   const unsigned g_knots = (unsigned)((nthr_knots + tpb - 1) / tpb);
-  timed(H, 5, [&] { k_init<<<g_knots, tpb, 0, st>>>(H->dS, H->d_x0raw, n0); });
-  if (x0_dev) timed(H, 5, [&] { k_init_devx0<<<(B + 127) / 128, 128, 0, st>>>(H->dS, x0_dev, ldx, n0); });
+  timed(H, CAFE_K_MISC, [&] { k_init<<<g_knots, tpb, 0, st>>>(H->dS, H->d_x0raw, n0); });
+  if (x0_dev) timed(H, CAFE_K_MISC, [&] { k_init_devx0<<<(B + 127) / 128, 128, 0, st>>>(H->dS, x0_dev, ldx, n0); });
   if (H->guess_B > 0) {
     // warm start: Xbar (= X), Ubar (= U) and K of the caller's guess replace the cold-start values; the first rollout (eps = 0)
     // then applies U = Ubar + K (X - Xbar) around it, which is how the reference re-solves after MHPCProblem::update
@@ -526,21 +525,40 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
     CUDA_OK(cudaMalloc(&d_us, segs.size() * sizeof(UnpackSeg)));
     CUDA_OK(cudaMemcpyAsync(d_us, segs.data(), segs.size() * sizeof(UnpackSeg), cudaMemcpyHostToDevice, st));
     dim3 grid(592, (unsigned)segs.size());
-    timed(H, 5, [&] { k_unpack<<<grid, 256, 0, st>>>(d_us, (int)segs.size(), H->ldb, B, off, H->d_guess); });
+    timed(H, CAFE_K_MISC, [&] { k_unpack<<<grid, 256, 0, st>>>(d_us, (int)segs.size(), H->ldb, B, off, H->d_guess); });
     CUDA_OK(cudaStreamSynchronize(st));
     cudaFree(d_us);
   }
+  // one rollout group = the thread-per-knot kernel (trial states and controls; SRB / HKD / terminal knots completely) followed, on
+  // whole-body decks, by the leg-parallel rigid-body terms and the cooperative KKT solve of the running whole-body knots
+  const int n_wbk = S.n_wbk;
+  auto roll_group = [&](cudaStream_t sq, int a0, int a1, const int* list, int n_list, bool tm) {
+    auto run = [&](int slot, auto&& f) { if (tm) timed(H, slot, f); else { f(); H->launches[slot]++; } };
+    run(CAFE_K_ROLL, [&] { cafe_dev::launch_roll(H->dS, S.n_knots, sq, a0, a1, list, n_list); });
+    if (n_wbk > 0) {
+      run(CAFE_K_WB_TERMS, [&] { cafe_dev::launch_wb_terms(H->dS, n_wbk, sq, a0, a1, list, n_list); });
+      run(CAFE_K_WB_FWD, [&] { cafe_dev::launch_wb_fwd(H->dS, n_wbk, sq, a0, a1, list, n_list); });
+    }
+  };
+  auto lq_group = [&](cudaStream_t sq, const int* list, int n_list, bool tm) {
+    auto run = [&](int slot, auto&& f) { if (tm) timed(H, slot, f); else { f(); H->launches[slot]++; } };
+    run(CAFE_K_LQ, [&] { cafe_dev::launch_lq(H->dS, S.n_knots, sq, list, n_list); });
+    if (n_wbk > 0) {
+      run(CAFE_K_WB_DERIVS, [&] { cafe_dev::launch_wb_derivs(H->dS, n_wbk, sq, list, n_list); });
+      run(CAFE_K_WB_LQ, [&] { cafe_dev::launch_wb_lq(H->dS, n_wbk, sq, list, n_list); });
+    }
+  };
   // ---- initial rollout (eps = 0) and bookkeeping
   {
     SolverDev S0 = S;  // same pointers, ladder {0}
     S0.NA = 1; S0.eps[0] = 0.0;
     CUDA_OK(cudaMemcpyAsync(H->dS, &S0, sizeof(SolverDev), cudaMemcpyHostToDevice, st));
-    timed(H, 1, [&] { cafe_dev::launch_compact(H->dS, st, 0); });   // every problem is active: the identity list
-    timed(H, 0, [&] { cafe_dev::launch_roll(H->dS, S.n_knots, st, 0, 1, S.c.act_list, B); });
+    timed(H, CAFE_K_SELECT, [&] { cafe_dev::launch_compact(H->dS, st, 0); });   // every problem is active: the identity list
+    roll_group(st, 0, 1, S.c.act_list, B, true);
     CUDA_OK(cudaMemsetAsync(S.c.n_active, 0, sizeof(int), st));
-    timed(H, 1, [&] { cafe_dev::launch_select(H->dS, B, st, 0); });
-    timed(H, 1, [&] { cafe_dev::launch_compact(H->dS, st, 0); });
-    timed(H, 2, [&] { cafe_dev::launch_accept(H->dS, nthr_knots, st); });
+    timed(H, CAFE_K_SELECT, [&] { cafe_dev::launch_select(H->dS, B, st, 0); });
+    timed(H, CAFE_K_SELECT, [&] { cafe_dev::launch_compact(H->dS, st, 0); });
+    timed(H, CAFE_K_ACCEPT, [&] { cafe_dev::launch_accept(H->dS, nthr_knots, st); });
     CUDA_OK(cudaStreamSynchronize(st));  // S0 must stay alive until the copy has been consumed
     CUDA_OK(cudaMemcpyAsync(H->dS, &S, sizeof(SolverDev), cudaMemcpyHostToDevice, st));
   }
@@ -556,7 +574,7 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
     const bool split = !H->profiling && H->split_min > 0 && n_act >= H->split_min;
     const int a1_first = 1 < S.NA ? 1 : S.NA;
     if (split) {
-      // the active list in split_n parts on as many streams: LQ -> dense -> sweep -> first line-search group per part
+      // the active list in split_n parts on as many streams: LQ -> sweep -> first line-search group per part
       const int np = H->split_n;
       const int part = ((n_act + np - 1) / np + 127) & ~127;
       const int* lst = S.c.act_list;
@@ -566,37 +584,35 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
         if (cnt <= 0) break;
         cudaStream_t sq = q == 0 ? st : H->stream2[q - 1];
         if (q > 0) CUDA_OK(cudaStreamWaitEvent(sq, H->ev_fork, 0));
-        cafe_dev::launch_lq(H->dS, S.n_knots, sq, lst + first, cnt);
-        if (H->bwd_variant == 1) launch_lq_wb_dense(H, lst + first, cnt, sq);
+        lq_group(sq, lst + first, cnt, false);
         launch_bwd(H, first, cnt, sq);
-        cafe_dev::launch_roll(H->dS, S.n_knots, sq, 0, a1_first, lst + first, cnt);
-        H->launches[3]++; H->launches[4]++; H->launches[0]++;
+        H->launches[CAFE_K_BWD]++;
+        roll_group(sq, 0, a1_first, lst + first, cnt, false);
         if (q > 0) { CUDA_OK(cudaEventRecord(H->ev_join[q - 1], sq)); CUDA_OK(cudaStreamWaitEvent(st, H->ev_join[q - 1], 0)); }
       }
     } else {
-      timed(H, 3, [&] { cafe_dev::launch_lq(H->dS, S.n_knots, st, S.c.act_list, n_act); });
-      if (H->bwd_variant == 1) timed(H, 5, [&] { launch_lq_wb_dense(H); });
-      timed(H, 4, [&] { launch_bwd(H); });
+      lq_group(st, S.c.act_list, n_act, true);
+      timed(H, CAFE_K_BWD, [&] { launch_bwd(H); });
     }
     // staged line search: step sizes are evaluated in growing groups; most problems accept one of the first
     for (int a0 = 0, width = 1; a0 < S.NA; a0 += width, width *= 2) {
       const int a1 = (a0 + width < S.NA) ? a0 + width : S.NA;
       // the first group runs over the active list (problems that skip the line search return at once), later groups over
       // the list of line searches that still need step sizes
-      if (a0 == 0) { if (!split) timed(H, 0, [&] { cafe_dev::launch_roll(H->dS, S.n_knots, st, a0, a1, S.c.act_list, n_act); }); }
-      else timed(H, 0, [&] { cafe_dev::launch_roll(H->dS, S.n_knots, st, a0, a1, S.c.pend_list, H->h_nactive[1]); });
+      if (a0 == 0) { if (!split) roll_group(st, a0, a1, S.c.act_list, n_act, true); }
+      else roll_group(st, a0, a1, S.c.pend_list, H->h_nactive[1], true);
       CUDA_OK(cudaMemsetAsync(S.c.n_pending, 0, sizeof(int), st));
-      timed(H, 1, [&] { cafe_dev::launch_ls_scan(H->dS, B, st, a0, a1); });
+      timed(H, CAFE_K_SELECT, [&] { cafe_dev::launch_ls_scan(H->dS, B, st, a0, a1); });
       if (a1 >= S.NA) break;
-      timed(H, 1, [&] { cafe_dev::launch_compact(H->dS, st, 1); });
+      timed(H, CAFE_K_SELECT, [&] { cafe_dev::launch_compact(H->dS, st, 1); });
       CUDA_OK(cudaMemcpyAsync(H->h_nactive + 1, S.c.n_pending, sizeof(int), cudaMemcpyDeviceToHost, st));
       CUDA_OK(cudaStreamSynchronize(st));
       if (H->h_nactive[1] == 0) break;
     }
     CUDA_OK(cudaMemsetAsync(S.c.n_active, 0, sizeof(int), st));
-    timed(H, 1, [&] { cafe_dev::launch_select(H->dS, B, st, 1); });
-    timed(H, 1, [&] { cafe_dev::launch_compact(H->dS, st, 0); });
-    timed(H, 2, [&] { cafe_dev::launch_accept(H->dS, nthr_knots, st); });
+    timed(H, CAFE_K_SELECT, [&] { cafe_dev::launch_select(H->dS, B, st, 1); });
+    timed(H, CAFE_K_SELECT, [&] { cafe_dev::launch_compact(H->dS, st, 0); });
+    timed(H, CAFE_K_ACCEPT, [&] { cafe_dev::launch_accept(H->dS, nthr_knots, st); });
   }
   CUDA_OK(cudaEventRecord(H->eve, st));
   CUDA_OK(cudaStreamSynchronize(st));

@@ -1,10 +1,9 @@
 // wb_gen_wrappers.cu — out-of-line instantiations of the generated whole-body routines (gen/wb_gen.h), one copy each,
 // with plain array outputs. Separate translation unit (relocatable device code) so that the slow ptxas pass over these
 // straight-line functions only re-runs when the generated header changes.
-// The routines that only k_lq calls (RNEA derivatives, kinematic partials) carry a CAFE_GEN_SYNC marker every 1024 operations: a CTA
-// barrier here. k_lq gives every CTA one knot (knot_kernels.cuh), so all live threads of a CTA run the same routine and meet at the same
-// markers; the four warps then stay within ~10 KB of the straight-line code and share instruction-cache lines.
-#define CAFE_GEN_SYNC __syncthreads();
+// These per-leg instantiations serve the terminal knots (impact map and its Jacobian) and the single-shooting chains only; the running
+// knots use the leg-generic routines of gen/wb_leg_gen.h (wb_leg_kernels.cu). No lock-step markers here.
+#define CAFE_GEN_SYNC
 #define CAFE_HD __device__ __forceinline__   // device-only instantiations here (the host tests include the header on their own)
 #include "gen/wb_gen.h"
 #include "wb_pieces.h"
@@ -28,15 +27,6 @@ __device__ void wbg_terms(const double* q, const double* v, double* nle, double*
   wbg_terms_leg0(q, v, nle, Mlow, J, gam, pf, vf); wbg_terms_leg1(q, v, nle, Mlow, J, gam, pf, vf);
   wbg_terms_leg2(q, v, nle, Mlow, J, gam, pf, vf); wbg_terms_leg3(q, v, nle, Mlow, J, gam, pf, vf);
 }
-// lock-step variant (see wbg_rnea_derivs_lockstep): every live thread of the CTA evaluates a running knot of the same phase
-__device__ void wbg_terms_lockstep(const double* q, const double* v, double* nle, double* Mlow, double* J, double* gam, double* pf, double* vf) {
-  for (int i = 0; i < 6; ++i) nle[i] = 0.0;
-  __syncthreads(); wbg_terms_trunk(q, v, nle, Mlow);
-  __syncthreads(); wbg_terms_leg0(q, v, nle, Mlow, J, gam, pf, vf);
-  __syncthreads(); wbg_terms_leg1(q, v, nle, Mlow, J, gam, pf, vf);
-  __syncthreads(); wbg_terms_leg2(q, v, nle, Mlow, J, gam, pf, vf);
-  __syncthreads(); wbg_terms_leg3(q, v, nle, Mlow, J, gam, pf, vf);
-}
 __device__ __noinline__ void wbg_feet(const double* q, const double* v, double* pf, double* vf, double* J) {
   cafe_gen_wb::wb_feet(q, v, [&](int i, double x) { pf[i] = x; }, [&](int i, double x) { vf[i] = x; }, [&](int i, double x) { J[i] = x; });
 }
@@ -54,16 +44,6 @@ __device__ void wbg_rnea_derivs(const double* q, const double* v, const double* 
   wbg_rnea_trunk(q, v, a, dq, dv, st);
   wbg_rnea_leg0(q, v, a, dq, dv, st); wbg_rnea_leg1(q, v, a, dq, dv, st); wbg_rnea_leg2(q, v, a, dq, dv, st); wbg_rnea_leg3(q, v, a, dq, dv, st);
 }
-// Lock-step variants for k_lq (every live thread of the CTA evaluates the same running knot): a CTA barrier between the pieces keeps
-// the four warps inside the same stretch of straight-line code, so that they share instruction-cache lines (ncu: stall_no_instruction
-// 8.5 cycles per issue without it; each leg piece is tens of KB of SASS).
-__device__ void wbg_rnea_derivs_lockstep(const double* q, const double* v, const double* a, double* dq, double* dv, size_t st) {
-  __syncthreads(); wbg_rnea_trunk(q, v, a, dq, dv, st);
-  __syncthreads(); wbg_rnea_leg0(q, v, a, dq, dv, st);
-  __syncthreads(); wbg_rnea_leg1(q, v, a, dq, dv, st);
-  __syncthreads(); wbg_rnea_leg2(q, v, a, dq, dv, st);
-  __syncthreads(); wbg_rnea_leg3(q, v, a, dq, dv, st);
-}
 __device__ __noinline__ void wbg_grav_derivs(const double* q, double* dq) {
   cafe_gen_wb::wb_grav_derivs(q, [&](int i, double x) { dq[i] = x; });
 }
@@ -77,12 +57,6 @@ CAFE_KIN_FOOT(0) CAFE_KIN_FOOT(1) CAFE_KIN_FOOT(2) CAFE_KIN_FOOT(3)
 __device__ void wbg_kin_partials(const double* q, const double* v, const double* a, const double* F, double* dvq, double* daq, double* dav, double* djtf, size_t st) {
   wbg_kin_foot0(q, v, a, F, dvq, daq, dav, djtf, st); wbg_kin_foot1(q, v, a, F, dvq, daq, dav, djtf, st);
   wbg_kin_foot2(q, v, a, F, dvq, daq, dav, djtf, st); wbg_kin_foot3(q, v, a, F, dvq, daq, dav, djtf, st);
-}
-__device__ void wbg_kin_partials_lockstep(const double* q, const double* v, const double* a, const double* F, double* dvq, double* daq, double* dav, double* djtf, size_t st) {
-  __syncthreads(); wbg_kin_foot0(q, v, a, F, dvq, daq, dav, djtf, st);
-  __syncthreads(); wbg_kin_foot1(q, v, a, F, dvq, daq, dav, djtf, st);
-  __syncthreads(); wbg_kin_foot2(q, v, a, F, dvq, daq, dav, djtf, st);
-  __syncthreads(); wbg_kin_foot3(q, v, a, F, dvq, daq, dav, djtf, st);
 }
 __device__ __noinline__ void wbg_footvel_partial(const double* q, const double* v, double* dvq) {
   cafe_gen_wb::wb_footvel_partial(q, v, [&](int i, double x) { dvq[i] = x; });

@@ -144,7 +144,18 @@ long cafe_hkd_lcm_command_size(int n_steps);
 int cafe_gpu_get_hkd_lcm_commands(CafeHandle* h, int n_steps, float* out /*[B][cafe_hkd_lcm_command_size]*/);
 int cafe_gpu_get_hkd_lcm_commands_device(CafeHandle* h, int n_steps, float* out_dev);
 /* device-time breakdown of the last solve, ms per kernel family, and launch counts */
-#define CAFE_NKERNELS 6 /* 0 roll 1 select 2 accept 3 lq 4 bwd 5 misc */
+/* timing slots of cafe_gpu_get_timing: one per kernel family */
+#define CAFE_K_ROLL 0      /* k_roll: trial states / controls of every knot; SRB, HKD and terminal knots completely */
+#define CAFE_K_SELECT 1    /* k_ls_scan, k_select, k_compact */
+#define CAFE_K_ACCEPT 2    /* k_accept */
+#define CAFE_K_LQ 3        /* k_lq: SRB / HKD knots, terminal knots (incl. impact-map Jacobians) */
+#define CAFE_K_BWD 4       /* k_bwd2: backward sweep + linear rollout */
+#define CAFE_K_MISC 5      /* initialisation, warm-start unpack */
+#define CAFE_K_WB_TERMS 6  /* k_wb_terms: leg-parallel rigid-body terms of the whole-body trial knots */
+#define CAFE_K_WB_FWD 7    /* k_wb_fwd: cooperative KKT contact dynamics, x+, GRF, cost, defects */
+#define CAFE_K_WB_DERIVS 8 /* k_wb_derivs: leg-parallel RNEA derivatives and foot kinematic partials */
+#define CAFE_K_WB_LQ 9     /* k_wb_lq: cooperative KKT sensitivities (A, B, C, D) and cost / barrier partials */
+#define CAFE_NKERNELS 10
 int cafe_gpu_get_timing(CafeHandle* h, double ms[CAFE_NKERNELS], long launches[CAFE_NKERNELS], int* ticks);
 /* device time (CUDA events on the solver's stream) of the last cafe_gpu_solve_batch*, in ms */
 int cafe_gpu_get_solve_ms(CafeHandle* h, double* ms);

@@ -82,7 +82,8 @@ def gen_lib():
     os.makedirs(out, exist_ok=True)
     so = os.path.join(out, "libgen_host.so")
     src = os.path.join(REPO, "tests", "gen_host.cpp")
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(os.path.join(REPO, "cafe_mpc_b200/csrc/gen/wb_gen.h"))):
+    deps = [src] + [os.path.join(REPO, "cafe_mpc_b200/csrc", f) for f in ("gen/wb_gen.h", "gen/wb_leg_gen.h", "wb_leg_tables.h")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
         subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", so, src], check=True)
     return C.CDLL(so)
 
@@ -94,6 +95,44 @@ def gen_wb(lib, name, ins, out_shapes):
     pout = (C.c_void_p * len(outs))(*[a.ctypes.data for a in outs])
     assert lib.gen_eval_wb(name.encode(), pin, pout) == 0
     return [o.reshape(s, order="F") for o, s in zip(outs, out_shapes)]
+
+
+def gen_wbl(lib, name, ins, out_shapes):
+    ins = [np.ascontiguousarray(np.asarray(a, dtype=np.float64)) for a in ins]
+    outs = [np.zeros(int(np.prod(s))) for s in out_shapes]
+    pin = (C.c_void_p * len(ins))(*[a.ctypes.data for a in ins])
+    pout = (C.c_void_p * len(outs))(*[a.ctypes.data for a in outs])
+    assert lib.gen_eval_wbl(name.encode(), pin, pout) == 0
+    return [o.reshape(s, order="F") for o, s in zip(outs, out_shapes)]
+
+
+def test_leg_generic_routines_match_per_leg_routines_and_reference_casadi(gen_lib):
+    """The leg-generic routines of the running whole-body knots (gen/wb_leg_gen.h: one routine for all four legs, the mirrored leg
+    constants as data; derivatives in forward mode, a few directions per routine), assembled through their compact-slot tables like
+    the device kernels do, equal the per-leg routines of gen/wb_gen.h and the reference's CasADi kinematic partials."""
+    rng = np.random.default_rng(23)
+    for _ in range(4):
+        q, v, a, F = rng.normal(size=18) * .6, rng.normal(size=18), rng.normal(size=18) * 3, rng.normal(size=12) * 20
+        shapes_t = [(18,), (18, 18), (12, 18), (12,), (12,), (12,)]
+        new = gen_wbl(gen_lib, "wbl_terms", [q, v], shapes_t)
+        old = gen_wb(gen_lib, "wb_terms_pieces", [q, v], shapes_t)
+        for x, y in zip(new, old):
+            np.testing.assert_allclose(x, y, rtol=0, atol=1e-14 * max(1.0, np.max(np.abs(y))))
+        shapes_d = [(18, 18), (18, 18), (12, 18), (12, 18), (12, 18), (18, 18)]
+        dq, dv, dvq, daq, dav, djtf = gen_wbl(gen_lib, "wbl_derivs", [q, v, a, F], shapes_d)
+        odq, odv = gen_wb(gen_lib, "wb_rnea_derivs", [q, v, a], [(18, 18)] * 2)
+        odvq, odaq, odav, odjtf = gen_wb(gen_lib, "wb_kin_partials", [q, v, a, F], [(12, 18)] * 3 + [(18, 18)])
+        for x, y in ((dq, odq), (dv, odv), (dvq, odvq), (daq, odaq), (dav, odav), (djtf, odjtf)):
+            np.testing.assert_allclose(x, y, rtol=0, atol=2e-13 * max(1.0, np.max(np.abs(y))))
+        rv = casadi_eval("footVelPartialDq", [q, v], [(3, 18)] * 4)
+        raq = casadi_eval("footAccPartialDq", [q, v, a], [(3, 18)] * 4)
+        rav = casadi_eval("footAccPartialDv", [q, v, a], [(3, 18)] * 4)
+        rf = casadi_eval("footForcePartialDq", [q, F], [(18, 18)] * 4)
+        for f in range(4):
+            np.testing.assert_allclose(dvq[3 * f:3 * f + 3], rv[f], rtol=0, atol=1e-13)
+            np.testing.assert_allclose(daq[3 * f:3 * f + 3], raq[f], rtol=0, atol=2e-12)
+            np.testing.assert_allclose(dav[3 * f:3 * f + 3], rav[f], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(djtf, sum(rf), rtol=0, atol=1e-12)
 
 
 def test_generated_kinematic_partials_match_reference_casadi(gen_lib):

@@ -12,7 +12,7 @@ that replaces the CasADi-generated kinematic partials."""
 import math
 import xml.etree.ElementTree as ET
 
-from symbolic import Ctx, Sym
+from symbolic import Ctx, Dual, Sym
 
 GRAV = 9.81
 LEGS = ["fl", "fr", "hl", "hr"]
@@ -86,7 +86,9 @@ class WBModel:
 
     def __init__(self, ctx, params, hip_yaw):
         self.c = ctx
-        K = ctx.const
+        # numbers become constants of the DAG; symbolic scalars pass through (leg-generic pieces: tools/gen_wb_leg.py
+        # hands the mirrored leg constants in as input variables)
+        K = lambda x: x if isinstance(x, (Sym, Dual)) else ctx.const(x)
         self.K = K
         I3 = [[K(1.0 if i == j else 0.0) for j in range(3)] for i in range(3)]
         z3 = [K(0.0)] * 3
