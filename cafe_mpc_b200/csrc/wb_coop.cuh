@@ -23,12 +23,14 @@ namespace cafe_dev {
 #define CAFE_FULL 0xffffffffu
 static_assert(CAFE_TM_LEG_W == CAFE_WBL_TM_W && CAFE_DP_LEG_W == CAFE_WBL_DP_W, "device_types.cuh and gen/wb_leg_gen.h disagree");
 
-static __constant__ unsigned char c_tm_kind[CAFE_WBL_TM_W] = CAFE_WBL_TM_KIND;
-static __constant__ unsigned char c_tm_row[CAFE_WBL_TM_W] = CAFE_WBL_TM_ROW;
-static __constant__ unsigned char c_tm_col[CAFE_WBL_TM_W] = CAFE_WBL_TM_COL;
-static __constant__ unsigned char c_dp_kind[CAFE_WBL_DP_W] = CAFE_WBL_DP_KIND;
-static __constant__ unsigned char c_dp_row[CAFE_WBL_DP_W] = CAFE_WBL_DP_ROW;
-static __constant__ unsigned char c_dp_col[CAFE_WBL_DP_W] = CAFE_WBL_DP_COL;
+// compact slot -> (array, local row, local column). The lanes of a warp read DIFFERENT slots: plain global arrays (one coalesced,
+// L1-resident load per warp), not __constant__ (a constant-bank access with 32 distinct addresses is replayed 32 times).
+static __device__ const unsigned char c_tm_kind[CAFE_WBL_TM_W] = CAFE_WBL_TM_KIND;
+static __device__ const unsigned char c_tm_row[CAFE_WBL_TM_W] = CAFE_WBL_TM_ROW;
+static __device__ const unsigned char c_tm_col[CAFE_WBL_TM_W] = CAFE_WBL_TM_COL;
+static __device__ const unsigned char c_dp_kind[CAFE_WBL_DP_W] = CAFE_WBL_DP_KIND;
+static __device__ const unsigned char c_dp_row[CAFE_WBL_DP_W] = CAFE_WBL_DP_ROW;
+static __device__ const unsigned char c_dp_col[CAFE_WBL_DP_W] = CAFE_WBL_DP_COL;
 
 // global coordinate of local coordinate l (0..5 base, 6..8 leg) of leg f
 __device__ __forceinline__ int wbl_g(int f, int l) { return l < 6 ? l : 3 * f + l; }
@@ -64,24 +66,48 @@ struct WbSm {
   static constexpr int totalLq = (oLx + 128 + 1) & ~1;
 };
 
+// stage W elements of a batch-major array (element e at src[e * ldb]) into shared memory, 32 element-threads per problem: every
+// load is issued before the first store, so that one memory round trip covers the whole pack
+template <int W>
+__device__ __forceinline__ void wb_stage(double* __restrict__ dst, const double* __restrict__ src, int ldb, int e0) {
+  constexpr int NI = (W + 31) / 32;
+  double v[NI];
+#pragma unroll
+  for (int i = 0; i < NI; ++i) { const int e = e0 + 32 * i; v[i] = (e < W) ? src[(size_t)e * ldb] : 0.0; }
+#pragma unroll
+  for (int i = 0; i < NI; ++i) { const int e = e0 + 32 * i; if (e < W) dst[e] = v[i]; }
+}
+
 // in-place Cholesky of the lower triangle (column-major, ld LD), n <= 32: lane i owns row j + i of the current column
-template <int LD>
-__device__ __forceinline__ void chol_warp(double* A, int n, int lane) {
-  for (int j = 0; j < n; ++j) {
+// dinv[j] = 1 / L(j,j)
+template <int LD, int NMAX>
+__device__ __forceinline__ void chol_warp(double* A, double* dinv, int n, int lane) {
+#pragma unroll
+  for (int j = 0; j < NMAX; ++j) {
+    if (j >= n) break;
     const int i = j + lane;
     double s = 0;
-    if (i < n) { s = A[i + LD * j]; for (int k = 0; k < j; ++k) s -= A[i + LD * k] * A[j + LD * k]; }
+    if (i < n) {
+      s = A[i + LD * j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) s -= A[i + LD * k] * A[j + LD * k];
+    }
     const double d = sqrt(__shfl_sync(CAFE_FULL, s, 0));
     const double inv = 1.0 / d;
     if (i < n) A[i + LD * j] = (lane == 0) ? d : s * inv;
+    if (lane == 0) dinv[j] = inv;
     __syncwarp();
   }
 }
 
 struct WbRows {   // active contact rows of a contact set: row(c) = 3 foot(c / 3) + c % 3 (bit arithmetic: no thread-local arrays)
-  int nr; unsigned cm;
-  __device__ __forceinline__ void set(const int* contact) { cm = 0; for (int f = 0; f < 4; ++f) if (contact[f] > 0) cm |= 1u << f; nr = 3 * __popc(cm); }
-  __device__ __forceinline__ int row(int c) const { return 3 * (int)__fns(cm, 0, c / 3 + 1) + c % 3; }
+  int nr; unsigned cm; unsigned long long rp;   // rp: row(c) in nibble c
+  __device__ __forceinline__ void set(const int* contact) {
+    cm = 0; rp = 0; int j = 0;
+    for (int f = 0; f < 4; ++f) if (contact[f] > 0) { cm |= 1u << f; for (int r = 0; r < 3; ++r) rp |= (unsigned long long)(3 * f + r) << (4 * (3 * j + r)); ++j; }
+    nr = 3 * j;
+  }
+  __device__ __forceinline__ int row(int c) const { return (int)((rp >> (4 * c)) & 15ull); }
   // index among the active rows of foot row fr = 3 f + r, or -1
   __device__ __forceinline__ int arow(int fr) const { const int f = fr / 3; return ((cm >> f) & 1u) ? 3 * __popc(cm & ((1u << f) - 1u)) + fr % 3 : -1; }
 };
@@ -116,9 +142,9 @@ __device__ __forceinline__ void wb_assemble_terms(double* sm, const double* stg,
 // S = Y^T Y + damping I, chol(S), 1/diag
 __device__ __forceinline__ void wb_factor(double* sm, const WbRows& rw, double damping, bool with_rhs, int lane) {
   double* L = sm + WbSm::oL; const double* J = sm + WbSm::oJ; double* Y = sm + WbSm::oY; double* S = sm + WbSm::oS;
-  chol_warp<WbSm::ldL>(L, 18, lane);
-  if (lane < 18) sm[WbSm::oDinv + lane] = 1.0 / L[lane + WbSm::ldL * lane];
+  chol_warp<WbSm::ldL, 18>(L, sm + WbSm::oDinv, 18, lane);
   const int nr = rw.nr;
+  const double* dinv = sm + WbSm::oDinv;
   if (lane < nr || (with_rhs && lane == nr)) {
     double y[18];
     if (lane < nr) { const int row = rw.row(lane);
@@ -133,16 +159,16 @@ __device__ __forceinline__ void wb_factor(double* sm, const WbRows& rw, double d
       double s = y[i];
 #pragma unroll
       for (int k = 0; k < i; ++k) s -= L[i + WbSm::ldL * k] * y[k];
-      y[i] = s / L[i + WbSm::ldL * i];
+      y[i] = s * dinv[i];
     }
     double* dst = (lane < nr) ? Y + WbSm::ldY * lane : sm + WbSm::oMb;
 #pragma unroll
     for (int i = 0; i < 18; ++i) dst[i] = y[i];
   }
   __syncwarp();
-  for (int c = 0; c < nr; ++c) {
-    const int r = c + lane;
-    if (r < nr) {
+  for (int e = lane; e < nr * nr; e += 32) {   // lower triangle of S, one entry per lane and round
+    const int r = e % nr, c = e / nr;
+    if (r >= c) {
       double d = 0;
 #pragma unroll
       for (int i = 0; i < 18; ++i) d += Y[i + WbSm::ldY * r] * Y[i + WbSm::ldY * c];
@@ -150,9 +176,7 @@ __device__ __forceinline__ void wb_factor(double* sm, const WbRows& rw, double d
     }
   }
   __syncwarp();
-  chol_warp<WbSm::ldS>(S, nr, lane);
-  if (lane < nr) sm[WbSm::oSdinv + lane] = 1.0 / S[lane + WbSm::ldS * lane];
-  __syncwarp();
+  chol_warp<WbSm::ldS, 12>(S, sm + WbSm::oSdinv, nr, lane);
 }
 
 // running cost of a whole-body knot (QuadraticTrackingCost + foot costs + dt * ReB terms) and the minimum of the path-constraint
@@ -228,7 +252,7 @@ __device__ __forceinline__ double wb_cost_coop(const PhaseDev& ph, const double*
 
 // ------------------------------------------------------------------------------------------------ K-ROLL, whole-body running knots
 // grid (ceil(n_list / 4), n_wbk, a1 - a0), 128 threads
-__global__ void __launch_bounds__(128) k_wb_fwd(const SolverDev* __restrict__ Sp, int a0, const int* __restrict__ list, int n_list) {
+__global__ void __launch_bounds__(128, 4) k_wb_fwd(const SolverDev* __restrict__ Sp, int a0, const int* __restrict__ list, int n_list) {
   const SolverDev& S = *Sp;
   extern __shared__ __align__(16) double smem[];
   const int t = threadIdx.x, w = t >> 5, lane = t & 31;
@@ -243,7 +267,7 @@ __global__ void __launch_bounds__(128) k_wb_fwd(const SolverDev* __restrict__ Sp
       double* sm = smem + p * WbSm::totalFwd;
       double* stg = sm + WbSm::oStg;
       const double* tm = ph.tm + ((size_t)(a * h + k) * CAFE_TM_W) * ldb + b;
-      for (int e = t >> 2; e < CAFE_TM_W; e += 32) stg[e] = tm[(size_t)e * ldb];
+      wb_stage<CAFE_TM_W>(stg, tm, ldb, t >> 2);
       for (int e = t >> 2; e < 36; e += 32) sm[WbSm::oX + e] = ph.Xt[aX + gix(k, 36, e, ldb, b)];
       for (int e = t >> 2; e < 12; e += 32) sm[WbSm::oU + e] = ph.Ut[aU + gix(k, 12, e, ldb, b)];
       for (int e = t >> 2; e < CAFE_REF_W; e += 32)
@@ -270,19 +294,20 @@ __global__ void __launch_bounds__(128) k_wb_fwd(const SolverDev* __restrict__ Sp
     const int r = rw.row(lane);
     lam = -d - (sm[WbSm::oGam + r] + 2.0 * ph.BG_alpha * sm[WbSm::oVf + r]);
   }
+  const double* sdinv = sm + WbSm::oSdinv; const double* dinv = sm + WbSm::oDinv;
   for (int i = 0; i < nr; ++i) {
-    const double xi = __shfl_sync(CAFE_FULL, lam, i) / Ss[i + WbSm::ldS * i];
+    const double xi = __shfl_sync(CAFE_FULL, lam, i) * sdinv[i];
     if (lane == i) lam = xi; else if (lane > i && lane < nr) lam -= Ss[lane + WbSm::ldS * i] * xi;
   }
   for (int i = nr - 1; i >= 0; --i) {
-    const double xi = __shfl_sync(CAFE_FULL, lam, i) / Ss[i + WbSm::ldS * i];
+    const double xi = __shfl_sync(CAFE_FULL, lam, i) * sdinv[i];
     if (lane == i) lam = xi; else if (lane < i) lam -= Ss[i + WbSm::ldS * lane] * xi;
   }
   // qdd = L^-T (L^-1 b + Y lambda)
   double mb = lane < 18 ? sm[WbSm::oMb + lane] : 0.0;
   for (int c = 0; c < nr; ++c) { const double lc = __shfl_sync(CAFE_FULL, lam, c); if (lane < 18) mb += Y[lane + WbSm::ldY * c] * lc; }
   for (int i = 17; i >= 0; --i) {
-    const double xi = __shfl_sync(CAFE_FULL, mb, i) / L[i + WbSm::ldL * i];
+    const double xi = __shfl_sync(CAFE_FULL, mb, i) * dinv[i];
     if (lane == i) mb = xi; else if (lane < i) mb -= L[i + WbSm::ldL * lane] * xi;
   }
   // outputs: GRF (y), qdd, x+ and the defect against the next shooting state
@@ -318,6 +343,90 @@ __global__ void __launch_bounds__(128) k_wb_fwd(const SolverDev* __restrict__ Sp
   if (lane == 0) { ph.cost_t[aS + (size_t)k * ldb + b] = l; ph.ming_t[aS + (size_t)k * ldb + b] = ming; }
 }
 
+// column z of [q v tau] (lane = column, two passes over the 48 columns): r <- L^-1 R_z; w = Ls^-T Ls^-1 (Y^T r - a_z); r <- L^-T (Y w - r).
+// NR = number of contact rows (compile time: the loops unroll without predicates). State columns go back into the lane's (dead) columns
+// of R / a, control columns straight to the problem-major tiles.
+template <int NR>
+__device__ __forceinline__ void wb_colsolve(double* sm, double* __restrict__ ABt, double* __restrict__ CDt, const WbRows& rw, double dt, int lane) {
+  // volatile: the ~700 operand loads of a pass stay in program order next to their use (fully unrolled, ptxas otherwise hoists
+  // them all to the top of the pass and spills 4 KB per thread)
+  const volatile double* L = sm + WbSm::oL; const volatile double* dinv = sm + WbSm::oDinv; const volatile double* Y = sm + WbSm::oY;
+  const volatile double* Ls = sm + WbSm::oS; const volatile double* sdinv = sm + WbSm::oSdinv;
+  double* R = sm + WbSm::oR; double* Aa = sm + WbSm::oA;
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    const int col = pass * 32 + lane;
+    if (col >= 48) break;
+    double r[18], wv[NR > 0 ? NR : 1];
+    if (col < 36) {
+#pragma unroll
+      for (int i = 0; i < 18; ++i) r[i] = R[i + 18 * col];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 18; ++i) r[i] = (i == 6 + (col - 36)) ? -1.0 : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 18; ++i) {
+      double s = r[i];
+#pragma unroll
+      for (int kk = 0; kk < i; ++kk) s -= L[i + WbSm::ldL * kk] * r[kk];
+      r[i] = s * dinv[i];
+    }
+    if constexpr (NR > 0) {
+#pragma unroll
+      for (int c = 0; c < NR; ++c) {
+        double d = 0;
+#pragma unroll
+        for (int i = 0; i < 18; ++i) d += Y[i + WbSm::ldY * c] * r[i];
+        wv[c] = d - ((col < 36) ? Aa[c + 12 * col] : 0.0);
+      }
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        double s = wv[i];
+#pragma unroll
+        for (int kk = 0; kk < i; ++kk) s -= Ls[i + WbSm::ldS * kk] * wv[kk];
+        wv[i] = s * sdinv[i];
+        }
+#pragma unroll
+      for (int i = NR - 1; i >= 0; --i) {
+        wv[i] *= sdinv[i];
+#pragma unroll
+        for (int kk = 0; kk < i; ++kk) wv[kk] -= Ls[i + WbSm::ldS * kk] * wv[i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 18; ++i) {
+      double d = -r[i];
+      if constexpr (NR > 0) {
+#pragma unroll
+        for (int c = 0; c < NR; ++c) d += Y[i + WbSm::ldY * c] * wv[c];
+      }
+      r[i] = d;
+    }
+#pragma unroll
+    for (int i = 17; i >= 0; --i) {
+      r[i] *= dinv[i];
+#pragma unroll
+      for (int kk = 0; kk < i; ++kk) r[kk] -= L[i + WbSm::ldL * kk] * r[i];
+    }
+    if (col < 36) {
+#pragma unroll
+      for (int i = 0; i < 18; ++i) R[i + 18 * col] = ((col == 18 + i) ? 1.0 : 0.0) + r[i] * dt;
+      if constexpr (NR > 0) {
+#pragma unroll
+        for (int c = 0; c < NR; ++c) Aa[c + 12 * col] = wv[c];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 18; ++i) ABt[i + 20 * col] = r[i] * dt;
+      if constexpr (NR > 0) {
+#pragma unroll
+        for (int c = 0; c < NR; ++c) CDt[rw.row(c) + 12 * col] = wv[c];
+      }
+    }
+  }
+}
+
 // --------------------------------------------------------------------------------------------------- K-LQ, whole-body running knots
 // grid (ceil(n_list / 4), n_wbk), 128 threads. lxx_list: structural pattern of lxx is implied by the contact flags of the record.
 __global__ void __launch_bounds__(128) k_wb_lq(const SolverDev* __restrict__ Sp, const int* __restrict__ list, int n_list) {
@@ -333,7 +442,7 @@ __global__ void __launch_bounds__(128) k_wb_lq(const SolverDev* __restrict__ Sp,
   if (bp >= 0) {
     double* stg = smem + p4 * WbSm::totalLq + WbSm::oStg;
     const double* dp = ph.dp + ((size_t)k * CAFE_DP_W) * ldb + bp;
-    for (int e = t >> 2; e < CAFE_DP_W; e += 32) stg[e] = dp[(size_t)e * ldb];
+    wb_stage<CAFE_DP_W>(stg, dp, ldb, t >> 2);
   }
   __syncthreads();
   const int j = blockIdx.x * CAFE_WB_PKS + w;
@@ -397,7 +506,7 @@ __global__ void __launch_bounds__(128) k_wb_lq(const SolverDev* __restrict__ Sp,
     double* stg = smp + WbSm::oStg;
     const int a = S.c.cur_slot[bp];
     const double* tm = ph.tm + ((size_t)(a * h + k) * CAFE_TM_W) * ldb + bp;
-    for (int e = t >> 2; e < CAFE_TM_W; e += 32) stg[e] = tm[(size_t)e * ldb];
+    wb_stage<CAFE_TM_W>(stg, tm, ldb, t >> 2);
     for (int e = t >> 2; e < 36; e += 32) smp[WbSm::oX + e] = ph.X[gix(k, 36, e, ldb, bp)];
     for (int e = t >> 2; e < 12; e += 32) { smp[WbSm::oU + e] = ph.U[gix(k, 12, e, ldb, bp)]; smp[WbSm::oGrf + e] = ph.Y[gix(k, 12, e, ldb, bp)]; }
     for (int e = t >> 2; e < CAFE_REF_W; e += 32)
@@ -411,82 +520,16 @@ __global__ void __launch_bounds__(128) k_wb_lq(const SolverDev* __restrict__ Sp,
     for (int e = lane; e < nr * 18; e += 32) { const int c = e % nr, col = e / nr; Aa[c + 12 * (18 + col)] += bg2 * J[rw.row(c) + WbSm::ldJ * col]; }
   }
   wb_factor(sm, rw, 0.0, false, lane);   // damping 0 for the sensitivities (computeKKTContactDynamicMatrixInverse, WBM.cpp:467)
-  const double* L = sm + WbSm::oL; const double* dinv = sm + WbSm::oDinv; const double* Y = sm + WbSm::oY;
-  const double* Ls = sm + WbSm::oS; const double* sdinv = sm + WbSm::oSdinv;
+  __syncwarp();
   const double dt = ph.dt;
   double* ABt = ph.ABpm + ((size_t)b * h + k) * CAFE_WB_AB_TILE;
   double* CDt = ph.CDpm + ((size_t)b * h + k) * CAFE_WB_CD_TILE;
-  // ---- column z of [q v tau]: r <- L^-1 R_z; w = Ls^-T Ls^-1 (Y^T r - a_z); r <- L^-T (Y w - r)
-#pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {
-    const int col = pass * 32 + lane;
-    if (col >= 48) break;
-    double r[18], wv[12];
-    if (col < 36) {
-#pragma unroll
-      for (int i = 0; i < 18; ++i) r[i] = R[i + 18 * col];
-    } else {
-#pragma unroll
-      for (int i = 0; i < 18; ++i) r[i] = (i == 6 + (col - 36)) ? -1.0 : 0.0;
-    }
-#pragma unroll
-    for (int i = 0; i < 18; ++i) {
-      double s = r[i];
-#pragma unroll
-      for (int kk = 0; kk < i; ++kk) s -= L[i + WbSm::ldL * kk] * r[kk];
-      r[i] = s * dinv[i];
-    }
-#pragma unroll
-    for (int c = 0; c < 12; ++c) {
-      if (c < nr) {
-        double d = 0;
-#pragma unroll
-        for (int i = 0; i < 18; ++i) d += Y[i + WbSm::ldY * c] * r[i];
-        wv[c] = d - ((col < 36) ? Aa[c + 12 * col] : 0.0);
-      } else wv[c] = 0.0;
-    }
-#pragma unroll
-    for (int i = 0; i < 12; ++i) {
-      if (i < nr) {
-        double s = wv[i];
-#pragma unroll
-        for (int kk = 0; kk < i; ++kk) s -= Ls[i + WbSm::ldS * kk] * wv[kk];
-        wv[i] = s * sdinv[i];
-      }
-    }
-#pragma unroll
-    for (int i = 11; i >= 0; --i) {
-      if (i < nr) {
-        wv[i] *= sdinv[i];
-#pragma unroll
-        for (int kk = 0; kk < i; ++kk) wv[kk] -= Ls[i + WbSm::ldS * kk] * wv[i];
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 18; ++i) {
-      double d = -r[i];
-#pragma unroll
-      for (int c = 0; c < 12; ++c) if (c < nr) d += Y[i + WbSm::ldY * c] * wv[c];
-      r[i] = d;
-    }
-#pragma unroll
-    for (int i = 17; i >= 0; --i) {
-      r[i] *= dinv[i];
-#pragma unroll
-      for (int kk = 0; kk < i; ++kk) r[kk] -= L[i + WbSm::ldL * kk] * r[i];
-    }
-    if (col < 36) {
-      // back into this lane's (dead) columns of R / a; they leave the SM as contiguous runs below
-#pragma unroll
-      for (int i = 0; i < 18; ++i) R[i + 18 * col] = ((col == 18 + i) ? 1.0 : 0.0) + r[i] * dt;
-#pragma unroll
-      for (int c = 0; c < 12; ++c) if (c < nr) Aa[c + 12 * col] = wv[c];
-    } else {
-#pragma unroll
-      for (int i = 0; i < 18; ++i) ABt[i + 20 * col] = r[i] * dt;
-#pragma unroll
-      for (int c = 0; c < 12; ++c) if (c < nr) CDt[rw.row(c) + 12 * col] = wv[c];
-    }
+  switch (nr) {   // CTA-uniform (a phase has one contact set)
+    case 0: wb_colsolve<0>(sm, ABt, CDt, rw, dt, lane); break;
+    case 3: wb_colsolve<3>(sm, ABt, CDt, rw, dt, lane); break;
+    case 6: wb_colsolve<6>(sm, ABt, CDt, rw, dt, lane); break;
+    case 9: wb_colsolve<9>(sm, ABt, CDt, rw, dt, lane); break;
+    default: wb_colsolve<12>(sm, ABt, CDt, rw, dt, lane); break;
   }
   __syncwarp();
   for (int e = lane; e < 18 * 36; e += 32) { const int i = e % 18, c = e / 18; ABt[i + 20 * c] = R[e]; }
