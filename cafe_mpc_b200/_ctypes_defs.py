@@ -5,7 +5,7 @@ CAFE_MAX_PHASES = 16
 CAFE_MAX_N, CAFE_MAX_M, CAFE_MAX_P = 36, 24, 12
 CAFE_REF_W = 120
 CAFE_TRACE_W = 12
-CAFE_NKERNELS = 10
+CAFE_NKERNELS = 11
 MODEL_HKD, MODEL_WB, MODEL_SRB = 0, 1, 2
 MODEL_DIMS = {MODEL_HKD: (24, 24, 0), MODEL_WB: (36, 12, 12), MODEL_SRB: (12, 12, 0)}
 

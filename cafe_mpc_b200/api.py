@@ -275,7 +275,7 @@ class MultiPhaseDDP:
         n = (C.c_long * CAFE_NKERNELS)()
         ticks = C.c_int()
         check(lib.cafe_gpu_get_timing(self._h, C.byref(ms), C.byref(n), C.byref(ticks)))
-        names = ["roll", "select", "accept", "lq", "bwd", "misc", "wb_terms", "wb_fwd", "wb_derivs", "wb_lq"]
+        names = ["roll", "select", "accept", "lq", "bwd", "misc", "wb_terms", "wb_fwd", "wb_derivs", "wb_sens", "wb_cost"]
         return {"ms": dict(zip(names, list(ms))), "launches": dict(zip(names, list(n))), "ticks": ticks.value}
 
 

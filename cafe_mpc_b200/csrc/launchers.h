@@ -16,7 +16,8 @@ void launch_select(const SolverDev* dS, int B, cudaStream_t st, int mode);
 void launch_wb_terms(const SolverDev* dS, int n_wbk, cudaStream_t st, int a0, int a1, const int* list, int n_list);
 void launch_wb_fwd(const SolverDev* dS, int n_wbk, cudaStream_t st, int a0, int a1, const int* list, int n_list);
 void launch_wb_derivs(const SolverDev* dS, int n_wbk, cudaStream_t st, const int* list, int n_list);
-void launch_wb_lq(const SolverDev* dS, int n_wbk, cudaStream_t st, const int* list, int n_list);
+void launch_wb_sens(const SolverDev* dS, int n_wbk, cudaStream_t st, const int* list, int n_list);
+void launch_wb_cost(const SolverDev* dS, int n_wbk, cudaStream_t st, const int* list, int n_list);
 size_t knot_kernels_local_bytes();
 int wb_coop_configure();   // opt-in shared-memory sizes of the cooperative kernels (0 = ok)
 }  // namespace cafe_dev

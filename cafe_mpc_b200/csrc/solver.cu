@@ -545,7 +545,8 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
     run(CAFE_K_LQ, [&] { cafe_dev::launch_lq(H->dS, S.n_knots, sq, list, n_list); });
     if (n_wbk > 0) {
       run(CAFE_K_WB_DERIVS, [&] { cafe_dev::launch_wb_derivs(H->dS, n_wbk, sq, list, n_list); });
-      run(CAFE_K_WB_LQ, [&] { cafe_dev::launch_wb_lq(H->dS, n_wbk, sq, list, n_list); });
+      run(CAFE_K_WB_SENS, [&] { cafe_dev::launch_wb_sens(H->dS, n_wbk, sq, list, n_list); });
+      run(CAFE_K_WB_COST, [&] { cafe_dev::launch_wb_cost(H->dS, n_wbk, sq, list, n_list); });
     }
   };
   // ---- initial rollout (eps = 0) and bookkeeping

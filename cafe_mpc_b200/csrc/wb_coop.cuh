@@ -6,10 +6,11 @@
 //
 //   k_wb_fwd  (rollout)        KKTContactDynamics: chol(M), Y = L^-1 Jc^T, chol(Y^T Y + 1e-12 I), lambda, qdd; x+, GRF, running cost,
 //                              barrier minima, defects                          <= WBM.cpp:17-57, :368-424; SinglePhase.cpp:200-232
-//   k_wb_lq   (linearisation)  KKT sensitivities  dlambda/dz = S^-1 (Jc M^-1 R - a), dqdd/dz = -M^-1 (R - Jc^T dlambda/dz) column by
-//                              column -> A, B, C, D tiles; cost / barrier partials lx, lu, ly, lxx (structural pattern), luu, lyy
-//                                                                               <= WBM.cpp:60-139, :459-505; MHPCCost.cpp:4-291;
-//                                                                                  MHPCConstraint.cpp:9-288; SinglePhase.cpp:265-320, :405-418
+//   k_wb_sens (linearisation)  KKT sensitivities  dlambda/dz = S^-1 (Jc M^-1 R - a), dqdd/dz = -M^-1 (R - Jc^T dlambda/dz) column by
+//                              column -> A, B, C, D tiles                      <= WBM.cpp:60-139, :459-505
+//   k_wb_cost (linearisation)  cost / barrier partials lx, lu, ly, lxx (structural pattern), luu, lyy, running cost
+//                                                                               <= MHPCCost.cpp:4-291; MHPCConstraint.cpp:9-288;
+//                                                                                  SinglePhase.cpp:236-320, :405-418
 // Arithmetic order: sums that the thread-per-knot code accumulated sequentially (base-block shares of M / nle / dtau, Cholesky
 // updates, forward substitutions, cost terms) are accumulated in the same order here; the back substitutions run as column
 // updates (descending), which differs from the row form in rounding only.
@@ -35,7 +36,8 @@ static __device__ const unsigned char c_dp_col[CAFE_WBL_DP_W] = CAFE_WBL_DP_COL;
 // global coordinate of local coordinate l (0..5 base, 6..8 leg) of leg f
 __device__ __forceinline__ int wbl_g(int f, int l) { return l < 6 ? l : 3 * f + l; }
 
-// ---- per-warp shared-memory plan (doubles)
+// ---- per-warp shared-memory plan (doubles). Three kernels share the first block; occupancy is what bounds these latency-bound kernels,
+// so every kernel keeps only what it needs: k_wb_fwd 8.8 KB, k_wb_sens 17.6 KB, k_wb_cost 11 KB per (problem, knot).
 struct WbSm {
   static constexpr int ldL = 19, ldJ = 12, ldY = 19, ldS = 13;
   static constexpr int oL = 0;                    // M (lower) -> chol(M), 18 x 18, ld 19
@@ -48,23 +50,37 @@ struct WbSm {
   static constexpr int oX = oVf + 12;             // x 36 | u 12 | grf 12
   static constexpr int oU = oX + 36;
   static constexpr int oGrf = oU + 12;
-  static constexpr int oRec = oGrf + 12;          // reference record of the knot (CAFE_REF_W)
-  static constexpr int oScr = oRec + CAFE_REF_W;  // scratch of the cost routine (160)
-  static constexpr int oStg = oScr + 160;         // staging of the packs; after the assembly: Y | S | 1/Ls(i,i) | mb
+  static constexpr int oStg = oGrf + 12;          // staging of the packs; after the assembly: Y | S | 1/Ls(i,i) | mb
   static constexpr int oY = oStg;                 // Y = L^-1 Jc^T, 18 x nr, ld 19
   static constexpr int oS = oY + 12 * ldY;        // S -> chol(S), nr x nr, ld 13
   static constexpr int oSdinv = oS + 12 * ldS;
   static constexpr int oMb = oSdinv + 12;         // L^-1 (tau - nle)
-  static constexpr int szAfter = oMb + 18 - oStg;
-  static constexpr int stgFwd = CAFE_TM_W + 48 > szAfter ? CAFE_TM_W + 48 : szAfter;   // rollout: TM | x | u
-  static constexpr int totalFwd = (oStg + stgFwd + 1) & ~1;
-  static constexpr int stgLq = CAFE_DP_W > stgFwd ? CAFE_DP_W : stgFwd;                 // linearisation: DP, then TM | x | u
-  static constexpr int oR = (oStg + stgLq + 1) & ~1;   // R 18 x 36 (ld 18) -> results
+  static constexpr int szStg = oMb + 18 - oStg;   // 414 = trunk + two legs of the derivative pack
+  static_assert(szStg >= CAFE_TM_W && szStg >= CAFE_DP_TRUNK_W + 2 * CAFE_DP_LEG_W, "staging area");
+  // rollout: the cost scratch (160) reuses the Jacobian tile, dead once Y is formed
+  static constexpr int oScrFwd = oJ;
+  static constexpr int totalFwd = (oStg + szStg + 1) & ~1;
+  // sensitivities
+  static constexpr int oR = totalFwd;                  // R 18 x 36 (ld 18) -> results
   static constexpr int oA = oR + 648;                  // a nr x 36 (ld 12) -> results
-  static constexpr int oDvq = oA + 432;                // dv_foot/dq, 12 x 18 (ld 12)
-  static constexpr int oLx = oDvq + 216;               // lx 36 | dposw 12 | dvelw 12 | dg 36 | misc
-  static constexpr int totalLq = (oLx + 128 + 1) & ~1;
+  static constexpr int oJt = oA + 432;                 // shared 3 x 3 block of d(J^T F)/dq
+  static constexpr int totalSens = (oJt + 10 + 1) & ~1;
+  // cost partials
+  static constexpr int oDvq = totalFwd;                // dv_foot/dq, compact: foot f at 18 f, element r + 3 (local column - 3)
+  static constexpr int oScr = oDvq + 72;               // scratch of the cost routine (160)
+  static constexpr int oLx = oScr + 160;               // dposw 12 | dvelw 12 | dg 36
+  static constexpr int totalCost = (oLx + 64 + 1) & ~1;
 };
+
+// the knot's reference record as a problem sees it: the deck's shared record (stride 1) or the problem's own (stride ldb)
+struct RecRef {
+  const double* p; size_t st;
+  __device__ __forceinline__ double operator[](int i) const { return p[(size_t)i * st]; }
+};
+__device__ __forceinline__ RecRef wb_rec(const PhaseDev& ph, int k, int ldb, int b) {
+  if (ph.ref_pp) return RecRef{ph.ref_pp + (size_t)k * CAFE_REF_W * (size_t)ldb + b, (size_t)ldb};
+  return RecRef{ph.ref + (size_t)k * CAFE_REF_W, 1};
+}
 
 // stage W elements of a batch-major array (element e at src[e * ldb]) into shared memory, 32 element-threads per problem: every
 // load is issued before the first store, so that one memory round trip covers the whole pack
@@ -114,12 +130,13 @@ struct WbRows {   // active contact rows of a contact set: row(c) = 3 foot(c / 3
 
 // staged terms pack (stg[0..CAFE_TM_W)) -> M (lower, zero elsewhere), nle, J, gam, pf, vf. Shares of the base block are added in
 // the order trunk, leg 0..3 (MassDst / BiasDst of wb_pieces.h onto a zero-initialised destination).
+template <bool WITH_M = true>
 __device__ __forceinline__ void wb_assemble_terms(double* sm, const double* stg, int lane) {
   double* M = sm + WbSm::oL; double* J = sm + WbSm::oJ; double* nle = sm + WbSm::oNle;
-  for (int e = lane; e < 18 * WbSm::ldL; e += 32) M[e] = 0.0;
+  if (WITH_M) for (int e = lane; e < 18 * WbSm::ldL; e += 32) M[e] = 0.0;
   for (int e = lane; e < 216; e += 32) J[e] = 0.0;
   __syncwarp();
-  for (int e = lane; e < 36; e += 32) { const int r = e % 6, c = e / 6; if (r >= c) M[r + WbSm::ldL * c] = stg[6 + e]; }
+  if (WITH_M) for (int e = lane; e < 36; e += 32) { const int r = e % 6, c = e / 6; if (r >= c) M[r + WbSm::ldL * c] = stg[6 + e]; }
   if (lane < 6) nle[lane] = stg[lane];
   __syncwarp();
   for (int f = 0; f < 4; ++f) {
@@ -128,7 +145,7 @@ __device__ __forceinline__ void wb_assemble_terms(double* sm, const double* stg,
       const int kind = c_tm_kind[e], r = c_tm_row[e], c = c_tm_col[e];
       const double v = lg[e];
       if (kind == 0) { const int i = wbl_g(f, r); if (r < 6) nle[i] += v; else nle[i] = v; }
-      else if (kind == 1) { const int idx = wbl_g(f, r) + WbSm::ldL * wbl_g(f, c); if (r < 6 && c < 6) M[idx] += v; else M[idx] = v; }
+      else if (kind == 1) { if (WITH_M) { const int idx = wbl_g(f, r) + WbSm::ldL * wbl_g(f, c); if (r < 6 && c < 6) M[idx] += v; else M[idx] = v; } }
       else if (kind == 2) J[(3 * f + r) + WbSm::ldJ * wbl_g(f, c)] = v;
       else if (kind == 3) sm[WbSm::oGam + 3 * f + r] = v;
       else if (kind == 4) sm[WbSm::oPf + 3 * f + r] = v;
@@ -181,9 +198,9 @@ __device__ __forceinline__ void wb_factor(double* sm, const WbRows& rw, double d
 
 // running cost of a whole-body knot (QuadraticTrackingCost + foot costs + dt * ReB terms) and the minimum of the path-constraint
 // values, from x, u, y (= GRF), pf, vf, rec in shared memory; same terms and summation order as WBModel::running_cost_k
-__device__ __forceinline__ double wb_cost_coop(const PhaseDev& ph, const double* sm, double* scr, bool reb, int lane, double& ming) {
+__device__ __forceinline__ double wb_cost_coop(const PhaseDev& ph, const double* sm, const RecRef rec, double* scr, bool reb, int lane, double& ming) {
   const double* x = sm + WbSm::oX; const double* u = sm + WbSm::oU; const double* y = sm + WbSm::oGrf;
-  const double* pf = sm + WbSm::oPf; const double* vf = sm + WbSm::oVf; const double* rec = sm + WbSm::oRec;
+  const double* pf = sm + WbSm::oPf; const double* vf = sm + WbSm::oVf;
   const double dt = ph.dt;
   for (int i = lane; i < 36; i += 32) { const double dx = x[i] - rec[CAFE_REF_XR + i]; scr[i] = dx * ph.q[i] * dx; }
   if (lane < 12) { const double du = u[lane] - rec[CAFE_REF_UR + lane]; scr[36 + lane] = du * ph.r[lane] * du; }
@@ -270,8 +287,6 @@ __global__ void __launch_bounds__(128, 4) k_wb_fwd(const SolverDev* __restrict__
       wb_stage<CAFE_TM_W>(stg, tm, ldb, t >> 2);
       for (int e = t >> 2; e < 36; e += 32) sm[WbSm::oX + e] = ph.Xt[aX + gix(k, 36, e, ldb, b)];
       for (int e = t >> 2; e < 12; e += 32) sm[WbSm::oU + e] = ph.Ut[aU + gix(k, 12, e, ldb, b)];
-      for (int e = t >> 2; e < CAFE_REF_W; e += 32)
-        sm[WbSm::oRec + e] = ph.ref_pp ? ph.ref_pp[((size_t)k * CAFE_REF_W + e) * (size_t)ldb + b] : ph.ref[(size_t)k * CAFE_REF_W + e];
     }
   }
   __syncthreads();
@@ -318,7 +333,7 @@ __global__ void __launch_bounds__(128, 4) k_wb_fwd(const SolverDev* __restrict__
   if (lane < nr) sm[WbSm::oGrf + rw.row(lane)] = lam;
   __syncwarp();
   if (lane < 12) ph.Yt[aY + gix(k, 12, lane, ldb, b)] = sm[WbSm::oGrf + lane];
-  double* scr = sm + WbSm::oScr;
+  double* scr = sm + WbSm::oScrFwd;   // the Jacobian tile is dead (Y is formed)
   const double* x = sm + WbSm::oX;
   if (lane < 18) {
     ph.qdd_t[((size_t)(a * h + k) * 18 + lane) * ldb + b] = mb;
@@ -339,7 +354,7 @@ __global__ void __launch_bounds__(128, 4) k_wb_fwd(const SolverDev* __restrict__
   if (lane == 1) { double nrm = 0; for (int i = 0; i < 36; ++i) nrm += scr[i] * scr[i]; if (sqrt(nrm) > 1e6) atomicOr(&ph.fail_t[(size_t)a * ldb + b], 1); }
   __syncwarp();
   double ming;
-  const double l = wb_cost_coop(ph, sm, scr, S.opt.ReB_active != 0, lane, ming);
+  const double l = wb_cost_coop(ph, sm, wb_rec(ph, k, ldb, b), scr, S.opt.ReB_active != 0, lane, ming);
   if (lane == 0) { ph.cost_t[aS + (size_t)k * ldb + b] = l; ph.ming_t[aS + (size_t)k * ldb + b] = ming; }
 }
 
@@ -427,9 +442,9 @@ __device__ __forceinline__ void wb_colsolve(double* sm, double* __restrict__ ABt
   }
 }
 
-// --------------------------------------------------------------------------------------------------- K-LQ, whole-body running knots
-// grid (ceil(n_list / 4), n_wbk), 128 threads. lxx_list: structural pattern of lxx is implied by the contact flags of the record.
-__global__ void __launch_bounds__(128) k_wb_lq(const SolverDev* __restrict__ Sp, const int* __restrict__ list, int n_list) {
+// --------------------------------------------------------------------------------------------------- K-LQ, whole-body running knots (1)
+// KKT sensitivities -> problem-major [A B], [C D] tiles. grid (ceil(n_list / 4), n_wbk), 128 threads.
+__global__ void __launch_bounds__(128, 3) k_wb_sens(const SolverDev* __restrict__ Sp, const int* __restrict__ list, int n_list) {
   const SolverDev& S = *Sp;
   extern __shared__ __align__(16) double smem[];
   const int t = threadIdx.x, w = t >> 5, lane = t & 31;
@@ -438,79 +453,74 @@ __global__ void __launch_bounds__(128) k_wb_lq(const SolverDev* __restrict__ Sp,
   const int ldb = S.ldb, h = ph.h;
   const int p4 = t & 3, jp = blockIdx.x * CAFE_WB_PKS + p4;
   const int bp = jp < n_list ? list[jp] : -1;
-  // ---- stage the derivative pieces of the four problems
-  if (bp >= 0) {
-    double* stg = smem + p4 * WbSm::totalLq + WbSm::oStg;
-    const double* dp = ph.dp + ((size_t)k * CAFE_DP_W) * ldb + bp;
-    wb_stage<CAFE_DP_W>(stg, dp, ldb, t >> 2);
-  }
-  __syncthreads();
   const int j = blockIdx.x * CAFE_WB_PKS + w;
   const bool live = j < n_list;
   const int b = live ? list[j] : 0;
-  double* sm = smem + w * WbSm::totalLq;
+  double* sm = smem + w * WbSm::totalSens;
   WbRows rw; rw.set(ph.contact);
   const int nr = rw.nr;
-  double* R = sm + WbSm::oR; double* Aa = sm + WbSm::oA; double* dvq = sm + WbSm::oDvq;
+  double* R = sm + WbSm::oR; double* Aa = sm + WbSm::oA; double* jt = sm + WbSm::oJt;
   const double bg2 = 2.0 * ph.BG_alpha;
-  if (live) {
-    // ---- R = [dtau/dq - d(J^T F)/dq | dtau/dv] (18 x 36), a = [da/dq + 2 BG dv/dq | da/dv (+ 2 BG J below)] on the active rows
-    const double* stg = sm + WbSm::oStg;
-    for (int e = lane; e < 648; e += 32) R[e] = 0.0;
-    for (int e = lane; e < 432; e += 32) Aa[e] = 0.0;
-    for (int e = lane; e < 216; e += 32) dvq[e] = 0.0;
-    __syncwarp();
-    if (lane < 18) { const int dv = lane >= 9, idx = lane % 9; R[(3 + idx % 3) + 18 * (3 + idx / 3 + (dv ? 18 : 0))] = stg[lane]; }
-    __syncwarp();
-    for (int f = 0; f < 4; ++f) {   // dtau shares in the order trunk, leg 0..3 (RneaDst of wb_pieces.h); foot rows of a, dv/dq
-      const double* lg = stg + CAFE_DP_TRUNK_W + f * CAFE_WBL_DP_W;
-      for (int e = lane; e < CAFE_WBL_DP_JTF; e += 32) {
-        const int kind = c_dp_kind[e], r = c_dp_row[e], c = c_dp_col[e];
-        const double v = lg[e];
-        if (kind <= 1) {
-          const int idx = wbl_g(f, r) + 18 * (wbl_g(f, c) + (kind == 1 ? 18 : 0));
-          const bool shared = r < 6 && c >= 3 && c <= 5, first = (f == 0 && r < 3);
-          if (shared && !first) R[idx] += v; else R[idx] = v;
-        } else if (kind == 2) {
-          dvq[(3 * f + r) + 12 * wbl_g(f, c)] = v;
-        } else {
-          const int ar = rw.arow(3 * f + r);
-          if (ar >= 0) Aa[ar + 12 * (wbl_g(f, c) + (kind == 4 ? 18 : 0))] = v;
+  const double* dpp = ph.dp + ((size_t)k * CAFE_DP_W) * ldb;
+  // ---- R = [dtau/dq - d(J^T F)/dq | dtau/dv] (18 x 36), a = [da/dq + 2 BG dv/dq | da/dv (+ 2 BG J below)] on the active rows.
+  //      The derivative pack is staged in two halves (trunk + legs 0, 1; legs 2, 3): shared memory is what bounds the occupancy.
+  for (int half = 0; half < 2; ++half) {
+    if (bp >= 0) {
+      double* stg = smem + p4 * WbSm::totalSens + WbSm::oStg;
+      if (half == 0) wb_stage<CAFE_DP_TRUNK_W + 2 * CAFE_DP_LEG_W>(stg, dpp + bp, ldb, t >> 2);
+      else wb_stage<2 * CAFE_DP_LEG_W>(stg + CAFE_DP_TRUNK_W, dpp + (size_t)(CAFE_DP_TRUNK_W + 2 * CAFE_DP_LEG_W) * ldb + bp, ldb, t >> 2);
+    }
+    __syncthreads();
+    if (live) {
+      const double* stg = sm + WbSm::oStg;
+      if (half == 0) {
+        for (int e = lane; e < 648; e += 32) R[e] = 0.0;
+        for (int e = lane; e < 432; e += 32) Aa[e] = 0.0;
+        if (lane < 9) jt[lane] = 0.0;
+        __syncwarp();
+        if (lane < 18) { const int dv = lane >= 9, idx = lane % 9; R[(3 + idx % 3) + 18 * (3 + idx / 3 + (dv ? 18 : 0))] = stg[lane]; }
+        __syncwarp();
+      }
+      for (int fl = 0; fl < 2; ++fl) {   // dtau shares in the order trunk, leg 0..3 (RneaDst of wb_pieces.h); foot rows of a
+        const int f = 2 * half + fl;
+        const double* lg = stg + CAFE_DP_TRUNK_W + fl * CAFE_WBL_DP_W;
+        for (int e = lane; e < CAFE_WBL_DP_JTF; e += 32) {
+          const int kind = c_dp_kind[e], r = c_dp_row[e], c = c_dp_col[e];
+          const double v = lg[e];
+          if (kind <= 1) {
+            const int idx = wbl_g(f, r) + 18 * (wbl_g(f, c) + (kind == 1 ? 18 : 0));
+            const bool shared = r < 6 && c >= 3 && c <= 5, first = (f == 0 && r < 3);
+            if (shared && !first) R[idx] += v; else R[idx] = v;
+          } else if (kind >= 3) {
+            const int ar = rw.arow(3 * f + r);
+            if (ar >= 0) Aa[ar + 12 * (wbl_g(f, c) + (kind == 4 ? 18 : 0))] = v;
+          }
         }
+        __syncwarp();
+        for (int e = CAFE_WBL_DP_DVQ + lane; e < CAFE_WBL_DP_DAQ; e += 32) {   // + 2 BG dv_foot/dq
+          const int r = c_dp_row[e], c = c_dp_col[e];
+          const int ar = rw.arow(3 * f + r);
+          if (ar >= 0) Aa[ar + 12 * wbl_g(f, c)] += bg2 * lg[e];
+        }
+        // d(J^T F)/dq: private entries leave R at once, the shared block (rows, columns 3..5) is summed foot 0..3 first (JtfDst)
+        for (int e = CAFE_WBL_DP_JTF + lane; e < CAFE_WBL_DP_W; e += 32) {
+          const int r = c_dp_row[e], c = c_dp_col[e];
+          const double v = lg[e];
+          const bool shared = r >= 3 && r <= 5 && c >= 3 && c <= 5;
+          if (shared) { if (f == 0) jt[(r - 3) + 3 * (c - 3)] = v; else jt[(r - 3) + 3 * (c - 3)] += v; }
+          else R[wbl_g(f, r) + 18 * wbl_g(f, c)] -= v;
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
-    // d(J^T F)/dq: private entries leave R at once, the shared block rows, columns 3..5 is summed foot 0..3 first (JtfDst)
-    double* jt = sm + WbSm::oLx;   // 9 words of scratch
-    if (lane < 9) jt[lane] = 0.0;
-    __syncwarp();
-    for (int f = 0; f < 4; ++f) {
-      const double* lg = stg + CAFE_DP_TRUNK_W + f * CAFE_WBL_DP_W;
-      for (int e = CAFE_WBL_DP_JTF + lane; e < CAFE_WBL_DP_W; e += 32) {
-        const int r = c_dp_row[e], c = c_dp_col[e];
-        const double v = lg[e];
-        const bool shared = r >= 3 && r <= 5 && c >= 3 && c <= 5;
-        if (shared) { if (f == 0) jt[(r - 3) + 3 * (c - 3)] = v; else jt[(r - 3) + 3 * (c - 3)] += v; }
-        else R[wbl_g(f, r) + 18 * wbl_g(f, c)] -= v;
-      }
-      __syncwarp();
-    }
-    if (lane < 9) R[(3 + lane % 3) + 18 * (3 + lane / 3)] -= jt[lane];
-    for (int e = lane; e < nr * 18; e += 32) { const int c = e % nr, col = e / nr; Aa[c + 12 * col] += bg2 * dvq[rw.row(c) + 12 * col]; }
-    __syncwarp();
+    __syncthreads();
   }
-  __syncthreads();
-  // ---- stage the rigid-body terms of the trial that produced the current iterate, x, u, y and the reference record
+  if (live && lane < 9) R[(3 + lane % 3) + 18 * (3 + lane / 3)] -= jt[lane];
+  // ---- rigid-body terms of the trial that produced the current iterate
   if (bp >= 0) {
-    double* smp = smem + p4 * WbSm::totalLq;
-    double* stg = smp + WbSm::oStg;
+    double* stg = smem + p4 * WbSm::totalSens + WbSm::oStg;
     const int a = S.c.cur_slot[bp];
-    const double* tm = ph.tm + ((size_t)(a * h + k) * CAFE_TM_W) * ldb + bp;
-    wb_stage<CAFE_TM_W>(stg, tm, ldb, t >> 2);
-    for (int e = t >> 2; e < 36; e += 32) smp[WbSm::oX + e] = ph.X[gix(k, 36, e, ldb, bp)];
-    for (int e = t >> 2; e < 12; e += 32) { smp[WbSm::oU + e] = ph.U[gix(k, 12, e, ldb, bp)]; smp[WbSm::oGrf + e] = ph.Y[gix(k, 12, e, ldb, bp)]; }
-    for (int e = t >> 2; e < CAFE_REF_W; e += 32)
-      smp[WbSm::oRec + e] = ph.ref_pp ? ph.ref_pp[((size_t)k * CAFE_REF_W + e) * (size_t)ldb + bp] : ph.ref[(size_t)k * CAFE_REF_W + e];
+    wb_stage<CAFE_TM_W>(stg, ph.tm + ((size_t)(a * h + k) * CAFE_TM_W) * ldb + bp, ldb, t >> 2);
   }
   __syncthreads();
   if (!live) return;
@@ -534,11 +544,49 @@ __global__ void __launch_bounds__(128) k_wb_lq(const SolverDev* __restrict__ Sp,
   __syncwarp();
   for (int e = lane; e < 18 * 36; e += 32) { const int i = e % 18, c = e / 18; ABt[i + 20 * c] = R[e]; }
   for (int e = lane; e < nr * 36; e += 32) { const int c = e % nr, cc = e / nr; CDt[rw.row(c) + 12 * cc] = Aa[c + 12 * cc]; }
+}
+
+// --------------------------------------------------------------------------------------------------- K-LQ, whole-body running knots (2)
+// cost and barrier partials lx, lu, ly, lxx (structural pattern), luu, lyy and the running cost. grid (ceil(n_list / 4), n_wbk), 128 threads.
+__global__ void __launch_bounds__(128, 4) k_wb_cost(const SolverDev* __restrict__ Sp, const int* __restrict__ list, int n_list) {
+  const SolverDev& S = *Sp;
+  extern __shared__ __align__(16) double smem[];
+  const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+  const int gk = S.wbk_gk[blockIdx.y], pi = S.knot_phase[gk], k = S.knot_k[gk];
+  const PhaseDev& ph = S.ph[pi];
+  const int ldb = S.ldb, h = ph.h;
+  {
+    const int p4 = t & 3, jp = blockIdx.x * CAFE_WB_PKS + p4;
+    const int bp = jp < n_list ? list[jp] : -1;
+    if (bp >= 0) {
+      double* smp = smem + p4 * WbSm::totalCost;
+      const int a = S.c.cur_slot[bp];
+      wb_stage<CAFE_TM_W>(smp + WbSm::oStg, ph.tm + ((size_t)(a * h + k) * CAFE_TM_W) * ldb + bp, ldb, t >> 2);
+      const double* dpp = ph.dp + ((size_t)k * CAFE_DP_W) * ldb + bp;
+      for (int e = t >> 2; e < 72; e += 32) smp[WbSm::oDvq + e] = dpp[(size_t)(CAFE_DP_TRUNK_W + (e / 18) * CAFE_WBL_DP_W + CAFE_WBL_DP_DVQ + e % 18) * ldb];
+      for (int e = t >> 2; e < 36; e += 32) smp[WbSm::oX + e] = ph.X[gix(k, 36, e, ldb, bp)];
+      for (int e = t >> 2; e < 12; e += 32) { smp[WbSm::oU + e] = ph.U[gix(k, 12, e, ldb, bp)]; smp[WbSm::oGrf + e] = ph.Y[gix(k, 12, e, ldb, bp)]; }
+    }
+  }
+  __syncthreads();
+  const int j = blockIdx.x * CAFE_WB_PKS + w;
+  if (j >= n_list) return;
+  const int b = list[j];
+  double* sm = smem + w * WbSm::totalCost;
+  wb_assemble_terms<false>(sm, sm + WbSm::oStg, lane);
+  const double dt = ph.dt;
+  const RecRef rec = wb_rec(ph, k, ldb, b);
+  const double* dvqc = sm + WbSm::oDvq;
+  // dv_foot(3f+a)/dq_i from the compact store (non-zero for the base-rotation columns 3..5 and the leg's own three columns)
+  auto dvq_at = [&](int f, int a, int i) -> double {
+    const int lc = (i >= 3 && i < 6) ? i - 3 : (i >= 6 + 3 * f && i < 9 + 3 * f) ? 3 + i - (6 + 3 * f) : -1;
+    return lc >= 0 ? dvqc[18 * f + a + 3 * lc] : 0.0;
+  };
   // ---- cost and barrier partials
-  const double* x = sm + WbSm::oX; const double* u = sm + WbSm::oU; const double* grf = sm + WbSm::oGrf; const double* rec = sm + WbSm::oRec;
+  const double* x = sm + WbSm::oX; const double* u = sm + WbSm::oU; const double* grf = sm + WbSm::oGrf;
   const double* J = sm + WbSm::oJ; const double* pf = sm + WbSm::oPf; const double* vf = sm + WbSm::oVf;
   const bool reb = S.opt.ReB_active != 0;
-  double* lxs = sm + WbSm::oLx; double* dposw = lxs + 36; double* dvelw = lxs + 48; double* dg = lxs + 60;
+  double* dposw = sm + WbSm::oLx; double* dvelw = dposw + 12; double* dg = dposw + 24;
   // lu, luu (diagonal): tracking + torque-limit barrier
   if (lane < 12) {
     const int i = lane;
@@ -596,7 +644,7 @@ __global__ void __launch_bounds__(128) k_wb_lq(const SolverDev* __restrict__ Sp,
       if (i >= 3 && i < 18) { double g = 0; for (int a = 0; a < 3; ++a) g += J[3 * f + a + WbSm::ldJ * i] * dposw[3 * f + a]; lx += g * dt; }
       if (!c) {
         double g = 0;
-        for (int a = 0; a < 3; ++a) g += ((i < 18) ? dvq[3 * f + a + 12 * i] : J[3 * f + a + WbSm::ldJ * (i - 18)]) * dvelw[3 * f + a];
+        for (int a = 0; a < 3; ++a) g += ((i < 18) ? dvq_at(f, a, i) : J[3 * f + a + WbSm::ldJ * (i - 18)]) * dvelw[3 * f + a];
         lx += g * dt;
       }
     }
@@ -628,7 +676,7 @@ __global__ void __launch_bounds__(128) k_wb_lq(const SolverDev* __restrict__ Sp,
   // lxx, structural pattern only (see WBModel::lq_knot): a foot Jacobian has the base-rotation columns 3..5 and its own three joint
   // columns, the swing-foot velocity Jacobian [dv/dq | J] additionally the six base columns and the leg columns of the velocity half.
   double* lxxg = ph.lxx + gix(k, 1296, 0, ldb, b);
-  auto jxv = [&](int f, int a, int i) -> double { return (i < 18) ? dvq[3 * f + a + 12 * i] : J[3 * f + a + WbSm::ldJ * (i - 18)]; };
+  auto jxv = [&](int f, int a, int i) -> double { return (i < 18) ? dvq_at(f, a, i) : J[3 * f + a + WbSm::ldJ * (i - 18)]; };
   // (a) the 9 x 9 block of the base columns {3,4,5,18..23}, shared by the feet: accumulated foot by foot
   for (int e = lane; e < 81; e += 32) {
     const int p = e % 9, q = e / 9;
@@ -664,7 +712,7 @@ __global__ void __launch_bounds__(128) k_wb_lq(const SolverDev* __restrict__ Sp,
   if (lane < 3) lxxg[(size_t)(37 * lane) * ldb] = dg[lane];
   // ---- running cost at the current iterate (compute_cost, SinglePhase.cpp:236-262)
   double ming;
-  const double l = wb_cost_coop(ph, sm, sm + WbSm::oScr, reb, lane, ming);
+  const double l = wb_cost_coop(ph, sm, rec, sm + WbSm::oScr, reb, lane, ming);
   if (lane == 0) ph.lk[(size_t)k * ldb + b] = l;
 }
 

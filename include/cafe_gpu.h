@@ -154,8 +154,9 @@ int cafe_gpu_get_hkd_lcm_commands_device(CafeHandle* h, int n_steps, float* out_
 #define CAFE_K_WB_TERMS 6  /* k_wb_terms: leg-parallel rigid-body terms of the whole-body trial knots */
 #define CAFE_K_WB_FWD 7    /* k_wb_fwd: cooperative KKT contact dynamics, x+, GRF, cost, defects */
 #define CAFE_K_WB_DERIVS 8 /* k_wb_derivs: leg-parallel RNEA derivatives and foot kinematic partials */
-#define CAFE_K_WB_LQ 9     /* k_wb_lq: cooperative KKT sensitivities (A, B, C, D) and cost / barrier partials */
-#define CAFE_NKERNELS 10
+#define CAFE_K_WB_SENS 9   /* k_wb_sens: cooperative KKT sensitivities (A, B, C, D tiles) */
+#define CAFE_K_WB_COST 10  /* k_wb_cost: cooperative cost / barrier partials and running cost */
+#define CAFE_NKERNELS 11
 int cafe_gpu_get_timing(CafeHandle* h, double ms[CAFE_NKERNELS], long launches[CAFE_NKERNELS], int* ticks);
 /* device time (CUDA events on the solver's stream) of the last cafe_gpu_solve_batch*, in ms */
 int cafe_gpu_get_solve_ms(CafeHandle* h, double* ms);
