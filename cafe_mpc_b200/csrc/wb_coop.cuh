@@ -269,7 +269,7 @@ __device__ __forceinline__ double wb_cost_coop(const PhaseDev& ph, const double*
 
 // ------------------------------------------------------------------------------------------------ K-ROLL, whole-body running knots
 // grid (ceil(n_list / 4), n_wbk, a1 - a0), 128 threads
-__global__ void __launch_bounds__(128, 4) k_wb_fwd(const SolverDev* __restrict__ Sp, int a0, const int* __restrict__ list, int n_list) {
+__global__ void __launch_bounds__(128, 6) k_wb_fwd(const SolverDev* __restrict__ Sp, int a0, const int* __restrict__ list, int n_list) {
   const SolverDev& S = *Sp;
   extern __shared__ __align__(16) double smem[];
   const int t = threadIdx.x, w = t >> 5, lane = t & 31;
@@ -548,7 +548,7 @@ __global__ void __launch_bounds__(128, 3) k_wb_sens(const SolverDev* __restrict_
 
 // --------------------------------------------------------------------------------------------------- K-LQ, whole-body running knots (2)
 // cost and barrier partials lx, lu, ly, lxx (structural pattern), luu, lyy and the running cost. grid (ceil(n_list / 4), n_wbk), 128 threads.
-__global__ void __launch_bounds__(128, 4) k_wb_cost(const SolverDev* __restrict__ Sp, const int* __restrict__ list, int n_list) {
+__global__ void __launch_bounds__(128, 5) k_wb_cost(const SolverDev* __restrict__ Sp, const int* __restrict__ list, int n_list) {
   const SolverDev& S = *Sp;
   extern __shared__ __align__(16) double smem[];
   const int t = threadIdx.x, w = t >> 5, lane = t & 31;
