@@ -4,10 +4,15 @@
   python bench.py --gpus N --steps K --warmup W          our CUDA path (one process per GPU under torchrun)
   python bench.py --impl reference ...                    the CPU restatement of the reference (oracle) on all host cores
 
-A "step" = one complete solve of a batch of perturbed-initial-state problems (every problem to its own
-termination). value = solves/s with x0 resident in HBM; e2e = same through the host-buffer C-ABI calls
-(H2D of x0, solve, D2H of the command records; for N>1 also the final NCCL gather to rank 0)."""
+A "step" = one complete solve of a batch of perturbed-initial-state problems (every problem to its own termination).
+value = solves/s with x0 resident in HBM; e2e = the same through the host-buffer C-ABI calls (H2D of x0, solve, pack of the command
+records, for N > 1 the NCCL gather to rank 0 through cafe_gpu_gather_commands, D2H of ALL records on rank 0).
+
+Scaling: --scaling strong (default) keeps the GLOBAL batch at --batch (the headline: 4096 MHPC trot problems cut over N GPUs);
+--scaling weak gives every GPU --batch problems. torch.distributed is plumbing only (rendezvous, barriers, max over ranks, handing the
+NCCL id around); the solve and the gather go through the C ABI."""
 import argparse
+import glob
 import json
 import os
 import statistics
@@ -24,26 +29,52 @@ METRIC = "batched HS-DDP solves/sec"
 UNIT = "solves/s"
 F_BWD = {0: 233280.0, 1: 373392.0, 2: 30096.0}  # dense flop per knot of one backward-sweep pass
 F_LIN = {0: 6960.0, 1: 8200.0, 2: 1800.0}        # linear rollout per knot
-# algorithmic bytes of one LQ approximation per knot: inputs X, U, Y, Defect + the reference's outputs
-# A, B, C, D, lx, lu, ly, lxx, luu, lyy (model ids 0 HKD (24,24,0), 1 WB (36,12,12), 2 SRB (12,12,0)), 8 bytes per double
-def _lq_doubles(n, m, p):
-    return (2 * n + m + p) + (n * n + n * m + p * n + p * m + n + m + p + n * n + m * m + p * p)
-B_LQ = {0: 8.0 * _lq_doubles(24, 24, 0), 1: 8.0 * _lq_doubles(36, 12, 12), 2: 8.0 * _lq_doubles(12, 12, 0)}
+# operation counts of the generated straight-line routines (tools/gen_wb.py, tools/gen_wb_leg.py print them; one op = one flop)
+OPS_TERMS = 197 + 4 * 1886
+OPS_DERIVS = 851 + 4 * (1834 + 2453 + 2014 + 2691 + 1909 + 1502 + 1781 + 866 + 850)
+TM_NNZ, DP_NNZ = 13 + 4 * 79, 18 + 4 * 198       # doubles a knot's rigid-body terms / derivative pieces occupy
+
+
+def _chol_flop(n):
+    return sum((n - j) * (2 * j + 1) for j in range(n))
+
+
+def wb_fwd_flop(nr):
+    """k_wb_fwd per (problem, knot, step size): chol(M), Y = L^-1 Jc^T (+ rhs), S = Y^T Y, chol(S), lambda, qdd; x+, defects, cost"""
+    return _chol_flop(18) + (nr + 1) * 324 + nr * (nr + 1) // 2 * 36 + _chol_flop(nr) + 36 * nr + 2 * nr * nr + 36 * nr + 324 + 800
+
+
+def wb_sens_flop(nr):
+    """k_wb_sens per (problem, knot): factorisation + 48 columns of L^-1, Y^T, Ls^-T Ls^-1, Y, L^-T + assembly of R, a"""
+    return _chol_flop(18) + nr * 324 + nr * (nr + 1) // 2 * 36 + _chol_flop(nr) + 48 * (2 * 324 + 4 * 18 * nr + 2 * nr * nr) + 2000
 
 
 def workload_name(args):
     if args.workload == "hkd":
-        return "HKD trot (3 phases h=11/25/24, n=m=24), %d perturbed problems per GPU" % args.batch
+        return "HKD trot (3 phases h=11/25/24, n=m=24)"
     if args.workload == "barrel":
-        return ("MHPC running barrel roll at the impact-bearing start offset k0=205 (WB flight h=22 -> 4-foot landing impact -> WB h=3; SRB h=10), "
-                "%d perturbed problems per GPU" % args.batch)
+        return "MHPC running barrel roll at the impact-bearing start offset k0=205 (WB flight h=22 -> 4-foot landing impact -> WB h=3; SRB h=10)"
     if args.workload == "barrel_to":
         return ("in-place barrel roll (BarrelRoll/BarrelRollTO.cpp): 6 WB phases / 125 knots, joint-speed barrier, two 4-foot landings, solve started from "
-                "the interpolated state trajectory, %d perturbed problems per GPU" % args.batch)
+                "the interpolated state trajectory")
     if args.workload == "loco":
-        return ("LocoProblem (Locomotion/Loco_TO.cpp): whole-body-only 1.0 s flypace plan, 9 WB phases / 100 knots, three flight -> stance "
-                "touchdowns, torque + GRF barriers, %d perturbed problems per GPU" % args.batch)
-    return "MHPC trot (WB h=11 + WB h=14, n=36 m=12 p=12; SRB h=10, n=m=12), %d perturbed problems per GPU" % args.batch
+        return "LocoProblem (Locomotion/Loco_TO.cpp): whole-body-only 1.0 s flypace plan, 9 WB phases / 100 knots, three flight -> stance touchdowns, torque + GRF barriers"
+    return "MHPC trot (WB h=11 + WB h=14, n=36 m=12 p=12; SRB h=10, n=m=12)"
+
+
+SETTINGS = {"hkd": "HKDMPC/settings (10x5 iteration caps, alpha 0.1)",
+            "mhpc": "MHPC/settings (10x20 iteration caps, alpha 0.5, BG_alpha 10, cost_weights_regular, constraint_params_regular)",
+            "barrel": "MHPC/settings (10x20 iteration caps, alpha 0.5, BG_alpha 10, cost_weights_barrel, constraint_params_barrel)",
+            "barrel_to": "BarrelRoll/setting (30x10 iteration caps, alpha 0.5, BG_alpha 10, br_cost_weights, br_constraint_params)",
+            "loco": "Locomotion/settings (30x10 iteration caps, alpha 0.5, BG_alpha 10, loco_cost_weights, loco_constraint_params)"}
+
+
+def make_config(args, world):
+    """the same dict in both arms (ours and --impl reference): the workload the metric is quoted on"""
+    Bg = args.batch if args.scaling == "strong" else args.batch * world
+    return {"workload": "%s, %d perturbed problems (SplitMix64 table, SURVEY.md section 8d)" % (workload_name(args), Bg),
+            "global_batch": Bg, "scaling": args.scaling, "settings": SETTINGS[args.workload],
+            "l2": "working set per solve (GBs of per-problem arrays) exceeds the 126 MB L2; no flush needed"}
 
 
 def make_problem(workload):
@@ -126,23 +157,27 @@ def cpu_sample(x0, cores, per_core, workload):
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     cores = len(os.sched_getaffinity(0))
     prob, opt, gen_x0, n0 = make_problem(args.workload)
     per_core = args.cpu_per_core
-    x0 = gen_x0(min(args.batch, cores * per_core))
+    cfg = make_config(args, world)
+    x0 = gen_x0(min(cfg["global_batch"], cores * per_core))
     vals = []
     for i in range(args.warmup + args.steps):
         v, n = cpu_sample(x0, cores, per_core, args.workload)
         if i >= args.warmup:
             vals.append(v)
     v = sum(vals) / len(vals)
-    sample = "%d problems of the workload (first of the SplitMix64 table), %d per core, one single-threaded oracle instance per core" % (len(x0), per_core)
+    sample = ("each step = the first %d problems of the workload's table (%d per core), one single-threaded instance of the CPU restatement of the reference "
+              "solver (oracle/, reference CasADi C from oracle/_ref) per host core; the reference itself needs Eigen / Boost / Pinocchio / LCM and cannot be "
+              "built in this image" % (len(x0), per_core))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * len(x0) / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": {"workload": workload_name(args), "note": "CPU restatement of the reference solver (oracle/), reference CasADi C linked from oracle/_ref; the reference itself needs Eigen/Boost/Pinocchio/LCM and cannot be built in this image"},
+        "ms_per_step": 1e3 * len(x0) / v, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
@@ -153,7 +188,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--batch", type=int, default=4096, help="problems per GPU")
+    ap.add_argument("--batch", type=int, default=4096, help="global batch (--scaling strong) or problems per GPU (--scaling weak)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--workload", default="mhpc", choices=["mhpc", "hkd", "barrel", "loco", "barrel_to"])
     ap.add_argument("--gain-knots", type=int, default=8)
     ap.add_argument("--cpu-per-core", type=int, default=8)
@@ -166,8 +202,7 @@ def main():
     import torch
     import torch.distributed as dist
     import cafe_mpc_b200 as cm
-    from cafe_mpc_b200 import distributed as cdist
-    from cafe_mpc_b200 import workload
+    from cafe_mpc_b200 import api as capi
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -175,21 +210,31 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    B = args.batch
-    Bg = B * world
+    cfg = make_config(args, world)
+    Bg = cfg["global_batch"]
     prob, opt, gen_x0, n0 = make_problem(args.workload)
     x0_all = gen_x0(Bg) if Bg <= 8192 else np.tile(gen_x0(8192), ((Bg + 8191) // 8192, 1))[:Bg]
-    lo, hi = cdist.shard_range(Bg, world, rank)
+    lo, hi = capi.shard_range(Bg, world, rank)
+    per = (Bg + world - 1) // world
+    B = hi - lo
     x0 = np.ascontiguousarray(x0_all[lo:hi])
-    solver = cm.MultiPhaseDDP(prob, local, B)
+    solver = cm.MultiPhaseDDP(prob, local, per)
+    if world > 1:
+        # the NCCL id of the solver's own communicator travels over torch.distributed (plumbing); the gather itself is the C ABI's
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        solver.comm_init_rank(world, rank, bytes(idt.cpu().numpy().tobytes()))
     if args.workload == "barrel_to":
         solver.set_initial_guess(prob.initial_guess(x0))   # BarrelRollTO.cpp:131-147: part of the problem set-up, stays in force
     # device-resident inputs: x0 as [n0][ldb]
     x0_dev = torch.from_numpy(np.ascontiguousarray(x0.T)).cuda()
     x0_pin = torch.from_numpy(x0).pin_memory()
     rec = solver.command_size(args.gain_knots)
-    cmd_dev = torch.empty((B, rec), dtype=torch.float64, device="cuda")
-    cmd_pin = torch.empty((B, rec), dtype=torch.float64).pin_memory()
+    n_out = world * per if world > 1 else B
+    cmd_dev = torch.empty((n_out if rank == 0 else 1, rec), dtype=torch.float64, device="cuda")
+    cmd_pin = torch.empty((n_out if rank == 0 else 1, rec), dtype=torch.float64).pin_memory()
 
     def barrier():
         if world > 1:
@@ -204,10 +249,9 @@ def main():
         solver.set_initial_condition(x0_pin.numpy())
         solver.solve(opt)                                            # H2D of x0 inside
         if world > 1:
-            solver.get_commands_device(args.gain_knots, cmd_dev.data_ptr())
-            out = cdist.gather_records(cmd_dev, Bg, world, rank)     # the one collective: NCCL gather to rank 0
+            solver.gather_commands(args.gain_knots, per, cmd_dev.data_ptr())   # pack + the one collective: NCCL send / recv to rank 0
             if rank == 0:
-                cmd_pin.copy_(out[:B], non_blocking=False)           # rank 0 reads the result on the host
+                cmd_pin.copy_(cmd_dev, non_blocking=False)           # rank 0 reads EVERY rank's records on the host
         else:
             solver.get_commands(args.gain_knots, out=cmd_pin.numpy())  # D2H of the command records
         return float(cmd_pin[0, 0])
@@ -235,94 +279,136 @@ def main():
     wall_e2e = time.perf_counter() - t1
     sampler.stop.set()
     sampler.join(timeout=2)
-    tt = torch.tensor([wall, wall_e2e, dev_ms], dtype=torch.float64, device="cuda")
+    it_sum = float(sum(i["iter"] for i in info)); it_max = float(max(i["iter"] for i in info))
+    tt = torch.tensor([wall, wall_e2e, dev_ms, it_max], dtype=torch.float64, device="cuda")
+    ts = torch.tensor([it_sum, float(launches)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    wall, wall_e2e, dev_ms = [float(v) for v in tt.cpu()]
+        dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+    wall, wall_e2e, dev_ms, it_max = [float(v) for v in tt.cpu()]
+    it_sum, launches = [float(v) for v in ts.cpu()]
 
-    # ---- roofline of the dominant kernel (k_bwd), measured live with per-launch CUDA events on its stream
     roof = None
     cpu = None
     if rank == 0:
-        solver.set_profiling(True)
-        step_resident()
-        tm = solver.get_timing()
-        solver.set_profiling(False)
-        pinfo = solver.get_solver_info()
-        phases = prob.phases()
-        f_sweep = sum(F_BWD[p.model] * p.horizon for p in phases)
-        f_lin = sum(F_LIN[p.model] * p.horizon for p in phases)
-        flops = sum(i["reg_iter_total"] * f_sweep + i["iter"] * f_lin for i in pinfo)
-        n_l = max(tm["launches"]["bwd"], 1)
-        peak = cm.measure_fp64_peak(local)
-        ach = flops / (tm["ms"]["bwd"] * 1e-3) / 1e12
-        share = tm["ms"]["bwd"] / max(sum(tm["ms"].values()), 1e-9)
-        traffic, traffic_src = _ncu_traffic("k_bwd2") if (args.workload == "mhpc" and B == 4096) else (None, None)
-        roof_bwd = {"bound": "tensor", "pipe": "fp64 tensor pipe (DMMA m8n8k4) + fp64 FMA pipe", "kernel": "k_bwd2", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                "traffic": traffic, "traffic_source": traffic_src, "flop_per_launch": flops / n_l, "avg_launch_ms": tm["ms"]["bwd"] / n_l, "share_of_step": share,
-                "peak_source": "measured live: cafe_gpu_measure_fp64_peak = max(DFMA chains, DMMA m8n8k4 chains) microbenchmark; MEASURED_PEAKS.json has no fp64 entry"}
-        # the LQ stage (k_lq + its cooperative whole-body part k_lq_wb_dense, timed in the "misc" slot): HBM-bound by design, every
-        # active problem reads its iterate and writes the linearisation once per DDP iteration
-        lq_ms = tm["ms"]["lq"] + tm["ms"]["misc"]
-        n_lq = max(tm["launches"]["lq"], 1)
-        b_pass = sum(B_LQ[p.model] * p.horizon for p in phases)
-        lq_bytes = sum(i["iter"] * b_pass for i in pinfo)
-        t_lq, _ = _ncu_traffic("k_lq") if (args.workload == "mhpc" and B == 4096) else (None, None)
-        t_ds, _ = _ncu_traffic("k_lq_wb_dense") if (args.workload == "mhpc" and B == 4096) else (None, None)
-        n_wb = sum(1 for p in phases if p.model == 1)
-        roof_lq = {"bound": "hbm", "kernel": "k_lq (+ k_lq_wb_dense)", "achieved": lq_bytes / (lq_ms * 1e-3) / 1e9, "peak": _hbm_peak(), "unit": "GB/s",
-                   "frac": lq_bytes / (lq_ms * 1e-3) / 1e9 / _hbm_peak(), "traffic": (t_lq + n_wb * t_ds) if (t_lq and t_ds) else t_lq,
-                   "traffic_source": traffic_src, "bytes_per_launch": lq_bytes / n_lq, "avg_launch_ms": lq_ms / n_lq,
-                   "share_of_step": lq_ms / max(sum(tm["ms"].values()), 1e-9),
-                   "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy bandwidth)",
-                   "note": "algorithmic bytes = the reference's dense LQ inputs and outputs per knot (A,B,C,D, cost partials); whole-body decks: DRAM traffic "
-                           "far above it = register spills and thread-local arrays of the generated routines; HKD decks: structural zeros of A, B, lxx, "
-                           "luu are never rewritten, so fewer bytes move than this count"}
-        # `roofline` is the stage with the larger share of the step; the other one rides along
-        roof = dict(roof_lq if lq_ms > tm["ms"]["bwd"] else roof_bwd)
-        roof["other"] = roof_bwd if lq_ms > tm["ms"]["bwd"] else roof_lq
-        roof["kernel_ms"] = tm["ms"]; roof["hbm_peak_gbs"] = _hbm_peak()
-        # secondary figures per kernel family: share of the step and, where a committed ncu capture exists, the HBM fraction
-        # (DRAM bytes of one full-batch launch x launches / live kernel time; later ticks run fewer active problems, so this is an upper bound)
-        per = {}
-        tot_ms = max(sum(tm["ms"].values()), 1e-9)
-        for fam, kname in (("roll", "k_roll"), ("lq", "k_lq"), ("bwd", "k_bwd2"), ("misc", None), ("select", None), ("accept", None)):
-            e = {"ms": tm["ms"][fam], "launches": tm["launches"][fam], "share_of_step": tm["ms"][fam] / tot_ms}
-            tb, _ = _ncu_traffic(kname) if (kname and args.workload == "mhpc" and B == 4096) else (None, None)
-            if tb and tm["ms"][fam] > 0:
-                gbs = tb * tm["launches"][fam] / (tm["ms"][fam] * 1e-3) / 1e9
-                e["hbm_gbs_upper_bound"] = gbs; e["hbm_frac_upper_bound"] = gbs / _hbm_peak()
-            per[fam] = e
-        roof["per_kernel"] = per
+        roof = roofline(args, solver, prob, step_resident, local, B, Bg)
         if not args.no_cpu_baseline:
             cores = len(os.sched_getaffinity(0))
             v, n = cpu_sample(x0_all[: cores * args.cpu_per_core], cores, args.cpu_per_core, args.workload)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": "%d problems (first of the same SplitMix64 table), one single-threaded oracle instance per core" % n}
-    if rank == 0:
-        it = [i["iter"] for i in info]
+        cfg = dict(cfg)
+        cfg.update({"per_gpu_batch": per, "parallelism": "batch sharded over %d GPU(s), no collective in the solve" % world,
+                    "mean_ddp_iterations": it_sum / Bg, "max_ddp_iterations": it_max})
         print(json.dumps({
             "metric": METRIC, "value": Bg * args.steps / wall, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": 1e3 * wall / args.steps, "device_ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args), "global_batch": Bg, "per_gpu_batch": B, "parallelism": "batch sharded over %d GPU(s), no collective in the solve" % world,
-                       "settings": {"hkd": "HKDMPC/settings (10x5 iteration caps, alpha 0.1)",
-                                    "mhpc": "MHPC/settings (10x20 iteration caps, alpha 0.5, BG_alpha 10, cost_weights_regular, constraint_params_regular)",
-                                    "barrel": "MHPC/settings (10x20 iteration caps, alpha 0.5, BG_alpha 10, cost_weights_barrel, constraint_params_barrel)",
-                                    "barrel_to": "BarrelRoll/setting (30x10 iteration caps, alpha 0.5, BG_alpha 10, br_cost_weights, br_constraint_params)",
-                                    "loco": "Locomotion/settings (30x10 iteration caps, alpha 0.5, BG_alpha 10, loco_cost_weights, loco_constraint_params)"}[args.workload],
-                       "l2": "working set per solve (GBs of per-problem arrays) exceeds the 126 MB L2; no flush needed",
-                       "mean_ddp_iterations": sum(it) / len(it), "max_ddp_iterations": max(it)},
-            "e2e": {"value": Bg * args.steps / wall_e2e, "unit": UNIT, "h2d_bytes_per_step": int(B * n0 * 8), "d2h_bytes_per_step": int(B * rec * 8),
-                    "what": "cafe_gpu_solve_batch(host x0) + cafe_gpu_get_commands (Xbar,Ubar,Y all knots; K,Qu,Quu,Qux first %d knots)%s" % (args.gain_knots, " + NCCL gather to rank 0" if world > 1 else "")},
+            "ms_per_step": 1e3 * wall / args.steps, "device_ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+            "e2e": {"value": Bg * args.steps / wall_e2e, "unit": UNIT, "h2d_bytes_per_step": int(Bg * n0 * 8), "d2h_bytes_per_step": int(n_out * rec * 8),
+                    "what": "cafe_gpu_solve_batch(host x0) + %s (Xbar,Ubar,Y all knots; K,Qu,Quu,Qux first %d knots); byte counts are whole-job totals per step"
+                            % ("cafe_gpu_gather_commands (pack + NCCL send/recv to rank 0) + D2H of all %d records on rank 0" % n_out if world > 1 else "cafe_gpu_get_commands", args.gain_knots)},
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu}))
     if world > 1:
         dist.destroy_process_group()
 
 
+def roofline(args, solver, prob, step_resident, local, B, Bg):
+    """Per-kernel roofline figures of rank 0's shard, measured live with per-launch CUDA events on the solver's stream (profiling mode:
+    one stream, a host sync per launch). For every kernel: algorithmic bytes and flops per work unit x the units it was
+    launched on, its measured time, BOTH fractions (HBM and fp64), and the DRAM bytes of one full-batch launch from the committed
+    ncu --set full capture where one exists. `roofline` itself is the kernel with the largest share of the step."""
+    import cafe_mpc_b200 as cm
+    solver.set_profiling(True)
+    step_resident()
+    tm = solver.get_timing()
+    solver.set_profiling(False)
+    pinfo = solver.get_solver_info()
+    phases = prob.phases()
+    peak64 = cm.measure_fp64_peak(local)
+    hbm = _hbm_peak()
+    tot_ms = max(sum(tm["ms"].values()), 1e-9)
+    # per-unit algorithmic work of the whole-body kernels, averaged over the running knots of the deck (contact rows differ per phase)
+    wb = [(p.horizon, 3 * sum(1 for c in p.contact if c > 0)) for p in phases if p.model == 1]
+    n_wbk = max(sum(h for h, _ in wb), 1)
+    avg = lambda f: sum(h * f(nr) for h, nr in wb) / n_wbk
+    lxx_nnz = _lxx_nnz(prob, phases) if wb else 0.0
+    model = {   # doubles in, doubles out, flop per unit
+        "wb_terms": (36, TM_NNZ, OPS_TERMS),
+        "wb_fwd": (TM_NNZ + 36 + 12 + 72, 36 + 12 + 18 + 3, avg(wb_fwd_flop)),
+        "wb_derivs": (36 + 18 + 12, DP_NNZ, OPS_DERIVS),
+        "wb_sens": (DP_NNZ + TM_NNZ, 18 * 48 + avg(lambda nr: nr * 48), avg(wb_sens_flop)),
+        "wb_cost": (TM_NNZ + 72 + 60, 36 + 12 + 12 + 12 + 36 + lxx_nnz + 1, 4000.0),
+    }
+    names = {"roll": "k_roll", "lq": "k_lq", "bwd": "k_bwd2", "wb_terms": "k_wb_terms", "wb_fwd": "k_wb_fwd", "wb_derivs": "k_wb_derivs", "wb_sens": "k_wb_sens",
+             "wb_cost": "k_wb_cost", "select": "k_ls_scan / k_select / k_compact", "accept": "k_accept", "misc": "k_init / k_unpack"}
+    full = args.workload == "mhpc" and B == 4096
+    per = {}
+    for fam in tm["ms"]:
+        ms, nl, units = tm["ms"][fam], tm["launches"][fam], tm["units"][fam]
+        e = {"kernel": names[fam], "ms": ms, "launches": nl, "share_of_step": ms / tot_ms}
+        if fam in model and ms > 0:
+            din, dout, fl = model[fam]
+            e.update({"units": units, "bytes_per_unit": 8.0 * (din + dout), "flop_per_unit": fl,
+                      "hbm_gbs": 8.0 * (din + dout) * units / (ms * 1e-3) / 1e9, "fp64_tflops": fl * units / (ms * 1e-3) / 1e12})
+        if fam == "bwd" and ms > 0:
+            f_sweep = sum(F_BWD[p.model] * p.horizon for p in phases)
+            f_lin = sum(F_LIN[p.model] * p.horizon for p in phases)
+            flops = sum(i["reg_iter_total"] * f_sweep + i["iter"] * f_lin for i in pinfo)
+            b_sweep = 8.0 * sum(_bwd_doubles(p.model, lxx_nnz) * p.horizon for p in phases)
+            byts = sum(i["reg_iter_total"] * b_sweep for i in pinfo)
+            e.update({"units": units, "flop_total": flops, "bytes_total": byts, "hbm_gbs": byts / (ms * 1e-3) / 1e9, "fp64_tflops": flops / (ms * 1e-3) / 1e12})
+        if "hbm_gbs" in e:
+            e["hbm_frac"] = e["hbm_gbs"] / hbm
+            e["fp64_frac"] = e["fp64_tflops"] / peak64
+        tb, src = _ncu_traffic(names[fam]) if full else (None, None)
+        if tb:
+            e["dram_bytes_full_batch_launch_ncu"] = tb
+            e["traffic_source"] = src
+        per[fam] = e
+    top = max(per, key=lambda k: per[k]["ms"])
+    t = per[top]
+    bound = "tensor" if top == "bwd" else "hbm"
+    ach = t.get("fp64_tflops") if bound == "tensor" else t.get("hbm_gbs")
+    roof = {"bound": bound, "kernel": t["kernel"], "achieved": ach, "peak": peak64 if bound == "tensor" else hbm, "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
+            "frac": (ach / (peak64 if bound == "tensor" else hbm)) if ach else None, "traffic": t.get("dram_bytes_full_batch_launch_ncu"),
+            "traffic_source": t.get("traffic_source"), "avg_launch_ms": t["ms"] / max(t["launches"], 1), "share_of_step": t["share_of_step"],
+            "pipe": "fp64 tensor pipe (DMMA m8n8k4) + fp64 FMA pipe" if bound == "tensor" else None,
+            "peak_source": ("measured live: cafe_gpu_measure_fp64_peak = max(DFMA chains, DMMA m8n8k4 chains) microbenchmark; MEASURED_PEAKS.json has no fp64 entry"
+                            if bound == "tensor" else "MEASURED_PEAKS.json hbm_gbs (burst copy bandwidth)"),
+            "fp64_peak_tflops": peak64, "hbm_peak_gbs": hbm,
+            "achieved_definition": "k_bwd2: dense flop counts of the reference's sweep formulas (SURVEY.md 8d: WB 373 392 / HKD 233 280 / SRB 30 096 per knot and sweep + "
+                                   "linear rollout) x the bit-exact per-problem sweep counters / live kernel time; other kernels: algorithmic bytes (inputs + outputs of "
+                                   "the kernel per work unit, DESIGN.md section 3) x launched units / live kernel time",
+            "kernel_ms": tm["ms"], "per_kernel": per}
+    return roof
+
+
+def _bwd_doubles(model, lxx_nnz):
+    """doubles one sweep pass + the linear rollout move per knot (inputs of the sweep, its outputs, inputs of the linear rollout)"""
+    if model == 1:
+        ab, cd, k = 18 * 48, 12 * 48, 12 * 36
+        return (ab + cd + lxx_nnz + 36 + 12 + 36 + 12 + 12 + 36) + (2 * k + 144 + k + 12 + 36 + 12) + (k + ab + lxx_nnz + 12 + 48 + 36 + 12 + 36)
+    n, m = (24, 24) if model == 0 else (12, 12)
+    return (n * n + n * m + n * n + m * m + 3 * n + m) + (2 * m * n + m * m + m * n + m + n + m) + (m * n + n * n + n * m + n * n + m * m + 3 * n + 2 * m)
+
+
+def _lxx_nnz(prob, phases):
+    """mean number of structural non-zeros of lxx over the running whole-body knots (cafe_deck_lq_pattern)"""
+    import ctypes as C
+    from cafe_mpc_b200.lib import lib
+    tot, cnt = 0, 0
+    for pi, p in enumerate(phases):
+        if p.model != 1:
+            continue
+        for k in range(p.horizon):
+            w = (C.c_ulonglong * 21)()
+            if lib.cafe_deck_lq_pattern(prob.deck, pi, k, 2, w) > 0:
+                tot += sum(bin(x).count("1") for x in w); cnt += 1
+    return tot / max(cnt, 1)
+
+
 def _ncu_traffic(kernel):
     """DRAM bytes per launch of `kernel` from the committed ncu --set full summary of the newest round (profiles/rNN_traffic.json)."""
-    import glob
     files = sorted(glob.glob(os.path.join(REPO, "profiles", "r*_traffic.json")))
     if not files:
         return None, None

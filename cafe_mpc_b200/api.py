@@ -265,6 +265,13 @@ class MultiPhaseDDP:
     def get_commands_device(self, n_gain_knots, dev_ptr):
         check(lib.cafe_gpu_get_commands_device(self._h, n_gain_knots, C.c_void_p(dev_ptr)))
 
+    # ---- one process per GPU (torchrun / MPI): NCCL communicator of this rank's solver and the final gather (include/cafe_gpu.h)
+    def comm_init_rank(self, nranks, rank, unique_id):
+        check(lib.cafe_gpu_comm_init_rank(self._h, nranks, rank, unique_id))
+
+    def gather_commands(self, n_gain_knots, per_rank, out_dev_ptr):
+        check(lib.cafe_gpu_gather_commands(self._h, n_gain_knots, per_rank, C.c_void_p(out_dev_ptr)))
+
     def solve_ms(self):
         v = C.c_double()
         check(lib.cafe_gpu_get_solve_ms(self._h, C.byref(v)))
@@ -276,7 +283,63 @@ class MultiPhaseDDP:
         ticks = C.c_int()
         check(lib.cafe_gpu_get_timing(self._h, C.byref(ms), C.byref(n), C.byref(ticks)))
         names = ["roll", "select", "accept", "lq", "bwd", "misc", "wb_terms", "wb_fwd", "wb_derivs", "wb_sens", "wb_cost"]
-        return {"ms": dict(zip(names, list(ms))), "launches": dict(zip(names, list(n))), "ticks": ticks.value}
+        un = (C.c_double * CAFE_NKERNELS)()
+        check(lib.cafe_gpu_get_units(self._h, C.byref(un)))
+        return {"ms": dict(zip(names, list(ms))), "launches": dict(zip(names, list(n))), "units": dict(zip(names, list(un))), "ticks": ticks.value}
+
+
+def nccl_unique_id():
+    """128-byte NCCL id made by rank 0; the launcher (torch.distributed, MPI, a file) hands it to every rank."""
+    buf = C.create_string_buffer(128)
+    check(lib.cafe_gpu_nccl_unique_id(buf))
+    return buf.raw
+
+
+def shard_range(B, nranks, rank):
+    lo, hi = C.c_int(), C.c_int()
+    check(lib.cafe_gpu_shard_range(B, nranks, rank, C.byref(lo), C.byref(hi)))
+    return lo.value, hi.value
+
+
+class MultiGPUDDP:
+    """One process, several GPUs of one box (cafe_gpu_create_multi): the batch is cut into contiguous slices, one solver per GPU, the
+    command records are gathered on the first GPU by one NCCL group of sends / receives."""
+
+    def __init__(self, problem, ndev, max_batch, devices=None):
+        self.problem = problem
+        self._m = C.c_void_p()
+        devs = (C.c_int * ndev)(*devices) if devices is not None else None
+        check(lib.cafe_gpu_create_multi(problem.deck, ndev, devs, max_batch, C.byref(self._m)))
+        self.ndev = ndev
+        self.B = 0
+
+    def close(self):
+        if self._m and self._m.value:
+            lib.cafe_gpu_multi_destroy(self._m)
+            self._m = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def solve(self, x0, option):
+        x0 = np.ascontiguousarray(np.atleast_2d(x0), dtype=np.float64)
+        self.B = x0.shape[0]
+        check(lib.cafe_gpu_multi_solve_batch(self._m, x0.ctypes.data_as(C.c_void_p), self.B, C.byref(option)))
+
+    def get_solver_info(self):
+        info = (Info * self.B)()
+        check(lib.cafe_gpu_multi_get_info(self._m, info))
+        return [i.as_dict() for i in info]
+
+    def get_commands(self, n_gain_knots=8, out=None):
+        sz = lib.cafe_command_size(self.problem.deck, n_gain_knots)
+        if out is None:
+            out = np.zeros((self.B, sz))
+        check(lib.cafe_gpu_multi_get_commands(self._m, n_gain_knots, out.ctypes.data_as(C.c_void_p)))
+        return out
 
 
 def unpack_solution(deck, sol):

@@ -59,6 +59,7 @@ struct CafeHandle {
   bool profiling = false;
   double ms[CAFE_NKERNELS] = {0};
   long launches[CAFE_NKERNELS] = {0};
+  double units[CAFE_NKERNELS] = {0};   // work items launched per slot: (problem, knot[, step size]) for the knot kernels, problems for the sweep
   int ticks = 0;
   int bwd_variant = 0;  // 0: HKD deck (24,24,0)   1: MHPC deck (36,24->12,12)
   size_t bwd_smem = 0;
@@ -466,6 +467,7 @@ extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, 
 
 extern "C" int cafe_gpu_destroy(CafeHandle* H) {
   if (!H) return 0;
+  cafe_gpu_comm_destroy(H);
   cudaSetDevice(H->device);
   cudaFree(H->arena); cudaFree(H->d_ref); cudaFree(H->d_ref_pp); cudaFree(H->d_lxx_mask); cudaFree(H->d_hkd_mask); cudaFree(H->d_guess); cudaFree(H->d_x0raw); cudaFree(H->dS); cudaFree(H->d_pack); cudaFree(H->d_segs);
   if (H->h_nactive) cudaFreeHost(H->h_nactive);
@@ -494,7 +496,7 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
   if (S.NA > H->NA) { cafe::set_last_error("step-size ladder longer than the allocated trial slots"); return CAFE_ERR_UNSUPPORTED; }
   // trial-slot strides are fixed by the allocation (H->NA slots), the ladder may be shorter
   H->B = B;
-  for (int i = 0; i < CAFE_NKERNELS; ++i) { H->ms[i] = 0; H->launches[i] = 0; }
+  for (int i = 0; i < CAFE_NKERNELS; ++i) { H->ms[i] = 0; H->launches[i] = 0; H->units[i] = 0; }
   H->ticks = 0;
   cudaStream_t st = H->stream;
   CUDA_OK(cudaEventRecord(H->evs, st));
@@ -535,6 +537,8 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
   auto roll_group = [&](cudaStream_t sq, int a0, int a1, const int* list, int n_list, bool tm) {
     auto run = [&](int slot, auto&& f) { if (tm) timed(H, slot, f); else { f(); H->launches[slot]++; } };
     run(CAFE_K_ROLL, [&] { cafe_dev::launch_roll(H->dS, S.n_knots, sq, a0, a1, list, n_list); });
+    H->units[CAFE_K_ROLL] += (double)n_list * S.n_knots * (a1 - a0);
+    H->units[CAFE_K_WB_TERMS] += (double)n_list * n_wbk * (a1 - a0); H->units[CAFE_K_WB_FWD] += (double)n_list * n_wbk * (a1 - a0);
     if (n_wbk > 0) {
       run(CAFE_K_WB_TERMS, [&] { cafe_dev::launch_wb_terms(H->dS, n_wbk, sq, a0, a1, list, n_list); });
       run(CAFE_K_WB_FWD, [&] { cafe_dev::launch_wb_fwd(H->dS, n_wbk, sq, a0, a1, list, n_list); });
@@ -543,6 +547,8 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
   auto lq_group = [&](cudaStream_t sq, const int* list, int n_list, bool tm) {
     auto run = [&](int slot, auto&& f) { if (tm) timed(H, slot, f); else { f(); H->launches[slot]++; } };
     run(CAFE_K_LQ, [&] { cafe_dev::launch_lq(H->dS, S.n_knots, sq, list, n_list); });
+    H->units[CAFE_K_LQ] += (double)n_list * S.n_knots; H->units[CAFE_K_BWD] += (double)n_list;
+    H->units[CAFE_K_WB_DERIVS] += (double)n_list * n_wbk; H->units[CAFE_K_WB_SENS] += (double)n_list * n_wbk; H->units[CAFE_K_WB_COST] += (double)n_list * n_wbk;
     if (n_wbk > 0) {
       run(CAFE_K_WB_DERIVS, [&] { cafe_dev::launch_wb_derivs(H->dS, n_wbk, sq, list, n_list); });
       run(CAFE_K_WB_SENS, [&] { cafe_dev::launch_wb_sens(H->dS, n_wbk, sq, list, n_list); });
@@ -636,6 +642,11 @@ extern "C" int cafe_gpu_get_timing(CafeHandle* H, double ms[CAFE_NKERNELS], long
   if (!H) return CAFE_ERR_ARG;
   for (int i = 0; i < CAFE_NKERNELS; ++i) { if (ms) ms[i] = H->ms[i]; if (launches) launches[i] = H->launches[i]; }
   if (ticks) *ticks = H->ticks;
+  return 0;
+}
+extern "C" int cafe_gpu_get_units(CafeHandle* H, double units[CAFE_NKERNELS]) {
+  if (!H || !units) return CAFE_ERR_ARG;
+  for (int i = 0; i < CAFE_NKERNELS; ++i) units[i] = H->units[i];
   return 0;
 }
 extern "C" int cafe_gpu_get_solve_ms(CafeHandle* H, double* ms) { if (!H || !ms) return CAFE_ERR_ARG; *ms = H->total_ms; return 0; }
@@ -1109,5 +1120,263 @@ extern "C" int cafe_gpu_measure_fp64_peak(int device, double* tflops) {
   cudaFree(d);
   CUDA_OK(cudaGetLastError());
   *tflops = best;
+  return 0;
+}
+
+// =====================================================================================================================
+// Multi-GPU: problems are independent, so GPU g solves the contiguous slice [g ceil(B/G), min(B, (g+1) ceil(B/G)))
+// with the deck replicated and NO traffic during the solve; the only collective is the final gather of the packed command
+// records to the first GPU (NCCL send / recv in one group over NVLink / NVSwitch). Two ways in:
+//   * one process, G GPUs        cafe_gpu_create_multi ... (ncclCommInitAll, one host thread per GPU during the solve)
+//   * one process per GPU        cafe_gpu_nccl_unique_id + cafe_gpu_comm_init_rank + cafe_gpu_gather_commands (torchrun, MPI)
+// NCCL is opened at run time (dlopen): the library loads, and single-GPU use works, on a box without it.
+#include <dlfcn.h>
+#include <thread>
+#include <nccl.h>
+
+namespace {
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) { api.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL); if (api.lib) break; }
+    if (api.lib) {
+      bool ok = true;
+      auto sym = [&](const char* n) { void* p = dlsym(api.lib, n); if (!p) ok = false; return p; };
+      api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+      api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+      api.CommInitAll = reinterpret_cast<decltype(api.CommInitAll)>(sym("ncclCommInitAll"));
+      api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+      api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+      api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+      api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
+      api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
+      api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+      if (!ok) { dlclose(api.lib); api.lib = nullptr; }
+    }
+  }
+  return api.lib ? &api : nullptr;
+}
+#define NCCL_OK(call)                                                                                      \
+  do {                                                                                                     \
+    ncclResult_t r_ = (call);                                                                              \
+    if (r_ != ncclSuccess) { cafe::set_last_error(std::string(#call) + ": " + N->GetErrorString(r_)); return CAFE_ERR_CUDA; } \
+  } while (0)
+}  // namespace
+
+struct CafeComm { ncclComm_t comm = nullptr; int nranks = 0, rank = 0; double* d_send = nullptr; size_t send_bytes = 0; };
+
+extern "C" int cafe_gpu_shard_range(int B, int nranks, int rank, int* lo, int* hi) {
+  if (B < 0 || nranks <= 0 || rank < 0 || rank >= nranks || !lo || !hi) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
+  const int per = (B + nranks - 1) / nranks;
+  *lo = std::min(B, rank * per); *hi = std::min(B, (rank + 1) * per);
+  return 0;
+}
+
+extern "C" int cafe_gpu_nccl_unique_id(char id[128]) {
+  NcclApi* N = nccl_api();
+  if (!N) { cafe::set_last_error("NCCL (libnccl.so.2) is not available"); return CAFE_ERR_UNSUPPORTED; }
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  ncclUniqueId u;
+  NCCL_OK(N->GetUniqueId(&u));
+  std::memcpy(id, &u, 128);
+  return 0;
+}
+
+// the handle's communicator lives beside it (the handle struct itself stays what the single-GPU path needs)
+#include <map>
+#include <mutex>
+namespace { std::map<CafeHandle*, CafeComm> g_comms; std::mutex g_comm_mu; }
+
+extern "C" int cafe_gpu_comm_init_rank(CafeHandle* H, int nranks, int rank, const char id[128]) {
+  NcclApi* N = nccl_api();
+  if (!N) { cafe::set_last_error("NCCL (libnccl.so.2) is not available"); return CAFE_ERR_UNSUPPORTED; }
+  if (!H || nranks <= 0 || rank < 0 || rank >= nranks || !id) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
+  CUDA_OK(cudaSetDevice(H->device));
+  ncclUniqueId u;
+  std::memcpy(&u, id, 128);
+  CafeComm c; c.nranks = nranks; c.rank = rank;
+  NCCL_OK(N->CommInitRank(&c.comm, nranks, u, rank));
+  std::lock_guard<std::mutex> lk(g_comm_mu);
+  g_comms[H] = c;
+  return 0;
+}
+
+extern "C" int cafe_gpu_comm_destroy(CafeHandle* H) {
+  NcclApi* N = nccl_api();
+  std::lock_guard<std::mutex> lk(g_comm_mu);
+  auto it = g_comms.find(H);
+  if (it == g_comms.end()) return 0;
+  if (N && it->second.comm) N->CommDestroy(it->second.comm);
+  if (it->second.d_send) { cudaSetDevice(H->device); cudaFree(it->second.d_send); }
+  g_comms.erase(it);
+  return 0;
+}
+
+// Packs this rank's command records and gathers the ranks' slices to rank 0: rank r's records land at out_dev[r * per_rank ...] (device
+// buffer of rank 0, [nranks * per_rank][cafe_command_size] doubles; ignored on the other ranks). Ragged tails are fine (a rank sends its
+// own H->B records). Stream-ordered on the handle's stream; returns after the transfer has completed.
+extern "C" int cafe_gpu_gather_commands(CafeHandle* H, int n_gain_knots, int per_rank, double* out_dev) {
+  NcclApi* N = nccl_api();
+  if (!N) { cafe::set_last_error("NCCL (libnccl.so.2) is not available"); return CAFE_ERR_UNSUPPORTED; }
+  CafeComm c;
+  { std::lock_guard<std::mutex> lk(g_comm_mu); auto it = g_comms.find(H); if (it == g_comms.end()) { cafe::set_last_error("no communicator: call cafe_gpu_comm_init_rank first"); return CAFE_ERR_ARG; } c = it->second; }
+  if (per_rank < H->B || (c.rank == 0 && !out_dev)) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
+  CUDA_OK(cudaSetDevice(H->device));
+  const size_t rec = (size_t)cafe_command_size(&H->deck, n_gain_knots);
+  double* src = nullptr;
+  if (c.rank == 0) src = out_dev;   // rank 0 packs straight into its slot of the gathered buffer
+  else {
+    const size_t need = (size_t)per_rank * rec * sizeof(double);   // a full slot: a ragged last shard is zero-padded
+    if (need > c.send_bytes) {
+      cudaFree(c.d_send); c.d_send = nullptr;
+      CUDA_OK(cudaMalloc(&c.d_send, need)); c.send_bytes = need;
+      std::lock_guard<std::mutex> lk(g_comm_mu); g_comms[H] = c;
+    }
+    src = c.d_send;
+    if (H->B < per_rank) CUDA_OK(cudaMemsetAsync(src + (size_t)H->B * rec, 0, (size_t)(per_rank - H->B) * rec * sizeof(double), H->stream));
+  }
+  int rc = cafe_gpu_get_commands_device(H, n_gain_knots, src);
+  if (rc) return rc;
+  // equal slots of per_rank records: rank 0 need not know the other ranks' (possibly ragged) counts
+  NCCL_OK(N->GroupStart());
+  if (c.rank == 0) {
+    for (int r = 1; r < c.nranks; ++r) NCCL_OK(N->Recv(out_dev + (size_t)r * per_rank * rec, (size_t)per_rank * rec, ncclDouble, r, c.comm, H->stream));
+  } else {
+    NCCL_OK(N->Send(src, (size_t)per_rank * rec, ncclDouble, 0, c.comm, H->stream));
+  }
+  NCCL_OK(N->GroupEnd());
+  CUDA_OK(cudaStreamSynchronize(H->stream));
+  return 0;
+}
+
+// ---- one process, several GPUs
+struct CafeMulti {
+  int ndev = 0, max_batch = 0, per = 0, B = 0;
+  std::vector<CafeHandle*> h;
+  std::vector<ncclComm_t> comms;
+  std::vector<double*> d_send;     // per GPU > 0: packed records of its slice
+  std::vector<size_t> send_bytes;
+  double* d_all = nullptr; size_t all_bytes = 0;   // on GPU 0: the gathered records
+  std::vector<int> lo, hi;
+};
+
+extern "C" int cafe_gpu_multi_destroy(CafeMulti* M) {
+  if (!M) return 0;
+  NcclApi* N = nccl_api();
+  for (size_t g = 0; g < M->h.size(); ++g) {
+    if (M->h[g]) { cudaSetDevice(M->h[g]->device); if (g < M->d_send.size()) cudaFree(M->d_send[g]); if (g == 0) cudaFree(M->d_all); }
+    if (N && g < M->comms.size() && M->comms[g]) N->CommDestroy(M->comms[g]);
+    cafe_gpu_destroy(M->h[g]);
+  }
+  delete M;
+  return 0;
+}
+
+extern "C" int cafe_gpu_create_multi(const CafeDeck* deck, int ndev, const int* devices, int max_batch, CafeMulti** out) {
+  if (!deck || !out || ndev <= 0 || max_batch <= 0) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
+  NcclApi* N = nccl_api();
+  if (ndev > 1 && !N) { cafe::set_last_error("NCCL (libnccl.so.2) is not available"); return CAFE_ERR_UNSUPPORTED; }
+  CafeMulti* M = new CafeMulti();
+  M->ndev = ndev; M->max_batch = max_batch; M->per = (max_batch + ndev - 1) / ndev;
+  M->h.assign(ndev, nullptr); M->comms.assign(ndev, nullptr); M->d_send.assign(ndev, nullptr); M->send_bytes.assign(ndev, 0);
+  M->lo.assign(ndev, 0); M->hi.assign(ndev, 0);
+  std::vector<int> devs(ndev);
+  for (int g = 0; g < ndev; ++g) devs[g] = devices ? devices[g] : g;
+  for (int g = 0; g < ndev; ++g) {
+    int rc = cafe_gpu_create(deck, devs[g], M->per, &M->h[g]);
+    if (rc) { cafe_gpu_multi_destroy(M); return rc; }
+  }
+  if (ndev > 1) {
+    ncclResult_t r = N->CommInitAll(M->comms.data(), ndev, devs.data());
+    if (r != ncclSuccess) { cafe::set_last_error(std::string("ncclCommInitAll: ") + N->GetErrorString(r)); cafe_gpu_multi_destroy(M); return CAFE_ERR_CUDA; }
+  }
+  *out = M;
+  return 0;
+}
+
+extern "C" int cafe_gpu_multi_ndev(const CafeMulti* M) { return M ? M->ndev : 0; }
+extern "C" CafeHandle* cafe_gpu_multi_handle(CafeMulti* M, int g) { return (M && g >= 0 && g < M->ndev) ? M->h[g] : nullptr; }
+
+// x0: host [B][n0]. GPU g solves rows [lo_g, hi_g); one host thread per GPU (the tick loop polls one counter per tick and GPU)
+extern "C" int cafe_gpu_multi_solve_batch(CafeMulti* M, const double* x0, int B, const CafeOptions* opt) {
+  if (!M || !x0 || !opt || B <= 0 || B > M->max_batch) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
+  M->B = B;
+  const int n0 = M->h[0]->S.ph[0].n;
+  const int per = (B + M->ndev - 1) / M->ndev;
+  std::vector<int> rc(M->ndev, 0);
+  std::vector<std::thread> th;
+  for (int g = 0; g < M->ndev; ++g) {
+    M->lo[g] = std::min(B, g * per); M->hi[g] = std::min(B, (g + 1) * per);
+    const int nb = M->hi[g] - M->lo[g];
+    if (nb <= 0) { M->h[g]->B = 0; continue; }
+    th.emplace_back([&, g, nb] { rc[g] = cafe_gpu_solve_batch(M->h[g], x0 + (size_t)M->lo[g] * n0, nb, opt); });
+  }
+  for (auto& t : th) t.join();
+  for (int g = 0; g < M->ndev; ++g) if (rc[g]) return rc[g];
+  return 0;
+}
+
+extern "C" int cafe_gpu_multi_get_info(CafeMulti* M, CafeInfo* info) {
+  if (!M || !info) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
+  for (int g = 0; g < M->ndev; ++g) {
+    if (M->hi[g] <= M->lo[g]) continue;
+    int rc = cafe_gpu_get_info(M->h[g], info + M->lo[g]);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+// packs every GPU's command records, gathers them on the first GPU (one NCCL group of sends / receives) and copies the B records to
+// the host: cmd = host [B][cafe_command_size(deck, n_gain_knots)]
+extern "C" int cafe_gpu_multi_get_commands(CafeMulti* M, int n_gain_knots, double* cmd) {
+  if (!M || !cmd || n_gain_knots < 0 || M->B <= 0) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
+  NcclApi* N = nccl_api();
+  const size_t rec = (size_t)cafe_command_size(&M->h[0]->deck, n_gain_knots);
+  CafeHandle* H0 = M->h[0];
+  CUDA_OK(cudaSetDevice(H0->device));
+  const size_t need = (size_t)M->B * rec * sizeof(double);
+  if (need > M->all_bytes) { cudaFree(M->d_all); M->d_all = nullptr; CUDA_OK(cudaMalloc(&M->d_all, need)); M->all_bytes = need; }
+  for (int g = 0; g < M->ndev; ++g) {
+    const int nb = M->hi[g] - M->lo[g];
+    if (nb <= 0) continue;
+    CafeHandle* H = M->h[g];
+    CUDA_OK(cudaSetDevice(H->device));
+    double* dst = M->d_all + (size_t)M->lo[g] * rec;
+    if (g > 0) {
+      const size_t nbytes = (size_t)nb * rec * sizeof(double);
+      if (nbytes > M->send_bytes[g]) { cudaFree(M->d_send[g]); M->d_send[g] = nullptr; CUDA_OK(cudaMalloc(&M->d_send[g], nbytes)); M->send_bytes[g] = nbytes; }
+      dst = M->d_send[g];
+    }
+    int rc = cafe_gpu_get_commands_device(H, n_gain_knots, dst);
+    if (rc) return rc;
+  }
+  if (M->ndev > 1) {
+    NCCL_OK(N->GroupStart());
+    for (int g = 1; g < M->ndev; ++g) {
+      const int nb = M->hi[g] - M->lo[g];
+      if (nb <= 0) continue;
+      NCCL_OK(N->Send(M->d_send[g], (size_t)nb * rec, ncclDouble, 0, M->comms[g], M->h[g]->stream));
+      NCCL_OK(N->Recv(M->d_all + (size_t)M->lo[g] * rec, (size_t)nb * rec, ncclDouble, g, M->comms[0], H0->stream));
+    }
+    NCCL_OK(N->GroupEnd());
+  }
+  CUDA_OK(cudaSetDevice(H0->device));
+  CUDA_OK(cudaMemcpyAsync(cmd, M->d_all, need, cudaMemcpyDeviceToHost, H0->stream));
+  CUDA_OK(cudaStreamSynchronize(H0->stream));
+  for (int g = 1; g < M->ndev; ++g) { if (M->hi[g] > M->lo[g]) { CUDA_OK(cudaSetDevice(M->h[g]->device)); CUDA_OK(cudaStreamSynchronize(M->h[g]->stream)); } }
   return 0;
 }

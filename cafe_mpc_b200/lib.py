@@ -63,9 +63,24 @@ def _load():
     lib.cafe_gpu_get_solve_ms.argtypes = [vp, dp]
     lib.cafe_gpu_get_timing.argtypes = [vp, C.POINTER(C.c_double * CAFE_NKERNELS), C.POINTER(C.c_long * CAFE_NKERNELS), ip]
     lib.cafe_gpu_set_profiling.argtypes = [vp, C.c_int]
+    lib.cafe_gpu_get_units.argtypes = [vp, C.POINTER(C.c_double * CAFE_NKERNELS)]
     lib.cafe_gpu_debug_get.restype = C.c_long
     lib.cafe_gpu_debug_get.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, vp]
     lib.cafe_gpu_measure_fp64_peak.argtypes = [C.c_int, dp]
+    # multi-GPU
+    lib.cafe_gpu_shard_range.argtypes = [C.c_int, C.c_int, C.c_int, ip, ip]
+    lib.cafe_gpu_create_multi.argtypes = [C.POINTER(Deck), C.c_int, ip, C.c_int, C.POINTER(vp)]
+    lib.cafe_gpu_multi_destroy.argtypes = [vp]
+    lib.cafe_gpu_multi_ndev.argtypes = [vp]
+    lib.cafe_gpu_multi_handle.restype = vp
+    lib.cafe_gpu_multi_handle.argtypes = [vp, C.c_int]
+    lib.cafe_gpu_multi_solve_batch.argtypes = [vp, vp, C.c_int, C.POINTER(Options)]
+    lib.cafe_gpu_multi_get_info.argtypes = [vp, C.POINTER(Info)]
+    lib.cafe_gpu_multi_get_commands.argtypes = [vp, C.c_int, vp]
+    lib.cafe_gpu_nccl_unique_id.argtypes = [C.c_char_p]
+    lib.cafe_gpu_comm_init_rank.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
+    lib.cafe_gpu_comm_destroy.argtypes = [vp]
+    lib.cafe_gpu_gather_commands.argtypes = [vp, C.c_int, C.c_int, vp]
     return lib
 
 
@@ -83,5 +98,7 @@ EXPORTED = [
     "cafe_gpu_destroy", "cafe_gpu_solve_batch", "cafe_gpu_solve_batch_device", "cafe_gpu_get_info",
     "cafe_gpu_get_history", "cafe_gpu_get_trace", "cafe_gpu_get_solution", "cafe_gpu_get_commands", "cafe_gpu_get_commands_device", "cafe_gpu_get_solve_ms",
     "cafe_gpu_set_references", "cafe_gpu_set_initial_guess", "cafe_gpu_shift_guess", "cafe_gpu_get_planned_state", "cafe_lcm_command_size", "cafe_gpu_get_lcm_commands", "cafe_gpu_get_lcm_commands_device", "cafe_hkd_lcm_command_size", "cafe_gpu_get_hkd_lcm_commands", "cafe_gpu_get_hkd_lcm_commands_device",
-    "cafe_gpu_get_timing", "cafe_gpu_set_profiling", "cafe_gpu_debug_get", "cafe_gpu_measure_fp64_peak",
+    "cafe_gpu_get_timing", "cafe_gpu_get_units", "cafe_gpu_set_profiling", "cafe_gpu_debug_get", "cafe_gpu_measure_fp64_peak",
+    "cafe_gpu_shard_range", "cafe_gpu_create_multi", "cafe_gpu_multi_destroy", "cafe_gpu_multi_ndev", "cafe_gpu_multi_handle", "cafe_gpu_multi_solve_batch",
+    "cafe_gpu_multi_get_info", "cafe_gpu_multi_get_commands", "cafe_gpu_nccl_unique_id", "cafe_gpu_comm_init_rank", "cafe_gpu_comm_destroy", "cafe_gpu_gather_commands",
 ]

@@ -143,6 +143,28 @@ int cafe_gpu_get_lcm_commands_device(CafeHandle* h, int n_steps, float* out_dev)
 long cafe_hkd_lcm_command_size(int n_steps);
 int cafe_gpu_get_hkd_lcm_commands(CafeHandle* h, int n_steps, float* out /*[B][cafe_hkd_lcm_command_size]*/);
 int cafe_gpu_get_hkd_lcm_commands_device(CafeHandle* h, int n_steps, float* out_dev);
+/* ---- multi-GPU: the batch is cut into contiguous slices, GPU / rank g solves rows
+ * [g ceil(B/G), min(B, (g+1) ceil(B/G))) with the deck replicated and no traffic during the solve; the one collective is the final gather of
+ * the packed command records to the first GPU / rank 0 (NCCL send / recv in one group; NCCL is opened with dlopen at first use).
+ * Stands behind "one MultiPhaseDDP per problem" of the reference (HSDDPSolver/header/MultiPhaseDDP.h:31-93): the batch is ours. */
+typedef struct CafeMulti CafeMulti;
+int cafe_gpu_shard_range(int B, int nranks, int rank, int* lo, int* hi);
+/* (a) one process, ndev GPUs of one box: ncclCommInitAll; devices = NULL means 0..ndev-1; max_batch is the GLOBAL batch */
+int cafe_gpu_create_multi(const CafeDeck* deck, int ndev, const int* devices, int max_batch, CafeMulti** out);
+int cafe_gpu_multi_destroy(CafeMulti* m);
+int cafe_gpu_multi_ndev(const CafeMulti* m);
+CafeHandle* cafe_gpu_multi_handle(CafeMulti* m, int g); /* the per-GPU solver (histories, traces, debug reads) */
+int cafe_gpu_multi_solve_batch(CafeMulti* m, const double* x0 /*host [B][n0]*/, int B, const CafeOptions* opt);
+int cafe_gpu_multi_get_info(CafeMulti* m, CafeInfo* info /*[B]*/);
+int cafe_gpu_multi_get_commands(CafeMulti* m, int n_gain_knots, double* cmd /*host [B][cafe_command_size]*/);
+/* (b) one process per GPU (torchrun, MPI): rank 0 makes the id, the launcher hands it to every rank */
+int cafe_gpu_nccl_unique_id(char id[128]);
+int cafe_gpu_comm_init_rank(CafeHandle* h, int nranks, int rank, const char id[128]);
+int cafe_gpu_comm_destroy(CafeHandle* h);
+/* packs this rank's records and gathers all ranks' slices on rank 0: rank r's records land at out_dev + r * per_rank records (device
+ * buffer of rank 0 with nranks * per_rank records; per_rank >= the local batch, equal on all ranks; out_dev is ignored elsewhere) */
+int cafe_gpu_gather_commands(CafeHandle* h, int n_gain_knots, int per_rank, double* out_dev);
+
 /* device-time breakdown of the last solve, ms per kernel family, and launch counts */
 /* timing slots of cafe_gpu_get_timing: one per kernel family */
 #define CAFE_K_ROLL 0      /* k_roll: trial states / controls of every knot; SRB, HKD and terminal knots completely */
@@ -158,6 +180,8 @@ int cafe_gpu_get_hkd_lcm_commands_device(CafeHandle* h, int n_steps, float* out_
 #define CAFE_K_WB_COST 10  /* k_wb_cost: cooperative cost / barrier partials and running cost */
 #define CAFE_NKERNELS 11
 int cafe_gpu_get_timing(CafeHandle* h, double ms[CAFE_NKERNELS], long launches[CAFE_NKERNELS], int* ticks);
+/* work items launched per slot during the last solve: (problem, knot[, step size]) triples of the knot kernels, problems of the sweep */
+int cafe_gpu_get_units(CafeHandle* h, double units[CAFE_NKERNELS]);
 /* device time (CUDA events on the solver's stream) of the last cafe_gpu_solve_batch*, in ms */
 int cafe_gpu_get_solve_ms(CafeHandle* h, double* ms);
 /* enable per-kernel CUDA-event timing (costs a few us per launch) */
