@@ -1152,7 +1152,10 @@ NcclApi* nccl_api() {
   static bool tried = false;
   if (!tried) {
     tried = true;
-    for (const char* name : {"libnccl.so.2", "libnccl.so"}) { api.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL); if (api.lib) break; }
+    // CAFE_NCCL_LIB names a specific library; else whatever "libnccl.so.2" resolves to (a copy the process has already loaded, e.g.
+    // the one bundled with PyTorch, wins: two NCCL builds with the same SONAME cannot coexist in one process)
+    if (const char* e = getenv("CAFE_NCCL_LIB")) api.lib = dlopen(e, RTLD_NOW | RTLD_LOCAL);
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) { if (api.lib) break; api.lib = dlopen(name, RTLD_NOW | RTLD_LOCAL); }
     if (api.lib) {
       bool ok = true;
       auto sym = [&](const char* n) { void* p = dlsym(api.lib, n); if (!p) ok = false; return p; };
@@ -1216,10 +1219,10 @@ extern "C" int cafe_gpu_comm_init_rank(CafeHandle* H, int nranks, int rank, cons
 }
 
 extern "C" int cafe_gpu_comm_destroy(CafeHandle* H) {
-  NcclApi* N = nccl_api();
   std::lock_guard<std::mutex> lk(g_comm_mu);
   auto it = g_comms.find(H);
   if (it == g_comms.end()) return 0;
+  NcclApi* N = nccl_api();
   if (N && it->second.comm) N->CommDestroy(it->second.comm);
   if (it->second.d_send) { cudaSetDevice(H->device); cudaFree(it->second.d_send); }
   g_comms.erase(it);
@@ -1276,7 +1279,7 @@ struct CafeMulti {
 
 extern "C" int cafe_gpu_multi_destroy(CafeMulti* M) {
   if (!M) return 0;
-  NcclApi* N = nccl_api();
+  NcclApi* N = M->ndev > 1 ? nccl_api() : nullptr;
   for (size_t g = 0; g < M->h.size(); ++g) {
     if (M->h[g]) { cudaSetDevice(M->h[g]->device); if (g < M->d_send.size()) cudaFree(M->d_send[g]); if (g == 0) cudaFree(M->d_all); }
     if (N && g < M->comms.size() && M->comms[g]) N->CommDestroy(M->comms[g]);
@@ -1288,7 +1291,7 @@ extern "C" int cafe_gpu_multi_destroy(CafeMulti* M) {
 
 extern "C" int cafe_gpu_create_multi(const CafeDeck* deck, int ndev, const int* devices, int max_batch, CafeMulti** out) {
   if (!deck || !out || ndev <= 0 || max_batch <= 0) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
-  NcclApi* N = nccl_api();
+  NcclApi* N = ndev > 1 ? nccl_api() : nullptr;   // opened only when a collective is needed
   if (ndev > 1 && !N) { cafe::set_last_error("NCCL (libnccl.so.2) is not available"); return CAFE_ERR_UNSUPPORTED; }
   CafeMulti* M = new CafeMulti();
   M->ndev = ndev; M->max_batch = max_batch; M->per = (max_batch + ndev - 1) / ndev;
@@ -1344,7 +1347,7 @@ extern "C" int cafe_gpu_multi_get_info(CafeMulti* M, CafeInfo* info) {
 // the host: cmd = host [B][cafe_command_size(deck, n_gain_knots)]
 extern "C" int cafe_gpu_multi_get_commands(CafeMulti* M, int n_gain_knots, double* cmd) {
   if (!M || !cmd || n_gain_knots < 0 || M->B <= 0) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
-  NcclApi* N = nccl_api();
+  NcclApi* N = M->ndev > 1 ? nccl_api() : nullptr;
   const size_t rec = (size_t)cafe_command_size(&M->h[0]->deck, n_gain_knots);
   CafeHandle* H0 = M->h[0];
   CUDA_OK(cudaSetDevice(H0->device));

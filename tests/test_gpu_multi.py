@@ -8,6 +8,7 @@ import sys
 
 import numpy as np
 import pytest
+import torch  # noqa: F401  (before the solver library: the process then shares PyTorch's NCCL build, see cafe_gpu.h)
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
