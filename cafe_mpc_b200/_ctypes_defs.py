@@ -65,3 +65,4 @@ class Info(C.Structure):
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
+CAFE_STATUS_OK, CAFE_STATUS_REG_FAIL, CAFE_STATUS_DIVERGED = 0, 1, 2

@@ -4,6 +4,7 @@
 #include <exception>
 #include <string>
 #include "../../../include/cafe_gpu.h"
+#include "info_reader.h"
 #include "problem_builders.h"
 
 namespace cafe {
@@ -34,6 +35,26 @@ extern "C" int cafe_options_load(const char* fname, CafeOptions* out) {
   if (!fname || !out) { cafe::set_last_error("null argument"); return CAFE_ERR_ARG; }
   CAFE_TRY
   cafe::load_hsddp_setting(fname, *out);
+  return 0;
+  CAFE_CATCH(CAFE_ERR_IO)
+}
+
+// one key of a Boost-INFO settings file ("section.key"), for host code that mirrors the reference's load* helpers without Boost
+extern "C" int cafe_info_get_number(const char* fname, const char* key, double* out) {
+  if (!fname || !key || !out) { cafe::set_last_error("null argument"); return CAFE_ERR_ARG; }
+  CAFE_TRY
+  cafe::InfoFile pt(fname);
+  *out = pt.num(key);
+  return 0;
+  CAFE_CATCH(CAFE_ERR_IO)
+}
+extern "C" int cafe_info_get_string(const char* fname, const char* key, char* out, int cap) {
+  if (!fname || !key || !out || cap <= 0) { cafe::set_last_error("null argument"); return CAFE_ERR_ARG; }
+  CAFE_TRY
+  cafe::InfoFile pt(fname);
+  const std::string v = pt.str(key);
+  if ((int)v.size() + 1 > cap) { cafe::set_last_error("value longer than the buffer"); return CAFE_ERR_ARG; }
+  std::memcpy(out, v.c_str(), v.size() + 1);
   return 0;
   CAFE_CATCH(CAFE_ERR_IO)
 }
@@ -90,6 +111,44 @@ extern "C" int cafe_deck_build_loco(const char* reference_csv, const char* loco_
   *out = h;
   return 0;
   CAFE_CATCH(CAFE_ERR_IO)
+}
+
+// MHPCProblem<T>::set_problem_data(pdata, pconfig) + initialization with an MHPCConfig the caller holds in memory (loaded by
+// loadMHPCConfig and possibly edited, MHPCProblem.h:43-83, :198-212) instead of the name of its file
+extern "C" int cafe_deck_build_mhpc_config(const char* reference_csv, const CafeMHPCConfig* c, const char* settings_root, int k0, int loco,
+                                           CafeDeckHandle** out) {
+  if (!reference_csv || !c || !c->costFileName || !c->constraintParamFileName || !settings_root || !out) { cafe::set_last_error("null argument"); return CAFE_ERR_ARG; }
+  CAFE_TRY
+  CafeDeckHandle* h = new CafeDeckHandle();
+  try {
+    cafe::MHPCConfig cfg;
+    cfg.plan_dur_wb = (float)c->plan_dur_wb; cfg.plan_dur_srb = (float)c->plan_dur_srb; cfg.dt_mpc = c->dt_mpc;
+    cfg.dt_wb = (float)c->dt_wb; cfg.dt_srb = (float)c->dt_srb; cfg.BG_alpha = (double)c->BG_alpha; cfg.num_threads = 1;
+    cfg.costFileName = c->costFileName; cfg.constraintParamFileName = c->constraintParamFileName;
+    h->ref.load_top_level_data(reference_csv, false, k0);
+    cafe::MHPCProblem prob;
+    prob.loco = loco != 0;
+    prob.set_problem_data(&h->ref, cfg, settings_root);
+    prob.initialization(h->st);
+  } catch (...) { delete h; throw; }
+  *out = h;
+  return 0;
+  CAFE_CATCH(CAFE_ERR_IO)
+}
+
+// phase_start_times / phase_end_times of the problem data (MHPCProblemData::wb_phase_start_times, HKDProblemData::phase_start_times),
+// one pair per phase of the deck, seconds from the start of the plan
+extern "C" int cafe_deck_phase_times(const CafeDeckHandle* h, float* start_times, float* end_times) {
+  if (!h || !start_times || !end_times) { cafe::set_last_error("null argument"); return CAFE_ERR_ARG; }
+  const CafeDeck& d = h->st.deck;
+  float t = 0;
+  for (int i = 0; i < d.n_phases; ++i) {
+    const bool have = i < (int)h->st.phase_start_times.size() && i < (int)h->st.phase_end_times.size();
+    start_times[i] = have ? h->st.phase_start_times[i] : t;
+    end_times[i] = have ? h->st.phase_end_times[i] : t + (float)(d.phase[i].horizon * d.phase[i].dt);
+    t = end_times[i];
+  }
+  return 0;
 }
 
 extern "C" int cafe_deck_build_barrel_to(const char* cost_weights_json, const char* constraint_params_info, CafeDeckHandle** out) {

@@ -93,7 +93,7 @@ def check(rc):
 
 
 EXPORTED = [
-    "cafe_last_error", "cafe_options_load", "cafe_deck_build_hkd", "cafe_deck_build_mhpc", "cafe_deck_build_loco", "cafe_deck_build_barrel_to", "cafe_barrel_to_initial_guess", "cafe_deck_mark_mpc_update", "cafe_deck_get",
+    "cafe_last_error", "cafe_options_load", "cafe_info_get_number", "cafe_info_get_string", "cafe_deck_build_mhpc_config", "cafe_deck_phase_times", "cafe_deck_build_hkd", "cafe_deck_build_mhpc", "cafe_deck_build_loco", "cafe_deck_build_barrel_to", "cafe_barrel_to_initial_guess", "cafe_deck_mark_mpc_update", "cafe_deck_get",
     "cafe_deck_free", "cafe_hkd_state", "cafe_deck_lq_pattern", "cafe_solution_size", "cafe_command_size", "cafe_gpu_create",
     "cafe_gpu_destroy", "cafe_gpu_solve_batch", "cafe_gpu_solve_batch_device", "cafe_gpu_get_info",
     "cafe_gpu_get_history", "cafe_gpu_get_trace", "cafe_gpu_get_solution", "cafe_gpu_get_commands", "cafe_gpu_get_commands_device", "cafe_gpu_get_solve_ms",

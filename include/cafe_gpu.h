@@ -47,6 +47,10 @@ const char* cafe_last_error(void);
 
 /* ---- host-side problem setup ---- */
 int cafe_options_load(const char* ddp_setting_info, CafeOptions* out);
+/* one key ("section.key") of a Boost-INFO settings file, for host code that mirrors the reference's load* helpers
+ * (loadMHPCConfig, MHPCProblem.h:67-83) without Boost */
+int cafe_info_get_number(const char* info_file, const char* key, double* out);
+int cafe_info_get_string(const char* info_file, const char* key, char* out, int cap);
 /* reorder legs = true (HKD convention), k0 = number of leading reference samples to drop */
 int cafe_deck_build_hkd(const char* reference_csv, const char* constraint_params_info, float plan_duration,
                         float time_step, int nsteps_between_mpc, int k0, CafeDeckHandle** out);
@@ -60,6 +64,20 @@ int cafe_deck_build_mhpc(const char* reference_csv, const char* mhpc_config_info
  * phases carry the torque-limit and GRF barriers only (no joint-limit / min-height barrier), touchdown constraints as in MHPC. */
 int cafe_deck_build_loco(const char* reference_csv, const char* loco_config_info, const char* settings_root,
                          int k0, CafeDeckHandle** out);
+/* The same two builders from an MHPCConfig held in memory (the struct loadMHPCConfig fills, MHPCProblem.h:43-83; field types as there),
+ * i.e. MHPCProblem<T>::set_problem_data(pdata, pconfig) + prepare_initialization + initialize_parameters + initialize_multiPhaseProblem
+ * (MHPCProblem.h:198-212, MHPCProblem.cpp:13-250). loco != 0: LocoProblem's constraint set. Used by include/hsddp_facade/MHPCProblem.h. */
+typedef struct {
+  double plan_dur_wb, plan_dur_srb, dt_wb, dt_srb;
+  float dt_mpc, BG_alpha;
+  const char* costFileName;            /* relative to settings_root, as in mhpc_config.info */
+  const char* constraintParamFileName;
+} CafeMHPCConfig;
+int cafe_deck_build_mhpc_config(const char* reference_csv, const CafeMHPCConfig* config, const char* settings_root, int k0, int loco,
+                                CafeDeckHandle** out);
+/* start / end time of every phase of the deck in seconds from the start of the plan (MHPCProblemData::wb_phase_start_times /
+ * wb_phase_end_times, srb_start_time / srb_end_time; HKDProblemData::phase_start_times / phase_end_times): [n_phases] each */
+int cafe_deck_phase_times(const CafeDeckHandle* h, float* start_times, float* end_times);
 /* In-place barrel roll (MHPC/MHPC-Trajopt/BarrelRoll/BarrelRollTO.cpp:65-275): six hand-scheduled whole-body phases
  * (stance, right pair, flight, stance, flight, stance; switching times :70), per-phase weight sets from br_cost_weights.JSON, fixed
  * desired states (:277-339), the BarrelRoll:: barriers incl. the joint-speed limit (br_constraint_params.info), four-foot touchdown

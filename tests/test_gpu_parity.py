@@ -40,15 +40,15 @@ def test_single_hkd_solve_matches_oracle_and_golden(cm, hkd_problem, hkd_options
     assert [gi[k] for k in COUNTS] == [oi[k] for k in COUNTS]
     gh = s.get_history(256)[0, :gi["n_hist"]]
     np.testing.assert_allclose(gh[:, 0], oh[:, 0], rtol=RTOL)          # per-iteration cost
-    np.testing.assert_allclose(gh[:, 1:], oh[:, 1:], rtol=1e-7, atol=1e-12)  # feasibility / violations (values ~1e-5)
+    np.testing.assert_allclose(gh[:, 1:], oh[:, 1:], rtol=RTOL, atol=1e-13)  # feasibility / violations (values ~1e-5)
     gt = s.get_trace(256)[0, :gi["iter"]]
     assert np.array_equal(gt[:, 6:10], ot[:, 6:10])                     # reg iters, ls iters, success, accepted eps: exact
-    np.testing.assert_allclose(gt[:, 2:4], ot[:, 2:4], rtol=1e-8)       # expected cost change
+    np.testing.assert_allclose(gt[:, 2:4], ot[:, 2:4], rtol=RTOL, atol=1e-12)       # expected cost change
     gsol = s.get_solution()[0]
     gp, op = cm.unpack_solution(hkd_problem.deck, gsol), cm.unpack_solution(hkd_problem.deck, osol)
     for pg, po in zip(gp, op):
         for name in ("Xbar", "Ubar", "K", "dU", "Quu", "Qux", "G"):
-            assert relerr(pg[name], po[name]) < (RTOL if name in ("Xbar", "Ubar") else 1e-7), name
+            assert relerr(pg[name], po[name]) < RTOL, name
     g = np.load(os.path.join(REPO, "tests/golden/hkd_trot_nominal.npz"))
     assert [gi[k] for k in COUNTS] == list(g["counts"])
     np.testing.assert_allclose(gh[:, 0], g["hist"][:, 0], rtol=RTOL)
@@ -148,7 +148,7 @@ def test_full_size_batch_properties(cm, hkd_problem, hkd_options):
     for b in (0, 1, 511, 512, 1000, 1023):
         oi, _, _, _ = oracle_solve(hkd_problem.deck, hkd_options, x0[b])
         assert [i1[b][k] for k in COUNTS] == [oi[k] for k in COUNTS]
-        assert abs(i1[b]["cost"] - oi["cost"]) <= 1e-8 * abs(oi["cost"])
+        assert abs(i1[b]["cost"] - oi["cost"]) <= RTOL * abs(oi["cost"])
 
 
 def test_unsupported_options_fail_loudly(cm, hkd_problem, hkd_options):
@@ -203,7 +203,7 @@ def test_hkd_receding_horizon_chain_matches_oracle(cm, hkd_options):
             gp, op = cm.unpack_solution(p1.deck, sol1[b]), cm.unpack_solution(p1.deck, osol)
             for pg, po in zip(gp, op):
                 for name in ("Xbar", "Ubar", "K", "Quu", "Qux"):
-                    assert relerr(pg[name], po[name]) < (RTOL if name in ("Xbar", "Ubar") else 1e-7), (step, b, name)
+                    assert relerr(pg[name], po[name]) < RTOL, (step, b, name)
         if p1.single_shooting_phase >= 0:
             for b in range(B):
                 assert not np.any(s1.debug_get("Defect", p1.single_shooting_phase, b))
