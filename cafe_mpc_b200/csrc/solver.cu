@@ -54,6 +54,9 @@ struct CafeHandle {
   // on two streams, so that one half's kernels fill the wave tails of the other's (per-problem results do not depend on it)
   cudaStream_t stream2[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+  // linearisation of one part on two streams (k_lq | k_wb_derivs -> k_wb_sens, k_wb_cost): fork / derivatives-ready / join events per part
+  cudaEvent_t ev_lqf[2] = {nullptr, nullptr}, ev_lqd[2] = {nullptr, nullptr}, ev_lqj[2] = {nullptr, nullptr};
+  bool lq_overlap = true;   // CAFE_LQ_OVERLAP=0 keeps the linearisation on one stream
   int split_n = 2;       // number of parts (CAFE_SPLIT_N, 2..4)
   int split_min = 1024;  // smallest active list that is cut (CAFE_SPLIT_MIN; 0 = never)
   bool profiling = false;
@@ -64,6 +67,8 @@ struct CafeHandle {
   int bwd_variant = 0;  // 0: HKD deck (24,24,0)   1: MHPC deck (36,24->12,12)
   size_t bwd_smem = 0;
   int bwd_nt = 128;     // threads per problem of the MHPC sweep (dev switch CAFE_BWD_NT)
+  int bwd_small = 296;  // lists up to this length (one wave of two 256-thread CTAs per SM) are swept with 256 threads per problem: with the
+                        // machine under-filled the latency of one problem's sweep is what counts (CAFE_BWD_SMALL; 0 = never). Same bits either way.
   int bwd_pb = 4;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evs = nullptr, eve = nullptr;
   double total_ms = 0;
@@ -311,7 +316,7 @@ int launch_bwd(CafeHandle* H, int first = 0, int n_list = -1, cudaStream_t st = 
   SolverDev S = H->S;   // the kernel's descriptor: entries [first, first + n_list) of the active list
   S.c.act_list += first; S.n_act = n_list;
   if (H->bwd_variant == 0) k_bwd2<0, 128><<<grid, 128, H->bwd_smem, st>>>(S);
-  else if (H->bwd_nt == 256) k_bwd2<1, 256><<<grid, 256, H->bwd_smem, st>>>(S);
+  else if (H->bwd_nt == 256 || n_list <= H->bwd_small) k_bwd2<1, 256><<<grid, 256, H->bwd_smem, st>>>(S);
   else k_bwd2<1, 128><<<grid, 128, H->bwd_smem, st>>>(S);
   return 0;
 }
@@ -429,6 +434,8 @@ extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, 
   CUDA_OK_H(cudaStreamCreate(&H->stream));
   for (int i = 0; i < 3; ++i) { CUDA_OK_H(cudaStreamCreate(&H->stream2[i])); CUDA_OK_H(cudaEventCreateWithFlags(&H->ev_join[i], cudaEventDisableTiming)); }
   CUDA_OK_H(cudaEventCreateWithFlags(&H->ev_fork, cudaEventDisableTiming));
+  for (int i = 0; i < 2; ++i) { CUDA_OK_H(cudaEventCreateWithFlags(&H->ev_lqf[i], cudaEventDisableTiming)); CUDA_OK_H(cudaEventCreateWithFlags(&H->ev_lqd[i], cudaEventDisableTiming)); CUDA_OK_H(cudaEventCreateWithFlags(&H->ev_lqj[i], cudaEventDisableTiming)); }
+  if (const char* e = getenv("CAFE_LQ_OVERLAP")) H->lq_overlap = atoi(e) != 0;
   if (const char* e = getenv("CAFE_SPLIT_MIN")) H->split_min = atoi(e);
   if (const char* e = getenv("CAFE_SPLIT_N")) { H->split_n = atoi(e); if (H->split_n < 2) H->split_n = 2; if (H->split_n > 4) H->split_n = 4; }
   CUDA_OK_H(cudaEventCreate(&H->ev0));
@@ -447,6 +454,7 @@ extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, 
     CUDA_OK_H(cudaFuncSetAttribute(cafe_dev::k_bwd2<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H->bwd_smem));
     CUDA_OK_H(cudaFuncSetAttribute(cafe_dev::k_bwd2<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H->bwd_smem));
     if (const char* e = std::getenv("CAFE_BWD_NT")) H->bwd_nt = std::atoi(e) == 256 ? 256 : 128;
+    if (const char* e = std::getenv("CAFE_BWD_SMALL")) H->bwd_small = std::atoi(e);
   }
   if (!all_hkd && cafe_dev::wb_coop_configure() != 0) { cafe::set_last_error("cudaFuncSetAttribute (cooperative whole-body kernels) failed"); cafe_gpu_destroy(H); return CAFE_ERR_CUDA; }
   // Thread-local arrays survive only in the terminal-knot code of the whole-body model (impact map and its Jacobian) and in the
@@ -474,6 +482,7 @@ extern "C" int cafe_gpu_destroy(CafeHandle* H) {
   if (H->stream) cudaStreamDestroy(H->stream);
   for (int i = 0; i < 3; ++i) { if (H->stream2[i]) cudaStreamDestroy(H->stream2[i]); if (H->ev_join[i]) cudaEventDestroy(H->ev_join[i]); }
   if (H->ev_fork) cudaEventDestroy(H->ev_fork);
+  for (int i = 0; i < 2; ++i) { if (H->ev_lqf[i]) cudaEventDestroy(H->ev_lqf[i]); if (H->ev_lqd[i]) cudaEventDestroy(H->ev_lqd[i]); if (H->ev_lqj[i]) cudaEventDestroy(H->ev_lqj[i]); }
   if (H->ev0) cudaEventDestroy(H->ev0);
   if (H->ev1) cudaEventDestroy(H->ev1);
   if (H->evs) cudaEventDestroy(H->evs);
@@ -544,15 +553,22 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
       run(CAFE_K_WB_FWD, [&] { cafe_dev::launch_wb_fwd(H->dS, n_wbk, sq, a0, a1, list, n_list); });
     }
   };
-  auto lq_group = [&](cudaStream_t sq, const int* list, int n_list, bool tm) {
+  // sb != sq: the thread-per-knot kernel (SRB / HKD / terminal knots: one long dependent chain per thread, latency bound) and the cost
+  // partials of the whole-body knots run on the companion stream sb beside derivatives -> sensitivities on sq (slot e of the event arrays);
+  // k_wb_cost and k_wb_sens both read the derivative pack, nothing else is shared between the two chains
+  auto lq_group = [&](cudaStream_t sq, cudaStream_t sb, int e, const int* list, int n_list, bool tm) {
     auto run = [&](int slot, auto&& f) { if (tm) timed(H, slot, f); else { f(); H->launches[slot]++; } };
-    run(CAFE_K_LQ, [&] { cafe_dev::launch_lq(H->dS, S.n_knots, sq, list, n_list); });
     H->units[CAFE_K_LQ] += (double)n_list * S.n_knots; H->units[CAFE_K_BWD] += (double)n_list;
     H->units[CAFE_K_WB_DERIVS] += (double)n_list * n_wbk; H->units[CAFE_K_WB_SENS] += (double)n_list * n_wbk; H->units[CAFE_K_WB_COST] += (double)n_list * n_wbk;
+    const bool two = sb != sq && n_wbk > 0;
+    if (two) { cudaEventRecord(H->ev_lqf[e], sq); cudaStreamWaitEvent(sb, H->ev_lqf[e], 0); }
+    run(CAFE_K_LQ, [&] { cafe_dev::launch_lq(H->dS, S.n_knots, two ? sb : sq, list, n_list); });
     if (n_wbk > 0) {
       run(CAFE_K_WB_DERIVS, [&] { cafe_dev::launch_wb_derivs(H->dS, n_wbk, sq, list, n_list); });
+      if (two) { cudaEventRecord(H->ev_lqd[e], sq); cudaStreamWaitEvent(sb, H->ev_lqd[e], 0); }
       run(CAFE_K_WB_SENS, [&] { cafe_dev::launch_wb_sens(H->dS, n_wbk, sq, list, n_list); });
-      run(CAFE_K_WB_COST, [&] { cafe_dev::launch_wb_cost(H->dS, n_wbk, sq, list, n_list); });
+      run(CAFE_K_WB_COST, [&] { cafe_dev::launch_wb_cost(H->dS, n_wbk, two ? sb : sq, list, n_list); });
+      if (two) { cudaEventRecord(H->ev_lqj[e], sb); cudaStreamWaitEvent(sq, H->ev_lqj[e], 0); }
     }
   };
   // ---- initial rollout (eps = 0) and bookkeeping
@@ -591,14 +607,16 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
         if (cnt <= 0) break;
         cudaStream_t sq = q == 0 ? st : H->stream2[q - 1];
         if (q > 0) CUDA_OK(cudaStreamWaitEvent(sq, H->ev_fork, 0));
-        lq_group(sq, lst + first, cnt, false);
+        // companion streams: part 0 -> stream2[1], part 1 -> stream2[2] (two parts); more parts keep one stream each
+        cudaStream_t sb = (H->lq_overlap && np == 2) ? H->stream2[1 + q] : sq;
+        lq_group(sq, sb, q & 1, lst + first, cnt, false);
         launch_bwd(H, first, cnt, sq);
         H->launches[CAFE_K_BWD]++;
         roll_group(sq, 0, a1_first, lst + first, cnt, false);
         if (q > 0) { CUDA_OK(cudaEventRecord(H->ev_join[q - 1], sq)); CUDA_OK(cudaStreamWaitEvent(st, H->ev_join[q - 1], 0)); }
       }
     } else {
-      lq_group(st, S.c.act_list, n_act, true);
+      lq_group(st, (H->lq_overlap && !H->profiling) ? H->stream2[0] : st, 0, S.c.act_list, n_act, true);
       timed(H, CAFE_K_BWD, [&] { launch_bwd(H); });
     }
     // staged line search: step sizes are evaluated in growing groups; most problems accept one of the first
