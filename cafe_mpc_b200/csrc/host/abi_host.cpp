@@ -122,8 +122,8 @@ extern "C" int cafe_deck_build_mhpc_config(const char* reference_csv, const Cafe
   CafeDeckHandle* h = new CafeDeckHandle();
   try {
     cafe::MHPCConfig cfg;
-    cfg.plan_dur_wb = (float)c->plan_dur_wb; cfg.plan_dur_srb = (float)c->plan_dur_srb; cfg.dt_mpc = c->dt_mpc;
-    cfg.dt_wb = (float)c->dt_wb; cfg.dt_srb = (float)c->dt_srb; cfg.BG_alpha = (double)c->BG_alpha; cfg.num_threads = 1;
+    cfg.plan_dur_wb = c->plan_dur_wb; cfg.plan_dur_srb = c->plan_dur_srb; cfg.dt_mpc = c->dt_mpc;
+    cfg.dt_wb = c->dt_wb; cfg.dt_srb = c->dt_srb; cfg.BG_alpha = (double)c->BG_alpha; cfg.num_threads = 1;
     cfg.costFileName = c->costFileName; cfg.constraintParamFileName = c->constraintParamFileName;
     h->ref.load_top_level_data(reference_csv, false, k0);
     cafe::MHPCProblem prob;

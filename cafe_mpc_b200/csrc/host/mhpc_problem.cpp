@@ -31,11 +31,11 @@ void wb_lxx_pattern(const double* rec, unsigned long long out[21]) {
 
 void loadMHPCConfig(const std::string& fname, MHPCConfig& c) {
   InfoFile pt(fname);
-  c.plan_dur_wb = (float)pt.num("config.plan_dur_wb");  // the config fields are floats (MHPCProblem.h:45-57)
-  c.plan_dur_srb = (float)pt.num("config.plan_dur_srb");
-  c.dt_mpc = (float)pt.num("config.dt_mpc");
-  c.dt_wb = (float)pt.num("config.dt_wb");
-  c.dt_srb = (float)pt.num("config.dt_srb");
+  c.plan_dur_wb = pt.num("config.plan_dur_wb");  // doubles (MHPCProblem.h:25-35): the whole-body and SRB time steps reach the dynamics,
+  c.plan_dur_srb = pt.num("config.plan_dur_srb");  // the costs and the trajectories as 0.01 and 0.05 exactly, not float-rounded
+  c.dt_mpc = (float)pt.num("config.dt_mpc");     // float (MHPCProblem.h:38)
+  c.dt_wb = pt.num("config.dt_wb");
+  c.dt_srb = pt.num("config.dt_srb");
   c.BG_alpha = (double)(float)pt.num("config.BG_alpha");
   c.num_threads = pt.integer("config.nthreads");
   c.referenceFileName = pt.str("config.referenceFile");
@@ -47,7 +47,7 @@ void MHPCProblem::set_problem_data(QuadReference* quad_ref, const MHPCConfig& co
   quad_reference = quad_ref;
   pconfig = config;
   root = settings_root;
-  plan_dur_all = config.plan_dur_wb + config.plan_dur_srb;  // MHPCProblem.h:209
+  plan_dur_all = (float)(config.plan_dur_wb + config.plan_dur_srb);  // MHPCProblem.h:209 (a float member)
 }
 
 static CafeRebParam reb_params(const InfoFile& pt, const std::string& t) { return CafeRebParam{pt.num(t + "_ReB.delta"), pt.num(t + "_ReB.delta_min"), pt.num(t + "_ReB.eps")}; }
@@ -103,13 +103,13 @@ void MHPCProblem::initialization(DeckStorage& out) {
         for (int l = 0; l < 4; ++l) contact_prev[l] = contact_cur[l];
         start = end;
       }
-      t += pconfig.dt_wb;
+      t = (float)(t + pconfig.dt_wb);   // float t += double
     }
   }
   int n_srb = 0, srb_h = 0;
   float srb_start = 0;
   if (pconfig.plan_dur_srb > 1e-5) {
-    srb_start = pconfig.plan_dur_wb;
+    srb_start = (float)pconfig.plan_dur_wb;
     srb_h = (int)std::round(pconfig.plan_dur_srb / pconfig.dt_srb);
     n_srb = srb_h > 0 ? 1 : 0;
   }
@@ -135,7 +135,7 @@ void MHPCProblem::initialization(DeckStorage& out) {
   /* ---- WB phases (MHPCProblem.cpp:176-217, :403-601) */
   for (int i = 0; i < n_wb; ++i) {
     CafePhase& ph = deck.phase[i];
-    ph.dt = (double)pconfig.dt_wb;
+    ph.dt = pconfig.dt_wb;   // Trajectory<T>(pconfig->dt_wb, h): T timeStep, the dt of dynamics and costs (MHPCProblem.cpp:183, :410)
     ph.t_offset = out.phase_start_times[i] - out.phase_start_times[0];
     ph.has_reset = 1;
     if (i < n_wb - 1) for (int l = 0; l < 4; ++l) ph.next_contact[l] = deck.phase[i + 1].contact[l];
@@ -169,7 +169,7 @@ void MHPCProblem::initialization(DeckStorage& out) {
     for (int j = 0; j < 3; ++j) { ph.joint_lb[j] = lb[j]; ph.joint_ub[j] = ub[j]; }
     for (int k = 0; k <= ph.horizon; ++k) {
       float t_cost = (float)((double)ph.t_offset + (double)k * ph.dt);
-      float t_init = out.phase_start_times[i] + k * pconfig.dt_wb;
+      float t_init = (float)(out.phase_start_times[i] + k * pconfig.dt_wb);
       if (quad_reference->index_at_t(t_cost) != quad_reference->index_at_t(t_init)) throw std::runtime_error("reference index mismatch (WB)");
       fill_wb_record(&out.ref[(size_t)(ph.knot_offset + k) * CAFE_REF_W], *quad_reference->get_a_reference_ptr_at_t(t_cost));
     }
@@ -177,7 +177,7 @@ void MHPCProblem::initialization(DeckStorage& out) {
   /* ---- SRB phase (MHPCProblem.cpp:219-249, :487-521) */
   if (n_srb) {
     CafePhase& ph = deck.phase[n_wb];
-    ph.dt = (double)pconfig.dt_srb;
+    ph.dt = pconfig.dt_srb;
     ph.t_offset = srb_start;
     ph.has_reset = 0;
     ph.next_model = -1;
@@ -190,7 +190,7 @@ void MHPCProblem::initialization(DeckStorage& out) {
     ph.h_min = 0.18;  // MHPCConstraint.h:199
     for (int k = 0; k <= ph.horizon; ++k) {
       float t_cost = (float)((double)ph.t_offset + (double)k * ph.dt);
-      float t_init = srb_start + k * pconfig.dt_srb;
+      float t_init = (float)(srb_start + k * pconfig.dt_srb);
       if (quad_reference->index_at_t(t_cost) != quad_reference->index_at_t(t_init)) throw std::runtime_error("reference index mismatch (SRB)");
       fill_srb_record(&out.ref[(size_t)(ph.knot_offset + k) * CAFE_REF_W], *quad_reference->get_a_reference_ptr_at_t(t_cost));
     }
@@ -237,7 +237,7 @@ void build_barrel_to_deck(const std::string& cost_json, const std::string& const
   CafeDeck& deck = out.deck;
   std::memset(&deck, 0, sizeof(deck));
   out.phase_start_times.clear(); out.phase_end_times.clear();
-  const double dt = 0.01;  // BarrelRollTO.cpp:68 (a double here, not the float of mhpc_config.info)
+  const double dt = 0.01;  // BarrelRollTO.cpp:68
   deck.n_phases = 6;
   deck.BG_alpha = 10.0;    // :89
   deck.hip_yaw = 3.1415;

@@ -44,9 +44,10 @@ class HKDProblem {  // HKDProblem.h:93-168
   CafeAlParam td_al_param{};
 };
 
-struct MHPCConfig {  // MHPCProblem.h:43-65
-  float plan_dur_wb, plan_dur_srb, dt_mpc, dt_wb, dt_srb;
-  double BG_alpha;
+struct MHPCConfig {  // MHPCProblem.h:23-65: the four plan durations / time steps are doubles, dt_mpc and BG_alpha floats
+  double plan_dur_wb, plan_dur_srb, dt_wb, dt_srb;
+  float dt_mpc;
+  double BG_alpha;     // (double)(float) of the file's value
   int num_threads;
   std::string referenceFileName, costFileName, constraintParamFileName;
 };

@@ -37,7 +37,7 @@ def test_mhpc_phase_schedule_golden(mhpc):
     assert [tuple(p.contact) for p in ph[:2]] == [(1, 1, 1, 1), (0, 1, 1, 0)]
     assert [p.next_model for p in ph] == [1, 2, -1]
     assert [p.n_td for p in ph] == [0, 0, 0]
-    assert ph[0].dt == float(np.float32(0.01)) and ph[2].dt == float(np.float32(0.05))
+    assert ph[0].dt == 0.01 and ph[2].dt == 0.05          # doubles in MHPCConfig (MHPCProblem.h:25-35), unlike the HKD float time step
     assert ph[2].t_offset == 0.25
     d = mhpc.deck.contents
     assert d.BG_alpha == 10.0 and d.hip_yaw == 3.1415 and d.n_records == 12 + 15 + 11
@@ -498,3 +498,45 @@ def test_oracle_barrel_to_matches_committed_golden(cm):
     np.testing.assert_allclose(hist[:, 0], g["hist_0"][:, 0], rtol=1e-9)
     np.testing.assert_allclose(sol, g["sol_0"], rtol=0, atol=1e-8 * np.abs(sol).max())
     assert hist[-1, 0] < 0.05 * hist[0, 0]   # 3 635 -> 125: the roll is being found
+
+
+# ------------------------------------------------------------------ the deck against an independent reader of the input files
+@pytest.mark.parametrize("k0", [0, 8, 12, 20, 36])
+def test_mhpc_deck_equals_an_independent_reading_of_the_input_files(cm, k0):
+    """Every field of every CafePhase and every per-knot reference record of the MHPC trot deck equals what tests/deck_check.py derives
+    from quad_reference.csv / mhpc_config.info / cost_weights / constraint_params by following the reference's set-up code with the
+    reference's float / double types (no code shared with csrc/host or oracle/): a wrong weight, reference index, ReB / AL parameter,
+    touchdown foot or time step in the deck builders fails here, where the GPU-vs-oracle tests (same deck on both sides) cannot see it."""
+    from deck_check import expected_mhpc_deck
+    root = os.path.join(REPO, "data")
+    exp = expected_mhpc_deck(CSV, os.path.join(root, "MHPC/settings/mhpc_config.info"), root, k0)
+    prob = cm.MHPCProblem(CSV, k0=k0)
+    d = prob.deck.contents
+    assert d.n_phases == len(exp)
+    ref = prob.reference_records()
+    off = 0
+    for i, e in enumerate(exp):
+        p = d.phase[i]
+        n, m = (36, 12) if e["model"] == 1 else (12, 12)
+        assert (p.model, p.horizon, p.knot_offset, p.next_model) == (e["model"], e["horizon"], off, e["next_model"]), i
+        assert p.dt == e["dt"] and p.t_offset == float(e["t_offset"])
+        assert tuple(p.contact) == e["contact"] and tuple(p.next_contact) == tuple(e["next_contact"])
+        assert p.n_td == len(e["td_foot"]) and list(p.td_foot)[:p.n_td] == e["td_foot"]
+        assert list(p.q)[:n] == [float(v) for v in e["q"]] and list(p.qf)[:n] == [float(v) for v in e["qf"]] and list(p.r)[:m] == e["r"]
+        for name, val in e["reb"].items():
+            r = getattr(p, name)
+            assert (r.delta, r.delta_min, r.eps) == val, (i, name)
+        if e["model"] == 1:
+            assert list(p.w_footreg) == e["w_footreg"] and list(p.w_swingpos) == e["w_swingpos"] and list(p.w_swingvel) == e["w_swingvel"]
+            assert (p.al_td.lambda_, p.al_td.sigma, p.al_td.sigma_max) == e["al_td"]
+            assert p.has_reset == 1 and (p.mu, p.h_min, p.torque_limit) == (0.6, 0.20, 17.0)     # MHPCConstraint.cpp:11,77; MHPCConstraint.h:148
+        else:
+            assert p.has_reset == 0 and p.h_min == 0.18                                            # MHPCConstraint.h:199
+        for k, r in enumerate(e["records"]):
+            g = ref[off + k]
+            assert np.array_equal(g[0:n], r["xr"]), (i, k)
+            assert np.array_equal(g[36:36 + 12], r["ur"]) and np.array_equal(g[60:60 + len(r["yr"])], r["yr"])
+            assert np.array_equal(g[72:84], r["pf"]) and np.array_equal(g[84:87], r["pcom"]) and np.array_equal(g[87:99], r["vf"])
+            assert np.array_equal(g[99:103], r["contact"]) and np.array_equal(g[103:115], r["qJ"])
+        off += e["horizon"] + 1
+    assert d.n_records == off
