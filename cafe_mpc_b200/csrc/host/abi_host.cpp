@@ -180,6 +180,18 @@ extern "C" int cafe_deck_mark_mpc_update(CafeDeckHandle* h, int nsteps, int* mar
   // MHPCProblem.cpp:366-369: every phase but a tail phase not longer than the shift gets update_SS_config(h + 1); a tail phase that
   // short was opened by this very update (an older one has grown past nsteps), its SS_set is still empty (SinglePhase.cpp:34)
   if (d.phase[last].horizon <= nsteps) { d.phase[last].single_shooting = 1; *marked_phase = last; }
+  // In the update path a phase receives its touchdown constraint (and, whole-body, the touchdown-velocity penalty that comes with it) only once the
+  // contact change has reached the tail of the plan: add_tconstr_one_phase is called when the knot appended to the last phase carries a new contact
+  // (MHPCProblem.cpp:346-350, HKDProblem.cpp:186-196), whereas initialization() attaches it from the look-ahead contact at plan end + dt_mpc
+  // (:533-537). A tail phase whose terminal record still shows its own contact has therefore none yet; its reset map does use the look-ahead
+  // contact (update_resetmap runs for every phase on every update, :357).
+  {
+    CafePhase& p = d.phase[last];
+    const double* r = d.ref + ((size_t)p.knot_offset + p.horizon) * CAFE_REF_W + CAFE_REF_CONTACT;
+    bool change = false;
+    for (int l = 0; l < 4; ++l) change |= ((r[l] > 0) != (p.contact[l] > 0));
+    if (!change) p.n_td = 0;
+  }
   return 0;
 }
 

@@ -540,3 +540,49 @@ def test_mhpc_deck_equals_an_independent_reading_of_the_input_files(cm, k0):
             assert np.array_equal(g[99:103], r["contact"]) and np.array_equal(g[103:115], r["qJ"])
         off += e["horizon"] + 1
     assert d.n_records == off
+
+
+# ------------------------------------------------------------------ the MPC update against an independent restatement of the reference's deque operations
+def test_mpc_update_chain_equals_an_independent_restatement_of_the_reference_update(cm):
+    """Forty consecutive MPC updates (start offsets 0, 2, ... 80: phases vanish at the front, grow and open at the tail) walked with
+    tests/update_check.py - the reference's own sequence of deque operations (MHPCProblem::update / update_WB_plan, QuadReference::step,
+    Trajectory::pop_front / push_back_state, quirk 14), no code shared with the product - against the three product pieces that stand for it:
+    the deck re-cut at the new start offset (cafe_deck_build_mhpc + cafe_deck_mark_mpc_update: horizons, contacts, touchdown feet, which tail
+    phase is single shooting) and the shifted guess (cafe_mpc_b200/mpc.py, which the device shift is held bit-identical to by the GPU tests)."""
+    from cafe_mpc_b200 import mpc
+    from update_check import MHPCPlan
+    root = os.path.join(REPO, "data")
+    plan = MHPCPlan(CSV, os.path.join(root, "MHPC/settings/mhpc_config.info"), root, 0)
+    rng = np.random.default_rng(7)
+    prev, k_prev = cm.MHPCProblem(CSV, k0=0), 0
+    opened = removed = 0
+    for step in range(40):
+        # a tagged "solution" of the previous problem (random numbers: every knot recognisable)
+        old = []
+        for ph in prev.phases():
+            n, m = (36, 12) if ph.model == 1 else (12, 12)
+            old.append({"Xbar": rng.standard_normal((ph.horizon + 1, n)), "Ubar": rng.standard_normal((ph.horizon, m)), "K": rng.standard_normal((ph.horizon, m, n))})
+        plan.load_solution(old)
+        n_before = len(plan.horizon)
+        nsteps = plan.update()
+        assert nsteps == 2
+        k_new = k_prev + nsteps
+        new = cm.MHPCProblem(CSV, k0=k_new, mpc_update_nsteps=nsteps)
+        wb = [p for p in new.phases() if p.model == 1]
+        assert [p.horizon for p in wb] == plan.horizon, (k_new, [p.horizon for p in wb], plan.horizon)
+        assert [tuple(p.contact) for p in wb] == plan.contact
+        for i, p in enumerate(wb):
+            assert tuple(list(p.td_foot)[:p.n_td]) == plan.touchdown_feet(i), (k_new, i)
+            assert bool(p.single_shooting) == (not plan.has_ss[i]), (k_new, i)
+        removed += len(plan.horizon) < n_before or (len(plan.horizon) == n_before and not plan.has_ss[-1])
+        opened += not plan.has_ss[-1]
+        g = mpc.shift_guess(prev, k_prev, new, k_new, old)
+        for i in range(len(wb)):
+            if not plan.has_ss[i]:
+                continue                         # freshly opened phase: no shooting states, its Xbar is never read (mpc.py header)
+            np.testing.assert_array_equal(g[i]["Xbar"], np.array(plan.X[i]), err_msg="X %d %d" % (k_new, i))
+            np.testing.assert_array_equal(g[i]["Ubar"], np.array(plan.U[i]))
+            np.testing.assert_array_equal(g[i]["K"], np.array(plan.K[i][:-1]))
+        np.testing.assert_array_equal(g[len(wb)]["Xbar"], old[-1]["Xbar"])       # update_SRB_plan: nsteps = 0, the SRB arrays stay
+        prev, k_prev = new, k_new
+    assert opened >= 3 and removed >= 3

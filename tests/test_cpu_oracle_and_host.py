@@ -336,3 +336,42 @@ def test_hkd_receding_horizon_shift_and_single_shooting_tail(cm, hkd_options):
     assert oracle_get("Defect", 3).any() and iw["cost"] != im["cost"]
     ic, _, _, _ = oracle_solve(p1.deck, ort, x1)
     assert iw["iter"] <= 2 and iw["feas"] < 0.05 * ic["feas"]
+
+
+def test_hkd_mpc_update_chain_equals_an_independent_restatement_of_the_reference_update(cm):
+    """Forty consecutive HKD MPC updates (start offsets 0, 2, ... 80) walked with tests/update_check.py::HKDPlan - the reference's own deque
+    operations (HKDProblem.cpp:117-222), no code shared with the product - against the deck re-cut at the new offset (cafe_deck_build_hkd +
+    cafe_deck_mark_mpc_update: horizons, contacts, touchdown feet, the single-shooting tail) and the shifted guess of cafe_mpc_b200/mpc.py."""
+    from cafe_mpc_b200 import mpc
+    from update_check import HKDPlan
+    csv = os.path.join(REPO, "data/Reference/Data/trot/heuristic/quad_reference.csv")
+    prev, k_prev = cm.HKDProblem(csv, k0=0), 0
+    ph0 = prev.phases()
+    plan = HKDPlan(csv, 0, 0.6, 0.01, 2, [p.horizon for p in ph0], [tuple(p.contact) for p in ph0], [tuple(list(p.td_foot)[:p.n_td]) for p in ph0])
+    rng = np.random.default_rng(11)
+    opened = removed = 0
+    for step in range(40):
+        old = [{"Xbar": rng.standard_normal((p.horizon + 1, 24)), "Ubar": rng.standard_normal((p.horizon, 24)), "K": rng.standard_normal((p.horizon, 24, 24))}
+               for p in prev.phases()]
+        plan.load_solution(old)
+        n_before = len(plan.horizon)
+        plan.update()
+        k_new = k_prev + 2
+        new = cm.HKDProblem(csv, k0=k_new, mpc_update=True)
+        ph = new.phases()
+        assert [p.horizon for p in ph] == plan.horizon, (k_new, [p.horizon for p in ph], plan.horizon)
+        assert [tuple(p.contact) for p in ph] == plan.contact
+        for i, p in enumerate(ph):
+            assert tuple(list(p.td_foot)[:p.n_td]) == plan.td[i], (k_new, i)
+            assert bool(p.single_shooting) == (not plan.has_ss[i]), (k_new, i)
+        opened += not plan.has_ss[-1]
+        removed += len(plan.horizon) < n_before + (not plan.has_ss[-1])
+        g = mpc.shift_guess(prev, k_prev, new, k_new, old)
+        for i in range(len(ph)):
+            if not plan.has_ss[i]:
+                continue
+            np.testing.assert_array_equal(g[i]["Xbar"], np.array(plan.X[i]), err_msg="X %d %d" % (k_new, i))
+            np.testing.assert_array_equal(g[i]["Ubar"], np.array(plan.U[i]), err_msg="U %d %d" % (k_new, i))
+            np.testing.assert_array_equal(g[i]["K"], np.array(plan.K[i][:-1]))
+        prev, k_prev = new, k_new
+    assert opened >= 3 and removed >= 3

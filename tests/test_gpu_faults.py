@@ -85,22 +85,24 @@ def test_regularisation_beyond_1e2_gives_up_like_the_oracle(cm, setup):
 
 
 def test_far_initial_state_matches_the_oracle(cm, setup):
-    """an initial state 1 km from the plan: large search directions, full steps are rejected by the merit test, small ones accepted.
-    (Further out - 1e4 and beyond - the solve is numerically chaotic: absolute positions of 1e4 leave 1e-12 for the leg kinematics and
-    differences of that size grow to O(1) in three iterations, in the oracle as well as here, so no two implementations agree there.)"""
+    """an initial state 1 km from the plan: large search directions, full steps are rejected by the merit test, small ones accepted
+    (6, 5 and 4 trials in the first three iterations). Absolute positions of 1e3 leave 1e-13 for the leg kinematics and differences
+    of that size grow by an order of magnitude per iteration (1e-9 in the third, 1e-4 in the sixth, where they start to flip
+    regularisation decisions - further out, at 1e4, within three iterations): the comparison stops after three iterations."""
     from cafe_mpc_b200 import workload
     prob, opt = setup
+    opt = copy.copy(opt); opt.max_AL_iter = 1; opt.max_DDP_iter = 3
     x0 = workload.mhpc_batch(3)
     x0[:, 0] += 1e3
     s = _solve(cm, prob, opt, x0)
     info = s.get_solver_info(); hist = s.get_history(64); trace = s.get_trace(64)
     for b in range(3):
         oi, oh, ot, _ = oracle_solve(prob.deck, opt, x0[b])
+        assert oi["ls_iter_total"] >= 12                                        # full steps were rejected
         assert [info[b][k] for k in COUNTS] == [oi[k] for k in COUNTS], b
         n = oi["iter"]
         assert np.array_equal(trace[b, :n, 6:10], ot[:n, 6:10])
-        np.testing.assert_allclose(hist[b, :3, 0], oh[:3, 0], rtol=1e-9)          # before the amplification sets in
-        np.testing.assert_allclose(hist[b, :oi["n_hist"], 0], oh[:, 0], rtol=2e-3)
+        np.testing.assert_allclose(hist[b, :oi["n_hist"], 0], oh[:, 0], rtol=1e-7)
 
 
 @pytest.mark.parametrize("off,n_ls", [(4e7, 7), (1e8, 8)])
