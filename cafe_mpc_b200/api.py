@@ -229,6 +229,12 @@ class MultiPhaseDDP:
         offset k0) on the device - the receding-horizon update of MHPCProblem::update without a host round trip."""
         check(lib.cafe_gpu_shift_guess(self._h, prev._h, prev_k0, k0, self.B if B is None else B))
 
+    def update_deck(self, problem, k_advance, B=None):
+        """The MPC update on this solver (cafe_gpu_update_deck): `problem` (the deck re-cut k_advance knots later) replaces the current one,
+        the previous solution becomes the warm start, device buffers are re-used. B = 0: cold start on the new deck."""
+        check(lib.cafe_gpu_update_deck(self._h, problem.deck, k_advance, self.B if B is None else B))
+        self.problem = problem
+
     def planned_state(self, knots_ahead):
         """[B, n] planned state `knots_ahead` knots after the start of the plan."""
         n = MODEL_DIMS[self.problem.phases()[0].model][0]
@@ -236,9 +242,12 @@ class MultiPhaseDDP:
         check(lib.cafe_gpu_get_planned_state(self._h, knots_ahead, out.ctypes.data_as(C.c_void_p)))
         return out
 
-    def get_lcm_commands(self, n_steps=8):
-        """float32 MHPC_Command_lcmt record per problem (see include/cafe_gpu.h); use unpack_lcm_command to name the fields."""
-        out = np.zeros((self.B, lib.cafe_lcm_command_size(n_steps)), dtype=np.float32)
+    def get_lcm_commands(self, n_steps=8, out=None):
+        """float32 MHPC_Command_lcmt record per problem (see include/cafe_gpu.h); use unpack_lcm_command to name the fields.
+        out: caller's [B, cafe_lcm_command_size] float32 buffer (page-locked memory makes the copy several times faster)."""
+        if out is None:
+            out = np.zeros((self.B, lib.cafe_lcm_command_size(n_steps)), dtype=np.float32)
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.shape == (self.B, lib.cafe_lcm_command_size(n_steps))
         check(lib.cafe_gpu_get_lcm_commands(self._h, n_steps, out.ctypes.data_as(C.c_void_p)))
         return out
 

@@ -5,6 +5,7 @@
 //     k_lq -> k_bwd (sweep + linear rollout + merit parameter) -> k_roll (all step sizes at once)
 //          -> k_select (Armijo over step sizes, exits, AL update) -> k_accept
 // Per-problem control state lives on the device; the host only polls one counter per tick.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -49,6 +50,10 @@ struct CafeHandle {
   int* h_nactive = nullptr;  // pinned
   double* d_pack = nullptr; size_t pack_bytes = 0;
   PackSeg* d_segs = nullptr; int max_segs = 0;
+  // small host tables for the pack / unpack / shift kernels: one growable device buffer + one pinned staging buffer per handle, copies
+  // stream-ordered on `stream` (no allocation, no host synchronisation in the MPC loop)
+  char* d_tab = nullptr; char* h_tab = nullptr; size_t tab_cap = 0; cudaEvent_t ev_tab = nullptr; bool tab_busy = false;
+  size_t ref_cap = 0, lxx_mask_cap = 0, ref_pp_cap = 0;   // capacities (elements) of d_ref / d_lxx_mask: cafe_gpu_update_deck re-uses them
   cudaStream_t stream = nullptr;
   // second stream of a tick: the active list is cut in two and the LQ -> dense -> sweep -> first rollout chains of the halves run
   // on two streams, so that one half's kernels fill the wave tails of the other's (per-problem results do not depend on it)
@@ -334,14 +339,32 @@ int launch_bwd(CafeHandle* H, int first = 0, int n_list = -1, cudaStream_t st = 
     }                                                                                        \
   } while (0)
 
-extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, CafeHandle** out) {
-  if (!deck || !out || max_batch <= 0 || deck->n_phases <= 0 || deck->n_phases > CAFE_MAX_PHASES) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cafe::set_last_error("no CUDA device: this library has no CPU fallback"); return CAFE_ERR_CUDA; }
-  if (device < 0 || device >= ndev) { cafe::set_last_error("bad device index"); return CAFE_ERR_ARG; }
-  CUDA_OK(cudaSetDevice(device));
-  bool all_hkd = true;
-  int n_knots = 0;
+// device copy of a host table, ordered on H->stream behind everything already queued there
+template <class T>
+static int upload_table(CafeHandle* H, const std::vector<T>& v, T** out) {
+  const size_t bytes = v.size() * sizeof(T);
+  if (bytes > H->tab_cap) {
+    if (H->tab_busy) { CUDA_OK(cudaEventSynchronize(H->ev_tab)); H->tab_busy = false; }
+    cudaFree(H->d_tab); if (H->h_tab) cudaFreeHost(H->h_tab);
+    H->d_tab = nullptr; H->h_tab = nullptr; H->tab_cap = 0;
+    const size_t cap = std::max<size_t>(2 * bytes, 256 * 1024);
+    CUDA_OK(cudaMalloc(&H->d_tab, cap));
+    CUDA_OK(cudaMallocHost(&H->h_tab, cap));
+    H->tab_cap = cap;
+  }
+  if (!H->ev_tab) CUDA_OK(cudaEventCreateWithFlags(&H->ev_tab, cudaEventDisableTiming));
+  if (H->tab_busy) CUDA_OK(cudaEventSynchronize(H->ev_tab));   // the staging buffer may still be read by the previous copy
+  std::memcpy(H->h_tab, v.data(), bytes);
+  CUDA_OK(cudaMemcpyAsync(H->d_tab, H->h_tab, bytes, cudaMemcpyHostToDevice, H->stream));
+  CUDA_OK(cudaEventRecord(H->ev_tab, H->stream));
+  H->tab_busy = true;
+  *out = reinterpret_cast<T*>(H->d_tab);
+  return 0;
+}
+
+static int validate_deck(const CafeDeck* deck, bool& all_hkd, int& n_knots) {
+  if (!deck || deck->n_phases <= 0 || deck->n_phases > CAFE_MAX_PHASES) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
+  all_hkd = true; n_knots = 0;
   for (int i = 0; i < deck->n_phases; ++i) { all_hkd = all_hkd && deck->phase[i].model == CAFE_MODEL_HKD; n_knots += deck->phase[i].horizon + 1; }
   bool any_hkd = false;
   for (int i = 0; i < deck->n_phases; ++i) any_hkd = any_hkd || deck->phase[i].model == CAFE_MODEL_HKD;
@@ -357,8 +380,12 @@ extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, 
     if (p.reb_grf.delta < p.reb_grf.delta_min || p.reb_torque.delta < p.reb_torque.delta_min || p.reb_joint.delta < p.reb_joint.delta_min ||
         p.reb_minheight.delta < p.reb_minheight.delta_min || (p.joint_speed_limit && p.reb_jointvel.delta < p.reb_jointvel.delta_min)) { cafe::set_last_error("ReB delta < delta_min is not supported"); return CAFE_ERR_UNSUPPORTED; }
   }
-  CafeHandle* H = new CafeHandle();
-  H->device = device; H->max_batch = max_batch; H->ldb = (max_batch + 31) / 32 * 32;
+  return 0;
+}
+
+// everything of a handle that depends on the deck: descriptor, arena layout, reference records, structural masks. Called by
+// cafe_gpu_create and, with the allocations of the previous deck re-used where they are large enough, by cafe_gpu_update_deck.
+static int configure(CafeHandle* H, const CafeDeck* deck, bool all_hkd, int n_knots) {
   H->deck = *deck;
   H->ref_host.assign(deck->ref, deck->ref + (size_t)deck->n_records * CAFE_REF_W);
   H->deck.ref = H->ref_host.data();
@@ -393,14 +420,24 @@ extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, 
   Carver sz;
   size_t zb = 0;
   carve(H, sz, zb);
-  H->arena_bytes = sz.off + 256;
-  cudaError_t e = cudaMalloc(&H->arena, H->arena_bytes);
-  if (e != cudaSuccess) { cafe::set_last_error(std::string("cudaMalloc arena: ") + cudaGetErrorString(e)); H->arena = nullptr; cafe_gpu_destroy(H); return CAFE_ERR_CUDA; }
+  const size_t need_arena = sz.off + 256;
+  if (need_arena > H->arena_bytes) {
+    // a horizon window moves a few knots between phases from one MPC step to the next: room for that, so that updates re-use the arena
+    cudaFree(H->arena); H->arena = nullptr; H->arena_bytes = 0;
+    const size_t want = need_arena + need_arena / 16;
+    cudaError_t e = cudaMalloc(&H->arena, want);
+    if (e != cudaSuccess) { cafe::set_last_error(std::string("cudaMalloc arena: ") + cudaGetErrorString(e)); H->arena = nullptr; return CAFE_ERR_CUDA; }
+    H->arena_bytes = want;
+  }
   Carver cv; cv.base = H->arena;
   carve(H, cv, H->zero_bytes);
-  CUDA_OK_H(cudaMemset(H->arena, 0, H->arena_bytes));
-  CUDA_OK_H(cudaMalloc(&H->d_ref, H->ref_host.size() * sizeof(double)));
-  CUDA_OK_H(cudaMemcpy(H->d_ref, H->ref_host.data(), H->ref_host.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemsetAsync(H->arena, 0, need_arena, H->stream));   // behind whatever still reads the previous layout on this stream
+  if (H->ref_host.size() > H->ref_cap) {
+    cudaFree(H->d_ref); H->d_ref = nullptr; H->ref_cap = 0;
+    CUDA_OK(cudaMalloc(&H->d_ref, (H->ref_host.size() + 8 * CAFE_REF_W) * sizeof(double)));
+    H->ref_cap = H->ref_host.size() + 8 * CAFE_REF_W;
+  }
+  CUDA_OK(cudaMemcpyAsync(H->d_ref, H->ref_host.data(), H->ref_host.size() * sizeof(double), cudaMemcpyHostToDevice, H->stream));
   for (int i = 0; i < deck->n_phases; ++i) { S.ph[i].ref = H->d_ref + (size_t)deck->phase[i].knot_offset * CAFE_REF_W; S.ph[i].ref_pp = nullptr; }
   {
     // structural pattern of the whole-body lxx per knot (cafe::wb_lxx_pattern, host/mhpc_problem.cpp)
@@ -416,22 +453,42 @@ extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, 
       }
     }
     if (!masks.empty()) {
-      CUDA_OK_H(cudaMalloc(&H->d_lxx_mask, masks.size() * sizeof(unsigned long long)));
-      CUDA_OK_H(cudaMemcpy(H->d_lxx_mask, masks.data(), masks.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+      if (masks.size() > H->lxx_mask_cap) {
+        cudaFree(H->d_lxx_mask); H->d_lxx_mask = nullptr; H->lxx_mask_cap = 0;
+        CUDA_OK(cudaMalloc(&H->d_lxx_mask, (masks.size() + 8 * CAFE_LXX_MASK_WORDS) * sizeof(unsigned long long)));
+        H->lxx_mask_cap = masks.size() + 8 * CAFE_LXX_MASK_WORDS;
+      }
+      CUDA_OK(cudaMemcpyAsync(H->d_lxx_mask, masks.data(), masks.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, H->stream));
     }
     for (int i = 0; i < deck->n_phases; ++i) S.ph[i].lxx_mask = (deck->phase[i].model == CAFE_MODEL_WB && H->d_lxx_mask) ? H->d_lxx_mask + first[i] : nullptr;
   }
-  if (all_hkd) {
+  if (all_hkd && !H->d_hkd_mask) {
     unsigned long long hm[36];
     cafe::hkd_lq_patterns(hm);
-    CUDA_OK_H(cudaMalloc(&H->d_hkd_mask, sizeof(hm)));
-    CUDA_OK_H(cudaMemcpy(H->d_hkd_mask, hm, sizeof(hm), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMalloc(&H->d_hkd_mask, sizeof(hm)));
+    CUDA_OK(cudaMemcpy(H->d_hkd_mask, hm, sizeof(hm), cudaMemcpyHostToDevice));
   }
   for (int i = 0; i < deck->n_phases; ++i) S.ph[i].hkd_mask = (deck->phase[i].model == CAFE_MODEL_HKD) ? H->d_hkd_mask : nullptr;
+  CUDA_OK(cudaStreamSynchronize(H->stream));   // `masks` and the caller's deck must outlive the copies
+  H->guess_B = 0; H->ref_pp_B = 0; H->B = 0;
+  return 0;
+}
+
+extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, CafeHandle** out) {
+  if (!deck || !out || max_batch <= 0) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cafe::set_last_error("no CUDA device: this library has no CPU fallback"); return CAFE_ERR_CUDA; }
+  if (device < 0 || device >= ndev) { cafe::set_last_error("bad device index"); return CAFE_ERR_ARG; }
+  bool all_hkd = true; int n_knots = 0;
+  if (int rc = validate_deck(deck, all_hkd, n_knots)) return rc;
+  CUDA_OK(cudaSetDevice(device));
+  CafeHandle* H = new CafeHandle();
+  H->device = device; H->max_batch = max_batch; H->ldb = (max_batch + 31) / 32 * 32;
+  CUDA_OK_H(cudaStreamCreate(&H->stream));
+  if (int rc = configure(H, deck, all_hkd, n_knots)) { cafe_gpu_destroy(H); return rc; }
   CUDA_OK_H(cudaMalloc(&H->d_x0raw, (size_t)H->ldb * CAFE_MAX_N * sizeof(double)));
   CUDA_OK_H(cudaMalloc(&H->dS, sizeof(SolverDev)));
   CUDA_OK_H(cudaMallocHost(&H->h_nactive, 64));
-  CUDA_OK_H(cudaStreamCreate(&H->stream));
   for (int i = 0; i < 3; ++i) { CUDA_OK_H(cudaStreamCreate(&H->stream2[i])); CUDA_OK_H(cudaEventCreateWithFlags(&H->ev_join[i], cudaEventDisableTiming)); }
   CUDA_OK_H(cudaEventCreateWithFlags(&H->ev_fork, cudaEventDisableTiming));
   for (int i = 0; i < 2; ++i) { CUDA_OK_H(cudaEventCreateWithFlags(&H->ev_lqf[i], cudaEventDisableTiming)); CUDA_OK_H(cudaEventCreateWithFlags(&H->ev_lqd[i], cudaEventDisableTiming)); CUDA_OK_H(cudaEventCreateWithFlags(&H->ev_lqj[i], cudaEventDisableTiming)); }
@@ -477,6 +534,8 @@ extern "C" int cafe_gpu_destroy(CafeHandle* H) {
   if (!H) return 0;
   cafe_gpu_comm_destroy(H);
   cudaSetDevice(H->device);
+  if (H->tab_busy && H->ev_tab) cudaEventSynchronize(H->ev_tab);
+  cudaFree(H->d_tab); if (H->h_tab) cudaFreeHost(H->h_tab); if (H->ev_tab) cudaEventDestroy(H->ev_tab);
   cudaFree(H->arena); cudaFree(H->d_ref); cudaFree(H->d_ref_pp); cudaFree(H->d_lxx_mask); cudaFree(H->d_hkd_mask); cudaFree(H->d_guess); cudaFree(H->d_x0raw); cudaFree(H->dS); cudaFree(H->d_pack); cudaFree(H->d_segs);
   if (H->h_nactive) cudaFreeHost(H->h_nactive);
   if (H->stream) cudaStreamDestroy(H->stream);
@@ -533,12 +592,9 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
       off += (long)h * m + (long)h * m * m + (long)h * m * n + (long)(h + 1) * n;  // Qu, Quu, Qux, G
     }
     UnpackSeg* d_us = nullptr;
-    CUDA_OK(cudaMalloc(&d_us, segs.size() * sizeof(UnpackSeg)));
-    CUDA_OK(cudaMemcpyAsync(d_us, segs.data(), segs.size() * sizeof(UnpackSeg), cudaMemcpyHostToDevice, st));
+    if (int rc = upload_table(H, segs, &d_us)) return rc;
     dim3 grid(592, (unsigned)segs.size());
     timed(H, CAFE_K_MISC, [&] { k_unpack<<<grid, 256, 0, st>>>(d_us, (int)segs.size(), H->ldb, B, off, H->d_guess); });
-    CUDA_OK(cudaStreamSynchronize(st));
-    cudaFree(d_us);
   }
   // one rollout group = the thread-per-knot kernel (trial states and controls; SRB / HKD / terminal knots completely) followed, on
   // whole-body decks, by the leg-parallel rigid-body terms and the cooperative KKT solve of the running whole-body knots
@@ -811,33 +867,46 @@ extern "C" int cafe_gpu_set_initial_guess(CafeHandle* H, const double* guess, in
 //        * knots past the old plan's end repeat its last state (push_back_state(X.back())), zero control and gain,
 //        * a phase the old plan did not have starts from the new deck's reference states (zero control and gain),
 //        * the trailing reduced-order phase is kept as it is while its horizon is unchanged (update_SRB_plan: nsteps = 0).
-extern "C" int cafe_gpu_shift_guess(CafeHandle* dst, CafeHandle* src, int src_k0, int dst_k0, int B) {
-  if (!dst || !src || dst == src || B <= 0 || B > dst->max_batch || B > src->B || dst_k0 < src_k0) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
-  if (dst->device != src->device) { cafe::set_last_error("both solvers must live on the same device"); return CAFE_ERR_ARG; }
-  CUDA_OK(cudaSetDevice(dst->device));
+// the phases of the deck the shifted guess is for: dimensions, stance, reference records on the device
+struct ShiftDst { int n_phases; struct P { int model, n, m, p, h, contact[4]; const double* ref; const double* ref_pp; } ph[CAFE_MAX_PHASES]; };
+static ShiftDst shift_dst_of(const SolverDev& S) {
+  ShiftDst d; d.n_phases = S.n_phases;
+  for (int i = 0; i < S.n_phases; ++i) {
+    const PhaseDev& p = S.ph[i];
+    d.ph[i] = ShiftDst::P{p.model, p.n, p.m, p.p, p.h, {p.contact[0], p.contact[1], p.contact[2], p.contact[3]}, p.ref, p.ref_pp};
+  }
+  return d;
+}
+static int build_shift(const SolverDev& src, int src_k0, const ShiftDst& dst, int dst_k0, std::vector<ShiftEntry>& ent, long& sol_size) {
   struct Range { int idx, s, e; int contact[4]; };
-  auto wb_ranges = [](const CafeHandle* H, int k0) {
-    std::vector<Range> out;
-    int s = k0;
-    const int lead = H->S.ph[0].model;  // whole-body for MHPC decks, hybrid kinodynamic for HKD decks (HKDProblem::update, HKDProblem.cpp:117-222)
-    if (lead == CAFE_MODEL_SRB) return out;
-    for (int i = 0; i < H->S.n_phases && H->S.ph[i].model == lead; ++i) {
-      Range r{i, s, s + H->S.ph[i].h, {0, 0, 0, 0}};
-      for (int f = 0; f < 4; ++f) r.contact[f] = H->S.ph[i].contact[f];
-      out.push_back(r);
-      s += H->S.ph[i].h;
-    }
-    return out;
-  };
-  const std::vector<Range> old_r = wb_ranges(src, src_k0), new_r = wb_ranges(dst, dst_k0);
-  if (old_r.empty() || new_r.empty() || src->S.ph[0].model != dst->S.ph[0].model) { cafe::set_last_error("both decks must start with full-order phases of the same model"); return CAFE_ERR_UNSUPPORTED; }
-  const int lead_model = dst->S.ph[0].model;
-  const PhaseDev& last = src->S.ph[old_r.back().idx];
+  std::vector<Range> old_r, new_r;
+  {
+    int s = src_k0;
+    const int lead = src.ph[0].model;  // whole-body for MHPC decks, hybrid kinodynamic for HKD decks (HKDProblem::update, HKDProblem.cpp:117-222)
+    if (lead != CAFE_MODEL_SRB)
+      for (int i = 0; i < src.n_phases && src.ph[i].model == lead; ++i) {
+        Range r{i, s, s + src.ph[i].h, {0, 0, 0, 0}};
+        for (int f = 0; f < 4; ++f) r.contact[f] = src.ph[i].contact[f];
+        old_r.push_back(r);
+        s += src.ph[i].h;
+      }
+    s = dst_k0;
+    const int lead2 = dst.ph[0].model;
+    if (lead2 != CAFE_MODEL_SRB)
+      for (int i = 0; i < dst.n_phases && dst.ph[i].model == lead2; ++i) {
+        Range r{i, s, s + dst.ph[i].h, {0, 0, 0, 0}};
+        for (int f = 0; f < 4; ++f) r.contact[f] = dst.ph[i].contact[f];
+        new_r.push_back(r);
+        s += dst.ph[i].h;
+      }
+  }
+  if (old_r.empty() || new_r.empty() || src.ph[0].model != dst.ph[0].model) { cafe::set_last_error("both decks must start with full-order phases of the same model"); return CAFE_ERR_UNSUPPORTED; }
+  const int lead_model = dst.ph[0].model;
+  const PhaseDev& last = src.ph[old_r.back().idx];
   const int old_end = old_r.back().e;
-  std::vector<ShiftEntry> ent;
   long off = 0;
-  for (int i = 0; i < dst->S.n_phases; ++i) {
-    const PhaseDev& ph = dst->S.ph[i];
+  for (int i = 0; i < dst.n_phases; ++i) {
+    const ShiftDst::P& ph = dst.ph[i];
     const int n = ph.n, m = ph.m, p = ph.p, h = ph.h;
     const long oX = off, oU = oX + (long)(h + 1) * n, oK = oU + (long)h * m + (long)h * p + (long)h * m;
     off = oK + (long)h * m * n + (long)h * m + (long)h * m * m + (long)h * m * n + (long)(h + 1) * n;
@@ -850,8 +919,8 @@ extern "C" int cafe_gpu_shift_guess(CafeHandle* dst, CafeHandle* src, int src_k0
     };
     if (ph.model != lead_model) {
       const int j = (int)old_r.size() + (i - (int)new_r.size());
-      const bool keep = j >= 0 && j < src->S.n_phases && src->S.ph[j].model == ph.model && src->S.ph[j].h == h;
-      for (int k = 0; k <= h; ++k) { x_from(keep ? &src->S.ph[j] : nullptr, k, k); if (keep && k < h) uk_from(src->S.ph[j], k, k); }
+      const bool keep = j >= 0 && j < src.n_phases && src.ph[j].model == ph.model && src.ph[j].h == h;
+      for (int k = 0; k <= h; ++k) { x_from(keep ? &src.ph[j] : nullptr, k, k); if (keep && k < h) uk_from(src.ph[j], k, k); }
       continue;
     }
     const Range& nr = new_r[i];
@@ -864,33 +933,85 @@ extern "C" int cafe_gpu_shift_guess(CafeHandle* dst, CafeHandle* src, int src_k0
     const bool continues_last = sr && sr->idx == old_r.back().idx;
     for (int k = 0; k <= h; ++k) {
       const int a = nr.s + k;
-      if (sr && sr->s <= a && a <= sr->e) x_from(&src->S.ph[sr->idx], a - sr->s, k);
+      if (sr && sr->s <= a && a <= sr->e) x_from(&src.ph[sr->idx], a - sr->s, k);
       else if (continues_last && a > old_end) x_from(&last, last.h, k);
       else x_from(nullptr, 0, k);
-      if (k < h && sr && sr->s <= a && a < sr->e) uk_from(src->S.ph[sr->idx], a - sr->s, k);
+      if (k < h && sr && sr->s <= a && a < sr->e) uk_from(src.ph[sr->idx], a - sr->s, k);
     }
   }
-  const long sol_size = cafe_solution_size(&dst->deck);
-  if (off != sol_size) { cafe::set_last_error("internal: packed record size mismatch"); return CAFE_ERR_ARG; }
+  sol_size = off;
+  return 0;
+}
+// fills owner->d_guess (B packed records of sol_size doubles) on owner->stream
+static int run_shift(CafeHandle* owner, const std::vector<ShiftEntry>& ent, int ldb_src, int B, long sol_size) {
   const size_t need = (size_t)B * (size_t)sol_size * sizeof(double);
-  if (need > dst->guess_bytes) {
-    cudaFree(dst->d_guess); dst->d_guess = nullptr; dst->guess_bytes = 0;
-    CUDA_OK(cudaMalloc(&dst->d_guess, need));
-    dst->guess_bytes = need;
+  if (need > owner->guess_bytes) {
+    cudaFree(owner->d_guess); owner->d_guess = nullptr; owner->guess_bytes = 0;
+    CUDA_OK(cudaMalloc(&owner->d_guess, need + need / 8));
+    owner->guess_bytes = need + need / 8;
   }
+  cudaStream_t st = owner->stream;
+  CUDA_OK(cudaMemsetAsync(owner->d_guess, 0, need, st));
+  ShiftEntry* d_ent = nullptr;
+  if (int rc = upload_table(owner, ent, &d_ent)) return rc;
+  dim3 grid(64, (unsigned)ent.size());
+  k_shift_guess<<<grid, 256, 0, st>>>(d_ent, (int)ent.size(), ldb_src, owner->ldb, B, sol_size, owner->d_guess);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int cafe_gpu_shift_guess(CafeHandle* dst, CafeHandle* src, int src_k0, int dst_k0, int B) {
+  if (!dst || !src || dst == src || B <= 0 || B > dst->max_batch || B > src->B || dst_k0 < src_k0) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
+  if (dst->device != src->device) { cafe::set_last_error("both solvers must live on the same device"); return CAFE_ERR_ARG; }
+  CUDA_OK(cudaSetDevice(dst->device));
+  std::vector<ShiftEntry> ent;
+  long sol_size = 0;
+  if (int rc = build_shift(src->S, src_k0, shift_dst_of(dst->S), dst_k0, ent, sol_size)) return rc;
+  if (sol_size != cafe_solution_size(&dst->deck)) { cafe::set_last_error("internal: packed record size mismatch"); return CAFE_ERR_ARG; }
   // the previous solve ran on src's stream: order this after it, and later solves of dst after this
   CUDA_OK(cudaStreamSynchronize(src->stream));
-  cudaStream_t st = dst->stream;
-  CUDA_OK(cudaMemsetAsync(dst->d_guess, 0, need, st));
-  ShiftEntry* d_ent = nullptr;
-  CUDA_OK(cudaMalloc(&d_ent, ent.size() * sizeof(ShiftEntry)));
-  CUDA_OK(cudaMemcpyAsync(d_ent, ent.data(), ent.size() * sizeof(ShiftEntry), cudaMemcpyHostToDevice, st));
-  dim3 grid(64, (unsigned)ent.size());
-  k_shift_guess<<<grid, 256, 0, st>>>(d_ent, (int)ent.size(), src->ldb, dst->ldb, B, sol_size, dst->d_guess);
-  CUDA_OK(cudaStreamSynchronize(st));
-  CUDA_OK(cudaGetLastError());
-  cudaFree(d_ent);
+  if (int rc = run_shift(dst, ent, src->ldb, B, sol_size)) return rc;
+  CUDA_OK(cudaStreamSynchronize(dst->stream));
   dst->guess_B = B;
+  return 0;
+}
+
+// ---- the MPC update on ONE handle (MHPCLocomotion::update_mpc_if_needed -> MHPCProblem::update, MHPCLocomotion.cpp:91-150, MHPCProblem.cpp:252-397;
+//      HKDMPCSolver::update -> HKDProblem::update): the deck re-cut `k_advance` knots later replaces the handle's deck, the previous solution
+//      becomes the warm start (the rules of cafe_gpu_shift_guess), and the device arena, reference and mask buffers are re-used - a horizon
+//      window only moves a few knots between phases from step to step, so nothing is allocated in steady state. Everything is queued on
+//      the handle's stream: the shift reads the old layout, then the arena is cleared and laid out for the new deck. Per-problem
+//      references (cafe_gpu_set_references) do not survive the update. B = 0: new deck, cold start.
+extern "C" int cafe_gpu_update_deck(CafeHandle* H, const CafeDeck* deck, int k_advance, int B) {
+  if (!H || !deck || k_advance < 0 || B < 0 || B > H->max_batch || (B > 0 && B > H->B)) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
+  bool all_hkd = true; int n_knots = 0;
+  if (int rc = validate_deck(deck, all_hkd, n_knots)) return rc;
+  if (all_hkd != (H->bwd_variant == 0)) { cafe::set_last_error("the new deck must be of the same family (HKD or whole-body / SRB) as the handle's"); return CAFE_ERR_UNSUPPORTED; }
+  CUDA_OK(cudaSetDevice(H->device));
+  if (B > 0) {
+    // the new deck's reference records go to the device first: states of phases the old plan did not have are taken from them
+    const size_t nref = (size_t)deck->n_records * CAFE_REF_W;
+    if (nref > H->ref_cap) {
+      CUDA_OK(cudaStreamSynchronize(H->stream));
+      cudaFree(H->d_ref); H->d_ref = nullptr; H->ref_cap = 0;
+      CUDA_OK(cudaMalloc(&H->d_ref, (nref + 8 * CAFE_REF_W) * sizeof(double)));
+      H->ref_cap = nref + 8 * CAFE_REF_W;
+    }
+    CUDA_OK(cudaMemcpyAsync(H->d_ref, deck->ref, nref * sizeof(double), cudaMemcpyHostToDevice, H->stream));
+    ShiftDst d; d.n_phases = deck->n_phases;
+    for (int i = 0; i < deck->n_phases; ++i) {
+      const CafePhase& p = deck->phase[i];
+      d.ph[i] = ShiftDst::P{p.model, cafe_model_n(p.model), cafe_model_m(p.model), cafe_model_p(p.model), p.horizon,
+                            {p.contact[0], p.contact[1], p.contact[2], p.contact[3]}, H->d_ref + (size_t)p.knot_offset * CAFE_REF_W, nullptr};
+    }
+    std::vector<ShiftEntry> ent;
+    long sol_size = 0;
+    if (int rc = build_shift(H->S, 0, d, k_advance, ent, sol_size)) return rc;
+    if (sol_size != cafe_solution_size(deck)) { cafe::set_last_error("internal: packed record size mismatch"); return CAFE_ERR_ARG; }
+    if (int rc = run_shift(H, ent, H->ldb, B, sol_size)) return rc;
+  }
+  if (int rc = configure(H, deck, all_hkd, n_knots)) return rc;
+  H->guess_B = B;
   return 0;
 }
 
@@ -935,7 +1056,11 @@ extern "C" int cafe_gpu_set_references(CafeHandle* H, const double* refs, int B)
   std::vector<double> t(nrec * W * ldb, 0.0);  // batch-major transpose
   for (int b = 0; b < B; ++b)
     for (size_t e = 0; e < nrec * W; ++e) t[e * ldb + b] = refs[(size_t)b * nrec * W + e];
-  if (!H->d_ref_pp) CUDA_OK(cudaMalloc(&H->d_ref_pp, t.size() * sizeof(double)));
+  if (t.size() > H->ref_pp_cap) {
+    cudaFree(H->d_ref_pp); H->d_ref_pp = nullptr; H->ref_pp_cap = 0;
+    CUDA_OK(cudaMalloc(&H->d_ref_pp, (t.size() + 8 * W * ldb) * sizeof(double)));
+    H->ref_pp_cap = t.size() + 8 * W * ldb;
+  }
   CUDA_OK(cudaMemcpy(H->d_ref_pp, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
   for (int i = 0; i < S.n_phases; ++i) S.ph[i].ref_pp = H->d_ref_pp + (size_t)H->deck.phase[i].knot_offset * W * ldb;
   H->ref_pp_B = B;
@@ -979,14 +1104,12 @@ static int lcm_impl(CafeHandle* H, int n_steps, float* out, float* dev_out, bool
       dst = reinterpret_cast<float*>(H->d_pack);
     }
     PackSegF* d_segs = nullptr;
-    CUDA_OK(cudaMalloc(&d_segs, segs.size() * sizeof(PackSegF)));
-    CUDA_OK(cudaMemcpyAsync(d_segs, segs.data(), segs.size() * sizeof(PackSegF), cudaMemcpyHostToDevice, H->stream));
+    if (int rc = upload_table(H, segs, &d_segs)) return rc;
     dim3 grid(592, (unsigned)segs.size());
     k_pack_lcm<<<grid, 256, 0, H->stream>>>(d_segs, (int)segs.size(), H->ldb, H->B, rec, dst);
     if (out) CUDA_OK(cudaMemcpyAsync(out, dst, need, cudaMemcpyDeviceToHost, H->stream));
     CUDA_OK(cudaStreamSynchronize(H->stream));
     CUDA_OK(cudaGetLastError());
-    cudaFree(d_segs);
     return 0;
   }
   int wb_knots = 0;
@@ -1020,14 +1143,12 @@ static int lcm_impl(CafeHandle* H, int n_steps, float* out, float* dev_out, bool
     dst = reinterpret_cast<float*>(H->d_pack);
   }
   PackSegF* d_segs = nullptr;
-  CUDA_OK(cudaMalloc(&d_segs, segs.size() * sizeof(PackSegF)));
-  CUDA_OK(cudaMemcpyAsync(d_segs, segs.data(), segs.size() * sizeof(PackSegF), cudaMemcpyHostToDevice, H->stream));
+  if (int rc = upload_table(H, segs, &d_segs)) return rc;
   dim3 grid(592, (unsigned)segs.size());
   k_pack_lcm<<<grid, 256, 0, H->stream>>>(d_segs, (int)segs.size(), H->ldb, H->B, rec, dst);
   if (out) CUDA_OK(cudaMemcpyAsync(out, dst, need, cudaMemcpyDeviceToHost, H->stream));
   CUDA_OK(cudaStreamSynchronize(H->stream));
   CUDA_OK(cudaGetLastError());
-  cudaFree(d_segs);
   return 0;
 }
 extern "C" int cafe_gpu_get_lcm_commands(CafeHandle* H, int n_steps, float* out) { return lcm_impl(H, n_steps, out, nullptr); }

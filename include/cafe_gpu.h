@@ -132,6 +132,13 @@ int cafe_gpu_shift_guess(CafeHandle* dst, CafeHandle* src, int src_k0, int dst_k
 /* Planned state `knots_ahead` knots after the start of the plan, out [B][n] (host): the state an MPC loop hands to the next solve
  * (MHPCLocomotion::update takes it from the simulator; a closed-loop Monte-Carlo without one uses the plan's own prediction). */
 int cafe_gpu_get_planned_state(CafeHandle* h, int knots_ahead, double* out);
+/* The MPC update on ONE solver (MHPCLocomotion::update_mpc_if_needed -> MHPCProblem::update, MHPC/MHPCLocomotion.cpp:91-150,
+ * MHPC/MHPC-Trajopt/MHPCProblem.cpp:252-397; HKDMPCSolver::update -> HKDProblem::update, HKDMPC/HKD-TrajOpt/HKDProblem.cpp:117-222):
+ * `new_deck` (the problem re-cut k_advance knots later, cafe_deck_build_* + cafe_deck_mark_mpc_update) replaces the solver's deck, the
+ * previous solution of the first B problems becomes the warm start by the rules of cafe_gpu_shift_guess, and the device arena,
+ * reference and mask buffers of the handle are re-used (nothing is allocated in steady state). B = 0: new deck, cold start.
+ * Per-problem references do not survive the update (set them again). */
+int cafe_gpu_update_deck(CafeHandle* h, const CafeDeck* new_deck, int k_advance, int B);
 /* x0: host [B][n0] row per problem. Runs every problem of the batch to its own termination. */
 int cafe_gpu_solve_batch(CafeHandle* h, const double* x0, int B, const CafeOptions* opt);
 /* same with x0 already resident on the device, layout [n0][ldb] (component-major), ldb >= B */

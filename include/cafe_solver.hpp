@@ -135,6 +135,8 @@ class MultiPhaseDDP {
   // receding horizon (MHPCProblem::update, MHPCProblem.cpp:252-397): warm start of this solver (deck at start offset k0) from the plan held
   // by `prev` (deck at start offset prev_k0), shifted on the device; and the planned state `knots_ahead` knots into the plan, [B][n]
   void shift_guess_from(const MultiPhaseDDP& prev, int prev_k0, int k0) { check(cafe_gpu_shift_guess(h_, prev.h_, prev_k0, k0, B_)); }
+  // the MPC update on this solver: `next` (the problem re-cut k_advance knots later) replaces the deck, the previous solution is the warm start
+  void update_deck(const ProblemBase& next, int k_advance) { check(cafe_gpu_update_deck(h_, next.deck(), k_advance, B_)); }
   std::vector<double> planned_state(int knots_ahead, int n) const { std::vector<double> v((size_t)B_ * n); check(cafe_gpu_get_planned_state(h_, knots_ahead, v.data())); return v; }
   // cost / dynamics feasibility / terminal / path constraint buffers (get_solver_info(cost_out, ...), MultiPhaseDDP.cpp:554-563)
   std::vector<double> get_history(int cap) const { std::vector<double> v((size_t)B_ * cap * 4); check(cafe_gpu_get_history(h_, v.data(), cap)); return v; }

@@ -331,6 +331,50 @@ def test_device_shift_equals_host_shift(cm, opt):
         s, prob, k0 = sd, p1, k1
 
 
+def test_update_deck_on_one_handle_equals_fresh_handles(cm, opt):
+    """cafe_gpu_update_deck: the MPC update on ONE solver (deck replaced, previous solution shifted into the warm start, device arena re-used)
+    gives bit for bit the solves of the two-handle path (a fresh solver per MPC step + cafe_gpu_shift_guess) over eight consecutive updates
+    on marked decks - start offsets 8 .. 22: the front phase shrinks to one knot (10) and disappears (12), a single-shooting tail opens
+    (12) and grows - and the float32 wire records agree as well."""
+    from cafe_mpc_b200 import workload
+    ort = copy.copy(opt)
+    ort.max_AL_iter = opt.max_AL_iter_runtime; ort.max_DDP_iter = opt.max_DDP_iter_runtime
+    B, k0 = 5, 6
+    prob = cm.MHPCProblem(CSV, k0=k0)
+    x0 = workload.mhpc_batch(B)
+    one = solve_gpu(cm, prob, opt, x0)          # the solver that is updated in place
+    two = solve_gpu(cm, prob, opt, x0)          # the chain of fresh solvers
+    shapes = set()
+    for step in range(8):
+        k1 = k0 + 2
+        p1 = cm.MHPCProblem(CSV, k0=k1, mpc_update_nsteps=2)
+        shapes.add(tuple(p.horizon for p in p1.phases()))
+        x1 = two.planned_state(2)
+        assert np.array_equal(x1, one.planned_state(2)), step
+        x1 = x1 + 1e-3 * (x0 - x0[0])
+        nxt = cm.MultiPhaseDDP(p1, 0, B)
+        nxt.set_initial_condition(x1)
+        nxt.shift_guess_from(two, k0, k1)
+        nxt.solve(ort)
+        one.update_deck(p1, 2)
+        one.set_initial_condition(x1)
+        one.solve(ort)
+        ia, ib = nxt.get_solver_info(), one.get_solver_info()
+        assert [[i[k] for k in COUNTS] for i in ia] == [[i[k] for k in COUNTS] for i in ib], step
+        assert np.array_equal(nxt.get_solution(), one.get_solution()), step
+        assert np.array_equal(nxt.get_lcm_commands(8), one.get_lcm_commands(8)), step
+        two.close()
+        two, prob, k0 = nxt, p1, k1
+    assert (1, 24, 10) in shapes and (24, 1, 10) in shapes and len(shapes) == 8
+    # cold start on a new deck through the same entry: equals a fresh solver
+    p2 = cm.MHPCProblem(CSV, k0=0)
+    one.update_deck(p2, 0, B=0)
+    one.set_initial_condition(x0)
+    one.solve(opt)
+    fresh = solve_gpu(cm, p2, opt, x0)
+    assert np.array_equal(fresh.get_solution(), one.get_solution())
+
+
 # ---- next tier (SURVEY.md §2 row 12): LocoProblem, whole-body-only locomotion TO (9 WB phases, 100 knots, three flight -> stance impacts)
 def test_loco_problem_matches_oracle_and_golden(cm):
     from cafe_mpc_b200 import workload

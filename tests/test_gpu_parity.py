@@ -250,6 +250,39 @@ def test_hkd_device_shift_equals_host_shift(cm, hkd_options):
         s, prob, k0 = sd, p1, k1
 
 
+def test_hkd_update_deck_on_one_handle_equals_fresh_handles(cm, hkd_options):
+    """cafe_gpu_update_deck on HKD decks: seven consecutive MPC updates on one solver (tail phase opened at offset 2, front phase removed at 12)
+    equal the chain of fresh solvers + cafe_gpu_shift_guess bit for bit, wire records included."""
+    import copy
+    from cafe_mpc_b200 import workload
+    csv = os.path.join(REPO, "data/Reference/Data/trot/heuristic/quad_reference.csv")
+    ort = copy.copy(hkd_options)
+    ort.max_AL_iter = 2; ort.max_DDP_iter = 1
+    B, k0 = 5, 0
+    prob = cm.HKDProblem(csv, k0=k0)
+    x0 = workload.hkd_batch(prob, B)
+    one = solve_gpu(cm, prob, hkd_options, x0)
+    two = solve_gpu(cm, prob, hkd_options, x0)
+    for step in range(7):
+        k1 = k0 + 2
+        p1 = cm.HKDProblem(csv, k0=k1, mpc_update=True)
+        x1 = two.planned_state(2)
+        assert np.array_equal(x1, one.planned_state(2)), step
+        nxt = cm.MultiPhaseDDP(p1, 0, B)
+        nxt.set_initial_condition(x1)
+        nxt.shift_guess_from(two, k0, k1)
+        nxt.solve(ort)
+        one.update_deck(p1, 2)
+        one.set_initial_condition(x1)
+        one.solve(ort)
+        ia, ib = nxt.get_solver_info(), one.get_solver_info()
+        assert [[i[k] for k in COUNTS] for i in ia] == [[i[k] for k in COUNTS] for i in ib], step
+        assert np.array_equal(nxt.get_solution(), one.get_solution()), step
+        assert np.array_equal(nxt.get_hkd_lcm_commands(9), one.get_hkd_lcm_commands(9)), step
+        two.close()
+        two, prob, k0 = nxt, p1, k1
+
+
 def test_hkd_lcm_command_packing(cm, hkd_options):
     """cafe_gpu_get_hkd_lcm_commands == the loops of HKDMPCSolver::publish_mpc_cmd (HKDMPC.cpp:243-290) applied to the packed solution:
     float32 casts of Ubar, Xbar[:12] and K(m, n) for m, n < 12, nine steps that cross the first phase boundary (start offset 8: h = 3)."""
