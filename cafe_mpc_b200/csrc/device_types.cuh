@@ -90,6 +90,25 @@ struct PhaseDev {
   int* fail_t;                             // [NA][ldb]
   // augmented-Lagrangian state of the touchdown constraints
   double *al_sigma, *al_lambda, *hval;     // [4][ldb]
+  // relaxed-barrier parameters per (running knot, path-constraint element, problem) (PathConstraintBase::params, ConstraintsBase.h:173-209):
+  // update_params multiplies eps by update_ReB and delta by update_relax (floored at delta_min) for every element that is violated at the
+  // end of an outer iteration, so a parameter is the deck's initial value after n such updates - the count n is what is stored.
+  // Elements: HKD 5 per leg (20); SRB 1; WB torque 24 | joint speed 24 | joint 24 | min height 1 | GRF 5 per foot (93).
+  unsigned char* reb_n;                    // [h][reb_ne][ldb]
+  int reb_ne, reb_dyn;                     // reb_dyn = 0: every parameter keeps its initial value (update factors 1, the shipped settings)
+  double reb_br, reb_bw;                   // update_relax, update_ReB
+};
+
+// the relaxed-barrier parameters of one (problem, knot): element e -> (delta, eps)
+struct RebCtx {
+  const unsigned char* n; size_t st; double br, bw;
+  __device__ __forceinline__ void get(const CafeRebParam& p0, int e, double& delta, double& eps) const {
+    delta = p0.delta; eps = p0.eps;
+    if (n) {
+      const int c = n[(size_t)e * st];
+      for (int i = 0; i < c; ++i) { eps *= bw; delta *= br; delta = fmax(delta, p0.delta_min); }   // update_weight, update_relax (:79-85)
+    }
+  }
 };
 
 struct CtrlDev {
@@ -110,6 +129,7 @@ struct CtrlDev {
   // most of the batch has already converged.
   int *act_list, *pend_list;
   int *cur_slot;  // trial slot whose rollout produced the current iterate X, U (its rigid-body terms are reused by the linearisation)
+  int *reb_upd;   // relaxed-barrier updates decided by k_select in this tick (applied per knot by k_reb_update)
 };
 
 struct SolverDev {
@@ -134,3 +154,7 @@ __device__ __forceinline__ const double* knot_record(const PhaseDev& ph, int k, 
 
 // element (k, c) of problem b in an array with NC components per knot
 __device__ __forceinline__ size_t gix(int k, int NC, int c, int ldb, int b) { return ((size_t)k * NC + c) * (size_t)ldb + b; }
+__device__ __forceinline__ RebCtx reb_ctx(const PhaseDev& ph, int k, int ldb, int b) {
+  return RebCtx{ph.reb_dyn ? ph.reb_n + ((size_t)k * ph.reb_ne) * (size_t)ldb + b : nullptr, (size_t)ldb, ph.reb_br, ph.reb_bw};
+}
+__host__ __device__ inline int cafe_reb_elements(int model) { return model == CAFE_MODEL_WB ? 93 : model == CAFE_MODEL_HKD ? 20 : 1; }

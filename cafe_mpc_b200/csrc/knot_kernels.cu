@@ -28,5 +28,6 @@ void launch_compact(const SolverDev* dS, cudaStream_t st, int mode) { k_compact<
 void launch_accept(const SolverDev* dS, long long nthreads, cudaStream_t st) { k_accept<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(dS); }
 void launch_ls_scan(const SolverDev* dS, int B, cudaStream_t st, int a0, int a1) { k_ls_scan<<<(B + 127) / 128, 128, 0, st>>>(dS, a0, a1); }
 void launch_select(const SolverDev* dS, int B, cudaStream_t st, int mode) { k_select<<<(B + 127) / 128, 128, 0, st>>>(dS, mode); }
+void launch_reb_update(const SolverDev* dS, long long nthreads, cudaStream_t st) { k_reb_update<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(dS); }
 
 }  // namespace cafe_dev

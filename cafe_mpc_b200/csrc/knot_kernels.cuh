@@ -61,7 +61,7 @@ __device__ __noinline__ void single_shooting_state(const SolverDev& S, int pi, i
       for (int i = 0; i < M; ++i) u[i] += Kg[(size_t)(i + M * j) * ldb] * dj;
     }
     for (int i = 0; i < M; ++i) u[i] = ph.Ubar[gix(kk, M, i, ldb, b)] + eps * ph.dU[gix(kk, M, i, ldb, b)] + u[i];
-    Model::roll(ph, rec, x, u, xn, y, S.opt.ReB_active != 0, l, ming);
+    Model::roll(ph, rec, x, u, xn, y, S.opt.ReB_active != 0, l, ming, reb_ctx(ph, kk, ldb, b));   // only xn is used
     for (int i = 0; i < N; ++i) x[i] = xn[i];
   }
 }
@@ -112,7 +112,7 @@ __device__ void roll_knot(const SolverDev& S, int pi, int k, int a, int b) {
     if constexpr (Model::COOP) return;
     double xn[N], y[PY > 0 ? PY : 1];
     double l, ming;
-    Model::roll(ph, rec, x, u, xn, y, S.opt.ReB_active != 0, l, ming);
+    Model::roll(ph, rec, x, u, xn, y, S.opt.ReB_active != 0, l, ming, reb_ctx(ph, k, ldb, b));
     double nrm = 0, dsq = 0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
@@ -373,6 +373,7 @@ __global__ void k_select(const SolverDev* __restrict__ Sp, int mode) {
   const CtrlDev& c = S.c;
   const CafeOptions& o = S.opt;
   const int ldb = S.ldb;
+  c.reb_upd[b] = 0;
   if (!c.active[b]) { c.sel[b] = -1; return; }
   if (mode == 0 || !c.do_ls[b]) c.sel[b] = -1;
   bool inner_done = false;
@@ -436,12 +437,58 @@ __global__ void k_select(const SolverDev* __restrict__ Sp, int mode) {
         }
       }
     }
-    /* ReB update: with update_relax == update_ReB == 1 and delta >= delta_min (checked at create) it is the identity */
+    // PathConstraintBase::update_params (ConstraintsBase.h:194-209, called at :538): decided here, applied per (knot, element) by
+    // k_reb_update once k_accept has left the last rollout in X, U, Y - the trajectory the reference's constraint data belong to
+    if (o.ReB_active) c.reb_upd[b] += 1;
     if (c.iter_ou[b] >= o.max_AL_iter) { c.active[b] = 0; break; }
     c.iter_ou[b] += 1; c.max_t_prev[b] = mt; c.max_p_prev[b] = mp; c.reg[b] = 0; c.iter_in[b] = 0;
     if (o.max_DDP_iter > 0) break;
   }
   if (c.active[b]) atomicAdd(c.n_active, 1);
+}
+
+// ------------------------------------------------------------------------------------------ K-REB-UPDATE
+// PathConstraintBase::update_params (ConstraintsBase.h:194-209): every element whose value g of the last rollout is not above
+// -pconstr_thresh gets eps *= update_ReB, delta = max(delta * update_relax, delta_min) - here: its update count grows (RebCtx::get
+// replays the multiplications). Thread per (problem, running knot); launched only when the parameters can change (reb_dyn).
+// g as SinglePhase::hybrid_rollout left it (compute_path_constraints on X[k], U[k], Y[k], SinglePhase.cpp:222): after k_accept
+// these are the arrays X, U, Y. Elements that do not exist for a phase (swing feet, switched-off constraint sets) are never read.
+__global__ void k_reb_update(const SolverDev* __restrict__ Sp) {
+  const SolverDev& S = *Sp;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = (int)(t % S.ldb);
+  const int gk = (int)(t / S.ldb);
+  if (gk >= S.n_knots || b >= S.B) return;
+  const int cnt = S.c.reb_upd[b];
+  if (cnt <= 0) return;
+  const int pi = S.knot_phase[gk], k = S.knot_k[gk];
+  const PhaseDev& ph = S.ph[pi];
+  if (k >= ph.h || !ph.reb_dyn) return;
+  const int ldb = S.ldb;
+  const double thresh = S.opt.pconstr_thresh;
+  unsigned char* np = ph.reb_n + ((size_t)k * ph.reb_ne) * (size_t)ldb + b;
+  auto hit = [&](int e, double g) {
+    if (g > -thresh) return;
+    const int v = np[(size_t)e * ldb] + cnt;
+    np[(size_t)e * ldb] = (unsigned char)(v > 255 ? 255 : v);
+  };
+  auto grf5 = [&](int e0, double fx, double fy, double fz) {
+    const double mu = ph.mu;
+    hit(e0, fz); hit(e0 + 1, -fx + mu * fz); hit(e0 + 2, fx + mu * fz); hit(e0 + 3, -fy + mu * fz); hit(e0 + 4, fy + mu * fz);
+  };
+  if (ph.model == CAFE_MODEL_HKD) {
+    for (int leg = 0; leg < 4; ++leg)
+      if (ph.contact[leg] > 0) grf5(5 * leg, ph.U[gix(k, 24, 3 * leg, ldb, b)], ph.U[gix(k, 24, 3 * leg + 1, ldb, b)], ph.U[gix(k, 24, 3 * leg + 2, ldb, b)]);
+  } else if (ph.model == CAFE_MODEL_SRB) {
+    hit(0, ph.X[gix(k, 12, 2, ldb, b)] - ph.h_min);
+  } else {
+    for (int i = 0; i < 12; ++i) { const double u = ph.U[gix(k, 12, i, ldb, b)]; hit(i, -u - (-ph.torque_limit)); hit(12 + i, u - (-ph.torque_limit)); }
+    if (ph.joint_speed_limit) for (int i = 0; i < 12; ++i) { const double v = ph.X[gix(k, 36, 24 + i, ldb, b)]; hit(24 + i, v - ph.jointvel_lb); hit(36 + i, -v - (-ph.jointvel_ub)); }
+    if (!ph.no_joint_limit) for (int i = 0; i < 12; ++i) { const double q = ph.X[gix(k, 36, 6 + i, ldb, b)]; hit(48 + i, q - ph.joint_lb[i % 3]); hit(60 + i, -q - (-ph.joint_ub[i % 3])); }
+    if (!ph.no_min_height) hit(72, ph.X[gix(k, 36, 2, ldb, b)] - ph.h_min);
+    for (int f = 0; f < 4; ++f)
+      if (ph.contact[f] > 0) grf5(73 + 5 * f, ph.Y[gix(k, 12, 3 * f, ldb, b)], ph.Y[gix(k, 12, 3 * f + 1, ldb, b)], ph.Y[gix(k, 12, 3 * f + 2, ldb, b)]);
+  }
 }
 
 }  // namespace cafe_dev

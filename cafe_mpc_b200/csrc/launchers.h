@@ -11,6 +11,7 @@ void launch_compact(const SolverDev* dS, cudaStream_t st, int mode);
 void launch_accept(const SolverDev* dS, long long nthreads, cudaStream_t st);
 void launch_ls_scan(const SolverDev* dS, int B, cudaStream_t st, int a0, int a1);
 void launch_select(const SolverDev* dS, int B, cudaStream_t st, int mode);
+void launch_reb_update(const SolverDev* dS, long long nthreads, cudaStream_t st);
 // whole-body running knots (n_wbk of them per problem): leg-parallel rigid-body routines (wb_leg_kernels.cu) and the cooperative
 // shared-memory kernels that consume them (wb_coop.cu)
 void launch_wb_terms(const SolverDev* dS, int n_wbk, cudaStream_t st, int a0, int a1, const int* list, int n_list);

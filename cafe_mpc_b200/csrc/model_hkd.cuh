@@ -62,7 +62,7 @@ struct HKDModel {
 
   // running cost l_k = tracking + foot-placement regulariser + dt * ReB(GRF); ming = min(0, g_i)
   __device__ static double running_cost(const PhaseDev& ph, const double* rec, const double* x, const double* u,
-                                        const double* y, bool reb, double& ming) {
+                                        const double* y, bool reb, double& ming, const RebCtx& rcx) {
     (void)y;
     double s = 0;
 #pragma unroll
@@ -94,7 +94,7 @@ struct HKDModel {
         const double fx = u[3 * leg], fy = u[3 * leg + 1], fz = u[3 * leg + 2], mu = ph.mu;
         const double g[5] = {fz, -fx + mu * fz, fx + mu * fz, -fy + mu * fz, fy + mu * fz};
 #pragma unroll
-        for (int i = 0; i < 5; ++i) { ming = fmin(ming, g[i]); rc += ph.reb_grf.eps * reb_value(g[i], ph.reb_grf.delta); }
+        for (int i = 0; i < 5; ++i) { double dl, ep; rcx.get(ph.reb_grf, 5 * leg + i, dl, ep); ming = fmin(ming, g[i]); rc += ep * reb_value(g[i], dl); }
       }
     }
     if (reb && any) l += ph.dt * rc;
@@ -103,9 +103,9 @@ struct HKDModel {
 
   // dynamics + running cost of one trial knot
   __device__ static void roll(const PhaseDev& ph, const double* rec, const double* x, const double* u, double* xn, double* y,
-                              bool reb, double& l, double& ming) {
+                              bool reb, double& l, double& ming, const RebCtx& rcx) {
     dynamics(ph, rec, x, u, xn, y);
-    l = running_cost(ph, rec, x, u, y, reb, ming);
+    l = running_cost(ph, rec, x, u, y, reb, ming, rcx);
   }
 
   __device__ static double terminal_cost(const PhaseDev& ph, const double* rec, const double* x) {
@@ -144,6 +144,7 @@ struct HKDModel {
   __device__ static double lq_knot(const PhaseDev& ph, int k, int ldb, int b, const double* rec, const double* x,
                                    const double* u, const double* y, bool reb) {
     const double dt = ph.dt;
+    const RebCtx rcx = reb_ctx(ph, k, ldb, b);
     {
       const double c[4] = {(double)ph.contact[0], (double)ph.contact[1], (double)ph.contact[2], (double)ph.contact[3]};
       double* Ag = ph.A + gix(k, 576, 0, ldb, b);
@@ -190,9 +191,10 @@ struct HKDModel {
         const double Al[5][3] = {{0, 0, 1}, {-1, 0, mu}, {1, 0, mu}, {0, -1, mu}, {0, 1, mu}};
 #pragma unroll
         for (int i = 0; i < 5; ++i) {
-          double bd, bdd;
-          reb_derivs(g[i], ph.reb_grf.delta, bd, bdd);
-          const double e1 = ph.reb_grf.eps * bd, e2 = ph.reb_grf.eps * bdd;
+          double bd, bdd, dl, ep;
+          rcx.get(ph.reb_grf, 5 * leg + i, dl, ep);
+          reb_derivs(g[i], dl, bd, bdd);
+          const double e1 = ep * bd, e2 = ep * bdd;
 #pragma unroll
           for (int r = 0; r < 3; ++r) {
             gr[r] += e1 * Al[i][r];
@@ -220,7 +222,7 @@ struct HKDModel {
       ph.lu[gix(k, 24, i, ldb, b)] = lu[i];
     }
     double ming;
-    return running_cost(ph, rec, x, u, y, reb, ming);
+    return running_cost(ph, rec, x, u, y, reb, ming, rcx);
   }
 
   // terminal cost partials (+ AL terms) and the reset-map Jacobian Px at X[h]

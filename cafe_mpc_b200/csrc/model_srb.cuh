@@ -15,7 +15,7 @@ struct SRBModel {
   static constexpr int N = 12, M = 12, PY = 0;
   static constexpr bool COOP = false;
 
-  __device__ static double running_cost(const PhaseDev& ph, const double* rec, const double* x, const double* u, bool reb, double& ming) {
+  __device__ static double running_cost(const PhaseDev& ph, const double* rec, const double* x, const double* u, bool reb, double& ming, const RebCtx& rcx) {
     double s = 0;
 #pragma unroll
     for (int i = 0; i < 12; ++i) { const double dx = x[i] - rec[CAFE_REF_XR + i]; s += dx * ph.q[i] * dx; }
@@ -27,13 +27,13 @@ struct SRBModel {
     l *= ph.dt;
     const double g = x[2] - ph.h_min;
     ming = fmin(0.0, g);
-    if (reb) l += ph.dt * (ph.reb_minheight.eps * reb_value(g, ph.reb_minheight.delta));
+    if (reb) { double dl, ep; rcx.get(ph.reb_minheight, 0, dl, ep); l += ph.dt * (ep * reb_value(g, dl)); }
     return l;
   }
 
   // dynamics + running cost of one trial knot
   __device__ static void roll(const PhaseDev& ph, const double* rec, const double* x, const double* u, double* xn, double* y,
-                              bool reb, double& l, double& ming) {
+                              bool reb, double& l, double& ming, const RebCtx& rcx) {
     (void)y;
     double xd[12];
 #pragma unroll
@@ -41,7 +41,7 @@ struct SRBModel {
     cafe_gen_srb::srb_dynamics(x, u, rec + CAFE_REF_PF, rec + CAFE_REF_CONTACT, [&](int i, double v) { xd[i] = v; });
 #pragma unroll
     for (int i = 0; i < 12; ++i) xn[i] = x[i] + xd[i] * ph.dt;
-    l = running_cost(ph, rec, x, u, reb, ming);
+    l = running_cost(ph, rec, x, u, reb, ming, rcx);
   }
 
   __device__ static double terminal_cost(const PhaseDev& ph, const double* rec, const double* x) {
@@ -70,20 +70,22 @@ struct SRBModel {
     double* lxxg = ph.lxx + gix(k, 144, 0, ldb, b);
     double* luug = ph.luu + gix(k, 144, 0, ldb, b);
     const double g = x[2] - ph.h_min;
-    double bd = 0, bdd = 0;
-    if (reb) reb_derivs(g, ph.reb_minheight.delta, bd, bdd);
+    double bd = 0, bdd = 0, mh_delta, mh_eps;
+    const RebCtx rcx = reb_ctx(ph, k, ldb, b);
+    rcx.get(ph.reb_minheight, 0, mh_delta, mh_eps);
+    if (reb) reb_derivs(g, mh_delta, bd, bdd);
 #pragma unroll
     for (int i = 0; i < 12; ++i) {
       double lx = dt * ph.q[i] * (x[i] - rec[CAFE_REF_XR + i]);
       double lxx = dt * ph.q[i];
-      if (i == 2 && reb) { lx += dt * (ph.reb_minheight.eps * bd); lxx += dt * (ph.reb_minheight.eps * bdd); }
+      if (i == 2 && reb) { lx += dt * (mh_eps * bd); lxx += dt * (mh_eps * bdd); }
       ph.lx[gix(k, 12, i, ldb, b)] = lx;
       lxxg[(size_t)(13 * i) * ldb] = lxx;
       ph.lu[gix(k, 12, i, ldb, b)] = dt * ph.r[i] * (u[i] - rec[CAFE_REF_UR + i]);
       luug[(size_t)(13 * i) * ldb] = dt * ph.r[i];
     }
     double ming;
-    return running_cost(ph, rec, x, u, reb, ming);
+    return running_cost(ph, rec, x, u, reb, ming, rcx);
   }
 
   __device__ static void lq_terminal(const PhaseDev& ph, int ldb, int b, const double* rec, const double* x, bool al) {

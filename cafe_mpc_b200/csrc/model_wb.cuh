@@ -123,7 +123,7 @@ struct WBModel {
 
   // running cost from already evaluated foot kinematics (pf, vf) + ReB terms
   __device__ static double running_cost_k(const PhaseDev& ph, const double* rec, const double* x, const double* u, const double* y,
-                                          const double* pf, const double* vf, bool reb, double& ming) {
+                                          const double* pf, const double* vf, bool reb, double& ming, const RebCtx& rcx) {
     double s = 0;
     for (int i = 0; i < 36; ++i) { const double dx = x[i] - rec[CAFE_REF_XR + i]; s += dx * ph.q[i] * dx; }
     double l = 0.5 * s;
@@ -150,26 +150,27 @@ struct WBModel {
     ming = 0;
     if (true) {
       // path constraints in the reference's order: torque, [joint speed: BarrelRollTO.cpp:190-198], joint, min height, GRF (MHPCProblem.cpp:436-481)
-      double c_t = 0, c_j = 0, c_h = 0, c_g = 0, c_v = 0, m_t = 0, m_j = 0, m_h = 0, m_g = 0, m_v = 0;
-      for (int i = 0; i < 12; ++i) { const double g = -u[i] - (-ph.torque_limit); m_t = fmin(m_t, g); c_t += ph.reb_torque.eps * reb_value(g, ph.reb_torque.delta); }
-      for (int i = 0; i < 12; ++i) { const double g = u[i] - (-ph.torque_limit); m_t = fmin(m_t, g); c_t += ph.reb_torque.eps * reb_value(g, ph.reb_torque.delta); }
+      // element numbering of the per-element barrier parameters: torque 0..23 | joint speed 24..47 | joint 48..71 | min height 72 | GRF 73 + 5 f + i
+      double c_t = 0, c_j = 0, c_h = 0, c_g = 0, c_v = 0, m_t = 0, m_j = 0, m_h = 0, m_g = 0, m_v = 0, dl, ep;
+      for (int i = 0; i < 12; ++i) { const double g = -u[i] - (-ph.torque_limit); m_t = fmin(m_t, g); rcx.get(ph.reb_torque, i, dl, ep); c_t += ep * reb_value(g, dl); }
+      for (int i = 0; i < 12; ++i) { const double g = u[i] - (-ph.torque_limit); m_t = fmin(m_t, g); rcx.get(ph.reb_torque, 12 + i, dl, ep); c_t += ep * reb_value(g, dl); }
       const bool jl = !ph.no_joint_limit, mh = !ph.no_min_height;  // LocoProblem keeps torque + GRF only (LocoProblem.cpp:64-82)
       if (ph.joint_speed_limit) {
-        for (int i = 0; i < 12; ++i) { const double g = x[24 + i] - ph.jointvel_lb; m_v = fmin(m_v, g); c_v += ph.reb_jointvel.eps * reb_value(g, ph.reb_jointvel.delta); }
-        for (int i = 0; i < 12; ++i) { const double g = -x[24 + i] - (-ph.jointvel_ub); m_v = fmin(m_v, g); c_v += ph.reb_jointvel.eps * reb_value(g, ph.reb_jointvel.delta); }
+        for (int i = 0; i < 12; ++i) { const double g = x[24 + i] - ph.jointvel_lb; m_v = fmin(m_v, g); rcx.get(ph.reb_jointvel, 24 + i, dl, ep); c_v += ep * reb_value(g, dl); }
+        for (int i = 0; i < 12; ++i) { const double g = -x[24 + i] - (-ph.jointvel_ub); m_v = fmin(m_v, g); rcx.get(ph.reb_jointvel, 36 + i, dl, ep); c_v += ep * reb_value(g, dl); }
       }
       if (jl) {
-        for (int i = 0; i < 12; ++i) { const double g = x[6 + i] - ph.joint_lb[i % 3]; m_j = fmin(m_j, g); c_j += ph.reb_joint.eps * reb_value(g, ph.reb_joint.delta); }
-        for (int i = 0; i < 12; ++i) { const double g = -x[6 + i] - (-ph.joint_ub[i % 3]); m_j = fmin(m_j, g); c_j += ph.reb_joint.eps * reb_value(g, ph.reb_joint.delta); }
+        for (int i = 0; i < 12; ++i) { const double g = x[6 + i] - ph.joint_lb[i % 3]; m_j = fmin(m_j, g); rcx.get(ph.reb_joint, 48 + i, dl, ep); c_j += ep * reb_value(g, dl); }
+        for (int i = 0; i < 12; ++i) { const double g = -x[6 + i] - (-ph.joint_ub[i % 3]); m_j = fmin(m_j, g); rcx.get(ph.reb_joint, 60 + i, dl, ep); c_j += ep * reb_value(g, dl); }
       }
-      if (mh) { const double g = x[2] - ph.h_min; m_h = fmin(m_h, g); c_h += ph.reb_minheight.eps * reb_value(g, ph.reb_minheight.delta); }
+      if (mh) { const double g = x[2] - ph.h_min; m_h = fmin(m_h, g); rcx.get(ph.reb_minheight, 72, dl, ep); c_h += ep * reb_value(g, dl); }
       bool any = false;
       for (int f = 0; f < 4; ++f)
         if (ph.contact[f] > 0) {
           any = true;
           const double fx = y[3 * f], fy = y[3 * f + 1], fz = y[3 * f + 2], mu = ph.mu;
           const double g[5] = {fz, -fx + mu * fz, fx + mu * fz, -fy + mu * fz, fy + mu * fz};
-          for (int i = 0; i < 5; ++i) { m_g = fmin(m_g, g[i]); c_g += ph.reb_grf.eps * reb_value(g[i], ph.reb_grf.delta); }
+          for (int i = 0; i < 5; ++i) { m_g = fmin(m_g, g[i]); rcx.get(ph.reb_grf, 73 + 5 * f + i, dl, ep); c_g += ep * reb_value(g[i], dl); }
         }
       ming = fmin(fmin(fmin(m_t, m_j), fmin(m_h, m_g)), m_v);
       if (reb) { l += ph.dt * c_t; if (ph.joint_speed_limit) l += ph.dt * c_v; if (jl) l += ph.dt * c_j; if (mh) l += ph.dt * c_h; if (any) l += ph.dt * c_g; }
@@ -178,12 +179,12 @@ struct WBModel {
   }
 
   __device__ __noinline__ static void roll(const PhaseDev& ph, const double* rec, const double* x, const double* u, double* xn, double* y,
-                              bool reb, double& l, double& ming) {
+                              bool reb, double& l, double& ming, const RebCtx& rcx) {
     WBScratch s;
     forward(ph, x, u, s);
     for (int i = 0; i < 18; ++i) { xn[i] = x[i] + x[18 + i] * ph.dt; xn[18 + i] = x[18 + i] + s.qdd[i] * ph.dt; }
     for (int i = 0; i < 12; ++i) y[i] = s.grf[i];
-    l = running_cost_k(ph, rec, x, u, y, s.pf, s.vf, reb, ming);
+    l = running_cost_k(ph, rec, x, u, y, s.pf, s.vf, reb, ming, rcx);
   }
 
   __device__ static void feet(const double* x, double* pf, double* vf, double* J) {

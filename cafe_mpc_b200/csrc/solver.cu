@@ -240,7 +240,7 @@ void carve(CafeHandle* H, Carver& cv, size_t& zero_bytes) {
   c.iter_ou = cv.take<int>(ldb); c.iter_in = cv.take<int>(ldb); c.iter = cv.take<int>(ldb); c.ls_total = cv.take<int>(ldb);
   c.reg_total = cv.take<int>(ldb); c.n_hist = cv.take<int>(ldb); c.status = cv.take<int>(ldb);
   c.n_active = cv.take<int>(64);
-  c.act_list = cv.take<int>(ldb); c.pend_list = cv.take<int>(ldb); c.cur_slot = cv.take<int>(ldb);
+  c.act_list = cv.take<int>(ldb); c.pend_list = cv.take<int>(ldb); c.cur_slot = cv.take<int>(ldb); c.reb_upd = cv.take<int>(ldb);
   c.reg = cv.take<double>(ldb); c.cost = cv.take<double>(ldb); c.merit = cv.take<double>(ldb); c.feas = cv.take<double>(ldb);
   c.merit_rho = cv.take<double>(ldb); c.dV1 = cv.take<double>(ldb); c.dV2 = cv.take<double>(ldb);
   c.cost_prev = cv.take<double>(ldb); c.merit_prev = cv.take<double>(ldb);
@@ -267,6 +267,8 @@ void carve(CafeHandle* H, Carver& cv, size_t& zero_bytes) {
     ph.lk = cv.take<double>((h + 1) * ldb); ph.dsq = cv.take<double>((h + 1) * ldb);
     ph.al_sigma = cv.take<double>(4 * ldb); ph.al_lambda = cv.take<double>(4 * ldb); ph.hval = cv.take<double>(4 * ldb);
     ph.maxh_t = cv.take<double>((size_t)NA * ldb); ph.ht = cv.take<double>((size_t)NA * 4 * ldb);
+    ph.reb_ne = cafe_reb_elements(ph.model);
+    ph.reb_n = cv.take<unsigned char>(h * (size_t)ph.reb_ne * ldb + 1);
   }
   zero_bytes = cv.off;
   // ---- region whose zero pattern is static (zeroed once at create)
@@ -377,8 +379,6 @@ static int validate_deck(const CafeDeck* deck, bool& all_hkd, int& n_knots) {
     if (p.single_shooting && i > 0 && (deck->phase[i - 1].model != p.model || deck->phase[i - 1].single_shooting)) {
       cafe::set_last_error("a single-shooting phase must follow a shooting phase of the same model"); return CAFE_ERR_UNSUPPORTED;
     }
-    if (p.reb_grf.delta < p.reb_grf.delta_min || p.reb_torque.delta < p.reb_torque.delta_min || p.reb_joint.delta < p.reb_joint.delta_min ||
-        p.reb_minheight.delta < p.reb_minheight.delta_min || (p.joint_speed_limit && p.reb_jointvel.delta < p.reb_jointvel.delta_min)) { cafe::set_last_error("ReB delta < delta_min is not supported"); return CAFE_ERR_UNSUPPORTED; }
   }
   return 0;
 }
@@ -553,13 +553,25 @@ extern "C" int cafe_gpu_destroy(CafeHandle* H) {
 static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_dev, int ldx, int B, const CafeOptions* opt) {
   if (!H || !opt || B <= 0 || B > H->max_batch) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
   if (!opt->MS) { cafe::set_last_error("single shooting (MS = false) is not supported: every knot must be a shooting node"); return CAFE_ERR_UNSUPPORTED; }
-  if (opt->update_relax != 1.0 || opt->update_ReB != 1.0) { cafe::set_last_error("update_relax / update_ReB != 1 are not supported by this build"); return CAFE_ERR_UNSUPPORTED; }
+  if (opt->max_AL_iter > 250) { cafe::set_last_error("more than 250 outer iterations: the relaxed-barrier update counts are 8 bits wide"); return CAFE_ERR_UNSUPPORTED; }
   if (opt->max_AL_iter * opt->max_DDP_iter + 1 > CAFE_HIST_CAP) { cafe::set_last_error("iteration caps exceed the history capacity"); return CAFE_ERR_UNSUPPORTED; }
   if (H->guess_B > 0 && B > H->guess_B) { cafe::set_last_error("batch larger than the initial-guess set"); return CAFE_ERR_ARG; }
   if (H->S.ph[0].ref_pp && B > H->ref_pp_B) { cafe::set_last_error("batch larger than the per-problem reference set"); return CAFE_ERR_ARG; }
   CUDA_OK(cudaSetDevice(H->device));
   SolverDev& S = H->S;
   S.B = B; S.opt = *opt;
+  {
+    // the relaxed-barrier parameters stay at their initial values unless an update can change one (ConstraintsBase.h:79-85, :194-209):
+    // a factor different from 1, or an initial delta below its floor delta_min
+    bool dyn = opt->ReB_active && (opt->update_relax != 1.0 || opt->update_ReB != 1.0);
+    for (int i = 0; i < S.n_phases && opt->ReB_active; ++i) {
+      const CafePhase& p = H->deck.phase[i];
+      dyn = dyn || p.reb_grf.delta < p.reb_grf.delta_min || p.reb_torque.delta < p.reb_torque.delta_min || p.reb_joint.delta < p.reb_joint.delta_min ||
+            p.reb_minheight.delta < p.reb_minheight.delta_min || (p.joint_speed_limit && p.reb_jointvel.delta < p.reb_jointvel.delta_min);
+    }
+    for (int i = 0; i < S.n_phases; ++i) { S.ph[i].reb_dyn = dyn ? 1 : 0; S.ph[i].reb_br = opt->update_relax; S.ph[i].reb_bw = opt->update_ReB; }
+  }
+  const bool reb_dyn = S.ph[0].reb_dyn != 0;
   S.NA = compute_alphas(*opt, S.eps);
   if (S.NA > H->NA) { cafe::set_last_error("step-size ladder longer than the allocated trial slots"); return CAFE_ERR_UNSUPPORTED; }
   // trial-slot strides are fixed by the allocation (H->NA slots), the ladder may be shorter
@@ -638,6 +650,7 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
     timed(H, CAFE_K_SELECT, [&] { cafe_dev::launch_select(H->dS, B, st, 0); });
     timed(H, CAFE_K_SELECT, [&] { cafe_dev::launch_compact(H->dS, st, 0); });
     timed(H, CAFE_K_ACCEPT, [&] { cafe_dev::launch_accept(H->dS, nthr_knots, st); });
+    if (reb_dyn) timed(H, CAFE_K_ACCEPT, [&] { cafe_dev::launch_reb_update(H->dS, nthr_knots, st); });
     CUDA_OK(cudaStreamSynchronize(st));  // S0 must stay alive until the copy has been consumed
     CUDA_OK(cudaMemcpyAsync(H->dS, &S, sizeof(SolverDev), cudaMemcpyHostToDevice, st));
   }
@@ -694,6 +707,7 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
     timed(H, CAFE_K_SELECT, [&] { cafe_dev::launch_select(H->dS, B, st, 1); });
     timed(H, CAFE_K_SELECT, [&] { cafe_dev::launch_compact(H->dS, st, 0); });
     timed(H, CAFE_K_ACCEPT, [&] { cafe_dev::launch_accept(H->dS, nthr_knots, st); });
+    if (reb_dyn) timed(H, CAFE_K_ACCEPT, [&] { cafe_dev::launch_reb_update(H->dS, nthr_knots, st); });
   }
   CUDA_OK(cudaEventRecord(H->eve, st));
   CUDA_OK(cudaStreamSynchronize(st));

@@ -198,7 +198,7 @@ __device__ __forceinline__ void wb_factor(double* sm, const WbRows& rw, double d
 
 // running cost of a whole-body knot (QuadraticTrackingCost + foot costs + dt * ReB terms) and the minimum of the path-constraint
 // values, from x, u, y (= GRF), pf, vf, rec in shared memory; same terms and summation order as WBModel::running_cost_k
-__device__ __forceinline__ double wb_cost_coop(const PhaseDev& ph, const double* sm, const RecRef rec, double* scr, bool reb, int lane, double& ming) {
+__device__ __forceinline__ double wb_cost_coop(const PhaseDev& ph, const double* sm, const RecRef rec, double* scr, bool reb, int lane, double& ming, const RebCtx& rcx) {
   const double* x = sm + WbSm::oX; const double* u = sm + WbSm::oU; const double* y = sm + WbSm::oGrf;
   const double* pf = sm + WbSm::oPf; const double* vf = sm + WbSm::oVf;
   const double dt = ph.dt;
@@ -220,19 +220,20 @@ __device__ __forceinline__ double wb_cost_coop(const PhaseDev& ph, const double*
   double mn = 0;
   for (int e = lane; e < 93; e += 32) {
     double g = 0, delta = 1, eps = 0; bool on = true;
-    if (e < 24) { const int i = e % 12; g = (e < 12 ? -u[i] : u[i]) + ph.torque_limit; delta = ph.reb_torque.delta; eps = ph.reb_torque.eps; }
-    else if (e < 48) { const int i = (e - 24) % 12; on = jv; g = (e < 36) ? x[24 + i] - ph.jointvel_lb : -x[24 + i] + ph.jointvel_ub; delta = ph.reb_jointvel.delta; eps = ph.reb_jointvel.eps; }
-    else if (e < 72) { const int i = (e - 48) % 12; on = jl; g = (e < 60) ? x[6 + i] - ph.joint_lb[i % 3] : -x[6 + i] + ph.joint_ub[i % 3]; delta = ph.reb_joint.delta; eps = ph.reb_joint.eps; }
-    else if (e == 72) { on = mh; g = x[2] - ph.h_min; delta = ph.reb_minheight.delta; eps = ph.reb_minheight.eps; }
+    const CafeRebParam* p0;
+    if (e < 24) { const int i = e % 12; g = (e < 12 ? -u[i] : u[i]) + ph.torque_limit; p0 = &ph.reb_torque; }
+    else if (e < 48) { const int i = (e - 24) % 12; on = jv; g = (e < 36) ? x[24 + i] - ph.jointvel_lb : -x[24 + i] + ph.jointvel_ub; p0 = &ph.reb_jointvel; }
+    else if (e < 72) { const int i = (e - 48) % 12; on = jl; g = (e < 60) ? x[6 + i] - ph.joint_lb[i % 3] : -x[6 + i] + ph.joint_ub[i % 3]; p0 = &ph.reb_joint; }
+    else if (e == 72) { on = mh; g = x[2] - ph.h_min; p0 = &ph.reb_minheight; }
     else {
       const int f = (e - 73) / 5, i = (e - 73) % 5;
       on = ph.contact[f] > 0;
       const double fx = y[3 * f], fy = y[3 * f + 1], fz = y[3 * f + 2], mu = ph.mu;
       g = (i == 0) ? fz : (i == 1) ? -fx + mu * fz : (i == 2) ? fx + mu * fz : (i == 3) ? -fy + mu * fz : fy + mu * fz;
-      delta = ph.reb_grf.delta; eps = ph.reb_grf.eps;
+      p0 = &ph.reb_grf;
     }
     double val = 0;
-    if (on) { mn = fmin(mn, g); val = eps * reb_value(g, delta); }
+    if (on) { rcx.get(*p0, e, delta, eps); mn = fmin(mn, g); val = eps * reb_value(g, delta); }
     scr[56 + e] = val;
   }
   for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(CAFE_FULL, mn, o));
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(128, 6) k_wb_fwd(const SolverDev* __restrict__
   if (lane == 1) { double nrm = 0; for (int i = 0; i < 36; ++i) nrm += scr[i] * scr[i]; if (sqrt(nrm) > 1e6) atomicOr(&ph.fail_t[(size_t)a * ldb + b], 1); }
   __syncwarp();
   double ming;
-  const double l = wb_cost_coop(ph, sm, wb_rec(ph, k, ldb, b), scr, S.opt.ReB_active != 0, lane, ming);
+  const double l = wb_cost_coop(ph, sm, wb_rec(ph, k, ldb, b), scr, S.opt.ReB_active != 0, lane, ming, reb_ctx(ph, k, ldb, b));
   if (lane == 0) { ph.cost_t[aS + (size_t)k * ldb + b] = l; ph.ming_t[aS + (size_t)k * ldb + b] = ming; }
 }
 
@@ -586,6 +587,7 @@ __global__ void __launch_bounds__(128, 5) k_wb_cost(const SolverDev* __restrict_
   const double* x = sm + WbSm::oX; const double* u = sm + WbSm::oU; const double* grf = sm + WbSm::oGrf;
   const double* J = sm + WbSm::oJ; const double* pf = sm + WbSm::oPf; const double* vf = sm + WbSm::oVf;
   const bool reb = S.opt.ReB_active != 0;
+  const RebCtx rcx = reb_ctx(ph, k, ldb, b);
   double* dposw = sm + WbSm::oLx; double* dvelw = dposw + 12; double* dg = dposw + 24;
   // lu, luu (diagonal): tracking + torque-limit barrier
   if (lane < 12) {
@@ -593,11 +595,12 @@ __global__ void __launch_bounds__(128, 5) k_wb_cost(const SolverDev* __restrict_
     double lu = dt * ph.r[i] * (u[i] - rec[CAFE_REF_UR + i]);
     double luu = dt * ph.r[i];
     if (reb) {
-      double bd1, bdd1, bd2, bdd2;
-      reb_derivs(-u[i] + ph.torque_limit, ph.reb_torque.delta, bd1, bdd1);
-      reb_derivs(u[i] + ph.torque_limit, ph.reb_torque.delta, bd2, bdd2);
-      lu += dt * (ph.reb_torque.eps * bd1 * (-1.0) + ph.reb_torque.eps * bd2);
-      luu += dt * (ph.reb_torque.eps * bdd1 + ph.reb_torque.eps * bdd2);
+      double bd1, bdd1, bd2, bdd2, dl1, ep1, dl2, ep2;
+      rcx.get(ph.reb_torque, i, dl1, ep1); rcx.get(ph.reb_torque, 12 + i, dl2, ep2);
+      reb_derivs(-u[i] + ph.torque_limit, dl1, bd1, bdd1);
+      reb_derivs(u[i] + ph.torque_limit, dl2, bd2, bdd2);
+      lu += dt * (ep1 * bd1 * (-1.0) + ep2 * bd2);
+      luu += dt * (ep1 * bdd1 + ep2 * bdd2);
     }
     ph.lu[gix(k, 12, i, ldb, b)] = lu;
     ph.luu[gix(k, 144, 13 * i, ldb, b)] = luu;
@@ -618,9 +621,10 @@ __global__ void __launch_bounds__(128, 5) k_wb_cost(const SolverDev* __restrict_
       const double Al[5][3] = {{0, 0, 1}, {-1, 0, mu}, {1, 0, mu}, {0, -1, mu}, {0, 1, mu}};
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
-        double bd, bdd;
-        reb_derivs(g[i], ph.reb_grf.delta, bd, bdd);
-        const double e1 = ph.reb_grf.eps * bd, e2 = ph.reb_grf.eps * bdd;
+        double bd, bdd, dl, ep;
+        rcx.get(ph.reb_grf, 73 + 5 * f + i, dl, ep);
+        reb_derivs(g[i], dl, bd, bdd);
+        const double e1 = ep * bd, e2 = ep * bdd;
 #pragma unroll
         for (int r = 0; r < 3; ++r) { gr[r] += e1 * Al[i][r];
 #pragma unroll
@@ -650,24 +654,27 @@ __global__ void __launch_bounds__(128, 5) k_wb_cost(const SolverDev* __restrict_
     }
     double v = dt * ph.q[i];
     if (jl && i >= 6 && i < 18) {
-      double b1, d1, b2, d2;
-      reb_derivs(x[i] - ph.joint_lb[(i - 6) % 3], ph.reb_joint.delta, b1, d1);
-      reb_derivs(-x[i] + ph.joint_ub[(i - 6) % 3], ph.reb_joint.delta, b2, d2);
-      lx += dt * (ph.reb_joint.eps * b1 - ph.reb_joint.eps * b2);
-      v += dt * (ph.reb_joint.eps * d1 + ph.reb_joint.eps * d2);
+      double b1, d1, b2, d2, dl1, ep1, dl2, ep2;
+      rcx.get(ph.reb_joint, 48 + (i - 6), dl1, ep1); rcx.get(ph.reb_joint, 60 + (i - 6), dl2, ep2);
+      reb_derivs(x[i] - ph.joint_lb[(i - 6) % 3], dl1, b1, d1);
+      reb_derivs(-x[i] + ph.joint_ub[(i - 6) % 3], dl2, b2, d2);
+      lx += dt * (ep1 * b1 - ep2 * b2);
+      v += dt * (ep1 * d1 + ep2 * d2);
     }
     if (mh && i == 2) {
-      double b1, d1;
-      reb_derivs(x[2] - ph.h_min, ph.reb_minheight.delta, b1, d1);
-      lx += dt * (ph.reb_minheight.eps * b1);
-      v += dt * (ph.reb_minheight.eps * d1);
+      double b1, d1, dl1, ep1;
+      rcx.get(ph.reb_minheight, 72, dl1, ep1);
+      reb_derivs(x[2] - ph.h_min, dl1, b1, d1);
+      lx += dt * (ep1 * b1);
+      v += dt * (ep1 * d1);
     }
     if (jv && i >= 24) {
-      double b1, b2, d1, d2;
-      reb_derivs(x[i] - ph.jointvel_lb, ph.reb_jointvel.delta, b1, d1);
-      reb_derivs(-x[i] + ph.jointvel_ub, ph.reb_jointvel.delta, b2, d2);
-      lx += dt * (ph.reb_jointvel.eps * b1 - ph.reb_jointvel.eps * b2);
-      v += dt * (ph.reb_jointvel.eps * d1 + ph.reb_jointvel.eps * d2);
+      double b1, b2, d1, d2, dl1, ep1, dl2, ep2;
+      rcx.get(ph.reb_jointvel, 24 + (i - 24), dl1, ep1); rcx.get(ph.reb_jointvel, 36 + (i - 24), dl2, ep2);
+      reb_derivs(x[i] - ph.jointvel_lb, dl1, b1, d1);
+      reb_derivs(-x[i] + ph.jointvel_ub, dl2, b2, d2);
+      lx += dt * (ep1 * b1 - ep2 * b2);
+      v += dt * (ep1 * d1 + ep2 * d2);
     }
     ph.lx[gix(k, 36, i, ldb, b)] = lx;
     dg[i] = v;
@@ -712,7 +719,7 @@ __global__ void __launch_bounds__(128, 5) k_wb_cost(const SolverDev* __restrict_
   if (lane < 3) lxxg[(size_t)(37 * lane) * ldb] = dg[lane];
   // ---- running cost at the current iterate (compute_cost, SinglePhase.cpp:236-262)
   double ming;
-  const double l = wb_cost_coop(ph, sm, rec, sm + WbSm::oScr, reb, lane, ming);
+  const double l = wb_cost_coop(ph, sm, rec, sm + WbSm::oScr, reb, lane, ming, rcx);
   if (lane == 0) ph.lk[(size_t)k * ldb + b] = l;
 }
 
