@@ -43,9 +43,9 @@ class MultiPhaseDDP {
     if (d->deck()->n_phases != n_phases) throw std::invalid_argument("set_multiPhaseProblem: the deck has another number of phases");
     for (int i = 0; i < n_phases; ++i)
       if (phases[i]->cafe_deck != d || phases[i]->cafe_phase_index != i) throw std::invalid_argument("set_multiPhaseProblem: phases must be the consecutive phases of one problem");
-    if (d != deck_) {   // another problem, or the next MPC window: its deck differs (horizons, references), the solver is re-created in solve()
-      if (h_) { cafe_gpu_destroy(h_); h_ = nullptr; }
-      deck_ = d;
+    if (d != deck_) {   // another problem, or the next MPC window: its deck differs (horizons, references); solve() hands it to the
+      deck_ = d;        // existing solver with cafe_gpu_update_deck (device buffers re-used) or creates the solver
+      deck_changed_ = true;
     }
   }
   void set_initial_condition(DVec<T> x0_in) { x0 = x0_in; x0_batch.assign(x0.data(), x0.data() + x0.size()); B_ = 1; }
@@ -63,7 +63,10 @@ class MultiPhaseDDP {
     using cafe_facade::check;
     if (!deck_) throw std::logic_error("solve: set_multiPhaseProblem first");
     if (B_ <= 0) throw std::logic_error("solve: set_initial_condition first");
-    if (!h_) check(cafe_gpu_create(deck_->deck(), device_, std::max(max_batch_, B_), &h_));
+    if (h_ && deck_changed_ && cafe_gpu_update_deck(h_, deck_->deck(), 0, 0) != 0) { cafe_gpu_destroy(h_); h_ = nullptr; }   // e.g. another model family
+    if (h_ && B_ > cap_) { cafe_gpu_destroy(h_); h_ = nullptr; }
+    if (!h_) { cap_ = std::max(max_batch_, B_); check(cafe_gpu_create(deck_->deck(), device_, cap_, &h_)); }
+    deck_changed_ = false;
     const long rec = cafe_solution_size(deck_->deck());
     std::vector<double> one(rec), guess((size_t)rec * B_);
     long off = 0;
@@ -113,8 +116,9 @@ class MultiPhaseDDP {
   int n_phases = 0;
   DVec<T> x0;
   std::vector<double> x0_batch;
-  int B_ = 0, device_ = 0, max_batch_ = 1;
+  int B_ = 0, device_ = 0, max_batch_ = 1, cap_ = 0;
   CafeHandle* h_ = nullptr;
+  bool deck_changed_ = false;
   std::shared_ptr<cafe_facade::DeckOwner> deck_;
   std::vector<CafeInfo> info_;
   std::vector<double> hist_;
