@@ -118,6 +118,27 @@ def test_mhpc_batch_1024_properties(cm, opt):
             assert np.all(np.linalg.eigvalsh(0.5 * (Quu + Quu.T)) > 0)
 
 
+def test_mhpc_headline_batch_4096_against_the_oracle(cm, opt):
+    """The headline batch (BASELINE metric: 4096 MHPC trot problems on one GPU; the two-stream tick and the list compaction are active at
+    this size only): 64 problems spread over the batch against the oracle (counters bit-exact, cost history / solution 1e-9), every
+    problem converged, and the first 1024 problems equal to the same problems solved as a 1024 batch, bit for bit (a problem's result does
+    not depend on the batch it is solved in)."""
+    from cafe_mpc_b200 import workload
+    prob = cm.MHPCProblem(CSV)
+    B = 4096
+    x0 = workload.mhpc_batch(B)
+    assert len(np.unique(x0.round(12), axis=0)) == B
+    s = solve_gpu(cm, prob, opt, x0)
+    info = s.get_solver_info()
+    assert all(i["status"] == 0 and i["feas"] <= opt.dynamics_feas_thresh for i in info)
+    compare_with_oracle(cm, prob, opt, x0, s, tuple(range(17, B, 64)))
+    head = s.get_commands(8)[:1024].copy()
+    s.close()
+    s2 = solve_gpu(cm, prob, opt, x0[:1024])
+    assert np.array_equal(head, s2.get_commands(8))
+    assert [tuple(i[k] for k in COUNTS) for i in info[:1024]] == [tuple(i[k] for k in COUNTS) for i in s2.get_solver_info()]
+
+
 # ---- BASELINE config 4: MHPC running barrel roll (multi-phase with impact jumps)
 @pytest.mark.parametrize("k0", [0, 205])
 def test_barrel_roll_matches_oracle_and_golden(cm, opt, k0):
