@@ -487,36 +487,36 @@ def test_barrel_to_matches_oracle_and_golden(cm):
     assert oi["cost"] < 0.01 * oh[0, 0] and oi["max_tconstr"] < fopt.tconstr_thresh   # the roll was found, both landings enforced
 
 
-def test_barrel_to_32_problems_at_full_caps_against_two_roundings_of_the_oracle(cm):
+def test_barrel_to_32_problems_at_full_caps_against_four_roundings_of_the_oracle(cm):
     """All 32 problems of the in-place barrel roll at the full 30 x 10 caps (~270 iterations, ~2 000 line-search trials each) against the
-    committed counters of the CPU oracle in TWO roundings: the regular build (FMA contraction) and the same sources built without it
-    (tests/golden/barrel_to_two_roundings.json, made by tools/oracle_sensitivity.py). The two builds of the oracle agree with each other
-    on 29 problems and part ways on three (13, 15, 29: a difference of 1e-16 in the first sweep, amplified 3-5 x per iteration while the
-    roll is being found, flips one Armijo test): "decisions bit-exact" is well posed on the 29, and there the GPU must reproduce every
-    counter and the final cost to 1e-8; on the three it must still end at the same iteration / outer-iteration counts and within the
-    spread of the two oracle builds (1e-3)."""
+    committed counters of the CPU oracle in FOUR roundings of one algorithm (tests/golden/barrel_to_four_roundings.json, made by
+    tools/oracle_sensitivity.py): the oracle's sources with / without FMA contraction x the reference's CasADi kinematic-partial file
+    compiled -O1 / -O3. The four builds agree with each other on 28 problems and part ways on four (13, 15, 27, 29: a last-bit difference in
+    the first sweep, amplified 3-5 x per iteration while the roll is being found, flips one Armijo test): "decisions bit-exact" is well posed
+    on the 28, and there the GPU must reproduce every counter and the final cost to 1e-8; on the four it must still end at the same
+    iteration / outer-iteration counts and within the spread of the oracle builds (1e-3)."""
     import json
     from cafe_mpc_b200 import workload
     prob = cm.BarrelRollProblem()
     fopt = cm.load_hsddp_setting(workload.BARREL_TO_DDP_SETTING)
-    g = json.load(open(os.path.join(REPO, "tests/golden/barrel_to_two_roundings.json")))
+    g = json.load(open(os.path.join(REPO, "tests/golden/barrel_to_four_roundings.json")))["builds"]
     x0 = workload.mhpc_batch(32)
     s = cm.MultiPhaseDDP(prob, 0, 32)
     s.set_initial_condition(x0)
     s.set_initial_guess(prob.initial_guess(x0))
     s.solve(fopt)
     info = s.get_solver_info()
-    split = [b for b in range(32) if g["fma"][b][0] != g["no_fma"][b][0]]
-    assert split == [13, 15, 29]
+    split = [b for b in range(32) if len(set(tuple(col[b][0]) for col in g.values())) > 1]
+    assert split == [13, 15, 27, 29]
     bad = []
     for b in range(32):
         got = [info[b][k] for k in COUNTS]
-        ca, cb = g["fma"][b], g["no_fma"][b]
+        ref = g["fma_kinO3"][b]
         if b in split:
-            assert [got[i] for i in (0, 1, 4, 5)] == [ca[0][i] for i in (0, 1, 4, 5)], b
-            assert min(abs(info[b]["cost"] - c[1]) for c in (ca, cb)) < 1e-3 * abs(ca[1]), b
-        elif got != ca[0] or abs(info[b]["cost"] - ca[1]) > 1e-8 * abs(ca[1]):
-            bad.append((b, got, ca[0], info[b]["cost"], ca[1]))
+            assert [got[i] for i in (0, 1, 4, 5)] == [ref[0][i] for i in (0, 1, 4, 5)], b
+            assert min(abs(info[b]["cost"] - col[b][1]) for col in g.values()) < 1e-3 * abs(ref[1]), b
+        elif got != ref[0] or abs(info[b]["cost"] - ref[1]) > 1e-8 * abs(ref[1]):
+            bad.append((b, got, ref[0], info[b]["cost"], ref[1]))
     assert not bad, bad
 
 

@@ -3,7 +3,7 @@ the regular build (-O3 -march=x86-64-v3: fused multiply-adds, AVX2 reductions) a
 (-O2 -ffp-contract=off -march=x86-64), i.e. two legal roundings of one and the same algorithm, and counts the problems whose counters
 (status, iterations, line-search trials, regularisation steps, outer iterations, history length) differ.
 usage: oracle_sensitivity.py [mhpc|hkd|barrel|loco|barrel_to] [N] [variant.so] [dump.json]
-dump.json receives, per problem, the counters and the final cost of both builds (tests/golden/barrel_to_two_roundings.json was made this way)."""
+dump.json receives, per problem, the counters and the final cost of both builds (tests/golden/barrel_to_four_roundings.json merges two such dumps: the kinematic-partial file of oracle/_ref compiled -O1 and -O3)."""
 import ctypes as C, json, multiprocessing as mp, os, subprocess, sys, time
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "tests")); sys.path.insert(0, os.path.join(R, "tools"))
