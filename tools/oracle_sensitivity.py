@@ -47,7 +47,13 @@ if __name__ == "__main__":
         a = pool.map(worker, [(kind, c, None) for c in chunks])
     with mp.Pool(cores) as pool:
         b = pool.map(worker, [(kind, c, variant) for c in chunks])
-    a = [r for ch in a for r in ch]; b = [r for ch in b for r in ch]
+    def in_order(chunked):   # chunk c holds problems c, c + cores, c + 2 cores, ...
+        out = [None] * N
+        for c, ch in enumerate(chunked):
+            for j, r in enumerate(ch):
+                out[c + cores * j] = r
+        return out
+    a = in_order(a); b = in_order(b)
     mism = sum(1 for ra, rb in zip(a, b) if ra[0] != rb[0])
     cost = max(abs(ra[1] - rb[1]) / max(abs(ra[1]), 1e-300) for ra, rb in zip(a, b))
     sol = max(np.abs(ra[2] - rb[2]).max() / np.abs(ra[2]).max() for ra, rb in zip(a, b))
