@@ -338,6 +338,11 @@ class MultiGPUDDP:
         self.B = x0.shape[0]
         check(lib.cafe_gpu_multi_solve_batch(self._m, x0.ctypes.data_as(C.c_void_p), self.B, C.byref(option)))
 
+    def update_deck(self, problem, k_advance, B=None):
+        """cafe_gpu_multi_update_deck: the MPC update on every GPU's solver (B = 0: cold start on the new deck)"""
+        check(lib.cafe_gpu_multi_update_deck(self._m, problem.deck, k_advance, self.B if B is None else B))
+        self.problem = problem
+
     def get_solver_info(self):
         info = (Info * self.B)()
         check(lib.cafe_gpu_multi_get_info(self._m, info))

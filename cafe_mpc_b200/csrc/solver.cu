@@ -1486,6 +1486,18 @@ extern "C" int cafe_gpu_multi_solve_batch(CafeMulti* M, const double* x0, int B,
   return 0;
 }
 
+// the MPC update on every GPU's solver (cafe_gpu_update_deck): each keeps its slice of the previous solve as the warm start. B = the batch of
+// the previous cafe_gpu_multi_solve_batch (the slices must not move), or 0 for a cold start on the new deck.
+extern "C" int cafe_gpu_multi_update_deck(CafeMulti* M, const CafeDeck* deck, int k_advance, int B) {
+  if (!M || !deck || (B != 0 && B != M->B)) { cafe::set_last_error("bad argument: B must be the previous batch size or 0"); return CAFE_ERR_ARG; }
+  for (int g = 0; g < M->ndev; ++g) {
+    const int nb = B > 0 ? M->hi[g] - M->lo[g] : 0;
+    int rc = cafe_gpu_update_deck(M->h[g], deck, k_advance, nb > 0 ? nb : 0);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
 extern "C" int cafe_gpu_multi_get_info(CafeMulti* M, CafeInfo* info) {
   if (!M || !info) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
   for (int g = 0; g < M->ndev; ++g) {

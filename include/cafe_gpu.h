@@ -180,6 +180,7 @@ int cafe_gpu_multi_destroy(CafeMulti* m);
 int cafe_gpu_multi_ndev(const CafeMulti* m);
 CafeHandle* cafe_gpu_multi_handle(CafeMulti* m, int g); /* the per-GPU solver (histories, traces, debug reads) */
 int cafe_gpu_multi_solve_batch(CafeMulti* m, const double* x0 /*host [B][n0]*/, int B, const CafeOptions* opt);
+int cafe_gpu_multi_update_deck(CafeMulti* m, const CafeDeck* new_deck, int k_advance, int B); /* cafe_gpu_update_deck on every GPU's slice */
 int cafe_gpu_multi_get_info(CafeMulti* m, CafeInfo* info /*[B]*/);
 int cafe_gpu_multi_get_commands(CafeMulti* m, int n_gain_knots, double* cmd /*host [B][cafe_command_size]*/);
 /* (b) one process per GPU (torchrun, MPI): rank 0 makes the id, the launcher hands it to every rank */

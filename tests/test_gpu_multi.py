@@ -43,6 +43,31 @@ def test_create_multi_on_one_gpu_equals_single_solver():
     assert np.array_equal(m.get_commands(8), cmd1)
 
 
+@pytest.mark.parametrize("ndev", [1, 2])
+def test_multi_mpc_update_equals_single_solver(ndev):
+    """cafe_gpu_multi_update_deck: two MPC updates on every GPU's slice == the same updates on one solver, bit for bit"""
+    if _ngpu() < ndev:
+        pytest.skip("needs %d GPUs" % ndev)
+    import copy
+    import cafe_mpc_b200 as cm
+    from cafe_mpc_b200 import api, workload
+    opt = cm.load_hsddp_setting(os.path.join(REPO, "data/MHPC/settings/ddp_setting.info"))
+    ort = copy.copy(opt); ort.max_AL_iter = opt.max_AL_iter_runtime; ort.max_DDP_iter = opt.max_DDP_iter_runtime
+    B, k0 = 22, 8
+    x0 = workload.mhpc_batch(B)
+    prob = cm.MHPCProblem(CSV, k0=k0)
+    one = cm.MultiPhaseDDP(prob, 0, B); one.set_initial_condition(x0); one.solve(opt)
+    m = api.MultiGPUDDP(prob, ndev, B); m.solve(x0, opt)
+    for step in range(2):
+        k0 += 2
+        p1 = cm.MHPCProblem(CSV, k0=k0, mpc_update_nsteps=2)
+        x1 = one.planned_state(2) + 1e-3 * (x0 - x0[0])
+        one.update_deck(p1, 2); one.set_initial_condition(x1); one.solve(ort)
+        m.update_deck(p1, 2); m.solve(x1, ort)
+        assert m.get_solver_info() == one.get_solver_info(), step
+        assert np.array_equal(m.get_commands(8), one.get_commands(8)), step
+
+
 @pytest.mark.parametrize("ndev", [2, 4])
 def test_create_multi_equals_single_gpu_bitwise(ndev):
     if _ngpu() < ndev:
