@@ -156,6 +156,7 @@ def cpu_sample(x0, cores, per_core, workload):
 
 
 def run_reference(args):
+    os.environ["CAFE_HOST_ONLY"] = "1"   # before cafe_mpc_b200 is imported: deck builders from libcafe_host.so, no CUDA library in this process
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:

@@ -10,6 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libcafe_gpu.so")
+HOST_LIB = os.path.join(HERE, "libcafe_host.so")   # the problem builders / settings readers alone, g++ only: what the CPU baseline arm loads
 
 # source -> dependencies besides itself (paths relative to csrc/)
 ABI = ["../../include/cafe_gpu.h", "../../include/cafe_deck.h"]
@@ -79,6 +80,16 @@ def build(force=False, verbose=False):
         if res.returncode != 0:
             sys.stderr.write(logs[-1])
             raise RuntimeError("nvcc link failed")
+    # host-only library: the same four host sources compiled by g++ (no CUDA runtime in the process that loads it)
+    host_src = [os.path.join(CSRC, s) for s in SOURCES if s.startswith("host/")]
+    host_deps = host_src + [os.path.join(CSRC, d) for s in SOURCES if s.startswith("host/") for d in SOURCES[s]]
+    if force or _stale(HOST_LIB, host_deps):
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", HOST_LIB] + host_src + ["-lstdc++", "-lm"]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        logs.append(" ".join(cmd) + "\n" + res.stdout + res.stderr)
+        if res.returncode != 0:
+            sys.stderr.write(logs[-1])
+            raise RuntimeError("host library build failed")
     if logs:
         with open(os.path.join(HERE, "build.log"), "a" if not force else "w") as f:
             f.write("\n".join(logs))

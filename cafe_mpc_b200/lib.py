@@ -1,14 +1,17 @@
 """ctypes binding of libcafe_gpu.so (the C ABI in include/cafe_gpu.h).
 
 The library must be built (cafe_mpc_b200/build.py or __graft_entry__.build()); there is no
-Python / CPU fallback: if it is missing, importing this module raises."""
+Python / CPU fallback: if it is missing, importing this module raises.
+CAFE_HOST_ONLY=1 (set by bench.py's CPU baseline arm before the import) loads libcafe_host.so instead: the problem builders and settings
+readers alone, built by g++ - no solver entry point exists in that process and no CUDA code is mapped."""
 import ctypes as C
 import os
 
 from ._ctypes_defs import Deck, Info, Options, CAFE_NKERNELS
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcafe_gpu.so")
+HOST_ONLY = os.environ.get("CAFE_HOST_ONLY", "0") == "1"
+LIB_PATH = os.path.join(HERE, "libcafe_host.so" if HOST_ONLY else "libcafe_gpu.so")
 
 
 class CafeError(RuntimeError):
@@ -20,7 +23,7 @@ class CafeError(RuntimeError):
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
-            "libcafe_gpu.so is not built (%s). Run `python cafe_mpc_b200/build.py`; "
+            "the library is not built (%s). Run `python cafe_mpc_b200/build.py`; "
             "the product path has no fallback implementation." % LIB_PATH)
     lib = C.CDLL(LIB_PATH)
     vp, dp, ip = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)
@@ -42,6 +45,8 @@ def _load():
     lib.cafe_solution_size.argtypes = [C.POINTER(Deck)]
     lib.cafe_command_size.restype = C.c_long
     lib.cafe_command_size.argtypes = [C.POINTER(Deck), C.c_int]
+    if HOST_ONLY:
+        return lib
     lib.cafe_lcm_command_size.restype = C.c_long
     lib.cafe_lcm_command_size.argtypes = [C.c_int]
     lib.cafe_hkd_lcm_command_size.restype = C.c_long

@@ -12,6 +12,7 @@ import pytest
 from oracle_bindings import casadi_eval, oracle_solve
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSV_TROT = os.path.join(REPO, "data/Reference/Data/trot/heuristic/quad_reference.csv")
 
 
 # ------------------------------------------------------------------ golden vectors
@@ -227,6 +228,28 @@ def test_abi_exports_every_declared_symbol(cm):
     for name in declared:
         assert hasattr(lib, name), name
     assert declared == set(EXPORTED)
+
+
+def test_host_only_library_maps_no_cuda_code(built_lib):
+    """libcafe_host.so (what bench.py's CPU baseline arm loads, CAFE_HOST_ONLY=1): the problem builders and settings readers compiled by g++ alone -
+    the same decks as the full library, no CUDA library mapped into the process, and no solver entry point to fall back on."""
+    import subprocess, sys
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import cafe_mpc_b200 as cm\n"
+        "p = cm.MHPCProblem(%r); h = cm.HKDProblem(%r)\n"
+        "print([x.horizon for x in p.phases()], [x.horizon for x in h.phases()])\n"
+        "m = open('/proc/self/maps').read()\n"
+        "print(m.count('libcuda'), m.count('libcudart'), m.count('libcafe_gpu'), m.count('libcafe_host') > 0)\n"
+        "from cafe_mpc_b200.lib import lib\n"
+        "print(hasattr(lib, 'cafe_gpu_create'), hasattr(lib, 'cafe_gpu_solve_batch'))\n" % (REPO, CSV_TROT, CSV_TROT))
+    env = dict(os.environ, CAFE_HOST_ONLY="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = r.stdout.strip().splitlines()
+    assert lines[0] == "[11, 14, 10] [11, 25, 24]"
+    assert lines[1] == "0 0 0 True"
+    assert lines[2] == "False False"
 
 
 def test_abi_sizes_and_argument_errors(cm, hkd_problem):
