@@ -221,7 +221,7 @@ struct Bwd2Layout {
 // One phase of the sweep. N, M, PY: phase dimensions; NNEXT: state dimension of the next phase (for the jump); WB: use the
 // whole-body block structure. On entry, when the phase has a successor, sG/sH hold G0+/H0+ of the successor (ld ldH).
 template <int N, int M, int PY, int NNEXT, bool WB, int NT, class L>
-__device__ void sweep_phase2(const SolverDev& S, int pi, int b, int t, bool run, bool& ok, double reg, double* sm, double& min_piv) {
+__device__ void sweep_phase2(const SolverDev& S, int pi, int b, int t, bool run, bool& ok, double reg, double* sm, double& min_piv, double& dv1, double& dv2) {
   const PhaseDev& ph = S.ph[pi];
   const int ldb = S.ldb, h = ph.h;
   constexpr int ldH = L::ldH, ldA = L::ldA, ldM = L::ldM, ldP = L::ldP;
@@ -235,6 +235,9 @@ __device__ void sweep_phase2(const SolverDev& S, int pi, int b, int t, bool run,
   double* sL = sT;    // LDL^T factor after T is dead
   (void)sLy; (void)sCD; (void)sSCD; (void)sLyy;
   const double dt = ph.dt;
+  // expected cost change from the sweep itself, used when there is no linear rollout (MS = false): dV_k = -Qu^T dU, dV_1 -= dV_k, dV_2 += dV_k
+  // per phase, phases summed last to first (SinglePhase.cpp:383-387, MultiPhaseDDP.cpp:174-213); thread 0 keeps the sums
+  double pdv1 = 0, pdv2 = 0;
 
   // ---- boundary: (G', H') = (Px^T G0+, Px^T H0+ Px) (impact_aware_step), G[h] = Phix + G', H[h] = Phixx + H'
   if (ph.has_next) {
@@ -487,6 +490,12 @@ __device__ void sweep_phase2(const SolverDev& S, int pi, int b, int t, bool run,
         ph.G[gix(k, N, j, ldb, b)] = s;
       }
       for (int j = t; j < M; j += NT) ph.dU[gix(k, M, j, ldb, b)] = dUs[j];
+      if (t == 0 && !S.opt.MS) {
+        double d = 0;
+        for (int i = 0; i < M; ++i) d += sQu[i] * dUs[i];
+        const double dV_k = -d;
+        pdv1 -= dV_k; pdv2 += dV_k;
+      }
       double* Kg = ph.K + gix(k, M * N, 0, ldb, b);
       for (int e = t; e < M * N; e += NT) Kg[(size_t)e * ldb] = sK[(e % M) + ldM * (e / M)];
       {   // second, problem-major copy (the ld x N tile as it is) for the linear rollout of this kernel: 16-byte stores / copies
@@ -519,6 +528,7 @@ __device__ void sweep_phase2(const SolverDev& S, int pi, int b, int t, bool run,
   __syncthreads();
   if (run && ok) for (int i = t; i < N; i += NT) { sG[i] = sGn[i]; ph.G[gix(0, N, i, ldb, b)] = sGn[i]; }
   __syncthreads();
+  dv1 += pdv1; dv2 += pdv2;
 }
 
 // multiple-shooting linear rollout of one phase (SinglePhase::linear_rollout), eps = 1. Every knot's operands are staged with
@@ -716,6 +726,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NT, 4) k_bwd2(const 
   // every word of the tiles is finite from here on (the fragment loads of partial edge tiles read neighbouring tiles)
   for (int e = t; e < L::total; e += NT) sm[e] = 0.0;
   double min_piv = 1e300;
+  double sdv1 = 0, sdv2 = 0;   // thread 0: expected cost change summed by the sweep (MS = false)
   for (int round = 0;; ++round) {
     cl.sync();
     bool any = false;
@@ -728,14 +739,15 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NT, 4) k_bwd2(const 
     const bool sweeping = s_state == 0;
     bool ok = true;
     const double reg = s_reg;
+    if (sweeping) { sdv1 = 0; sdv2 = 0; }   // a sweep that is repeated with more regularisation starts its sums again
     for (int pi = S.n_phases - 1; pi >= 0; --pi) {
       const int model = S.ph[pi].model, nm = S.ph[pi].has_next ? S.ph[pi + 1].model : -1;
       if constexpr (DECK == 0) {
-        if (model == CAFE_MODEL_HKD) sweep_phase2<24, 24, 0, 24, false, NT, L>(S, pi, b, t, sweeping, ok, reg, sm, min_piv);
+        if (model == CAFE_MODEL_HKD) sweep_phase2<24, 24, 0, 24, false, NT, L>(S, pi, b, t, sweeping, ok, reg, sm, min_piv, sdv1, sdv2);
       } else {
-        if (model == CAFE_MODEL_SRB) sweep_phase2<12, 12, 0, 12, false, NT, L>(S, pi, b, t, sweeping, ok, reg, sm, min_piv);
-        else if (model == CAFE_MODEL_WB && nm == CAFE_MODEL_SRB) sweep_phase2<36, 12, 12, 12, true, NT, L>(S, pi, b, t, sweeping, ok, reg, sm, min_piv);
-        else if (model == CAFE_MODEL_WB) sweep_phase2<36, 12, 12, 36, true, NT, L>(S, pi, b, t, sweeping, ok, reg, sm, min_piv);
+        if (model == CAFE_MODEL_SRB) sweep_phase2<12, 12, 0, 12, false, NT, L>(S, pi, b, t, sweeping, ok, reg, sm, min_piv, sdv1, sdv2);
+        else if (model == CAFE_MODEL_WB && nm == CAFE_MODEL_SRB) sweep_phase2<36, 12, 12, 12, true, NT, L>(S, pi, b, t, sweeping, ok, reg, sm, min_piv, sdv1, sdv2);
+        else if (model == CAFE_MODEL_WB) sweep_phase2<36, 12, 12, 36, true, NT, L>(S, pi, b, t, sweeping, ok, reg, sm, min_piv, sdv1, sdv2);
       }
       (void)nm;
     }
@@ -758,7 +770,8 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NT, 4) k_bwd2(const 
     for (int i = t; i < NX; i += NT) sDx[i] = 0.0;
     __syncthreads();
     double part1 = 0, part2 = 0;
-    for (int pi = 0; pi < S.n_phases; ++pi) {
+    // MS = false: no linear rollout (MultiPhaseDDP.cpp:330-333) - dX stays zero, the expected cost change is the sweep's
+    for (int pi = 0; pi < S.n_phases && S.opt.MS; ++pi) {
       const int model = S.ph[pi].model;
       if constexpr (DECK == 0) {
         if (model == CAFE_MODEL_HKD) lin_phase2<24, 24, false, NT, L>(S, pi, b, t, success, sm, part1, part2);
@@ -776,6 +789,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NT, 4) k_bwd2(const 
       __syncthreads();
     }
     dV1 = sRed[0]; dV2 = sRed[NT];
+    if (!S.opt.MS) { dV1 = sdv1; dV2 = sdv2; }
   }
   if (t == 0 && mine) {
     double r = s_reg / 20;

@@ -32,6 +32,29 @@
 namespace cafe_dev {
 
 // ------------------------------------------------------------------------------------------- K-ROLL
+// knots 0 .. kend-1 of phase pi integrated in place from x (the state at knot 0): U = Ubar + eps dU + K (X - Xbar)
+template <class Model>
+__device__ __noinline__ void chain_phase(const SolverDev& S, int pi, int kend, int a, int b, double* x) {
+  constexpr int N = Model::N, M = Model::M, PY = Model::PY;
+  const PhaseDev& ph = S.ph[pi];
+  const int ldb = S.ldb;
+  const double eps = S.eps[a];
+  double rec_local[CAFE_REF_W];
+  for (int kk = 0; kk < kend; ++kk) {
+    const double* rec = knot_record(ph, kk, ldb, b, rec_local);
+    double u[M], xn[N], y[PY > 0 ? PY : 1], l, ming;
+    for (int i = 0; i < M; ++i) u[i] = 0;
+    const double* Kg = ph.K + gix(kk, M * N, 0, ldb, b);
+    for (int j = 0; j < N; ++j) {
+      const double dj = x[j] - ph.Xbar[gix(kk, N, j, ldb, b)];
+      for (int i = 0; i < M; ++i) u[i] += Kg[(size_t)(i + M * j) * ldb] * dj;
+    }
+    for (int i = 0; i < M; ++i) u[i] = ph.Ubar[gix(kk, M, i, ldb, b)] + eps * ph.dU[gix(kk, M, i, ldb, b)] + u[i];
+    Model::roll(ph, rec, x, u, xn, y, S.opt.ReB_active != 0, l, ming, reb_ctx(ph, kk, ldb, b));   // only xn is used
+    for (int i = 0; i < N; ++i) x[i] = xn[i];
+  }
+}
+
 // State of knot k of a phase WITHOUT shooting states (PhaseDev::single_shooting; SinglePhase.cpp:187-221 with an empty SS_set): the
 // phase is integrated from the state the previous phase hands over (its trial end state through the reset map; the solver's x0 for
 // the first phase), U = Ubar + eps dU + K (X - Xbar). Such a phase is the freshly opened tail of an MPC update, at most dt_mpc / dt
@@ -50,19 +73,26 @@ __device__ __noinline__ void single_shooting_state(const SolverDev& S, int pi, i
     for (int i = 0; i < N; ++i) xe[i] = pv.Xbar[gix(pv.h, N, i, ldb, b)] + eps * pv.dX[gix(pv.h, N, i, ldb, b)];
     Model::resetmap(pv, xe, x);
   }
-  double rec_local[CAFE_REF_W];
-  for (int kk = 0; kk < k; ++kk) {
-    const double* rec = knot_record(ph, kk, ldb, b, rec_local);
-    double u[M], xn[N], y[PY > 0 ? PY : 1], l, ming;
-    for (int i = 0; i < M; ++i) u[i] = 0;
-    const double* Kg = ph.K + gix(kk, M * N, 0, ldb, b);
-    for (int j = 0; j < N; ++j) {
-      const double dj = x[j] - ph.Xbar[gix(kk, N, j, ldb, b)];
-      for (int i = 0; i < M; ++i) u[i] += Kg[(size_t)(i + M * j) * ldb] * dj;
+  chain_phase<Model>(S, pi, k, a, b, x);
+}
+
+// Whole-problem single shooting (HSDDP_OPTION::MS = false: MultiPhaseDDP::hybrid_rollout clears every phase's shooting set,
+// MultiPhaseDDP.cpp:65-68, so X[0] = x_init and X[k+1] = Xsim[k+1] everywhere, SinglePhase.cpp:187-221): the state of knot k of phase pi is
+// the chain from the solver's x0 through every earlier phase and its reset map. Every knot's thread repeats the chain up to its own knot
+// (quadratic work: the option is there for completeness - no shipped problem uses it - not for speed).
+__device__ __noinline__ void whole_problem_shooting_state(const SolverDev& S, int pi, int k, int a, int b, double* x /*[CAFE_MAX_N]*/) {
+  const int ldb = S.ldb;
+  for (int i = 0; i < S.ph[0].n; ++i) x[i] = S.x0[(size_t)i * ldb + b];
+  for (int q = 0; q <= pi; ++q) {
+    const PhaseDev& ph = S.ph[q];
+    const int kend = (q == pi) ? k : ph.h;
+    double xn[CAFE_MAX_N];
+    switch (ph.model) {
+      case CAFE_MODEL_HKD: chain_phase<HKDModel>(S, q, kend, a, b, x); if (q < pi) HKDModel::resetmap(ph, x, xn); break;
+      case CAFE_MODEL_WB: chain_phase<WBModel>(S, q, kend, a, b, x); if (q < pi) WBModel::resetmap(ph, x, xn); break;
+      default: chain_phase<SRBModel>(S, q, kend, a, b, x); if (q < pi) SRBModel::resetmap(ph, x, xn); break;
     }
-    for (int i = 0; i < M; ++i) u[i] = ph.Ubar[gix(kk, M, i, ldb, b)] + eps * ph.dU[gix(kk, M, i, ldb, b)] + u[i];
-    Model::roll(ph, rec, x, u, xn, y, S.opt.ReB_active != 0, l, ming, reb_ctx(ph, kk, ldb, b));   // only xn is used
-    for (int i = 0; i < N; ++i) x[i] = xn[i];
+    if (q < pi) for (int i = 0; i < S.ph[q + 1].n; ++i) x[i] = xn[i];
   }
 }
 
@@ -78,7 +108,10 @@ __device__ void roll_knot(const SolverDev& S, int pi, int k, int a, int b) {
   const size_t aS = (size_t)a * (h + 1) * ldb;
   double x[N], dlt[N];
   const bool ss = ph.single_shooting != 0;
-  if (ss) single_shooting_state<Model>(S, pi, k, a, b, x);
+  if (ss) {
+    if (S.opt.MS) single_shooting_state<Model>(S, pi, k, a, b, x);
+    else { double xw[CAFE_MAX_N]; whole_problem_shooting_state(S, pi, k, a, b, xw); for (int i = 0; i < N; ++i) x[i] = xw[i]; }
+  }
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     const double xb = ph.Xbar[gix(k, N, i, ldb, b)];

@@ -552,7 +552,6 @@ extern "C" int cafe_gpu_destroy(CafeHandle* H) {
 
 static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_dev, int ldx, int B, const CafeOptions* opt) {
   if (!H || !opt || B <= 0 || B > H->max_batch) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
-  if (!opt->MS) { cafe::set_last_error("single shooting (MS = false) is not supported: every knot must be a shooting node"); return CAFE_ERR_UNSUPPORTED; }
   if (opt->max_AL_iter > 250) { cafe::set_last_error("more than 250 outer iterations: the relaxed-barrier update counts are 8 bits wide"); return CAFE_ERR_UNSUPPORTED; }
   if (opt->max_AL_iter * opt->max_DDP_iter + 1 > CAFE_HIST_CAP) { cafe::set_last_error("iteration caps exceed the history capacity"); return CAFE_ERR_UNSUPPORTED; }
   if (H->guess_B > 0 && B > H->guess_B) { cafe::set_last_error("batch larger than the initial-guess set"); return CAFE_ERR_ARG; }
@@ -571,6 +570,8 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
     }
     for (int i = 0; i < S.n_phases; ++i) { S.ph[i].reb_dyn = dyn ? 1 : 0; S.ph[i].reb_br = opt->update_relax; S.ph[i].reb_bw = opt->update_ReB; }
   }
+  // MS = false: MultiPhaseDDP::hybrid_rollout clears every phase's shooting set (MultiPhaseDDP.cpp:65-68) - whole-problem single shooting
+  for (int i = 0; i < S.n_phases; ++i) S.ph[i].single_shooting = (H->deck.phase[i].single_shooting || !opt->MS) ? 1 : 0;
   const bool reb_dyn = S.ph[0].reb_dyn != 0;
   S.NA = compute_alphas(*opt, S.eps);
   if (S.NA > H->NA) { cafe::set_last_error("step-size ladder longer than the allocated trial slots"); return CAFE_ERR_UNSUPPORTED; }

@@ -196,7 +196,9 @@ void Phase::linear_rollout(double eps) {
  * (update_SS_config(h+1): HKDProblem.cpp:105, MHPCProblem.cpp:209,243). */
 bool Phase::hybrid_rollout(double eps, bool MS) {
   Xsim[0] = x_init;
-  const bool ss = ph->single_shooting != 0;  /* empty SS_set: the freshly opened tail phase of an MPC update (MHPCProblem.cpp:366-369) */
+  /* empty SS_set: the freshly opened tail phase of an MPC update (MHPCProblem.cpp:366-369), or every phase when MS is off
+   * (MultiPhaseDDP::hybrid_rollout calls update_SS_config(0) on each phase, MultiPhaseDDP.cpp:65-68) */
+  const bool ss = ph->single_shooting != 0 || !MS;
   /* SS_set.front()==0 */
   if (!ss) for (int i = 0; i < n; ++i) X[0][i] = Xbar[0][i] + eps * dX[0][i];
   else X[0] = x_init;

@@ -118,6 +118,29 @@ def test_mhpc_batch_1024_properties(cm, opt):
             assert np.all(np.linalg.eigvalsh(0.5 * (Quu + Quu.T)) > 0)
 
 
+@pytest.mark.parametrize("k0", [0, 20])
+def test_mhpc_whole_problem_single_shooting_matches_oracle(cm, opt, k0):
+    """MS = false on the cascaded-fidelity deck: the chain runs through whole-body phases, the touchdown impact (k0 = 20) and the
+    whole-body -> single-rigid-body reset map; expected cost change from the sweep. GPU == oracle: counters bit-exact; costs and
+    trajectories at 1e-7 / 1e-6 instead of 1e-9 - a 35-knot open-loop chain compounds the 1e-13 per-knot differences of the two
+    whole-body models (measured 1.7e-9 on one history entry)."""
+    from cafe_mpc_b200 import workload
+    o = copy.copy(opt); o.MS = 0; o.max_AL_iter = 3; o.max_DDP_iter = 6
+    prob = cm.MHPCProblem(CSV, k0=k0)
+    x0 = workload.mhpc_batch(3)
+    s = solve_gpu(cm, prob, o, x0)
+    info = s.get_solver_info(); hist = s.get_history(64); sol = s.get_solution()
+    for b in range(3):
+        oi, oh, ot, osol = oracle_solve(prob.deck, o, x0[b])
+        assert [info[b][k] for k in COUNTS] == [oi[k] for k in COUNTS], (b, info[b], oi)
+        np.testing.assert_allclose(hist[b, :oi["n_hist"], 0], oh[:, 0], rtol=1e-7)
+        assert info[b]["feas"] == 0.0
+        gp, op = cm.unpack_solution(prob.deck, sol[b]), cm.unpack_solution(prob.deck, osol)
+        for pg, po in zip(gp, op):
+            for name in ("Xbar", "Ubar", "Y", "K"):
+                assert relerr(pg[name], po[name]) < 1e-6, (b, name)
+
+
 def test_mhpc_headline_batch_4096_against_the_oracle(cm, opt):
     """The headline batch (BASELINE metric: 4096 MHPC trot problems on one GPU; the two-stream tick and the list compaction are active at
     this size only): 64 problems spread over the batch against the oracle (counters bit-exact, cost history / solution 1e-9), every

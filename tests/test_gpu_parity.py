@@ -158,12 +158,30 @@ def test_unsupported_options_fail_loudly(cm, hkd_problem, hkd_options):
     x0 = workload.hkd_batch(hkd_problem, 2)
     s = cm.MultiPhaseDDP(hkd_problem, 0, 2)
     s.set_initial_condition(x0)
-    opt = copy.copy(hkd_options); opt.MS = 0
-    with pytest.raises(CafeError):
+    opt = copy.copy(hkd_options); opt.max_AL_iter = 400
+    with pytest.raises(CafeError):   # more outer iterations than the history / barrier-update counters hold
         s.solve(opt)
     s.set_initial_condition(workload.hkd_batch(hkd_problem, 3))
     with pytest.raises(CafeError):  # batch larger than the handle's capacity
         s.solve(hkd_options)
+
+
+def test_whole_problem_single_shooting_matches_oracle(cm, hkd_problem, hkd_options):
+    """HSDDP_OPTION::MS = false (MultiPhaseDDP.cpp:65-68, :330-333; SinglePhase.cpp:187-221): no shooting states anywhere - every phase is
+    integrated from the state the previous one hands over, defects vanish, there is no linear rollout and the expected cost change comes
+    from the backward sweep (SinglePhase.cpp:383-387). GPU == oracle: counters bit-exact, history / solution 1e-9; feasibility exactly 0."""
+    import copy
+    from cafe_mpc_b200 import workload
+    opt = copy.copy(hkd_options); opt.MS = 0
+    x0 = workload.hkd_batch(hkd_problem, 4)
+    s = solve_gpu(cm, hkd_problem, opt, x0)
+    info = s.get_solver_info(); hist = s.get_history(64); sol = s.get_solution()
+    for b in range(4):
+        oi, oh, ot, osol = oracle_solve(hkd_problem.deck, opt, x0[b])
+        assert [info[b][k] for k in COUNTS] == [oi[k] for k in COUNTS], (b, info[b], oi)
+        np.testing.assert_allclose(hist[b, :oi["n_hist"], 0], oh[:, 0], rtol=1e-9)
+        assert np.all(hist[b, :oi["n_hist"], 1] == 0.0) and info[b]["feas"] == 0.0
+        assert np.abs(sol[b] - osol).max() <= 1e-9 * np.abs(osol).max(), b
 
 
 def test_hkd_receding_horizon_chain_matches_oracle(cm, hkd_options):
