@@ -40,6 +40,16 @@ with open(os.path.join(P, tag + "_ncu_full_mhpc.txt"), "w") as f:
             if h in d: f.write("  %s = %s %s\n" % (h, d[h], u[h]))
         for h in hdr:
             if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("per_issue_active.ratio") and float(d[h] or 0) > 0.3: f.write("  %s = %s\n" % (h, d[h]))
+        # executed fp64 flops, counted by the hardware: thread-level DFMA (x2), DADD, DMUL + tensor-pipe fp64 ops, per elapsed cycle, against the
+        # DFMA peak of the chip (sm__sass_thread_inst_executed_op_dfma_pred_on.sum.peak_sustained x 2 flop per cycle)
+        try:
+            g = lambda h: float(d[h].replace(",", ""))
+            scal = 2 * g("smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed") + g("smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed") + g("smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed")
+            tens = g("sm__ops_path_tensor_src_fp64.sum.per_cycle_elapsed")
+            peak = 2 * g("sm__sass_thread_inst_executed_op_dfma_pred_on.sum.peak_sustained")
+            f.write("  executed_fp64_flop_per_cycle: scalar pipe %.1f + tensor pipe %.1f = %.1f of %.0f (%.3f of the fp64 peak)\n" % (scal, tens, scal + tens, peak, (scal + tens) / peak))
+        except (KeyError, ValueError):
+            pass
         key = name.split("(")[0].split("<")[0].replace("void ", "").replace("cafe_dev::", "")
         def gb(h): return float(d[h]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}[u[h]]
         if key not in traffic: traffic[key] = {"dram_bytes_per_launch": gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum"), "duration_ms_under_ncu": float(d["gpu__time_duration.sum"]) * {"ms": 1, "us": 1e-3, "ns": 1e-6, "s": 1e3}[u["gpu__time_duration.sum"]]}
