@@ -257,6 +257,36 @@ def main():
             solver.get_commands(args.gain_knots, out=cmd_pin.numpy())  # D2H of the command records
         return float(cmd_pin[0, 0])
 
+    # N > 1, second way of collecting the records (reported beside `e2e` as `e2e_host_collect`): no inter-GPU traffic at all - every rank copies its
+    # own shard over its own PCIe link straight into ONE page-locked host buffer that all ranks map (POSIX shared memory registered with
+    # cudaHostRegister in every process), rank 0 reads the whole batch from it once every rank has finished
+    shm, host_all = None, None
+    if world > 1:
+        from multiprocessing import shared_memory
+        name = [None]
+        if rank == 0:
+            shm = shared_memory.SharedMemory(create=True, size=n_out * rec * 8)
+            name[0] = shm.name
+        dist.broadcast_object_list(name, 0)
+        if rank != 0:
+            shm = shared_memory.SharedMemory(name=name[0])
+            try:   # the creator (rank 0) unlinks it; keep this process' resource tracker from doing so a second time at exit
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(shm._name, "shared_memory")
+            except Exception:
+                pass
+        host_all = np.ndarray((n_out, rec), dtype=np.float64, buffer=shm.buf)
+        if int(torch.cuda.cudart().cudaHostRegister(host_all.ctypes.data, host_all.nbytes, 0)) != 0:
+            host_all = None   # not page-lockable here: the figure is omitted
+    my_rows = host_all[rank * per: rank * per + B] if host_all is not None else None
+
+    def step_e2e_host():
+        solver.set_initial_condition(x0_pin.numpy())
+        solver.solve(opt)
+        solver.get_commands(args.gain_knots, out=my_rows)           # D2H of this rank's records into the shared page-locked buffer
+        dist.barrier()                                               # every shard has landed
+        return float(host_all[0, 0])
+
     for _ in range(max(args.warmup, 3)):
         step_resident()
     sampler = ClockSampler(local)
@@ -278,15 +308,27 @@ def main():
         step_e2e()
     barrier()
     wall_e2e = time.perf_counter() - t1
+    wall_e2e_host = 0.0
+    if world > 1:
+        ok_all = torch.tensor([1.0 if host_all is not None else 0.0], device="cuda")
+        dist.all_reduce(ok_all, op=dist.ReduceOp.MIN)
+        if float(ok_all.cpu()) > 0:
+            step_e2e_host()
+            barrier()
+            t2 = time.perf_counter()
+            for _ in range(args.steps):
+                step_e2e_host()
+            barrier()
+            wall_e2e_host = time.perf_counter() - t2
     sampler.stop.set()
     sampler.join(timeout=2)
     it_sum = float(sum(i["iter"] for i in info)); it_max = float(max(i["iter"] for i in info))
-    tt = torch.tensor([wall, wall_e2e, dev_ms, it_max], dtype=torch.float64, device="cuda")
+    tt = torch.tensor([wall, wall_e2e, dev_ms, it_max, wall_e2e_host], dtype=torch.float64, device="cuda")
     ts = torch.tensor([it_sum, float(launches)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(ts, op=dist.ReduceOp.SUM)
-    wall, wall_e2e, dev_ms, it_max = [float(v) for v in tt.cpu()]
+    wall, wall_e2e, dev_ms, it_max, wall_e2e_host = [float(v) for v in tt.cpu()]
     it_sum, launches = [float(v) for v in ts.cpu()]
 
     roof = None
@@ -308,8 +350,19 @@ def main():
             "e2e": {"value": Bg * args.steps / wall_e2e, "unit": UNIT, "h2d_bytes_per_step": int(Bg * n0 * 8), "d2h_bytes_per_step": int(n_out * rec * 8),
                     "what": "cafe_gpu_solve_batch(host x0) + %s (Xbar,Ubar,Y all knots; K,Qu,Quu,Qux first %d knots); byte counts are whole-job totals per step"
                             % ("cafe_gpu_gather_commands (pack + NCCL send/recv to rank 0) + D2H of all %d records on rank 0" % n_out if world > 1 else "cafe_gpu_get_commands", args.gain_knots)},
+            "e2e_host_collect": ({"value": Bg * args.steps / wall_e2e_host, "unit": UNIT,
+                                  "what": "cafe_gpu_solve_batch(host x0) + cafe_gpu_get_commands of every rank's shard over its own PCIe link into one page-locked host "
+                                          "buffer shared by the ranks (POSIX shared memory + cudaHostRegister): no inter-GPU traffic, rank 0 holds all %d records" % n_out}
+                                 if wall_e2e_host > 0 else None),
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu}))
     if world > 1:
+        if host_all is not None:
+            torch.cuda.cudart().cudaHostUnregister(host_all.ctypes.data)
+        del my_rows, host_all
+        dist.barrier()
+        shm.close()
+        if rank == 0:
+            shm.unlink()
         dist.destroy_process_group()
 
 
