@@ -268,7 +268,7 @@ __device__ void sweep_phase2(const SolverDev& S, int pi, int b, int t, bool run,
   const unsigned long long* hm = WB ? nullptr : ph.hkd_mask;   // HKD: structural patterns of A, B, lxx, luu (else nullptr)
   auto stage = [&](int k, int t0, int nt) {
     if constexpr (WB) {
-      // the producer (k_lq_wb_dense) wrote these two tiles problem-major in exactly this layout: contiguous 16-byte copies
+      // the producer (k_wb_sens) wrote these two tiles problem-major in exactly this layout: contiguous 16-byte copies
       static_assert(ldA * (N + M) == CAFE_WB_AB_TILE && ldP * (N + M) == CAFE_WB_CD_TILE && L::oAB % 2 == 0 && L::oCD % 2 == 0, "tile layout");
       const double* ABt = ph.ABpm + ((size_t)b * h + k) * CAFE_WB_AB_TILE;
       for (int e = t0; e < CAFE_WB_AB_TILE / 2; e += nt) cp_async16(sAB + 2 * e, ABt + 2 * e);

@@ -10,20 +10,6 @@
 #include "../../include/cafe_deck.h"
 
 #define CAFE_MAX_ALPHAS 12
-// per-(problem, WB knot) hand-off from k_lq to k_lq_wb_dense (raw pieces; the dense kernel combines them):
-//   chol(M) | Y = L^-1 Jc^T | chol(S) | dtau_dq | dtau_dv | d(J^T F)/dq | da/dq | da/dv | dv/dq | J     (foot rows 3f+r, ld 12)
-// the generated routines write their (static) non-zero patterns straight into this array, which is zeroed once at create
-#define CAFE_KKT_L 0
-#define CAFE_KKT_Y 324
-#define CAFE_KKT_LS 540
-#define CAFE_KKT_RQ 684
-#define CAFE_KKT_RV 1008
-#define CAFE_KKT_JTF 1332
-#define CAFE_KKT_AQ 1656
-#define CAFE_KKT_AV 1872
-#define CAFE_KKT_DVQ 2088
-#define CAFE_KKT_J 2304
-#define CAFE_KKT_PACK 2520
 // problem-major tiles of the whole-body sweep (doubles): [A B] rows 18..35 as 20 x 48 (ld 20), [C D] 12 x 48, K 12 x 36
 #define CAFE_WB_AB_TILE 960
 #define CAFE_WB_CD_TILE 576
@@ -63,7 +49,6 @@ struct PhaseDev {
   double *A, *Bm, *C, *D;                  // [h][n*n | n*m | p*n | p*m][ldb], column-major per knot
   double *lx, *lu, *ly, *lxx, *luu, *lyy;  // [h][...][ldb]
   double *Phix, *Phixx, *Px;               // [n | n*n | n_next*n][ldb]
-  double *kkt;                             // WB only: [h][CAFE_KKT_PACK][ldb]  (legacy hand-off, unused by the leg-parallel path)
   // WB only: rigid-body terms of every line-search trial (k_wb_terms -> k_wb_fwd; the accepted trial's are reused by the next
   // linearisation), joint accelerations of every trial, derivative pieces of the current iterate (k_wb_derivs -> k_wb_lq)
   double *tm;                              // [NA][h][CAFE_TM_W][ldb]

@@ -1,5 +1,5 @@
 // knot_kernels.cuh — the per-(problem, knot) kernels and the per-problem control kernels of the batched HS-DDP path (sm_100a, fp64).
-// (The Riccati sweep lives in bwd2.cuh, the cooperative whole-body KKT sensitivities in dense_kernels.cuh.)
+// (The Riccati sweep lives in bwd2.cuh, the whole-body running knots in wb_leg_kernels.cu (straight-line rigid-body routines) and wb_coop.cuh (cooperative KKT kernels).)
 //
 //   k_roll    K-ROLL : hybrid rollout of every (problem, knot, step size) + constraint values + costs
 //                      <= SinglePhase::hybrid_rollout / compute_cost      HSDDPSolver/source/SinglePhase.cpp:182-262

@@ -280,7 +280,6 @@ void carve(CafeHandle* H, Carver& cv, size_t& zero_bytes) {
     ph.lx = cv.take<double>(h * n * ldb); ph.lu = cv.take<double>(h * m * ldb); ph.ly = cv.take<double>(h * p * ldb + 1);
     ph.lxx = cv.take<double>(h * n * n * ldb); ph.luu = cv.take<double>(h * m * m * ldb); ph.lyy = cv.take<double>(h * p * p * ldb + 1);
     ph.Phix = cv.take<double>(n * ldb); ph.Phixx = cv.take<double>(n * n * ldb); ph.Px = cv.take<double>(nn * n * ldb);
-    ph.kkt = nullptr;
     const bool wb = ph.model == CAFE_MODEL_WB;
     ph.tm = cv.take<double>(wb ? (size_t)NA * h * CAFE_TM_W * ldb : 1); ph.qdd_t = cv.take<double>(wb ? (size_t)NA * h * 18 * ldb : 1);
     ph.dp = cv.take<double>(wb ? h * (size_t)CAFE_DP_W * ldb : 1);
