@@ -507,6 +507,7 @@ extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, 
   } else {
     H->bwd_variant = 1; H->bwd_pb = 1;
     H->bwd_smem = (size_t)cafe_dev::Bwd2Layout<36, 12, 12, true>::total * sizeof(double);
+    if (const char* e = std::getenv("CAFE_BWD_SMEM_PAD")) H->bwd_smem += (size_t)std::atol(e);   // dev switch: fewer sweep CTAs per SM (room for a concurrent kernel)
     CUDA_OK_H(cudaFuncSetAttribute(cafe_dev::k_bwd2<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H->bwd_smem));
     CUDA_OK_H(cudaFuncSetAttribute(cafe_dev::k_bwd2<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)H->bwd_smem));
     if (const char* e = std::getenv("CAFE_BWD_NT")) H->bwd_nt = std::atoi(e) == 256 ? 256 : 128;
