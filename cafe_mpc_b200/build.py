@@ -38,7 +38,7 @@ NVCC_FLAGS = [
 _RC = os.environ.get("CAFE_KNOT_MAXRREG", "128")   # dev switch for occupancy experiments
 _MINB = str(max(1, 65536 // (128 * int(_RC))))
 _LRC = os.environ.get("CAFE_LEG_MAXRREG", "255")    # register cap of the leg-parallel straight-line kernels
-EXTRA = {"wb_gen_wrappers.cu": ["-maxrregcount=" + _RC], "wb_leg_kernels.cu": ["-maxrregcount=" + _LRC, "-DCAFE_LEG_MINB=" + str(max(1, 65536 // (128 * int(_LRC))))], "knot_kernels.cu": ["-maxrregcount=" + _RC, "-DCAFE_KNOT_MINB=" + _MINB] + os.environ.get("CAFE_KNOT_DEFS", "").split()}
+EXTRA = {"solver.cu": os.environ.get("CAFE_SOLVER_DEFS", "").split(), "wb_gen_wrappers.cu": ["-maxrregcount=" + _RC], "wb_leg_kernels.cu": ["-maxrregcount=" + _LRC, "-DCAFE_LEG_MINB=" + str(max(1, 65536 // (128 * int(_LRC))))], "knot_kernels.cu": ["-maxrregcount=" + _RC, "-DCAFE_KNOT_MINB=" + _MINB] + os.environ.get("CAFE_KNOT_DEFS", "").split()}
 
 
 def _mtime(p):

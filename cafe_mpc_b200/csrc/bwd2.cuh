@@ -42,6 +42,9 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 #ifndef CAFE_PACE
 #define CAFE_PACE 4
 #endif
+#ifndef CAFE_BWD_MINB
+#define CAFE_BWD_MINB 4   // resident sweep CTAs per SM the kernel is compiled for (register cap 65536 / (NT * CAFE_BWD_MINB)); shared memory allows 4
+#endif
 __device__ __forceinline__ void cluster_pace() { asm volatile("barrier.cluster.arrive.relaxed.aligned;\nbarrier.cluster.wait.aligned;\n" ::: "memory"); }
 // bit e of a structural-pattern mask (read-only, the same for every problem: served by L1)
 __device__ __forceinline__ bool mask_bit(const unsigned long long* __restrict__ m, int e) { return (__ldg(m + (e >> 6)) >> (e & 63)) & 1ULL; }
@@ -686,7 +689,7 @@ __device__ void lin_phase2(const SolverDev& S, int pi, int b, int t, bool run, d
 
 // DECK: 0 = HKD phases only (24,24,0); 1 = MHPC (WB 36,12,12 + SRB 12,12,0)
 template <int DECK, int NT>
-__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NT, 4) k_bwd2(const __grid_constant__ SolverDev S) {
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NT, CAFE_BWD_MINB) k_bwd2(const __grid_constant__ SolverDev S) {
   typedef Bwd2Layout<(DECK == 0 ? 24 : 36), (DECK == 0 ? 24 : 12), (DECK == 0 ? 0 : 12), (DECK == 1)> L;
   constexpr int NX = (DECK == 0 ? 24 : 36);
   extern __shared__ __align__(16) double sm[];
