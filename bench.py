@@ -265,19 +265,28 @@ def main():
         from multiprocessing import shared_memory
         name = [None]
         if rank == 0:
-            shm = shared_memory.SharedMemory(create=True, size=n_out * rec * 8)
-            name[0] = shm.name
-        dist.broadcast_object_list(name, 0)
-        if rank != 0:
-            shm = shared_memory.SharedMemory(name=name[0])
-            try:   # the creator (rank 0) unlinks it; keep this process' resource tracker from doing so a second time at exit
-                from multiprocessing import resource_tracker
-                resource_tracker.unregister(shm._name, "shared_memory")
+            try:   # only where /dev/shm has room for the records (a short tmpfs would end the process with SIGBUS on first touch)
+                st = os.statvfs("/dev/shm")
+                if st.f_bavail * st.f_frsize > 2 * n_out * rec * 8:
+                    shm = shared_memory.SharedMemory(create=True, size=n_out * rec * 8)
+                    name[0] = shm.name
             except Exception:
-                pass
-        host_all = np.ndarray((n_out, rec), dtype=np.float64, buffer=shm.buf)
-        if int(torch.cuda.cudart().cudaHostRegister(host_all.ctypes.data, host_all.nbytes, 0)) != 0:
-            host_all = None   # not page-lockable here: the figure is omitted
+                shm, name[0] = None, None
+        dist.broadcast_object_list(name, 0)
+        if name[0] is not None:
+            try:
+                if rank != 0:
+                    shm = shared_memory.SharedMemory(name=name[0])
+                    try:   # the creator (rank 0) unlinks it; keep this process' resource tracker from doing so a second time at exit
+                        from multiprocessing import resource_tracker
+                        resource_tracker.unregister(shm._name, "shared_memory")
+                    except Exception:
+                        pass
+                host_all = np.ndarray((n_out, rec), dtype=np.float64, buffer=shm.buf)
+                if int(torch.cuda.cudart().cudaHostRegister(host_all.ctypes.data, host_all.nbytes, 0)) != 0:
+                    host_all = None   # not page-lockable here: the figure is omitted
+            except Exception:
+                host_all = None
     my_rows = host_all[rank * per: rank * per + B] if host_all is not None else None
 
     def step_e2e_host():
@@ -360,9 +369,13 @@ def main():
             torch.cuda.cudart().cudaHostUnregister(host_all.ctypes.data)
         del my_rows, host_all
         dist.barrier()
-        shm.close()
-        if rank == 0:
-            shm.unlink()
+        if shm is not None:
+            try:
+                shm.close()
+                if rank == 0:
+                    shm.unlink()
+            except Exception:
+                pass
         dist.destroy_process_group()
 
 
