@@ -61,6 +61,7 @@ struct CafeHandle {
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
   // linearisation of one part on two streams (k_lq | k_wb_derivs -> k_wb_sens, k_wb_cost): fork / derivatives-ready / join events per part
   cudaEvent_t ev_lqf[2] = {nullptr, nullptr}, ev_lqd[2] = {nullptr, nullptr}, ev_lqj[2] = {nullptr, nullptr};
+  cudaEvent_t ev_lqc = nullptr;   // unsplit ticks: k_wb_cost on a third stream (it waits for the derivatives only, not for k_lq)
   bool lq_overlap = true;   // CAFE_LQ_OVERLAP=0 keeps the linearisation on one stream
   int split_n = 2;       // number of parts (CAFE_SPLIT_N, 2..4)
   int split_min = 1024;  // smallest active list that is cut (CAFE_SPLIT_MIN; 0 = never)
@@ -491,6 +492,7 @@ extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, 
   for (int i = 0; i < 3; ++i) { CUDA_OK_H(cudaStreamCreate(&H->stream2[i])); CUDA_OK_H(cudaEventCreateWithFlags(&H->ev_join[i], cudaEventDisableTiming)); }
   CUDA_OK_H(cudaEventCreateWithFlags(&H->ev_fork, cudaEventDisableTiming));
   for (int i = 0; i < 2; ++i) { CUDA_OK_H(cudaEventCreateWithFlags(&H->ev_lqf[i], cudaEventDisableTiming)); CUDA_OK_H(cudaEventCreateWithFlags(&H->ev_lqd[i], cudaEventDisableTiming)); CUDA_OK_H(cudaEventCreateWithFlags(&H->ev_lqj[i], cudaEventDisableTiming)); }
+  CUDA_OK_H(cudaEventCreateWithFlags(&H->ev_lqc, cudaEventDisableTiming));
   if (const char* e = getenv("CAFE_LQ_OVERLAP")) H->lq_overlap = atoi(e) != 0;
   if (const char* e = getenv("CAFE_SPLIT_MIN")) H->split_min = atoi(e);
   if (const char* e = getenv("CAFE_SPLIT_N")) { H->split_n = atoi(e); if (H->split_n < 2) H->split_n = 2; if (H->split_n > 4) H->split_n = 4; }
@@ -542,6 +544,7 @@ extern "C" int cafe_gpu_destroy(CafeHandle* H) {
   for (int i = 0; i < 3; ++i) { if (H->stream2[i]) cudaStreamDestroy(H->stream2[i]); if (H->ev_join[i]) cudaEventDestroy(H->ev_join[i]); }
   if (H->ev_fork) cudaEventDestroy(H->ev_fork);
   for (int i = 0; i < 2; ++i) { if (H->ev_lqf[i]) cudaEventDestroy(H->ev_lqf[i]); if (H->ev_lqd[i]) cudaEventDestroy(H->ev_lqd[i]); if (H->ev_lqj[i]) cudaEventDestroy(H->ev_lqj[i]); }
+  if (H->ev_lqc) cudaEventDestroy(H->ev_lqc);
   if (H->ev0) cudaEventDestroy(H->ev0);
   if (H->ev1) cudaEventDestroy(H->ev1);
   if (H->evs) cudaEventDestroy(H->evs);
@@ -625,7 +628,8 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
   // sb != sq: the thread-per-knot kernel (SRB / HKD / terminal knots: one long dependent chain per thread, latency bound) and the cost
   // partials of the whole-body knots run on the companion stream sb beside derivatives -> sensitivities on sq (slot e of the event arrays);
   // k_wb_cost and k_wb_sens both read the derivative pack, nothing else is shared between the two chains
-  auto lq_group = [&](cudaStream_t sq, cudaStream_t sb, int e, const int* list, int n_list, bool tm) {
+  // sc != sb: a third stream for k_wb_cost, so that it starts with the derivatives instead of queueing behind the latency-bound k_lq on sb
+  auto lq_group = [&](cudaStream_t sq, cudaStream_t sb, int e, const int* list, int n_list, bool tm, cudaStream_t sc = nullptr) {
     auto run = [&](int slot, auto&& f) { if (tm) timed(H, slot, f); else { f(); H->launches[slot]++; } };
     H->units[CAFE_K_LQ] += (double)n_list * S.n_knots; H->units[CAFE_K_BWD] += (double)n_list;
     H->units[CAFE_K_WB_DERIVS] += (double)n_list * n_wbk; H->units[CAFE_K_WB_SENS] += (double)n_list * n_wbk; H->units[CAFE_K_WB_COST] += (double)n_list * n_wbk;
@@ -634,9 +638,12 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
     run(CAFE_K_LQ, [&] { cafe_dev::launch_lq(H->dS, S.n_knots, two ? sb : sq, list, n_list); });
     if (n_wbk > 0) {
       run(CAFE_K_WB_DERIVS, [&] { cafe_dev::launch_wb_derivs(H->dS, n_wbk, sq, list, n_list); });
-      if (two) { cudaEventRecord(H->ev_lqd[e], sq); cudaStreamWaitEvent(sb, H->ev_lqd[e], 0); }
+      const bool three = two && sc != nullptr && sc != sb && sc != sq;
+      cudaStream_t s_cost = three ? sc : (two ? sb : sq);
+      if (two) { cudaEventRecord(H->ev_lqd[e], sq); cudaStreamWaitEvent(s_cost, H->ev_lqd[e], 0); }
       run(CAFE_K_WB_SENS, [&] { cafe_dev::launch_wb_sens(H->dS, n_wbk, sq, list, n_list); });
-      run(CAFE_K_WB_COST, [&] { cafe_dev::launch_wb_cost(H->dS, n_wbk, two ? sb : sq, list, n_list); });
+      run(CAFE_K_WB_COST, [&] { cafe_dev::launch_wb_cost(H->dS, n_wbk, s_cost, list, n_list); });
+      if (three) { cudaEventRecord(H->ev_lqc, sc); cudaStreamWaitEvent(sq, H->ev_lqc, 0); }
       if (two) { cudaEventRecord(H->ev_lqj[e], sb); cudaStreamWaitEvent(sq, H->ev_lqj[e], 0); }
     }
   };
@@ -686,7 +693,7 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
         if (q > 0) { CUDA_OK(cudaEventRecord(H->ev_join[q - 1], sq)); CUDA_OK(cudaStreamWaitEvent(st, H->ev_join[q - 1], 0)); }
       }
     } else {
-      lq_group(st, (H->lq_overlap && !H->profiling) ? H->stream2[0] : st, 0, S.c.act_list, n_act, true);
+      lq_group(st, (H->lq_overlap && !H->profiling) ? H->stream2[0] : st, 0, S.c.act_list, n_act, true, (H->lq_overlap && !H->profiling) ? H->stream2[1] : nullptr);
       timed(H, CAFE_K_BWD, [&] { launch_bwd(H); });
     }
     // staged line search: step sizes are evaluated in growing groups; most problems accept one of the first
