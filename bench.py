@@ -131,24 +131,37 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
+_CPU_PROBLEM = {}
+
+
 def _cpu_worker(task):
     from oracle_bindings import oracle_solve
     x0s, workload = task
-    prob, opt, _, _ = make_problem(workload)
+    if workload not in _CPU_PROBLEM:   # one deck per worker process
+        _CPU_PROBLEM[workload] = make_problem(workload)
+    prob, opt, _, _ = _CPU_PROBLEM[workload]
     t = time.perf_counter()
     for x in x0s:
         oracle_solve(prob.deck, opt, x, cap=320, guess=prob.initial_guess(x)[0] if workload == "barrel_to" else None)
     return time.perf_counter() - t
 
 
-def cpu_sample(x0, cores, per_core, workload):
-    """One single-threaded oracle instance per host core over disjoint slices."""
+def cpu_sample(x0, cores, per_core, workload, budget_s=0.0):
+    """One single-threaded oracle instance per host core over disjoint slices (SURVEY.md §8d). per_core > 0: that many problems per core;
+    per_core <= 0: as many of x0's problems as `budget_s` seconds allow at the rate of a one-problem-per-core probe - the whole batch if it fits."""
     import multiprocessing as mp
-    n = min(len(x0), cores * per_core)
-    chunks = [x0[i:n:cores] for i in range(cores)]
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
-        pool.map(_cpu_worker, [(c[:1], workload) for c in chunks])  # warm-up: imports, page-in
+        pool.map(_cpu_worker, [(x0[i:i + 1], workload) for i in range(min(cores, len(x0)))])  # warm-up: imports, page-in
+        t = time.perf_counter()
+        pool.map(_cpu_worker, [(x0[i:len(x0):cores][:2], workload) for i in range(cores)])  # probe: two problems per core
+        probe = (time.perf_counter() - t) / 2
+        if per_core > 0:
+            n = min(len(x0), cores * per_core)
+        else:
+            n = int(min(len(x0), max(cores, budget_s / max(probe, 1e-3) * cores)))
+            n -= n % cores if n >= cores else 0
+        chunks = [x0[i:n:cores] for i in range(cores)]
         t = time.perf_counter()
         pool.map(_cpu_worker, [(c, workload) for c in chunks])
         wall = time.perf_counter() - t
@@ -165,19 +178,26 @@ def run_reference(args):
     prob, opt, gen_x0, n0 = make_problem(args.workload)
     per_core = args.cpu_per_core
     cfg = make_config(args, world)
-    x0 = gen_x0(min(cfg["global_batch"], cores * per_core))
-    vals = []
+    Bg = cfg["global_batch"]
+    x0 = gen_x0(Bg if Bg <= 8192 else 8192)
+    vals, n, n_first = [], 0, 0
     for i in range(args.warmup + args.steps):
-        v, n = cpu_sample(x0, cores, per_core, args.workload)
+        # the first timed step covers the WHOLE batch when it fits about 20 s of wall time on these cores (MHPC trot: 4096 problems ~ 14 s on 16 cores),
+        # warm-up and later steps a prefix of about 2 s / 5 s (a rate does not depend on the sample size; the run stays within a few minutes)
+        budget = 2.0 if i < args.warmup else (20.0 if i == args.warmup else 5.0)
+        v, n = cpu_sample(x0, cores, per_core, args.workload, budget_s=budget)
         if i >= args.warmup:
             vals.append(v)
+        if i == args.warmup:
+            n_first = n
     v = sum(vals) / len(vals)
-    sample = ("each step = the first %d problems of the workload's table (%d per core), one single-threaded instance of the CPU restatement of the reference "
-              "solver (oracle/, reference CasADi C from oracle/_ref) per host core; the reference itself needs Eigen / Boost / Pinocchio / LCM and cannot be "
-              "built in this image" % (len(x0), per_core))
+    n = n_first
+    sample = ("first timed step = %s %d problems of the workload's table (later steps: a prefix of about 5 s), one single-threaded instance of the CPU restatement "
+              "of the reference solver (oracle/, reference CasADi C from oracle/_ref) per host core over disjoint slices; the reference itself needs Eigen / Boost / "
+              "Pinocchio / LCM and cannot be built in this image" % ("all" if n >= Bg else "the first", n))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * len(x0) / v, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": 1e3 * n / v, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
@@ -193,7 +213,7 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--workload", default="mhpc", choices=["mhpc", "hkd", "barrel", "loco", "barrel_to"])
     ap.add_argument("--gain-knots", type=int, default=8)
-    ap.add_argument("--cpu-per-core", type=int, default=8)
+    ap.add_argument("--cpu-per-core", type=int, default=0, help="CPU baseline: problems per core (0: as many as ~20 s / ~10 s allow, the whole batch if it fits)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -346,9 +366,9 @@ def main():
         roof = roofline(args, solver, prob, step_resident, local, B, Bg)
         if not args.no_cpu_baseline:
             cores = len(os.sched_getaffinity(0))
-            v, n = cpu_sample(x0_all[: cores * args.cpu_per_core], cores, args.cpu_per_core, args.workload)
+            v, n = cpu_sample(x0_all, cores, args.cpu_per_core, args.workload, budget_s=10.0)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": "%d problems (first of the same SplitMix64 table), one single-threaded oracle instance per core" % n}
+                   "sample": "%s %d problems of the same SplitMix64 table (about 10 s of CPU work), one single-threaded oracle instance per core" % ("all" if n >= Bg else "the first", n)}
         cfg = dict(cfg)
         cfg.update({"per_gpu_batch": per, "parallelism": "batch sharded over %d GPU(s), no collective in the solve" % world,
                     "mean_ddp_iterations": it_sum / Bg, "max_ddp_iterations": it_max})
