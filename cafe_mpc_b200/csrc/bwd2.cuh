@@ -199,7 +199,8 @@ struct Bwd2Layout {
   static constexpr int ldH = ld_mma(NX), KA = WBS ? 18 : NX, ldA = ld_mma(KA), ldM = ld_mma(MX), ldP = ld_mma(PX > 0 ? PX : 1);
   // vectors
   static constexpr int vG = 0, vGn = NX, vQx = 2 * NX, vD = 3 * NX, vDx = 4 * NX, vDxn = 5 * NX, vQu = 6 * NX, vDu = 6 * NX + MX,
-                       vDuL = 6 * NX + 2 * MX, vLy = 6 * NX + 3 * MX, vRed = vLy + PX + 1, nVec = vRed + 2 * 256 + 1;   // vRed: pivots / flags, then two NT-wide reduction rows (NT <= 256)
+                       vDuL = 6 * NX + 2 * MX, vLy = 6 * NX + 3 * MX, vRed = vLy + PX + 1, nVec = (vRed + 32 + 1) & ~1;   // vRed: flag + up to 24 pivots (the two NT-wide
+                       // rows of the final dV reduction live in the linear rollout's stage buffers, dead by then: oRed)
   static constexpr int oH = nVec;                       // H / Qxx / H_new      NX x NX (ldH)
   static constexpr int oAB = oH + ldH * (NX + 2);       // [A B] rows KA (ldA) x (NX+MX); two zero pad columns behind H (k padding of P = H(:,18:36))
   static constexpr int szAB = ldA * (NX + MX);
@@ -218,7 +219,11 @@ struct Bwd2Layout {
                        lLu = lLx + NX, lD = lLu + MX, lDU = lD + NX, szLin = (lDU + MX + 2) & ~1;   // even: the second stage stays 16-byte aligned
   static constexpr int oLin = nVec;
   static constexpr int endLin = oLin + 2 * szLin;
-  static constexpr int total = (endSweep > endLin ? endSweep : endLin) + 64;   // slack: fragment loads of partial edge tiles run past the last tile
+  static constexpr int oRed = oLin;   // 2 x 256 doubles
+  static_assert(2 * szLin >= 2 * 256, "reduction rows");
+  // slack behind the sweep's tiles only: fragment loads of partial edge tiles run past the last tile. (HKD: 57.3 KB, four problems per SM -
+  // with the reduction rows in nVec and the slack behind the larger linear-rollout plan it was 61.7 KB, three per SM.)
+  static constexpr int total = (endSweep + 64 > endLin ? endSweep + 64 : endLin);
 };
 
 // One phase of the sweep. N, M, PY: phase dimensions; NNEXT: state dimension of the next phase (for the jump); WB: use the
@@ -769,7 +774,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NT, CAFE_BWD_MINB) k
   double dV1 = 0, dV2 = 0;
   {
     double* sDx = sm + L::vDx;
-    double* sRed = sm + L::vRed;
+    double* sRed = sm + L::oRed;
     for (int i = t; i < NX; i += NT) sDx[i] = 0.0;
     __syncthreads();
     double part1 = 0, part2 = 0;
