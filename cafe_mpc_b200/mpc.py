@@ -129,3 +129,34 @@ def state_at(problem, phases, knots_ahead):
 def shifted_guess_batch(old_problem, old_k0, new_problem, new_k0, old_solutions):
     """Packed guesses [B, solution_size(new deck)] from packed previous solutions [B, solution_size(old deck)]."""
     return pack_solution(new_problem, shift_guess(old_problem, old_k0, new_problem, new_k0, unpack_batch(old_problem, old_solutions)))
+
+
+def initial_al(problem, B=None):
+    """[n_phases, 4, 2] (or [B, n_phases, 4, 2]) = (sigma, lambda) every touchdown-constraint element starts from (the deck's TD_AL values)."""
+    ph = problem.phases()
+    al = np.zeros((len(ph), 4, 2))
+    for i, p in enumerate(ph):
+        al[i, :p.n_td, 0] = p.al_td.sigma
+        al[i, :p.n_td, 1] = p.al_td.lambda_
+    return al if B is None else np.broadcast_to(al, (B,) + al.shape).copy()
+
+
+def shift_al(old_problem, old_k0, new_problem, new_k0, old_al):
+    """The augmented-Lagrangian parameters the re-solve after an MPC update starts from: old_al [..., n_old_phases, 4, 2] as the previous
+    solve left them -> [..., n_new_phases, 4, 2]. The reference keeps every phase's TouchDownConstraint object (and its sigma / lambda) for
+    as long as the phase lives - reset_params(), called by every update, is an empty function (ConstraintsBase.h:367-374, HKDProblem.cpp:208,
+    MHPCProblem.cpp:363) - so a phase that continues an old phase with the same touchdown feet inherits its values; a constraint that did
+    not exist before (a phase the old plan did not have, or a tail phase that only now got its touchdown constraint) starts from the deck's."""
+    old_al = np.asarray(old_al)
+    lead = old_al.shape[:-3]
+    new = np.broadcast_to(initial_al(new_problem), lead + (len(new_problem.phases()), 4, 2)).copy()
+    old_r, new_r = _wb_ranges(old_problem, old_k0), _wb_ranges(new_problem, new_k0)
+    oph, nph = old_problem.phases(), new_problem.phases()
+    for i, s, e, contact in new_r:
+        src = [r for r in old_r if r[3] == contact and r[1] <= e and r[2] >= s]
+        if not src:
+            continue
+        j = src[0][0]
+        if oph[j].n_td > 0 and oph[j].n_td == nph[i].n_td and list(oph[j].td_foot)[:oph[j].n_td] == list(nph[i].td_foot)[:nph[i].n_td]:
+            new[..., i, :, :] = old_al[..., j, :, :]
+    return new

@@ -602,15 +602,28 @@ static void apply_guess(Solver& S, const double* guess) {
   }
 }
 
-extern "C" int cafe_oracle_solve_warm(const CafeDeck* deck, const CafeOptions* opt, const double* x0, const double* guess, CafeInfo* info,
-                                      double* hist, int hist_cap, double* trace, int trace_cap, double* sol) {
+/* al_in / al_out: [n_phases][4][2] = (sigma, lambda) of every touchdown-constraint element. The reference's MPC loop never resets them:
+ * TerminalConstraintBase::reset_params is an empty function (ConstraintsBase.h:367-374), so what update_params left behind in one solve is
+ * what the next solve after HKDProblem::update / MHPCProblem::update starts from. al_in = NULL: the deck's initial values. */
+extern "C" int cafe_oracle_solve_al(const CafeDeck* deck, const CafeOptions* opt, const double* x0, const double* guess, const double* al_in,
+                                    double* al_out, CafeInfo* info, double* hist, int hist_cap, double* trace, int trace_cap, double* sol) {
   try {
     g_last.reset(new Solver());
     Solver& S = *g_last;
     S.setup(deck);
     if (guess) apply_guess(S, guess);
+    if (al_in)
+      for (size_t i = 0; i < S.phases.size(); ++i)
+        for (auto& tc : S.phases[i]->tcon)
+          for (int e = 0; e < tc.size && e < 4; ++e) { tc.params[e].sigma = al_in[(i * 4 + e) * 2]; tc.params[e].lambda = al_in[(i * 4 + e) * 2 + 1]; }
     S.x0.assign(x0, x0 + S.phases[0]->n);
     S.solve(*opt);
+    if (al_out)
+      for (size_t i = 0; i < S.phases.size(); ++i) {
+        for (int e = 0; e < 8; ++e) al_out[i * 8 + e] = 0;
+        for (auto& tc : S.phases[i]->tcon)
+          for (int e = 0; e < tc.size && e < 4; ++e) { al_out[(i * 4 + e) * 2] = tc.params[e].sigma; al_out[(i * 4 + e) * 2 + 1] = tc.params[e].lambda; }
+      }
     if (info) {
       info->status = S.reg_failed ? CAFE_STATUS_REG_FAIL : CAFE_STATUS_OK;
       info->iter = S.iter_; info->ls_iter_total = S.ls_iter_total_; info->reg_iter_total = S.reg_iter_total_;
@@ -633,6 +646,11 @@ extern "C" int cafe_oracle_solve_warm(const CafeDeck* deck, const CafeOptions* o
     std::fprintf(stderr, "cafe_oracle_solve: %s\n", e.what());
     return -1;
   }
+}
+
+extern "C" int cafe_oracle_solve_warm(const CafeDeck* deck, const CafeOptions* opt, const double* x0, const double* guess, CafeInfo* info,
+                                      double* hist, int hist_cap, double* trace, int trace_cap, double* sol) {
+  return cafe_oracle_solve_al(deck, opt, x0, guess, nullptr, nullptr, info, hist, hist_cap, trace, trace_cap, sol);
 }
 
 extern "C" int cafe_oracle_solve(const CafeDeck* deck, const CafeOptions* opt, const double* x0, CafeInfo* info,

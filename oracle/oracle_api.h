@@ -34,6 +34,11 @@ int cafe_oracle_solve(const CafeDeck* deck, const CafeOptions* opt, const double
  * whatever the trajectories hold (MultiPhaseDDP.cpp:238). */
 int cafe_oracle_solve_warm(const CafeDeck* deck, const CafeOptions* opt, const double* x0, const double* guess,
                            CafeInfo* info, double* hist, int hist_cap, double* trace, int trace_cap, double* sol);
+/* Same, with the augmented-Lagrangian parameters carried between the solves of an MPC loop: al_in / al_out [n_phases][4][2] = (sigma,
+ * lambda) per touchdown-constraint element (NULL = the deck's initial values / not wanted). The reference never resets them between MPC
+ * steps: TerminalConstraintBase::reset_params is empty (ConstraintsBase.h:367-374), called from HKDProblem.cpp:208 / MHPCProblem.cpp:363. */
+int cafe_oracle_solve_al(const CafeDeck* deck, const CafeOptions* opt, const double* x0, const double* guess, const double* al_in,
+                         double* al_out, CafeInfo* info, double* hist, int hist_cap, double* trace, int trace_cap, double* sol);
 
 /* Internal per-knot array of the most recent cafe_oracle_solve (names: X Xbar U Ubar Y Defect dX dU G Qu A B C D K
  * Quu Qux H lx lu ly lxx luu lyy l Phix Phixx Px). Returns the number of doubles written or -1. */

@@ -34,8 +34,10 @@ def oracle():
     return _lib
 
 
-def oracle_solve(deck, opt, x0, cap=256, guess=None):
-    """Returns (info dict, hist [n_hist,4], trace [iter,12], packed solution). guess: packed solution whose Xbar/Ubar/K start the solve."""
+def oracle_solve(deck, opt, x0, cap=256, guess=None, al=None):
+    """Returns (info dict, hist [n_hist,4], trace [iter,12], packed solution). guess: packed solution whose Xbar/Ubar/K start the solve.
+    al: [n_phases, 4, 2] (sigma, lambda) the touchdown constraints start from (the MPC loop's carry-over); then a fifth value is returned:
+    the parameters the solve left behind."""
     lib = oracle()
     x0 = np.ascontiguousarray(x0, dtype=np.float64)
     info = Info()
@@ -46,12 +48,21 @@ def oracle_solve(deck, opt, x0, cap=256, guess=None):
     if guess is not None:
         g = np.ascontiguousarray(guess, dtype=np.float64)
         assert g.size == sol.size
-    rc = lib.cafe_oracle_solve_warm(deck, C.byref(opt), x0.ctypes.data_as(C.c_void_p), g.ctypes.data_as(C.c_void_p) if g is not None else None,
-                                    C.byref(info), hist.ctypes.data_as(C.c_void_p), cap, trace.ctypes.data_as(C.c_void_p), cap,
-                                    sol.ctypes.data_as(C.c_void_p))
+    n_ph = deck.contents.n_phases
+    a_in = None
+    if al is not None:
+        a_in = np.ascontiguousarray(al, dtype=np.float64)
+        assert a_in.size == n_ph * 8
+    a_out = np.zeros((n_ph, 4, 2))
+    rc = lib.cafe_oracle_solve_al(deck, C.byref(opt), x0.ctypes.data_as(C.c_void_p), g.ctypes.data_as(C.c_void_p) if g is not None else None,
+                                  a_in.ctypes.data_as(C.c_void_p) if a_in is not None else None, a_out.ctypes.data_as(C.c_void_p),
+                                  C.byref(info), hist.ctypes.data_as(C.c_void_p), cap, trace.ctypes.data_as(C.c_void_p), cap,
+                                  sol.ctypes.data_as(C.c_void_p))
     if rc != 0:
         raise RuntimeError("oracle solve failed")
     d = info.as_dict()
+    if al is not None:
+        return d, hist[:d["n_hist"]], trace[:d["iter"]], sol, a_out
     return d, hist[:d["n_hist"]], trace[:d["iter"]], sol
 
 

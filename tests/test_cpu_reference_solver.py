@@ -1,0 +1,125 @@
+"""The oracle against the REFERENCE's own solver (CPU suite).
+
+tests/golden/ref_hkd_trot.npz holds what the reference's MultiPhaseDDP<T>::solve + HKDProblem<T>::initialization / update decided and
+produced on four HKD trot problems through the initial solve and six consecutive MPC updates: it was written by
+tools/make_ref_golden.py from oracle/_ref/ref_hkd, i.e. from the reference's HSDDPSolver / HKD-TrajOpt / QuadReference sources compiled
+unchanged (oracle/refbuild). These tests pin the oracle's restatement of the solver layer, the repo's deck builders, compute_hkd_state and
+the MPC shift (cafe_mpc_b200/mpc.py) to it: decisions (iteration, line-search and regularisation counts per DDP iteration, accepted step
+sizes, AL updates, phase layouts) bit-exact, everything else at 1e-9 relative (BASELINE.json north_star). The reference binary was built
+against a plain-loop stand-in for Eigen (not in this image), so last-bit agreement is not expected - 1e-9 is met with orders to spare.
+The GPU counterpart is tests/test_gpu_reference_solver.py."""
+import copy
+import os
+
+import numpy as np
+import pytest
+
+from oracle_bindings import oracle_solve
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSV = os.path.join(REPO, "data/Reference/Data/trot/heuristic/quad_reference.csv")
+RTOL = 1e-9
+
+
+def relerr(g, o):
+    o = np.asarray(o); g = np.asarray(g)
+    if o.size == 0:
+        return 0.0
+    return float(np.max(np.abs(g - o)) / max(np.max(np.abs(o)), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return np.load(os.path.join(REPO, "tests/golden/ref_hkd_trot.npz"))
+
+
+def check_deck_layout(prob, ref, pre):
+    ph = prob.phases()
+    assert [p.horizon for p in ph] == list(ref[pre + "horizons"])
+    assert [list(p.contact) for p in ph] == [list(c) for c in ref[pre + "contacts"]]
+
+
+def check_solve(cm, prob, ref, pre, info, trace, sol, full=False, rtol=RTOL):
+    """One solve (oracle or GPU: info dict, trace [iter,12], packed solution) against the reference's record `pre`."""
+    assert [info["iter"], info["ls_iter_total"], info["reg_iter_total"]] == list(ref[pre + "counters"]), pre
+    rt = ref[pre + "trace"]
+    assert trace.shape == rt.shape
+    assert np.array_equal(trace[:, 6:10], rt[:, 6:10]), pre            # sweeps, line-search trials, success, accepted step size: exact
+    assert np.array_equal(trace[:, 5] == 0, rt[:, 5] == 0)
+    np.testing.assert_allclose(trace[:, 0], rt[:, 0], rtol=rtol, err_msg=pre)              # cost at the start of every DDP iteration
+    np.testing.assert_allclose(trace[:, 10], rt[:, 10], rtol=rtol, err_msg=pre)            # ... and after its line search
+    np.testing.assert_allclose(trace[:, [1, 11]], rt[:, [1, 11]], rtol=rtol, atol=1e-13, err_msg=pre)    # dynamics infeasibility (down to 1e-5)
+    np.testing.assert_allclose(trace[:, 2:4], rt[:, 2:4], rtol=rtol, atol=1e-12, err_msg=pre)            # expected cost change
+    np.testing.assert_allclose(trace[:, 4:6], rt[:, 4:6], rtol=1e-8, atol=1e-12, err_msg=pre)            # merit parameter (a ratio of the above), regularisation
+    assert abs(info["cost"] - ref[pre + "final"][0]) <= rtol * abs(ref[pre + "final"][0])
+    assert abs(info["feas"] - ref[pre + "final"][1]) <= rtol * abs(ref[pre + "final"][1]) + 1e-13
+    kv = ref["kv"]
+    for i, p in enumerate(cm.unpack_solution(prob.deck, sol)):
+        q = pre + "ph%d_" % i
+        for name in ("Xbar", "Ubar", "dU"):
+            assert relerr(p[name], ref[q + name]) < rtol, (pre, i, name)
+        assert relerr(p["K"] @ kv, ref[q + "Kv"]) < rtol, (pre, i, "K v")
+        if i == 0:
+            assert relerr(p["K"][:4], ref[q + "K4"]) < rtol, (pre, "K4")
+        if full:
+            for name in ("K", "Quu", "Qux", "G", "Qu"):
+                assert relerr(p[name], ref[q + name]) < rtol, (pre, i, name)
+
+
+def test_initial_state_is_the_references(cm, ref):
+    """compute_hkd_state (HKDModel.h:66-96) as called by HKDMPCSolver::initialize, run by the reference itself."""
+    prob = cm.HKDProblem(CSV)
+    for b in range(len(ref["body"])):
+        x0 = prob.initial_state(ref["body"][b], ref["qJ"][b])
+        np.testing.assert_allclose(x0, ref["p%d_s0_x0" % b], rtol=0, atol=1e-15)
+
+
+def test_oracle_reproduces_the_reference_solver_on_the_initial_solves(cm, hkd_options, ref):
+    """MultiPhaseDDP<T>::solve on the problem HKDProblem<T>::initialization builds, caps 10 x 5 (30 - 38 DDP iterations, up to 73
+    line-search trials, four AL updates): every decision of every iteration and the whole solution."""
+    prob = cm.HKDProblem(CSV)
+    for b in range(len(ref["body"])):
+        pre = "p%d_s0_" % b
+        check_deck_layout(prob, ref, pre)
+        info, hist, trace, sol = oracle_solve(prob.deck, hkd_options, ref[pre + "x0"])
+        assert info["outer_iter"] - 1 == int(ref[pre + "n_al"]) or info["outer_iter"] == int(ref[pre + "n_al"])
+        check_solve(cm, prob, ref, pre, info, trace, sol, full=(b == 0))
+
+
+def test_oracle_and_mpc_shift_reproduce_the_reference_update_chain(cm, hkd_options, ref):
+    """HKDProblem<T>::update x 6 (HKDProblem.cpp:117-222: tail phase opened at offset 2, front phase removed at 12, Ubar[0] = 0) with the
+    re-solves of HKDMPCSolver<T>::update (caps 2 x 1): the re-cut decks, the warm start mpc.py shifts out of OUR previous solution and the
+    re-solve all equal the reference's at every step. x0 of step s = the plan's own prediction + the recorded nudge."""
+    from cafe_mpc_b200 import mpc
+    ort = copy.copy(hkd_options)
+    ort.max_AL_iter = 2; ort.max_DDP_iter = 1
+    kv = ref["kv"]
+    n_upd = ref["nudge"].shape[1]
+    for b in range(2):
+        prob, k0 = cm.HKDProblem(CSV), 0
+        info, hist, trace, sol, al = oracle_solve(prob.deck, hkd_options, ref["p%d_s0_x0" % b], al=mpc.initial_al(prob))
+        layouts = set()
+        for s in range(1, n_upd + 1):
+            pre = "p%d_s%d_" % (b, s)
+            k1 = k0 + 2
+            p1 = cm.HKDProblem(CSV, k0=k1, mpc_update=True)
+            check_deck_layout(p1, ref, pre)
+            layouts.add(tuple(ref[pre + "horizons"]))
+            guess = mpc.shifted_guess_batch(prob, k0, p1, k1, sol[None, :])[0]
+            for i, g in enumerate(cm.unpack_solution(p1.deck, guess)):
+                q = pre + "ph%d_" % i
+                if p1.phases()[i].single_shooting:
+                    # a tail phase this update opened: the reference leaves its fresh Trajectory zeroed (HKDProblem.cpp:166-167), mpc.py
+                    # writes reference states; neither is ever read (no shooting states, K = 0, the first rollout overwrites Xbar)
+                    assert not ref[q + "gXbar"].any() and not ref[q + "gUbar"].any() and not g["Ubar"].any() and not g["K"].any()
+                    continue
+                assert relerr(g["Xbar"], ref[q + "gXbar"]) < RTOL and relerr(g["Ubar"], ref[q + "gUbar"]) < RTOL, (pre, i)
+                assert relerr(g["K"] @ kv, ref[q + "gKv"]) < RTOL, (pre, i)
+            x1 = mpc.state_at(prob, cm.unpack_solution(prob.deck, sol), 2)
+            x1[3:6] += ref["nudge"][b, s - 1]
+            np.testing.assert_allclose(x1, ref[pre + "x0"], rtol=RTOL, atol=1e-12)
+            al = mpc.shift_al(prob, k0, p1, k1, al)
+            info, hist, trace, sol, al = oracle_solve(p1.deck, ort, x1, guess=guess, al=al)
+            check_solve(cm, p1, ref, pre, info, trace, sol)
+            prob, k0 = p1, k1
+        assert len(layouts) >= 3      # the chain went through a tail-phase opening and a front-phase removal

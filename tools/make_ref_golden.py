@@ -1,0 +1,195 @@
+#!/usr/bin/env python
+"""Golden vectors from the REFERENCE's own HS-DDP solver (test infrastructure; needs /root/reference, so it runs in the build
+container only - the fixture it writes travels).
+
+oracle/_ref/ref_hkd is the reference's MultiPhaseDDP / SinglePhase / constraints / trajectory management / HKDProblem / HKD costs
+and constraints / QuadReference / CasADi interface compiled unchanged from /root/reference (oracle/refbuild/Makefile) against the
+Eigen / Boost / LCM stand-ins of oracle/refbuild/shim. This script runs it on the first N_PROB problems of the HKD trot workload
+(problem 0 = the nominal problem of HKDMPCSolver::initialize, the others SplitMix64-perturbed, cafe_mpc_b200/workload.py) through the
+initial solve (caps of HKDMPC/settings/ddp_setting.info) and N_UPD consecutive MPC updates (HKDProblem::update, caps 2 x 1), and
+stores what the reference decided and produced in tests/golden/ref_hkd_trot.npz:
+
+  per problem b and solve s (0 = initial, s >= 1 = after the s-th update), prefix p{b}_s{s}_:
+    x0 [24], counters [3] = iter, ls_iter_total, reg_iter_total, final [4] = cost, feas, max_tconstr, max_pconstr,
+    trace [iter, 12] in the oracle's CAFE_TRACE_W layout (oracle/oracle_api.h; taken in full precision by a decorator around every
+      phase; column 4 (merit_rho) and 5 (reg_after) are derived from the observed columns with the solver's formulas),
+    n_al = number of AL parameter updates, horizons [n_phases], contacts [n_phases, 4],
+    per phase i: ph{i}_Xbar [(h+1), 24], ph{i}_Ubar [h, 24], ph{i}_dU [h, 24], ph{i}_Kv [h, 24] = K v for the fixed vector
+      v = cos(1 + 0..23), ph0_K4 [min(h,4), 24, 24] (the first gains of the plan); for s >= 1 also the warm start the reference's
+      update left behind: ph{i}_gXbar, ph{i}_gUbar, ph{i}_gKv.
+  p0_s0_ph{i}_K, _Quu, _Qux, _G, _Qu in full for the nominal initial solve.
+  inputs: body [N_PROB, 12], qJ [N_PROB, 12], nudge [N_PROB, N_UPD, 3].
+
+Usage: python tools/make_ref_golden.py   (builds oracle/_ref/ref_hkd first)"""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+N_PROB, N_UPD = 4, 6
+KV = np.cos(1.0 + np.arange(24))
+ARRAYS = ("Xbar", "Ubar", "K", "dU", "G", "Qu", "Quu", "Qux", "Defect")
+
+
+def parse(path):
+    """-> list over problems of list over solves of dict(guess=[phase dicts], x0, counters, final, events, solution=[phase dicts])"""
+    L = open(path).read().split("\n")
+    pos = 0
+
+    def phases(tag):
+        nonlocal pos
+        head = L[pos].split(); pos += 1
+        assert head[0] == tag and head[1] == "n_phases", head
+        out = []
+        for i in range(int(head[2])):
+            h = L[pos].split(); pos += 1
+            assert h[0] == "phase" and int(h[1]) == i
+            ph = dict(horizon=int(h[3]), contact=[int(v) for v in h[5:9]], start=float(h[10]), end=float(h[12]))
+            for name in ARRAYS:
+                t = L[pos].split(); pos += 1
+                assert t[0] == name, (t[0], name)
+                ph[name] = np.array(t[1:], dtype=np.float64)
+            hz = ph["horizon"]
+            ph["Xbar"] = ph["Xbar"].reshape(hz + 1, 24); ph["G"] = ph["G"].reshape(hz + 1, 24); ph["Defect"] = ph["Defect"].reshape(hz + 1, 24)
+            for name in ("Ubar", "dU", "Qu"):
+                ph[name] = ph[name].reshape(hz, 24)
+            for name in ("K", "Quu", "Qux"):
+                ph[name] = ph[name].reshape(hz, 24, 24).transpose(0, 2, 1)   # written column-major
+            out.append(ph)
+        return out
+
+    head = L[pos].split(); pos += 1
+    n_prob, n_upd = int(head[1]), int(head[3])
+    probs = []
+    for b in range(n_prob):
+        assert L[pos].split() == ["problem", str(b)]; pos += 1
+        solves = []
+        for s in range(n_upd + 1):
+            if s > 0:
+                assert L[pos].split() == ["update", str(s - 1)]; pos += 1
+            rec = dict(guess=phases("guess"))
+            t = L[pos].split(); pos += 1; assert t[0] == "x0"; rec["x0"] = np.array(t[1:], dtype=np.float64)
+            t = L[pos].split(); pos += 1; assert t[0] == "counters"; rec["counters"] = np.array([int(t[2]), int(t[4]), int(t[6])])
+            t = L[pos].split(); pos += 1; assert t[0] == "final"; rec["final"] = np.array([float(t[2]), float(t[4]), float(t[6]), float(t[8])])
+            t = L[pos].split(); pos += 1; assert t[0] == "float_cost_buffer"
+            t = L[pos].split(); pos += 1; assert t[0] == "events"
+            ne = int(t[1])
+            rec["events"] = [(int(a), int(p), float(x), float(y)) for a, p, x, y in (ln.split() for ln in L[pos:pos + ne])]
+            pos += ne
+            rec["solution"] = phases("solution")
+            solves.append(rec)
+        probs.append(solves)
+    return probs
+
+
+EV_ROLLOUT, EV_COST, EV_FEAS, EV_LQ, EV_BWD, EV_LIN, EV_ACCEPT, EV_AL = 1, 2, 3, 4, 5, 6, 7, 8
+
+
+def trace_of(events, n_phases, opt):
+    """The 12-column per-iteration record (oracle/oracle_api.h CAFE_TRACE_W) from the decorator's event list."""
+    # split at the LQ events of phase 0: an iteration = [cost + feas before it] LQ, sweeps, linear rollout, line-search trials
+    lq = [i for i, e in enumerate(events) if e[0] == EV_LQ and e[1] == 0]
+    rows = []
+    for n, i0 in enumerate(lq):
+        i1 = lq[n + 1] if n + 1 < len(lq) else len(events)
+        # cost / feas evaluated just before this LQ: the last n_phases COST / FEAS events before i0
+        pre = events[:i0]
+        cost = sum(e[2] for e in [e for e in pre if e[0] == EV_COST][-n_phases:])           # phase order, like MultiPhaseDDP::compute_cost
+        feas = np.sqrt(sum(e[2] for e in [e for e in pre if e[0] == EV_FEAS][-n_phases:]))
+        body = events[i0:i1]
+        # the next iteration's leading compute_cost / feasibility belong to it, not to this one: cut them off (they follow the last
+        # ACCEPT or the last line-search trial)
+        sweeps = [e for e in body if e[0] == EV_BWD and e[1] == n_phases - 1]
+        ok_sweep = [e for e in body if e[0] == EV_BWD and e[1] == 0 and e[3] == 1.0]
+        lin = [e for e in body if e[0] == EV_LIN]
+        dV1 = 0.0; dV2 = 0.0
+        for e in lin:            # phase order 0..n-1 (MultiPhaseDDP::linear_rollout)
+            dV1 += e[2]; dV2 += e[3]
+        row = np.zeros(12)
+        row[0], row[1], row[2], row[3] = cost, feas, dV1, dV2
+        dV_abs = abs(dV1 + 0.5 * dV2)
+        row[4] = dV_abs / ((1 - opt["merit_scale"]) * feas) + opt["merit_offset"] if feas > opt["dynamics_feas_thresh"] else 0.0
+        reg = ok_sweep[-1][2] if ok_sweep else sweeps[-1][2]
+        reg_after = reg / 20
+        row[5] = 0.0 if reg_after < 1e-06 else reg_after
+        row[6] = len(sweeps)
+        trials = [j for j, e in enumerate(body) if e[0] == EV_ROLLOUT and e[1] == 0]
+        row[7] = len(trials)
+        accepted = any(e[0] == EV_ACCEPT for e in body)
+        row[8] = 1.0 if accepted else 0.0
+        if trials:
+            j = trials[-1]
+            nxt = body[j:]
+            row[9] = body[j][2] if accepted else 0.0
+            c_after = sum(e[2] for e in [e for e in nxt if e[0] == EV_COST][:n_phases])
+            f_after = np.sqrt(sum(e[2] for e in [e for e in nxt if e[0] == EV_FEAS][:n_phases]))
+            row[10] = c_after if accepted else cost
+            row[11] = f_after
+        else:
+            row[10], row[11] = cost, feas
+        rows.append(row)
+    return np.array(rows).reshape(-1, 12)
+
+
+def main():
+    import cafe_mpc_b200 as cm
+    from cafe_mpc_b200 import workload as w
+    subprocess.check_call(["make", "-C", os.path.join(REPO, "oracle/refbuild"), "-j8"], stdout=subprocess.DEVNULL)
+    csv = os.path.join(REPO, "data/Reference/Data/trot/heuristic/quad_reference.csv")
+    prob = cm.HKDProblem(csv)
+    body = np.tile(w.HKD_NOMINAL_BODY, (N_PROB, 1)); qJ = np.tile(w.HKD_NOMINAL_QJ, (N_PROB, 1))
+    for b in range(1, N_PROB):
+        for j in range(12):
+            body[b, j] += w.HKD_BODY_SCALE[j] * (2 * w.uniform(b, j) - 1)
+            qJ[b, j] += w.HKD_QJ_SCALE[j] * (2 * w.uniform(b, 12 + j) - 1)
+    x0 = np.stack([prob.initial_state(body[b], qJ[b]) for b in range(N_PROB)])
+    assert np.array_equal(x0, w.hkd_batch(prob, N_PROB))
+    nudge = np.zeros((N_PROB, N_UPD, 3))
+    for b in range(N_PROB):
+        nudge[b, :] = 1e-3 * (x0[b, 3:6] - x0[0, 3:6])
+    opt = cm.load_hsddp_setting(os.path.join(REPO, "data/HKDMPC/settings/ddp_setting.info"))
+    optd = dict(merit_scale=opt.merit_scale, merit_offset=opt.merit_offset, dynamics_feas_thresh=opt.dynamics_feas_thresh)
+    with tempfile.TemporaryDirectory() as td:
+        fin, fout = os.path.join(td, "in.txt"), os.path.join(td, "out.txt")
+        with open(fin, "w") as f:
+            f.write("%d %d\n" % (N_PROB, N_UPD))
+            for b in range(N_PROB):
+                f.write(" ".join(repr(float(v)) for v in np.concatenate([body[b], qJ[b]])) + "\n")
+                for u in range(N_UPD):
+                    f.write(" ".join(repr(float(v)) for v in nudge[b, u]) + "\n")
+        # the reference reads "../HKDMPC/settings/*.info" relative to its working directory (HKDProblem.cpp:71, HKDMPC.cpp:23)
+        subprocess.check_call([os.path.join(REPO, "oracle/_ref/ref_hkd"), csv, fin, fout], cwd=os.path.join(REPO, "data/_run"), stdout=subprocess.DEVNULL)
+        probs = parse(fout)
+    out = dict(body=body, qJ=qJ, nudge=nudge, kv=KV)
+    for b, solves in enumerate(probs):
+        for s, rec in enumerate(solves):
+            pre = "p%d_s%d_" % (b, s)
+            sol = rec["solution"]
+            out[pre + "x0"] = rec["x0"]; out[pre + "counters"] = rec["counters"]; out[pre + "final"] = rec["final"]
+            out[pre + "trace"] = trace_of(rec["events"], len(sol), optd)
+            assert len(out[pre + "trace"]) == rec["counters"][0]
+            assert int(out[pre + "trace"][:, 7].sum()) == rec["counters"][1] and int(out[pre + "trace"][:, 6].sum()) == rec["counters"][2]
+            out[pre + "n_al"] = np.array(sum(1 for e in rec["events"] if e[0] == EV_AL and e[1] == 0))
+            out[pre + "horizons"] = np.array([p["horizon"] for p in sol]); out[pre + "contacts"] = np.array([p["contact"] for p in sol])
+            for i, p in enumerate(sol):
+                q = pre + "ph%d_" % i
+                out[q + "Xbar"], out[q + "Ubar"], out[q + "dU"] = p["Xbar"], p["Ubar"], p["dU"]
+                out[q + "Kv"] = p["K"] @ KV
+                if i == 0:
+                    out[q + "K4"] = p["K"][:4]
+                if b == 0 and s == 0:
+                    out[q + "K"], out[q + "Quu"], out[q + "Qux"], out[q + "G"], out[q + "Qu"] = p["K"], p["Quu"], p["Qux"], p["G"], p["Qu"]
+                if s > 0:
+                    g = rec["guess"][i]
+                    out[q + "gXbar"], out[q + "gUbar"], out[q + "gKv"] = g["Xbar"], g["Ubar"], g["K"] @ KV
+    dst = os.path.join(REPO, "tests/golden/ref_hkd_trot.npz")
+    np.savez_compressed(dst, **out)
+    print("wrote", dst, os.path.getsize(dst) // 1024, "KB;", "iterations of the initial solves:", [int(out["p%d_s0_counters" % b][0]) for b in range(N_PROB)])
+
+
+if __name__ == "__main__":
+    main()
