@@ -224,6 +224,24 @@ class MultiPhaseDDP:
         assert guess.shape[1] == lib.cafe_solution_size(self.problem.deck)
         check(lib.cafe_gpu_set_initial_guess(self._h, guess.ctypes.data_as(C.c_void_p), guess.shape[0]))
 
+    def set_al_params(self, al):
+        """Augmented-Lagrangian parameters the next solves start from, [B, n_phases, 4, 2] = (sigma, lambda) per touchdown-constraint element
+        (None: the deck's TD_AL values). The reference carries them from one MPC step to the next (cafe_gpu.h); update_deck and
+        shift_guess_from do so on the device by themselves."""
+        if al is None:
+            check(lib.cafe_gpu_set_al_params(self._h, None, 0))
+            return
+        al = np.ascontiguousarray(al, dtype=np.float64)
+        assert al.shape[1:] == (len(self.problem.phases()), 4, 2)
+        check(lib.cafe_gpu_set_al_params(self._h, al.ctypes.data_as(C.c_void_p), al.shape[0]))
+
+    def get_al_params(self, B=None):
+        """(sigma, lambda) of every touchdown-constraint element as the last solve left them: [B, n_phases, 4, 2]."""
+        B = B or self.B
+        out = np.zeros((B, len(self.problem.phases()), 4, 2))
+        check(lib.cafe_gpu_get_al_params(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def shift_guess_from(self, prev, prev_k0, k0, B=None):
         """Warm start from the solution held by the solver `prev` (deck at start offset prev_k0), shifted to this solver's deck (start
         offset k0) on the device - the receding-horizon update of MHPCProblem::update without a host round trip."""

@@ -46,6 +46,9 @@ struct CafeHandle {
   unsigned long long* d_hkd_mask = nullptr;   // structural A / B / lxx / luu patterns of the HKD model   // structural lxx patterns of the whole-body knots
   double* d_guess = nullptr; size_t guess_bytes = 0; int guess_B = 0;  // packed initial guesses [B][solution_size] (warm start)  // per-problem reference records [n_records][CAFE_REF_W][ldb]
   double* d_x0raw = nullptr;
+  // augmented-Lagrangian parameters the next solve starts from instead of the deck's (the MPC loop's carry-over: the reference never resets
+  // them, ConstraintsBase.h:367-374): [(phase * 4 + element) * 2 + {sigma, lambda}][ldb]; al_B = 0: deck values
+  double* d_al = nullptr; int al_B = 0;
   int* d_fail = nullptr; size_t fail_bytes = 0;
   int* h_nactive = nullptr;  // pinned
   double* d_pack = nullptr; size_t pack_bytes = 0;
@@ -105,6 +108,37 @@ __global__ void k_init(const SolverDev* __restrict__ Sp, const double* __restric
     for (int i = 0; i < n0; ++i) x0[(size_t)i * S.ldb + b] = x0raw[(size_t)b * n0 + i];
     S.c.active[b] = 1; S.c.do_ls[b] = 1; S.c.sel[b] = -1; S.c.min_pivot[b] = 1e300;
   }
+}
+
+// carried augmented-Lagrangian parameters replace the deck's initial values (after k_init)
+__global__ void k_apply_al(const SolverDev* __restrict__ Sp, const double* __restrict__ al) {
+  const SolverDev& S = *Sp;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= S.B) return;
+  for (int pi = 0; pi < S.n_phases; ++pi) {
+    const PhaseDev& ph = S.ph[pi];
+    for (int i = 0; i < ph.n_td; ++i) {
+      ph.al_sigma[(size_t)i * S.ldb + b] = al[(size_t)((pi * 4 + i) * 2) * S.ldb + b];
+      ph.al_lambda[(size_t)i * S.ldb + b] = al[(size_t)((pi * 4 + i) * 2 + 1) * S.ldb + b];
+    }
+  }
+}
+// the MPC update's carry-over: new phase pi continues old phase src[pi] (or -1: its constraint starts from the deck's values init[pi])
+struct AlCarry { int n_phases, src[CAFE_MAX_PHASES], n_td[CAFE_MAX_PHASES]; double sigma0[CAFE_MAX_PHASES], lambda0[CAFE_MAX_PHASES]; };
+__global__ void k_carry_al(const SolverDev* __restrict__ Sp, const __grid_constant__ AlCarry c, int B, int ldb_dst, double* __restrict__ al) {
+  const SolverDev& S = *Sp;   // the OLD layout
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  for (int pi = 0; pi < c.n_phases; ++pi)
+    for (int i = 0; i < 4; ++i) {
+      double sg = 0, lm = 0;
+      if (i < c.n_td[pi]) {
+        if (c.src[pi] >= 0) { const PhaseDev& ph = S.ph[c.src[pi]]; sg = ph.al_sigma[(size_t)i * S.ldb + b]; lm = ph.al_lambda[(size_t)i * S.ldb + b]; }
+        else { sg = c.sigma0[pi]; lm = c.lambda0[pi]; }
+      }
+      al[(size_t)((pi * 4 + i) * 2) * ldb_dst + b] = sg;
+      al[(size_t)((pi * 4 + i) * 2 + 1) * ldb_dst + b] = lm;
+    }
 }
 
 __global__ void k_init_devx0(const SolverDev* __restrict__ Sp, const double* __restrict__ x0dev, int ldx, int n0) {
@@ -487,6 +521,7 @@ extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, 
   CUDA_OK_H(cudaStreamCreate(&H->stream));
   if (int rc = configure(H, deck, all_hkd, n_knots)) { cafe_gpu_destroy(H); return rc; }
   CUDA_OK_H(cudaMalloc(&H->d_x0raw, (size_t)H->ldb * CAFE_MAX_N * sizeof(double)));
+  CUDA_OK_H(cudaMalloc(&H->d_al, (size_t)H->ldb * CAFE_MAX_PHASES * 8 * sizeof(double)));
   CUDA_OK_H(cudaMalloc(&H->dS, sizeof(SolverDev)));
   CUDA_OK_H(cudaMallocHost(&H->h_nactive, 64));
   for (int i = 0; i < 3; ++i) { CUDA_OK_H(cudaStreamCreate(&H->stream2[i])); CUDA_OK_H(cudaEventCreateWithFlags(&H->ev_join[i], cudaEventDisableTiming)); }
@@ -538,7 +573,7 @@ extern "C" int cafe_gpu_destroy(CafeHandle* H) {
   cudaSetDevice(H->device);
   if (H->tab_busy && H->ev_tab) cudaEventSynchronize(H->ev_tab);
   cudaFree(H->d_tab); if (H->h_tab) cudaFreeHost(H->h_tab); if (H->ev_tab) cudaEventDestroy(H->ev_tab);
-  cudaFree(H->arena); cudaFree(H->d_ref); cudaFree(H->d_ref_pp); cudaFree(H->d_lxx_mask); cudaFree(H->d_hkd_mask); cudaFree(H->d_guess); cudaFree(H->d_x0raw); cudaFree(H->dS); cudaFree(H->d_pack); cudaFree(H->d_segs);
+  cudaFree(H->arena); cudaFree(H->d_ref); cudaFree(H->d_ref_pp); cudaFree(H->d_lxx_mask); cudaFree(H->d_hkd_mask); cudaFree(H->d_guess); cudaFree(H->d_x0raw); cudaFree(H->d_al); cudaFree(H->dS); cudaFree(H->d_pack); cudaFree(H->d_segs);
   if (H->h_nactive) cudaFreeHost(H->h_nactive);
   if (H->stream) cudaStreamDestroy(H->stream);
   for (int i = 0; i < 3; ++i) { if (H->stream2[i]) cudaStreamDestroy(H->stream2[i]); if (H->ev_join[i]) cudaEventDestroy(H->ev_join[i]); }
@@ -558,6 +593,7 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
   if (opt->max_AL_iter > 250) { cafe::set_last_error("more than 250 outer iterations: the relaxed-barrier update counts are 8 bits wide"); return CAFE_ERR_UNSUPPORTED; }
   if (opt->max_AL_iter * opt->max_DDP_iter + 1 > CAFE_HIST_CAP) { cafe::set_last_error("iteration caps exceed the history capacity"); return CAFE_ERR_UNSUPPORTED; }
   if (H->guess_B > 0 && B > H->guess_B) { cafe::set_last_error("batch larger than the initial-guess set"); return CAFE_ERR_ARG; }
+  if (H->al_B > 0 && B > H->al_B) { cafe::set_last_error("batch larger than the carried augmented-Lagrangian parameter set"); return CAFE_ERR_ARG; }
   if (H->S.ph[0].ref_pp && B > H->ref_pp_B) { cafe::set_last_error("batch larger than the per-problem reference set"); return CAFE_ERR_ARG; }
   CUDA_OK(cudaSetDevice(H->device));
   SolverDev& S = H->S;
@@ -593,6 +629,7 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
   const unsigned g_knots = (unsigned)((nthr_knots + tpb - 1) / tpb);
   timed(H, CAFE_K_MISC, [&] { k_init<<<g_knots, tpb, 0, st>>>(H->dS, H->d_x0raw, n0); });
   if (x0_dev) timed(H, CAFE_K_MISC, [&] { k_init_devx0<<<(B + 127) / 128, 128, 0, st>>>(H->dS, x0_dev, ldx, n0); });
+  if (H->al_B > 0) timed(H, CAFE_K_MISC, [&] { k_apply_al<<<(B + 127) / 128, 128, 0, st>>>(H->dS, H->d_al); });
   if (H->guess_B > 0) {
     // warm start: Xbar (= X), Ubar (= U) and K of the caller's guess replace the cold-start values; the first rollout (eps = 0)
     // then applies U = Ubar + K (X - Xbar) around it, which is how the reference re-solves after MHPCProblem::update
@@ -964,6 +1001,45 @@ static int build_shift(const SolverDev& src, int src_k0, const ShiftDst& dst, in
   sol_size = off;
   return 0;
 }
+// which old phase's touchdown constraint a phase of the new deck inherits (the rules of cafe_mpc_b200/mpc.py::shift_al): the reference keeps a
+// phase's TouchDownConstraint object, and with it sigma / lambda, for as long as the phase lives - TerminalConstraintBase::reset_params, called
+// by every update (HKDProblem.cpp:208, MHPCProblem.cpp:363), is an empty function (ConstraintsBase.h:367-374). A phase that continues an
+// old phase (same stance, overlapping in absolute time) with the same touchdown feet inherits; any other constraint starts from the deck's values.
+static void build_al_carry(const CafeDeck& od, int old_k0, const CafeDeck& nd, int new_k0, AlCarry& c) {
+  c.n_phases = nd.n_phases;
+  const int lead_o = od.phase[0].model, lead_n = nd.phase[0].model;
+  int ns = new_k0;
+  for (int i = 0; i < nd.n_phases; ++i) {
+    const CafePhase& np_ = nd.phase[i];
+    c.src[i] = -1; c.n_td[i] = np_.n_td; c.sigma0[i] = np_.al_td.sigma; c.lambda0[i] = np_.al_td.lambda;
+    if (np_.model != lead_n || lead_n != lead_o || lead_n == CAFE_MODEL_SRB) continue;
+    const int ne = ns + np_.horizon;
+    int os = old_k0;
+    for (int j = 0; j < od.n_phases && od.phase[j].model == lead_o; ++j) {
+      const CafePhase& op = od.phase[j];
+      const int oe = os + op.horizon;
+      bool same = true;
+      for (int f = 0; f < 4; ++f) same = same && op.contact[f] == np_.contact[f];
+      if (same && os <= ne && oe >= ns) {
+        bool feet = op.n_td > 0 && op.n_td == np_.n_td;
+        for (int f = 0; feet && f < op.n_td; ++f) feet = op.td_foot[f] == np_.td_foot[f];
+        if (feet) c.src[i] = j;
+        break;
+      }
+      os = oe;
+    }
+    ns = ne;
+  }
+}
+static int run_al_carry(CafeHandle* owner, const CafeHandle* src, int src_k0, const CafeDeck& nd, int dst_k0, int B) {
+  AlCarry c;
+  build_al_carry(src->deck, src_k0, nd, dst_k0, c);
+  k_carry_al<<<(B + 127) / 128, 128, 0, owner->stream>>>(src->dS, c, B, owner->ldb, owner->d_al);
+  CUDA_OK(cudaGetLastError());
+  owner->al_B = B;
+  return 0;
+}
+
 // fills owner->d_guess (B packed records of sol_size doubles) on owner->stream
 static int run_shift(CafeHandle* owner, const std::vector<ShiftEntry>& ent, int ldb_src, int B, long sol_size) {
   const size_t need = (size_t)B * (size_t)sol_size * sizeof(double);
@@ -993,6 +1069,7 @@ extern "C" int cafe_gpu_shift_guess(CafeHandle* dst, CafeHandle* src, int src_k0
   // the previous solve ran on src's stream: order this after it, and later solves of dst after this
   CUDA_OK(cudaStreamSynchronize(src->stream));
   if (int rc = run_shift(dst, ent, src->ldb, B, sol_size)) return rc;
+  if (int rc = run_al_carry(dst, src, src_k0, dst->deck, dst_k0, B)) return rc;
   CUDA_OK(cudaStreamSynchronize(dst->stream));
   dst->guess_B = B;
   return 0;
@@ -1031,6 +1108,9 @@ extern "C" int cafe_gpu_update_deck(CafeHandle* H, const CafeDeck* deck, int k_a
     if (int rc = build_shift(H->S, 0, d, k_advance, ent, sol_size)) return rc;
     if (sol_size != cafe_solution_size(deck)) { cafe::set_last_error("internal: packed record size mismatch"); return CAFE_ERR_ARG; }
     if (int rc = run_shift(H, ent, H->ldb, B, sol_size)) return rc;
+    if (int rc = run_al_carry(H, H, 0, *deck, k_advance, B)) return rc;
+  } else {
+    H->al_B = 0;
   }
   if (int rc = configure(H, deck, all_hkd, n_knots)) return rc;
   H->guess_B = B;
@@ -1053,6 +1133,45 @@ extern "C" int cafe_gpu_get_planned_state(CafeHandle* H, int knots_ahead, double
   }
   cafe::set_last_error("beyond the plan");
   return CAFE_ERR_ARG;
+}
+
+// ---- augmented-Lagrangian parameters across the solves of an MPC loop. al / out: host [B][n_phases][4][2] = (sigma, lambda) per touchdown-
+//      constraint element (unused elements zero).
+extern "C" int cafe_gpu_set_al_params(CafeHandle* H, const double* al, int B) {
+  if (!H) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
+  if (!al) { H->al_B = 0; return 0; }
+  if (B <= 0 || B > H->max_batch) { cafe::set_last_error("bad batch size for the augmented-Lagrangian parameter set"); return CAFE_ERR_ARG; }
+  CUDA_OK(cudaSetDevice(H->device));
+  const int np_ = H->S.n_phases;
+  const size_t ldb = (size_t)H->ldb;
+  std::vector<double> t((size_t)CAFE_MAX_PHASES * 8 * ldb, 0.0);
+  for (int b = 0; b < B; ++b)
+    for (int e = 0; e < np_ * 8; ++e) t[(size_t)e * ldb + b] = al[(size_t)b * np_ * 8 + e];
+  CUDA_OK(cudaStreamSynchronize(H->stream));
+  CUDA_OK(cudaMemcpy(H->d_al, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
+  H->al_B = B;
+  return 0;
+}
+
+extern "C" int cafe_gpu_get_al_params(CafeHandle* H, double* out) {
+  if (!H || !out || H->B <= 0) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
+  CUDA_OK(cudaSetDevice(H->device));
+  CUDA_OK(cudaStreamSynchronize(H->stream));
+  const int np_ = H->S.n_phases, B = H->B;
+  const size_t ldb = (size_t)H->ldb;
+  std::vector<double> sg(4 * ldb), lm(4 * ldb);
+  for (int pi = 0; pi < np_; ++pi) {
+    const PhaseDev& ph = H->S.ph[pi];
+    CUDA_OK(cudaMemcpy(sg.data(), ph.al_sigma, 4 * ldb * sizeof(double), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(lm.data(), ph.al_lambda, 4 * ldb * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int b = 0; b < B; ++b)
+      for (int i = 0; i < 4; ++i) {
+        const bool on = i < ph.n_td;
+        out[((size_t)b * np_ + pi) * 8 + i * 2] = on ? sg[(size_t)i * ldb + b] : 0.0;
+        out[((size_t)b * np_ + pi) * 8 + i * 2 + 1] = on ? lm[(size_t)i * ldb + b] : 0.0;
+      }
+  }
+  return 0;
 }
 
 // ---- per-problem references with a shared contact schedule: every problem tracks its own records

@@ -104,7 +104,7 @@ EXPORTED = [
     "cafe_deck_free", "cafe_hkd_state", "cafe_deck_lq_pattern", "cafe_solution_size", "cafe_command_size", "cafe_gpu_create",
     "cafe_gpu_destroy", "cafe_gpu_solve_batch", "cafe_gpu_solve_batch_device", "cafe_gpu_get_info",
     "cafe_gpu_get_history", "cafe_gpu_get_trace", "cafe_gpu_get_solution", "cafe_gpu_get_commands", "cafe_gpu_get_commands_device", "cafe_gpu_get_solve_ms",
-    "cafe_gpu_set_references", "cafe_gpu_set_initial_guess", "cafe_gpu_shift_guess", "cafe_gpu_get_planned_state", "cafe_gpu_update_deck", "cafe_lcm_command_size", "cafe_gpu_get_lcm_commands", "cafe_gpu_get_lcm_commands_device", "cafe_hkd_lcm_command_size", "cafe_gpu_get_hkd_lcm_commands", "cafe_gpu_get_hkd_lcm_commands_device",
+    "cafe_gpu_set_references", "cafe_gpu_set_initial_guess", "cafe_gpu_set_al_params", "cafe_gpu_get_al_params", "cafe_gpu_shift_guess", "cafe_gpu_get_planned_state", "cafe_gpu_update_deck", "cafe_lcm_command_size", "cafe_gpu_get_lcm_commands", "cafe_gpu_get_lcm_commands_device", "cafe_hkd_lcm_command_size", "cafe_gpu_get_hkd_lcm_commands", "cafe_gpu_get_hkd_lcm_commands_device",
     "cafe_gpu_get_timing", "cafe_gpu_get_units", "cafe_gpu_set_profiling", "cafe_gpu_debug_get", "cafe_gpu_measure_fp64_peak",
     "cafe_gpu_shard_range", "cafe_gpu_create_multi", "cafe_gpu_multi_destroy", "cafe_gpu_multi_ndev", "cafe_gpu_multi_handle", "cafe_gpu_multi_solve_batch", "cafe_gpu_multi_update_deck",
     "cafe_gpu_multi_get_info", "cafe_gpu_multi_get_commands", "cafe_gpu_nccl_unique_id", "cafe_gpu_comm_init_rank", "cafe_gpu_comm_destroy", "cafe_gpu_gather_commands",

@@ -123,6 +123,15 @@ int cafe_gpu_set_references(CafeHandle* h, const double* refs, int B);
  * behind (MHPCProblem.cpp:252-397): MultiPhaseDDP::solve begins with hybrid_rollout(eps = 0), U = Ubar + K (X - Xbar), around
  * them (MultiPhaseDDP.cpp:238). Stays in force for the following solves; guess = NULL returns to the cold start. */
 int cafe_gpu_set_initial_guess(CafeHandle* h, const double* guess, int B);
+/* Augmented-Lagrangian parameters across the solves of an MPC loop. The reference keeps a phase's TouchDownConstraint object - and the
+ * sigma / lambda its update_params left behind (ConstraintsBase.h:375-392) - for as long as the phase lives: reset_params(), which
+ * HKDProblem::update / MHPCProblem::update call for every phase (HKDProblem.cpp:208, MHPCProblem.cpp:363), is an empty function
+ * (ConstraintsBase.h:367-374). al / out = host [B][n_phases][4][2] = (sigma, lambda) per touchdown-constraint element, unused entries zero.
+ * set: the following solves start from these values instead of the deck's TD_AL values (al = NULL returns to the deck's);
+ * get: the values the last solve left behind. cafe_gpu_update_deck and cafe_gpu_shift_guess carry them over on the device by themselves
+ * (a phase that continues an old phase with the same touchdown feet inherits, every other constraint starts from the deck's values). */
+int cafe_gpu_set_al_params(CafeHandle* h, const double* al, int B);
+int cafe_gpu_get_al_params(CafeHandle* h, double* out);
 /* The same warm start without leaving the device: the guess of `dst` (deck at start offset dst_k0 of the reference file) is built from
  * the solution held by `src` (deck at start offset src_k0 <= dst_k0, same device, solved with at least B problems) by the shift
  * MHPCProblem::update applies to the trajectories (MHPCProblem.cpp:252-397; Trajectory::pop_front / push_back_state,

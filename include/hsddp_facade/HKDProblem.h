@@ -73,14 +73,14 @@ class HKDProblem {
   void update() {
     if (!deck_) throw std::logic_error("HKDProblem::update before initialization");
     quad_ref_ptr->step(dt_mpc);
-    struct Old { int s, e; int contact[4]; shared_ptr<Traj_T> traj; };
+    struct Old { int s, e; int contact[4]; shared_ptr<Traj_T> traj; shared_ptr<Phase_T> phase; int n_td, td_foot[4]; };
     std::vector<Old> old;
     {
       const CafeDeck* d = deck_->deck();
       int s = deck_->k0;
       for (int i = 0; i < d->n_phases; ++i) {
-        Old o{s, s + d->phase[i].horizon, {0, 0, 0, 0}, pdata->trajectory_ptrs[i]};
-        for (int f = 0; f < 4; ++f) o.contact[f] = d->phase[i].contact[f];
+        Old o{s, s + d->phase[i].horizon, {0, 0, 0, 0}, pdata->trajectory_ptrs[i], pdata->phase_ptrs[i], d->phase[i].n_td, {0, 0, 0, 0}};
+        for (int f = 0; f < 4; ++f) { o.contact[f] = d->phase[i].contact[f]; o.td_foot[f] = d->phase[i].td_foot[f]; }
         old.push_back(o); s += d->phase[i].horizon;
       }
     }
@@ -100,6 +100,12 @@ class HKDProblem {
         if (same && o.s <= e && o.e >= s) { src = &o; break; }
       }
       const bool continues_last = src && src == &old.back();
+      if (src && src->phase->cafe_al_set && src->n_td > 0 && src->n_td == p.n_td) {
+        // the phase keeps its TouchDownConstraint object, hence sigma / lambda (reset_params is empty, ConstraintsBase.h:367-374)
+        bool feet = true;
+        for (int f = 0; f < p.n_td; ++f) feet = feet && src->td_foot[f] == p.td_foot[f];
+        if (feet) { for (int q = 0; q < 8; ++q) pdata->phase_ptrs[i]->cafe_al[q] = src->phase->cafe_al[q]; pdata->phase_ptrs[i]->cafe_al_set = true; }
+      }
       for (int k = 0; k <= p.horizon; ++k) {
         const int a = s + k;
         if (src && src->s <= a && a <= src->e) nt.Xbar[k] = src->traj->Xbar[a - src->s];

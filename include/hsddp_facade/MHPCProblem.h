@@ -196,14 +196,15 @@ class MHPCProblem {
     need_deck();
     quad_reference->step(pconfig->dt_mpc);
     const int nsteps = (int)round(pconfig->dt_mpc / pconfig->dt_wb);
-    struct Old { int s, e; int contact[4]; shared_ptr<WBTraj_T> traj; };
+    struct Old { int s, e; int contact[4]; shared_ptr<WBTraj_T> traj; shared_ptr<WBPhase_T> phase; int n_td, td_foot[4]; };
     std::vector<Old> old;
     {
       const CafeDeck* d = deck_->deck();
       int s = deck_->k0;
       for (int i = 0, w = 0; i < d->n_phases; ++i) if (d->phase[i].model == CAFE_MODEL_WB) {
-        Old o{s, s + d->phase[i].horizon, {0, 0, 0, 0}, pdata->wb_trajs[w++]};
-        for (int f = 0; f < 4; ++f) o.contact[f] = d->phase[i].contact[f];
+        Old o{s, s + d->phase[i].horizon, {0, 0, 0, 0}, pdata->wb_trajs[w], pdata->wb_phases[w], d->phase[i].n_td, {0, 0, 0, 0}};
+        ++w;
+        for (int f = 0; f < 4; ++f) { o.contact[f] = d->phase[i].contact[f]; o.td_foot[f] = d->phase[i].td_foot[f]; }
         old.push_back(o); s += d->phase[i].horizon;
       }
     }
@@ -220,7 +221,9 @@ class MHPCProblem {
         if (old_srb && old_srb->horizon == p.horizon) { pdata->srb_traj->Xbar = old_srb->Xbar; pdata->srb_traj->Ubar = old_srb->Ubar; pdata->srb_traj->K = old_srb->K; }
         continue;
       }
-      WBTraj_T& nt = *pdata->wb_trajs[w++];
+      WBTraj_T& nt = *pdata->wb_trajs[w];
+      WBPhase_T& nphase = *pdata->wb_phases[w];
+      ++w;
       const int e = s + p.horizon;
       const Old* src = nullptr;
       for (const Old& o : old) {
@@ -229,6 +232,12 @@ class MHPCProblem {
         if (same && o.s <= e && o.e >= s) { src = &o; break; }
       }
       const bool continues_last = src && src == &old.back();
+      if (src && src->phase->cafe_al_set && src->n_td > 0 && src->n_td == p.n_td) {
+        // the phase keeps its touchdown-constraint object, hence sigma / lambda (reset_params is empty, ConstraintsBase.h:367-374)
+        bool feet = true;
+        for (int f = 0; f < p.n_td; ++f) feet = feet && src->td_foot[f] == p.td_foot[f];
+        if (feet) { for (int q = 0; q < 8; ++q) nphase.cafe_al[q] = src->phase->cafe_al[q]; nphase.cafe_al_set = true; }
+      }
       for (int k = 0; k <= p.horizon; ++k) {
         const int a = s + k;
         if (src && src->s <= a && a <= src->e) nt.Xbar[k] = src->traj->Xbar[a - src->s];

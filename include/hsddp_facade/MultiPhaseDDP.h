@@ -74,6 +74,18 @@ class MultiPhaseDDP {
     if (off != rec) throw std::logic_error("solve: phase records do not add up to the deck's solution size");
     for (int b = 0; b < B_; ++b) std::copy(one.begin(), one.end(), guess.begin() + (size_t)b * rec);
     check(cafe_gpu_set_initial_guess(h_, guess.data(), B_));
+    {
+      // augmented-Lagrangian parameters: what the phases carry from the previous MPC step, else the deck's TD_AL values
+      const CafeDeck* d = deck_->deck();
+      std::vector<double> al((size_t)B_ * n_phases * 8, 0.0);
+      for (int i = 0; i < n_phases; ++i)
+        for (int e = 0; e < d->phase[i].n_td && e < 4; ++e) {
+          const double sg = phases[i]->cafe_al_set ? phases[i]->cafe_al[2 * e] : d->phase[i].al_td.sigma;
+          const double lm = phases[i]->cafe_al_set ? phases[i]->cafe_al[2 * e + 1] : d->phase[i].al_td.lambda;
+          for (int b = 0; b < B_; ++b) { al[((size_t)b * n_phases + i) * 8 + 2 * e] = sg; al[((size_t)b * n_phases + i) * 8 + 2 * e + 1] = lm; }
+        }
+      check(cafe_gpu_set_al_params(h_, al.data(), B_));
+    }
     const CafeOptions o = cafe_options_from_hsddp(option);
     check(cafe_gpu_solve_batch(h_, x0_batch.data(), B_, &o));
     info_.resize(B_);
@@ -81,6 +93,11 @@ class MultiPhaseDDP {
     check(cafe_gpu_get_solution(h_, 0, 1, one.data()));
     off = 0;
     for (auto& ph : phases) { ph->cafe_unpack_solution(one.data() + off); off += ph->cafe_record_size(); }
+    {
+      std::vector<double> al((size_t)B_ * n_phases * 8);
+      check(cafe_gpu_get_al_params(h_, al.data()));
+      for (int i = 0; i < n_phases; ++i) { for (int e = 0; e < 8; ++e) phases[i]->cafe_al[e] = al[(size_t)i * 8 + e]; phases[i]->cafe_al_set = true; }   // problem 0, like the trajectories
+    }
     hist_.assign((size_t)B_ * HIST_CAP * 4, 0.0);
     check(cafe_gpu_get_history(h_, hist_.data(), HIST_CAP));
     double ms = 0; check(cafe_gpu_get_solve_ms(h_, &ms)); solve_time_ = (float)ms;

@@ -43,4 +43,9 @@ class SinglePhaseBase {
   virtual long cafe_record_size() const = 0;                    // doubles this phase takes in the packed solution record
   virtual void cafe_pack_guess(double* rec) const = 0;          // Xbar, Ubar, K -> record (the other arrays zero)
   virtual void cafe_unpack_solution(const double* rec) = 0;     // record -> Xbar, X, Ubar, U, Y, dU, K, Qu, Quu, Qux, G
+  // (sigma, lambda) of the up to four elements of this phase's touchdown constraint as the last solve left them: in the reference this state
+  // lives in the phase's TouchDownConstraint object and survives every MPC update (reset_params is empty, ConstraintsBase.h:367-374);
+  // <Problem>::update() hands it to the phase that continues this one, MultiPhaseDDP::solve starts from it (cafe_gpu_set_al_params)
+  double cafe_al[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  bool cafe_al_set = false;
 };

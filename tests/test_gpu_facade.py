@@ -58,7 +58,7 @@ def test_facade_mhpc_sequence_equals_the_c_abi_path(cm):
     x0 = np.zeros((1, 36)); x0[0, 2] = 0.2486; x0[0, 6:18] = np.tile([0, -0.8, 1.6], 4)
     prob = cm.MHPCProblem(CSV, k0=k0)
     s = cm.MultiPhaseDDP(prob, 0, 1); s.set_initial_condition(x0); s.solve(opt)
-    sol = s.get_solution()
+    sol = s.get_solution(); al = s.get_al_params()
     n_wb = sum(1 for p in prob.phases() if p.model == 1)
     _compare(lines[0], s.get_solver_info()[0], cm.unpack_solution(prob.deck, sol[0]), n_wb)
     reg_total = s.get_solver_info()[0]["reg_iter_total"]
@@ -69,8 +69,9 @@ def test_facade_mhpc_sequence_equals_the_c_abi_path(cm):
         p1 = cm.MHPCProblem(CSV, k0=k1, mpc_update_nsteps=2)
         guess = mpc.shifted_guess_batch(prob, k0, p1, k1, sol)
         x1 = mpc.state_at(prob, cm.unpack_solution(prob.deck, sol[0]), 2)[None]
-        s1 = cm.MultiPhaseDDP(p1, 0, 1); s1.set_initial_condition(x1); s1.set_initial_guess(guess); s1.solve(ort)
-        sol = s1.get_solution()
+        s1 = cm.MultiPhaseDDP(p1, 0, 1); s1.set_initial_condition(x1); s1.set_initial_guess(guess)
+        s1.set_al_params(mpc.shift_al(prob, k0, p1, k1, al)); s1.solve(ort)     # the phases carry sigma / lambda over the update, like the reference's
+        sol = s1.get_solution(); al = s1.get_al_params()
         n_wb = sum(1 for p in p1.phases() if p.model == 1)
         _compare(lines[1 + step], s1.get_solver_info()[0], cm.unpack_solution(p1.deck, sol[0]), n_wb)
         reg_total += s1.get_solver_info()[0]["reg_iter_total"]       # the reference never resets reg_iter_total_ (MultiPhaseDDP.h:113)
@@ -89,7 +90,7 @@ def test_facade_hkd_sequence_equals_the_c_abi_path(cm):
     prob = cm.HKDProblem(CSV, k0=k0)
     x0 = prob.reference_records()[0, :24][None].copy(); x0[0, 5] += 0.01; x0[0, 9] += 0.05
     s = cm.MultiPhaseDDP(prob, 0, 1); s.set_initial_condition(x0); s.solve(opt)
-    sol = s.get_solution()
+    sol = s.get_solution(); al = s.get_al_params()
     _compare(lines[0], s.get_solver_info()[0], cm.unpack_solution(prob.deck, sol[0]), len(prob.phases()))
     ort = copy.copy(opt); ort.max_AL_iter = opt.max_AL_iter_runtime; ort.max_DDP_iter = opt.max_DDP_iter_runtime
     for step in range(n_upd):
@@ -97,7 +98,8 @@ def test_facade_hkd_sequence_equals_the_c_abi_path(cm):
         p1 = cm.HKDProblem(CSV, k0=k1, mpc_update=True)
         guess = mpc.shifted_guess_batch(prob, k0, p1, k1, sol)
         x1 = mpc.state_at(prob, cm.unpack_solution(prob.deck, sol[0]), 2)[None]
-        s1 = cm.MultiPhaseDDP(p1, 0, 1); s1.set_initial_condition(x1); s1.set_initial_guess(guess); s1.solve(ort)
-        sol = s1.get_solution()
+        s1 = cm.MultiPhaseDDP(p1, 0, 1); s1.set_initial_condition(x1); s1.set_initial_guess(guess)
+        s1.set_al_params(mpc.shift_al(prob, k0, p1, k1, al)); s1.solve(ort)
+        sol = s1.get_solution(); al = s1.get_al_params()
         _compare(lines[1 + step], s1.get_solver_info()[0], cm.unpack_solution(p1.deck, sol[0]), len(p1.phases()))
         prob, k0 = p1, k1

@@ -300,21 +300,25 @@ def test_receding_horizon_warm_start_matches_oracle(cm, opt):
     x0 = workload.mhpc_batch(B)
     s = solve_gpu(cm, prob, opt, x0)
     sol = s.get_solution()
+    al = s.get_al_params()
     for step in range(3):
         k1 = k0 + 2
         p1 = cm.MHPCProblem(CSV, k0=k1, mpc_update_nsteps=2)
         assert p1.single_shooting_phase == (1 if k1 == 12 else -1)
         guess = mpc.shifted_guess_batch(prob, k0, p1, k1, sol)
+        al1 = mpc.shift_al(prob, k0, p1, k1, al)      # the reference never resets sigma / lambda between MPC steps (ConstraintsBase.h:367-374)
         # the "measured" state of the next step: the plan's own prediction two knots ahead, nudged
         x1 = np.stack([mpc.state_at(prob, cm.unpack_solution(prob.deck, sol[b]), 2) for b in range(B)]) + 1e-3 * (x0 - x0[0])
         s1 = cm.MultiPhaseDDP(p1, 0, B)
         s1.set_initial_condition(x1)
         s1.set_initial_guess(guess)
+        s1.set_al_params(al1)
         s1.solve(ort)
-        info = s1.get_solver_info(); hist = s1.get_history(256); sol1 = s1.get_solution()
+        info = s1.get_solver_info(); hist = s1.get_history(256); sol1 = s1.get_solution(); al = s1.get_al_params()
         for b in range(B):
-            oi, oh, ot, osol = oracle_solve(p1.deck, ort, x1[b], guess=guess[b])
+            oi, oh, ot, osol, oal = oracle_solve(p1.deck, ort, x1[b], guess=guess[b], al=al1[b])
             assert [info[b][k] for k in COUNTS] == [oi[k] for k in COUNTS], (step, b)
+            np.testing.assert_allclose(al[b], oal, rtol=RTOL, atol=1e-12)
             np.testing.assert_allclose(hist[b, :oi["n_hist"], 0], oh[:, 0], rtol=RTOL)
             gp, op = cm.unpack_solution(p1.deck, sol1[b]), cm.unpack_solution(p1.deck, osol)
             for pg, po in zip(gp, op):
@@ -327,7 +331,7 @@ def test_receding_horizon_warm_start_matches_oracle(cm, opt):
                 assert not np.any(s1.debug_get("Defect", 1, b))
             p1ms = cm.MHPCProblem(CSV, k0=k1)
             s2 = cm.MultiPhaseDDP(p1ms, 0, B)
-            s2.set_initial_condition(x1); s2.set_initial_guess(guess); s2.solve(ort)
+            s2.set_initial_condition(x1); s2.set_initial_guess(guess); s2.set_al_params(al1); s2.solve(ort)
             assert all(a["cost"] != c["cost"] for a, c in zip(info, s2.get_solver_info()))
             s2.close()
         # the warm start pays: same caps from the cold start end far from feasible
@@ -362,6 +366,7 @@ def test_device_shift_equals_host_shift(cm, opt):
         sh = cm.MultiPhaseDDP(p1, 0, B)
         sh.set_initial_condition(x1)
         sh.set_initial_guess(mpc.shifted_guess_batch(prob, k0, p1, k1, sol))
+        sh.set_al_params(mpc.shift_al(prob, k0, p1, k1, s.get_al_params()))
         sh.solve(ort)
         # device path
         sd = cm.MultiPhaseDDP(p1, 0, B)

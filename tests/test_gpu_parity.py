@@ -199,6 +199,7 @@ def test_hkd_receding_horizon_chain_matches_oracle(cm, hkd_options):
     x0 = workload.hkd_batch(prob, B)
     s = solve_gpu(cm, prob, hkd_options, x0)
     sol = s.get_solution()
+    al = s.get_al_params()
     seen_ss = seen_removal = False
     for step in range(6):
         k1 = k0 + 2
@@ -206,17 +207,20 @@ def test_hkd_receding_horizon_chain_matches_oracle(cm, hkd_options):
         seen_ss = seen_ss or p1.single_shooting_phase >= 0
         seen_removal = seen_removal or len(p1.phases()) < len(prob.phases())
         guess = mpc.shifted_guess_batch(prob, k0, p1, k1, sol)
+        al1 = mpc.shift_al(prob, k0, p1, k1, al)      # the reference never resets sigma / lambda between MPC steps (ConstraintsBase.h:367-374)
         assert not mpc.unpack_batch(p1, guess)[0]["Ubar"][:, 0].any()
         x1 = np.stack([mpc.state_at(prob, cm.unpack_solution(prob.deck, sol[b]), 2) for b in range(B)])
         x1[:, 3:6] += 1e-3 * (x0[:, 3:6] - x0[0, 3:6])   # the "measured" state: the plan's own prediction, position nudged
         s1 = cm.MultiPhaseDDP(p1, 0, B)
         s1.set_initial_condition(x1)
         s1.set_initial_guess(guess)
+        s1.set_al_params(al1)
         s1.solve(ort)
-        info = s1.get_solver_info(); hist = s1.get_history(64); sol1 = s1.get_solution()
+        info = s1.get_solver_info(); hist = s1.get_history(64); sol1 = s1.get_solution(); al = s1.get_al_params()
         for b in range(B):
-            oi, oh, ot, osol = oracle_solve(p1.deck, ort, x1[b], guess=guess[b])
+            oi, oh, ot, osol, oal = oracle_solve(p1.deck, ort, x1[b], guess=guess[b], al=al1[b])
             assert [info[b][k] for k in COUNTS] == [oi[k] for k in COUNTS], (step, b)
+            np.testing.assert_allclose(al[b], oal, rtol=RTOL, atol=1e-12)
             np.testing.assert_allclose(hist[b, :oi["n_hist"], 0], oh[:, 0], rtol=RTOL, atol=1e-9)
             gp, op = cm.unpack_solution(p1.deck, sol1[b]), cm.unpack_solution(p1.deck, osol)
             for pg, po in zip(gp, op):
@@ -256,6 +260,7 @@ def test_hkd_device_shift_equals_host_shift(cm, hkd_options):
         sh = cm.MultiPhaseDDP(p1, 0, B)
         sh.set_initial_condition(x1)
         sh.set_initial_guess(mpc.shifted_guess_batch(prob, k0, p1, k1, sol))
+        sh.set_al_params(mpc.shift_al(prob, k0, p1, k1, s.get_al_params()))
         sh.solve(ort)
         sd = cm.MultiPhaseDDP(p1, 0, B)
         sd.set_initial_condition(x1)

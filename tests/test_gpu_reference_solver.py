@@ -1,0 +1,94 @@
+"""The CUDA path against the REFERENCE's own solver (GPU suite): tests/golden/ref_hkd_trot.npz is the record of the reference's
+MultiPhaseDDP<T>::solve / HKDProblem<T>::initialization / update, compiled unchanged from its sources (oracle/refbuild, tools/make_ref_golden.py;
+see tests/test_cpu_reference_solver.py for what the fixture holds and why 1e-9 rather than the last bit). Decisions bit-exact, per-iteration
+cost, gains and trajectories at 1e-9 relative (BASELINE.json north_star) - no oracle in between."""
+import copy
+import os
+
+import numpy as np
+import pytest
+
+from test_cpu_reference_solver import CSV, RTOL, check_deck_layout, check_solve, ref, relerr  # noqa: F401  (ref is a fixture)
+
+pytestmark = pytest.mark.gpu
+
+
+def test_gpu_reproduces_the_reference_solver_on_the_initial_solves(cm, hkd_options, ref):
+    """BASELINE config 1 against the reference itself: the HKD trot solve of HKDMPCSolver::initialize (problem 0) and three perturbed starts,
+    one batch; every decision of every DDP iteration (30 - 38 iterations, up to 73 line-search trials), the per-iteration record and the
+    solution; the nominal problem's gains, Quu, Qux, G, Qu in full."""
+    prob = cm.HKDProblem(CSV)
+    B = len(ref["body"])
+    x0 = np.stack([ref["p%d_s0_x0" % b] for b in range(B)])
+    s = cm.MultiPhaseDDP(prob, 0, B)
+    s.set_initial_condition(x0)
+    s.solve(hkd_options)
+    info, trace, sol = s.get_solver_info(), s.get_trace(256), s.get_solution()
+    for b in range(B):
+        pre = "p%d_s0_" % b
+        check_deck_layout(prob, ref, pre)
+        check_solve(cm, prob, ref, pre, info[b], trace[b, :info[b]["iter"]], sol[b], full=(b == 0))
+
+
+def test_gpu_update_deck_chain_reproduces_the_reference_update_chain(cm, hkd_options, ref):
+    """SURVEY §8(f)1 against the reference itself: HKDProblem<T>::update x 6 + the re-solves of HKDMPCSolver<T>::update (caps 2 x 1) on ONE
+    solver through cafe_gpu_update_deck - re-cut deck, on-device shift of the previous solution (Ubar[0] = 0), on-device carry-over of the
+    touchdown constraints' sigma / lambda (the reference never resets them) - all four problems in one batch. x0 of every step = the plan's
+    own prediction two knots ahead (cafe_gpu_get_planned_state) + the recorded nudge, which must equal the state the reference started from."""
+    ort = copy.copy(hkd_options)
+    ort.max_AL_iter = 2; ort.max_DDP_iter = 1
+    B = len(ref["body"])
+    n_upd = ref["nudge"].shape[1]
+    prob = cm.HKDProblem(CSV)
+    s = cm.MultiPhaseDDP(prob, 0, B)
+    s.set_initial_condition(np.stack([ref["p%d_s0_x0" % b] for b in range(B)]))
+    s.solve(hkd_options)
+    for step in range(1, n_upd + 1):
+        p1 = cm.HKDProblem(CSV, k0=2 * step, mpc_update=True)
+        x1 = s.planned_state(2)
+        x1[:, 3:6] += ref["nudge"][:, step - 1]
+        for b in range(B):
+            np.testing.assert_allclose(x1[b], ref["p%d_s%d_x0" % (b, step)], rtol=RTOL, atol=1e-12)
+        s.update_deck(p1, 2)
+        s.set_initial_condition(x1)
+        s.solve(ort)
+        info, trace, sol = s.get_solver_info(), s.get_trace(64), s.get_solution()
+        for b in range(B):
+            pre = "p%d_s%d_" % (b, step)
+            check_deck_layout(p1, ref, pre)
+            check_solve(cm, p1, ref, pre, info[b], trace[b, :info[b]["iter"]], sol[b])
+
+
+def test_gpu_fresh_solver_chain_with_carried_al_parameters(cm, hkd_options, ref):
+    """The same chain through the other entries: a fresh solver per MPC step, host-side shift (cafe_mpc_b200/mpc.py) handed over with
+    cafe_gpu_set_initial_guess, sigma / lambda read with cafe_gpu_get_al_params, shifted with mpc.shift_al and handed over with
+    cafe_gpu_set_al_params - and what happens without the carry-over: the re-solves part ways with the reference's."""
+    from cafe_mpc_b200 import mpc
+    ort = copy.copy(hkd_options)
+    ort.max_AL_iter = 2; ort.max_DDP_iter = 1
+    B = 2
+    prob, k0 = cm.HKDProblem(CSV), 0
+    s = cm.MultiPhaseDDP(prob, 0, B)
+    s.set_initial_condition(np.stack([ref["p%d_s0_x0" % b] for b in range(B)]))
+    s.solve(hkd_options)
+    assert np.any(s.get_al_params() != mpc.initial_al(prob, B))       # the initial solve did move sigma / lambda
+    differs = False
+    for step in range(1, 4):
+        k1 = k0 + 2
+        p1 = cm.HKDProblem(CSV, k0=k1, mpc_update=True)
+        sol = s.get_solution()
+        x1 = np.stack([ref["p%d_s%d_x0" % (b, step)] for b in range(B)])
+        s1 = cm.MultiPhaseDDP(p1, 0, B)
+        s1.set_initial_condition(x1)
+        s1.set_initial_guess(mpc.shifted_guess_batch(prob, k0, p1, k1, sol))
+        s1.solve(ort)                                                  # sigma / lambda back at the deck's values
+        reset_cost = [i["cost"] for i in s1.get_solver_info()]
+        s1.set_al_params(mpc.shift_al(prob, k0, p1, k1, s.get_al_params()))
+        s1.solve(ort)
+        info, trace, sol1 = s1.get_solver_info(), s1.get_trace(64), s1.get_solution()
+        for b in range(B):
+            check_solve(cm, p1, ref, "p%d_s%d_" % (b, step), info[b], trace[b, :info[b]["iter"]], sol1[b])
+            differs = differs or abs(reset_cost[b] - info[b]["cost"]) > 1e-6 * abs(info[b]["cost"])
+        s.close()
+        s, prob, k0 = s1, p1, k1
+    assert differs
