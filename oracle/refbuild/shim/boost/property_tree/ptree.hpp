@@ -20,6 +20,14 @@ class ptree {
  public:
   std::string value;
   std::vector<std::pair<std::string, ptree>> kids;
+  typedef std::vector<std::pair<std::string, ptree>>::iterator iterator;
+  typedef std::vector<std::pair<std::string, ptree>>::const_iterator const_iterator;
+  iterator begin() { return kids.begin(); }
+  iterator end() { return kids.end(); }
+  const_iterator begin() const { return kids.begin(); }
+  const_iterator end() const { return kids.end(); }
+  std::size_t size() const { return kids.size(); }
+  bool empty() const { return kids.empty(); }
 
   const ptree* find_path(const std::string& path) const {
     const ptree* n = this;
@@ -41,6 +49,7 @@ class ptree {
     if (!n) throw ptree_bad_path("No such node (" + path + ")");
     return *n;
   }
+  ptree& get_child(const std::string& path) { return const_cast<ptree&>(static_cast<const ptree*>(this)->get_child(path)); }
   template <class T> T get_value() const { return convert<T>(value); }
   template <class T> T get(const std::string& path) const { return get_child(path).template get_value<T>(); }
   template <class T> T get(const std::string& path, const T& dflt) const { const ptree* n = find_path(path); return n ? n->template get_value<T>() : dflt; }

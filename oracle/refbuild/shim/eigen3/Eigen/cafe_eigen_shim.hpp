@@ -19,6 +19,7 @@
 #include <cassert>
 #include <cmath>
 #include <cstddef>
+#include <initializer_list>
 #include <iomanip>
 #include <iostream>
 #include <limits>
@@ -39,6 +40,7 @@ namespace Eigen {
 typedef std::ptrdiff_t Index;
 constexpr int Dynamic = -1;
 enum { ColMajor = 0, RowMajor = 1, AutoAlign = 0, DontAlign = 2, DontAlignCols = 1 };
+enum { Lower = 1, Upper = 2 };
 
 template <class T> using aligned_allocator = std::allocator<T>;
 
@@ -49,6 +51,27 @@ template <class S, int R, int C, int O, int MR, int MC> struct traits<Matrix<S, 
 template <class S, int R, int C> struct traits<Block<S, R, C>> { typedef S Scalar; enum { Rows = R, Cols = C }; };
 
 namespace internal {
+// contiguous storage with plain references for every scalar type (std::vector<bool> has none)
+template <class S> class Buf {
+  S* p = nullptr; std::size_t n = 0;
+ public:
+  Buf() {}
+  Buf(std::size_t n_, const S& val) { assign(n_, val); }
+  explicit Buf(std::size_t n_) { assign(n_, S()); }
+  Buf(std::initializer_list<S> l) { p = l.size() ? new S[l.size()] : nullptr; n = l.size(); std::size_t i = 0; for (const S& x : l) p[i++] = x; }
+  Buf(const Buf& o) { p = o.n ? new S[o.n] : nullptr; n = o.n; for (std::size_t i = 0; i < n; ++i) p[i] = o.p[i]; }
+  Buf(Buf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  Buf& operator=(const Buf& o) { if (this != &o) { Buf t(o); swap(t); } return *this; }
+  Buf& operator=(Buf&& o) noexcept { if (this != &o) { delete[] p; p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+  ~Buf() { delete[] p; }
+  void assign(std::size_t n_, const S& val) { delete[] p; p = n_ ? new S[n_] : nullptr; n = n_; for (std::size_t i = 0; i < n; ++i) p[i] = val; }
+  void swap(Buf& o) { std::swap(p, o.p); std::swap(n, o.n); }
+  S* data() { return p; }
+  const S* data() const { return p; }
+  S& operator[](std::size_t i) { return p[i]; }
+  const S& operator[](std::size_t i) const { return p[i]; }
+  std::size_t size() const { return n; }
+};
 template <class S> inline S fresh_value() {
 #ifdef EIGEN_INITIALIZE_MATRICES_BY_NAN
   if (std::numeric_limits<S>::has_quiet_NaN) return std::numeric_limits<S>::quiet_NaN();
@@ -89,6 +112,16 @@ template <class S> struct WithFormat {
 template <class S> struct DiagonalWrapper { std::vector<S> d; };
 
 template <class D> class CommaInit;
+// the upper / lower triangle (diagonal included) of a matrix as an assignable set of coefficients
+template <class B, int Mode> struct TriangularView {
+  B m;   // a Block onto the matrix
+  explicit TriangularView(const B& b) : m(b) {}
+  template <class O> TriangularView& operator=(const TriangularView<O, Mode>& o) {
+    for (Index j = 0; j < m.cols(); ++j) for (Index i = 0; i < m.rows(); ++i) if (Mode == Upper ? i <= j : i >= j) m.coeffRef(i, j) = o.m.coeff(i, j);
+    return *this;
+  }
+  TriangularView& operator=(const TriangularView& o) { return this->template operator=<B>(o); }
+};
 // a 1 x 1 matrix converts to its coefficient (inner products); a plain (non-template) conversion so that the built-in
 // operators (double += x^T Q x) see it
 template <class D, class S, bool On> struct ScalarConv {};
@@ -103,7 +136,7 @@ class DenseBase {
   enum { RowsAtCompileTime = traits<D>::Rows, ColsAtCompileTime = traits<D>::Cols,
          SizeAtCompileTime = internal::prod_dim(traits<D>::Rows, traits<D>::Cols), IsVectorAtCompileTime = (traits<D>::Rows == 1 || traits<D>::Cols == 1) };
   typedef Matrix<Scalar, traits<D>::Rows, traits<D>::Cols> PlainObject;
-  typedef Matrix<Scalar, traits<D>::Cols, traits<D>::Rows> TransposeReturnType;
+  typedef Block<Scalar, traits<D>::Cols, traits<D>::Rows> TransposeReturnType;   // a strided view: A.transpose() is assignable like Eigen's
 
   D& derived() { return *static_cast<D*>(this); }
   const D& derived() const { return *static_cast<const D*>(this); }
@@ -155,6 +188,10 @@ class DenseBase {
   template <int N> Block<Scalar, traits<D>::Rows, N> leftCols() const { return mk<traits<D>::Rows, N>(0, 0, rows(), N); }
   template <int N> Block<Scalar, traits<D>::Rows, N> rightCols() const { return mk<traits<D>::Rows, N>(0, cols() - N, rows(), N); }
   template <int N> Block<Scalar, traits<D>::Rows, N> middleCols(Index j) const { return mk<traits<D>::Rows, N>(0, j, rows(), N); }
+  template <int BR, int BC> Block<Scalar, BR, BC> topLeftCorner() const { return mk<BR, BC>(0, 0, BR, BC); }
+  template <int BR, int BC> Block<Scalar, BR, BC> topRightCorner() const { return mk<BR, BC>(0, cols() - BC, BR, BC); }
+  template <int BR, int BC> Block<Scalar, BR, BC> bottomLeftCorner() const { return mk<BR, BC>(rows() - BR, 0, BR, BC); }
+  template <int BR, int BC> Block<Scalar, BR, BC> bottomRightCorner() const { return mk<BR, BC>(rows() - BR, cols() - BC, BR, BC); }
   Block<Scalar, Dynamic, Dynamic> topLeftCorner(Index r, Index c) const { return block(0, 0, r, c); }
   Block<Scalar, Dynamic, Dynamic> topRightCorner(Index r, Index c) const { return block(0, cols() - c, r, c); }
   Block<Scalar, Dynamic, Dynamic> bottomLeftCorner(Index r, Index c) const { return block(rows() - r, 0, r, c); }
@@ -171,9 +208,10 @@ class DenseBase {
   auto tail(Index n) const { return seg_<Dynamic>(size() - n, n); }
   template <int N> auto tail(Index n = N) const { return seg_<N>(size() - n, n); }
   // diagonal as a strided column view (writable: Q.diagonal() << ...)
-  Block<Scalar, Dynamic, 1> diagonal() const {
+  Block<Scalar, Dynamic, 1> diagonal(Index k = 0) const {   // k > 0: super-diagonal, k < 0: sub-diagonal
     D& d = const_cast<D&>(derived());
-    return Block<Scalar, Dynamic, 1>(d.ptr_(0, 0), std::min(rows(), cols()), 1, d.rs_() + d.cs_(), 0);
+    const Index i0 = k < 0 ? -k : 0, j0 = k > 0 ? k : 0;
+    return Block<Scalar, Dynamic, 1>(d.ptr_(i0, j0), std::min(rows() - i0, cols() - j0), 1, d.rs_() + d.cs_(), 0);
   }
 
   // ---- reductions
@@ -228,9 +266,11 @@ class DenseBase {
   template <class O> auto cwiseMin(const DenseBase<O>& o) const { return binary_(o, [](const Scalar& a, const Scalar& b) { return a < b ? a : b; }); }
 
   TransposeReturnType transpose() const {
-    TransposeReturnType r(cols(), rows());
-    for (Index j = 0; j < cols(); ++j) for (Index i = 0; i < rows(); ++i) r(j, i) = coeff(i, j);
-    return r;
+    D& d = const_cast<D&>(derived());
+    return TransposeReturnType(d.ptr_(0, 0), cols(), rows(), d.cs_(), d.rs_());
+  }
+  template <int Mode> TriangularView<Block<Scalar, traits<D>::Rows, traits<D>::Cols>, Mode> triangularView() const {
+    return TriangularView<Block<Scalar, traits<D>::Rows, traits<D>::Cols>, Mode>(mk<traits<D>::Rows, traits<D>::Cols>(0, 0, rows(), cols()));
   }
   template <int RF, int CF> auto replicate() const {
     Matrix<Scalar, internal::prod_dim(traits<D>::Rows, RF), internal::prod_dim(traits<D>::Cols, CF)> r(rows() * RF, cols() * CF);
@@ -317,7 +357,7 @@ class CommaInit {
 // ------------------------------------------------------------------------------------------------------------------
 template <class S, int R, int C, int Opt, int MR, int MC>
 class Matrix : public DenseBase<Matrix<S, R, C, Opt, MR, MC>>, public ScalarConv<Matrix<S, R, C, Opt, MR, MC>, S, R == 1 && C == 1> {
-  std::vector<S> v;
+  internal::Buf<S> v;
   Index r_, c_;
   typedef DenseBase<Matrix> Base;
  public:
@@ -370,7 +410,7 @@ class Matrix : public DenseBase<Matrix<S, R, C, Opt, MR, MC>>, public ScalarConv
     if (flip) std::swap(r, c);
     assert((R == Dynamic || R == r) && (C == Dynamic || C == c));
     if ((const void*)this == (const void*)&o && !flip) return;
-    std::vector<S> t((size_t)(r * c));
+    internal::Buf<S> t((size_t)(r * c));
     for (Index j = 0; j < c; ++j) for (Index i = 0; i < r; ++i) t[i + r * j] = (S)(flip ? o.coeff(j, i) : o.coeff(i, j));
     v.swap(t); r_ = r; c_ = c;
   }
@@ -380,7 +420,7 @@ class Matrix : public DenseBase<Matrix<S, R, C, Opt, MR, MC>>, public ScalarConv
   void resize(Index r, Index c) { assert((R == Dynamic || R == r) && (C == Dynamic || C == c)); if (r != r_ || c != c_) { r_ = r; c_ = c; v.assign(r * c, internal::fresh_value<S>()); } }
   void resize(Index n) { if (C == 1 || (R == Dynamic && C == Dynamic)) resize(n, 1); else resize(1, n); }
   void conservativeResize(Index r, Index c) {
-    std::vector<S> t((size_t)(r * c), internal::fresh_value<S>());
+    internal::Buf<S> t((size_t)(r * c), internal::fresh_value<S>());
     for (Index j = 0; j < std::min(c, c_); ++j) for (Index i = 0; i < std::min(r, r_); ++i) t[i + r * j] = v[i + r_ * j];
     v.swap(t); r_ = r; c_ = c;
   }

@@ -33,6 +33,21 @@ def ref():
     return np.load(os.path.join(REPO, "tests/golden/ref_hkd_trot.npz"))
 
 
+@pytest.fixture(scope="module")
+def ref_mhpc():
+    """The same record for the headline workload: the reference's MHPCProblem / WBM / MHPCCost / MHPCConstraint / MHPCReset / MHPCReference /
+    SRBM code and solver on the MHPC trot (oracle/_ref/ref_mhpc). Pinocchio is not in this image: behind its names stand the oracle's own
+    rigid-body recursions (oracle/refbuild/shim/pinocchio), so this file pins every layer of the whole-body problem EXCEPT the rigid-body
+    algorithms themselves (mass matrix, bias forces, RNEA derivatives, foot kinematics), which are pinned by the reference's known answers
+    (tests/test_cpu_mhpc.py::test_wb_contact_dynamics_known_answers) and its CasADi kinematic partials."""
+    return np.load(os.path.join(REPO, "tests/golden/ref_mhpc_trot.npz"))
+
+
+@pytest.fixture(scope="module")
+def mhpc_options(cm):
+    return cm.load_hsddp_setting(os.path.join(REPO, "data/MHPC/settings/ddp_setting.info"))
+
+
 def check_deck_layout(prob, ref, pre):
     ph = prob.phases()
     assert [p.horizon for p in ph] == list(ref[pre + "horizons"])
@@ -53,9 +68,9 @@ def check_solve(cm, prob, ref, pre, info, trace, sol, full=False, rtol=RTOL):
     np.testing.assert_allclose(trace[:, 4:6], rt[:, 4:6], rtol=1e-8, atol=1e-12, err_msg=pre)            # merit parameter (a ratio of the above), regularisation
     assert abs(info["cost"] - ref[pre + "final"][0]) <= rtol * abs(ref[pre + "final"][0])
     assert abs(info["feas"] - ref[pre + "final"][1]) <= rtol * abs(ref[pre + "final"][1]) + 1e-13
-    kv = ref["kv"]
     for i, p in enumerate(cm.unpack_solution(prob.deck, sol)):
         q = pre + "ph%d_" % i
+        kv = ref["kv"][:p["Xbar"].shape[1]]
         for name in ("Xbar", "Ubar", "dU"):
             assert relerr(p[name], ref[q + name]) < rtol, (pre, i, name)
         assert relerr(p["K"] @ kv, ref[q + "Kv"]) < rtol, (pre, i, "K v")
@@ -123,3 +138,53 @@ def test_oracle_and_mpc_shift_reproduce_the_reference_update_chain(cm, hkd_optio
             check_solve(cm, p1, ref, pre, info, trace, sol)
             prob, k0 = p1, k1
         assert len(layouts) >= 3      # the chain went through a tail-phase opening and a front-phase removal
+
+
+def test_oracle_reproduces_the_reference_mhpc_problem_on_the_initial_solves(cm, mhpc_options, ref_mhpc):
+    """BASELINE config 2 / the headline workload against the reference's own whole-body + SRB problem code and solver: MHPCProblem<T>::
+    initialization + MultiPhaseDDP<T>::solve (MHPCLocomotion.cpp:20-66) on the nominal and two perturbed trot starts."""
+    ref = ref_mhpc
+    prob = cm.MHPCProblem(CSV)
+    for b in range(len(ref["x0"])):
+        pre = "p%d_s0_" % b
+        check_deck_layout(prob, ref, pre)
+        np.testing.assert_array_equal(ref["x0"][b], ref[pre + "x0"])
+        info, hist, trace, sol = oracle_solve(prob.deck, mhpc_options, ref["x0"][b])
+        check_solve(cm, prob, ref, pre, info, trace, sol, full=(b == 0))
+
+
+def test_oracle_and_mpc_shift_reproduce_the_reference_mhpc_update_chain(cm, mhpc_options, ref_mhpc):
+    """MHPCProblem<T>::update x 8 (MHPCProblem.cpp:252-397: the front phase shrinks 11 -> 1 and disappears, a one-knot tail phase opens and
+    grows, the SRB plan keeps its data) with the re-solves of MHPCLocomotion<T>::update under the run-time caps: re-cut decks, shifted warm
+    start, carried sigma / lambda and the re-solves equal the reference's at every step."""
+    from cafe_mpc_b200 import mpc
+    ref = ref_mhpc
+    ort = copy.copy(mhpc_options)
+    ort.max_AL_iter = mhpc_options.max_AL_iter_runtime; ort.max_DDP_iter = mhpc_options.max_DDP_iter_runtime
+    n_upd = ref["nudge"].shape[1]
+    for b in (0, 2):
+        prob, k0 = cm.MHPCProblem(CSV), 0
+        info, hist, trace, sol, al = oracle_solve(prob.deck, mhpc_options, ref["x0"][b], al=mpc.initial_al(prob))
+        layouts = set()
+        for s in range(1, n_upd + 1):
+            pre = "p%d_s%d_" % (b, s)
+            k1 = k0 + 2
+            p1 = cm.MHPCProblem(CSV, k0=k1, mpc_update_nsteps=2)
+            check_deck_layout(p1, ref, pre)
+            layouts.add(tuple(ref[pre + "horizons"]))
+            guess = mpc.shifted_guess_batch(prob, k0, p1, k1, sol[None, :])[0]
+            for i, g in enumerate(cm.unpack_solution(p1.deck, guess)):
+                q = pre + "ph%d_" % i
+                if p1.phases()[i].single_shooting:
+                    assert not ref[q + "gUbar"].any() and not g["Ubar"].any() and not g["K"].any()     # a fresh phase: nothing of it is read
+                    continue
+                kv = ref["kv"][:g["Xbar"].shape[1]]
+                assert relerr(g["Xbar"], ref[q + "gXbar"]) < RTOL and relerr(g["Ubar"], ref[q + "gUbar"]) < RTOL, (pre, i)
+                assert relerr(g["K"] @ kv, ref[q + "gKv"]) < RTOL, (pre, i)
+            x1 = mpc.state_at(prob, cm.unpack_solution(prob.deck, sol), 2) + ref["nudge"][b, s - 1]
+            np.testing.assert_allclose(x1, ref[pre + "x0"], rtol=RTOL, atol=1e-12)
+            al = mpc.shift_al(prob, k0, p1, k1, al)
+            info, hist, trace, sol, al = oracle_solve(p1.deck, ort, x1, guess=guess, al=al)
+            check_solve(cm, p1, ref, pre, info, trace, sol)
+            prob, k0 = p1, k1
+        assert (1, 24, 10) in layouts and (24, 1, 10) in layouts

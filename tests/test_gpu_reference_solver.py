@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from test_cpu_reference_solver import CSV, RTOL, check_deck_layout, check_solve, ref, relerr  # noqa: F401  (ref is a fixture)
+from test_cpu_reference_solver import CSV, RTOL, check_deck_layout, check_solve, mhpc_options, ref, ref_mhpc, relerr  # noqa: F401  (fixtures)
 
 pytestmark = pytest.mark.gpu
 
@@ -92,3 +92,50 @@ def test_gpu_fresh_solver_chain_with_carried_al_parameters(cm, hkd_options, ref)
         s.close()
         s, prob, k0 = s1, p1, k1
     assert differs
+
+
+def test_gpu_reproduces_the_reference_mhpc_problem_on_the_initial_solves(cm, mhpc_options, ref_mhpc):
+    """The headline workload (MHPC trot: whole-body 11 + 14 knots, SRB 10 knots) against the reference's own problem code and solver
+    (tests/golden/ref_mhpc_trot.npz; what stands behind Pinocchio's names in that build: see the fixture in test_cpu_reference_solver.py)."""
+    ref = ref_mhpc
+    prob = cm.MHPCProblem(CSV)
+    B = len(ref["x0"])
+    s = cm.MultiPhaseDDP(prob, 0, B)
+    s.set_initial_condition(ref["x0"])
+    s.solve(mhpc_options)
+    info, trace, sol = s.get_solver_info(), s.get_trace(64), s.get_solution()
+    for b in range(B):
+        pre = "p%d_s0_" % b
+        check_deck_layout(prob, ref, pre)
+        check_solve(cm, prob, ref, pre, info[b], trace[b, :info[b]["iter"]], sol[b], full=(b == 0))
+
+
+def test_gpu_update_deck_chain_reproduces_the_reference_mhpc_update_chain(cm, mhpc_options, ref_mhpc):
+    """MHPCProblem<T>::update x 8 + the re-solves of MHPCLocomotion<T>::update (run-time caps) on ONE solver through cafe_gpu_update_deck: the
+    front phase shrinks from 11 knots to 1 and disappears, a one-knot whole-body phase opens at the tail and grows, touchdown constraints
+    appear and keep their sigma / lambda, the SRB plan keeps its data. Three problems in one batch, every step against the reference's record."""
+    ref = ref_mhpc
+    ort = copy.copy(mhpc_options)
+    ort.max_AL_iter = mhpc_options.max_AL_iter_runtime; ort.max_DDP_iter = mhpc_options.max_DDP_iter_runtime
+    B = len(ref["x0"])
+    n_upd = ref["nudge"].shape[1]
+    prob = cm.MHPCProblem(CSV)
+    s = cm.MultiPhaseDDP(prob, 0, B)
+    s.set_initial_condition(ref["x0"])
+    s.solve(mhpc_options)
+    seen_td = False
+    for step in range(1, n_upd + 1):
+        p1 = cm.MHPCProblem(CSV, k0=2 * step, mpc_update_nsteps=2)
+        seen_td = seen_td or any(p.n_td > 0 for p in p1.phases())
+        x1 = s.planned_state(2) + ref["nudge"][:, step - 1]
+        for b in range(B):
+            np.testing.assert_allclose(x1[b], ref["p%d_s%d_x0" % (b, step)], rtol=RTOL, atol=1e-12)
+        s.update_deck(p1, 2)
+        s.set_initial_condition(x1)
+        s.solve(ort)
+        info, trace, sol = s.get_solver_info(), s.get_trace(64), s.get_solution()
+        for b in range(B):
+            pre = "p%d_s%d_" % (b, step)
+            check_deck_layout(p1, ref, pre)
+            check_solve(cm, p1, ref, pre, info[b], trace[b, :info[b]["iter"]], sol[b])
+    assert seen_td

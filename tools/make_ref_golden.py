@@ -48,17 +48,18 @@ def parse(path):
         for i in range(int(head[2])):
             h = L[pos].split(); pos += 1
             assert h[0] == "phase" and int(h[1]) == i
-            ph = dict(horizon=int(h[3]), contact=[int(v) for v in h[5:9]], start=float(h[10]), end=float(h[12]))
+            ph = dict(horizon=int(h[3]), contact=[int(v) for v in h[5:9]], start=float(h[10]), end=float(h[12]), n=int(h[14]), m=int(h[16]))
             for name in ARRAYS:
                 t = L[pos].split(); pos += 1
                 assert t[0] == name, (t[0], name)
                 ph[name] = np.array(t[1:], dtype=np.float64)
-            hz = ph["horizon"]
-            ph["Xbar"] = ph["Xbar"].reshape(hz + 1, 24); ph["G"] = ph["G"].reshape(hz + 1, 24); ph["Defect"] = ph["Defect"].reshape(hz + 1, 24)
+            hz, n, m = ph["horizon"], ph["n"], ph["m"]
+            ph["Xbar"] = ph["Xbar"].reshape(hz + 1, n); ph["G"] = ph["G"].reshape(hz + 1, n); ph["Defect"] = ph["Defect"].reshape(hz + 1, n)
             for name in ("Ubar", "dU", "Qu"):
-                ph[name] = ph[name].reshape(hz, 24)
-            for name in ("K", "Quu", "Qux"):
-                ph[name] = ph[name].reshape(hz, 24, 24).transpose(0, 2, 1)   # written column-major
+                ph[name] = ph[name].reshape(hz, m)
+            ph["K"] = ph["K"].reshape(hz, n, m).transpose(0, 2, 1)      # written column-major: [knot][column][row] -> [knot][m][n]
+            ph["Qux"] = ph["Qux"].reshape(hz, n, m).transpose(0, 2, 1)
+            ph["Quu"] = ph["Quu"].reshape(hz, m, m).transpose(0, 2, 1)
             out.append(ph)
         return out
 
@@ -135,6 +136,66 @@ def trace_of(events, n_phases, opt):
     return np.array(rows).reshape(-1, 12)
 
 
+def store(out, probs, optd, kv_of):
+    for b, solves in enumerate(probs):
+        for s, rec in enumerate(solves):
+            pre = "p%d_s%d_" % (b, s)
+            sol = rec["solution"]
+            out[pre + "x0"] = rec["x0"]; out[pre + "counters"] = rec["counters"]; out[pre + "final"] = rec["final"]
+            out[pre + "trace"] = trace_of(rec["events"], len(sol), optd)
+            assert len(out[pre + "trace"]) == rec["counters"][0]
+            assert int(out[pre + "trace"][:, 7].sum()) == rec["counters"][1] and int(out[pre + "trace"][:, 6].sum()) == rec["counters"][2]
+            out[pre + "n_al"] = np.array(sum(1 for e in rec["events"] if e[0] == EV_AL and e[1] == 0))
+            out[pre + "horizons"] = np.array([p["horizon"] for p in sol]); out[pre + "contacts"] = np.array([p["contact"] for p in sol])
+            for i, p in enumerate(sol):
+                q = pre + "ph%d_" % i
+                kv = kv_of(p["n"])
+                out[q + "Xbar"], out[q + "Ubar"], out[q + "dU"] = p["Xbar"], p["Ubar"], p["dU"]
+                out[q + "Kv"] = p["K"] @ kv
+                if i == 0:
+                    out[q + "K4"] = p["K"][:4]
+                if b == 0 and s == 0:
+                    out[q + "K"], out[q + "Quu"], out[q + "Qux"], out[q + "G"], out[q + "Qu"] = p["K"], p["Quu"], p["Qux"], p["G"], p["Qu"]
+                if s > 0:
+                    g = rec["guess"][i]
+                    out[q + "gXbar"], out[q + "gUbar"], out[q + "gKv"] = g["Xbar"], g["Ubar"], g["K"] @ kv
+
+
+def main_mhpc():
+    """tests/golden/ref_mhpc_trot.npz: the reference's MHPCProblem (whole-body 11 + 14 knots, SRB 10 knots at the start of the trot reference)
+    through MHPCLocomotion's initial solve and N_UPD_MHPC MPC updates (run-time caps), oracle/_ref/ref_mhpc. Same keys as the HKD file; the
+    inputs are x0 [N, 36] and nudge [N, N_UPD_MHPC, 36]; kv is the 36-vector, SRB phases use its first 12 entries."""
+    import cafe_mpc_b200 as cm
+    from cafe_mpc_b200 import workload as w
+    N, U = 3, 8
+    csv = os.path.join(REPO, "data/Reference/Data/trot/heuristic/quad_reference.csv")
+    prob = cm.MHPCProblem(csv)
+    x0 = w.mhpc_batch(N)
+    nudge = np.zeros((N, U, 36))
+    for b in range(N):
+        nudge[b, :] = 1e-3 * (x0[b] - x0[0])
+    opt = cm.load_hsddp_setting(os.path.join(REPO, "data/MHPC/settings/ddp_setting.info"))
+    optd = dict(merit_scale=opt.merit_scale, merit_offset=opt.merit_offset, dynamics_feas_thresh=opt.dynamics_feas_thresh)
+    with tempfile.TemporaryDirectory() as td:
+        fin, fout = os.path.join(td, "in.txt"), os.path.join(td, "out.txt")
+        with open(fin, "w") as f:
+            f.write("%d %d\n" % (N, U))
+            for b in range(N):
+                f.write(" ".join(repr(float(v)) for v in x0[b]) + "\n")
+                for u in range(U):
+                    f.write(" ".join(repr(float(v)) for v in nudge[b, u]) + "\n")
+        subprocess.check_call([os.path.join(REPO, "oracle/_ref/ref_mhpc"), csv, repr(float(prob.deck.contents.hip_yaw)), fin, fout],
+                              cwd=os.path.join(REPO, "data/_run"), stdout=subprocess.DEVNULL)
+        probs = parse(fout)
+    kv36 = np.cos(1.0 + np.arange(36))
+    out = dict(x0=x0, nudge=nudge, kv=kv36)
+    store(out, probs, optd, lambda n: kv36[:n])
+    dst = os.path.join(REPO, "tests/golden/ref_mhpc_trot.npz")
+    np.savez_compressed(dst, **out)
+    print("wrote", dst, os.path.getsize(dst) // 1024, "KB;", "iterations of the initial solves:", [int(out["p%d_s0_counters" % b][0]) for b in range(N)],
+          "layouts:", sorted({tuple(out["p0_s%d_horizons" % s]) for s in range(U + 1)}))
+
+
 def main():
     import cafe_mpc_b200 as cm
     from cafe_mpc_b200 import workload as w
@@ -165,27 +226,7 @@ def main():
         subprocess.check_call([os.path.join(REPO, "oracle/_ref/ref_hkd"), csv, fin, fout], cwd=os.path.join(REPO, "data/_run"), stdout=subprocess.DEVNULL)
         probs = parse(fout)
     out = dict(body=body, qJ=qJ, nudge=nudge, kv=KV)
-    for b, solves in enumerate(probs):
-        for s, rec in enumerate(solves):
-            pre = "p%d_s%d_" % (b, s)
-            sol = rec["solution"]
-            out[pre + "x0"] = rec["x0"]; out[pre + "counters"] = rec["counters"]; out[pre + "final"] = rec["final"]
-            out[pre + "trace"] = trace_of(rec["events"], len(sol), optd)
-            assert len(out[pre + "trace"]) == rec["counters"][0]
-            assert int(out[pre + "trace"][:, 7].sum()) == rec["counters"][1] and int(out[pre + "trace"][:, 6].sum()) == rec["counters"][2]
-            out[pre + "n_al"] = np.array(sum(1 for e in rec["events"] if e[0] == EV_AL and e[1] == 0))
-            out[pre + "horizons"] = np.array([p["horizon"] for p in sol]); out[pre + "contacts"] = np.array([p["contact"] for p in sol])
-            for i, p in enumerate(sol):
-                q = pre + "ph%d_" % i
-                out[q + "Xbar"], out[q + "Ubar"], out[q + "dU"] = p["Xbar"], p["Ubar"], p["dU"]
-                out[q + "Kv"] = p["K"] @ KV
-                if i == 0:
-                    out[q + "K4"] = p["K"][:4]
-                if b == 0 and s == 0:
-                    out[q + "K"], out[q + "Quu"], out[q + "Qux"], out[q + "G"], out[q + "Qu"] = p["K"], p["Quu"], p["Qux"], p["G"], p["Qu"]
-                if s > 0:
-                    g = rec["guess"][i]
-                    out[q + "gXbar"], out[q + "gUbar"], out[q + "gKv"] = g["Xbar"], g["Ubar"], g["K"] @ KV
+    store(out, probs, optd, lambda n: KV)
     dst = os.path.join(REPO, "tests/golden/ref_hkd_trot.npz")
     np.savez_compressed(dst, **out)
     print("wrote", dst, os.path.getsize(dst) // 1024, "KB;", "iterations of the initial solves:", [int(out["p%d_s0_counters" % b][0]) for b in range(N_PROB)])
@@ -193,3 +234,4 @@ def main():
 
 if __name__ == "__main__":
     main()
+    main_mhpc()
