@@ -14,8 +14,9 @@
 // to the re-solves (0.9 dt_mpc) is not applied: results would depend on the machine.
 //
 // usage (cwd must be a directory D with D/../MHPC/settings/..., e.g. data/_run):
-//   ref_mhpc <quad_reference.csv> <hip_yaw> <in.txt> <out.txt>
+//   ref_mhpc <quad_reference.csv> <hip_yaw> <in.txt> <out.txt> [mhpc_config.info]
 //   in.txt : n_problems n_updates, then per problem 36 numbers (x0) and n_updates x 36 numbers (state nudges)
+//   the optional last argument replaces "../MHPC/settings/mhpc_config.info" (MHPCLocomotion.cpp:24), e.g. the barrel-roll configuration
 #include <cstdio>
 #include <fstream>
 #include <memory>
@@ -53,7 +54,7 @@ static void run_solve(FILE* f, MHPCProblemData<T>& pd, HSDDP_OPTION& opt, const 
 }
 
 int main(int argc, char** argv) {
-  if (argc < 5) { fprintf(stderr, "usage: ref_mhpc <quad_reference.csv> <hip_yaw> <in.txt> <out.txt>\n"); return 2; }
+  if (argc < 5) { fprintf(stderr, "usage: ref_mhpc <quad_reference.csv> <hip_yaw> <in.txt> <out.txt> [mhpc_config.info]\n"); return 2; }
   g_hip_yaw = atof(argv[2]);
   std::ifstream in(argv[3]);
   int n_prob = 0, n_upd = 0;
@@ -69,7 +70,7 @@ int main(int argc, char** argv) {
 
     // MHPCLocomotion<T>::initialize (MHPCLocomotion.cpp:20-66)
     MHPCConfig mpc_config;
-    loadMHPCConfig("../MHPC/settings/mhpc_config.info", mpc_config);
+    loadMHPCConfig(argc > 5 ? argv[5] : "../MHPC/settings/mhpc_config.info", mpc_config);
     HSDDP_OPTION ddp_setting;
     loadHSDDPSetting("../MHPC/settings/ddp_setting.info", ddp_setting);
     MHPCProblem<T> opt_problem;

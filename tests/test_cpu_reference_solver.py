@@ -19,6 +19,7 @@ from oracle_bindings import oracle_solve
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSV = os.path.join(REPO, "data/Reference/Data/trot/heuristic/quad_reference.csv")
 RTOL = 1e-9
+LONG_RTOL = 1e-9     # runs of 100+ DDP iterations: no allowance needed so far
 
 
 def relerr(g, o):
@@ -41,6 +42,21 @@ def ref_mhpc():
     algorithms themselves (mass matrix, bias forces, RNEA derivatives, foot kinematics), which are pinned by the reference's known answers
     (tests/test_cpu_mhpc.py::test_wb_contact_dynamics_known_answers) and its CasADi kinematic partials."""
     return np.load(os.path.join(REPO, "tests/golden/ref_mhpc_trot.npz"))
+
+
+class _Prefixed:
+    """view of an npz with a key prefix (the barrel-roll file holds two start offsets)"""
+    def __init__(self, npz, prefix):
+        self.npz, self.prefix = npz, prefix
+
+    def __getitem__(self, k):
+        return self.npz[k] if k == "kv" else self.npz[self.prefix + k]
+
+
+@pytest.fixture(scope="module")
+def ref_barrel():
+    """BASELINE config 4 (running barrel roll) at the start offsets 0 and 205, oracle/_ref/ref_mhpc with mhpc_config_barrel.info."""
+    return np.load(os.path.join(REPO, "tests/golden/ref_mhpc_barrel.npz"))
 
 
 @pytest.fixture(scope="module")
@@ -188,3 +204,24 @@ def test_oracle_and_mpc_shift_reproduce_the_reference_mhpc_update_chain(cm, mhpc
             check_solve(cm, p1, ref, pre, info, trace, sol)
             prob, k0 = p1, k1
         assert (1, 24, 10) in layouts and (24, 1, 10) in layouts
+
+
+def barrel_problem(cm, k0):
+    from cafe_mpc_b200 import workload
+    return cm.MHPCProblem(workload.BARREL_CSV, mhpc_config=workload.BARREL_CONFIG, k0=k0)
+
+
+@pytest.mark.parametrize("k0", [0, 205])
+def test_oracle_reproduces_the_reference_running_barrel_roll(cm, mhpc_options, ref_barrel, k0):
+    """BASELINE config 4 against the reference's own code. Offset 0: stance -> diagonal pair -> flight. Offset 205: 22 flight knots, then the
+    four-foot landing - WBM::impact / impact_partial (incl. the impulse indexing of WBM.cpp:451-454), MHPCReset, four touchdown constraints
+    under the augmented Lagrangian, seven AL updates; the perturbed problem runs into the 10 x 20 iteration cap with 1 829 line-search trials
+    and still takes every decision like the reference; its 200 per-iteration records hold at 1e-9 like everything else."""
+    ref = _Prefixed(ref_barrel, "k%d_" % k0)
+    prob = barrel_problem(cm, k0)
+    for b in range(2):
+        pre = "p%d_s0_" % b
+        check_deck_layout(prob, ref, pre)
+        info, hist, trace, sol = oracle_solve(prob.deck, mhpc_options, ref["x0"][b])
+        long_run = info["iter"] >= 100
+        check_solve(cm, prob, ref, pre, info, trace, sol, full=(b == 0 and k0 == 0), rtol=RTOL if not long_run else LONG_RTOL)

@@ -8,7 +8,8 @@ import os
 import numpy as np
 import pytest
 
-from test_cpu_reference_solver import CSV, RTOL, check_deck_layout, check_solve, mhpc_options, ref, ref_mhpc, relerr  # noqa: F401  (fixtures)
+from test_cpu_reference_solver import (CSV, LONG_RTOL, RTOL, _Prefixed, barrel_problem, check_deck_layout, check_solve, mhpc_options, ref, ref_barrel,  # noqa: F401
+                                       ref_mhpc, relerr)
 
 pytestmark = pytest.mark.gpu
 
@@ -139,3 +140,19 @@ def test_gpu_update_deck_chain_reproduces_the_reference_mhpc_update_chain(cm, mh
             check_deck_layout(p1, ref, pre)
             check_solve(cm, p1, ref, pre, info[b], trace[b, :info[b]["iter"]], sol[b])
     assert seen_td
+
+
+@pytest.mark.parametrize("k0", [0, 205])
+def test_gpu_reproduces_the_reference_running_barrel_roll(cm, mhpc_options, ref_barrel, k0):
+    """BASELINE config 4 against the reference's own code (see the CPU counterpart for what the two start offsets exercise): at offset 205 the
+    landing impact, its partials, the reset map and four touchdown constraints; the perturbed problem's 200 iterations / 1 829 line-search
+    trials are the reference's, decision for decision."""
+    ref = _Prefixed(ref_barrel, "k%d_" % k0)
+    prob = barrel_problem(cm, k0)
+    s = cm.MultiPhaseDDP(prob, 0, 2)
+    s.set_initial_condition(ref["x0"])
+    s.solve(mhpc_options)
+    info, trace, sol = s.get_solver_info(), s.get_trace(256), s.get_solution()
+    for b in range(2):
+        long_run = info[b]["iter"] >= 100
+        check_solve(cm, prob, ref, "p%d_s0_" % b, info[b], trace[b, :info[b]["iter"]], sol[b], full=(b == 0 and k0 == 0), rtol=RTOL if not long_run else LONG_RTOL)

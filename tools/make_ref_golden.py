@@ -232,6 +232,48 @@ def main():
     print("wrote", dst, os.path.getsize(dst) // 1024, "KB;", "iterations of the initial solves:", [int(out["p%d_s0_counters" % b][0]) for b in range(N_PROB)])
 
 
+def main_barrel():
+    """tests/golden/ref_mhpc_barrel.npz: BASELINE config 4, the running barrel roll (Reference/Data/running_br, cost_weights_barrel.JSON,
+    constraint_params_barrel.info through data/MHPC/settings/mhpc_config_barrel.info) at the start offsets 0 (stance -> diagonal pair -> flight)
+    and 205 (mid-roll flight of 22 knots -> four-foot landing impact with four touchdown constraints -> stance): the reference starts a plan
+    at the first record of its reference file, so the offset is produced by handing it the file without its first k0 records (18 lines each).
+    Two problems per offset (nominal + perturbed, workload.barrel_batch), initial solve only; keys prefixed k{k0}_."""
+    import cafe_mpc_b200 as cm
+    from cafe_mpc_b200 import workload as w
+    N = 2
+    opt = cm.load_hsddp_setting(os.path.join(REPO, "data/MHPC/settings/ddp_setting.info"))
+    optd = dict(merit_scale=opt.merit_scale, merit_offset=opt.merit_offset, dynamics_feas_thresh=opt.dynamics_feas_thresh)
+    kv36 = np.cos(1.0 + np.arange(36))
+    out = dict(kv=kv36)
+    src = open(w.BARREL_CSV).read().split("\n")
+    for k0 in (0, w.BARREL_K0_IMPACT):
+        prob = cm.MHPCProblem(w.BARREL_CSV, mhpc_config=w.BARREL_CONFIG, k0=k0)
+        x0 = w.barrel_batch(prob, N)
+        with tempfile.TemporaryDirectory() as td:
+            fin, fout, fcsv = os.path.join(td, "in.txt"), os.path.join(td, "out.txt"), os.path.join(td, "quad_reference.csv")
+            open(fcsv, "w").write("\n".join(src[:2] + src[2 + 18 * k0:]))
+            with open(fin, "w") as f:
+                f.write("%d 0\n" % N)
+                for b in range(N):
+                    f.write(" ".join(repr(float(v)) for v in x0[b]) + "\n")
+            subprocess.check_call([os.path.join(REPO, "oracle/_ref/ref_mhpc"), fcsv, repr(float(prob.deck.contents.hip_yaw)), fin, fout,
+                                   "../MHPC/settings/mhpc_config_barrel.info"], cwd=os.path.join(REPO, "data/_run"), stdout=subprocess.DEVNULL)
+            probs = parse(fout)
+        sub = {}
+        store(sub, probs, optd, lambda n: kv36[:n])
+        if k0 != 0:      # the full gain / Q arrays once are enough
+            for k in [k for k in sub if "_ph" in k and k.rsplit("_", 1)[1] in ("K", "Quu", "Qux", "G", "Qu")]:
+                del sub[k]
+        out["k%d_x0" % k0] = x0
+        for k, v in sub.items():
+            out["k%d_%s" % (k0, k)] = v
+        print("k0", k0, "counters", [list(sub["p%d_s0_counters" % b]) for b in range(N)])
+    dst = os.path.join(REPO, "tests/golden/ref_mhpc_barrel.npz")
+    np.savez_compressed(dst, **out)
+    print("wrote", dst, os.path.getsize(dst) // 1024, "KB")
+
+
 if __name__ == "__main__":
     main()
     main_mhpc()
+    main_barrel()
