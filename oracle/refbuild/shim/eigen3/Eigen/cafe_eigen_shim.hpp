@@ -41,6 +41,7 @@ typedef std::ptrdiff_t Index;
 constexpr int Dynamic = -1;
 enum { ColMajor = 0, RowMajor = 1, AutoAlign = 0, DontAlign = 2, DontAlignCols = 1 };
 enum { Lower = 1, Upper = 2 };
+constexpr int Infinity = -1;
 
 template <class T> using aligned_allocator = std::allocator<T>;
 
@@ -138,6 +139,11 @@ class DenseBase {
   typedef Matrix<Scalar, traits<D>::Rows, traits<D>::Cols> PlainObject;
   typedef Block<Scalar, traits<D>::Cols, traits<D>::Rows> TransposeReturnType;   // a strided view: A.transpose() is assignable like Eigen's
 
+  DenseBase() = default;
+  DenseBase(const DenseBase&) = default;
+  // assignment through a base reference reaches the derived object (const_cast<MatrixBase<T>&>(m) = ..., BarrelRollTO.cpp:44-52)
+  DenseBase& operator=(const DenseBase& o) { if (this != &o) derived().assign_(o); return *this; }
+  template <class O> D& operator=(const DenseBase<O>& o) { derived().assign_(o); return derived(); }
   D& derived() { return *static_cast<D*>(this); }
   const D& derived() const { return *static_cast<const D*>(this); }
   Index rows() const { return derived().rows_(); }

@@ -305,12 +305,9 @@ void computeGeneralizedGravityDerivatives(const ModelTpl<T>& m, DataTpl<T>&, con
   for (int r = 0; r < 18; ++r) for (int c = 0; c < 18; ++c) G(r, c) = tau[r].d[c];
 }
 
-// ---- centroidal.hpp: only used by the reference's diagnostic getters (WBM.cpp:140-165), not on the solve path
-template <class T, class Q, class V> const ForceTpl<T>& computeCentroidalMomentum(const ModelTpl<T>&, DataTpl<T>&, const Eigen::DenseBase<Q>&, const Eigen::DenseBase<V>&) {
-  throw std::logic_error("pinocchio stand-in: centroidal momentum is not provided");
-}
-template <class T, class Q, class V, class A> const ForceTpl<T>& computeCentroidalMomentumTimeVariation(const ModelTpl<T>&, DataTpl<T>&, const Eigen::DenseBase<Q>&, const Eigen::DenseBase<V>&, const Eigen::DenseBase<A>&) {
-  throw std::logic_error("pinocchio stand-in: centroidal momentum is not provided");
-}
+// ---- centroidal.hpp: only used by the reference's diagnostic getters (WBM.cpp:140-165) when its stand-alone programs publish a trajectory
+//      for the visualiser, never on the solve path: NOT provided, hg / dhg stay zero
+template <class T, class Q, class V> const ForceTpl<T>& computeCentroidalMomentum(const ModelTpl<T>&, DataTpl<T>& d, const Eigen::DenseBase<Q>&, const Eigen::DenseBase<V>&) { return d.hg; }
+template <class T, class Q, class V, class A> const ForceTpl<T>& computeCentroidalMomentumTimeVariation(const ModelTpl<T>&, DataTpl<T>& d, const Eigen::DenseBase<Q>&, const Eigen::DenseBase<V>&, const Eigen::DenseBase<A>&) { return d.dhg; }
 
 }  // namespace pinocchio

@@ -60,6 +60,56 @@ def ref_barrel():
 
 
 @pytest.fixture(scope="module")
+def ref_programs():
+    """The reference's stand-alone programs Loco_TO.cpp and BarrelRollTO.cpp run unchanged, main() included (oracle/_ref/ref_loco,
+    ref_barrel_to; tools/make_ref_golden.py::main_programs)."""
+    return np.load(os.path.join(REPO, "tests/golden/ref_programs.npz"))
+
+
+def program_problem(cm, name):
+    """(problem, options, x0 [36], packed initial guess or None) of the reference program `name`, as this repo builds them."""
+    from cafe_mpc_b200 import workload
+    x0 = workload.mhpc_batch(1)[0]          # both mains start from (0, 0, 0.2183), qJ = (0, -1, 2) x 4 (Loco_TO.cpp:49-55, BarrelRollTO.cpp:97-110)
+    if name == "loco":
+        return cm.LocoProblem(), cm.load_hsddp_setting(workload.LOCO_DDP_SETTING), x0, None
+    prob = cm.BarrelRollProblem()
+    return prob, cm.load_hsddp_setting(workload.BARREL_TO_DDP_SETTING), x0, prob.initial_guess(x0[None])[0]
+
+
+def check_program(cm, prob, ref, info, trace, sol, long_run):
+    """Against a reference program's record. Decisions of every DDP iteration bit-exact in both programs. Loco_TO (14 iterations): everything
+    else at 1e-9. BarrelRollTO (300 iterations, 2 089 line-search trials from a start with defect norm 58): rounding differences of 1e-13 in the
+    first sweep grow to 1e-6 in the per-iteration cost around iteration 30 and shrink again - measured between four roundings of the oracle
+    itself - so its history is held at 1e-5, its final cost at 1e-8 and its trajectories at 1e-5."""
+    pre = "p0_s0_"
+    assert [info["iter"], info["ls_iter_total"], info["reg_iter_total"]] == list(ref[pre + "counters"])
+    rt = ref[pre + "trace"]
+    assert np.array_equal(trace[:, 6:10], rt[:, 6:10])
+    if not long_run:
+        check_solve(cm, prob, ref, pre, info, trace, sol)
+        return
+    np.testing.assert_allclose(trace[:, [0, 10]], rt[:, [0, 10]], rtol=1e-5)
+    np.testing.assert_allclose(trace[:, [1, 11]], rt[:, [1, 11]], rtol=2e-3, atol=1e-8)       # infeasibility: down to 1e-3 at the end, where it is the more sensitive figure
+    assert abs(info["cost"] - ref[pre + "final"][0]) <= 1e-8 * abs(ref[pre + "final"][0])
+    for i, p in enumerate(cm.unpack_solution(prob.deck, sol)):
+        for name in ("Xbar", "Ubar"):
+            assert relerr(p[name], ref[pre + "ph%d_" % i + name]) < 1e-5, (i, name)
+
+
+@pytest.mark.parametrize("name", ["loco", "barrel_to"])
+def test_oracle_reproduces_the_reference_programs(cm, ref_programs, name):
+    """LocoProblem (Loco_TO.cpp) and the in-place barrel roll (BarrelRollTO.cpp, whose problem - switching times, six
+    desired states, per-phase weights, BarrelRoll:: barriers incl. the joint-speed limit, the interpolated initial trajectory - is built inside
+    its main()) against the programs themselves."""
+    ref = _Prefixed(ref_programs, name + "_")
+    prob, opt, x0, guess = program_problem(cm, name)
+    np.testing.assert_array_equal(x0, ref["p0_s0_x0"])
+    assert [p.horizon for p in prob.phases()] == list(ref["p0_s0_horizons"])
+    info, hist, trace, sol = oracle_solve(prob.deck, opt, x0, cap=320, guess=guess)
+    check_program(cm, prob, ref, info, trace, sol, long_run=(name == "barrel_to"))
+
+
+@pytest.fixture(scope="module")
 def mhpc_options(cm):
     return cm.load_hsddp_setting(os.path.join(REPO, "data/MHPC/settings/ddp_setting.info"))
 

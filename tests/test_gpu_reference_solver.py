@@ -8,8 +8,8 @@ import os
 import numpy as np
 import pytest
 
-from test_cpu_reference_solver import (CSV, LONG_RTOL, RTOL, _Prefixed, barrel_problem, check_deck_layout, check_solve, mhpc_options, ref, ref_barrel,  # noqa: F401
-                                       ref_mhpc, relerr)
+from test_cpu_reference_solver import (CSV, LONG_RTOL, RTOL, _Prefixed, barrel_problem, check_deck_layout, check_program, check_solve,  # noqa: F401
+                                       mhpc_options, program_problem, ref, ref_barrel, ref_mhpc, ref_programs, relerr)
 
 pytestmark = pytest.mark.gpu
 
@@ -156,3 +156,18 @@ def test_gpu_reproduces_the_reference_running_barrel_roll(cm, mhpc_options, ref_
     for b in range(2):
         long_run = info[b]["iter"] >= 100
         check_solve(cm, prob, ref, "p%d_s0_" % b, info[b], trace[b, :info[b]["iter"]], sol[b], full=(b == 0 and k0 == 0), rtol=RTOL if not long_run else LONG_RTOL)
+
+
+@pytest.mark.parametrize("name", ["loco", "barrel_to"])
+def test_gpu_reproduces_the_reference_programs(cm, ref_programs, name):
+    """SURVEY section 8(f)2 against the reference's stand-alone programs run unchanged (Loco_TO.cpp: 14 iterations; BarrelRollTO.cpp: 300
+    iterations, 2 089 line-search trials): every decision of every iteration is the program's; tolerances as in check_program."""
+    ref = _Prefixed(ref_programs, name + "_")
+    prob, opt, x0, guess = program_problem(cm, name)
+    s = cm.MultiPhaseDDP(prob, 0, 1)
+    s.set_initial_condition(x0[None])
+    if guess is not None:
+        s.set_initial_guess(guess[None])
+    s.solve(opt)
+    info = s.get_solver_info()[0]
+    check_program(cm, prob, ref, info, s.get_trace(320)[0, :info["iter"]], s.get_solution()[0], long_run=(name == "barrel_to"))

@@ -273,7 +273,43 @@ def main_barrel():
     print("wrote", dst, os.path.getsize(dst) // 1024, "KB")
 
 
+def main_programs():
+    """tests/golden/ref_programs.npz: the reference's stand-alone programs run UNCHANGED, main() included (oracle/_ref/ref_loco = Loco_TO.cpp,
+    oracle/_ref/ref_barrel_to = BarrelRollTO.cpp; the solve is wrapped at link time, oracle/refbuild/ref_program_driver.cpp). Their initial
+    states are hard-coded in main(): one problem each. Keys prefixed loco_ / barrel_to_, then as in the other files (p0_s0_...)."""
+    import cafe_mpc_b200 as cm
+    from cafe_mpc_b200 import workload as w
+    kv36 = np.cos(1.0 + np.arange(36))
+    out = dict(kv=kv36)
+    for name, exe, setting in (("loco", "ref_loco", w.LOCO_DDP_SETTING), ("barrel_to", "ref_barrel_to", w.BARREL_TO_DDP_SETTING)):
+        opt = cm.load_hsddp_setting(setting)
+        optd = dict(merit_scale=opt.merit_scale, merit_offset=opt.merit_offset, dynamics_feas_thresh=opt.dynamics_feas_thresh)
+        prob = cm.LocoProblem() if name == "loco" else cm.BarrelRollProblem()
+        with tempfile.TemporaryDirectory() as td:
+            fout = os.path.join(td, "out.txt")
+            env = dict(os.environ, REF_OUT=fout, REF_HIP_YAW=repr(float(prob.deck.contents.hip_yaw)))
+            subprocess.check_call([os.path.join(REPO, "oracle/_ref", exe)], cwd=os.path.join(REPO, "data/_run"), stdout=subprocess.DEVNULL, env=env)
+            text = open(fout).read()
+            cut = text.index("published ")
+            open(fout, "w").write(text[:cut])
+            probs = parse(fout)
+            pub = np.array([[float(v) for v in ln.split()[1:]] for ln in text[cut:].split("\n") if ln.startswith("wbtraj")])
+        sub = {}
+        store(sub, probs, optd, lambda n: kv36[:n])
+        for k in [k for k in sub if "_ph" in k and k.rsplit("_", 1)[1] in ("Quu", "Qux", "G", "Qu") or k.endswith("_K")]:
+            del sub[k]
+        for k, v in sub.items():
+            out["%s_%s" % (name, k)] = v
+        # what the program itself published for the visualiser (wbTraj_lcmt, doubles): Xbar[k], Ubar[k] of every knot but the terminal ones
+        out[name + "_published"] = pub
+        print(name, "counters", list(sub["p0_s0_counters"]), "final", sub["p0_s0_final"], "published", pub.shape)
+    dst = os.path.join(REPO, "tests/golden/ref_programs.npz")
+    np.savez_compressed(dst, **out)
+    print("wrote", dst, os.path.getsize(dst) // 1024, "KB")
+
+
 if __name__ == "__main__":
     main()
     main_mhpc()
     main_barrel()
+    main_programs()
