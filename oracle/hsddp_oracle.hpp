@@ -14,11 +14,15 @@
  * for it, including a restatement of Eigen 3.3's pivoted LDLT (used by the
  * reference for the positive-definiteness test and for Quu^-1, SinglePhase.cpp:366-375).
  *
- * PARITY STATUS: the reference solver itself cannot be built here (Eigen, Boost,
- * Pinocchio, LCM absent) and its repo holds no golden solver outputs, so the solver
- * layer of this oracle is "parity unpinned" against the real reference; what IS
- * pinned is the model math (reference CasADi C compiled unchanged into oracle/_ref)
- * and the phase schedules.
+ * PARITY STATUS: pinned. The reference's own solver and problem code (HSDDPSolver,
+ * HKD-TrajOpt, MHPC-Trajopt, Loco_TO.cpp, BarrelRollTO.cpp) compiles unchanged from
+ * /root/reference against stand-ins for Eigen / Boost / LCM / Pinocchio (oracle/refbuild,
+ * binaries in oracle/_ref); its records are committed (tests/golden/ref_*.npz) and this
+ * restatement reproduces them decision for decision, the rest at 1e-9
+ * (tests/test_cpu_reference_solver.py). The model math is pinned by the reference's CasADi C
+ * compiled unchanged into oracle/_ref; NOT pinned by those records: the rigid-body algorithms
+ * (oracle/wb_dynamics.hpp), which also stand behind the Pinocchio names in that build - they
+ * are held to the reference's known answers (test/testKKTDynamics.cpp) and its CasADi partials.
  */
 #pragma once
 #include <cmath>
