@@ -256,6 +256,9 @@ def main():
     n_out = world * per if world > 1 else B
     cmd_dev = torch.empty((n_out if rank == 0 else 1, rec), dtype=torch.float64, device="cuda")
     cmd_pin = torch.empty((n_out if rank == 0 else 1, rec), dtype=torch.float64).pin_memory()
+    # second slot of the two-deep collection pipeline (records of step i travel while step i + 1 is solved)
+    cmd_dev2 = [cmd_dev, torch.empty_like(cmd_dev)]
+    cmd_pin2 = [cmd_pin, torch.empty((n_out if rank == 0 else 1, rec), dtype=torch.float64).pin_memory()]
 
     def barrier():
         if world > 1:
@@ -276,6 +279,27 @@ def main():
         else:
             solver.get_commands(args.gain_knots, out=cmd_pin.numpy())  # D2H of the command records
         return float(cmd_pin[0, 0])
+
+    def run_e2e_pipelined(n):
+        """n end-to-end steps as a user's serving loop would run them: every step copies its x0 from page-locked host memory, solves, and hands its
+        records to the asynchronous collection (pack on the solver's stream; D2H - at N > 1 the NCCL send / recv to rank 0 and the D2H of ALL records
+        on rank 0 - on a copy stream) which overlaps the NEXT step's solve; the records of step i - 1 are read on the host while step i's travel.
+        Every byte of every step has landed when this returns."""
+        sink = 0.0
+        for i in range(n):
+            slot = i & 1
+            solver.set_initial_condition(x0_pin.numpy())
+            solver.solve(opt)                                        # H2D of x0 inside
+            if world > 1:
+                solver.gather_commands_async(args.gain_knots, per, cmd_dev2[slot].data_ptr() if rank == 0 else 0, cmd_pin2[slot].data_ptr() if rank == 0 else 0, slot)
+            else:
+                solver.get_commands_async(args.gain_knots, cmd_pin2[slot].numpy(), slot)
+            if i > 0:
+                solver.commands_wait(slot ^ 1)
+                sink += float(cmd_pin2[slot ^ 1][0, 0])
+        solver.commands_wait((n - 1) & 1)
+        sink += float(cmd_pin2[(n - 1) & 1][0, 0])
+        return sink
 
     # N > 1, second way of collecting the records (reported beside `e2e` as `e2e_host_collect`): no inter-GPU traffic at all - every rank copies its
     # own shard over its own PCIe link straight into ONE page-locked host buffer that all ranks map (POSIX shared memory registered with
@@ -336,6 +360,12 @@ def main():
     for _ in range(args.steps):
         step_e2e()
     barrier()
+    wall_e2e_blocking = time.perf_counter() - t1
+    run_e2e_pipelined(2)
+    barrier()
+    t1 = time.perf_counter()
+    run_e2e_pipelined(args.steps)
+    barrier()
     wall_e2e = time.perf_counter() - t1
     wall_e2e_host = 0.0
     if world > 1:
@@ -352,12 +382,12 @@ def main():
     sampler.stop.set()
     sampler.join(timeout=2)
     it_sum = float(sum(i["iter"] for i in info)); it_max = float(max(i["iter"] for i in info))
-    tt = torch.tensor([wall, wall_e2e, dev_ms, it_max, wall_e2e_host], dtype=torch.float64, device="cuda")
+    tt = torch.tensor([wall, wall_e2e, dev_ms, it_max, wall_e2e_host, wall_e2e_blocking], dtype=torch.float64, device="cuda")
     ts = torch.tensor([it_sum, float(launches)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(ts, op=dist.ReduceOp.SUM)
-    wall, wall_e2e, dev_ms, it_max, wall_e2e_host = [float(v) for v in tt.cpu()]
+    wall, wall_e2e, dev_ms, it_max, wall_e2e_host, wall_e2e_blocking = [float(v) for v in tt.cpu()]
     it_sum, launches = [float(v) for v in ts.cpu()]
 
     roof = None
@@ -377,8 +407,12 @@ def main():
             "ms_per_step": 1e3 * wall / args.steps, "device_ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
             "e2e": {"value": Bg * args.steps / wall_e2e, "unit": UNIT, "h2d_bytes_per_step": int(Bg * n0 * 8), "d2h_bytes_per_step": int(n_out * rec * 8),
-                    "what": "cafe_gpu_solve_batch(host x0) + %s (Xbar,Ubar,Y all knots; K,Qu,Quu,Qux first %d knots); byte counts are whole-job totals per step"
-                            % ("cafe_gpu_gather_commands (pack + NCCL send/recv to rank 0) + D2H of all %d records on rank 0" % n_out if world > 1 else "cafe_gpu_get_commands", args.gain_knots)},
+                    "what": "per step: cafe_gpu_solve_batch(host x0) + %s (Xbar,Ubar,Y all knots; K,Qu,Quu,Qux first %d knots); the collection of step i "
+                            "(copy stream) overlaps the solve of step i + 1, all records of all steps on the host before the clock stops; byte counts are whole-job totals per step"
+                            % ("cafe_gpu_gather_commands_async (pack + NCCL send/recv to rank 0 + D2H of all %d records on rank 0)" % n_out if world > 1 else "cafe_gpu_get_commands_async", args.gain_knots)},
+            "e2e_blocking": {"value": Bg * args.steps / wall_e2e_blocking, "unit": UNIT,
+                             "what": "the same steps with the blocking calls (%s): every step waits for its own records before the next x0 is copied"
+                                     % ("cafe_gpu_gather_commands + D2H on rank 0" if world > 1 else "cafe_gpu_get_commands")},
             "e2e_host_collect": ({"value": Bg * args.steps / wall_e2e_host, "unit": UNIT,
                                   "what": "cafe_gpu_solve_batch(host x0) + cafe_gpu_get_commands of every rank's shard over its own PCIe link into one page-locked host "
                                           "buffer shared by the ranks (POSIX shared memory + cudaHostRegister): no inter-GPU traffic, rank 0 holds all %d records" % n_out}

@@ -289,6 +289,16 @@ class MultiPhaseDDP:
     def command_size(self, n_gain_knots=8):
         return lib.cafe_command_size(self.problem.deck, n_gain_knots)
 
+    def get_commands_async(self, n_gain_knots, out_pinned, slot=0):
+        """cafe_gpu_get_commands_async: out_pinned = page-locked [B, command_size] array; returns at once, commands_wait(slot) blocks until it holds the records."""
+        check(lib.cafe_gpu_get_commands_async(self._h, n_gain_knots, out_pinned.ctypes.data_as(C.c_void_p), slot))
+
+    def commands_wait(self, slot=0):
+        check(lib.cafe_gpu_commands_wait(self._h, slot))
+
+    def gather_commands_async(self, n_gain_knots, per_rank, out_dev_ptr, out_host_ptr, slot=0):
+        check(lib.cafe_gpu_gather_commands_async(self._h, n_gain_knots, per_rank, C.c_void_p(out_dev_ptr), C.c_void_p(out_host_ptr), slot))
+
     def get_commands_device(self, n_gain_knots, dev_ptr):
         check(lib.cafe_gpu_get_commands_device(self._h, n_gain_knots, C.c_void_p(dev_ptr)))
 

@@ -50,8 +50,15 @@ struct CafeHandle {
   // them, ConstraintsBase.h:367-374): [(phase * 4 + element) * 2 + {sigma, lambda}][ldb]; al_B = 0: deck values
   double* d_al = nullptr; int al_B = 0;
   int* d_fail = nullptr; size_t fail_bytes = 0;
-  int* h_nactive = nullptr;  // pinned
+  int* h_nactive = nullptr;  // pinned, mapped: the list lengths are stored into it by the device (k_publish_int) - no copy engine on the tick path,
+  int* d_nactive_map = nullptr;   // so a bulk D2H of the previous solve's records (asynchronous collection) cannot delay a tick; its device address
   double* d_pack = nullptr; size_t pack_bytes = 0;
+  // asynchronous collection (cafe_gpu_get_commands_async / cafe_gpu_gather_commands_async): two slots, so that the records of solve i travel to
+  // the host while solve i + 1 runs. Per slot: a pack buffer, "packed" (solver stream) and "landed" (copy stream) events
+  cudaStream_t stream_copy = nullptr;
+  double* d_pack_async[2] = {nullptr, nullptr}; size_t pack_async_bytes[2] = {0, 0};
+  cudaEvent_t ev_packed[2] = {nullptr, nullptr}, ev_landed[2] = {nullptr, nullptr};
+  bool async_used[2] = {false, false};
   PackSeg* d_segs = nullptr; int max_segs = 0;
   // small host tables for the pack / unpack / shift kernels: one growable device buffer + one pinned staging buffer per handle, copies
   // stream-ordered on `stream` (no allocation, no host synchronisation in the MPC loop)
@@ -140,6 +147,9 @@ __global__ void k_carry_al(const SolverDev* __restrict__ Sp, const __grid_consta
       al[(size_t)((pi * 4 + i) * 2 + 1) * ldb_dst + b] = lm;
     }
 }
+
+// one word from device memory to mapped page-locked host memory (a posted store over PCIe): how the host learns a list length
+__global__ void k_publish_int(const int* __restrict__ src, int* __restrict__ dst_mapped) { *dst_mapped = *src; __threadfence_system(); }
 
 __global__ void k_init_devx0(const SolverDev* __restrict__ Sp, const double* __restrict__ x0dev, int ldx, int n0) {
   const SolverDev& S = *Sp;
@@ -523,7 +533,8 @@ extern "C" int cafe_gpu_create(const CafeDeck* deck, int device, int max_batch, 
   CUDA_OK_H(cudaMalloc(&H->d_x0raw, (size_t)H->ldb * CAFE_MAX_N * sizeof(double)));
   CUDA_OK_H(cudaMalloc(&H->d_al, (size_t)H->ldb * CAFE_MAX_PHASES * 8 * sizeof(double)));
   CUDA_OK_H(cudaMalloc(&H->dS, sizeof(SolverDev)));
-  CUDA_OK_H(cudaMallocHost(&H->h_nactive, 64));
+  CUDA_OK_H(cudaHostAlloc(&H->h_nactive, 64, cudaHostAllocMapped));
+  CUDA_OK_H(cudaHostGetDevicePointer(&H->d_nactive_map, H->h_nactive, 0));
   for (int i = 0; i < 3; ++i) { CUDA_OK_H(cudaStreamCreate(&H->stream2[i])); CUDA_OK_H(cudaEventCreateWithFlags(&H->ev_join[i], cudaEventDisableTiming)); }
   CUDA_OK_H(cudaEventCreateWithFlags(&H->ev_fork, cudaEventDisableTiming));
   for (int i = 0; i < 2; ++i) { CUDA_OK_H(cudaEventCreateWithFlags(&H->ev_lqf[i], cudaEventDisableTiming)); CUDA_OK_H(cudaEventCreateWithFlags(&H->ev_lqd[i], cudaEventDisableTiming)); CUDA_OK_H(cudaEventCreateWithFlags(&H->ev_lqj[i], cudaEventDisableTiming)); }
@@ -573,7 +584,10 @@ extern "C" int cafe_gpu_destroy(CafeHandle* H) {
   cudaSetDevice(H->device);
   if (H->tab_busy && H->ev_tab) cudaEventSynchronize(H->ev_tab);
   cudaFree(H->d_tab); if (H->h_tab) cudaFreeHost(H->h_tab); if (H->ev_tab) cudaEventDestroy(H->ev_tab);
-  cudaFree(H->arena); cudaFree(H->d_ref); cudaFree(H->d_ref_pp); cudaFree(H->d_lxx_mask); cudaFree(H->d_hkd_mask); cudaFree(H->d_guess); cudaFree(H->d_x0raw); cudaFree(H->d_al); cudaFree(H->dS); cudaFree(H->d_pack); cudaFree(H->d_segs);
+  cudaFree(H->arena); cudaFree(H->d_ref); cudaFree(H->d_ref_pp); cudaFree(H->d_lxx_mask); cudaFree(H->d_hkd_mask); cudaFree(H->d_guess); cudaFree(H->d_x0raw); cudaFree(H->d_al); cudaFree(H->d_pack_async[0]); cudaFree(H->d_pack_async[1]);
+  if (H->stream_copy) cudaStreamDestroy(H->stream_copy);
+  for (int i = 0; i < 2; ++i) { if (H->ev_packed[i]) cudaEventDestroy(H->ev_packed[i]); if (H->ev_landed[i]) cudaEventDestroy(H->ev_landed[i]); }
+  cudaFree(H->dS); cudaFree(H->d_pack); cudaFree(H->d_segs);
   if (H->h_nactive) cudaFreeHost(H->h_nactive);
   if (H->stream) cudaStreamDestroy(H->stream);
   for (int i = 0; i < 3; ++i) { if (H->stream2[i]) cudaStreamDestroy(H->stream2[i]); if (H->ev_join[i]) cudaEventDestroy(H->ev_join[i]); }
@@ -701,9 +715,9 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
   }
   const int max_ticks = opt->max_AL_iter * opt->max_DDP_iter + 2;
   for (int tick = 0; tick < max_ticks; ++tick) {
-    CUDA_OK(cudaMemcpyAsync(H->h_nactive, S.c.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+    k_publish_int<<<1, 1, 0, st>>>(S.c.n_active, H->d_nactive_map);
     CUDA_OK(cudaStreamSynchronize(st));
-    if (*H->h_nactive == 0) break;
+    if (*(volatile int*)H->h_nactive == 0) break;
     H->ticks++;
     const int n_act = *H->h_nactive;   // = length of c.act_list (k_compact)
     H->S.n_act = n_act;
@@ -744,7 +758,7 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
       timed(H, CAFE_K_SELECT, [&] { cafe_dev::launch_ls_scan(H->dS, B, st, a0, a1); });
       if (a1 >= S.NA) break;
       timed(H, CAFE_K_SELECT, [&] { cafe_dev::launch_compact(H->dS, st, 1); });
-      CUDA_OK(cudaMemcpyAsync(H->h_nactive + 1, S.c.n_pending, sizeof(int), cudaMemcpyDeviceToHost, st));
+      k_publish_int<<<1, 1, 0, st>>>(S.c.n_pending, H->d_nactive_map + 1);
       CUDA_OK(cudaStreamSynchronize(st));
       if (H->h_nactive[1] == 0) break;
     }
@@ -859,6 +873,26 @@ static int run_pack(CafeHandle* H, const std::vector<PackSeg>& segs, long rec_si
   return 0;
 }
 
+// pack on the solver's stream into `dev_dst` without waiting for it (the caller orders whatever reads dev_dst behind ev_packed[slot])
+static int run_pack_nowait(CafeHandle* H, const std::vector<PackSeg>& segs, long rec_size, int nb, double* dev_dst, int slot) {
+  if ((int)segs.size() > H->max_segs) { cafe::set_last_error("too many pack segments"); return CAFE_ERR_ARG; }
+  if (!H->stream_copy) {
+    CUDA_OK(cudaStreamCreateWithFlags(&H->stream_copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) { CUDA_OK(cudaEventCreateWithFlags(&H->ev_packed[i], cudaEventDisableTiming)); CUDA_OK(cudaEventCreateWithFlags(&H->ev_landed[i], cudaEventDisableTiming)); }
+  }
+  // the slot's previous transfer has finished reading its buffers before they are written again
+  if (H->async_used[slot]) CUDA_OK(cudaStreamWaitEvent(H->stream, H->ev_landed[slot], 0));
+  // the segment table is shared with the blocking packers: staged from pageable memory, i.e. copied out of `segs` before this call returns
+  CUDA_OK(cudaMemcpyAsync(H->d_segs, segs.data(), segs.size() * sizeof(PackSeg), cudaMemcpyHostToDevice, H->stream));
+  dim3 grid(592, (unsigned)segs.size());
+  k_pack<<<grid, 256, 0, H->stream>>>(H->d_segs, (int)segs.size(), H->ldb, 0, nb, rec_size, dev_dst);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaEventRecord(H->ev_packed[slot], H->stream));
+  CUDA_OK(cudaStreamWaitEvent(H->stream_copy, H->ev_packed[slot], 0));
+  H->async_used[slot] = true;
+  return 0;
+}
+
 extern "C" int cafe_gpu_get_solution(CafeHandle* H, int b0, int nb, double* sol) {
   if (!H || !sol || b0 < 0 || nb <= 0 || b0 + nb > H->B) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
   CUDA_OK(cudaSetDevice(H->device));
@@ -884,9 +918,41 @@ extern "C" int cafe_gpu_get_commands_device(CafeHandle* H, int n_gain_knots, dou
   if (!H || !cmd_dev || n_gain_knots < 0) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
   return commands_impl(H, n_gain_knots, nullptr, cmd_dev);
 }
+static long command_segments(CafeHandle* H, int n_gain_knots, std::vector<PackSeg>& segs);
 static int commands_impl(CafeHandle* H, int n_gain_knots, double* cmd, double* dev_out) {
   CUDA_OK(cudaSetDevice(H->device));
   std::vector<PackSeg> segs;
+  const long off = command_segments(H, n_gain_knots, segs);
+  return run_pack(H, segs, off, 0, H->B, cmd, dev_out);
+}
+// Asynchronous collection of the command records: packed on the solver's stream (the next solve may be started at once: it is ordered behind
+// the pack), copied to `cmd` (page-locked host memory, [B][cafe_command_size]) on a copy stream. slot = 0 / 1: two collections may be in flight.
+extern "C" int cafe_gpu_get_commands_async(CafeHandle* H, int n_gain_knots, double* cmd, int slot) {
+  if (!H || !cmd || n_gain_knots < 0 || slot < 0 || slot > 1 || H->B <= 0) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
+  CUDA_OK(cudaSetDevice(H->device));
+  std::vector<PackSeg> segs;
+  const long rec = command_segments(H, n_gain_knots, segs);
+  const size_t need = (size_t)H->B * rec * sizeof(double);
+  if (need > H->pack_async_bytes[slot]) {
+    if (H->async_used[slot]) CUDA_OK(cudaEventSynchronize(H->ev_landed[slot]));
+    cudaFree(H->d_pack_async[slot]); H->d_pack_async[slot] = nullptr; H->pack_async_bytes[slot] = 0;
+    CUDA_OK(cudaMalloc(&H->d_pack_async[slot], need));
+    H->pack_async_bytes[slot] = need;
+  }
+  if (int rc = run_pack_nowait(H, segs, rec, H->B, H->d_pack_async[slot], slot)) return rc;
+  CUDA_OK(cudaMemcpyAsync(cmd, H->d_pack_async[slot], need, cudaMemcpyDeviceToHost, H->stream_copy));
+  CUDA_OK(cudaEventRecord(H->ev_landed[slot], H->stream_copy));
+  return 0;
+}
+// blocks until the records of the slot's last asynchronous collection have landed
+extern "C" int cafe_gpu_commands_wait(CafeHandle* H, int slot) {
+  if (!H || slot < 0 || slot > 1) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
+  if (!H->async_used[slot]) return 0;
+  CUDA_OK(cudaSetDevice(H->device));
+  CUDA_OK(cudaEventSynchronize(H->ev_landed[slot]));
+  return 0;
+}
+static long command_segments(CafeHandle* H, int n_gain_knots, std::vector<PackSeg>& segs) {
   long off = 0;
   int left = n_gain_knots;
   for (int i = 0; i < H->S.n_phases; ++i) {
@@ -899,7 +965,7 @@ static int commands_impl(CafeHandle* H, int n_gain_knots, double* cmd, double* d
     add(ph.K, g, m * n); add(ph.Qu, g, m); add_pm(ph.Quu, g, m * m); add_pm(ph.Qux, g, m * n);
     left -= g;
   }
-  return run_pack(H, segs, off, 0, H->B, cmd, dev_out);
+  return off;
 }
 
 // ---- warm start: initial Xbar / Ubar / K per problem, in the packed solution layout (the other arrays of the record are ignored)
@@ -1543,6 +1609,43 @@ extern "C" int cafe_gpu_gather_commands(CafeHandle* H, int n_gain_knots, int per
   }
   NCCL_OK(N->GroupEnd());
   CUDA_OK(cudaStreamSynchronize(H->stream));
+  return 0;
+}
+
+// The same gather without blocking the solver: this rank's records are packed on the solver's stream, the NCCL send / recv and - on rank 0 -
+// the copy of ALL gathered records to `out_host` (page-locked, [nranks * per_rank][cafe_command_size]) run on the copy stream while the next solve
+// proceeds. out_dev: rank 0's device buffer of the slot (the other ranks pass NULL). cafe_gpu_commands_wait(h, slot) waits for it.
+extern "C" int cafe_gpu_gather_commands_async(CafeHandle* H, int n_gain_knots, int per_rank, double* out_dev, double* out_host, int slot) {
+  NcclApi* N = nccl_api();
+  if (!N) { cafe::set_last_error("NCCL (libnccl.so.2) is not available"); return CAFE_ERR_UNSUPPORTED; }
+  CafeComm c;
+  { std::lock_guard<std::mutex> lk(g_comm_mu); auto it = g_comms.find(H); if (it == g_comms.end()) { cafe::set_last_error("no communicator: call cafe_gpu_comm_init_rank first"); return CAFE_ERR_ARG; } c = it->second; }
+  if (slot < 0 || slot > 1 || per_rank < H->B || (c.rank == 0 && (!out_dev || !out_host))) { cafe::set_last_error("bad argument"); return CAFE_ERR_ARG; }
+  CUDA_OK(cudaSetDevice(H->device));
+  std::vector<PackSeg> segs;
+  const size_t rec = (size_t)command_segments(H, n_gain_knots, segs);
+  double* src = out_dev;   // rank 0 packs straight into its slot of the gathered buffer
+  if (c.rank != 0) {
+    const size_t need = (size_t)per_rank * rec * sizeof(double);
+    if (need > H->pack_async_bytes[slot]) {
+      if (H->async_used[slot]) CUDA_OK(cudaEventSynchronize(H->ev_landed[slot]));
+      cudaFree(H->d_pack_async[slot]); H->d_pack_async[slot] = nullptr; H->pack_async_bytes[slot] = 0;
+      CUDA_OK(cudaMalloc(&H->d_pack_async[slot], need));
+      H->pack_async_bytes[slot] = need;
+      CUDA_OK(cudaMemset(H->d_pack_async[slot], 0, need));   // a ragged last shard stays zero-padded
+    }
+    src = H->d_pack_async[slot];
+  }
+  if (int rc = run_pack_nowait(H, segs, (long)rec, H->B, src, slot)) return rc;
+  NCCL_OK(N->GroupStart());
+  if (c.rank == 0) {
+    for (int r = 1; r < c.nranks; ++r) NCCL_OK(N->Recv(out_dev + (size_t)r * per_rank * rec, (size_t)per_rank * rec, ncclDouble, r, c.comm, H->stream_copy));
+  } else {
+    NCCL_OK(N->Send(src, (size_t)per_rank * rec, ncclDouble, 0, c.comm, H->stream_copy));
+  }
+  NCCL_OK(N->GroupEnd());
+  if (c.rank == 0) CUDA_OK(cudaMemcpyAsync(out_host, out_dev, (size_t)c.nranks * per_rank * rec * sizeof(double), cudaMemcpyDeviceToHost, H->stream_copy));
+  CUDA_OK(cudaEventRecord(H->ev_landed[slot], H->stream_copy));
   return 0;
 }
 

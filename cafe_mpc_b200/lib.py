@@ -103,7 +103,7 @@ EXPORTED = [
     "cafe_last_error", "cafe_options_load", "cafe_info_get_number", "cafe_info_get_string", "cafe_deck_build_mhpc_config", "cafe_deck_phase_times", "cafe_deck_build_hkd", "cafe_deck_build_mhpc", "cafe_deck_build_loco", "cafe_deck_build_barrel_to", "cafe_barrel_to_initial_guess", "cafe_deck_mark_mpc_update", "cafe_deck_get",
     "cafe_deck_free", "cafe_hkd_state", "cafe_deck_lq_pattern", "cafe_solution_size", "cafe_command_size", "cafe_gpu_create",
     "cafe_gpu_destroy", "cafe_gpu_solve_batch", "cafe_gpu_solve_batch_device", "cafe_gpu_get_info",
-    "cafe_gpu_get_history", "cafe_gpu_get_trace", "cafe_gpu_get_solution", "cafe_gpu_get_commands", "cafe_gpu_get_commands_device", "cafe_gpu_get_solve_ms",
+    "cafe_gpu_get_history", "cafe_gpu_get_trace", "cafe_gpu_get_solution", "cafe_gpu_get_commands", "cafe_gpu_get_commands_device", "cafe_gpu_get_commands_async", "cafe_gpu_commands_wait", "cafe_gpu_gather_commands_async", "cafe_gpu_get_solve_ms",
     "cafe_gpu_set_references", "cafe_gpu_set_initial_guess", "cafe_gpu_set_al_params", "cafe_gpu_get_al_params", "cafe_gpu_shift_guess", "cafe_gpu_get_planned_state", "cafe_gpu_update_deck", "cafe_lcm_command_size", "cafe_gpu_get_lcm_commands", "cafe_gpu_get_lcm_commands_device", "cafe_hkd_lcm_command_size", "cafe_gpu_get_hkd_lcm_commands", "cafe_gpu_get_hkd_lcm_commands_device",
     "cafe_gpu_get_timing", "cafe_gpu_get_units", "cafe_gpu_set_profiling", "cafe_gpu_debug_get", "cafe_gpu_measure_fp64_peak",
     "cafe_gpu_shard_range", "cafe_gpu_create_multi", "cafe_gpu_multi_destroy", "cafe_gpu_multi_ndev", "cafe_gpu_multi_handle", "cafe_gpu_multi_solve_batch", "cafe_gpu_multi_update_deck",

@@ -161,6 +161,12 @@ int cafe_gpu_get_solution(CafeHandle* h, int b0, int nb, double* sol /*[nb][cafe
 int cafe_gpu_get_commands(CafeHandle* h, int n_gain_knots, double* cmd /*[B][cafe_command_size]*/);
 /* same, packed into a caller-owned DEVICE buffer (source of the final NCCL gather in multi-GPU runs) */
 int cafe_gpu_get_commands_device(CafeHandle* h, int n_gain_knots, double* cmd_dev);
+/* Collection overlapped with the next solve (a two-deep pipeline: solve i + 1 runs while the records of solve i travel). The records are packed on
+ * the solver's stream - a following cafe_gpu_solve_batch is ordered behind the pack and may be issued at once - and copied to `cmd` (page-locked host
+ * memory, [B][cafe_command_size]) by a copy stream. slot = 0 / 1; cafe_gpu_commands_wait(h, slot) blocks until that slot's records have landed.
+ * Same bytes as cafe_gpu_get_commands. */
+int cafe_gpu_get_commands_async(CafeHandle* h, int n_gain_knots, double* cmd_pinned, int slot);
+int cafe_gpu_commands_wait(CafeHandle* h, int slot);
 /* Wire-format step after the path: the per-problem part of MHPC_Command_lcmt (lcmtypes/MHPC_Command_lcmt.lcm), which
  * MHPCLocomotion::publish_mpc_cmd fills on the host from Xbar/Ubar/Y/K/Qu/Quu/Qux with cast<float>() (MHPCLocomotion.cpp:236-281).
  * Emitted as float32 directly from the device arrays for the first n_steps whole-body knots; per problem, in the struct's order:
@@ -199,6 +205,10 @@ int cafe_gpu_comm_destroy(CafeHandle* h);
 /* packs this rank's records and gathers all ranks' slices on rank 0: rank r's records land at out_dev + r * per_rank records (device
  * buffer of rank 0 with nranks * per_rank records; per_rank >= the local batch, equal on all ranks; out_dev is ignored elsewhere) */
 int cafe_gpu_gather_commands(CafeHandle* h, int n_gain_knots, int per_rank, double* out_dev);
+/* ... and without blocking the solver: pack on the solver's stream, NCCL send / recv and (rank 0) the copy of all gathered records to out_host
+ * (page-locked, [nranks * per_rank][cafe_command_size]) on the copy stream; out_dev = rank 0's device buffer of this slot (NULL on the other ranks);
+ * cafe_gpu_commands_wait(h, slot) waits. */
+int cafe_gpu_gather_commands_async(CafeHandle* h, int n_gain_knots, int per_rank, double* out_dev, double* out_host_pinned, int slot);
 
 /* device-time breakdown of the last solve, ms per kernel family, and launch counts */
 /* timing slots of cafe_gpu_get_timing: one per kernel family */

@@ -331,3 +331,30 @@ def test_hkd_lcm_command_packing(cm, hkd_options):
     from cafe_mpc_b200.lib import CafeError
     with pytest.raises(CafeError):
         s.get_hkd_lcm_commands(1000)
+
+
+def test_asynchronous_collection_equals_the_blocking_one(cm, hkd_problem, hkd_options):
+    """cafe_gpu_get_commands_async / cafe_gpu_commands_wait (pack on the solver's stream, D2H on a copy stream, two slots) deliver the bytes of
+    cafe_gpu_get_commands - also when the next solve, on other initial states, is issued before the records of the previous one are awaited."""
+    import torch
+    from cafe_mpc_b200 import workload
+    B = 48
+    x0 = workload.hkd_batch(hkd_problem, 2 * B)
+    s = cm.MultiPhaseDDP(hkd_problem, 0, B)
+    want = []
+    for part in (x0[:B], x0[B:]):
+        s.set_initial_condition(part); s.solve(hkd_options)
+        want.append(s.get_commands(8).copy())
+    assert not np.array_equal(want[0], want[1])
+    pin = [torch.zeros(want[0].shape, dtype=torch.float64).pin_memory() for _ in range(2)]
+    s.set_initial_condition(x0[:B]); s.solve(hkd_options)
+    s.get_commands_async(8, pin[0].numpy(), 0)
+    s.set_initial_condition(x0[B:]); s.solve(hkd_options)      # overwrites the solver's arrays: the pack of slot 0 is ordered before it
+    s.get_commands_async(8, pin[1].numpy(), 1)
+    s.commands_wait(0); s.commands_wait(1)
+    assert np.array_equal(pin[0].numpy(), want[0]) and np.array_equal(pin[1].numpy(), want[1])
+    # a slot can be re-used: the new pack waits for the slot's previous transfer
+    s.set_initial_condition(x0[:B]); s.solve(hkd_options)
+    s.get_commands_async(8, pin[1].numpy(), 1)
+    s.commands_wait(1)
+    assert np.array_equal(pin[1].numpy(), want[0])
