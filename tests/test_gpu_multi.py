@@ -95,4 +95,4 @@ def test_torchrun_gather_equals_single_gpu_bitwise(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     res = json.loads(r.stdout.strip().splitlines()[-1])
-    assert res["bitwise_equal"] and res["info_equal"], res
+    assert res["bitwise_equal"] and res["info_equal"] and res["async_bitwise_equal"], res

@@ -33,6 +33,15 @@ s.solve(opt)
 rec = s.command_size(8)
 buf = torch.zeros((world * per if rank == 0 else 1, rec), dtype=torch.float64, device="cuda")
 s.gather_commands(8, per, buf.data_ptr())
+# the asynchronous gather (pack on the solver's stream, NCCL + D2H on the copy stream) while another solve runs: same records on rank 0's host
+buf2 = torch.zeros((world * per if rank == 0 else 1, rec), dtype=torch.float64, device="cuda")
+pin2 = torch.zeros((world * per if rank == 0 else 1, rec), dtype=torch.float64).pin_memory()
+s.gather_commands_async(8, per, buf2.data_ptr() if rank == 0 else 0, pin2.data_ptr() if rank == 0 else 0, 0)
+s.set_initial_condition(x0[lo:hi][::-1].copy())     # other initial states: the solver's arrays are overwritten while the records travel
+s.solve(opt)
+s.commands_wait(0)
+s.set_initial_condition(x0[lo:hi])
+s.solve(opt)
 infos = [None] * world
 dist.all_gather_object(infos, s.get_solver_info())
 if rank == 0:
@@ -43,7 +52,8 @@ if rank == 0:
     ref = one.get_commands(8)
     if a.out:
         np.save(a.out, got)
-    print(json.dumps({"world": world, "batch": a.batch, "bitwise_equal": bool(np.array_equal(got, ref)), "info_equal": sum(infos, []) == one.get_solver_info(),
+    print(json.dumps({"world": world, "batch": a.batch, "bitwise_equal": bool(np.array_equal(got, ref)), "async_bitwise_equal": bool(np.array_equal(pin2.numpy()[: a.batch], ref)),
+                      "info_equal": sum(infos, []) == one.get_solver_info(),
                       "max_abs_diff": float(np.max(np.abs(got - ref)))}))
 dist.barrier()
 dist.destroy_process_group()
