@@ -13,7 +13,7 @@ typedef double T;
 
 struct Event { int type, phase; double a, b; };
 // event types
-enum { EV_ROLLOUT = 1, EV_COST = 2, EV_FEAS = 3, EV_LQ = 4, EV_BWD = 5, EV_LIN = 6, EV_ACCEPT = 7, EV_AL = 8, EV_REB = 9, EV_TCON = 10, EV_PCON = 11 };
+enum { EV_ROLLOUT = 1, EV_COST = 2, EV_FEAS = 3, EV_LQ = 4, EV_BWD = 5, EV_LIN = 6, EV_ACCEPT = 7, EV_AL = 8, EV_REB = 9, EV_TCON = 10, EV_PCON = 11, EV_BWD_DV = 12 };
 static std::vector<Event> g_log;
 
 class SpyPhase : public SinglePhaseBase<T> {
@@ -37,6 +37,7 @@ class SpyPhase : public SinglePhaseBase<T> {
   bool backward_sweep(T reg, DVec<T> G, DMat<T> H) override {
     const bool ok = p->backward_sweep(reg, G, H);
     g_log.push_back({EV_BWD, id, reg, ok ? 1.0 : 0.0});
+    if (ok) { T a, b; p->get_exp_cost_change(a, b); g_log.push_back({EV_BWD_DV, id, a, b}); }   // what MS = false takes its expected cost change from
     return ok;
   }
   DVec<T> resetmap(DVec<T>& x) override { return p->resetmap(x); }

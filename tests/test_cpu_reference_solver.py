@@ -275,3 +275,34 @@ def test_oracle_reproduces_the_reference_running_barrel_roll(cm, mhpc_options, r
         info, hist, trace, sol = oracle_solve(prob.deck, mhpc_options, ref["x0"][b])
         long_run = info["iter"] >= 100
         check_solve(cm, prob, ref, pre, info, trace, sol, full=(b == 0 and k0 == 0), rtol=RTOL if not long_run else LONG_RTOL)
+
+
+@pytest.fixture(scope="module")
+def ref_ss():
+    """HSDDP_OPTION::MS = false run by the reference itself (ref_hkd / ref_mhpc with `MS false` in ddp_setting.info; tools/make_ref_golden.py)."""
+    return np.load(os.path.join(REPO, "tests/golden/ref_single_shooting.npz"))
+
+
+# whole-problem single shooting integrates the entire horizon open loop around every trial: on the whole-body problem (35 knots from a cost of 978)
+# rounding differences between two correct implementations reach 1e-8 in the early iterations' cost (decisions stay equal); HKD holds 1e-9
+SS_RTOL = {"hkd": RTOL, "mhpc": 1e-6}
+
+
+def single_shooting_case(cm, ref_ss, kind, hkd_options, mhpc_options):
+    ref = _Prefixed(ref_ss, kind + "_")
+    prob = cm.HKDProblem(CSV) if kind == "hkd" else cm.MHPCProblem(CSV)
+    opt = copy.copy(hkd_options if kind == "hkd" else mhpc_options)
+    opt.MS = 0
+    x0 = np.stack([ref["p%d_s0_x0" % b] for b in range(2)])
+    return ref, prob, opt, x0
+
+
+@pytest.mark.parametrize("kind", ["hkd", "mhpc"])
+def test_oracle_reproduces_the_reference_in_whole_problem_single_shooting(cm, hkd_options, mhpc_options, ref_ss, kind):
+    """MS = false (MultiPhaseDDP.cpp:65-68: every phase's shooting set cleared; :330-333: no linear rollout; SinglePhase.cpp:383-387: the
+    expected cost change comes from the sweep) against the reference's own run with that setting, HKD and MHPC trot."""
+    ref, prob, opt, x0 = single_shooting_case(cm, ref_ss, kind, hkd_options, mhpc_options)
+    for b in range(2):
+        info, hist, trace, sol = oracle_solve(prob.deck, opt, x0[b])
+        assert info["feas"] == 0.0
+        check_solve(cm, prob, ref, "p%d_s0_" % b, info, trace, sol, rtol=SS_RTOL[kind])

@@ -8,8 +8,8 @@ import os
 import numpy as np
 import pytest
 
-from test_cpu_reference_solver import (CSV, LONG_RTOL, RTOL, _Prefixed, barrel_problem, check_deck_layout, check_program, check_solve,  # noqa: F401
-                                       mhpc_options, program_problem, ref, ref_barrel, ref_mhpc, ref_programs, relerr)
+from test_cpu_reference_solver import (CSV, LONG_RTOL, RTOL, SS_RTOL, _Prefixed, barrel_problem, check_deck_layout, check_program, check_solve,  # noqa: F401
+                                       mhpc_options, program_problem, ref, ref_barrel, ref_mhpc, ref_programs, ref_ss, relerr, single_shooting_case)
 
 pytestmark = pytest.mark.gpu
 
@@ -171,3 +171,16 @@ def test_gpu_reproduces_the_reference_programs(cm, ref_programs, name):
     s.solve(opt)
     info = s.get_solver_info()[0]
     check_program(cm, prob, ref, info, s.get_trace(320)[0, :info["iter"]], s.get_solution()[0], long_run=(name == "barrel_to"))
+
+
+@pytest.mark.parametrize("kind", ["hkd", "mhpc"])
+def test_gpu_reproduces_the_reference_in_whole_problem_single_shooting(cm, hkd_options, mhpc_options, ref_ss, kind):
+    """HSDDP_OPTION::MS = false on the GPU against the reference's own run with that setting (HKD and MHPC trot, two problems each)."""
+    ref, prob, opt, x0 = single_shooting_case(cm, ref_ss, kind, hkd_options, mhpc_options)
+    s = cm.MultiPhaseDDP(prob, 0, 2)
+    s.set_initial_condition(x0)
+    s.solve(opt)
+    info, trace, sol = s.get_solver_info(), s.get_trace(256), s.get_solution()
+    for b in range(2):
+        assert info[b]["feas"] == 0.0
+        check_solve(cm, prob, ref, "p%d_s0_" % b, info[b], trace[b, :info[b]["iter"]], sol[b], rtol=SS_RTOL[kind])

@@ -87,7 +87,7 @@ def parse(path):
     return probs
 
 
-EV_ROLLOUT, EV_COST, EV_FEAS, EV_LQ, EV_BWD, EV_LIN, EV_ACCEPT, EV_AL = 1, 2, 3, 4, 5, 6, 7, 8
+EV_ROLLOUT, EV_COST, EV_FEAS, EV_LQ, EV_BWD, EV_LIN, EV_ACCEPT, EV_AL, EV_BWD_DV = 1, 2, 3, 4, 5, 6, 7, 8, 12
 
 
 def trace_of(events, n_phases, opt):
@@ -110,6 +110,10 @@ def trace_of(events, n_phases, opt):
         dV1 = 0.0; dV2 = 0.0
         for e in lin:            # phase order 0..n-1 (MultiPhaseDDP::linear_rollout)
             dV1 += e[2]; dV2 += e[3]
+        if not lin:
+            # MS = false: no linear rollout, the expected cost change is the successful sweep's, summed last phase first (MultiPhaseDDP.cpp:174-213)
+            for e in [e for e in body if e[0] == EV_BWD_DV][-n_phases:]:
+                dV1 += e[2]; dV2 += e[3]
         row = np.zeros(12)
         row[0], row[1], row[2], row[3] = cost, feas, dV1, dV2
         dV_abs = abs(dV1 + 0.5 * dV2)
@@ -273,6 +277,75 @@ def main_barrel():
     print("wrote", dst, os.path.getsize(dst) // 1024, "KB")
 
 
+def settings_tree(td, ms_false):
+    """A copy of the settings directories the reference reads relative to its working directory, with the shooting switch overridden; returns the cwd."""
+    import shutil
+    for sub in ("HKDMPC/settings", "MHPC/settings"):
+        shutil.copytree(os.path.join(REPO, "data", sub), os.path.join(td, sub))
+        f = os.path.join(td, sub, "ddp_setting.info")
+        txt = open(f).read()
+        if ms_false:
+            import re
+            txt, n = re.subn(r"(\bMS\s+)true", r"\1false", txt)
+            assert n == 1
+        open(f, "w").write(txt)
+    run = os.path.join(td, "_run")
+    os.makedirs(run)
+    return run
+
+
+def main_single_shooting():
+    """tests/golden/ref_single_shooting.npz: HSDDP_OPTION::MS = false (whole-problem single shooting: MultiPhaseDDP.cpp:65-68, :330-333,
+    SinglePhase.cpp:187-221, :383-387) run by the reference itself - ddp_setting.info with `MS false`, everything else as shipped - on two HKD
+    and two MHPC trot problems (ref_hkd / ref_mhpc, initial solve). Keys prefixed hkd_ / mhpc_."""
+    import cafe_mpc_b200 as cm
+    from cafe_mpc_b200 import workload as w
+    csv = os.path.join(REPO, "data/Reference/Data/trot/heuristic/quad_reference.csv")
+    kv36 = np.cos(1.0 + np.arange(36))
+    out = dict(kv=kv36)
+    N = 2
+    with tempfile.TemporaryDirectory() as td:
+        run = settings_tree(td, True)
+        # HKD
+        opt = cm.load_hsddp_setting(os.path.join(REPO, "data/HKDMPC/settings/ddp_setting.info"))
+        optd = dict(merit_scale=opt.merit_scale, merit_offset=opt.merit_offset, dynamics_feas_thresh=opt.dynamics_feas_thresh)
+        fin, fout = os.path.join(td, "in.txt"), os.path.join(td, "out.txt")
+        body = np.tile(w.HKD_NOMINAL_BODY, (N, 1)); qJ = np.tile(w.HKD_NOMINAL_QJ, (N, 1))
+        for b in range(1, N):
+            for j in range(12):
+                body[b, j] += w.HKD_BODY_SCALE[j] * (2 * w.uniform(b, j) - 1)
+                qJ[b, j] += w.HKD_QJ_SCALE[j] * (2 * w.uniform(b, 12 + j) - 1)
+        with open(fin, "w") as f:
+            f.write("%d 0\n" % N)
+            for b in range(N):
+                f.write(" ".join(repr(float(v)) for v in np.concatenate([body[b], qJ[b]])) + "\n")
+        subprocess.check_call([os.path.join(REPO, "oracle/_ref/ref_hkd"), csv, fin, fout], cwd=run, stdout=subprocess.DEVNULL)
+        sub = {}
+        store(sub, parse(fout), optd, lambda n: kv36[:n])
+        for k, v in sub.items():
+            if not ("_ph" in k and k.rsplit("_", 1)[1] in ("K", "Quu", "Qux", "G", "Qu")):
+                out["hkd_" + k] = v
+        print("hkd MS=false counters", [list(sub["p%d_s0_counters" % b]) for b in range(N)])
+        # MHPC
+        prob = cm.MHPCProblem(csv)
+        x0 = w.mhpc_batch(N)
+        with open(fin, "w") as f:
+            f.write("%d 0\n" % N)
+            for b in range(N):
+                f.write(" ".join(repr(float(v)) for v in x0[b]) + "\n")
+        subprocess.check_call([os.path.join(REPO, "oracle/_ref/ref_mhpc"), csv, repr(float(prob.deck.contents.hip_yaw)), fin, fout], cwd=run, stdout=subprocess.DEVNULL)
+        sub = {}
+        store(sub, parse(fout), optd, lambda n: kv36[:n])
+        for k, v in sub.items():
+            if not ("_ph" in k and k.rsplit("_", 1)[1] in ("K", "Quu", "Qux", "G", "Qu")):
+                out["mhpc_" + k] = v
+        out["mhpc_x0"] = x0
+        print("mhpc MS=false counters", [list(sub["p%d_s0_counters" % b]) for b in range(N)])
+    dst = os.path.join(REPO, "tests/golden/ref_single_shooting.npz")
+    np.savez_compressed(dst, **out)
+    print("wrote", dst, os.path.getsize(dst) // 1024, "KB")
+
+
 def main_programs():
     """tests/golden/ref_programs.npz: the reference's stand-alone programs run UNCHANGED, main() included (oracle/_ref/ref_loco = Loco_TO.cpp,
     oracle/_ref/ref_barrel_to = BarrelRollTO.cpp; the solve is wrapped at link time, oracle/refbuild/ref_program_driver.cpp). Their initial
@@ -313,3 +386,4 @@ if __name__ == "__main__":
     main_mhpc()
     main_barrel()
     main_programs()
+    main_single_shooting()
