@@ -306,3 +306,29 @@ def test_oracle_reproduces_the_reference_in_whole_problem_single_shooting(cm, hk
         info, hist, trace, sol = oracle_solve(prob.deck, opt, x0[b])
         assert info["feas"] == 0.0
         check_solve(cm, prob, ref, "p%d_s0_" % b, info, trace, sol, rtol=SS_RTOL[kind])
+
+
+@pytest.fixture(scope="module")
+def ref_reb():
+    """PathConstraintBase::update_params with update_relax = 0.5, update_ReB = 2 run by the reference itself (ref_mhpc on the running barrel roll at
+    start offset 205, ddp_setting.info with those two factors; tools/make_ref_golden.py::main_reb)."""
+    return np.load(os.path.join(REPO, "tests/golden/ref_reb_update.npz"))
+
+
+REB_RTOL = 1e-8    # 104 / 200 iterations with barriers that tighten on the way: the feed-forward term dU (a residual that vanishes at convergence) differs by 1.3e-9
+
+
+def reb_case(cm, ref_reb, mhpc_options):
+    opt = copy.copy(mhpc_options)
+    opt.update_relax = float(ref_reb["update_relax"]); opt.update_ReB = float(ref_reb["update_ReB"])
+    return barrel_problem(cm, 205), opt
+
+
+def test_oracle_reproduces_the_reference_relaxed_barrier_updates(cm, mhpc_options, ref_reb):
+    """SURVEY section 8 row a10 against the reference's own code: relaxed-barrier parameters that change during the solve (delta halved down to
+    delta_min, eps doubled, per violated (knot, element), 11 and 20 update rounds) on the landing problem of the running barrel roll - 104
+    iterations / 301 line-search trials and 200 / 1 864, every decision the reference's."""
+    prob, opt = reb_case(cm, ref_reb, mhpc_options)
+    for b in range(2):
+        info, hist, trace, sol = oracle_solve(prob.deck, opt, ref_reb["x0"][b])
+        check_solve(cm, prob, ref_reb, "p%d_s0_" % b, info, trace, sol, rtol=REB_RTOL)

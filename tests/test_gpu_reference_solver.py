@@ -8,8 +8,8 @@ import os
 import numpy as np
 import pytest
 
-from test_cpu_reference_solver import (CSV, LONG_RTOL, RTOL, SS_RTOL, _Prefixed, barrel_problem, check_deck_layout, check_program, check_solve,  # noqa: F401
-                                       mhpc_options, program_problem, ref, ref_barrel, ref_mhpc, ref_programs, ref_ss, relerr, single_shooting_case)
+from test_cpu_reference_solver import (CSV, LONG_RTOL, REB_RTOL, RTOL, SS_RTOL, _Prefixed, barrel_problem, check_deck_layout, check_program, check_solve,  # noqa: F401
+                                       mhpc_options, program_problem, ref, ref_barrel, ref_mhpc, ref_programs, reb_case, ref_reb, ref_ss, relerr, single_shooting_case)
 
 pytestmark = pytest.mark.gpu
 
@@ -184,3 +184,15 @@ def test_gpu_reproduces_the_reference_in_whole_problem_single_shooting(cm, hkd_o
     for b in range(2):
         assert info[b]["feas"] == 0.0
         check_solve(cm, prob, ref, "p%d_s0_" % b, info[b], trace[b, :info[b]["iter"]], sol[b], rtol=SS_RTOL[kind])
+
+
+def test_gpu_reproduces_the_reference_relaxed_barrier_updates(cm, mhpc_options, ref_reb):
+    """PathConstraintBase::update_params with update_relax = 0.5, update_ReB = 2 (k_reb_update, RebCtx) against the reference's own run: the
+    landing problem of the running barrel roll, 104 iterations / 301 trials and 200 / 1 864."""
+    prob, opt = reb_case(cm, ref_reb, mhpc_options)
+    s = cm.MultiPhaseDDP(prob, 0, 2)
+    s.set_initial_condition(ref_reb["x0"])
+    s.solve(opt)
+    info, trace, sol = s.get_solver_info(), s.get_trace(256), s.get_solution()
+    for b in range(2):
+        check_solve(cm, prob, ref_reb, "p%d_s0_" % b, info[b], trace[b, :info[b]["iter"]], sol[b], rtol=REB_RTOL)

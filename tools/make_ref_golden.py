@@ -277,17 +277,21 @@ def main_barrel():
     print("wrote", dst, os.path.getsize(dst) // 1024, "KB")
 
 
-def settings_tree(td, ms_false):
-    """A copy of the settings directories the reference reads relative to its working directory, with the shooting switch overridden; returns the cwd."""
+def settings_tree(td, ms_false, overrides=None):
+    """A copy of the settings directories the reference reads relative to its working directory, with the shooting switch (and other ddp_setting
+    keys: overrides = {key: text}) overridden; returns the cwd."""
+    import re
     import shutil
     for sub in ("HKDMPC/settings", "MHPC/settings"):
         shutil.copytree(os.path.join(REPO, "data", sub), os.path.join(td, sub))
         f = os.path.join(td, sub, "ddp_setting.info")
         txt = open(f).read()
         if ms_false:
-            import re
             txt, n = re.subn(r"(\bMS\s+)true", r"\1false", txt)
             assert n == 1
+        for key, val in (overrides or {}).items():
+            txt, n = re.subn(r"(\b%s\s+)\S+" % key, r"\g<1>%s" % val, txt)
+            assert n == 1, key
         open(f, "w").write(txt)
     run = os.path.join(td, "_run")
     os.makedirs(run)
@@ -346,6 +350,44 @@ def main_single_shooting():
     print("wrote", dst, os.path.getsize(dst) // 1024, "KB")
 
 
+def main_reb():
+    """tests/golden/ref_reb_update.npz: PathConstraintBase::update_params (ConstraintsBase.h:79-85, :194-209) with update factors other than the
+    shipped 1 / 1, run by the reference itself: ddp_setting.info with update_relax = 0.5, update_ReB = 2 on the running barrel roll at start
+    offset 205 (the landing leaves friction / torque barriers violated at the end of outer iterations, so the relaxation and the weight of
+    those elements are updated seven times), two problems, ref_mhpc."""
+    import cafe_mpc_b200 as cm
+    from cafe_mpc_b200 import workload as w
+    N, k0 = 2, w.BARREL_K0_IMPACT
+    opt = cm.load_hsddp_setting(os.path.join(REPO, "data/MHPC/settings/ddp_setting.info"))
+    optd = dict(merit_scale=opt.merit_scale, merit_offset=opt.merit_offset, dynamics_feas_thresh=opt.dynamics_feas_thresh)
+    kv36 = np.cos(1.0 + np.arange(36))
+    out = dict(kv=kv36, update_relax=np.array(0.5), update_ReB=np.array(2.0))
+    src = open(w.BARREL_CSV).read().split("\n")
+    prob = cm.MHPCProblem(w.BARREL_CSV, mhpc_config=w.BARREL_CONFIG, k0=k0)
+    x0 = w.barrel_batch(prob, N)
+    with tempfile.TemporaryDirectory() as td:
+        run = settings_tree(td, False, {"update_relax": "0.5", "update_ReB": "2"})
+        fin, fout, fcsv = os.path.join(td, "in.txt"), os.path.join(td, "out.txt"), os.path.join(td, "quad_reference.csv")
+        open(fcsv, "w").write("\n".join(src[:2] + src[2 + 18 * k0:]))
+        with open(fin, "w") as f:
+            f.write("%d 0\n" % N)
+            for b in range(N):
+                f.write(" ".join(repr(float(v)) for v in x0[b]) + "\n")
+        subprocess.check_call([os.path.join(REPO, "oracle/_ref/ref_mhpc"), fcsv, repr(float(prob.deck.contents.hip_yaw)), fin, fout,
+                               "../MHPC/settings/mhpc_config_barrel.info"], cwd=run, stdout=subprocess.DEVNULL)
+        probs = parse(fout)
+    sub = {}
+    store(sub, probs, optd, lambda n: kv36[:n])
+    for k, v in sub.items():
+        if not ("_ph" in k and k.rsplit("_", 1)[1] in ("K", "Quu", "Qux", "G", "Qu")):
+            out[k] = v
+    out["x0"] = x0
+    print("reb counters", [list(sub["p%d_s0_counters" % b]) for b in range(N)], "n_reb_updates", [sum(1 for e in probs[b][0]["events"] if e[0] == 9 and e[1] == 0) for b in range(N)])
+    dst = os.path.join(REPO, "tests/golden/ref_reb_update.npz")
+    np.savez_compressed(dst, **out)
+    print("wrote", dst, os.path.getsize(dst) // 1024, "KB")
+
+
 def main_programs():
     """tests/golden/ref_programs.npz: the reference's stand-alone programs run UNCHANGED, main() included (oracle/_ref/ref_loco = Loco_TO.cpp,
     oracle/_ref/ref_barrel_to = BarrelRollTO.cpp; the solve is wrapped at link time, oracle/refbuild/ref_program_driver.cpp). Their initial
@@ -387,3 +429,4 @@ if __name__ == "__main__":
     main_barrel()
     main_programs()
     main_single_shooting()
+    main_reb()
