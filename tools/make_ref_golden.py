@@ -31,6 +31,7 @@ import numpy as np
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 N_PROB, N_UPD = 4, 6
+os.makedirs(os.path.join(REPO, "data/_run"), exist_ok=True)     # the working directory the reference resolves "../HKDMPC/settings/..." from
 KV = np.cos(1.0 + np.arange(24))
 ARRAYS = ("Xbar", "Ubar", "K", "dU", "G", "Qu", "Quu", "Qux", "Defect")
 
