@@ -49,6 +49,9 @@ struct CafeHandle {
   // augmented-Lagrangian parameters the next solve starts from instead of the deck's (the MPC loop's carry-over: the reference never resets
   // them, ConstraintsBase.h:367-374): [(phase * 4 + element) * 2 + {sigma, lambda}][ldb]; al_B = 0: deck values
   double* d_al = nullptr; int al_B = 0;
+  // relaxed-barrier update counts carried with the knots over an MPC update (PathConstraintBase::pop_front / push_back, ConstraintsBase.h:296-306;
+  // reset_params is empty): laid out for the CURRENT deck, phase i at reb_carry_off[i], [h][reb_ne][ldb] like PhaseDev::reb_n; reb_B = 0: none
+  unsigned char* d_reb_carry = nullptr; size_t reb_carry_bytes = 0, reb_carry_off[CAFE_MAX_PHASES] = {0}; int reb_B = 0;
   int* d_fail = nullptr; size_t fail_bytes = 0;
   int* h_nactive = nullptr;  // pinned, mapped: the list lengths are stored into it by the device (k_publish_int) - no copy engine on the tick path,
   int* d_nactive_map = nullptr;   // so a bulk D2H of the previous solve's records (asynchronous collection) cannot delay a tick; its device address
@@ -150,6 +153,16 @@ __global__ void k_carry_al(const SolverDev* __restrict__ Sp, const __grid_consta
 
 // one word from device memory to mapped page-locked host memory (a posted store over PCIe): how the host learns a list length
 __global__ void k_publish_int(const int* __restrict__ src, int* __restrict__ dst_mapped) { *dst_mapped = *src; __threadfence_system(); }
+
+// relaxed-barrier update counts of one knot of the new deck: copied from a knot of the previous plan, or zero (a constraint that did not exist)
+struct RebCarryEntry { const unsigned char* src; size_t dst; int ne; };
+__global__ void k_carry_reb(const RebCarryEntry* __restrict__ ent, int ldb_src, int ldb_dst, int B, unsigned char* __restrict__ out) {
+  const RebCarryEntry en = ent[blockIdx.y];
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < en.ne * ldb_dst; t += gridDim.x * blockDim.x) {
+    const int e = t / ldb_dst, b = t % ldb_dst;
+    out[en.dst + (size_t)e * ldb_dst + b] = (en.src && b < B) ? en.src[(size_t)e * ldb_src + b] : (unsigned char)0;
+  }
+}
 
 __global__ void k_init_devx0(const SolverDev* __restrict__ Sp, const double* __restrict__ x0dev, int ldx, int n0) {
   const SolverDev& S = *Sp;
@@ -584,7 +597,7 @@ extern "C" int cafe_gpu_destroy(CafeHandle* H) {
   cudaSetDevice(H->device);
   if (H->tab_busy && H->ev_tab) cudaEventSynchronize(H->ev_tab);
   cudaFree(H->d_tab); if (H->h_tab) cudaFreeHost(H->h_tab); if (H->ev_tab) cudaEventDestroy(H->ev_tab);
-  cudaFree(H->arena); cudaFree(H->d_ref); cudaFree(H->d_ref_pp); cudaFree(H->d_lxx_mask); cudaFree(H->d_hkd_mask); cudaFree(H->d_guess); cudaFree(H->d_x0raw); cudaFree(H->d_al); cudaFree(H->d_pack_async[0]); cudaFree(H->d_pack_async[1]);
+  cudaFree(H->arena); cudaFree(H->d_ref); cudaFree(H->d_ref_pp); cudaFree(H->d_lxx_mask); cudaFree(H->d_hkd_mask); cudaFree(H->d_guess); cudaFree(H->d_x0raw); cudaFree(H->d_al); cudaFree(H->d_reb_carry); cudaFree(H->d_pack_async[0]); cudaFree(H->d_pack_async[1]);
   if (H->stream_copy) cudaStreamDestroy(H->stream_copy);
   for (int i = 0; i < 2; ++i) { if (H->ev_packed[i]) cudaEventDestroy(H->ev_packed[i]); if (H->ev_landed[i]) cudaEventDestroy(H->ev_landed[i]); }
   cudaFree(H->dS); cudaFree(H->d_pack); cudaFree(H->d_segs);
@@ -644,6 +657,11 @@ static int solve_common(CafeHandle* H, const double* x0_host, const double* x0_d
   timed(H, CAFE_K_MISC, [&] { k_init<<<g_knots, tpb, 0, st>>>(H->dS, H->d_x0raw, n0); });
   if (x0_dev) timed(H, CAFE_K_MISC, [&] { k_init_devx0<<<(B + 127) / 128, 128, 0, st>>>(H->dS, x0_dev, ldx, n0); });
   if (H->al_B > 0) timed(H, CAFE_K_MISC, [&] { k_apply_al<<<(B + 127) / 128, 128, 0, st>>>(H->dS, H->d_al); });
+  if (H->reb_B > 0 && reb_dyn) {
+    if (B > H->reb_B) { cafe::set_last_error("batch larger than the carried relaxed-barrier parameter set"); return CAFE_ERR_ARG; }
+    for (int i = 0; i < S.n_phases; ++i)
+      if (S.ph[i].h > 0) CUDA_OK(cudaMemcpyAsync(S.ph[i].reb_n, H->d_reb_carry + H->reb_carry_off[i], (size_t)S.ph[i].h * S.ph[i].reb_ne * S.ldb, cudaMemcpyDeviceToDevice, st));
+  }
   if (H->guess_B > 0) {
     // warm start: Xbar (= X), Ubar (= U) and K of the caller's guess replace the cold-start values; the first rollout (eps = 0)
     // then applies U = Ubar + K (X - Xbar) around it, which is how the reference re-solves after MHPCProblem::update
@@ -1106,6 +1124,69 @@ static int run_al_carry(CafeHandle* owner, const CafeHandle* src, int src_k0, co
   return 0;
 }
 
+// the relaxed-barrier update counts travel with the knots (cafe_mpc_b200/mpc.py::shift_reb states the rules and where the reference has them from):
+// overlapping knots of a continued phase keep theirs, a knot appended at the tail copies the LAST knot's, the trailing reduced-order phase keeps
+// its data while its horizon is unchanged, everything else starts at zero updates. Only when the previous solve could change them (reb_dyn).
+static int run_reb_carry(CafeHandle* owner, const CafeHandle* src, int src_k0, const CafeDeck& nd, int dst_k0, int B) {
+  owner->reb_B = 0;
+  if (!src->S.ph[0].reb_dyn) return 0;
+  const CafeDeck& od = src->deck;
+  const size_t ldb = (size_t)owner->ldb;
+  size_t total = 0;
+  for (int i = 0; i < nd.n_phases; ++i) { owner->reb_carry_off[i] = total; total += (size_t)nd.phase[i].horizon * cafe_reb_elements(nd.phase[i].model) * ldb; }
+  if (total > owner->reb_carry_bytes) {
+    CUDA_OK(cudaStreamSynchronize(owner->stream));
+    cudaFree(owner->d_reb_carry); owner->d_reb_carry = nullptr; owner->reb_carry_bytes = 0;
+    CUDA_OK(cudaMalloc(&owner->d_reb_carry, total + total / 4 + 256));
+    owner->reb_carry_bytes = total + total / 4 + 256;
+  }
+  std::vector<RebCarryEntry> ent;
+  const int lead_o = od.phase[0].model, lead_n = nd.phase[0].model;
+  int n_lead_o = 0, n_lead_n = 0;
+  while (n_lead_o < od.n_phases && od.phase[n_lead_o].model == lead_o) ++n_lead_o;
+  while (n_lead_n < nd.n_phases && nd.phase[n_lead_n].model == lead_n) ++n_lead_n;
+  int ns = dst_k0;
+  for (int i = 0; i < nd.n_phases; ++i) {
+    const CafePhase& np_ = nd.phase[i];
+    const int ne = cafe_reb_elements(np_.model), h = np_.horizon;
+    auto dst_of = [&](int k) { return owner->reb_carry_off[i] + (size_t)k * ne * ldb; };
+    if (i >= n_lead_n || lead_n != lead_o || lead_n == CAFE_MODEL_SRB) {
+      const int j = n_lead_o + (i - n_lead_n);
+      const bool keep = i >= n_lead_n && j >= 0 && j < od.n_phases && od.phase[j].model == np_.model && od.phase[j].horizon == h;
+      for (int k = 0; k < h; ++k) ent.push_back(RebCarryEntry{keep ? src->S.ph[j].reb_n + (size_t)k * ne * src->ldb : nullptr, dst_of(k), ne});
+      continue;
+    }
+    const int ne_ = ns + h;
+    int os = src_k0, sj = -1, sjs = 0, sje = 0;
+    for (int j = 0; j < n_lead_o; ++j) {
+      const CafePhase& op = od.phase[j];
+      const int oe = os + op.horizon;
+      bool same = true;
+      for (int f = 0; f < 4; ++f) same = same && op.contact[f] == np_.contact[f];
+      if (same && os <= ne_ && oe >= ns) { sj = j; sjs = os; sje = oe; break; }
+      os = oe;
+    }
+    for (int k = 0; k < h; ++k) {
+      const int a = ns + k;
+      const unsigned char* sp = nullptr;
+      if (sj >= 0 && sje > sjs) {
+        if (a >= sjs && a < sje) sp = src->S.ph[sj].reb_n + (size_t)(a - sjs) * ne * src->ldb;
+        else if (a >= sje) sp = src->S.ph[sj].reb_n + (size_t)(sje - sjs - 1) * ne * src->ldb;   // push_back(): params.push_back(params.back())
+      }
+      ent.push_back(RebCarryEntry{sp, dst_of(k), ne});
+    }
+    ns = ne_;
+  }
+  if (ent.empty()) return 0;
+  RebCarryEntry* d_ent = nullptr;
+  if (int rc = upload_table(owner, ent, &d_ent)) return rc;
+  dim3 grid(64, (unsigned)ent.size());
+  k_carry_reb<<<grid, 256, 0, owner->stream>>>(d_ent, src->ldb, owner->ldb, B, owner->d_reb_carry);
+  CUDA_OK(cudaGetLastError());
+  owner->reb_B = B;
+  return 0;
+}
+
 // fills owner->d_guess (B packed records of sol_size doubles) on owner->stream
 static int run_shift(CafeHandle* owner, const std::vector<ShiftEntry>& ent, int ldb_src, int B, long sol_size) {
   const size_t need = (size_t)B * (size_t)sol_size * sizeof(double);
@@ -1136,6 +1217,7 @@ extern "C" int cafe_gpu_shift_guess(CafeHandle* dst, CafeHandle* src, int src_k0
   CUDA_OK(cudaStreamSynchronize(src->stream));
   if (int rc = run_shift(dst, ent, src->ldb, B, sol_size)) return rc;
   if (int rc = run_al_carry(dst, src, src_k0, dst->deck, dst_k0, B)) return rc;
+  if (int rc = run_reb_carry(dst, src, src_k0, dst->deck, dst_k0, B)) return rc;
   CUDA_OK(cudaStreamSynchronize(dst->stream));
   dst->guess_B = B;
   return 0;
@@ -1175,8 +1257,9 @@ extern "C" int cafe_gpu_update_deck(CafeHandle* H, const CafeDeck* deck, int k_a
     if (sol_size != cafe_solution_size(deck)) { cafe::set_last_error("internal: packed record size mismatch"); return CAFE_ERR_ARG; }
     if (int rc = run_shift(H, ent, H->ldb, B, sol_size)) return rc;
     if (int rc = run_al_carry(H, H, 0, *deck, k_advance, B)) return rc;
+    if (int rc = run_reb_carry(H, H, 0, *deck, k_advance, B)) return rc;
   } else {
-    H->al_B = 0;
+    H->al_B = 0; H->reb_B = 0;
   }
   if (int rc = configure(H, deck, all_hkd, n_knots)) return rc;
   H->guess_B = B;

@@ -160,3 +160,33 @@ def shift_al(old_problem, old_k0, new_problem, new_k0, old_al):
         if oph[j].n_td > 0 and oph[j].n_td == nph[i].n_td and list(oph[j].td_foot)[:oph[j].n_td] == list(nph[i].td_foot)[:nph[i].n_td]:
             new[..., i, :, :] = old_al[..., j, :, :]
     return new
+
+
+def shift_reb(old_problem, old_k0, new_problem, new_k0, old_reb, init_reb):
+    """The relaxed-barrier parameters the re-solve after an MPC update starts from. old_reb / init_reb: lists per phase of [h, ne, 2] = (delta, eps)
+    per running knot and element (tests/oracle_bindings.py) - what the previous solve left behind, and what the new deck would start from.
+    The reference keeps them with the knots of a phase (PathConstraintBase::pop_front / push_back, ConstraintsBase.h:296-306; reset_params, called
+    by every update, is empty, :191-193): popped knots take theirs along, a knot appended at the tail COPIES THE LAST KNOT's values, a phase the
+    old plan did not have starts from the deck's. Under the shipped settings (update_relax = update_ReB = 1) nothing ever changes them."""
+    old_r, new_r = _wb_ranges(old_problem, old_k0), _wb_ranges(new_problem, new_k0)
+    out = [np.array(r) for r in init_reb]
+    lead = new_problem.phases()[0].model
+    n_lead_old, n_lead_new = len(old_r), len(new_r)
+    for i, ph in enumerate(new_problem.phases()):
+        if ph.model != lead:
+            j = n_lead_old + (i - n_lead_new)       # the trailing reduced-order phase keeps its data while its horizon is unchanged
+            if 0 <= j < len(old_reb) and old_reb[j].shape == out[i].shape:
+                out[i] = np.array(old_reb[j])
+            continue
+        _, s, e, contact = new_r[i]
+        src = [r for r in old_r if r[3] == contact and r[1] <= e and r[2] >= s]
+        if not src or old_reb[src[0][0]].shape[1:] != out[i].shape[1:]:
+            continue
+        j, js, je = src[0][0], src[0][1], src[0][2]
+        for k in range(ph.horizon):
+            a = s + k
+            if js <= a < je:
+                out[i][k] = old_reb[j][a - js]
+            elif a >= je and je - js > 0:
+                out[i][k] = old_reb[j][je - js - 1]
+    return out

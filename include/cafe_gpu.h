@@ -129,7 +129,10 @@ int cafe_gpu_set_initial_guess(CafeHandle* h, const double* guess, int B);
  * (ConstraintsBase.h:367-374). al / out = host [B][n_phases][4][2] = (sigma, lambda) per touchdown-constraint element, unused entries zero.
  * set: the following solves start from these values instead of the deck's TD_AL values (al = NULL returns to the deck's);
  * get: the values the last solve left behind. cafe_gpu_update_deck and cafe_gpu_shift_guess carry them over on the device by themselves
- * (a phase that continues an old phase with the same touchdown feet inherits, every other constraint starts from the deck's values). */
+ * (a phase that continues an old phase with the same touchdown feet inherits, every other constraint starts from the deck's values), and with
+ * them the relaxed-barrier parameters when the last solve could change them (update_relax / update_ReB != 1): the per-(knot, element) update
+ * counts travel with the knots like PathConstraintBase::pop_front / push_back moves them (ConstraintsBase.h:296-306: a knot appended at the tail
+ * copies the last knot's values). */
 int cafe_gpu_set_al_params(CafeHandle* h, const double* al, int B);
 int cafe_gpu_get_al_params(CafeHandle* h, double* out);
 /* The same warm start without leaving the device: the guess of `dst` (deck at start offset dst_k0 of the reference file) is built from

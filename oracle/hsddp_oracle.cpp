@@ -605,8 +605,37 @@ static void apply_guess(Solver& S, const double* guess) {
 /* al_in / al_out: [n_phases][4][2] = (sigma, lambda) of every touchdown-constraint element. The reference's MPC loop never resets them:
  * TerminalConstraintBase::reset_params is an empty function (ConstraintsBase.h:367-374), so what update_params left behind in one solve is
  * what the next solve after HKDProblem::update / MHPCProblem::update starts from. al_in = NULL: the deck's initial values. */
-extern "C" int cafe_oracle_solve_al(const CafeDeck* deck, const CafeOptions* opt, const double* x0, const double* guess, const double* al_in,
-                                    double* al_out, CafeInfo* info, double* hist, int hist_cap, double* trace, int trace_cap, double* sol) {
+/* Relaxed-barrier parameters across the solves of an MPC loop. reb_in / reb_out: for every phase, for every knot k < h, for every element of
+ * every path constraint of the phase (in their order): (delta, eps) - cafe_oracle_reb_ne gives the elements per knot of every phase. The reference
+ * keeps them with the knots: PathConstraintBase::pop_front / push_back (ConstraintsBase.h:296-306; an appended knot copies the last knot's
+ * values), reset_params is empty (:191-193). */
+extern "C" int cafe_oracle_reb_ne(const CafeDeck* deck, int* ne) {
+  try {
+    Solver S;
+    S.setup(deck);
+    for (size_t i = 0; i < S.phases.size(); ++i) { int n = 0; for (auto& pc : S.phases[i]->pcon) n += pc.size; ne[i] = n; }
+    return 0;
+  } catch (const std::exception& e) { std::fprintf(stderr, "cafe_oracle_reb_ne: %s\n", e.what()); return -1; }
+}
+static void reb_io(Solver& S, const double* in, double* out) {
+  size_t o = 0;
+  for (auto& P : S.phases)
+    for (int k = 0; k < P->h; ++k)
+      for (auto& pc : P->pcon)
+        for (int e = 0; e < pc.size; ++e, o += 2) {
+          if (in) { pc.params[k][e].delta = in[o]; pc.params[k][e].eps = in[o + 1]; }
+          if (out) { out[o] = pc.params[k][e].delta; out[o + 1] = pc.params[k][e].eps; }
+        }
+}
+/* the values a fresh deck starts from */
+extern "C" int cafe_oracle_reb_init(const CafeDeck* deck, double* out) {
+  try { Solver S; S.setup(deck); reb_io(S, nullptr, out); return 0; }
+  catch (const std::exception& e) { std::fprintf(stderr, "cafe_oracle_reb_init: %s\n", e.what()); return -1; }
+}
+
+extern "C" int cafe_oracle_solve_carry(const CafeDeck* deck, const CafeOptions* opt, const double* x0, const double* guess, const double* al_in,
+                                       double* al_out, const double* reb_in, double* reb_out, CafeInfo* info, double* hist, int hist_cap,
+                                       double* trace, int trace_cap, double* sol) {
   try {
     g_last.reset(new Solver());
     Solver& S = *g_last;
@@ -616,8 +645,10 @@ extern "C" int cafe_oracle_solve_al(const CafeDeck* deck, const CafeOptions* opt
       for (size_t i = 0; i < S.phases.size(); ++i)
         for (auto& tc : S.phases[i]->tcon)
           for (int e = 0; e < tc.size && e < 4; ++e) { tc.params[e].sigma = al_in[(i * 4 + e) * 2]; tc.params[e].lambda = al_in[(i * 4 + e) * 2 + 1]; }
+    if (reb_in) reb_io(S, reb_in, nullptr);
     S.x0.assign(x0, x0 + S.phases[0]->n);
     S.solve(*opt);
+    if (reb_out) reb_io(S, nullptr, reb_out);
     if (al_out)
       for (size_t i = 0; i < S.phases.size(); ++i) {
         for (int e = 0; e < 8; ++e) al_out[i * 8 + e] = 0;
@@ -646,6 +677,11 @@ extern "C" int cafe_oracle_solve_al(const CafeDeck* deck, const CafeOptions* opt
     std::fprintf(stderr, "cafe_oracle_solve: %s\n", e.what());
     return -1;
   }
+}
+
+extern "C" int cafe_oracle_solve_al(const CafeDeck* deck, const CafeOptions* opt, const double* x0, const double* guess, const double* al_in,
+                                    double* al_out, CafeInfo* info, double* hist, int hist_cap, double* trace, int trace_cap, double* sol) {
+  return cafe_oracle_solve_carry(deck, opt, x0, guess, al_in, al_out, nullptr, nullptr, info, hist, hist_cap, trace, trace_cap, sol);
 }
 
 extern "C" int cafe_oracle_solve_warm(const CafeDeck* deck, const CafeOptions* opt, const double* x0, const double* guess, CafeInfo* info,

@@ -39,6 +39,14 @@ int cafe_oracle_solve_warm(const CafeDeck* deck, const CafeOptions* opt, const d
  * steps: TerminalConstraintBase::reset_params is empty (ConstraintsBase.h:367-374), called from HKDProblem.cpp:208 / MHPCProblem.cpp:363. */
 int cafe_oracle_solve_al(const CafeDeck* deck, const CafeOptions* opt, const double* x0, const double* guess, const double* al_in,
                          double* al_out, CafeInfo* info, double* hist, int hist_cap, double* trace, int trace_cap, double* sol);
+/* ... and the relaxed-barrier parameters, which the reference keeps with the knots of a phase (PathConstraintBase::pop_front / push_back,
+ * ConstraintsBase.h:296-306: an appended knot copies the LAST knot's values; reset_params empty, :191-193). reb_in / reb_out: per phase, per knot
+ * k < h, per element of the phase's path constraints in their order: (delta, eps); cafe_oracle_reb_ne: elements per knot of every phase;
+ * cafe_oracle_reb_init: the values a fresh deck starts from. Only matters when update_relax / update_ReB differ from the shipped 1 / 1. */
+int cafe_oracle_reb_ne(const CafeDeck* deck, int* ne);
+int cafe_oracle_reb_init(const CafeDeck* deck, double* out);
+int cafe_oracle_solve_carry(const CafeDeck* deck, const CafeOptions* opt, const double* x0, const double* guess, const double* al_in, double* al_out,
+                            const double* reb_in, double* reb_out, CafeInfo* info, double* hist, int hist_cap, double* trace, int trace_cap, double* sol);
 
 /* Internal per-knot array of the most recent cafe_oracle_solve (names: X Xbar U Ubar Y Defect dX dU G Qu A B C D K
  * Quu Qux H lx lu ly lxx luu lyy l Phix Phixx Px). Returns the number of doubles written or -1. */

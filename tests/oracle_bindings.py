@@ -34,10 +34,36 @@ def oracle():
     return _lib
 
 
-def oracle_solve(deck, opt, x0, cap=256, guess=None, al=None):
+def oracle_reb_layout(deck):
+    """[(h, ne)] per phase: knots with running constraints and relaxed-barrier elements per knot"""
+    lib = oracle()
+    n_ph = deck.contents.n_phases
+    ne = (C.c_int * n_ph)()
+    assert lib.cafe_oracle_reb_ne(deck, ne) == 0
+    return [(deck.contents.phase[i].horizon, ne[i]) for i in range(n_ph)]
+
+
+def oracle_reb_init(deck):
+    """list per phase of [h, ne, 2] = (delta, eps) a fresh deck starts from"""
+    lib = oracle()
+    lay = oracle_reb_layout(deck)
+    flat = np.zeros(sum(h * ne * 2 for h, ne in lay))
+    assert lib.cafe_oracle_reb_init(deck, flat.ctypes.data_as(C.c_void_p)) == 0
+    return reb_split(flat, lay)
+
+
+def reb_split(flat, lay):
+    out, o = [], 0
+    for h, ne in lay:
+        out.append(flat[o:o + h * ne * 2].reshape(h, ne, 2).copy()); o += h * ne * 2
+    return out
+
+
+def oracle_solve(deck, opt, x0, cap=256, guess=None, al=None, reb=None):
     """Returns (info dict, hist [n_hist,4], trace [iter,12], packed solution). guess: packed solution whose Xbar/Ubar/K start the solve.
     al: [n_phases, 4, 2] (sigma, lambda) the touchdown constraints start from (the MPC loop's carry-over); then a fifth value is returned:
-    the parameters the solve left behind."""
+    the parameters the solve left behind. reb: list per phase of [h, ne, 2] (delta, eps) the relaxed barriers start from; then a sixth value is
+    returned: what the solve left behind (same layout)."""
     lib = oracle()
     x0 = np.ascontiguousarray(x0, dtype=np.float64)
     info = Info()
@@ -54,13 +80,22 @@ def oracle_solve(deck, opt, x0, cap=256, guess=None, al=None):
         a_in = np.ascontiguousarray(al, dtype=np.float64)
         assert a_in.size == n_ph * 8
     a_out = np.zeros((n_ph, 4, 2))
-    rc = lib.cafe_oracle_solve_al(deck, C.byref(opt), x0.ctypes.data_as(C.c_void_p), g.ctypes.data_as(C.c_void_p) if g is not None else None,
-                                  a_in.ctypes.data_as(C.c_void_p) if a_in is not None else None, a_out.ctypes.data_as(C.c_void_p),
-                                  C.byref(info), hist.ctypes.data_as(C.c_void_p), cap, trace.ctypes.data_as(C.c_void_p), cap,
-                                  sol.ctypes.data_as(C.c_void_p))
+    r_in = r_out = None
+    if reb is not None:
+        lay = oracle_reb_layout(deck)
+        assert [r.shape for r in reb] == [(h, ne, 2) for h, ne in lay], ([r.shape for r in reb], lay)
+        r_in = np.ascontiguousarray(np.concatenate([r.ravel() for r in reb]) if reb else np.zeros(0))
+        r_out = np.zeros_like(r_in)
+    rc = lib.cafe_oracle_solve_carry(deck, C.byref(opt), x0.ctypes.data_as(C.c_void_p), g.ctypes.data_as(C.c_void_p) if g is not None else None,
+                                     a_in.ctypes.data_as(C.c_void_p) if a_in is not None else None, a_out.ctypes.data_as(C.c_void_p),
+                                     r_in.ctypes.data_as(C.c_void_p) if r_in is not None else None, r_out.ctypes.data_as(C.c_void_p) if r_out is not None else None,
+                                     C.byref(info), hist.ctypes.data_as(C.c_void_p), cap, trace.ctypes.data_as(C.c_void_p), cap,
+                                     sol.ctypes.data_as(C.c_void_p))
     if rc != 0:
         raise RuntimeError("oracle solve failed")
     d = info.as_dict()
+    if reb is not None:
+        return d, hist[:d["n_hist"]], trace[:d["iter"]], sol, a_out, reb_split(r_out, lay)
     if al is not None:
         return d, hist[:d["n_hist"]], trace[:d["iter"]], sol, a_out
     return d, hist[:d["n_hist"]], trace[:d["iter"]], sol

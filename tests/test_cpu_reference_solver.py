@@ -332,3 +332,32 @@ def test_oracle_reproduces_the_reference_relaxed_barrier_updates(cm, mhpc_option
     for b in range(2):
         info, hist, trace, sol = oracle_solve(prob.deck, opt, ref_reb["x0"][b])
         check_solve(cm, prob, ref_reb, "p%d_s0_" % b, info, trace, sol, rtol=REB_RTOL)
+
+
+def test_oracle_and_shift_reb_reproduce_the_reference_chain_with_changing_barriers(cm, mhpc_options, ref_reb):
+    """The relaxed-barrier parameters travel with the knots through MHPCProblem::update (PathConstraintBase::pop_front / push_back,
+    ConstraintsBase.h:296-306: an appended knot copies the LAST knot's delta / eps; reset_params empty): four MPC updates of the barrel roll's
+    landing problem with update_relax = 0.5, update_ReB = 2 against the reference's own chain. Without the carry-over the second re-solve is
+    off by 50 % in cost; with it (oracle entry cafe_oracle_solve_carry + mpc.shift_reb) every step equals the reference's."""
+    from cafe_mpc_b200 import mpc, workload
+    from oracle_bindings import oracle_reb_init
+    ref = _Prefixed(ref_reb, "chain_")
+    prob, opt = reb_case(cm, ref_reb, mhpc_options)
+    ort = copy.copy(opt)
+    ort.max_AL_iter = opt.max_AL_iter_runtime; ort.max_DDP_iter = opt.max_DDP_iter_runtime
+    k0 = 205
+    info, hist, trace, sol, al, reb = oracle_solve(prob.deck, opt, ref_reb["x0"][0], al=mpc.initial_al(prob), reb=oracle_reb_init(prob.deck))
+    check_solve(cm, prob, ref, "p0_s0_", info, trace, sol, rtol=REB_RTOL)
+    assert any(np.any(r != r0) for r, r0 in zip(reb, oracle_reb_init(prob.deck)))
+    for s in range(1, 5):
+        k1 = k0 + 2
+        p1 = cm.MHPCProblem(workload.BARREL_CSV, mhpc_config=workload.BARREL_CONFIG, k0=k1, mpc_update_nsteps=2)
+        check_deck_layout(p1, ref, "p0_s%d_" % s)
+        guess = mpc.shifted_guess_batch(prob, k0, p1, k1, sol[None, :])[0]
+        x1 = mpc.state_at(prob, cm.unpack_solution(prob.deck, sol), 2)
+        np.testing.assert_allclose(x1, ref["p0_s%d_x0" % s], rtol=REB_RTOL, atol=1e-10)
+        al = mpc.shift_al(prob, k0, p1, k1, al)
+        reb = mpc.shift_reb(prob, k0, p1, k1, reb, oracle_reb_init(p1.deck))
+        info, hist, trace, sol, al, reb = oracle_solve(p1.deck, ort, x1, guess=guess, al=al, reb=reb)
+        check_solve(cm, p1, ref, "p0_s%d_" % s, info, trace, sol, rtol=REB_RTOL)
+        prob, k0 = p1, k1

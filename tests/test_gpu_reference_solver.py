@@ -196,3 +196,25 @@ def test_gpu_reproduces_the_reference_relaxed_barrier_updates(cm, mhpc_options, 
     info, trace, sol = s.get_solver_info(), s.get_trace(256), s.get_solution()
     for b in range(2):
         check_solve(cm, prob, ref_reb, "p%d_s0_" % b, info[b], trace[b, :info[b]["iter"]], sol[b], rtol=REB_RTOL)
+
+
+def test_gpu_update_deck_carries_changing_barrier_parameters_like_the_reference(cm, mhpc_options, ref_reb):
+    """cafe_gpu_update_deck with update_relax = 0.5, update_ReB = 2: the per-(knot, element) update counts travel with the knots (an appended
+    knot copies the last knot's) - four MPC updates of the barrel roll's landing problem on one solver against the reference's own chain."""
+    from cafe_mpc_b200 import workload
+    ref = _Prefixed(ref_reb, "chain_")
+    prob, opt = reb_case(cm, ref_reb, mhpc_options)
+    ort = copy.copy(opt)
+    ort.max_AL_iter = opt.max_AL_iter_runtime; ort.max_DDP_iter = opt.max_DDP_iter_runtime
+    s = cm.MultiPhaseDDP(prob, 0, 2)
+    s.set_initial_condition(np.stack([ref_reb["x0"][0], ref_reb["x0"][0]]))      # two copies: the carry-over is per problem
+    s.solve(opt)
+    for step in range(1, 5):
+        p1 = cm.MHPCProblem(workload.BARREL_CSV, mhpc_config=workload.BARREL_CONFIG, k0=205 + 2 * step, mpc_update_nsteps=2)
+        x1 = s.planned_state(2)
+        s.update_deck(p1, 2)
+        s.set_initial_condition(x1)
+        s.solve(ort)
+        info, trace, sol = s.get_solver_info(), s.get_trace(64), s.get_solution()
+        for b in range(2):
+            check_solve(cm, p1, ref, "p0_s%d_" % step, info[b], trace[b, :info[b]["iter"]], sol[b], rtol=REB_RTOL)

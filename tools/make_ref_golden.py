@@ -377,6 +377,22 @@ def main_reb():
         subprocess.check_call([os.path.join(REPO, "oracle/_ref/ref_mhpc"), fcsv, repr(float(prob.deck.contents.hip_yaw)), fin, fout,
                                "../MHPC/settings/mhpc_config_barrel.info"], cwd=run, stdout=subprocess.DEVNULL)
         probs = parse(fout)
+        # the same settings through four MPC updates (problem 0): the relaxed-barrier parameters travel with the knots - PathConstraintBase::pop_front /
+        # push_back (ConstraintsBase.h:296-306: a knot appended at the tail copies the LAST knot's parameters), reset_params is empty
+        with open(fin, "w") as f:
+            f.write("1 4\n" + " ".join(repr(float(v)) for v in x0[0]) + "\n")
+            for u in range(4):
+                f.write(" ".join(["0"] * 36) + "\n")
+        fout2 = os.path.join(td, "out2.txt")
+        subprocess.check_call([os.path.join(REPO, "oracle/_ref/ref_mhpc"), fcsv, repr(float(prob.deck.contents.hip_yaw)), fin, fout2,
+                               "../MHPC/settings/mhpc_config_barrel.info"], cwd=run, stdout=subprocess.DEVNULL)
+        chain = parse(fout2)
+    sub = {}
+    store(sub, chain, optd, lambda n: kv36[:n])
+    for k, v in sub.items():
+        if not ("_ph" in k and k.rsplit("_", 1)[1] in ("K", "Quu", "Qux", "G", "Qu")):
+            out["chain_" + k] = v
+    print("reb chain counters", [list(sub["p0_s%d_counters" % s_]) for s_ in range(5)], [list(sub["p0_s%d_horizons" % s_]) for s_ in range(5)])
     sub = {}
     store(sub, probs, optd, lambda n: kv36[:n])
     for k, v in sub.items():
