@@ -142,6 +142,7 @@ class HKDProblem {
     auto owner = std::make_shared<cafe_facade::DeckOwner>();
     cafe_facade::check(cafe_deck_build_hkd(quad_ref_ptr->cafe_file().c_str(), cafe_constraint_params.c_str(), plan_duration, dt_sim, nsteps_between_mpc, k0, &owner->h));
     owner->k0 = k0;
+    owner->lineage = (mpc_update && deck_) ? deck_->lineage : cafe_facade::DeckOwner::next_lineage();
     if (mpc_update) { int which = -1; cafe_facade::check(cafe_deck_mark_mpc_update(owner->h, nsteps_between_mpc, &which)); }
     deck_ = owner;
   }

@@ -301,6 +301,7 @@ class MHPCProblem {
     auto owner = std::make_shared<cafe_facade::DeckOwner>();
     cafe_facade::check(cafe_deck_build_mhpc_config(quad_reference->cafe_file().c_str(), &c, cafe_settings_root.c_str(), k0, cafe_loco(), &owner->h));
     owner->k0 = k0;
+    owner->lineage = (mark_nsteps > 0 && deck_) ? deck_->lineage : cafe_facade::DeckOwner::next_lineage();
     if (mark_nsteps > 0) { int which = -1; cafe_facade::check(cafe_deck_mark_mpc_update(owner->h, mark_nsteps, &which)); }
     deck_ = owner;
   }

@@ -63,7 +63,14 @@ class MultiPhaseDDP {
     using cafe_facade::check;
     if (!deck_) throw std::logic_error("solve: set_multiPhaseProblem first");
     if (B_ <= 0) throw std::logic_error("solve: set_initial_condition first");
-    if (h_ && deck_changed_ && cafe_gpu_update_deck(h_, deck_->deck(), 0, 0) != 0) { cafe_gpu_destroy(h_); h_ = nullptr; }   // e.g. another model family
+    if (h_ && deck_changed_) {
+      // the next MPC window of the problem the solver has just solved (same lineage, same batch): the update on the device carries what lives there -
+      // the relaxed-barrier update counts travel with the knots (ConstraintsBase.h:296-306); trajectories and AL parameters are handed over from the
+      // phases below in any case. Anything else: new deck, cold start.
+      const int adv = deck_->k0 - solved_k0_;
+      const bool next_window = deck_->lineage == solved_lineage_ && adv >= 0 && B_ == solved_B_;
+      if (!(next_window && cafe_gpu_update_deck(h_, deck_->deck(), adv, B_) == 0) && cafe_gpu_update_deck(h_, deck_->deck(), 0, 0) != 0) { cafe_gpu_destroy(h_); h_ = nullptr; }   // e.g. another model family
+    }
     if (h_ && B_ > cap_) { cafe_gpu_destroy(h_); h_ = nullptr; }
     if (!h_) { cap_ = std::max(max_batch_, B_); check(cafe_gpu_create(deck_->deck(), device_, cap_, &h_)); }
     deck_changed_ = false;
@@ -88,6 +95,7 @@ class MultiPhaseDDP {
     }
     const CafeOptions o = cafe_options_from_hsddp(option);
     check(cafe_gpu_solve_batch(h_, x0_batch.data(), B_, &o));
+    solved_k0_ = deck_->k0; solved_lineage_ = deck_->lineage; solved_B_ = B_;
     info_.resize(B_);
     check(cafe_gpu_get_info(h_, info_.data()));
     check(cafe_gpu_get_solution(h_, 0, 1, one.data()));
@@ -136,6 +144,7 @@ class MultiPhaseDDP {
   int B_ = 0, device_ = 0, max_batch_ = 1, cap_ = 0;
   CafeHandle* h_ = nullptr;
   bool deck_changed_ = false;
+  int solved_k0_ = 0, solved_B_ = 0; long solved_lineage_ = -1;   // the deck of the last solve on h_
   std::shared_ptr<cafe_facade::DeckOwner> deck_;
   std::vector<CafeInfo> info_;
   std::vector<double> hist_;

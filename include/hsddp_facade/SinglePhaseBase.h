@@ -15,6 +15,9 @@ namespace cafe_facade {
 struct DeckOwner {
   CafeDeckHandle* h = nullptr;
   int k0 = 0;                  // start offset (in reference rows) the deck was built at; advanced by <Problem>::update()
+  long lineage = 0;            // decks that <Problem>::update() derives from one another share it: the solver may then carry state that lives on
+                               // the device over the update (relaxed-barrier update counts) instead of starting cold
+  static long next_lineage() { static long n = 0; return ++n; }
   ~DeckOwner() { if (h) cafe_deck_free(h); }
   const CafeDeck* deck() const { return cafe_deck_get(h); }
 };
