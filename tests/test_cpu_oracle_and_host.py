@@ -398,3 +398,22 @@ def test_hkd_mpc_update_chain_equals_an_independent_restatement_of_the_reference
             np.testing.assert_array_equal(g[i]["K"], np.array(plan.K[i][:-1]))
         prev, k_prev = new, k_new
     assert opened >= 3 and removed >= 3
+
+
+def test_counted_flops_of_the_hkd_sweep_stay_under_the_dense_formula(tmp_path):
+    """tools/count_flops.py (flops counted by the oracle built with an instrumented scalar). The oracle's products skip exact zeros, so the
+    counted sweep must land below SURVEY's dense F_bwd(24, 24, 0) = 233 280 per knot and not far below; the CasADi calls per knot are the reference's:
+    one hkinodyn per rollout knot, one hkinodyn_par per linearised knot."""
+    import json
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "hkd.json"
+    subprocess.run([sys.executable, os.path.join(repo, "tools", "count_flops.py"), "hkd", "--json", str(out)], check=True, capture_output=True, timeout=600)
+    d = json.load(open(out))
+    assert [p["model"] for p in d["phases"]] == ["HKD"] * 3
+    for p in d["phases"]:
+        bwd = p["stages"]["bwd"]["flop_per_knot"]
+        assert 0.6 * 233280 < bwd < 233280
+        assert p["stages"]["roll"]["casadi_calls"]["hkinodyn"] == p["horizon"]
+        assert p["stages"]["lq"]["casadi_calls"]["hkinodyn_par"] == p["horizon"]
+        assert p["stages"]["bwd"]["ops"]["sqrt"] == 0 and p["stages"]["lin"]["ops"]["div"] == 0
