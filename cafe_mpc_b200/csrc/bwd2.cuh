@@ -193,6 +193,125 @@ __device__ __forceinline__ void gemm_mma(const double* __restrict__ A, int lda, 
   }
 }
 
+// ---- the same product with PAIRS of tiles that share one operand fragment: 3 LDS.64 per two DMMAs instead of 4 (the k loops' shared-memory
+// wavefronts are a quarter of the kernel's LSU traffic). SH = 1: two row tiles of one tile column share b; SH = 2: two column tiles of one
+// tile row share a. Every tile still accumulates its k steps in the same order from zero, so the results are bit-identical to gemm_mma.
+#ifndef CAFE_BWD_PAIR
+#define CAFE_BWD_PAIR 1
+#endif
+template <int MM, int NN, int SH>
+struct PairsFull {
+  static constexpr int MT = (MM + 7) / 8, NTC = (NN + 7) / 8, MP = SH == 1 ? (MT + 1) / 2 : MT, NP = SH == 2 ? (NTC + 1) / 2 : NTC, COUNT = MP * NP;
+  static __device__ __forceinline__ void map(int p, int& m0, int& n0, bool& two) {
+    const int pm = p % MP, pn = p / MP;
+    if constexpr (SH == 1) { m0 = pm * 16; n0 = pn * 8; two = 2 * pm + 1 < MT; }
+    else { m0 = pm * 8; n0 = pn * 16; two = 2 * pn + 1 < NTC; }
+  }
+};
+// TilesQ in pairs of row tiles (needs an even number of row tiles in both column groups)
+template <int N, int M>
+struct PairsQ {
+  static constexpr int MT = (N + M + 7) / 8, NFULL = (N + 7) / 8, MS = N / 8, NREST = MT - NFULL;
+  static constexpr bool OK = MT % 2 == 0 && MS % 2 == 0;
+  static constexpr int PF = MT / 2, PR = (MT - MS) / 2, COUNT = NFULL * PF + NREST * PR;
+  static __device__ __forceinline__ void map(int p, int& m0, int& n0, bool& two) {
+    two = true;
+    if (p < NFULL * PF) { m0 = (p % PF) * 16; n0 = (p / PF) * 8; }
+    else { const int r = p - NFULL * PF; m0 = MS * 8 + (r % PR) * 16; n0 = (NFULL + r / PR) * 8; }
+  }
+};
+template <int MM, int NN, int KK, bool TA, int KK2, int NT, int SH, class PL, class Pre, class Epi>
+__device__ __forceinline__ void gemm_mma_pair(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
+                                              const double* __restrict__ A2, int lda2, const double* __restrict__ B2, int ldb2, int t, bool run, Pre pre, Epi epi) {
+  constexpr int NW = NT / 32, G2 = (NT > 128) ? 1 : 2, KS = (KK + 3) / 4, KS2 = (KK2 + 3) / 4;
+  static_assert(SH == 1 || SH == 2, "which operand is shared");
+  if (!run) return;
+  __syncwarp();
+  const int w = t >> 5, lane = t & 31, g = lane >> 2, tg = lane & 3;
+  for (int p0 = w; p0 < PL::COUNT; p0 += NW * G2) {
+    double c[G2][2][2];
+    int m0[G2][2], n0[G2][2];
+    bool two[G2];
+    const double* ap[G2][2]; const double* bp[G2][2]; const double* ap2[G2][2]; const double* bp2[G2][2];
+#pragma unroll
+    for (int u = 0; u < G2; ++u) {
+      const int p = p0 + u * NW;
+      int mm, nn; bool tw;
+      PL::map(p < PL::COUNT ? p : p0, mm, nn, tw);   // a pass that runs out of pairs repeats its first one (result dropped)
+      two[u] = tw;
+      m0[u][0] = mm; n0[u][0] = nn;
+      m0[u][1] = (SH == 1 && tw) ? mm + 8 : mm;        // half a pair: the second tile repeats the first (result dropped)
+      n0[u][1] = (SH == 2 && tw) ? nn + 8 : nn;
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        ap[u][v] = TA ? A + tg + lda * (m0[u][v] + g) : A + (m0[u][v] + g) + lda * tg;
+        bp[u][v] = B + tg + ldb * (n0[u][v] + g);
+        if constexpr (KK2 > 0) { ap2[u][v] = A2 + tg + lda2 * (m0[u][v] + g); bp2[u][v] = B2 + tg + ldb2 * (n0[u][v] + g); }
+        c[u][v][0] = 0; c[u][v][1] = 0;
+      }
+    }
+    double pv[G2][2][2];
+#pragma unroll
+    for (int u = 0; u < G2; ++u)
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const int i = m0[u][v] + g, j = n0[u][v] + 2 * tg;
+        const bool on = v == 0 || two[u];
+        pv[u][v][0] = (on && i < MM && j < NN) ? pre(i, j) : 0.0;
+        pv[u][v][1] = (on && i < MM && j + 1 < NN) ? pre(i, j + 1) : 0.0;
+      }
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+      for (int u = 0; u < G2; ++u) {
+        if constexpr (SH == 1) {
+          const double b = bp[u][0][ks * 4];
+          const double a0 = TA ? ap[u][0][ks * 4] : ap[u][0][ks * 4 * lda], a1 = TA ? ap[u][1][ks * 4] : ap[u][1][ks * 4 * lda];
+          dmma884(c[u][0][0], c[u][0][1], a0, b);
+          dmma884(c[u][1][0], c[u][1][1], a1, b);
+        } else {
+          const double a = TA ? ap[u][0][ks * 4] : ap[u][0][ks * 4 * lda];
+          const double b0 = bp[u][0][ks * 4], b1 = bp[u][1][ks * 4];
+          dmma884(c[u][0][0], c[u][0][1], a, b0);
+          dmma884(c[u][1][0], c[u][1][1], a, b1);
+        }
+      }
+    }
+    if constexpr (KK2 > 0) {
+#pragma unroll
+      for (int ks = 0; ks < KS2; ++ks) {
+#pragma unroll
+        for (int u = 0; u < G2; ++u) {
+          if constexpr (SH == 1) {
+            const double b = bp2[u][0][ks * 4];
+            const double a0 = ap2[u][0][ks * 4], a1 = ap2[u][1][ks * 4];
+            dmma884(c[u][0][0], c[u][0][1], a0, b);
+            dmma884(c[u][1][0], c[u][1][1], a1, b);
+          } else {
+            const double a = ap2[u][0][ks * 4];
+            const double b0 = bp2[u][0][ks * 4], b1 = bp2[u][1][ks * 4];
+            dmma884(c[u][0][0], c[u][0][1], a, b0);
+            dmma884(c[u][1][0], c[u][1][1], a, b1);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < G2; ++u) {
+      if (p0 + u * NW < PL::COUNT) {
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          if (v == 0 || two[u]) {
+            const int i = m0[u][v] + g, j = n0[u][v] + 2 * tg;
+            if (i < MM && j < NN) epi(i, j, c[u][v][0] + pv[u][v][0]);
+            if (i < MM && j + 1 < NN) epi(i, j + 1, c[u][v][1] + pv[u][v][1]);
+          }
+        }
+      }
+    }
+  }
+}
+
 // shared-memory plan (doubles) of one problem whose largest phase is (NX, MX, PX); WBS: structured whole-body storage
 template <int NX, int MX, int PX, bool WBS>
 struct Bwd2Layout {
@@ -324,11 +443,16 @@ __device__ void sweep_phase2(const SolverDev& S, int pi, int b, int t, bool run,
 #if CAFE_BWD_MMA
     if constexpr (WB) {
       // T = P [A2 B2] + [H(:,0:18), dt H(:,0:18), 0],  P = H(:,18:36)
-      gemm_mma<N, N + M, 18, false, 0, NT, TilesFull<N, N + M>>(sH + ldH * 18, ldH, sAB, ldA, nullptr, 0, nullptr, 0, t, a2, NoPre(), [&](int i, int j, double v) {
+      auto epiT = [&](int i, int j, double v) {
         if (j < 18) v += sH[i + ldH * j];
         else if (j < 36) v += dt * sH[i + ldH * (j - 18)];
         sT[i + ldH * j] = v;
-      });
+      };
+#if CAFE_BWD_PAIR
+      gemm_mma_pair<N, N + M, 18, false, 0, NT, 2, PairsFull<N, N + M, 2>>(sH + ldH * 18, ldH, sAB, ldA, nullptr, 0, nullptr, 0, t, a2, NoPre(), epiT);
+#else
+      gemm_mma<N, N + M, 18, false, 0, NT, TilesFull<N, N + M>>(sH + ldH * 18, ldH, sAB, ldA, nullptr, 0, nullptr, 0, t, a2, NoPre(), epiT);
+#endif
     } else {
       gemm_mma<N, N + M, N, false, 0, NT, TilesFull<N, N + M>>(sH, ldH, sAB, ldA, nullptr, 0, nullptr, 0, t, a2, NoPre(), [&](int i, int j, double v) { sT[i + ldH * j] = v; });
     }
@@ -373,8 +497,7 @@ __device__ void sweep_phase2(const SolverDev& S, int pi, int b, int t, bool run,
       const double* luug = ph.luu + gix(k, M * M, 0, ldb, b);
       const unsigned long long* lmask = WB ? ph.lxx_mask + (size_t)k * CAFE_LXX_MASK_WORDS : nullptr;
       (void)lmask;
-      gemm_mma<N + M, N + M, KA, true, PY, NT, TilesQ<N, M>>(sAB, ldA, sT + R0, ldH, sCD, ldP, sSCD, ldP, t, a2,
-        [&](int i, int j) -> double {   // lxx / luu: 8-byte loads of a problem-fastest array, issued before the k loop
+      auto preQ = [&](int i, int j) -> double {   // lxx / luu: 8-byte loads of a problem-fastest array, issued before the k loop
           if constexpr (WB) {           // only the structural non-zeros: lxx by its per-knot pattern, luu is diagonal
             if (j < N) return (i < N && mask_bit(lmask, i + N * j)) ? lxxg[(size_t)(i + N * j) * ldb] : 0.0;
             return (i >= N && i == j) ? luug[(size_t)((i - N) + M * (j - N)) * ldb] : 0.0;
@@ -382,8 +505,8 @@ __device__ void sweep_phase2(const SolverDev& S, int pi, int b, int t, bool run,
             if (j < N) return (i < N && (hm == nullptr || mask_bit(hm + 18, i + N * j))) ? lxxg[(size_t)(i + N * j) * ldb] : 0.0;
             return (i >= N && (hm == nullptr || mask_bit(hm + 27, (i - N) + M * (j - N)))) ? luug[(size_t)((i - N) + M * (j - N)) * ldb] : 0.0;
           }
-        },
-        [&](int i, int j, double v) {
+        };
+      auto epiQ = [&](int i, int j, double v) {
         if (j < N) {
           if (i < N) {   // Qxx = lxx + A^T T_A (+ C^T S_C) + reg I   (H is dead: written over it)
             if constexpr (WB) { if (i < 18) v += sT[i + ldH * j]; else v += dt * sT[(i - 18) + ldH * j]; }
@@ -397,7 +520,11 @@ __device__ void sweep_phase2(const SolverDev& S, int pi, int b, int t, bool run,
           if (iu == ju) v += reg;
           sQuu[iu + ldM * ju] = v;
         }
-      });
+      };
+      if constexpr (CAFE_BWD_PAIR && WB && PairsQ<N, M>::OK)
+        gemm_mma_pair<N + M, N + M, KA, true, PY, NT, 1, PairsQ<N, M>>(sAB, ldA, sT + R0, ldH, sCD, ldP, sSCD, ldP, t, a2, preQ, epiQ);
+      else
+        gemm_mma<N + M, N + M, KA, true, PY, NT, TilesQ<N, M>>(sAB, ldA, sT + R0, ldH, sCD, ldP, sSCD, ldP, t, a2, preQ, epiQ);
     }
 #else
     {
@@ -523,7 +650,10 @@ __device__ void sweep_phase2(const SolverDev& S, int pi, int b, int t, bool run,
     }
     __syncthreads();
 #if CAFE_BWD_MMA
-    gemm_mma<N, N, M, true, 0, NT, TilesFull<N, N>>(sQux, ldM, sK, ldM, nullptr, 0, nullptr, 0, t, a3, NoPre(), [&](int i, int j, double v) { sH[i + ldH * j] += v; });
+    if constexpr (CAFE_BWD_PAIR && WB)
+      gemm_mma_pair<N, N, M, true, 0, NT, 2, PairsFull<N, N, 2>>(sQux, ldM, sK, ldM, nullptr, 0, nullptr, 0, t, a3, NoPre(), [&](int i, int j, double v) { sH[i + ldH * j] += v; });
+    else
+      gemm_mma<N, N, M, true, 0, NT, TilesFull<N, N>>(sQux, ldM, sK, ldM, nullptr, 0, nullptr, 0, t, a3, NoPre(), [&](int i, int j, double v) { sH[i + ldH * j] += v; });
 #else
     gemm_nt<N, N, M, true, 0, NT>(sQux, ldM, sK, ldM, nullptr, 0, nullptr, 0, t, a3, [&](int i, int j, double v) { sH[i + ldH * j] += v; });
 #endif
