@@ -23,6 +23,10 @@ import sys
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from casadi2cuda import HEADER  # noqa: E402
+
+# the banner of casadi2cuda.py describes re-emitted reference code; these files come from the repository's own symbolic model
+_CASADI_NOTE = '// Re-emission (CSE + constant folding + dead-code elimination, SSA form, functor\n// outputs) of CasADi expression graphs shipped with the reference; see the tool\n// for the exact source function of every routine below.\n'
+_OWN_NOTE = "// Straight-line code (CSE + constant folding + dead-code elimination, SSA form, functor\n// outputs) emitted from this repository's OWN symbolic rigid-body model of the Mini Cheetah\n// (tools/wb_model.py, tools/symbolic.py); not derived from the reference's CasADi-generated code.\n"
 from symbolic import Ctx, emit_function  # noqa: E402
 from wb_model import WBModel, hardcoded_params, make_vars, params_from_urdf  # noqa: E402
 
@@ -102,7 +106,7 @@ def main():
         o_dv2 += [(3 * f + r + 12 * c, feet_v[f]["v"][r].d(q[c])) for c in range(18) for r in range(3)]
     pieces.append(emit_function(ctx2, "wb_footvel_partial", 2, [o_dv2]))
     with open(out, "w") as fh:
-        fh.write(HEADER.replace("tools/casadi2cuda.py", "tools/gen_wb.py (symbolic whole-body model, tools/wb_model.py)"))
+        fh.write(HEADER.replace("tools/casadi2cuda.py", "tools/gen_wb.py (symbolic whole-body model, tools/wb_model.py)").replace(_CASADI_NOTE, _OWN_NOTE))
         fh.write("#ifndef CAFE_GEN_SYNC\n#define CAFE_GEN_SYNC\n#endif\n")
         fh.write("namespace cafe_gen_wb {\n\n")
         for code, meta in pieces:

@@ -23,6 +23,10 @@ import sys
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from casadi2cuda import HEADER  # noqa: E402
+
+# the banner of casadi2cuda.py describes re-emitted reference code; these files come from the repository's own symbolic model
+_CASADI_NOTE = '// Re-emission (CSE + constant folding + dead-code elimination, SSA form, functor\n// outputs) of CasADi expression graphs shipped with the reference; see the tool\n// for the exact source function of every routine below.\n'
+_OWN_NOTE = "// Straight-line code (CSE + constant folding + dead-code elimination, SSA form, functor\n// outputs) emitted from this repository's OWN symbolic rigid-body model of the Mini Cheetah\n// (tools/wb_model.py, tools/symbolic.py); not derived from the reference's CasADi-generated code.\n"
 from symbolic import Ctx, Dual, emit_function  # noqa: E402
 from wb_model import WBModel, hardcoded_params, make_vars, params_from_urdf  # noqa: E402
 
@@ -206,7 +210,7 @@ def main():
             fh.write("#define CAFE_WBL_DP_%s %d\n" % (pn, o))
         write_table("DP", [t[0] for t in tables["DP"]], [t[1] for t in tables["DP"]], [t[2] for t in tables["DP"]])
     with open(out, "w") as fh:
-        fh.write(HEADER.replace("tools/casadi2cuda.py", "tools/gen_wb_leg.py (symbolic whole-body model, tools/wb_model.py; leg-generic pieces)"))
+        fh.write(HEADER.replace("tools/casadi2cuda.py", "tools/gen_wb_leg.py (symbolic whole-body model, tools/wb_model.py; leg-generic pieces)").replace(_CASADI_NOTE, _OWN_NOTE))
         fh.write("#include \"../wb_leg_tables.h\"\n")
         fh.write("#ifndef CAFE_GEN_SYNC\n#define CAFE_GEN_SYNC\n#endif\n")
         fh.write("namespace cafe_gen_wbl {\n\n")
