@@ -220,6 +220,10 @@ struct PairsQ {
     else { const int r = p - NFULL * PF; m0 = MS * 8 + (r % PR) * 16; n0 = (NFULL + r / PR) * 8; }
   }
 };
+// the pair lists cover exactly the tiles of the tile lists they replace (whole-body phase: N = 36, M = 12)
+static_assert(PairsQ<36, 12>::OK && 2 * PairsQ<36, 12>::COUNT == TilesQ<36, 12>::COUNT, "Q product: 16 pairs = 32 tiles");
+static_assert(PairsFull<36, 48, 2>::COUNT == 15 && 2 * PairsFull<36, 48, 2>::COUNT == TilesFull<36, 48>::COUNT, "T = P [A2 B2]: 15 pairs = 30 tiles");
+static_assert(PairsFull<36, 36, 2>::COUNT == 15 && TilesFull<36, 36>::COUNT == 25, "H += Qux^T K: 15 pairs (5 of them half) = 25 tiles");
 template <int MM, int NN, int KK, bool TA, int KK2, int NT, int SH, class PL, class Pre, class Epi>
 __device__ __forceinline__ void gemm_mma_pair(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
                                               const double* __restrict__ A2, int lda2, const double* __restrict__ B2, int ldb2, int t, bool run, Pre pre, Epi epi) {
