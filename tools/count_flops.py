@@ -128,6 +128,15 @@ def main():
             print(f"{i:5d} {model:>5} {h:3d} {STAGES[s]:>5} {(own + cflop) / h:11.0f} {own / h:10.0f} {cflop / h:9.0f}   "
                   + " / ".join(f"{ops[i, s, k] / h:.0f}" for k in range(5)) + "; " + ", ".join(f"{k} {n / h:.2f}" for k, n in cc.items()))
         out["phases"].append(row)
+    # one whole solve of the same problem
+    sops = np.zeros(nk, dtype=np.int64); scalls = np.zeros(nc, dtype=np.int64); cnt = (C.c_int * 3)()
+    lib.cafe_count_solve.argtypes = [C.POINTER(Deck), C.POINTER(Options), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    assert lib.cafe_count_solve(deck, C.byref(opt), x0.ctypes.data, sops.ctypes.data, scalls.ctypes.data, cnt) == 0
+    own = int(sops[:5].sum()); cflop = int(sum(int(scalls[c]) * cas.get(names[c], 0) for c in range(nc)))
+    out["solve"] = {"flop": own + cflop, "own": own, "casadi": cflop, "iterations": cnt[0], "line_search_trials": cnt[1], "regularisation_steps": cnt[2],
+                    "ops": {KINDS[k]: int(sops[k]) for k in range(nk)}}
+    print("whole solve of the nominal problem: %.1f MFLOP (%.1f own C++ + %.1f CasADi), %d iterations, %d line-search trials, %d sweeps"
+          % ((own + cflop) / 1e6, own / 1e6, cflop / 1e6, cnt[0], cnt[1], cnt[2]))
     if a.json:
         json.dump(out, open(os.path.join(REPO, a.json) if not os.path.isabs(a.json) else a.json, "w"), indent=1)
 

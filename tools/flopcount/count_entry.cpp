@@ -115,3 +115,26 @@ extern "C" int cafe_count_first_iteration(const CafeDeck* deck, const CafeOption
     return -1;
   }
 }
+
+/* One whole solve (oracle::Solver::solve, the loop of MultiPhaseDDP::solve) under the counters: ops[kind], calls[casadi function], counters = iterations,
+ * line-search trials, regularisation steps. Returns 0, -1 on failure. */
+extern "C" int cafe_count_solve(const CafeDeck* deck, const CafeOptions* opt, const double* x0, long long* ops, long long* calls, int* counters) {
+  try {
+    std::memset(g_cnt, 0, sizeof(g_cnt));
+    std::memset(g_calls, 0, sizeof(g_calls));
+    g_bucket = 1;
+    Solver S;
+    S.setup(deck);
+    S.x0.assign(x0, x0 + S.phases[0]->n);
+    g_bucket = 0;
+    S.solve(*opt);
+    g_bucket = 1;
+    for (int k = 0; k < flopcount::NKIND; ++k) ops[k] = g_cnt[0][k];
+    for (int c = 0; c < N_CASADI; ++c) calls[c] = g_calls[0][c];
+    counters[0] = S.iter_; counters[1] = S.ls_iter_total_; counters[2] = S.reg_iter_total_;
+    return 0;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "cafe_count_solve: %s\n", e.what());
+    return -1;
+  }
+}
