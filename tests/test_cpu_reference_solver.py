@@ -361,3 +361,23 @@ def test_oracle_and_shift_reb_reproduce_the_reference_chain_with_changing_barrie
         info, hist, trace, sol, al, reb = oracle_solve(p1.deck, ort, x1, guess=guess, al=al, reb=reb)
         check_solve(cm, p1, ref, "p0_s%d_" % s, info, trace, sol, rtol=REB_RTOL)
         prob, k0 = p1, k1
+
+
+def test_reference_record_of_the_headline_batch_matches_the_oracle_on_a_spread_sample(cm):
+    """tests/golden/ref_mhpc_headline.npz = the reference's own solver build on all 4096 problems of the headline batch (tools/ref_headline.py; that tool
+    compares the oracle with every one of them). Here: the record belongs to the table `workload.mhpc_batch` produces today, and 32 problems spread over
+    the batch through the oracle take every decision like the reference (final cost 1e-9)."""
+    import hashlib
+    from cafe_mpc_b200 import workload
+    from oracle_bindings import oracle_solve
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = np.load(os.path.join(repo, "tests/golden/ref_mhpc_headline.npz"))
+    x0 = workload.mhpc_batch(4096)
+    assert hashlib.sha1(np.ascontiguousarray(x0).tobytes()).hexdigest() == str(ref["x0_sha1"])
+    assert ref["counters"].shape == (4096, 3) and ref["counters"][:, 0].min() >= 1
+    prob = cm.MHPCProblem(os.path.join(repo, "data/Reference/Data/trot/heuristic/quad_reference.csv"))
+    opt = cm.load_hsddp_setting(os.path.join(repo, "data/MHPC/settings/ddp_setting.info"))
+    for b in range(5, 4096, 128):
+        info, _, _, _ = oracle_solve(prob.deck, opt, x0[b], cap=320)
+        assert [info["iter"], info["ls_iter_total"], info["reg_iter_total"]] == ref["counters"][b].tolist(), b
+        assert abs(info["cost"] - ref["final_cost"][b]) <= 1e-9 * abs(ref["final_cost"][b]), b
